@@ -1,0 +1,295 @@
+// DHE (deep hash embedding) — SipHash-2-4 multi-hash encoder + CUDA-core fp32 MLP path.
+//
+// Restates inductive/dh_embedder.py:140-170 (128 keyed SipHash-2-4 of the 8-byte LE id, % 2^24,
+// held as exact fp32) and :70-89 (Linear-GELU x3, Linear-Sigmoid) of the reference.  The
+// reference calls the csiphash C wheel once per (id, key) from a Python loop; here one thread
+// computes one (id, key) hash with the per-key initial state staged in shared memory.
+// The tensor-core MLP lives in tc_dhe.cu; this file holds the hash kernel and the fp32 path.
+#include "common.cuh"
+
+namespace oov {
+
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int b) { return (x << b) | (x >> (64 - b)); }
+
+#define OOV_SIPROUND(v0, v1, v2, v3) \
+    do {                             \
+        v0 += v1; v1 = rotl64(v1, 13); v1 ^= v0; v0 = rotl64(v0, 32); \
+        v2 += v3; v3 = rotl64(v3, 16); v3 ^= v2;                      \
+        v0 += v3; v3 = rotl64(v3, 21); v3 ^= v0;                      \
+        v2 += v1; v1 = rotl64(v1, 17); v1 ^= v2; v2 = rotl64(v2, 32); \
+    } while (0)
+
+// SipHash-2-4 of one 8-byte message m given the key-derived initial state.
+__device__ __forceinline__ uint64_t siphash24_8(uint64_t v0, uint64_t v1, uint64_t v2, uint64_t v3, uint64_t m) {
+    v3 ^= m;
+    OOV_SIPROUND(v0, v1, v2, v3);
+    OOV_SIPROUND(v0, v1, v2, v3);
+    v0 ^= m;
+    const uint64_t b = 8ull << 56;           // length block: len = 8, no tail bytes
+    v3 ^= b;
+    OOV_SIPROUND(v0, v1, v2, v3);
+    OOV_SIPROUND(v0, v1, v2, v3);
+    v0 ^= b;
+    v2 ^= 0xff;
+    OOV_SIPROUND(v0, v1, v2, v3);
+    OOV_SIPROUND(v0, v1, v2, v3);
+    OOV_SIPROUND(v0, v1, v2, v3);
+    OOV_SIPROUND(v0, v1, v2, v3);
+    return v0 ^ v1 ^ v2 ^ v3;
+}
+
+__device__ __forceinline__ uint64_t load_le64(const uint8_t* p) {
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v |= (uint64_t)p[i] << (8 * i);
+    return v;
+}
+
+constexpr int HASH_THREADS = 256;
+
+// One thread per (id, key); j (key) is the fastest index so the [n, H] output is coalesced.
+__global__ void __launch_bounds__(HASH_THREADS)
+dhe_hash_kernel(const int64_t* __restrict__ ids, int64_t ids_stride, int64_t n,
+                const uint8_t* __restrict__ keys, int H, uint64_t mod, uint32_t* __restrict__ out) {
+    extern __shared__ uint64_t kst[];        // SoA: v0[H] | v1[H] | v2[H] | v3[H]
+    for (int j = threadIdx.x; j < H; j += HASH_THREADS) {
+        const uint64_t k0 = load_le64(keys + 16 * j), k1 = load_le64(keys + 16 * j + 8);
+        kst[j] = k0 ^ 0x736f6d6570736575ull;
+        kst[H + j] = k1 ^ 0x646f72616e646f6dull;
+        kst[2 * H + j] = k0 ^ 0x6c7967656e657261ull;
+        kst[3 * H + j] = k1 ^ 0x7465646279746573ull;
+    }
+    __syncthreads();
+    const bool pow2 = (mod & (mod - 1)) == 0;
+    const int64_t total = n * (int64_t)H;
+    for (int64_t t = (int64_t)blockIdx.x * HASH_THREADS + threadIdx.x; t < total; t += (int64_t)gridDim.x * HASH_THREADS) {
+        const int64_t i = t / H;
+        const int j = (int)(t - i * H);
+        const uint64_t m = (uint64_t)ids[i * ids_stride];   // LE bytes of the int64 id == its value
+        const uint64_t h = siphash24_8(kst[j], kst[H + j], kst[2 * H + j], kst[3 * H + j], m);
+        out[t] = (uint32_t)(pow2 ? (h & (mod - 1)) : (h % mod));
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// fp32 linear + activation: C[n, N] = act(A[n, K] . W[N, K]^T + b)
+// 64x64 CTA tile, 16-deep K slices, 256 threads, 4x4 micro-tile.
+// ------------------------------------------------------------------------------------
+enum { ACT_GELU = 0, ACT_SIGMOID = 1 };
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <bool A_IS_U32, int ACT>
+__global__ void __launch_bounds__(256)
+linear_act_simt(const void* __restrict__ A_, int64_t n, int K, const float* __restrict__ W, const float* __restrict__ bias,
+                int N, float* __restrict__ C, int64_t ldc,
+                // final-layer assemble (ACT_SIGMOID only): out rows + ids; C may be NULL then
+                const int64_t* __restrict__ ids, int64_t ids_stride, int64_t n_old,
+                const void* __restrict__ iv_table, int iv_dtype, void* __restrict__ out, int out_dtype, int64_t out_stride) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Ws[16][64 + 4];
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    const int64_t m0 = (int64_t)blockIdx.y * 64;
+    const int n0 = blockIdx.x * 64;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        // 64 rows x 16 k = 1024 elements per operand, 4 per thread; k fastest in global
+        for (int e = tid; e < 64 * 16; e += 256) {
+            const int r = e >> 4, kk = e & 15;
+            const int64_t gr = m0 + r;
+            float av = 0.f;
+            if (gr < n && k0 + kk < K) {
+                if (A_IS_U32) av = (float)reinterpret_cast<const uint32_t*>(A_)[gr * K + k0 + kk];   // < 2^24: exact
+                else av = reinterpret_cast<const float*>(A_)[gr * K + k0 + kk];
+            }
+            As[kk][r] = av;
+            const int gn = n0 + r;
+            Ws[kk][r] = (gn < N && k0 + kk < K) ? __ldg(W + (size_t)gn * K + k0 + kk) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 w = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t gr = m0 + ty * 4 + i;
+        if (gr >= n) continue;
+        int64_t id = 0;
+        bool is_iv = false;
+        if (ACT == ACT_SIGMOID && ids != nullptr) {
+            id = ids[gr * ids_stride];
+            is_iv = id < n_old;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            float v = acc[i][j] + __ldg(bias + gn);
+            v = (ACT == ACT_GELU) ? gelu_erf(v) : sigmoidf(v);
+            if (ACT == ACT_SIGMOID && out != nullptr) {
+                if (is_iv) {
+                    if (iv_table == nullptr || id < 0) continue;
+                    v = load_elem(iv_table, iv_dtype, id * (int64_t)N + gn);
+                }
+                store_elem(out, out_dtype, gr * out_stride + gn, v);
+            } else {
+                C[gr * ldc + gn] = v;
+            }
+        }
+    }
+}
+
+int check_rows_public(const oov_rows* r, const char* who);
+constexpr int64_t DHE_CHUNK = 1 << 16;     // rows per pass of the fp32 path (bounds the workspace)
+
+static int check_net(const oov_dhe_net* net, const char* who) {
+    OOV_REQUIRE(net != nullptr, OOV_ERR_ARG, "%s: net is NULL", who);
+    OOV_REQUIRE(net->H > 0 && net->hidden > 0 && net->D > 0, OOV_ERR_ARG, "%s: bad net dims", who);
+    for (int l = 0; l < 4; ++l) OOV_REQUIRE(net->w[l] && net->b[l], OOV_ERR_ARG, "%s: NULL weight/bias %d", who, l);
+    return OOV_OK;
+}
+
+static size_t dhe_simt_workspace(int64_t n, const oov_dhe_net* net) {
+    const int64_t c = n < DHE_CHUNK ? n : DHE_CHUNK;
+    return align_up((size_t)c * net->H * 4, 256) + 2 * align_up((size_t)c * net->hidden * 4, 256);
+}
+
+static int launch_hash(const int64_t* ids, int64_t ids_stride, int64_t n, const uint8_t* keys, int H, uint64_t mod,
+                       uint32_t* out, cudaStream_t st) {
+    if (n == 0) return OOV_OK;
+    int64_t blocks = cdiv(n * (int64_t)H, HASH_THREADS);
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    dhe_hash_kernel<<<(unsigned)blocks, HASH_THREADS, (size_t)H * 32, st>>>(ids, ids_stride, n, keys, H, mod, out);
+    OOV_LAUNCH_CHECK("dhe_hash_kernel");
+    return OOV_OK;
+}
+
+// hashes: [n, H] u32 already computed; rows (optional) gives the assemble contract for the last layer
+static int mlp_simt(const uint32_t* hashes, int64_t n, const oov_dhe_net* net, const oov_rows* rows,
+                    void* out, int out_dtype, int64_t out_stride, float* act0, float* act1, cudaStream_t st) {
+    const dim3 blk(256);
+    const unsigned gy = (unsigned)cdiv(n, 64);
+    const int hid = net->hidden;
+    linear_act_simt<true, ACT_GELU><<<dim3((unsigned)cdiv(hid, 64), gy), blk, 0, st>>>(
+        hashes, n, net->H, net->w[0], net->b[0], hid, act0, hid, nullptr, 1, 0, nullptr, 0, nullptr, 0, 0);
+    OOV_LAUNCH_CHECK("linear_act_simt L1");
+    linear_act_simt<false, ACT_GELU><<<dim3((unsigned)cdiv(hid, 64), gy), blk, 0, st>>>(
+        act0, n, hid, net->w[1], net->b[1], hid, act1, hid, nullptr, 1, 0, nullptr, 0, nullptr, 0, 0);
+    OOV_LAUNCH_CHECK("linear_act_simt L2");
+    linear_act_simt<false, ACT_GELU><<<dim3((unsigned)cdiv(hid, 64), gy), blk, 0, st>>>(
+        act1, n, hid, net->w[2], net->b[2], hid, act0, hid, nullptr, 1, 0, nullptr, 0, nullptr, 0, 0);
+    OOV_LAUNCH_CHECK("linear_act_simt L3");
+    linear_act_simt<false, ACT_SIGMOID><<<dim3((unsigned)cdiv(net->D, 64), gy), blk, 0, st>>>(
+        act0, n, hid, net->w[3], net->b[3], net->D, nullptr, 0,
+        rows ? rows->ids : nullptr, rows ? rows->ids_stride : 1, rows ? rows->n_old : 0,
+        rows ? rows->iv_table : nullptr, rows ? rows->iv_dtype : 0, out, out_dtype, out_stride);
+    OOV_LAUNCH_CHECK("linear_act_simt L4");
+    return OOV_OK;
+}
+
+}  // namespace oov
+
+using namespace oov;
+
+extern "C" {
+
+int oov_dhe_hash(const int64_t* ids, int64_t ids_stride, int64_t n, const uint8_t* keys, int32_t H, uint64_t mod,
+                 uint32_t* hashes, void* stream) {
+    OOV_REQUIRE(n >= 0 && H > 0 && H <= 4096 && ids_stride >= 1, OOV_ERR_ARG, "oov_dhe_hash: bad shape n=%lld H=%d", (long long)n, H);
+    OOV_REQUIRE(keys && (n == 0 || (ids && hashes)), OOV_ERR_ARG, "oov_dhe_hash: NULL pointer");
+    OOV_REQUIRE(mod >= 1 && mod <= (1ull << 32), OOV_ERR_ARG, "oov_dhe_hash: mod must be in [1, 2^32]");
+    return launch_hash(ids, ids_stride, n, keys, H, mod, hashes, (cudaStream_t)stream);
+}
+
+size_t oov_dhe_workspace(int64_t n, const oov_dhe_net* net, int32_t path) {
+    (void)path;
+    if (!net || n <= 0) return 0;
+    return dhe_simt_workspace(n, net);
+}
+
+int oov_dhe_mlp(const uint32_t* hashes, int64_t n, const oov_dhe_net* net, void* out, int32_t out_dtype,
+                int64_t out_stride, void* workspace, size_t workspace_bytes, int32_t path, void* stream) {
+    int rc = check_net(net, "oov_dhe_mlp");
+    if (rc) return rc;
+    OOV_REQUIRE(n >= 0 && dtype_ok(out_dtype) && out_stride >= net->D, OOV_ERR_ARG, "oov_dhe_mlp: bad n/out_dtype/out_stride");
+    OOV_REQUIRE(path == OOV_PATH_AUTO || path == OOV_PATH_SIMT_FP32, OOV_ERR_ARG, "oov_dhe_mlp: unsupported path %d", path);
+    if (n == 0) return OOV_OK;
+    OOV_REQUIRE(hashes && out, OOV_ERR_ARG, "oov_dhe_mlp: NULL pointer");
+    const int64_t c = n < DHE_CHUNK ? n : DHE_CHUNK;
+    const size_t hsz = align_up((size_t)c * net->H * 4, 256), asz = align_up((size_t)c * net->hidden * 4, 256);
+    OOV_REQUIRE(workspace && workspace_bytes >= hsz + 2 * asz, OOV_ERR_WORKSPACE, "oov_dhe_mlp: workspace %zu < %zu",
+                workspace_bytes, hsz + 2 * asz);
+    float* act0 = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + hsz);
+    float* act1 = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + hsz + asz);
+    const size_t osz = dtype_size(out_dtype);
+    for (int64_t r0 = 0; r0 < n; r0 += c) {
+        const int64_t cn = n - r0 < c ? n - r0 : c;
+        rc = mlp_simt(hashes + r0 * net->H, cn, net, nullptr, reinterpret_cast<char*>(out) + (size_t)r0 * out_stride * osz,
+                      out_dtype, out_stride, act0, act1, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return OOV_OK;
+}
+
+int oov_dhe_embed(const uint8_t* keys, uint64_t mod, const oov_dhe_net* net, const oov_rows* rows,
+                  void* workspace, size_t workspace_bytes, int32_t path, void* stream) {
+    int rc = check_net(net, "oov_dhe_embed");
+    if (rc) return rc;
+    rc = check_rows_public(rows, "oov_dhe_embed");
+    if (rc) return rc;
+    OOV_REQUIRE(keys, OOV_ERR_ARG, "oov_dhe_embed: keys is NULL");
+    OOV_REQUIRE(rows->D == net->D, OOV_ERR_ARG, "oov_dhe_embed: rows->D=%d != net->D=%d", rows->D, net->D);
+    OOV_REQUIRE(mod >= 1 && mod <= (1ull << 32), OOV_ERR_ARG, "oov_dhe_embed: mod must be in [1, 2^32]");
+    OOV_REQUIRE(path == OOV_PATH_AUTO || path == OOV_PATH_SIMT_FP32, OOV_ERR_ARG, "oov_dhe_embed: unsupported path %d", path);
+    const int64_t n = rows->n;
+    if (n == 0) return OOV_OK;
+    const int64_t c = n < DHE_CHUNK ? n : DHE_CHUNK;
+    const size_t hsz = align_up((size_t)c * net->H * 4, 256), asz = align_up((size_t)c * net->hidden * 4, 256);
+    OOV_REQUIRE(workspace && workspace_bytes >= hsz + 2 * asz, OOV_ERR_WORKSPACE, "oov_dhe_embed: workspace %zu < %zu",
+                workspace_bytes, hsz + 2 * asz);
+    uint32_t* hashes = reinterpret_cast<uint32_t*>(workspace);
+    float* act0 = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + hsz);
+    float* act1 = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + hsz + asz);
+    const size_t osz = dtype_size(rows->out_dtype);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int64_t r0 = 0; r0 < n; r0 += c) {
+        const int64_t cn = n - r0 < c ? n - r0 : c;
+        oov_rows sub = *rows;
+        sub.ids = rows->ids + r0 * rows->ids_stride;
+        sub.n = cn;
+        sub.out = reinterpret_cast<char*>(rows->out) + (size_t)r0 * rows->out_stride * osz;
+        // dh_embedder.py:219-245: DHE hashes the raw id (prime pad NOT removed)
+        rc = launch_hash(sub.ids, sub.ids_stride, cn, keys, net->H, mod, hashes, st);
+        if (rc) return rc;
+        rc = mlp_simt(hashes, cn, net, &sub, sub.out, sub.out_dtype, sub.out_stride, act0, act1, st);
+        if (rc) return rc;
+    }
+    return OOV_OK;
+}
+
+size_t oov_dhe_packed_bytes(const oov_dhe_net* net) { (void)net; return 0; }
+int oov_dhe_pack(const oov_dhe_net* net, void* packed, void* stream) {
+    (void)net; (void)packed; (void)stream;
+    oov::set_error("oov_dhe_pack: tcgen05 MLP path not built yet");
+    return OOV_ERR_ARG;
+}
+
+}  // extern "C"

@@ -1,0 +1,561 @@
+// Full-sort scoring + masks + top-k — CUDA-core (fp32 FMA) path, plus the shard merge and the
+// collector hit matrix.
+//
+// Restates bpr.py:151-156 / directau.py:193-198 (score = user_e @ all_item_e.T),
+// inductive/evaluator.py:91-94 (pad column and history -> -inf), evaluator/collector.py:153-166
+// (torch.topk + hit gather) and inductive/collector_filter.py:172-175 (item-segment filter) of the
+// reference — without ever materialising the [Q, N] score matrix: every warp streams item rows,
+// keeps a register-resident sorted top-k list per user (lane j holds entry j), and only items
+// that beat the current k-th entry pay for the mask checks and the insertion.
+// The tensor-core (tcgen05) variant lives in tc_score.cu and shares the merge kernels below.
+#include "common.cuh"
+
+namespace oov {
+
+// ---------------------------------------------------------------- warp-resident sorted list
+// KR registers per lane, entry e = r * 32 + lane, sorted descending by key64 (0 = empty).
+template <int KR>
+struct WarpList {
+    unsigned long long e[KR];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int r = 0; r < KR; ++r) e[r] = 0ull;
+    }
+    // k-th best so far (entry k-1), broadcast to the warp
+    __device__ __forceinline__ unsigned long long kth(int k) const {
+        const int kk = k - 1;
+        unsigned long long v = 0;
+#pragma unroll
+        for (int r = 0; r < KR; ++r)
+            if ((kk >> 5) == r) v = __shfl_sync(0xffffffffu, e[r], kk & 31);
+        return v;
+    }
+    // insert a warp-uniform key x (all lanes call); entries beyond k are harmless extra slots
+    __device__ __forceinline__ void insert(unsigned long long x, int lane) {
+        unsigned long long carry = x;              // value entering register r at its insertion point / lane 0
+        bool placed = false;
+#pragma unroll
+        for (int r = 0; r < KR; ++r) {
+            const unsigned m = __ballot_sync(0xffffffffu, carry > e[r]);   // suffix of lanes with smaller entries
+            const unsigned long long last = __shfl_sync(0xffffffffu, e[r], 31);
+            if (placed) {
+                // whole register shifts up by one, lane 0 takes the previous register's last entry
+                const unsigned long long up = __shfl_up_sync(0xffffffffu, e[r], 1);
+                e[r] = lane == 0 ? carry : up;
+                carry = last;
+            } else if (m) {
+                const int pos = __ffs(m) - 1;
+                const unsigned long long up = __shfl_up_sync(0xffffffffu, e[r], 1);
+                if (lane > pos) e[r] = up;
+                else if (lane == pos) e[r] = carry;
+                carry = last;
+                placed = true;
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ bool sorted_contains(const int32_t* __restrict__ cols, int lo, int hi, int64_t gid) {
+    int l = lo, h = hi;
+    while (l < h) {
+        const int mid = (l + h) >> 1;
+        if ((int64_t)cols[mid] < gid) l = mid + 1; else h = mid;
+    }
+    return l < hi && (int64_t)cols[l] == gid;
+}
+
+template <typename T> __device__ __forceinline__ void load16(const T* p, float (&x)[16]);
+template <> __device__ __forceinline__ void load16<float>(const float* p, float (&x)[16]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p) + j);
+        x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
+    }
+}
+template <> __device__ __forceinline__ void load16<__nv_bfloat16>(const __nv_bfloat16* p, float (&x)[16]) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(p) + j);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 f = __bfloat1622float2(h[q]);
+            x[8 * j + 2 * q] = f.x; x[8 * j + 2 * q + 1] = f.y;
+        }
+    }
+}
+
+constexpr int FS_THREADS = 256;
+constexpr int FS_WARPS = FS_THREADS / 32;
+
+// grid = (item CTAs, user tiles).  Each warp owns 32-item batches (one item per lane), strided over
+// the grid, and TQ register lists.  Requires D % 16 == 0 and 16-byte aligned rows (checked on host).
+template <typename T, int TQ, int KR>
+__global__ void __launch_bounds__(FS_THREADS)
+fullsort_topk_simt(const T* __restrict__ users, const T* __restrict__ items, int64_t Q, int64_t N, int D, int k,
+                   int64_t item_id_offset, int mask_pad, int64_t seg_lo, int64_t seg_hi,
+                   const int32_t* __restrict__ hist_rowptr, const int32_t* __restrict__ hist_cols,
+                   unsigned long long* __restrict__ partial /* [gridDim.x][Q][k] */) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* us = reinterpret_cast<float*>(smem_raw);                                   // [TQ][D]
+    unsigned long long* lists = reinterpret_cast<unsigned long long*>(us + TQ * D);   // [FS_WARPS][TQ][KR*32]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t q0 = (int64_t)blockIdx.y * TQ;
+
+    for (int i = tid; i < TQ * D; i += FS_THREADS) {
+        const int u = i / D, d = i - u * D;
+        us[i] = (q0 + u < Q) ? to_f32<T>(users[(q0 + u) * D + d]) : 0.f;
+    }
+    __syncthreads();
+
+    WarpList<KR> wl[TQ];
+#pragma unroll
+    for (int u = 0; u < TQ; ++u) wl[u].clear();
+    unsigned long long thr[TQ];
+#pragma unroll
+    for (int u = 0; u < TQ; ++u) thr[u] = 0ull;
+    int hlo[TQ], hhi[TQ];
+#pragma unroll
+    for (int u = 0; u < TQ; ++u) {
+        hlo[u] = hhi[u] = 0;
+        if (hist_rowptr != nullptr && q0 + u < Q) { hlo[u] = hist_rowptr[q0 + u]; hhi[u] = hist_rowptr[q0 + u + 1]; }
+    }
+
+    const int64_t n_batches = (N + 31) / 32;
+    for (int64_t b = (int64_t)blockIdx.x * FS_WARPS + warp; b < n_batches; b += (int64_t)gridDim.x * FS_WARPS) {
+        const int64_t li = b * 32 + lane;                     // local item row of this lane
+        const bool valid = li < N;
+        const T* row = items + (valid ? li : 0) * D;
+        float acc[TQ];
+#pragma unroll
+        for (int u = 0; u < TQ; ++u) acc[u] = 0.f;
+        for (int d0 = 0; d0 < D; d0 += 16) {
+            float x[16];
+            load16<T>(row + d0, x);
+#pragma unroll
+            for (int u = 0; u < TQ; ++u) {
+                const float4* up = reinterpret_cast<const float4*>(us + u * D + d0);
+                float a = acc[u];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 w = up[j];
+                    a = fmaf(x[4 * j], w.x, a); a = fmaf(x[4 * j + 1], w.y, a);
+                    a = fmaf(x[4 * j + 2], w.z, a); a = fmaf(x[4 * j + 3], w.w, a);
+                }
+                acc[u] = a;
+            }
+        }
+        const int64_t gid = li + item_id_offset;
+        // per-item masks: pad item 0 (evaluator.py:92) and the item-segment filter (collector_filter.py:172-175)
+        const bool item_masked = (mask_pad && gid == 0) || gid < seg_lo || gid >= seg_hi;
+#pragma unroll
+        for (int u = 0; u < TQ; ++u) {
+            if (q0 + u >= Q) continue;                         // warp-uniform
+            unsigned long long key = valid ? make_key64(item_masked ? -INFINITY : acc[u], (uint32_t)li) : 0ull;
+            unsigned m = __ballot_sync(0xffffffffu, key > thr[u]);
+            while (m) {                                        // rare after warm-up
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                unsigned long long x = __shfl_sync(0xffffffffu, key, src);
+                const int64_t xg = __shfl_sync(0xffffffffu, gid, src);
+                // history (evaluator.py:93-94) is only probed for candidates that beat the threshold
+                if (hhi[u] > hlo[u] && sorted_contains(hist_cols, hlo[u], hhi[u], xg))
+                    x = make_key64(-INFINITY, key64_idx(x));
+                if (x > thr[u]) {
+                    wl[u].insert(x, lane);
+                    thr[u] = wl[u].kth(k);
+                }
+            }
+        }
+    }
+
+    // CTA-level merge of the FS_WARPS lists per user, then one partial list per (CTA, user)
+#pragma unroll
+    for (int u = 0; u < TQ; ++u)
+#pragma unroll
+        for (int r = 0; r < KR; ++r) lists[((size_t)warp * TQ + u) * (KR * 32) + r * 32 + lane] = wl[u].e[r];
+    __syncthreads();
+    for (int u = warp; u < TQ; u += FS_WARPS) {
+        if (q0 + u >= Q) continue;
+        WarpList<KR> fin;
+        fin.clear();
+        unsigned long long t = 0ull;
+        for (int w = 0; w < FS_WARPS; ++w) {
+#pragma unroll
+            for (int r = 0; r < KR; ++r) {
+                const unsigned long long key = lists[((size_t)w * TQ + u) * (KR * 32) + r * 32 + lane];
+                unsigned m = __ballot_sync(0xffffffffu, key > t);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const unsigned long long x = __shfl_sync(0xffffffffu, key, src);
+                    if (x > t) { fin.insert(x, lane); t = fin.kth(k); }
+                }
+            }
+        }
+        unsigned long long* dst = partial + ((size_t)blockIdx.x * Q + (q0 + u)) * k;
+#pragma unroll
+        for (int r = 0; r < KR; ++r)
+            if (r * 32 + lane < k) dst[r * 32 + lane] = fin.e[r];
+    }
+}
+
+// one warp per user: merge P partial lists of k key64 entries; decode to (score, global id)
+template <int KR>
+__global__ void __launch_bounds__(256)
+merge_keys_kernel(const unsigned long long* __restrict__ partial, int P, int64_t Q, int k, int64_t item_id_offset,
+                  float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= Q) return;
+    WarpList<KR> fin;
+    fin.clear();
+    unsigned long long t = 0ull;
+    const int64_t total = (int64_t)P * k;
+    for (int64_t i0 = 0; i0 < total; i0 += 32) {
+        const int64_t i = i0 + lane;
+        unsigned long long key = 0ull;
+        if (i < total) {
+            const int64_t p = i / k, j = i - p * k;
+            key = partial[((size_t)p * Q + q) * k + j];
+        }
+        unsigned m = __ballot_sync(0xffffffffu, key > t);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const unsigned long long x = __shfl_sync(0xffffffffu, key, src);
+            if (x > t) { fin.insert(x, lane); t = fin.kth(k); }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < KR; ++r) {
+        const int j = r * 32 + lane;
+        if (j < k) {
+            const unsigned long long key = fin.e[r];
+            out_scores[q * k + j] = key ? key64_score(key) : -INFINITY;
+            out_idx[q * k + j] = key ? (int64_t)key64_idx(key) + item_id_offset : -1;
+        }
+    }
+}
+
+// shard merge: candidates are (fp32 score, int64 global id) — [G, Q, k]
+template <int KR>
+__global__ void __launch_bounds__(256)
+merge_cands_kernel(const float* __restrict__ cs, const int64_t* __restrict__ ci, int G, int64_t Q, int k,
+                   float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= Q) return;
+    WarpList<KR> fin;
+    fin.clear();
+    unsigned long long t = 0ull;
+    const int64_t total = (int64_t)G * k;
+    for (int64_t i0 = 0; i0 < total; i0 += 32) {
+        const int64_t i = i0 + lane;
+        unsigned long long key = 0ull;
+        if (i < total) {
+            const int64_t g = i / k, j = i - g * k;
+            const int64_t id = ci[((size_t)g * Q + q) * k + j];
+            if (id >= 0) key = make_key64(cs[((size_t)g * Q + q) * k + j], (uint32_t)id);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, key > t);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const unsigned long long x = __shfl_sync(0xffffffffu, key, src);
+            if (x > t) { fin.insert(x, lane); t = fin.kth(k); }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < KR; ++r) {
+        const int j = r * 32 + lane;
+        if (j < k) {
+            const unsigned long long key = fin.e[r];
+            out_scores[q * k + j] = key ? key64_score(key) : -INFINITY;
+            out_idx[q * k + j] = key ? (int64_t)key64_idx(key) : -1;
+        }
+    }
+}
+
+__global__ void topk_hits_kernel(const int64_t* __restrict__ topk_idx, int64_t Q, int k,
+                                 const int32_t* __restrict__ pos_rowptr, const int32_t* __restrict__ pos_cols,
+                                 int32_t* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Q * (k + 1)) return;
+    const int64_t q = t / (k + 1);
+    const int j = (int)(t - q * (k + 1));
+    const int lo = pos_rowptr[q], hi = pos_rowptr[q + 1];
+    if (j == k) { out[t] = hi - lo; return; }                  // pos_len column (collector.py:163)
+    out[t] = sorted_contains(pos_cols, lo, hi, topk_idx[q * k + j]) ? 1 : 0;
+}
+
+// dense scores (the reference's materialised matrix) — one warp per 32 items x TQ users
+template <typename T, int TQ>
+__global__ void __launch_bounds__(FS_THREADS)
+fullsort_scores_simt(const T* __restrict__ users, const T* __restrict__ items, int64_t Q, int64_t N, int D,
+                     int64_t item_id_offset, int mask_pad, int64_t seg_lo, int64_t seg_hi,
+                     float* __restrict__ scores, int64_t ld) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* us = reinterpret_cast<float*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t q0 = (int64_t)blockIdx.y * TQ;
+    for (int i = tid; i < TQ * D; i += FS_THREADS) {
+        const int u = i / D, d = i - u * D;
+        us[i] = (q0 + u < Q) ? to_f32<T>(users[(q0 + u) * D + d]) : 0.f;
+    }
+    __syncthreads();
+    const int64_t n_batches = (N + 31) / 32;
+    for (int64_t b = (int64_t)blockIdx.x * FS_WARPS + warp; b < n_batches; b += (int64_t)gridDim.x * FS_WARPS) {
+        const int64_t li = b * 32 + lane;
+        const bool valid = li < N;
+        const T* row = items + (valid ? li : 0) * D;
+        float acc[TQ];
+#pragma unroll
+        for (int u = 0; u < TQ; ++u) acc[u] = 0.f;
+        for (int d0 = 0; d0 < D; d0 += 16) {
+            float x[16];
+            load16<T>(row + d0, x);
+#pragma unroll
+            for (int u = 0; u < TQ; ++u) {
+                const float4* up = reinterpret_cast<const float4*>(us + u * D + d0);
+                float a = acc[u];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 w = up[j];
+                    a = fmaf(x[4 * j], w.x, a); a = fmaf(x[4 * j + 1], w.y, a);
+                    a = fmaf(x[4 * j + 2], w.z, a); a = fmaf(x[4 * j + 3], w.w, a);
+                }
+                acc[u] = a;
+            }
+        }
+        const int64_t gid = li + item_id_offset;
+        const bool item_masked = (mask_pad && gid == 0) || gid < seg_lo || gid >= seg_hi;
+        if (valid) {
+#pragma unroll
+            for (int u = 0; u < TQ; ++u)
+                if (q0 + u < Q) scores[(q0 + u) * ld + li] = item_masked ? -INFINITY : acc[u];
+        }
+    }
+}
+__global__ void hist_scatter_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols, int64_t Q,
+                                    int64_t N, int64_t item_id_offset, float* __restrict__ scores, int64_t ld) {
+    const int64_t q = blockIdx.x;
+    if (q >= Q) return;
+    for (int h = rowptr[q] + threadIdx.x; h < rowptr[q + 1]; h += blockDim.x) {
+        const int64_t li = (int64_t)cols[h] - item_id_offset;
+        if (li >= 0 && li < N) scores[q * ld + li] = -INFINITY;
+    }
+}
+
+
+// top-k of an already materialised (and masked) score matrix: one CTA per row — the dense entry point
+// behind Collector.eval_batch_collect (collector.py:153-159) for callers that hold [Q, N] scores.
+template <int KR>
+__global__ void __launch_bounds__(FS_THREADS)
+dense_topk_kernel(const float* __restrict__ scores, int64_t ld, int64_t N, int k,
+                  float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+    __shared__ unsigned long long lists[FS_WARPS * KR * 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t q = blockIdx.x;
+    const float* row = scores + q * ld;
+    WarpList<KR> wl;
+    wl.clear();
+    unsigned long long t = 0ull;
+    for (int64_t i0 = (int64_t)warp * 32; i0 < N; i0 += FS_THREADS) {
+        const int64_t i = i0 + lane;
+        const unsigned long long key = i < N ? make_key64(__ldg(row + i), (uint32_t)i) : 0ull;
+        unsigned m = __ballot_sync(0xffffffffu, key > t);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const unsigned long long x = __shfl_sync(0xffffffffu, key, src);
+            if (x > t) { wl.insert(x, lane); t = wl.kth(k); }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < KR; ++r) lists[(warp * KR + r) * 32 + lane] = wl.e[r];
+    __syncthreads();
+    if (warp != 0) return;
+    WarpList<KR> fin;
+    fin.clear();
+    t = 0ull;
+    for (int w = 0; w < FS_WARPS; ++w) {
+#pragma unroll
+        for (int r = 0; r < KR; ++r) {
+            const unsigned long long key = lists[(w * KR + r) * 32 + lane];
+            unsigned m = __ballot_sync(0xffffffffu, key > t);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const unsigned long long x = __shfl_sync(0xffffffffu, key, src);
+                if (x > t) { fin.insert(x, lane); t = fin.kth(k); }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < KR; ++r) {
+        const int j = r * 32 + lane;
+        if (j < k) {
+            const unsigned long long key = fin.e[r];
+            out_scores[q * k + j] = key ? key64_score(key) : -INFINITY;
+            out_idx[q * k + j] = key ? (int64_t)key64_idx(key) : -1;
+        }
+    }
+}
+
+static int pick_item_ctas(int64_t N, int64_t user_tiles) {
+    int64_t want = cdiv(N, 32 * FS_WARPS);                 // one batch per warp at least
+    int64_t cap = (int64_t)num_sms() * 2;
+    if (user_tiles >= 4) cap = num_sms();                  // keep the partial-list volume bounded
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+struct TopkCfg { int TQ, KR; };
+static TopkCfg topk_cfg(int k) {
+    if (k <= 32) return {16, 1};
+    if (k <= 64) return {8, 2};
+    return {4, 4};
+}
+
+template <typename T>
+static int launch_fullsort_simt(const T* users, const T* items, int64_t Q, int64_t N, int D, int k,
+                                int64_t off, int mask_pad, int64_t seg_lo, int64_t seg_hi,
+                                const int32_t* hr, const int32_t* hc, float* out_scores, int64_t* out_idx,
+                                unsigned long long* partial, int P, cudaStream_t st) {
+    const TopkCfg c = topk_cfg(k);
+    const dim3 grid((unsigned)P, (unsigned)cdiv(Q, c.TQ));
+    const size_t smem = (size_t)c.TQ * D * 4 + (size_t)FS_WARPS * c.TQ * c.KR * 32 * 8;
+#define OOV_FS_CASE(TQ_, KR_)                                                                                         \
+    {                                                                                                                 \
+        auto kern = fullsort_topk_simt<T, TQ_, KR_>;                                                                  \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        kern<<<grid, FS_THREADS, smem, st>>>(users, items, Q, N, D, k, off, mask_pad, seg_lo, seg_hi, hr, hc, partial); \
+        OOV_LAUNCH_CHECK("fullsort_topk_simt");                                                                       \
+        merge_keys_kernel<KR_><<<(unsigned)cdiv(Q * 32, 256), 256, 0, st>>>(partial, P, Q, k, off, out_scores, out_idx); \
+        OOV_LAUNCH_CHECK("merge_keys_kernel");                                                                        \
+    }
+    if (c.KR == 1) OOV_FS_CASE(16, 1)
+    else if (c.KR == 2) OOV_FS_CASE(8, 2)
+    else OOV_FS_CASE(4, 4)
+#undef OOV_FS_CASE
+    return OOV_OK;
+}
+
+}  // namespace oov
+
+using namespace oov;
+
+extern "C" {
+
+size_t oov_fullsort_topk_workspace(int64_t Q, int64_t N, int32_t D, int32_t k, int32_t path) {
+    (void)D; (void)path;
+    if (Q <= 0 || N <= 0 || k <= 0) return 0;
+    const TopkCfg c = topk_cfg(k);
+    const int P = pick_item_ctas(N, cdiv(Q, c.TQ));
+    return align_up((size_t)P * Q * k * 8, 256);
+}
+
+int oov_fullsort_topk(const void* users, const void* items, int32_t dtype, int64_t Q, int64_t N, int32_t D, int32_t k,
+                      int64_t item_id_offset, int32_t mask_pad, int64_t seg_lo, int64_t seg_hi,
+                      const int32_t* hist_rowptr, const int32_t* hist_cols, float* out_scores, int64_t* out_idx,
+                      void* workspace, size_t workspace_bytes, int32_t path, void* stream) {
+    OOV_REQUIRE(dtype_ok(dtype), OOV_ERR_ARG, "oov_fullsort_topk: bad dtype %d", dtype);
+    OOV_REQUIRE(Q >= 0 && N >= 0 && D > 0 && k > 0 && k <= 128, OOV_ERR_ARG,
+                "oov_fullsort_topk: bad shape Q=%lld N=%lld D=%d k=%d (k <= 128)", (long long)Q, (long long)N, D, k);
+    OOV_REQUIRE(N < (1ll << 32), OOV_ERR_ARG, "oov_fullsort_topk: shard has %lld rows (max 2^32-1)", (long long)N);
+    OOV_REQUIRE(D % 16 == 0, OOV_ERR_ARG, "oov_fullsort_topk: D=%d must be a multiple of 16 (pad the tables)", D);
+    OOV_REQUIRE((hist_rowptr == nullptr) == (hist_cols == nullptr), OOV_ERR_ARG, "oov_fullsort_topk: rowptr/cols mismatch");
+    OOV_REQUIRE(path == OOV_PATH_AUTO || path == OOV_PATH_SIMT_FP32, OOV_ERR_ARG, "oov_fullsort_topk: unsupported path %d", path);
+    if (Q == 0) return OOV_OK;
+    OOV_REQUIRE(users && out_scores && out_idx && (N == 0 || items), OOV_ERR_ARG, "oov_fullsort_topk: NULL pointer");
+    OOV_REQUIRE(aligned(users, 16) && aligned(items, 16), OOV_ERR_ALIGN, "oov_fullsort_topk: tables must be 16-byte aligned");
+    const TopkCfg c = topk_cfg(k);
+    const int P = pick_item_ctas(N > 0 ? N : 1, cdiv(Q, c.TQ));
+    const size_t need = (size_t)P * Q * k * 8;
+    OOV_REQUIRE(workspace && workspace_bytes >= need, OOV_ERR_WORKSPACE, "oov_fullsort_topk: workspace %zu < %zu",
+                workspace_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* partial = reinterpret_cast<unsigned long long*>(workspace);
+    if (dtype == OOV_F32)
+        return launch_fullsort_simt<float>((const float*)users, (const float*)items, Q, N, D, k, item_id_offset, mask_pad,
+                                           seg_lo, seg_hi, hist_rowptr, hist_cols, out_scores, out_idx, partial, P, st);
+    return launch_fullsort_simt<__nv_bfloat16>((const __nv_bfloat16*)users, (const __nv_bfloat16*)items, Q, N, D, k,
+                                               item_id_offset, mask_pad, seg_lo, seg_hi, hist_rowptr, hist_cols,
+                                               out_scores, out_idx, partial, P, st);
+}
+
+int oov_fullsort_scores(const void* users, const void* items, int32_t dtype, int64_t Q, int64_t N, int32_t D,
+                        int64_t item_id_offset, int32_t mask_pad, int64_t seg_lo, int64_t seg_hi,
+                        const int32_t* hist_rowptr, const int32_t* hist_cols, float* scores, int64_t scores_stride,
+                        void* stream) {
+    OOV_REQUIRE(dtype_ok(dtype) && Q >= 0 && N >= 0 && D > 0 && D % 16 == 0 && scores_stride >= N, OOV_ERR_ARG,
+                "oov_fullsort_scores: bad argument (D must be a multiple of 16)");
+    OOV_REQUIRE((hist_rowptr == nullptr) == (hist_cols == nullptr), OOV_ERR_ARG, "oov_fullsort_scores: rowptr/cols mismatch");
+    if (Q == 0 || N == 0) return OOV_OK;
+    OOV_REQUIRE(users && items && scores, OOV_ERR_ARG, "oov_fullsort_scores: NULL pointer");
+    OOV_REQUIRE(aligned(users, 16) && aligned(items, 16), OOV_ERR_ALIGN, "oov_fullsort_scores: tables must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    constexpr int TQ = 16;
+    const dim3 grid((unsigned)pick_item_ctas(N, 1), (unsigned)cdiv(Q, TQ));
+    const size_t smem = (size_t)TQ * D * 4;
+    if (dtype == OOV_F32) {
+        auto kern = fullsort_scores_simt<float, TQ>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, FS_THREADS, smem, st>>>((const float*)users, (const float*)items, Q, N, D, item_id_offset, mask_pad,
+                                             seg_lo, seg_hi, scores, scores_stride);
+    } else {
+        auto kern = fullsort_scores_simt<__nv_bfloat16, TQ>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, FS_THREADS, smem, st>>>((const __nv_bfloat16*)users, (const __nv_bfloat16*)items, Q, N, D,
+                                             item_id_offset, mask_pad, seg_lo, seg_hi, scores, scores_stride);
+    }
+    OOV_LAUNCH_CHECK("fullsort_scores_simt");
+    if (hist_rowptr != nullptr) {
+        hist_scatter_kernel<<<(unsigned)Q, 64, 0, st>>>(hist_rowptr, hist_cols, Q, N, item_id_offset, scores, scores_stride);
+        OOV_LAUNCH_CHECK("hist_scatter_kernel");
+    }
+    return OOV_OK;
+}
+
+int oov_dense_topk(const float* scores, int64_t scores_stride, int64_t Q, int64_t N, int32_t k,
+                   float* out_scores, int64_t* out_idx, void* stream) {
+    OOV_REQUIRE(Q >= 0 && N >= 0 && k > 0 && k <= 128 && scores_stride >= N && N < (1ll << 32), OOV_ERR_ARG,
+                "oov_dense_topk: bad shape Q=%lld N=%lld k=%d", (long long)Q, (long long)N, k);
+    if (Q == 0) return OOV_OK;
+    OOV_REQUIRE(out_scores && out_idx && (N == 0 || scores), OOV_ERR_ARG, "oov_dense_topk: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (k <= 32) dense_topk_kernel<1><<<(unsigned)Q, FS_THREADS, 0, st>>>(scores, scores_stride, N, k, out_scores, out_idx);
+    else if (k <= 64) dense_topk_kernel<2><<<(unsigned)Q, FS_THREADS, 0, st>>>(scores, scores_stride, N, k, out_scores, out_idx);
+    else dense_topk_kernel<4><<<(unsigned)Q, FS_THREADS, 0, st>>>(scores, scores_stride, N, k, out_scores, out_idx);
+    OOV_LAUNCH_CHECK("dense_topk_kernel");
+    return OOV_OK;
+}
+
+int oov_topk_merge(const float* cand_scores, const int64_t* cand_idx, int32_t G, int64_t Q, int32_t k,
+                   float* out_scores, int64_t* out_idx, void* stream) {
+    OOV_REQUIRE(G > 0 && Q >= 0 && k > 0 && k <= 128, OOV_ERR_ARG, "oov_topk_merge: bad shape");
+    if (Q == 0) return OOV_OK;
+    OOV_REQUIRE(cand_scores && cand_idx && out_scores && out_idx, OOV_ERR_ARG, "oov_topk_merge: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned blocks = (unsigned)cdiv(Q * 32, 256);
+    if (k <= 32) merge_cands_kernel<1><<<blocks, 256, 0, st>>>(cand_scores, cand_idx, G, Q, k, out_scores, out_idx);
+    else if (k <= 64) merge_cands_kernel<2><<<blocks, 256, 0, st>>>(cand_scores, cand_idx, G, Q, k, out_scores, out_idx);
+    else merge_cands_kernel<4><<<blocks, 256, 0, st>>>(cand_scores, cand_idx, G, Q, k, out_scores, out_idx);
+    OOV_LAUNCH_CHECK("merge_cands_kernel");
+    return OOV_OK;
+}
+
+int oov_topk_hits(const int64_t* topk_idx, int64_t Q, int32_t k, const int32_t* pos_rowptr, const int32_t* pos_cols,
+                  int32_t* out_hits, void* stream) {
+    OOV_REQUIRE(Q >= 0 && k > 0, OOV_ERR_ARG, "oov_topk_hits: bad shape");
+    if (Q == 0) return OOV_OK;
+    OOV_REQUIRE(topk_idx && pos_rowptr && pos_cols && out_hits, OOV_ERR_ARG, "oov_topk_hits: NULL pointer");
+    topk_hits_kernel<<<(unsigned)cdiv(Q * (k + 1), 256), 256, 0, (cudaStream_t)stream>>>(topk_idx, Q, k, pos_rowptr,
+                                                                                        pos_cols, out_hits);
+    OOV_LAUNCH_CHECK("topk_hits_kernel");
+    return OOV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,201 @@
+"""Retrieval models on the OOV path — mirrors reference model/abstract_recommender.py:117-203
+(InductiveGeneralRecommender), model/general_recommender/bpr.py:32-163 and directau.py:18-198.
+
+Same constructor `(config, dataset, inductive_mapper=None, inductive_embedder=None)`, parameter
+names (`user_embedding`, `item_embedding`, `user_oov_buckets`, `item_oov_buckets`, hence the same
+state_dict keys incl. `inductive_embedder.*`) and methods (`get_user_embedding`,
+`get_item_embedding`, `ind_full_sort_predict`, `full_sort_predict`, `predict`).  Differences are in
+HOW: in-vocab gather + OOV embed is one fused pass (`assemble_rows`), and `full_sort_topk` fuses
+scoring, the pad/history/segment masks and top-k so the [Q, N] score matrix is never written.
+Training (`calculate_loss`, backward through the OOV buckets) is outside this path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import ops
+from .._lib import INT64_MAX
+
+
+def xavier_normal_initialization(module):
+    """reference model/init.py: xavier_normal_ for Embedding / Linear weights, zero Linear bias."""
+    if isinstance(module, nn.Embedding):
+        nn.init.xavier_normal_(module.weight.data)
+    elif isinstance(module, nn.Linear):
+        nn.init.xavier_normal_(module.weight.data)
+        if module.bias is not None:
+            nn.init.constant_(module.bias.data, 0)
+
+
+def _cfg(config, key, default=None):
+    try:
+        v = config[key]
+    except (KeyError, IndexError):
+        v = None
+    return default if v is None else v
+
+
+class InductiveGeneralRecommender(nn.Module):
+    def __init__(self, config, dataset, inductive_mapper=None, inductive_embedder=None):
+        super().__init__()
+        self.USER_ID = config["USER_ID_FIELD"]
+        self.ITEM_ID = config["ITEM_ID_FIELD"]
+        self.NEG_ITEM_ID = _cfg(config, "NEG_PREFIX", "neg_") + self.ITEM_ID
+        self.n_users = dataset.num(self.USER_ID)
+        self.n_items = dataset.num(self.ITEM_ID)
+        self.device = config["device"]
+
+        self.n_user_oov_buckets = 0
+        self.n_item_oov_buckets = 0
+        self.embedding_size = config["embedding_size"]
+        self.inductive_mapper = inductive_mapper
+        self.inductive_embedder = inductive_embedder
+        self.oov_freeze_embedding = _cfg(config, "oov_freeze_embedding", False)
+        self.oov_training = False
+        if self.inductive_mapper is None and self.inductive_embedder is None:
+            raise NotImplementedError("Must provide either self.inductive_mapper or self.inductive_embedder")
+        self.n_new_items = self.inductive_mapper.n_new_items if self.inductive_mapper else self.inductive_embedder.n_new_items
+
+        if _cfg(config, "add_oov_buckets", False):
+            self.n_user_oov_buckets = config["user_oov_buckets"]
+            self.user_oov_buckets = nn.Embedding(self.n_user_oov_buckets, self.embedding_size)
+            self.n_item_oov_buckets = config["item_oov_buckets"]
+            self.item_oov_buckets = nn.Embedding(self.n_item_oov_buckets, self.embedding_size)
+
+        # dtype of the assembled tables fed to the scoring kernel ('float32' | 'bfloat16')
+        td = _cfg(config, "table_dtype", "float32")
+        self.table_dtype = torch.bfloat16 if str(td) in ("bfloat16", "bf16", "torch.bfloat16") else torch.float32
+        self._item_cache: Optional[Tuple[int, torch.Tensor]] = None
+
+    # --- train/eval switches (abstract_recommender.py:147-171) -----------------------------
+    def set_oov_train(self, no_freeze=False):
+        self.oov_training = True
+        for m in (self.inductive_mapper, self.inductive_embedder):
+            if m is not None:
+                m.set_train()
+        if self.oov_freeze_embedding and not no_freeze:
+            self.freeze_non_oov_layers()
+
+    def set_oov_eval(self, no_freeze=False):
+        self.oov_training = False
+        for m in (self.inductive_mapper, self.inductive_embedder):
+            if m is not None:
+                m.set_eval()
+        if self.oov_freeze_embedding and not no_freeze:
+            self.unfreeze_non_oov_layers()
+
+    def freeze_non_oov_layers(self):
+        self.user_embedding.weight.requires_grad = False
+        self.item_embedding.weight.requires_grad = False
+
+    def unfreeze_non_oov_layers(self):
+        self.user_embedding.weight.requires_grad = True
+        self.item_embedding.weight.requires_grad = True
+
+    def _user_id_lookup(self, user_ids):
+        return ops.gather_rows(self.user_embedding.weight.detach(), user_ids)
+
+    def _item_id_lookup(self, item_ids):
+        return ops.gather_rows(self.item_embedding.weight.detach(), item_ids)
+
+    # --- fused gather + OOV embed (bpr.py:48-78, 94-125) ----------------------------------------
+    def _assemble(self, side: str, ids: torch.Tensor, out=None, out_dtype=torch.float32) -> torch.Tensor:
+        ids = ids.to(self.device)
+        table = (self.user_embedding if side == "user" else self.item_embedding).weight.detach()
+        n_old = self.n_users if side == "user" else self.n_items
+        if self.inductive_mapper is not None:
+            ids = self.inductive_mapper.map_user_ids(ids) if side == "user" else self.inductive_mapper.map_item_ids(ids)
+        if self.inductive_embedder is not None:
+            return self.inductive_embedder.assemble_rows(side, ids, self, n_old, table, out=out, out_dtype=out_dtype)
+        # mapper only: in-vocab rows from the table, mapped OOV rows from *_oov_buckets(id - n_old)
+        if out is None:
+            out = torch.zeros((ids.shape[0], self.embedding_size), dtype=out_dtype, device=self.device)
+        ops.gather_rows(table, ids, out=out)                                    # skips ids >= n_old
+        buckets = (self.user_oov_buckets if side == "user" else self.item_oov_buckets).weight.detach()
+        ops.gather_rows(buckets, ids, idx_offset=-n_old, out=out)               # skips ids < n_old
+        return out
+
+    def get_user_embedding(self, new_user_ids):
+        return self._assemble("user", new_user_ids)
+
+    def get_item_embedding(self, item):
+        return self._assemble("item", item)
+
+    def forward(self, user, item):
+        return self.get_user_embedding(user), self.get_item_embedding(item)
+
+    def predict(self, interaction):
+        user_e, item_e = self.forward(interaction[self.USER_ID], interaction[self.ITEM_ID])
+        return torch.mul(user_e, item_e).sum(dim=1)
+
+    # --- full-sort: reference-shaped (dense) and fused ------------------------------------------
+    def ind_full_sort_predict(self, interaction, item_ids):
+        """bpr.py:151-156: flat [Q * N] raw dot products over `item_ids` (dense, for drop-in use)."""
+        user_e = self._assemble("user", interaction[self.USER_ID], out_dtype=self.table_dtype)
+        all_item_e = self._assemble("item", item_ids, out_dtype=self.table_dtype)
+        return ops.fullsort_scores(user_e, all_item_e).view(-1)
+
+    def full_sort_predict(self, interaction):
+        user_e = self._assemble("user", interaction[self.USER_ID], out_dtype=self.table_dtype)
+        all_item_e = self.item_embedding.weight.detach().to(self.table_dtype)
+        return ops.fullsort_scores(user_e, all_item_e).view(-1)
+
+    def build_item_table(self, n_total_items: Optional[int] = None, row_range: Optional[Tuple[int, int]] = None,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """All-item embedding table `get_item_embedding(arange(N))` (bpr.py:154) in `table_dtype`;
+        `row_range=(lo, hi)` builds one contiguous shard (SURVEY §8e row-sharding)."""
+        n_total = self.n_new_items if n_total_items is None else n_total_items
+        lo, hi = (0, n_total) if row_range is None else row_range
+        ids = torch.arange(lo, hi, device=self.device, dtype=torch.int64)
+        return self._assemble("item", ids, out=out, out_dtype=self.table_dtype)
+
+    def full_sort_topk(self, interaction, k: int, n_total_items: Optional[int] = None, history_index=None,
+                       seg: Tuple[int, int] = (0, INT64_MAX), item_table: Optional[torch.Tensor] = None,
+                       item_id_offset: int = 0, hist_csr=None):
+        """Fused replacement of ind_full_sort_predict + evaluator.py:91-94 masks + collector.py:153 top-k.
+
+        Returns (scores fp32 [Q, k], item ids int64 [Q, k]).  The item table is rebuilt on every call
+        (what bpr.py:154 does) unless `item_table` (e.g. a shard built by `build_item_table`) is given.
+        `history_index` is the (row, item) pair of tensors the FullSortEvalDataLoader yields."""
+        users = interaction[self.USER_ID] if not isinstance(interaction, torch.Tensor) else interaction
+        user_e = self._assemble("user", users, out_dtype=self.table_dtype)
+        if item_table is None:
+            item_table = self.build_item_table(n_total_items)
+        if hist_csr is None and history_index is not None:
+            hist_csr = ops.pairs_to_csr(history_index[0].to(self.device), history_index[1].to(self.device), user_e.shape[0])
+        return ops.fullsort_topk(user_e, item_table, k, item_id_offset=item_id_offset, mask_pad=True, seg=seg, hist=hist_csr)
+
+
+class BPR(InductiveGeneralRecommender):
+    """reference model/general_recommender/bpr.py:32-163."""
+
+    def __init__(self, config, dataset, inductive_mapper=None, inductive_embedder=None):
+        super().__init__(config, dataset, inductive_mapper, inductive_embedder)
+        self.user_embedding = nn.Embedding(self.n_users, self.embedding_size)
+        self.item_embedding = nn.Embedding(self.n_items, self.embedding_size)
+        self.apply(xavier_normal_initialization)
+
+
+class DirectAU(InductiveGeneralRecommender):
+    """reference model/general_recommender/directau.py:18-198.  `forward`/`predict` L2-normalise,
+    `ind_full_sort_predict` does NOT (directau.py:193-198) — kept as is."""
+
+    def __init__(self, config, dataset, inductive_mapper=None, inductive_embedder=None):
+        super().__init__(config, dataset, inductive_mapper, inductive_embedder)
+        self.gamma = _cfg(config, "gamma", 1.0)
+        self.user_embedding = nn.Embedding(self.n_users, self.embedding_size)
+        self.item_embedding = nn.Embedding(self.n_items, self.embedding_size)
+        self.restore_user_e = None
+        self.restore_item_e = None
+        self.other_parameter_name = ["restore_user_e", "restore_item_e"]
+        self.apply(xavier_normal_initialization)
+
+    def forward(self, user, item):
+        return F.normalize(self.get_user_embedding(user), dim=-1), F.normalize(self.get_item_embedding(item), dim=-1)
+
+    def full_sort_predict(self, interaction):
+        raise NotImplementedError()      # directau.py:183-184

@@ -1,0 +1,467 @@
+"""Tensor-level wrappers over the C-ABI (include/oov_b200.h).
+
+torch is plumbing here: it owns device memory and the current stream; every op below
+hands raw device pointers + sizes to liboov_b200.so and returns torch tensors.  All ops
+are asynchronous on `torch.cuda.current_stream()` and never synchronise with the host.
+They raise if the tensors are not on a CUDA device — there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import INT64_MAX, OOV_BF16, OOV_F32, PATH_AUTO, PATH_SIMT_FP32, PATH_TCGEN05, OovDheNet, OovRows
+
+TIE_EPS = 1e-6      # north_star: projection-sign ties with |x| < 1e-6 are counted and reported
+MAX_HASH = 16777216  # reference dh_embedder.py:53
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return OOV_F32
+    if t.dtype == torch.bfloat16:
+        return OOV_BF16
+    raise ValueError(f"unsupported dtype {t.dtype}: tables/outputs must be float32 or bfloat16")
+
+
+def _torch_dtype(code_or_dtype) -> torch.dtype:
+    if isinstance(code_or_dtype, torch.dtype):
+        return code_or_dtype
+    return torch.float32 if code_or_dtype == OOV_F32 else torch.bfloat16
+
+
+def _cuda(t: Optional[torch.Tensor], name: str, dtype=None, allow_none=False) -> None:
+    if t is None:
+        if allow_none:
+            return
+        raise ValueError(f"{name} is None")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must live on a CUDA device (got {t.device}); oov_b200 has no CPU fallback")
+    if dtype is not None and t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype} (got {t.dtype})")
+
+
+def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_ws_cache: dict = {}
+
+
+def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    """Per-(device, stream) scratch buffer, grown on demand and reused (ordered by the stream)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def _ids_1d(ids: torch.Tensor, name="ids") -> Tuple[torch.Tensor, int]:
+    _cuda(ids, name, torch.int64)
+    if ids.dim() != 1:
+        raise ValueError(f"{name} must be 1-D (got shape {tuple(ids.shape)})")
+    stride = ids.stride(0) if ids.numel() > 1 else 1
+    if stride < 1:
+        ids = ids.contiguous()
+        stride = 1
+    return ids, stride
+
+
+def make_rows(ids: torch.Tensor, D: int, out: Optional[torch.Tensor] = None, out_dtype=torch.float32,
+              n_old: int = 0, iv_table: Optional[torch.Tensor] = None, prime_pad: int = 0):
+    """Build the `oov_rows` struct.  `out` may be a strided view [n, D] with unit inner stride
+    (e.g. column f of a [B, fields, D] tensor); it is allocated when None."""
+    ids, ids_stride = _ids_1d(ids)
+    n = ids.shape[0]
+    if out is None:
+        out = torch.empty((n, D), dtype=_torch_dtype(out_dtype), device=ids.device)
+    _cuda(out, "out")
+    if out.dim() != 2 or out.shape[0] != n or out.shape[1] != D or (D > 1 and out.stride(1) != 1):
+        raise ValueError(f"out must be [n={n}, D={D}] with unit inner stride (got {tuple(out.shape)}, strides {out.stride()})")
+    out_stride = out.stride(0) if n > 1 else max(D, out.stride(0))
+    if iv_table is not None:
+        _cuda(iv_table, "iv_table")
+        if iv_table.dim() != 2 or iv_table.shape[1] != D or not iv_table.is_contiguous():
+            raise ValueError("iv_table must be contiguous [rows, D]")
+        if iv_table.shape[0] < n_old:
+            raise ValueError(f"iv_table has {iv_table.shape[0]} rows < n_old={n_old}")
+    r = OovRows()
+    r.ids, r.ids_stride, r.n, r.n_old, r.prime_pad = ids.data_ptr(), ids_stride, n, int(n_old), int(prime_pad)
+    r.iv_table = 0 if iv_table is None else iv_table.data_ptr()
+    r.iv_dtype = OOV_F32 if iv_table is None else _dt(iv_table)
+    r.out_dtype, r.out, r.out_stride, r.D = _dt(out), out.data_ptr(), out_stride, D
+    return r, out, (ids, iv_table)          # keep-alive tuple
+
+
+def new_counter(device) -> torch.Tensor:
+    """uint64 device counter (held in an int64 tensor) for the reported projection-sign ties."""
+    return torch.zeros(1, dtype=torch.int64, device=device)
+
+
+# ------------------------------------------------------------------------------------ LSH / SLSH
+def _feat_planes(feat: torch.Tensor, planes: torch.Tensor):
+    _cuda(feat, "feature_mat", torch.float32)
+    _cuda(planes, "planes", torch.float32)
+    if feat.dim() != 2 or planes.dim() != 2 or feat.shape[1] != planes.shape[1]:
+        raise ValueError(f"feature_mat {tuple(feat.shape)} / planes {tuple(planes.shape)} mismatch")
+    return feat.contiguous(), planes.contiguous()
+
+
+def lsh_bits(feat, planes, ids, prime_pad: int = 0, tie_eps: float = TIE_EPS,
+             tie_count: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Packed multi-hot words int32 [n, ceil(B/32)] (bit b&31 of word b>>5 = plane b).
+    reference: TorchLSHash.hash_points (torch_hash.py:55-60) on feature_mat[ids]."""
+    feat, planes = _feat_planes(feat, planes)
+    ids, stride = _ids_1d(ids)
+    B, F = planes.shape
+    bits = torch.empty((ids.shape[0], (B + 31) // 32), dtype=torch.int32, device=feat.device)
+    _lib.check(_lib.load().oov_lsh_bits(_p(feat), feat.shape[0], F, _p(planes), B, _p(ids), stride, ids.shape[0],
+                                        int(prime_pad), float(tie_eps), _p(bits), _p(tie_count), PATH_AUTO, _stream()))
+    return bits
+
+
+def lsh_embed(feat, planes, oov_weight, ids, out=None, out_dtype=torch.float32, n_old: int = 0, iv_table=None,
+              prime_pad: int = 0, tie_eps: float = TIE_EPS, tie_count=None, return_bits: bool = False,
+              path: int = PATH_AUTO):
+    """(H @ W) / H.sum(1) for OOV rows (lsh_embedder.py:141-179) + in-vocab gather (bpr.py:94-125)."""
+    feat, planes = _feat_planes(feat, planes)
+    _cuda(oov_weight, "oov_weight")
+    oov_weight = oov_weight.contiguous()
+    B, F = planes.shape
+    if oov_weight.dim() != 2 or oov_weight.shape[0] != B:
+        raise ValueError(f"oov_weight must be [B={B}, D] (got {tuple(oov_weight.shape)})")
+    D = oov_weight.shape[1]
+    rows, out, keep = make_rows(ids, D, out, out_dtype, n_old, iv_table, prime_pad)
+    lib = _lib.load()
+    bits = torch.empty((rows.n, (B + 31) // 32), dtype=torch.int32, device=feat.device) if return_bits else None
+    ws_bytes = 0 if return_bits else lib.oov_lsh_embed_workspace(rows.n, B, D, path)
+    ws = _workspace(ws_bytes, feat.device) if ws_bytes else None
+    _lib.check(lib.oov_lsh_embed(_p(feat), feat.shape[0], F, _p(planes), B, _p(oov_weight), _dt(oov_weight),
+                                 C.byref(rows), float(tie_eps), _p(bits), _p(tie_count), _p(ws),
+                                 0 if ws is None else ws.numel(), path, _stream()))
+    return (out, bits) if return_bits else out
+
+
+def slsh_embed(feat, planes, n_buckets: int, oov_weight, ids, out=None, out_dtype=torch.float32, n_old: int = 0,
+               iv_table=None, prime_pad: int = 0, tie_eps: float = TIE_EPS, tie_count=None,
+               return_buckets: bool = False):
+    """bucket = (bits_req + popcount(bits)) % n_buckets; out = W[bucket]
+    (single_lsh_embedder.py:82-109).  `oov_weight=None` computes bucket ids only."""
+    feat, planes = _feat_planes(feat, planes)
+    bits_req, F = planes.shape
+    lib = _lib.load()
+    buckets = None
+    if oov_weight is None:
+        ids, stride = _ids_1d(ids)
+        rows = OovRows()
+        rows.ids, rows.ids_stride, rows.n, rows.n_old, rows.prime_pad = ids.data_ptr(), stride, ids.shape[0], int(n_old), int(prime_pad)
+        rows.D = 1
+        out = None
+        return_buckets = True
+        wptr, wdt = None, OOV_F32
+    else:
+        _cuda(oov_weight, "oov_weight")
+        oov_weight = oov_weight.contiguous()
+        if oov_weight.dim() != 2 or oov_weight.shape[0] != n_buckets:
+            raise ValueError(f"oov_weight must be [n_buckets={n_buckets}, D] (got {tuple(oov_weight.shape)})")
+        rows, out, keep = make_rows(ids, oov_weight.shape[1], out, out_dtype, n_old, iv_table, prime_pad)
+        wptr, wdt = oov_weight, _dt(oov_weight)
+    if return_buckets:
+        buckets = torch.empty((rows.n,), dtype=torch.int64, device=feat.device)
+    _lib.check(lib.oov_slsh_embed(_p(feat), feat.shape[0], F, _p(planes), bits_req, int(n_buckets), _p(wptr), wdt,
+                                  C.byref(rows), float(tie_eps), _p(buckets), _p(tie_count), _stream()))
+    if oov_weight is None:
+        return buckets
+    return (out, buckets) if return_buckets else out
+
+
+# ------------------------------------------------------------------------------------ DHE
+class DheNet:
+    """Device view of one 4-layer hash net (dh_embedder.py:70-89): fp32 nn.Linear weights [out, in]."""
+
+    def __init__(self, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor]):
+        if len(weights) != 4 or len(biases) != 4:
+            raise ValueError("DHE net has exactly 4 Linear layers")
+        self.w = [w.detach().contiguous() for w in weights]
+        self.b = [b.detach().contiguous() for b in biases]
+        for t in self.w + self.b:
+            _cuda(t, "dhe weight", torch.float32)
+        self.H, self.hidden, self.D = self.w[0].shape[1], self.w[0].shape[0], self.w[3].shape[0]
+        if self.w[1].shape != (self.hidden, self.hidden) or self.w[2].shape != (self.hidden, self.hidden) \
+                or self.w[3].shape[1] != self.hidden:
+            raise ValueError("DHE net layer shapes are inconsistent")
+        s = OovDheNet()
+        for l in range(4):
+            s.w[l] = self.w[l].data_ptr()
+            s.b[l] = self.b[l].data_ptr()
+        s.H, s.hidden, s.D = self.H, self.hidden, self.D
+        self.struct = s
+
+    @classmethod
+    def from_sequential(cls, net: torch.nn.Sequential) -> "DheNet":
+        lin = [m for m in net if isinstance(m, torch.nn.Linear)]
+        return cls([m.weight for m in lin], [m.bias for m in lin])
+
+
+def keys_tensor(keys: Sequence[bytes], device) -> torch.Tensor:
+    """list of 16-byte keys (dh_embedder.py:95-120) -> uint8 [H, 16] on the device."""
+    if any(len(k) != 16 for k in keys):
+        raise ValueError("SipHash keys must be 16 bytes")
+    return torch.tensor(list(b"".join(keys)), dtype=torch.uint8).view(len(keys), 16).to(device)
+
+
+def dhe_hash(ids, keys: torch.Tensor, mod: int = MAX_HASH) -> torch.Tensor:
+    """int32 [n, H]: LE_u64(SipHash-2-4(key_j, LE8(id_i))) % mod  (dh_embedder.py:140-170)."""
+    ids, stride = _ids_1d(ids)
+    _cuda(keys, "keys", torch.uint8)
+    keys = keys.contiguous()
+    out = torch.empty((ids.shape[0], keys.shape[0]), dtype=torch.int32, device=ids.device)
+    _lib.check(_lib.load().oov_dhe_hash(_p(ids), stride, ids.shape[0], _p(keys), keys.shape[0], int(mod), _p(out), _stream()))
+    return out
+
+
+def dhe_mlp(hashes: torch.Tensor, net: DheNet, out=None, out_dtype=torch.float32, path: int = PATH_AUTO):
+    _cuda(hashes, "hashes", torch.int32)
+    hashes = hashes.contiguous()
+    n = hashes.shape[0]
+    if hashes.dim() != 2 or hashes.shape[1] != net.H:
+        raise ValueError(f"hashes must be [n, H={net.H}]")
+    if out is None:
+        out = torch.empty((n, net.D), dtype=_torch_dtype(out_dtype), device=hashes.device)
+    lib = _lib.load()
+    ws = _workspace(lib.oov_dhe_workspace(n, C.byref(net.struct), path), hashes.device)
+    _lib.check(lib.oov_dhe_mlp(_p(hashes), n, C.byref(net.struct), _p(out), _dt(out), out.stride(0) if n > 1 else net.D,
+                               _p(ws), ws.numel(), path, _stream()))
+    return out
+
+
+def dhe_embed(ids, keys: torch.Tensor, net: DheNet, out=None, out_dtype=torch.float32, n_old: int = 0, iv_table=None,
+              mod: int = MAX_HASH, path: int = PATH_AUTO):
+    """hash + MLP (+ in-vocab gather).  DHE does not de-pad ids (dh_embedder.py:219-245)."""
+    _cuda(keys, "keys", torch.uint8)
+    keys = keys.contiguous()
+    if keys.shape[0] != net.H:
+        raise ValueError(f"{keys.shape[0]} keys but the net expects H={net.H}")
+    rows, out, keep = make_rows(ids, net.D, out, out_dtype, n_old, iv_table, 0)
+    lib = _lib.load()
+    ws = _workspace(lib.oov_dhe_workspace(rows.n, C.byref(net.struct), path), keys.device)
+    _lib.check(lib.oov_dhe_embed(_p(keys), int(mod), C.byref(net.struct), C.byref(rows), _p(ws), ws.numel(), path, _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------ mean / zero / gathers
+def col_mean(table: torch.Tensor) -> torch.Tensor:
+    """fp32 [D] mean over ALL rows (mean_embedder.py:55-60)."""
+    _cuda(table, "table")
+    table = table.contiguous()
+    rows_, D = table.shape
+    lib = _lib.load()
+    ws = _workspace(lib.oov_col_mean_workspace(rows_, D), table.device)
+    out = torch.empty((D,), dtype=torch.float32, device=table.device)
+    _lib.check(lib.oov_col_mean(_p(table), _dt(table), rows_, D, _p(out), _p(ws), ws.numel(), _stream()))
+    return out
+
+
+def const_embed(vec: Optional[torch.Tensor], ids, D: int, out=None, out_dtype=torch.float32, n_old: int = 0, iv_table=None):
+    """OOV rows get `vec` (None = zeros): MeanEmbedder / ZeroEmbedder + in-vocab gather."""
+    if vec is not None:
+        _cuda(vec, "vec", torch.float32)
+        vec = vec.contiguous()
+        if vec.numel() != D:
+            raise ValueError("vec must have D elements")
+    rows, out, keep = make_rows(ids, D, out, out_dtype, n_old, iv_table, 0)
+    _lib.check(_lib.load().oov_const_embed(_p(vec), C.byref(rows), _stream()))
+    return out
+
+
+def gather_rows(table: torch.Tensor, idx, idx_offset: int = 0, out=None, out_dtype=None):
+    _cuda(table, "table")
+    table = table.contiguous()
+    idx, stride = _ids_1d(idx, "idx")
+    n, D = idx.shape[0], table.shape[1]
+    if out is None:
+        out = torch.empty((n, D), dtype=table.dtype if out_dtype is None else _torch_dtype(out_dtype), device=table.device)
+    _lib.check(_lib.load().oov_gather_rows(_p(table), _dt(table), table.shape[0], D, _p(idx), stride, n, int(idx_offset),
+                                           _p(out), _dt(out), out.stride(0) if n > 1 else D, _stream()))
+    return out
+
+
+def map_ids(ids, n_old: int, n_buckets: int, fn: str) -> torch.Tensor:
+    code = {"mod": 0, "fast": 1, "3round": 2, "64bit": 3}.get(fn)
+    if code is None:
+        raise ValueError(f"Unknown hash function {fn}")
+    _cuda(ids, "ids", torch.int64)
+    ids = ids.contiguous()
+    out = torch.empty_like(ids)
+    _lib.check(_lib.load().oov_map_ids(_p(ids), ids.numel(), int(n_old), int(n_buckets), code, _p(out), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------ scoring + top-k
+def _hist(hist, Q, device):
+    if hist is None:
+        return None, None
+    rowptr, cols = hist
+    _cuda(rowptr, "hist_rowptr", torch.int32)
+    _cuda(cols, "hist_cols", torch.int32)
+    if rowptr.numel() != Q + 1:
+        raise ValueError(f"hist_rowptr must have Q+1={Q + 1} entries")
+    if cols.numel() == 0:                      # keep a valid pointer for the NULL-consistency check
+        cols = torch.zeros(1, dtype=torch.int32, device=device)
+    return rowptr.contiguous(), cols.contiguous()
+
+
+def _pad16(users: torch.Tensor, items: torch.Tensor):
+    """The scoring kernels read rows with 128-bit loads: zero-pad D to a multiple of 16 (zeros add
+    nothing to a dot product).  A copy — only taken for embedding sizes that are not 16-aligned."""
+    D = users.shape[1]
+    if D % 16 == 0:
+        return users, items
+    pad = 16 - D % 16
+    return torch.nn.functional.pad(users, (0, pad)), torch.nn.functional.pad(items, (0, pad))
+
+
+def fullsort_topk(users: torch.Tensor, items: torch.Tensor, k: int, item_id_offset: int = 0, mask_pad: bool = True,
+                  seg: Tuple[int, int] = (0, INT64_MAX), hist=None, path: int = PATH_AUTO):
+    """Fused score + mask + top-k: returns (scores fp32 [Q,k], global ids int64 [Q,k]) ordered by
+    (score desc, id asc).  reference: bpr.py:151-156 + evaluator.py:91-94 + collector.py:153-159."""
+    _cuda(users, "users")
+    _cuda(items, "items")
+    if users.dtype != items.dtype:
+        raise ValueError("users and items must share a dtype")
+    users, items = users.contiguous(), items.contiguous()
+    Q, D = users.shape
+    N = items.shape[0]
+    if N and items.shape[1] != D:
+        raise ValueError("users / items embedding size mismatch")
+    users, items = _pad16(users, items)
+    D = users.shape[1]
+    rowptr, cols = _hist(hist, Q, users.device)
+    out_s = torch.empty((Q, k), dtype=torch.float32, device=users.device)
+    out_i = torch.empty((Q, k), dtype=torch.int64, device=users.device)
+    lib = _lib.load()
+    ws = _workspace(lib.oov_fullsort_topk_workspace(Q, max(N, 1), D, k, path), users.device)
+    _lib.check(lib.oov_fullsort_topk(_p(users), _p(items), _dt(users), Q, N, D, k, int(item_id_offset), int(bool(mask_pad)),
+                                     int(seg[0]), int(seg[1]), _p(rowptr), _p(cols), _p(out_s), _p(out_i), _p(ws),
+                                     ws.numel(), path, _stream()))
+    return out_s, out_i
+
+
+def fullsort_scores(users, items, item_id_offset: int = 0, mask_pad: bool = False, seg=(0, INT64_MAX), hist=None):
+    """Dense fp32 [Q, N] scores (what the reference materialises); masks optional."""
+    _cuda(users, "users")
+    _cuda(items, "items")
+    users, items = users.contiguous(), items.contiguous()
+    Q, D = users.shape
+    N = items.shape[0]
+    users, items = _pad16(users, items)
+    D = users.shape[1]
+    rowptr, cols = _hist(hist, Q, users.device)
+    scores = torch.empty((Q, N), dtype=torch.float32, device=users.device)
+    _lib.check(_lib.load().oov_fullsort_scores(_p(users), _p(items), _dt(users), Q, N, D, int(item_id_offset),
+                                               int(bool(mask_pad)), int(seg[0]), int(seg[1]), _p(rowptr), _p(cols),
+                                               _p(scores), N, _stream()))
+    return scores
+
+
+def dense_topk(scores: torch.Tensor, k: int):
+    """torch.topk(scores, k) replacement for a materialised fp32 [Q, N] matrix (collector.py:153-159)."""
+    _cuda(scores, "scores", torch.float32)
+    if scores.dim() != 2 or scores.stride(1) != 1:
+        scores = scores.contiguous()
+    Q, N = scores.shape
+    out_s = torch.empty((Q, k), dtype=torch.float32, device=scores.device)
+    out_i = torch.empty((Q, k), dtype=torch.int64, device=scores.device)
+    _lib.check(_lib.load().oov_dense_topk(_p(scores), scores.stride(0) if Q > 1 else N, Q, N, k, _p(out_s), _p(out_i), _stream()))
+    return out_s, out_i
+
+
+def topk_merge(cand_scores: torch.Tensor, cand_idx: torch.Tensor):
+    """[G, Q, k] shard candidates -> global (scores, ids) [Q, k]."""
+    _cuda(cand_scores, "cand_scores", torch.float32)
+    _cuda(cand_idx, "cand_idx", torch.int64)
+    cand_scores, cand_idx = cand_scores.contiguous(), cand_idx.contiguous()
+    G, Q, k = cand_scores.shape
+    out_s = torch.empty((Q, k), dtype=torch.float32, device=cand_scores.device)
+    out_i = torch.empty((Q, k), dtype=torch.int64, device=cand_scores.device)
+    _lib.check(_lib.load().oov_topk_merge(_p(cand_scores), _p(cand_idx), G, Q, k, _p(out_s), _p(out_i), _stream()))
+    return out_s, out_i
+
+
+def topk_hits(topk_idx: torch.Tensor, pos_rowptr: torch.Tensor, pos_cols: torch.Tensor) -> torch.Tensor:
+    """'rec.topk' matrix [Q, k+1] = [hits | pos_len] (collector.py:160-166)."""
+    _cuda(topk_idx, "topk_idx", torch.int64)
+    _cuda(pos_rowptr, "pos_rowptr", torch.int32)
+    _cuda(pos_cols, "pos_cols", torch.int32)
+    topk_idx = topk_idx.contiguous()
+    Q, k = topk_idx.shape
+    if pos_cols.numel() == 0:
+        pos_cols = torch.zeros(1, dtype=torch.int32, device=topk_idx.device)
+    out = torch.empty((Q, k + 1), dtype=torch.int32, device=topk_idx.device)
+    _lib.check(_lib.load().oov_topk_hits(_p(topk_idx), Q, k, _p(pos_rowptr.contiguous()), _p(pos_cols.contiguous()), _p(out), _stream()))
+    return out
+
+
+def pairs_to_csr(rows_idx: torch.Tensor, cols_idx: torch.Tensor, Q: int):
+    """(row, item) index pairs (general_dataloader.py:270-292 history_index / positive_u,i) -> CSR
+    with ascending columns per row.  Pure index plumbing, done with torch ops on the device."""
+    if rows_idx is None or rows_idx.numel() == 0:
+        dev = rows_idx.device if rows_idx is not None else "cuda"
+        return torch.zeros(Q + 1, dtype=torch.int32, device=dev), torch.zeros(0, dtype=torch.int32, device=dev)
+    key = rows_idx.to(torch.int64) * (1 << 32) + cols_idx.to(torch.int64)
+    key, _ = torch.sort(key)
+    r = torch.div(key, 1 << 32, rounding_mode="floor")
+    c = key - r * (1 << 32)
+    counts = torch.bincount(r, minlength=Q)
+    rowptr = torch.zeros(Q + 1, dtype=torch.int64, device=key.device)
+    rowptr[1:] = torch.cumsum(counts, 0)
+    return rowptr.to(torch.int32), c.to(torch.int32)
+
+
+# ------------------------------------------------------------------------------------ context models
+def token_gather(tokens: torch.Tensor, offsets: torch.Tensor, table: torch.Tensor, n_users: int, n_items: int,
+                 user_const=None, item_const=None, uid_idx: int = 0, iid_idx: int = 1, out=None, out_dtype=None):
+    """[B, fields] ids -> [B, fields, D]; OOV user/item cells get the constants when given, else are
+    left for a following *_embed call (abstract_recommender.py:794-842)."""
+    _cuda(tokens, "token_fields", torch.int64)
+    _cuda(offsets, "offsets", torch.int64)
+    _cuda(table, "table")
+    tokens, offsets, table = tokens.contiguous(), offsets.contiguous(), table.contiguous()
+    Bn, fields = tokens.shape
+    D = table.shape[1]
+    if out is None:
+        out = torch.empty((Bn, fields, D), dtype=table.dtype if out_dtype is None else _torch_dtype(out_dtype), device=table.device)
+    for v, nm in ((user_const, "user_const"), (item_const, "item_const")):
+        _cuda(v, nm, torch.float32, allow_none=True)
+    _lib.check(_lib.load().oov_token_gather(_p(tokens), Bn, fields, _p(offsets), _p(table), _dt(table), table.shape[0], D,
+                                            int(n_users), int(n_items), uid_idx, iid_idx, _p(user_const), _p(item_const),
+                                            _p(out), _dt(out), _stream()))
+    return out
+
+
+def first_order_sum(tokens, offsets, table1, n_users: int, n_items: int, oov_user_val=None, oov_item_val=None,
+                    uid_idx: int = 0, iid_idx: int = 1) -> torch.Tensor:
+    """[B] = sum over fields of the D=1 table with OOV cells replaced (layers.py:1634-1693)."""
+    _cuda(tokens, "token_fields", torch.int64)
+    _cuda(table1, "table1", torch.float32)
+    tokens, offsets = tokens.contiguous(), offsets.contiguous()
+    t1 = table1.contiguous().view(-1)
+    Bn, fields = tokens.shape
+    out = torch.empty((Bn,), dtype=torch.float32, device=tokens.device)
+    _lib.check(_lib.load().oov_first_order_sum(_p(tokens), Bn, fields, _p(offsets), _p(t1), t1.numel(), int(n_users),
+                                               int(n_items), uid_idx, iid_idx, _p(oov_user_val), _p(oov_item_val),
+                                               _p(out), _stream()))
+    return out
+
+
+def launch_count() -> int:
+    return int(_lib.load().oov_launch_count())

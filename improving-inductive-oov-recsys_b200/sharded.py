@@ -1,0 +1,102 @@
+"""Row-sharded full-sort retrieval over N GPUs — no reference counterpart: the
+reference's inductive path is single-process (its driver never sets local_rank, configurator.py:487-494).
+
+One process per GPU (`torch.distributed`, NCCL over NVLink).  Items are independent rows, so the item
+side is row-sharded and the small state (planes, OOV buckets, DHE nets/keys, user tables, the query
+batch) is replicated.  Each rank embeds its own rows, runs the fused score+mask+top-k on its shard and
+contributes `[S, Q, k]` (score, global id) candidates; ONE all-gather moves 16·S·Q·k bytes per rank and
+every rank merges G·S·k -> k with the deterministic (score desc, id asc) rule, so all ranks hold the
+same answer.  There is no other data-path collective.
+
+Load balance: new (OOV) ids are appended after the in-vocab ids, and OOV rows are the expensive ones to
+embed, so each rank owns one slice of the in-vocab range AND one slice of the OOV range (S = 2 segments)
+instead of one contiguous slice of [0, N).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ._lib import INT64_MAX
+
+
+def split_range(lo: int, hi: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, near-equal split of [lo, hi) — the first (hi-lo) % world ranks get one extra row."""
+    n = max(hi - lo, 0)
+    base, rem = divmod(n, world)
+    start = lo + rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_segments(n_old: int, n_total: int, rank: int, world: int, balanced: bool = True) -> List[Tuple[int, int]]:
+    """Item-id segments owned by `rank`.  balanced: [slice of in-vocab ids, slice of OOV ids]."""
+    if not balanced:
+        return [split_range(0, n_total, rank, world)]
+    return [split_range(0, min(n_old, n_total), rank, world), split_range(min(n_old, n_total), n_total, rank, world)]
+
+
+def pack_candidates(scores: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """(fp32 [.., k], int64 [.., k]) -> int64 [.., k, 2]: one buffer, one all-gather."""
+    bits = scores.contiguous().view(torch.int32).to(torch.int64)
+    return torch.stack([bits, idx], dim=-1).contiguous()
+
+
+def unpack_candidates(buf: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    scores = buf[..., 0].to(torch.int32).contiguous().view(torch.float32)
+    return scores, buf[..., 1].contiguous()
+
+
+class ShardedRetrieval:
+    """Row-sharded `full_sort_topk`.  `model` is a BPR / DirectAU from `model/general.py`.
+
+    `local_topk_fn(user_e, table, k, item_id_offset, seg, hist) -> (scores, ids)` and
+    `merge_fn(cand_scores [L,Q,k], cand_idx [L,Q,k]) -> (scores, ids)` default to the CUDA kernels;
+    the CPU (gloo) tests inject oracle stand-ins to exercise the exchange logic without a GPU.
+    """
+
+    def __init__(self, model, n_total_items: int, rank: Optional[int] = None, world_size: Optional[int] = None,
+                 group=None, balanced: bool = True, local_topk_fn: Optional[Callable] = None,
+                 merge_fn: Optional[Callable] = None, build_table_fn: Optional[Callable] = None):
+        self.model = model
+        self.group = group
+        inited = dist.is_available() and dist.is_initialized()
+        self.rank = rank if rank is not None else (dist.get_rank(group) if inited else 0)
+        self.world = world_size if world_size is not None else (dist.get_world_size(group) if inited else 1)
+        self.n_total = n_total_items
+        self.segments = [s for s in shard_segments(model.n_items, n_total_items, self.rank, self.world, balanced)]
+        if local_topk_fn is None or merge_fn is None:
+            from . import ops
+            local_topk_fn = local_topk_fn or (lambda ue, tab, k, off, seg, hist: ops.fullsort_topk(
+                ue, tab, k, item_id_offset=off, mask_pad=True, seg=seg, hist=hist))
+            merge_fn = merge_fn or ops.topk_merge
+        self._local_topk, self._merge = local_topk_fn, merge_fn
+        self._build = build_table_fn or (lambda lo, hi: model.build_item_table(n_total_items, row_range=(lo, hi)))
+        self.tables: Optional[List[torch.Tensor]] = None
+
+    def build_shard(self) -> List[torch.Tensor]:
+        """Embed this rank's rows (in-vocab gather + OOV embed); no communication."""
+        self.tables = [self._build(lo, hi) for lo, hi in self.segments]
+        return self.tables
+
+    def local_candidates(self, user_e: torch.Tensor, k: int, hist=None, seg=(0, INT64_MAX)) -> torch.Tensor:
+        if self.tables is None:
+            self.build_shard()
+        packed = []
+        for (lo, hi), tab in zip(self.segments, self.tables):
+            s, i = self._local_topk(user_e, tab, k, lo, seg, hist)
+            packed.append(pack_candidates(s, i))
+        return torch.stack(packed, dim=0)                       # [S, Q, k, 2]
+
+    def topk(self, user_e: torch.Tensor, k: int, hist=None, seg=(0, INT64_MAX)):
+        """Global (scores [Q,k], ids [Q,k]) — identical on every rank."""
+        local = self.local_candidates(user_e, k, hist, seg)
+        if self.world > 1:
+            cand = torch.empty((self.world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype,
+                               device=local.device)              # ranks concatenated along dim 0
+            dist.all_gather_into_tensor(cand, local, group=self.group)
+        else:
+            cand = local
+        cs, ci = unpack_candidates(cand)
+        return self._merge(cs, ci)

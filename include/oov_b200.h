@@ -1,0 +1,236 @@
+/*
+ * oov_b200.h — C-ABI of the B200-native OOV inductive-embedding + full-sort top-k path.
+ *
+ * One shared library (liboov_b200.so, sm_100a only, no CPU fallback).  Every entry
+ * point is `extern "C"`, takes plain device pointers + sizes (no torch types), is
+ * asynchronous on the given CUDA stream (`stream` = cudaStream_t cast to void*),
+ * performs no host synchronisation and no persistent allocation, and returns an
+ * int status (0 = ok, negative = error; `oov_last_error()` gives the message).
+ * The reference (snap-research/improving-inductive-oov-recsys) is pure Python: the
+ * "FFI" a maintainer adds is a ctypes binding; each entry point
+ * below names the reference code it replaces (paths relative to RecBole/recbole/).
+ *
+ * Conventions
+ *   - dtype codes: OOV_F32 (0) or OOV_BF16 (1) for tables / outputs.
+ *   - ids are int64 (oov_prime_pad = 112062759511 > 2^32, properties/overall.yaml:71).
+ *   - `oov_rows` describes the "assemble" contract shared by all embed calls: for row i,
+ *       id = ids[i * ids_stride]
+ *       id <  n_old : out[i] = iv_table[id]      (in-vocab gather; skipped if iv_table == NULL)
+ *       id >= n_old : out[i] = embedder(id)      (OOV)
+ *     which is model/general_recommender/bpr.py:48-125 / directau.py:107-172 without the
+ *     boolean-mask indexing (and its device->host syncs).
+ */
+#ifndef OOV_B200_H_
+#define OOV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OOV_OK 0
+#define OOV_ERR_ARG (-1)          /* bad shape / null pointer / unsupported size */
+#define OOV_ERR_ALIGN (-2)        /* pointer or stride not aligned as required   */
+#define OOV_ERR_ARCH (-3)         /* device is not sm_100                        */
+#define OOV_ERR_CUDA (-4)         /* a CUDA runtime call failed                  */
+#define OOV_ERR_WORKSPACE (-5)    /* workspace too small                         */
+
+#define OOV_F32 0
+#define OOV_BF16 1
+
+/* precision / path selector for the GEMM-shaped ops */
+#define OOV_PATH_AUTO 0           /* tcgen05 where the shape allows, else SIMT   */
+#define OOV_PATH_SIMT_FP32 1      /* CUDA-core fp32 FMA (exact-sign projections) */
+#define OOV_PATH_TCGEN05 2        /* tensor cores (tcgen05.mma + TMEM)           */
+
+const char* oov_version(void);
+const char* oov_last_error(void);
+/* OOV_OK iff `device` is compute capability 10.x; the Python host refuses to run otherwise. */
+int oov_check_device(int device);
+/* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
+uint64_t oov_launch_count(void);
+
+typedef struct oov_rows {
+    const int64_t* ids;     /* device; n ids spaced ids_stride elements apart            */
+    int64_t ids_stride;     /* 1 = contiguous; `fields` for a column of a [B,fields] batch */
+    int64_t n;
+    int64_t n_old;          /* ids < n_old are in-vocab                                  */
+    int64_t prime_pad;      /* 0 = eval; > 0 = training mode: feature row = id - prime_pad
+                               when id >= prime_pad (inductive/lsh_embedder.py:153-155)   */
+    const void* iv_table;   /* [>= n_old, D]; NULL = leave in-vocab rows of out untouched */
+    int32_t iv_dtype;
+    int32_t out_dtype;
+    void* out;              /* row i at out + i * out_stride elements                    */
+    int64_t out_stride;
+    int32_t D;
+    int32_t _pad;
+} oov_rows;
+
+/* ------------------------------------------------------------------------------------
+ * LSH  — replaces inductive/torch_hash.py:55-60 (TorchLSHash.hash_points) and
+ *        inductive/lsh_embedder.py:116-179 (_hash_node, embed_user_ids, embed_item_ids).
+ * feat   : [n_feat_rows, F] fp32 row-major feature matrix (lsh_embedder.py:80-106)
+ * planes : [B, F] fp32 (uniform_planes[0]); B = n_oov_buckets for `lsh`
+ * bits   : uint32 [n, ceil(B/32)], bit (b & 31) of word (b >> 5) = !(x.p_b < 0)
+ *          (so +0, -0 and NaN give 1, as in torch_hash.py:57-59)
+ * tie_count : optional device counter, incremented once per projection with |x| < tie_eps
+ * ------------------------------------------------------------------------------------ */
+int oov_lsh_bits(const float* feat, int64_t n_feat_rows, int32_t F,
+                 const float* planes, int32_t B,
+                 const int64_t* ids, int64_t ids_stride, int64_t n, int64_t prime_pad,
+                 float tie_eps, uint32_t* bits, unsigned long long* tie_count,
+                 int32_t path, void* stream);
+
+/* out[i] = (H_i @ W) / sum(H_i) for OOV rows — lsh_embedder.py:156-158,176-178; an
+ * all-zero H_i gives NaN (0/0) like the reference.  `bits_out` (optional) receives the
+ * multi-hot words of every row (garbage for in-vocab rows). */
+int oov_lsh_embed(const float* feat, int64_t n_feat_rows, int32_t F,
+                  const float* planes, int32_t B,
+                  const void* oov_weight, int32_t w_dtype,     /* [B, D] model.*_oov_buckets.weight */
+                  const oov_rows* rows, float tie_eps,
+                  uint32_t* bits_out, unsigned long long* tie_count,
+                  void* workspace, size_t workspace_bytes,
+                  int32_t path, void* stream);
+size_t oov_lsh_embed_workspace(int64_t n, int32_t B, int32_t D, int32_t path);
+
+/* ------------------------------------------------------------------------------------
+ * SLSH — replaces inductive/single_lsh_embedder.py:77-109.
+ * planes [bits_req, F]; bucket = (bits_req + popcount(bits)) % n_buckets
+ * (== ((2 ** H).sum(1)).long() % n_buckets, single_lsh_embedder.py:86); out[i] = W[bucket].
+ * bucket_out (optional int64 [n]) receives the bucket id of every OOV row (-1 for in-vocab).
+ * ------------------------------------------------------------------------------------ */
+int oov_slsh_embed(const float* feat, int64_t n_feat_rows, int32_t F,
+                   const float* planes, int32_t bits_req, int32_t n_buckets,
+                   const void* oov_weight, int32_t w_dtype,    /* [n_buckets, D]; NULL = ids only */
+                   const oov_rows* rows, float tie_eps,
+                   int64_t* bucket_out, unsigned long long* tie_count, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * DHE — replaces inductive/dh_embedder.py:140-170 (_get_hashes/_hash_ids; csiphash
+ *       SipHash-2-4) and :70-89,191-217 (the 4-layer hash nets).
+ * keys   : device uint8 [H, 16]
+ * hashes : uint32 [n, H] = LE_u64(SipHash-2-4(key_j, LE8(id_i))) % mod   (mod = 2^24)
+ * ------------------------------------------------------------------------------------ */
+int oov_dhe_hash(const int64_t* ids, int64_t ids_stride, int64_t n,
+                 const uint8_t* keys, int32_t H, uint64_t mod,
+                 uint32_t* hashes, void* stream);
+
+typedef struct oov_dhe_net {
+    const float* w[4];      /* nn.Linear weights [out, in]: [hid,H], [hid,hid], [hid,hid], [D,hid] */
+    const float* b[4];
+    int32_t H, hidden, D, _pad;
+} oov_dhe_net;
+
+/* out[i] = Sigmoid(L4(GELU(L3(GELU(L2(GELU(L1(float(hashes_i)))))))))  (erf GELU) */
+int oov_dhe_mlp(const uint32_t* hashes, int64_t n, const oov_dhe_net* net,
+                void* out, int32_t out_dtype, int64_t out_stride,
+                void* workspace, size_t workspace_bytes, int32_t path, void* stream);
+/* hash + MLP + assemble (dh_embedder.py:219-245; ids are NOT de-padded there). */
+int oov_dhe_embed(const uint8_t* keys, uint64_t mod, const oov_dhe_net* net,
+                  const oov_rows* rows, void* workspace, size_t workspace_bytes,
+                  int32_t path, void* stream);
+size_t oov_dhe_workspace(int64_t n, const oov_dhe_net* net, int32_t path);
+
+/* Pre-packed weights for the tcgen05 MLP (bf16, K-major tiles).  `packed` must hold
+ * oov_dhe_packed_bytes(net) bytes; repack after every weight update. */
+size_t oov_dhe_packed_bytes(const oov_dhe_net* net);
+int oov_dhe_pack(const oov_dhe_net* net, void* packed, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * mean / zero — replaces inductive/mean_embedder.py:42-87, zero_embedder.py:36-60.
+ * ------------------------------------------------------------------------------------ */
+/* mean[d] = (1/rows) * sum_r table[r, d]  (ALL rows, incl. the pad row 0); fp32 out.
+ * workspace: oov_col_mean_workspace(rows, D) bytes. */
+int oov_col_mean(const void* table, int32_t dtype, int64_t rows, int32_t D,
+                 float* mean_out, void* workspace, size_t workspace_bytes, void* stream);
+size_t oov_col_mean_workspace(int64_t rows, int32_t D);
+/* OOV rows get the constant vector `vec` (fp32 [D]; NULL = zeros), in-vocab rows are gathered. */
+int oov_const_embed(const float* vec, const oov_rows* rows, void* stream);
+
+/* Plain row gather out[i] = table[idx[i]] (nn.Embedding lookups bpr.py:80-84; the
+ * inductive_mapper path's *_oov_buckets(mapped_id - n_old)). */
+int oov_gather_rows(const void* table, int32_t dtype, int64_t table_rows, int32_t D,
+                    const int64_t* idx, int64_t idx_stride, int64_t n, int64_t idx_offset,
+                    void* out, int32_t out_dtype, int64_t out_stride, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Full-sort scoring + masks + top-k — replaces bpr.py:151-156 / directau.py:193-198
+ * (score = user_e @ all_item_e.T), inductive/evaluator.py:91-94 (pad column + history
+ * -> -inf) and evaluator/collector.py:153-159 (torch.topk(scores, max(topk))).
+ *
+ * users [Q, D], items [N, D] (this shard's rows), same dtype.  Scores are fp32.
+ * Masked to -inf: global item id 0 (pad) when mask_pad != 0; ids outside
+ * [seg_lo, seg_hi) (inductive/collector_filter.py:172-175; pass 0, INT64_MAX for none);
+ * (user q, item) pairs of the CSR history (hist_rowptr int32 [Q+1], hist_cols int32,
+ * global item ids, ascending per row; NULL = none).
+ * Output per user: k (score, global id) pairs ordered by (score desc, id asc); NaN
+ * ranks above every number like torch.topk.  global id = local row + item_id_offset.
+ * If N < k the tail is filled with (-inf, -1).
+ * ------------------------------------------------------------------------------------ */
+int oov_fullsort_topk(const void* users, const void* items, int32_t dtype,
+                      int64_t Q, int64_t N, int32_t D, int32_t k,
+                      int64_t item_id_offset, int32_t mask_pad,
+                      int64_t seg_lo, int64_t seg_hi,
+                      const int32_t* hist_rowptr, const int32_t* hist_cols,
+                      float* out_scores, int64_t* out_idx,
+                      void* workspace, size_t workspace_bytes, int32_t path, void* stream);
+size_t oov_fullsort_topk_workspace(int64_t Q, int64_t N, int32_t D, int32_t k, int32_t path);
+
+/* Dense scores [Q, N] fp32 (the reference's materialised matrix; kept for parity tests
+ * and for callers that need `rec.score`): masks applied as above. */
+int oov_fullsort_scores(const void* users, const void* items, int32_t dtype,
+                        int64_t Q, int64_t N, int32_t D,
+                        int64_t item_id_offset, int32_t mask_pad, int64_t seg_lo, int64_t seg_hi,
+                        const int32_t* hist_rowptr, const int32_t* hist_cols,
+                        float* scores, int64_t scores_stride, void* stream);
+
+/* torch.topk(scores, k) of an already materialised [Q, N] fp32 matrix (collector.py:153-159 for
+ * callers that hold dense scores): (score desc, index asc), NaN first. */
+int oov_dense_topk(const float* scores, int64_t scores_stride, int64_t Q, int64_t N, int32_t k,
+                   float* out_scores, int64_t* out_idx, void* stream);
+
+/* Merge G per-shard candidate lists [G, Q, k] into the global top-k (the
+ * lists arrive by NCCL all-gather).  Order: (score desc, id asc), NaN first. */
+int oov_topk_merge(const float* cand_scores, const int64_t* cand_idx,
+                   int32_t G, int64_t Q, int32_t k,
+                   float* out_scores, int64_t* out_idx, void* stream);
+
+/* 'rec.topk' rows of evaluator/collector.py:160-166: hits[q, j] = 1 iff topk_idx[q, j] is a
+ * positive of user q (CSR pos_rowptr/pos_cols, ascending), last column = number of positives. */
+int oov_topk_hits(const int64_t* topk_idx, int64_t Q, int32_t k,
+                  const int32_t* pos_rowptr, const int32_t* pos_cols,
+                  int32_t* out_hits /* [Q, k+1] */, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Context models — replaces model/abstract_recommender.py:794-842 (embed_token_fields)
+ * with model/layers.py:150-153 (FMEmbedding), and model/layers.py:1634-1693.
+ * tokens [Bn, fields] int64; offsets [fields] int64; table [V, D].
+ * out[b, f] = table[tokens[b,f] + offsets[f]], except column uid_idx (resp. iid_idx) of
+ * rows whose id >= n_users (resp. n_items): those get user_const / item_const (fp32 [D])
+ * when given, else are left for an oov_*_embed call with ids_stride = fields,
+ * out_stride = fields * D.
+ * ------------------------------------------------------------------------------------ */
+int oov_token_gather(const int64_t* tokens, int64_t Bn, int32_t fields, const int64_t* offsets,
+                     const void* table, int32_t dtype, int64_t table_rows, int32_t D,
+                     int64_t n_users, int64_t n_items, int32_t uid_idx, int32_t iid_idx,
+                     const float* user_const, const float* item_const,
+                     void* out, int32_t out_dtype, void* stream);
+/* First-order term: out[b] = sum_f table1[tokens[b,f] + offsets[f]] with the OOV user/item
+ * entries replaced by oov_user_val[b] / oov_item_val[b] (fp32 [Bn], produced by a D = 1 embed). */
+int oov_first_order_sum(const int64_t* tokens, int64_t Bn, int32_t fields, const int64_t* offsets,
+                        const float* table1, int64_t table_rows,
+                        int64_t n_users, int64_t n_items, int32_t uid_idx, int32_t iid_idx,
+                        const float* oov_user_val, const float* oov_item_val,
+                        float* out, void* stream);
+
+/* inductive_mapper=random (inductive/random_mapper.py:70-130): new_id = id (id < n_old) or
+ * n_old + hash(id - n_old) % n_buckets.  fn: 0 mod, 1 fast, 2 3round, 3 64bit. */
+int oov_map_ids(const int64_t* ids, int64_t n, int64_t n_old, int64_t n_buckets, int32_t fn,
+                int64_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OOV_B200_H_ */

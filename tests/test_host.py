@@ -1,0 +1,174 @@
+"""CPU: host-side logic of the product — feature-matrix build, factory / constructor surface and
+state_dict keys (vs the golden fixtures of the reference), CSR helpers, shard arithmetic, metrics."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import parity_util as pu
+
+
+class Config(dict):
+    def __getitem__(self, key):
+        return dict.get(self, key, None)
+
+
+class Dataset:
+    def __init__(self, n_users, n_items, uf, itf):
+        self._num = {"user_id": n_users, "item_id": n_items}
+        self.user_num, self.item_num = n_users, n_items
+        self._uf, self._if = uf, itf
+
+    def num(self, f):
+        return self._num[f]
+
+    def get_user_feature(self):
+        return self._uf
+
+    def get_item_feature(self):
+        return self._if
+
+
+def _features(id_field, cols):
+    import oov_b200
+    d = {id_field: torch.arange(cols[0].shape[0])}
+    for i, c in enumerate(cols):
+        d[f"f{i}"] = torch.from_numpy(c)
+    return oov_b200.Interaction(d)
+
+
+def _cfg(case, kind, **kw):
+    c = Config(USER_ID_FIELD="user_id", ITEM_ID_FIELD="item_id", NEG_PREFIX="neg_", device="cpu",
+               embedding_size=case.D, add_oov_buckets=True, inductive_embedder=kind,
+               oov_normalization_type=getattr(case, "normalization", "per-feature"), topk=[10, 20])
+    c.update(kw)
+    return c
+
+
+@pytest.mark.parametrize("name", ["bpr_lsh_ml100k", "directau_lsh_global", "bpr_lsh_tinybuckets", "directau_slsh", "bpr_slsh_odd"])
+def test_feature_mats_and_state_dict_keys(name):
+    import oov_b200
+    case = cases.CASES[name]
+    inp = cases.retrieval_inputs(case)
+    g = pu.load_golden(name)
+    ds = Dataset(case.n_old_users, case.n_old_items, _features("user_id", inp["user_cols"]), _features("item_id", inp["item_cols"]))
+    cfg = _cfg(case, case.embedder, user_oov_buckets=case.B_user, item_oov_buckets=case.B_item)
+    emb = oov_b200.get_inductive_embedder(cfg, ds, mode=f"host-{name}", user_num=case.n_old_users, item_num=case.n_old_items)
+    assert emb.n_new_users == case.n_all_users and emb.n_new_items == case.n_all_items
+    pu.assert_close(emb.user_feature_mat.numpy(), g["user_feature_mat"], rtol=1e-6, atol=1e-7, what="user_feature_mat")
+    pu.assert_close(emb.item_feature_mat.numpy(), g["item_feature_mat"], rtol=1e-6, atol=1e-7, what="item_feature_mat")
+    planes = emb.item_lsh.uniform_planes[0]
+    want_planes = case.B_item if case.embedder == "lsh" else int(np.ceil(np.log2(case.B_item)))
+    assert tuple(planes.shape) == (want_planes, g["item_feature_mat"].shape[1])
+    cls = oov_b200.BPR if case.model == "BPR" else oov_b200.DirectAU
+    model = cls(cfg, ds, inductive_mapper=None, inductive_embedder=emb)
+    assert sorted(model.state_dict().keys()) == sorted(g["state_dict_keys"].tolist())
+    assert model.n_new_items == case.n_all_items
+    # training-mode switches propagate like abstract_recommender.py:147-171
+    model.set_oov_train()
+    assert emb.training and model.oov_training
+    model.set_oov_eval()
+    assert not emb.training
+
+
+def test_model_requires_mapper_or_embedder():
+    import oov_b200
+    case = cases.CASES["bpr_mean"]
+    ds = Dataset(10, 10, None, None)
+    with pytest.raises(NotImplementedError):
+        oov_b200.BPR(_cfg(case, None), ds)
+
+
+def test_feature_cache_shared_between_lsh_embedders():
+    """get_inductive.py:46-50 + lsh_embedder.py:77-106: second lsh embedder of the same mode reuses the
+    cached matrices (how the first-order embedder shares features)."""
+    import oov_b200
+    case = cases.CASES["directau_lsh_global"]
+    inp = cases.retrieval_inputs(case)
+    ds = Dataset(case.n_old_users, case.n_old_items, _features("user_id", inp["user_cols"]), _features("item_id", inp["item_cols"]))
+    cfg = _cfg(case, "lsh", user_oov_buckets=8, item_oov_buckets=8)
+    a = oov_b200.get_inductive_embedder(cfg, ds, mode="cache-test")
+    b = oov_b200.get_inductive_embedder(cfg, ds, mode="cache-test", embedding_size=1)
+    assert a.item_feature_mat is b.item_feature_mat
+    c = oov_b200.get_inductive_embedder(cfg, ds, mode="other-mode")
+    assert c.item_feature_mat is not a.item_feature_mat
+
+
+def test_factory_rejects_out_of_scope_embedders_and_unknown_norm():
+    import oov_b200
+    case = cases.CASES["bpr_mean"]
+    inp = cases.retrieval_inputs(case)
+    ds = Dataset(case.n_old_users, case.n_old_items, _features("user_id", inp["user_cols"]), _features("item_id", inp["item_cols"]))
+    for kind in ("knn", "dnn", "fdhe"):
+        with pytest.raises(NotImplementedError):
+            oov_b200.get_inductive_embedder(_cfg(case, kind, user_oov_buckets=4, item_oov_buckets=4), ds, mode="x")
+    assert oov_b200.get_inductive_embedder(_cfg(case, None), ds, mode="x") is None
+    with pytest.raises(ValueError, match="Invalid normalization type"):
+        oov_b200.get_inductive_embedder(_cfg(case, "slsh", user_oov_buckets=4, item_oov_buckets=4,
+                                             oov_normalization_type="bogus"), ds, mode="y")
+
+
+def test_dhe_key_file_protocol(tmp_path, monkeypatch):
+    """dh_embedder.py:95-120: keys are created once under ./hash_keys/<n>.hashes and re-read afterwards.
+    (Constructing the embedder on CPU touches no kernel; key upload needs a device, so stub it.)"""
+    import oov_b200
+    from oov_b200.inductive import dh_embedder
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(dh_embedder.ops, "keys_tensor", lambda keys, device: torch.zeros(len(keys), 16, dtype=torch.uint8))
+    fu = oov_b200.Interaction({"user_id": torch.arange(4), "f0": torch.ones(4, 2)})
+    a = dh_embedder.DeepHashEmbedder(fu, fu, 2, 2, 4, 4, 8, "cpu", cases.OOV_PRIME_PAD, 16)
+    path = tmp_path / "hash_keys" / "16.hashes"
+    assert path.exists()
+    stored = json.load(open(path))
+    assert len(stored) == 16 and all(len(bytes.fromhex(s)) == 16 for s in stored)
+    b = dh_embedder.DeepHashEmbedder(fu, fu, 2, 2, 4, 4, 8, "cpu", cases.OOV_PRIME_PAD, 16)
+    assert a.hash_keys == b.hash_keys
+    want = {f"{s}_hash_net.{i}.{p}" for s in ("user", "item") for i in (0, 2, 4, 6) for p in ("weight", "bias")}
+    assert want == set(a.state_dict().keys())
+    assert a.item_hash_net[0].in_features == 16 and a.item_hash_net[6].out_features == 8
+
+
+def test_pairs_to_csr():
+    from oov_b200 import ops
+    hu = torch.tensor([2, 0, 2, 2, 0])
+    hi = torch.tensor([9, 4, 1, 5, 3])
+    rp, cols = ops.pairs_to_csr(hu, hi, 4)
+    assert rp.tolist() == [0, 2, 2, 5, 5] and cols.tolist() == [3, 4, 1, 5, 9]
+    rp0, c0 = ops.pairs_to_csr(torch.zeros(0, dtype=torch.int64), torch.zeros(0, dtype=torch.int64), 3)
+    assert rp0.tolist() == [0, 0, 0, 0] and c0.numel() == 0
+    w_rp, w_c = pu.history_csr(hu.numpy(), hi.numpy(), 4)
+    assert rp.tolist() == w_rp.tolist() and cols.tolist() == w_c.tolist()
+
+
+def test_shard_arithmetic_and_packing():
+    from oov_b200 import sharded
+    for n, world in ((10, 4), (7, 8), (1_000_003, 8), (0, 2)):
+        parts = [sharded.split_range(5, 5 + n, r, world) for r in range(world)]
+        assert parts[0][0] == 5 and parts[-1][1] == 5 + n
+        assert all(a[1] == b[0] for a, b in zip(parts[:-1], parts[1:]))
+        sizes = [b - a for a, b in parts]
+        assert max(sizes) - min(sizes) <= 1
+    segs = [sharded.shard_segments(100, 260, r, 4) for r in range(4)]
+    assert sorted(x for s in segs for x in range(s[0][0], s[0][1])) == list(range(100))
+    assert sorted(x for s in segs for x in range(s[1][0], s[1][1])) == list(range(100, 260))
+    assert sharded.shard_segments(100, 260, 1, 4, balanced=False) == [(65, 130)]
+    s = torch.tensor([[1.5, -0.0, float("-inf"), float("nan")]])
+    i = torch.tensor([[7, 1 << 40, -1, 3]])
+    s2, i2 = sharded.unpack_candidates(sharded.pack_candidates(s, i))
+    assert torch.equal(i2, i) and torch.equal(s2.view(torch.int32), s.view(torch.int32))
+
+
+def test_topk_metrics():
+    from oov_b200.evaluator import topk_metrics
+    rec = np.array([[1, 0, 0, 1, 2], [0, 0, 0, 0, 1], [0, 1, 0, 0, 3]])
+    m = topk_metrics(rec, [2, 4])
+    assert m["hit@2"] == pytest.approx(2 / 3) and m["hit@4"] == pytest.approx(2 / 3)
+    assert m["recall@4"] == pytest.approx((1.0 + 0 + 1 / 3) / 3)
+    assert m["precision@2"] == pytest.approx((0.5 + 0 + 0.5) / 3)
+    assert m["mrr@4"] == pytest.approx((1 + 0 + 0.5) / 3)
+    dcg0 = 1 + 1 / np.log2(5)
+    idcg0 = 1 + 1 / np.log2(3)
+    assert m["ndcg@4"] == pytest.approx((dcg0 / idcg0 + 0 + (1 / np.log2(3)) / (1 + 1 / np.log2(3) + 1 / np.log2(4))) / 3)
