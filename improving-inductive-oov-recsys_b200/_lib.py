@@ -51,8 +51,7 @@ SIGNATURES = {
     "oov_dhe_mlp": (c_i32, [c_vp, c_i64, C.POINTER(OovDheNet), c_vp, c_i32, c_i64, c_vp, c_sz, c_i32, c_vp]),
     "oov_dhe_embed": (c_i32, [c_vp, c_u64, C.POINTER(OovDheNet), C.POINTER(OovRows), c_vp, c_sz, c_i32, c_vp]),
     "oov_dhe_workspace": (c_sz, [c_i64, C.POINTER(OovDheNet), c_i32]),
-    "oov_dhe_packed_bytes": (c_sz, [C.POINTER(OovDheNet)]),
-    "oov_dhe_pack": (c_i32, [C.POINTER(OovDheNet), c_vp, c_vp]),
+    "oov_tc_linear": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_i32, c_vp, c_i32, c_i64, c_vp]),
     "oov_col_mean": (c_i32, [c_vp, c_i32, c_i64, c_i32, c_vp, c_vp, c_sz, c_vp]),
     "oov_col_mean_workspace": (c_sz, [c_i64, c_i32]),
     "oov_const_embed": (c_i32, [c_vp, C.POINTER(OovRows), c_vp]),

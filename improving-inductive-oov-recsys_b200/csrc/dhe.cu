@@ -157,6 +157,20 @@ linear_act_simt(const void* __restrict__ A_, int64_t n, int K, const float* __re
 }
 
 int check_rows_public(const oov_rows* r, const char* who);
+namespace tc {
+size_t dhe_tc_workspace(int64_t n, const oov_dhe_net* net);
+bool dhe_tc_supported(const oov_dhe_net* net, uint64_t mod);
+int dhe_tc_run(const uint8_t* keys, uint64_t mod, const oov_dhe_net* net, const uint32_t* hashes_u32,
+               const int64_t* ids, int64_t ids_stride, int64_t n, int64_t n_old, const void* iv_table, int iv_dtype,
+               void* out, int out_dtype, int64_t out_stride, void* workspace, size_t workspace_bytes, cudaStream_t st);
+}  // namespace tc
+// OOV_PATH_AUTO: bf16 outputs take the tensor-core path (bf16 operands, fp32 accumulate, rtol 1e-3 contract),
+// fp32 outputs take the CUDA-core fp32 path (rtol 1e-5 contract).
+static bool use_tc(int path, int out_dtype, const oov_dhe_net* net, uint64_t mod) {
+    if (path == OOV_PATH_SIMT_FP32) return false;
+    if (!tc::dhe_tc_supported(net, mod)) return false;
+    return path == OOV_PATH_TCGEN05 || out_dtype == OOV_BF16;
+}
 constexpr int64_t DHE_CHUNK = 1 << 16;     // rows per pass of the fp32 path (bounds the workspace)
 
 static int check_net(const oov_dhe_net* net, const char* who) {
@@ -220,9 +234,11 @@ int oov_dhe_hash(const int64_t* ids, int64_t ids_stride, int64_t n, const uint8_
 }
 
 size_t oov_dhe_workspace(int64_t n, const oov_dhe_net* net, int32_t path) {
-    (void)path;
     if (!net || n <= 0) return 0;
-    return dhe_simt_workspace(n, net);
+    const size_t a = dhe_simt_workspace(n, net);
+    if (path == OOV_PATH_SIMT_FP32 || !tc::dhe_tc_supported(net, 1ull << 24)) return a;
+    const size_t b = tc::dhe_tc_workspace(n, net);      // AUTO may pick either path: size for the larger
+    return a > b ? a : b;
 }
 
 int oov_dhe_mlp(const uint32_t* hashes, int64_t n, const oov_dhe_net* net, void* out, int32_t out_dtype,
@@ -230,9 +246,14 @@ int oov_dhe_mlp(const uint32_t* hashes, int64_t n, const oov_dhe_net* net, void*
     int rc = check_net(net, "oov_dhe_mlp");
     if (rc) return rc;
     OOV_REQUIRE(n >= 0 && dtype_ok(out_dtype) && out_stride >= net->D, OOV_ERR_ARG, "oov_dhe_mlp: bad n/out_dtype/out_stride");
-    OOV_REQUIRE(path == OOV_PATH_AUTO || path == OOV_PATH_SIMT_FP32, OOV_ERR_ARG, "oov_dhe_mlp: unsupported path %d", path);
+    OOV_REQUIRE(path >= OOV_PATH_AUTO && path <= OOV_PATH_TCGEN05, OOV_ERR_ARG, "oov_dhe_mlp: unsupported path %d", path);
     if (n == 0) return OOV_OK;
     OOV_REQUIRE(hashes && out, OOV_ERR_ARG, "oov_dhe_mlp: NULL pointer");
+    OOV_REQUIRE(path != OOV_PATH_TCGEN05 || tc::dhe_tc_supported(net, 1ull << 24), OOV_ERR_ARG,
+                "oov_dhe_mlp: net shape not supported by the tcgen05 path");
+    if (use_tc(path, out_dtype, net, 1ull << 24))
+        return tc::dhe_tc_run(nullptr, 1ull << 24, net, hashes, nullptr, 1, n, 0, nullptr, 0, out, out_dtype, out_stride,
+                              workspace, workspace_bytes, (cudaStream_t)stream);
     const int64_t c = n < DHE_CHUNK ? n : DHE_CHUNK;
     const size_t hsz = align_up((size_t)c * net->H * 4, 256), asz = align_up((size_t)c * net->hidden * 4, 256);
     OOV_REQUIRE(workspace && workspace_bytes >= hsz + 2 * asz, OOV_ERR_WORKSPACE, "oov_dhe_mlp: workspace %zu < %zu",
@@ -258,9 +279,15 @@ int oov_dhe_embed(const uint8_t* keys, uint64_t mod, const oov_dhe_net* net, con
     OOV_REQUIRE(keys, OOV_ERR_ARG, "oov_dhe_embed: keys is NULL");
     OOV_REQUIRE(rows->D == net->D, OOV_ERR_ARG, "oov_dhe_embed: rows->D=%d != net->D=%d", rows->D, net->D);
     OOV_REQUIRE(mod >= 1 && mod <= (1ull << 32), OOV_ERR_ARG, "oov_dhe_embed: mod must be in [1, 2^32]");
-    OOV_REQUIRE(path == OOV_PATH_AUTO || path == OOV_PATH_SIMT_FP32, OOV_ERR_ARG, "oov_dhe_embed: unsupported path %d", path);
+    OOV_REQUIRE(path >= OOV_PATH_AUTO && path <= OOV_PATH_TCGEN05, OOV_ERR_ARG, "oov_dhe_embed: unsupported path %d", path);
     const int64_t n = rows->n;
     if (n == 0) return OOV_OK;
+    OOV_REQUIRE(path != OOV_PATH_TCGEN05 || tc::dhe_tc_supported(net, mod), OOV_ERR_ARG,
+                "oov_dhe_embed: net shape / modulus not supported by the tcgen05 path");
+    if (use_tc(path, rows->out_dtype, net, mod))
+        return tc::dhe_tc_run(keys, mod, net, nullptr, rows->ids, rows->ids_stride, n, rows->n_old, rows->iv_table,
+                              rows->iv_dtype, rows->out, rows->out_dtype, rows->out_stride, workspace, workspace_bytes,
+                              (cudaStream_t)stream);
     const int64_t c = n < DHE_CHUNK ? n : DHE_CHUNK;
     const size_t hsz = align_up((size_t)c * net->H * 4, 256), asz = align_up((size_t)c * net->hidden * 4, 256);
     OOV_REQUIRE(workspace && workspace_bytes >= hsz + 2 * asz, OOV_ERR_WORKSPACE, "oov_dhe_embed: workspace %zu < %zu",
@@ -283,13 +310,6 @@ int oov_dhe_embed(const uint8_t* keys, uint64_t mod, const oov_dhe_net* net, con
         if (rc) return rc;
     }
     return OOV_OK;
-}
-
-size_t oov_dhe_packed_bytes(const oov_dhe_net* net) { (void)net; return 0; }
-int oov_dhe_pack(const oov_dhe_net* net, void* packed, void* stream) {
-    (void)net; (void)packed; (void)stream;
-    oov::set_error("oov_dhe_pack: tcgen05 MLP path not built yet");
-    return OOV_ERR_ARG;
 }
 
 }  // extern "C"

@@ -1,0 +1,478 @@
+// tcgen05 / TMA / TMEM linear layer:  C[M, N] = act(A[M, K] . W[N, K]^T + bias)   (bf16 operands, fp32 accumulate)
+//
+// Warp-specialised persistent kernel (one CTA per SM, 384 threads):
+//   warp 0      TMA producer   : cp.async.bulk.tensor 128B-swizzled K-major tiles of A (128 x 64) and W (BN x 64)
+//   warp 1      MMA issuer     : one elected thread issues tcgen05.mma (M = 128, N = BN, K = 16), accumulators in TMEM
+//   warp 2      TMEM allocator : 2 x BN columns (double-buffered accumulator), deallocates at exit
+//   warps 4-11  epilogue       : tcgen05.ld (lane = output row, 32 columns per load) -> bias + GELU(erf)/sigmoid -> store
+// Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), persistent tile loop.
+//
+// Used for the DHE hash nets (reference inductive/dh_embedder.py:70-89): layer-1 inputs are the 24-bit hash
+// values split into three exact bf16 bytes (h = 65536 a + 256 b + c) against [65536 W1 | 256 W1 | W1], so the
+// un-normalised integers reach the MMA un-rounded; hidden activations are bf16, accumulation is fp32.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace oov {
+namespace tc {
+
+// ------------------------------------------------------------------ host: tensor map encode via the driver entry point
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+                      uint32_t box_rows) {
+    PFN_encodeTiled fn = get_encode_fn();
+    OOV_REQUIRE(fn != nullptr, OOV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    OOV_REQUIRE(aligned(base, 16) && row_stride_bytes % 16 == 0, OOV_ERR_ALIGN,
+                "TMA operand must be 16-byte aligned with a 16-byte multiple row stride");
+    OOV_REQUIRE(box_rows >= 1 && box_rows <= 256 && rows >= 1 && inner >= 1, OOV_ERR_ARG, "bad TMA box");
+    cuuint64_t gdim[2] = {inner, rows};
+    cuuint64_t gstride[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estride[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    OOV_REQUIRE(r == CUDA_SUCCESS, OOV_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+    return OOV_OK;
+}
+
+// ------------------------------------------------------------------ kernel
+constexpr int BM = 128, BK = 64;
+constexpr int GEMM_THREADS = 384;
+constexpr int EPI_WARP0 = 4, N_EPI_WARPS = 8;
+
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_SIGMOID = 2 };
+
+struct LinearEpi {
+    const float* bias;       // [N] or NULL
+    void* out;               // row r at out + r * ld elements
+    int64_t ld;
+    int out_dtype;           // OOV_F32 | OOV_BF16
+    int act;
+    // optional assemble contract for the last DHE layer (rows whose id < n_old take the in-vocab row instead)
+    const int64_t* ids;
+    int64_t ids_stride;
+    int64_t n_old;
+    const void* iv_table;
+    int iv_dtype;
+};
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+    if (act == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    if (act == ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+    return v;
+}
+
+template <int BN> struct GemmSmem {
+    static constexpr int A_BYTES = BM * BK * 2;            // 16 KB
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN >= 256) ? 4 : 6;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + alignment slack
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 int64_t M, int N, int K, LinearEpi epi) {
+    using S = GemmSmem<BN>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + S::STAGES;
+    uint64_t* tmem_full = empty_bar + S::STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m_tiles = (M + BM - 1) / BM;
+    const int n_tiles = (N + BN - 1) / BN;
+    const int64_t total_tiles = m_tiles * n_tiles;
+    const int k_blocks = (K + BK - 1) / BK;
+    constexpr uint32_t TMEM_COLS = 2 * BN;                  // 512 (BN = 256) or 128 (BN = 64): powers of two >= 32
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < S::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], N_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int64_t mt = t / n_tiles; const int nt = (int)(t - mt * n_tiles);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                    unsigned char* sa = smem + stage * S::STAGE_BYTES;
+                    tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, (int)(mt * BM));
+                    tma_load_2d(sa + S::A_BYTES, &tmB, &full_bar[stage], kb * BK, nt * BN);
+                    if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);           // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);               // TMA bytes have landed
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+                    const uint64_t adesc = make_sw128_desc(sa);
+                    const uint64_t bdesc = make_sw128_desc(sa + S::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)                 // +32 B along K per UMMA_K = 16 bf16
+                        tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                    tc_commit(&empty_bar[stage]);                     // frees the smem slot when the MMAs retire
+                    if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tmem_full[acc]);                           // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;                         // TMEM lane quarter this warp may access
+        const int half = (warp - EPI_WARP0) >> 2;       // column half handled by this warp
+        constexpr int COLS_PER_HALF = BN / 2;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int64_t mt = t / n_tiles; const int nt = (int)(t - mt * n_tiles);
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int64_t row = mt * BM + q * 32 + lane;
+            const bool row_ok = row < M;
+            bool take_iv = false;
+            int64_t id = 0;
+            if (epi.ids != nullptr && row_ok) {
+                id = epi.ids[row * epi.ids_stride];
+                take_iv = id < epi.n_old;
+            }
+#pragma unroll 1
+            for (int c0 = 0; c0 < COLS_PER_HALF; c0 += 32) {
+                const int col_in_tile = half * COLS_PER_HALF + c0;
+                uint32_t v[32];
+                tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + col_in_tile), v);
+                tc_wait_ld();
+                const int col0 = nt * BN + col_in_tile;
+                if (!row_ok || col0 >= N) continue;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(v[j]);
+                    if (epi.bias != nullptr && col0 + j < N) x += __ldg(epi.bias + col0 + j);
+                    f[j] = act_apply(x, epi.act);
+                }
+                if (take_iv) {
+                    if (epi.iv_table == nullptr || id < 0) continue;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < N) f[j] = load_elem(epi.iv_table, epi.iv_dtype, id * (int64_t)N + col0 + j);
+                }
+                if (epi.out_dtype == OOV_BF16) {
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(epi.out) + row * epi.ld + col0;
+                    if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                            pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            reinterpret_cast<uint4*>(o)[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < N) o[j] = __float2bfloat16_rn(f[j]);
+                    }
+                } else {
+                    float* o = reinterpret_cast<float*>(epi.out) + row * epi.ld + col0;
+                    if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            reinterpret_cast<float4*>(o)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < N) o[j] = f[j];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int BN>
+static int launch_linear(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, int64_t M, int N, int K,
+                         const LinearEpi& epi, cudaStream_t st) {
+    using S = GemmSmem<BN>;
+    CUtensorMap tmA, tmB;
+    int rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BM);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, BN);
+    if (rc) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        OOV_REQUIRE(e == cudaSuccess, OOV_ERR_CUDA, "cudaFuncSetAttribute(tc_linear_kernel): %s", cudaGetErrorString(e));
+        attr_done = true;
+    }
+    const int64_t tiles = cdiv(M, BM) * cdiv(N, BN);
+    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    tc_linear_kernel<BN><<<grid, GEMM_THREADS, S::TOTAL, st>>>(tmA, tmB, M, N, K, epi);
+    OOV_LAUNCH_CHECK("tc_linear_kernel");
+    return OOV_OK;
+}
+
+int tc_linear(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, int64_t M, int N, int K,
+              const LinearEpi& epi, cudaStream_t st) {
+    if (M == 0) return OOV_OK;
+    if (N > 64) return launch_linear<256>(A, lda, W, ldw, M, N, K, epi, st);
+    return launch_linear<64>(A, lda, W, ldw, M, N, K, epi, st);
+}
+
+// ------------------------------------------------------------------ DHE on tensor cores
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int b) { return (x << b) | (x >> (64 - b)); }
+#define TC_SIPROUND(v0, v1, v2, v3) \
+    do {                            \
+        v0 += v1; v1 = rotl64(v1, 13); v1 ^= v0; v0 = rotl64(v0, 32); \
+        v2 += v3; v3 = rotl64(v3, 16); v3 ^= v2;                      \
+        v0 += v3; v3 = rotl64(v3, 21); v3 ^= v0;                      \
+        v2 += v1; v1 = rotl64(v1, 17); v1 ^= v2; v2 = rotl64(v2, 32); \
+    } while (0)
+
+// SipHash-2-4 (dh_embedder.py:140-152) writing the 24-bit value as three exact bf16 bytes:
+// A1[i, j] = (h >> 16) & 255, A1[i, H + j] = (h >> 8) & 255, A1[i, 2H + j] = h & 255
+__global__ void __launch_bounds__(256)
+dhe_hash_split_kernel(const int64_t* __restrict__ ids, int64_t ids_stride, int64_t n, const uint8_t* __restrict__ keys,
+                      int H, uint64_t mod, __nv_bfloat16* __restrict__ A1, int64_t lda) {
+    extern __shared__ uint64_t kst[];
+    for (int j = threadIdx.x; j < H; j += 256) {
+        uint64_t k0 = 0, k1 = 0;
+        for (int b = 0; b < 8; ++b) { k0 |= (uint64_t)keys[16 * j + b] << (8 * b); k1 |= (uint64_t)keys[16 * j + 8 + b] << (8 * b); }
+        kst[j] = k0 ^ 0x736f6d6570736575ull;
+        kst[H + j] = k1 ^ 0x646f72616e646f6dull;
+        kst[2 * H + j] = k0 ^ 0x6c7967656e657261ull;
+        kst[3 * H + j] = k1 ^ 0x7465646279746573ull;
+    }
+    __syncthreads();
+    const bool pow2 = (mod & (mod - 1)) == 0;
+    const int64_t total = n * (int64_t)H;
+    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+        const int64_t i = t / H;
+        const int j = (int)(t - i * H);
+        const uint64_t m = (uint64_t)ids[i * ids_stride];
+        uint64_t v0 = kst[j], v1 = kst[H + j], v2 = kst[2 * H + j], v3 = kst[3 * H + j];
+        v3 ^= m; TC_SIPROUND(v0, v1, v2, v3); TC_SIPROUND(v0, v1, v2, v3); v0 ^= m;
+        const uint64_t b = 8ull << 56;
+        v3 ^= b; TC_SIPROUND(v0, v1, v2, v3); TC_SIPROUND(v0, v1, v2, v3); v0 ^= b;
+        v2 ^= 0xff;
+        TC_SIPROUND(v0, v1, v2, v3); TC_SIPROUND(v0, v1, v2, v3); TC_SIPROUND(v0, v1, v2, v3); TC_SIPROUND(v0, v1, v2, v3);
+        const uint64_t hsh = v0 ^ v1 ^ v2 ^ v3;
+        const uint32_t h = (uint32_t)(pow2 ? (hsh & (mod - 1)) : (hsh % mod));
+        __nv_bfloat16* row = A1 + i * lda;
+        row[j] = __float2bfloat16_rn((float)((h >> 16) & 255u));
+        row[H + j] = __float2bfloat16_rn((float)((h >> 8) & 255u));
+        row[2 * H + j] = __float2bfloat16_rn((float)(h & 255u));
+    }
+}
+
+// pack fp32 nn.Linear weights into bf16: layer 1 as [65536 W1 | 256 W1 | W1] (power-of-two scaling is exact)
+__global__ void dhe_pack_kernel(const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ w3,
+                                const float* __restrict__ w4, int H, int hid, int D, int K1p,
+                                __nv_bfloat16* __restrict__ p1, __nv_bfloat16* __restrict__ p2,
+                                __nv_bfloat16* __restrict__ p3, __nv_bfloat16* __restrict__ p4) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n1 = (int64_t)hid * K1p, n2 = (int64_t)hid * hid, n4 = (int64_t)D * hid;
+    if (t < n1) {
+        const int o = (int)(t / K1p), kk = (int)(t - (int64_t)o * K1p);
+        float v = 0.f;
+        if (kk < 3 * H) {
+            const int piece = kk / H, j = kk - piece * H;
+            const float wb = __bfloat162float(__float2bfloat16_rn(w1[(int64_t)o * H + j]));
+            v = wb * (piece == 0 ? 65536.f : (piece == 1 ? 256.f : 1.f));
+        }
+        p1[t] = __float2bfloat16_rn(v);
+    }
+    if (t < n2) { p2[t] = __float2bfloat16_rn(w2[t]); p3[t] = __float2bfloat16_rn(w3[t]); }
+    if (t < n4) p4[t] = __float2bfloat16_rn(w4[t]);
+}
+
+struct DhePackedLayout { size_t off[4]; size_t total; int K1p; };
+static DhePackedLayout packed_layout(const oov_dhe_net* net) {
+    DhePackedLayout L;
+    L.K1p = (3 * net->H + 7) / 8 * 8;                   // rows must be 16-byte multiples for TMA
+    size_t o = 0;
+    L.off[0] = o; o += align_up((size_t)net->hidden * L.K1p * 2, 256);
+    L.off[1] = o; o += align_up((size_t)net->hidden * net->hidden * 2, 256);
+    L.off[2] = o; o += align_up((size_t)net->hidden * net->hidden * 2, 256);
+    L.off[3] = o; o += align_up((size_t)net->D * net->hidden * 2, 256);
+    L.total = o;
+    return L;
+}
+
+constexpr int64_t TC_DHE_CHUNK = 1 << 18;
+
+size_t dhe_tc_workspace(int64_t n, const oov_dhe_net* net) {
+    const DhePackedLayout L = packed_layout(net);
+    const int64_t c = n < TC_DHE_CHUNK ? n : TC_DHE_CHUNK;
+    return L.total + align_up((size_t)c * L.K1p * 2, 1024) + 2 * align_up((size_t)c * net->hidden * 2, 1024) + 1024;
+}
+bool dhe_tc_supported(const oov_dhe_net* net, uint64_t mod) {
+    return mod <= (1ull << 24) && net->hidden % 8 == 0 && net->hidden >= 64 && net->D >= 8;
+}
+
+int dhe_tc_pack(const oov_dhe_net* net, void* packed, cudaStream_t st) {
+    const DhePackedLayout L = packed_layout(net);
+    char* p = reinterpret_cast<char*>(packed);
+    const int64_t n1 = (int64_t)net->hidden * L.K1p, n2 = (int64_t)net->hidden * net->hidden, n4 = (int64_t)net->D * net->hidden;
+    int64_t mx = n1 > n2 ? n1 : n2;
+    if (n4 > mx) mx = n4;
+    dhe_pack_kernel<<<(unsigned)cdiv(mx, 256), 256, 0, st>>>(net->w[0], net->w[1], net->w[2], net->w[3], net->H, net->hidden,
+                                                            net->D, L.K1p, (__nv_bfloat16*)(p + L.off[0]),
+                                                            (__nv_bfloat16*)(p + L.off[1]), (__nv_bfloat16*)(p + L.off[2]),
+                                                            (__nv_bfloat16*)(p + L.off[3]));
+    OOV_LAUNCH_CHECK("dhe_pack_kernel");
+    return OOV_OK;
+}
+
+// hash -> 4 tcgen05 linear layers.  `hashes_u32` (optional) replaces the hash step (oov_dhe_mlp).
+int dhe_tc_run(const uint8_t* keys, uint64_t mod, const oov_dhe_net* net, const uint32_t* hashes_u32,
+               const int64_t* ids, int64_t ids_stride, int64_t n, int64_t n_old, const void* iv_table, int iv_dtype,
+               void* out, int out_dtype, int64_t out_stride, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+__global__ void split_u32_kernel(const uint32_t* __restrict__ h, int64_t n, int H, __nv_bfloat16* __restrict__ A1, int64_t lda) {
+    const int64_t total = n * (int64_t)H;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / H;
+        const int j = (int)(t - i * H);
+        const uint32_t v = h[t];
+        __nv_bfloat16* row = A1 + i * lda;
+        row[j] = __float2bfloat16_rn((float)((v >> 16) & 255u));
+        row[H + j] = __float2bfloat16_rn((float)((v >> 8) & 255u));
+        row[2 * H + j] = __float2bfloat16_rn((float)(v & 255u));
+    }
+}
+
+int dhe_tc_run(const uint8_t* keys, uint64_t mod, const oov_dhe_net* net, const uint32_t* hashes_u32,
+               const int64_t* ids, int64_t ids_stride, int64_t n, int64_t n_old, const void* iv_table, int iv_dtype,
+               void* out, int out_dtype, int64_t out_stride, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    const DhePackedLayout L = packed_layout(net);
+    OOV_REQUIRE(workspace && workspace_bytes >= dhe_tc_workspace(n, net), OOV_ERR_WORKSPACE, "dhe (tcgen05): workspace %zu < %zu",
+                workspace_bytes, dhe_tc_workspace(n, net));
+    char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+    char* packed = ws;
+    const int64_t c = n < TC_DHE_CHUNK ? n : TC_DHE_CHUNK;
+    char* a1 = ws + align_up(L.total, 1024);
+    char* act0 = a1 + align_up((size_t)c * L.K1p * 2, 1024);
+    char* act1 = act0 + align_up((size_t)c * net->hidden * 2, 1024);
+    int rc = dhe_tc_pack(net, packed, st);
+    if (rc) return rc;
+    const int hid = net->hidden, H = net->H;
+    const size_t osz = dtype_size(out_dtype);
+    for (int64_t r0 = 0; r0 < n; r0 += c) {
+        const int64_t cn = n - r0 < c ? n - r0 : c;
+        __nv_bfloat16* A1 = reinterpret_cast<__nv_bfloat16*>(a1);
+        if (L.K1p != 3 * H) cudaMemsetAsync(A1, 0, (size_t)cn * L.K1p * 2, st);
+        int64_t blocks = cdiv(cn * (int64_t)H, 256);
+        const int64_t cap = (int64_t)num_sms() * 16;
+        if (blocks > cap) blocks = cap;
+        if (hashes_u32 != nullptr) {
+            split_u32_kernel<<<(unsigned)blocks, 256, 0, st>>>(hashes_u32 + r0 * H, cn, H, A1, L.K1p);
+            OOV_LAUNCH_CHECK("split_u32_kernel");
+        } else {
+            dhe_hash_split_kernel<<<(unsigned)blocks, 256, (size_t)H * 32, st>>>(ids + r0 * ids_stride, ids_stride, cn, keys, H, mod,
+                                                                                A1, L.K1p);
+            OOV_LAUNCH_CHECK("dhe_hash_split_kernel");
+        }
+        LinearEpi e{};
+        e.out_dtype = OOV_BF16; e.act = ACT_GELU; e.ld = hid;
+        e.bias = net->b[0]; e.out = act0;
+        rc = tc_linear(A1, L.K1p, (const __nv_bfloat16*)(packed + L.off[0]), L.K1p, cn, hid, L.K1p, e, st);
+        if (rc) return rc;
+        e.bias = net->b[1]; e.out = act1;
+        rc = tc_linear((const __nv_bfloat16*)act0, hid, (const __nv_bfloat16*)(packed + L.off[1]), hid, cn, hid, hid, e, st);
+        if (rc) return rc;
+        e.bias = net->b[2]; e.out = act0;
+        rc = tc_linear((const __nv_bfloat16*)act1, hid, (const __nv_bfloat16*)(packed + L.off[2]), hid, cn, hid, hid, e, st);
+        if (rc) return rc;
+        LinearEpi f{};
+        f.bias = net->b[3]; f.act = ACT_SIGMOID; f.out_dtype = out_dtype; f.ld = out_stride;
+        f.out = reinterpret_cast<char*>(out) + (size_t)r0 * out_stride * osz;
+        f.ids = ids ? ids + r0 * ids_stride : nullptr; f.ids_stride = ids_stride; f.n_old = n_old;
+        f.iv_table = iv_table; f.iv_dtype = iv_dtype;
+        if (hashes_u32 != nullptr) f.ids = nullptr;
+        rc = tc_linear((const __nv_bfloat16*)act0, hid, (const __nv_bfloat16*)(packed + L.off[3]), hid, cn, net->D, hid, f, st);
+        if (rc) return rc;
+    }
+    return OOV_OK;
+}
+
+}  // namespace tc
+}  // namespace oov
+
+using namespace oov;
+
+extern "C" {
+
+int oov_tc_linear(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int32_t N, int32_t K,
+                  const float* bias, int32_t act, void* out, int32_t out_dtype, int64_t ld_out, void* stream) {
+    OOV_REQUIRE(M >= 0 && N > 0 && K > 0 && lda >= K && ldw >= K && ld_out >= N && dtype_ok(out_dtype) && act >= 0 && act <= 2,
+                OOV_ERR_ARG, "oov_tc_linear: bad argument");
+    OOV_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, OOV_ERR_ALIGN, "oov_tc_linear: lda/ldw must be multiples of 8 elements");
+    if (M == 0) return OOV_OK;
+    OOV_REQUIRE(A && W && out, OOV_ERR_ARG, "oov_tc_linear: NULL pointer");
+    tc::LinearEpi e{};
+    e.bias = bias; e.out = out; e.ld = ld_out; e.out_dtype = out_dtype; e.act = act;
+    return tc::tc_linear((const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)W, ldw, M, N, K, e, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -258,6 +258,23 @@ def dhe_embed(ids, keys: torch.Tensor, net: DheNet, out=None, out_dtype=torch.fl
     return out
 
 
+def tc_linear(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, act: str = "none",
+              out_dtype=torch.float32) -> torch.Tensor:
+    """act(A @ W.T + bias) on the tensor cores: A [M, K], W [N, K] bf16, fp32 accumulate (tcgen05 + TMEM)."""
+    _cuda(A, "A", torch.bfloat16)
+    _cuda(W, "W", torch.bfloat16)
+    _cuda(bias, "bias", torch.float32, allow_none=True)
+    A, W = A.contiguous(), W.contiguous()
+    M, K = A.shape
+    N = W.shape[0]
+    if W.shape[1] != K:
+        raise ValueError("A / W inner dimensions differ")
+    out = torch.empty((M, N), dtype=_torch_dtype(out_dtype), device=A.device)
+    code = {"none": 0, "gelu": 1, "sigmoid": 2}[act]
+    _lib.check(_lib.load().oov_tc_linear(_p(A), K, _p(W), K, M, N, K, _p(bias), code, _p(out), _dt(out), N, _stream()))
+    return out
+
+
 # ------------------------------------------------------------------------------------ mean / zero / gathers
 def col_mean(table: torch.Tensor) -> torch.Tensor:
     """fp32 [D] mean over ALL rows (mean_embedder.py:55-60)."""

@@ -133,10 +133,11 @@ int oov_dhe_embed(const uint8_t* keys, uint64_t mod, const oov_dhe_net* net,
                   int32_t path, void* stream);
 size_t oov_dhe_workspace(int64_t n, const oov_dhe_net* net, int32_t path);
 
-/* Pre-packed weights for the tcgen05 MLP (bf16, K-major tiles).  `packed` must hold
- * oov_dhe_packed_bytes(net) bytes; repack after every weight update. */
-size_t oov_dhe_packed_bytes(const oov_dhe_net* net);
-int oov_dhe_pack(const oov_dhe_net* net, void* packed, void* stream);
+/* One bf16 linear layer on the tensor cores (the building block of the tcgen05 DHE path):
+ * out[M, N] = act(A[M, K] . W[N, K]^T + bias); A, W bf16 row-major (lda, ldw in elements, multiples of 8),
+ * fp32 accumulate in TMEM; act: 0 none, 1 GELU(erf), 2 sigmoid; out fp32 or bf16. */
+int oov_tc_linear(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int32_t N, int32_t K,
+                  const float* bias, int32_t act, void* out, int32_t out_dtype, int64_t ld_out, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * mean / zero — replaces inductive/mean_embedder.py:42-87, zero_embedder.py:36-60.
