@@ -94,8 +94,11 @@ class InductiveEvaluator:
         self.collectors = {name: Collector(config) for name in COLLECTORS}
         self.tot_item_num: Optional[int] = None
         self.item_range = None
-        # collector_filter.py:249-250 shifts new-item positives by -n_old_items while the score columns stay
-        # global; reference_compat=True reproduces that, False compares in global ids.
+        # reference_compat=True reproduces two quirks of collector_filter.py bit for bit:
+        #   * :172-175 picks the masked item segment from `return_old_USERS` (old users -> new items blanked,
+        #     new users -> old items blanked), whatever `return_old_items` says;
+        #   * :249-250 shifts new-item positives by -n_old_items while the score columns stay global.
+        # reference_compat=False masks by `return_old_items` and compares in global ids.
         self.reference_compat = reference_compat
 
     def eval_batch(self, batched_data, item_table: Optional[torch.Tensor] = None):
@@ -115,7 +118,8 @@ class InductiveEvaluator:
         old_user_rows = users < self.n_old_users
         results = {}
         for name, (ru, ri) in COLLECTORS.items():
-            idx = passes["all" if ri is None else ("old" if ri else "new")]
+            keep_old_segment = ru if self.reference_compat else ri
+            idx = passes["all" if ri is None else ("old" if keep_old_segment else "new")]
             pmask = torch.ones_like(positive_u, dtype=torch.bool)
             if ri is not None:
                 pmask &= (positive_i < self.n_old_items) if ri else (positive_i >= self.n_old_items)

@@ -147,11 +147,28 @@ class InductiveGeneralRecommender(nn.Module):
     def build_item_table(self, n_total_items: Optional[int] = None, row_range: Optional[Tuple[int, int]] = None,
                          out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """All-item embedding table `get_item_embedding(arange(N))` (bpr.py:154) in `table_dtype`;
-        `row_range=(lo, hi)` builds one contiguous shard (SURVEY §8e row-sharding)."""
+        `row_range=(lo, hi)` builds one contiguous shard (SURVEY §8e row-sharding).
+
+        The ids are a known contiguous range, so the in-vocab / OOV split at n_items is done on the host
+        (no mask, no sync): rows < n_items are a gather-cast of the table, rows >= n_items go to the
+        embedder with nothing to skip."""
         n_total = self.n_new_items if n_total_items is None else n_total_items
         lo, hi = (0, n_total) if row_range is None else row_range
-        ids = torch.arange(lo, hi, device=self.device, dtype=torch.int64)
-        return self._assemble("item", ids, out=out, out_dtype=self.table_dtype)
+        n = max(hi - lo, 0)
+        if out is None:
+            out = torch.empty((n, self.embedding_size), dtype=self.table_dtype, device=self.device)
+        if self.inductive_mapper is not None or self.inductive_embedder is None or n == 0:
+            ids = torch.arange(lo, hi, device=self.device, dtype=torch.int64)
+            return self._assemble("item", ids, out=out, out_dtype=self.table_dtype)
+        split = min(max(self.n_items, lo), hi)
+        if split > lo:
+            ids_iv = torch.arange(lo, split, device=self.device, dtype=torch.int64)
+            ops.gather_rows(self.item_embedding.weight.detach(), ids_iv, out=out[: split - lo])
+        if hi > split:
+            ids_oov = torch.arange(split, hi, device=self.device, dtype=torch.int64)
+            self.inductive_embedder.assemble_rows("item", ids_oov, self, 0, None, out=out[split - lo:],
+                                                  out_dtype=self.table_dtype)
+        return out
 
     def full_sort_topk(self, interaction, k: int, n_total_items: Optional[int] = None, history_index=None,
                        seg: Tuple[int, int] = (0, INT64_MAX), item_table: Optional[torch.Tensor] = None,

@@ -158,7 +158,8 @@ def test_inductive_evaluator_collectors(name, G):
         assert (got[:, -1] == want[:, -1]).all(), cname          # pos_len column
         # rows whose k-th / (k+1)-th scores are clearly separated inside the collector's item segment
         ru, ri = oov_b200.evaluator.COLLECTORS[cname]
-        seg = o.segment_mask(ora["scores_masked"], case.n_old_items, ri)
+        # collector_filter.py:172-175 selects the blanked segment from return_old_USERS (sic)
+        seg = o.segment_mask(ora["scores_masked"], case.n_old_items, None if ri is None else ru)
         rows = g[f"{key}_rows"] if f"{key}_rows" in g.files else np.arange(case.Q)
         srt = -np.sort(-o.order_key(seg[rows]), axis=1)
         with np.errstate(invalid="ignore"):
