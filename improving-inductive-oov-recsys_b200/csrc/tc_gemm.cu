@@ -55,8 +55,7 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64
 
 // ------------------------------------------------------------------ kernel
 constexpr int BM = 128, BK = 64;
-constexpr int GEMM_THREADS = 384;
-constexpr int EPI_WARP0 = 4, N_EPI_WARPS = 8;
+constexpr int EPI_WARP0 = 4;
 
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_SIGMOID = 2 };
 
@@ -66,6 +65,7 @@ struct LinearEpi {
     int64_t ld;
     int out_dtype;           // OOV_F32 | OOV_BF16
     int act;
+    int debug;               // profiling only: bit 0 = skip global stores, bit 1 = skip the TMEM drain entirely
     // optional assemble contract for the last DHE layer (rows whose id < n_old take the in-vocab row instead)
     const int64_t* ids;
     int64_t ids_stride;
@@ -74,29 +74,57 @@ struct LinearEpi {
     int iv_dtype;
 };
 
-__device__ __forceinline__ float act_apply(float v, int act) {
-    if (act == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
-    if (act == ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32-level):
+// 2 MUFU (rcp, ex2) + ~12 FMA-class ops instead of erff's ~35 — the epilogue of a 512-wide layer is ALU-bound.
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float t = x * 0.70710678118654752440f;
+    const float ax = fabsf(t);
+    float k;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(k) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+    float poly = fmaf(1.061405429f, k, -1.453152027f);
+    poly = fmaf(poly, k, 1.421413741f);
+    poly = fmaf(poly, k, -0.284496736f);
+    poly = fmaf(poly, k, 0.254829592f);
+    poly *= k;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * ax * -1.4426950408889634f));
+    const float erf_abs = fmaf(-poly, e, 1.0f);
+    const float erf_v = copysignf(erf_abs, t);
+    const float hx = 0.5f * x;
+    return fmaf(hx, erf_v, hx);
+}
+template <int ACT> __device__ __forceinline__ float act_apply(float v) {
+    if (ACT == ACT_GELU) return gelu_fast(v);
+    if (ACT == ACT_SIGMOID) return 1.f / (1.f + expf(-v));
     return v;
 }
 
-template <int BN> struct GemmSmem {
+template <int BN, bool FAST> struct GemmSmem {
     static constexpr int A_BYTES = BM * BK * 2;            // 16 KB
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN >= 256) ? 4 : 6;
+    static constexpr int STAGES = FAST ? 3 : ((BN >= 256) ? 4 : 6);
+    static constexpr int NEPI = FAST ? 16 : 8;             // epilogue warps
+    static constexpr int THREADS = (EPI_WARP0 + NEPI) * 32;
+    static constexpr int STAGING_BYTES = FAST ? NEPI * 32 * 128 : 0;   // per warp: 32 rows x 64 bf16, XOR-swizzled
+    static constexpr int BIAS_BYTES = FAST ? 4096 : 0;                 // N <= 1024 floats
     static constexpr int BAR_BYTES = 256;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + alignment slack
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// FAST = bf16 output, N % 64 == 0, N <= 1024, no assemble: 16 epilogue warps (lane quarter x column quarter), both
+// tcgen05.ld of the warp's 64 columns in flight together, TMEM released as soon as they land, bias from smem,
+// results staged through XOR-swizzled smem so every global store instruction writes four full 128-byte lines.
+template <int BN, int ACT, bool FAST>
+__global__ void __launch_bounds__(GemmSmem<BN, FAST>::THREADS, 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  int64_t M, int N, int K, LinearEpi epi) {
-    using S = GemmSmem<BN>;
+    using S = GemmSmem<BN, FAST>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
+    unsigned char* staging = smem + S::STAGES * S::STAGE_BYTES;
+    float* bias_s = reinterpret_cast<float*>(staging + S::STAGING_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + S::STAGING_BYTES + S::BIAS_BYTES);
     uint64_t* empty_bar = full_bar + S::STAGES;
     uint64_t* tmem_full = empty_bar + S::STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -115,10 +143,13 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < S::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], N_EPI_WARPS); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], S::NEPI); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (FAST) {
+        for (int i = threadIdx.x; i < N; i += S::THREADS) bias_s[i] = epi.bias ? __ldg(epi.bias + i) : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -169,76 +200,140 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue =====================
         const int q = warp & 3;                         // TMEM lane quarter this warp may access
-        const int half = (warp - EPI_WARP0) >> 2;       // column half handled by this warp
-        constexpr int COLS_PER_HALF = BN / 2;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int64_t mt = t / n_tiles; const int nt = (int)(t - mt * n_tiles);
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tc_fence_after();
-            const int64_t row = mt * BM + q * 32 + lane;
-            const bool row_ok = row < M;
-            bool take_iv = false;
-            int64_t id = 0;
-            if (epi.ids != nullptr && row_ok) {
-                id = epi.ids[row * epi.ids_stride];
-                take_iv = id < epi.n_old;
+        if (FAST) {
+            const int cq = (warp - EPI_WARP0) >> 2;     // column quarter: 64 of the tile's 256 columns
+            unsigned char* stg = staging + (warp - EPI_WARP0) * (32 * 128);
+            for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int64_t mt = t / n_tiles; const int nt = (int)(t - mt * n_tiles);
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cq * 64);
+                uint32_t v0[32], v1[32];
+                if (!(epi.debug & 2)) {
+                    tc_ld_32x32(taddr, v0);
+                    tc_ld_32x32(taddr + 32, v1);
+                    tc_wait_ld();
+                }
+                // accumulator is in registers: hand the TMEM stage back to the MMA warp right away
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                const int col0 = nt * BN + cq * 64;
+                if (col0 >= N || (epi.debug & 2)) continue;         // warp-uniform
+                // two halves of 32 columns: activation -> bf16 pairs -> staging row `lane`
+                // (16-byte chunk c of the row lives at physical chunk c ^ (row & 7): conflict-free both ways)
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float2 b = *reinterpret_cast<const float2*>(bias_s + col0 + hf * 32 + 2 * j);
+                        const uint32_t r0 = hf ? v1[2 * j] : v0[2 * j], r1 = hf ? v1[2 * j + 1] : v0[2 * j + 1];
+                        const float x0 = act_apply<ACT>(__uint_as_float(r0) + b.x);
+                        const float x1 = act_apply<ACT>(__uint_as_float(r1) + b.y);
+                        __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                        pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                    if (epi.debug & 1) {
+                        uint32_t x = 0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) x ^= pk[j];
+                        if (x == 0x12345678u) reinterpret_cast<uint32_t*>(epi.out)[0] = x;
+                        continue;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        *reinterpret_cast<uint4*>(stg + lane * 128 + (((hf * 4 + c) ^ (lane & 7)) << 4)) =
+                            make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                }
+                if (epi.debug & 1) continue;
+                __syncwarp();
+                const int64_t row_base = mt * BM + q * 32;
+                __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(epi.out) + col0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {                    // 4 rows x 128 B per instruction
+                    const int r = i * 4 + (lane >> 3), c = lane & 7;
+                    const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 128 + ((c ^ (r & 7)) << 4));
+                    if (row_base + r < M)
+                        *reinterpret_cast<uint4*>(obase + (row_base + r) * epi.ld + c * 8) = val;
+                }
+                __syncwarp();
             }
+        } else {
+            const int half = (warp - EPI_WARP0) >> 2;       // column half handled by this warp
+            constexpr int COLS_PER_HALF = BN / 2;
+            for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int64_t mt = t / n_tiles; const int nt = (int)(t - mt * n_tiles);
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                const int64_t row = mt * BM + q * 32 + lane;
+                const bool row_ok = row < M;
+                bool take_iv = false;
+                int64_t id = 0;
+                if (epi.ids != nullptr && row_ok) {
+                    id = epi.ids[row * epi.ids_stride];
+                    take_iv = id < epi.n_old;
+                }
 #pragma unroll 1
-            for (int c0 = 0; c0 < COLS_PER_HALF; c0 += 32) {
-                const int col_in_tile = half * COLS_PER_HALF + c0;
-                uint32_t v[32];
-                tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + col_in_tile), v);
-                tc_wait_ld();
-                const int col0 = nt * BN + col_in_tile;
-                if (!row_ok || col0 >= N) continue;
-                float f[32];
+                for (int c0 = 0; c0 < COLS_PER_HALF; c0 += 32) {
+                    if (epi.debug & 2) break;
+                    const int col_in_tile = half * COLS_PER_HALF + c0;
+                    uint32_t v[32];
+                    tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + col_in_tile), v);
+                    tc_wait_ld();
+                    const int col0 = nt * BN + col_in_tile;
+                    if (!row_ok || col0 >= N) continue;
+                    float f[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(v[j]);
-                    if (epi.bias != nullptr && col0 + j < N) x += __ldg(epi.bias + col0 + j);
-                    f[j] = act_apply(x, epi.act);
-                }
-                if (take_iv) {
-                    if (epi.iv_table == nullptr || id < 0) continue;
+                    for (int j = 0; j < 32; ++j) {
+                        float x = __uint_as_float(v[j]);
+                        if (epi.bias != nullptr && col0 + j < N) x += __ldg(epi.bias + col0 + j);
+                        f[j] = act_apply<ACT>(x);
+                    }
+                    if (epi.debug & 1) continue;
+                    if (take_iv) {
+                        if (epi.iv_table == nullptr || id < 0) continue;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < N) f[j] = load_elem(epi.iv_table, epi.iv_dtype, id * (int64_t)N + col0 + j);
-                }
-                if (epi.out_dtype == OOV_BF16) {
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(epi.out) + row * epi.ld + col0;
-                    if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-                        uint32_t pk[16];
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < N) f[j] = load_elem(epi.iv_table, epi.iv_dtype, id * (int64_t)N + col0 + j);
+                    }
+                    if (epi.out_dtype == OOV_BF16) {
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(epi.out) + row * epi.ld + col0;
+                        if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                            uint32_t pk[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                            pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                            for (int j = 0; j < 16; ++j) {
+                                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                reinterpret_cast<uint4*>(o)[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < N) o[j] = __float2bfloat16_rn(f[j]);
                         }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            reinterpret_cast<uint4*>(o)[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
                     } else {
+                        float* o = reinterpret_cast<float*>(epi.out) + row * epi.ld + col0;
+                        if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < N) o[j] = __float2bfloat16_rn(f[j]);
-                    }
-                } else {
-                    float* o = reinterpret_cast<float*>(epi.out) + row * epi.ld + col0;
-                    if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                            for (int j = 0; j < 8; ++j)
+                                reinterpret_cast<float4*>(o)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            reinterpret_cast<float4*>(o)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < N) o[j] = f[j];
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < N) o[j] = f[j];
+                        }
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
@@ -250,10 +345,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
-template <int BN>
+template <int BN, int ACT, bool FAST>
 static int launch_linear(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, int64_t M, int N, int K,
                          const LinearEpi& epi, cudaStream_t st) {
-    using S = GemmSmem<BN>;
+    using S = GemmSmem<BN, FAST>;
     CUtensorMap tmA, tmB;
     int rc = make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BM);
     if (rc) return rc;
@@ -261,22 +356,33 @@ static int launch_linear(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat1
     if (rc) return rc;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<BN, ACT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         OOV_REQUIRE(e == cudaSuccess, OOV_ERR_CUDA, "cudaFuncSetAttribute(tc_linear_kernel): %s", cudaGetErrorString(e));
         attr_done = true;
     }
     const int64_t tiles = cdiv(M, BM) * cdiv(N, BN);
     const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-    tc_linear_kernel<BN><<<grid, GEMM_THREADS, S::TOTAL, st>>>(tmA, tmB, M, N, K, epi);
+    tc_linear_kernel<BN, ACT, FAST><<<grid, S::THREADS, S::TOTAL, st>>>(tmA, tmB, M, N, K, epi);
     OOV_LAUNCH_CHECK("tc_linear_kernel");
     return OOV_OK;
+}
+
+template <int ACT>
+static int tc_linear_act(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, int64_t M, int N, int K,
+                         const LinearEpi& epi, cudaStream_t st) {
+    const bool fast = epi.out_dtype == OOV_BF16 && N > 64 && N % 64 == 0 && N <= 1024 && epi.ids == nullptr &&
+                      epi.ld % 8 == 0 && aligned(epi.out, 16);
+    if (fast) return launch_linear<256, ACT, true>(A, lda, W, ldw, M, N, K, epi, st);
+    if (N > 64) return launch_linear<256, ACT, false>(A, lda, W, ldw, M, N, K, epi, st);
+    return launch_linear<64, ACT, false>(A, lda, W, ldw, M, N, K, epi, st);
 }
 
 int tc_linear(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, int64_t M, int N, int K,
               const LinearEpi& epi, cudaStream_t st) {
     if (M == 0) return OOV_OK;
-    if (N > 64) return launch_linear<256>(A, lda, W, ldw, M, N, K, epi, st);
-    return launch_linear<64>(A, lda, W, ldw, M, N, K, epi, st);
+    if (epi.act == ACT_GELU) return tc_linear_act<ACT_GELU>(A, lda, W, ldw, M, N, K, epi, st);
+    if (epi.act == ACT_SIGMOID) return tc_linear_act<ACT_SIGMOID>(A, lda, W, ldw, M, N, K, epi, st);
+    return tc_linear_act<ACT_NONE>(A, lda, W, ldw, M, N, K, epi, st);
 }
 
 // ------------------------------------------------------------------ DHE on tensor cores
@@ -465,13 +571,15 @@ extern "C" {
 
 int oov_tc_linear(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int32_t N, int32_t K,
                   const float* bias, int32_t act, void* out, int32_t out_dtype, int64_t ld_out, void* stream) {
+    const int debug = act >> 8;      // undocumented profiling bits (see LinearEpi::debug)
+    act &= 0xff;
     OOV_REQUIRE(M >= 0 && N > 0 && K > 0 && lda >= K && ldw >= K && ld_out >= N && dtype_ok(out_dtype) && act >= 0 && act <= 2,
                 OOV_ERR_ARG, "oov_tc_linear: bad argument");
     OOV_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, OOV_ERR_ALIGN, "oov_tc_linear: lda/ldw must be multiples of 8 elements");
     if (M == 0) return OOV_OK;
     OOV_REQUIRE(A && W && out, OOV_ERR_ARG, "oov_tc_linear: NULL pointer");
     tc::LinearEpi e{};
-    e.bias = bias; e.out = out; e.ld = ld_out; e.out_dtype = out_dtype; e.act = act;
+    e.bias = bias; e.out = out; e.ld = ld_out; e.out_dtype = out_dtype; e.act = act; e.debug = debug;
     return tc::tc_linear((const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)W, ldw, M, N, K, e, (cudaStream_t)stream);
 }
 

@@ -443,6 +443,25 @@ static int launch_fullsort_simt(const T* users, const T* items, int64_t Q, int64
     return OOV_OK;
 }
 
+// shared with the tcgen05 scoring kernel (tc_score.cu): merge P partial key lists per user
+int launch_merge_keys(const unsigned long long* partial, int P, int64_t Q, int k, int64_t off, float* out_scores,
+                      int64_t* out_idx, cudaStream_t st) {
+    const unsigned blocks = (unsigned)cdiv(Q * 32, 256);
+    if (k <= 32) merge_keys_kernel<1><<<blocks, 256, 0, st>>>(partial, P, Q, k, off, out_scores, out_idx);
+    else if (k <= 64) merge_keys_kernel<2><<<blocks, 256, 0, st>>>(partial, P, Q, k, off, out_scores, out_idx);
+    else merge_keys_kernel<4><<<blocks, 256, 0, st>>>(partial, P, Q, k, off, out_scores, out_idx);
+    OOV_LAUNCH_CHECK("merge_keys_kernel");
+    return OOV_OK;
+}
+
+namespace tc {
+bool score_tc_supported(int dtype, int D, int k);
+size_t score_tc_workspace(int64_t Q, int64_t N, int k);
+int score_tc_run(const void* users, const void* items, int64_t Q, int64_t N, int D, int k, int64_t item_id_offset,
+                 int mask_pad, int64_t seg_lo, int64_t seg_hi, const int32_t* hist_rowptr, const int32_t* hist_cols,
+                 float* out_scores, int64_t* out_idx, void* workspace, size_t workspace_bytes, cudaStream_t st);
+}  // namespace tc
+
 }  // namespace oov
 
 using namespace oov;
@@ -450,11 +469,15 @@ using namespace oov;
 extern "C" {
 
 size_t oov_fullsort_topk_workspace(int64_t Q, int64_t N, int32_t D, int32_t k, int32_t path) {
-    (void)D; (void)path;
     if (Q <= 0 || N <= 0 || k <= 0) return 0;
     const TopkCfg c = topk_cfg(k);
     const int P = pick_item_ctas(N, cdiv(Q, c.TQ));
-    return align_up((size_t)P * Q * k * 8, 256);
+    size_t a = align_up((size_t)P * Q * k * 8, 256);
+    if (path != OOV_PATH_SIMT_FP32 && tc::score_tc_supported(OOV_BF16, D, k)) {
+        const size_t b = tc::score_tc_workspace(Q, N, k);
+        if (b > a) a = b;
+    }
+    return a;
 }
 
 int oov_fullsort_topk(const void* users, const void* items, int32_t dtype, int64_t Q, int64_t N, int32_t D, int32_t k,
@@ -467,10 +490,17 @@ int oov_fullsort_topk(const void* users, const void* items, int32_t dtype, int64
     OOV_REQUIRE(N < (1ll << 32), OOV_ERR_ARG, "oov_fullsort_topk: shard has %lld rows (max 2^32-1)", (long long)N);
     OOV_REQUIRE(D % 16 == 0, OOV_ERR_ARG, "oov_fullsort_topk: D=%d must be a multiple of 16 (pad the tables)", D);
     OOV_REQUIRE((hist_rowptr == nullptr) == (hist_cols == nullptr), OOV_ERR_ARG, "oov_fullsort_topk: rowptr/cols mismatch");
-    OOV_REQUIRE(path == OOV_PATH_AUTO || path == OOV_PATH_SIMT_FP32, OOV_ERR_ARG, "oov_fullsort_topk: unsupported path %d", path);
+    OOV_REQUIRE(path >= OOV_PATH_AUTO && path <= OOV_PATH_TCGEN05, OOV_ERR_ARG, "oov_fullsort_topk: unsupported path %d", path);
     if (Q == 0) return OOV_OK;
     OOV_REQUIRE(users && out_scores && out_idx && (N == 0 || items), OOV_ERR_ARG, "oov_fullsort_topk: NULL pointer");
     OOV_REQUIRE(aligned(users, 16) && aligned(items, 16), OOV_ERR_ALIGN, "oov_fullsort_topk: tables must be 16-byte aligned");
+    // bf16 tables take the tensor-core path (tcgen05 GEMM fused with the top-k epilogue); fp32 tables the fp32 FMA path
+    const bool tc_ok = tc::score_tc_supported(dtype, D, k) && N >= 1;
+    OOV_REQUIRE(path != OOV_PATH_TCGEN05 || tc_ok, OOV_ERR_ARG,
+                "oov_fullsort_topk: tcgen05 path needs bf16 tables, D <= 64 (multiple of 8) and k <= 32");
+    if (tc_ok && path != OOV_PATH_SIMT_FP32)
+        return tc::score_tc_run(users, items, Q, N, D, k, item_id_offset, mask_pad, seg_lo, seg_hi, hist_rowptr, hist_cols,
+                                out_scores, out_idx, workspace, workspace_bytes, (cudaStream_t)stream);
     const TopkCfg c = topk_cfg(k);
     const int P = pick_item_ctas(N > 0 ? N : 1, cdiv(Q, c.TQ));
     const size_t need = (size_t)P * Q * k * 8;

@@ -259,7 +259,7 @@ def dhe_embed(ids, keys: torch.Tensor, net: DheNet, out=None, out_dtype=torch.fl
 
 
 def tc_linear(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, act: str = "none",
-              out_dtype=torch.float32) -> torch.Tensor:
+              out_dtype=torch.float32, _debug: int = 0) -> torch.Tensor:
     """act(A @ W.T + bias) on the tensor cores: A [M, K], W [N, K] bf16, fp32 accumulate (tcgen05 + TMEM)."""
     _cuda(A, "A", torch.bfloat16)
     _cuda(W, "W", torch.bfloat16)
@@ -270,7 +270,7 @@ def tc_linear(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = N
     if W.shape[1] != K:
         raise ValueError("A / W inner dimensions differ")
     out = torch.empty((M, N), dtype=_torch_dtype(out_dtype), device=A.device)
-    code = {"none": 0, "gelu": 1, "sigmoid": 2}[act]
+    code = {"none": 0, "gelu": 1, "sigmoid": 2}[act] | (_debug << 8)
     _lib.check(_lib.load().oov_tc_linear(_p(A), K, _p(W), K, M, N, K, _p(bias), code, _p(out), _dt(out), N, _stream()))
     return out
 

@@ -124,3 +124,93 @@ def test_dhe_tc_large_matches_simt(tmp_path):
     torch.cuda.synchronize()
     assert (a - b).abs().max().item() < 5e-3
     assert (a - b).abs().mean().item() < 5e-4
+
+
+# ------------------------------------------------------------------------------------------------ fused tcgen05 score + top-k
+def _ref_scores(users, items, off, hist, seg, mask_pad=True):
+    s = (users.float() @ items.float().T).cpu().numpy()
+    n = s.shape[1]
+    gid = np.arange(n) + off
+    if mask_pad:
+        s[:, gid == 0] = -np.inf
+    s[:, (gid < seg[0]) | (gid >= seg[1])] = -np.inf
+    if hist is not None:
+        hu, hi = hist
+        loc = hi - off
+        ok = (loc >= 0) & (loc < n)
+        s[hu[ok], loc[ok]] = -np.inf
+    return s
+
+
+@pytest.mark.parametrize("Q,N,D,k", [(1, 50, 64, 5), (100, 257, 64, 20), (256, 5000, 64, 20), (300, 5000, 16, 32),
+                                     (1024, 70_001, 64, 20), (129, 1024, 32, 1), (64, 200_003, 64, 10)])
+def test_tc_score_topk_vs_fp32_reference(Q, N, D, k):
+    from oov_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(Q + N + D + k)
+    users = torch.randn(Q, D, generator=g).to(torch.bfloat16).to(DEV)
+    items = torch.randn(N, D, generator=g).to(torch.bfloat16).to(DEV)
+    if N > 40:
+        items[10:20] = items[30:40]                        # exact score ties -> (score desc, id asc) must hold
+    hu = torch.randint(0, Q, (min(5 * Q, 3000),), generator=g)
+    hi = torch.randint(0, N, (hu.numel(),), generator=g) + 1000
+    off = 1000
+    hist = ops.pairs_to_csr(hu.to(DEV), hi.to(DEV), Q)
+    for seg in ((0, 1 << 62), (off + N // 3, off + 2 * N // 3)):
+        s_tc, i_tc = ops.fullsort_topk(users, items, k, item_id_offset=off, hist=hist, seg=seg, path=ops.PATH_TCGEN05)
+        s_si, i_si = ops.fullsort_topk(users, items, k, item_id_offset=off, hist=hist, seg=seg, path=ops.PATH_SIMT_FP32)
+        torch.cuda.synchronize()
+        ref = _ref_scores(users, items, off, (hu.numpy(), hi.numpy()), seg)
+        scale = float(np.abs(ref[np.isfinite(ref)]).max())
+        for nm, s_, i_ in (("tcgen05", s_tc, i_tc), ("simt", s_si, i_si)):
+            idx = i_.cpu().numpy() - off
+            kk = min(k, N)
+            ok, msg = o.topk_sets_match(ref, idx[:, :kk], kk, rtol=1e-5, atol=1e-5 * scale)
+            assert ok, f"{nm} seg={seg}: {msg}"
+            picked = np.take_along_axis(ref, idx[:, :kk], axis=1)
+            pu.assert_close(s_.cpu().numpy()[:, :kk], picked, rtol=1e-5, atol=1e-5 * scale, what=f"{nm} scores")
+            if kk < k:
+                assert (idx[:, kk:] == -1 - off).all()
+            key = o.order_key(s_.cpu().numpy())
+            assert (key[:, :-1] >= key[:, 1:]).all(), nm
+            tie = key[:, :-1] == key[:, 1:]
+            assert (i_.cpu().numpy()[:, :-1][tie] < i_.cpu().numpy()[:, 1:][tie]).all(), nm
+
+
+def test_tc_score_nan_rows_rank_first():
+    """An all-zero LSH multi-hot row gives a NaN item embedding (lsh_embedder.py:158); torch.topk ranks NaN first."""
+    from oov_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(1)
+    users = torch.randn(40, 64, generator=g).to(torch.bfloat16).to(DEV)
+    items = torch.randn(3000, 64, generator=g).to(torch.bfloat16).to(DEV)
+    items[[5, 700, 2999]] = float("nan")
+    s, i = ops.fullsort_topk(users, items, 5, mask_pad=False, path=ops.PATH_TCGEN05)
+    assert (i[:, :3].cpu() == torch.tensor([5, 700, 2999])).all()
+    assert torch.isnan(s[:, :3]).all() and not torch.isnan(s[:, 3:]).any()
+
+
+def test_tc_score_shard_merge_equals_global():
+    """Row-sharding property on the tensor-core path at a larger size (the multi-GPU data path, emulated as
+    independent launches on one GPU): merge of per-shard top-ks == top-k over the whole table, bit for bit."""
+    from oov_b200 import ops
+    torch.manual_seed(0)
+    Q, N, D, k = 512, 1_000_003, 64, 20
+    users = torch.randn(Q, D, device=DEV).to(torch.bfloat16)
+    items = torch.randn(N, D, device=DEV).to(torch.bfloat16)
+    items[1000:1010] = items[900_000:900_010]
+    hu = torch.randint(0, Q, (20_000,), device=DEV)
+    hi = torch.randint(1, N, (20_000,), device=DEV)
+    hist = ops.pairs_to_csr(hu, hi, Q)
+    s_all, i_all = ops.fullsort_topk(users, items, k, hist=hist)
+    bounds = [0, 250_000, 250_001, 777_777, N]
+    cs, ci = [], []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        s, i = ops.fullsort_topk(users, items[a:b], k, item_id_offset=a, hist=hist)
+        cs.append(s)
+        ci.append(i)
+    ms, mi = ops.topk_merge(torch.stack(cs), torch.stack(ci))
+    assert torch.equal(mi, i_all) and torch.equal(ms, s_all)
+    ref = users.float() @ items.float().T
+    ref[:, 0] = -float("inf")
+    ref[hu, hi] = -float("inf")
+    ok, msg = o.topk_sets_match(ref.cpu().numpy(), i_all.cpu().numpy(), k, rtol=1e-5, atol=1e-4)
+    assert ok, msg
