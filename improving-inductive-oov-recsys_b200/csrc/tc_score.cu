@@ -2,22 +2,31 @@
 //
 // Replaces bpr.py:151-156 / directau.py:193-198 (score = user_e @ all_item_e.T), inductive/evaluator.py:91-94
 // (pad + history -> -inf) and evaluator/collector.py:153-159 (torch.topk) in ONE kernel: the [Q, N] score matrix
-// only ever exists as 128 x 256 fp32 tiles in TMEM.
+// only ever exists as 128 x 128 fp32 tiles in TMEM.
 //
-// grid = (item CTAs, user groups of 256).  Per CTA (384 threads):
-//   warp 0      TMA producer : the group's two 128-user tiles once (A, resident), then 256-item tiles (B) through
-//                              a 3-stage mbarrier ring — K-major, 128B-swizzled, straight from the bf16 tables
-//   warp 1      MMA issuer   : per item tile, 4 x tcgen05.mma (M 128, N 256, K 16) per user tile -> accumulator
-//                              `ut` (TMEM columns ut*256 ..), then releases the smem slot
-//   warp 2      TMEM alloc (512 columns)
-//   warps 4-7   epilogue of user tile 0, warps 8-11 of user tile 1: thread = one user (TMEM lane); per 32-column
-//               tcgen05.ld it takes a NaN-propagating 3-input max tree and compares ONCE with the user's running
-//               k-th best; only chunks that beat it are scanned, masked (pad / segment / history probe) and
-//               inserted into the user's sorted list (smem, thread-private column) -> epilogue cost ~1 instr/score.
-// While one user tile's accumulator is being drained the tensor core fills the other one.
+// grid = (item ranges, user groups of 512).  Every CTA owns a CONTIGUOUS range of 128-item tiles.  608 threads:
+//   warp 0       TMA producer : the group's four 128-user tiles once (A, resident), then 128-item tiles (B) through
+//                               an mbarrier ring — K-major, 128B-swizzled, straight from the bf16 tables
+//   warp 1       MMA issuer   : per item tile and user tile `ut`, 4 x tcgen05.mma (M 128, N 128, K 16) into
+//                               accumulator `ut` (TMEM columns ut*128 ..); the tensor core works on the other
+//                               three user tiles while one is being drained
+//   warp 2       TMEM alloc (512 columns)
+//   warps 3-18   epilogue     : thread = one user (TMEM lane).  Per 32-column tcgen05.ld (double-buffered in
+//                               registers) a NaN-propagating 3-input max tree is compared ONCE with the user's
+//                               threshold; only groups that beat it are scanned, masked (pad / segment / history)
+//                               and inserted into the user's sorted list (smem, thread-private column).
+// Threshold sharing: a user is scored by P = gridDim.x CTAs ("streams"), and a short stream's own k-th best is a
+// weak filter.  Every stream publishes its j-th best score (j = ceil(k / G), G = min(P, k)) with a plain store;
+// the streams are dealt into G groups and T = min over groups of (max over the group's streams of the published
+// value) has at least G * j >= k distinct scores at or above it, so dropping scores strictly below T is exact.
+// Threads refresh T on a doubling schedule (after tiles 1, 2, 4, 8, ...): total candidates per user stay near
+// k' ln(N) for the whole grid instead of P k ln(N / P).
+// History: items are visited in increasing id order, so each thread walks its user's sorted CSR history with a
+// cursor (one register holds the next masked id) instead of searching.
 // Every CTA writes its per-user lists as key64 = (ordered score << 32 | ~local_row); merge_keys_kernel (topk.cu)
 // reduces the per-CTA lists to the final (score desc, id asc) top-k.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -30,13 +39,17 @@ int launch_merge_keys(const unsigned long long* partial, int P, int64_t Q, int k
 namespace tc {
 
 constexpr int SC_BM = 128;            // users per MMA (TMEM lanes)
-constexpr int SC_BN = 256;            // items per tile (TMEM columns per accumulator)
-constexpr int SC_UG = 256;            // users per CTA (two accumulators)
-constexpr int SC_STAGES = 3;
-constexpr int SC_THREADS = 384;
-constexpr int SC_KMAX = 32;
+constexpr int SC_BN = 128;            // items per tile (TMEM columns per accumulator)
+constexpr int SC_NUT = 4;             // user tiles (accumulators) per CTA
+constexpr int SC_UG = SC_BM * SC_NUT; // users per CTA
+constexpr int SC_MAX_STAGES = 6;
+constexpr int SC_EPI_WARP0 = 3;
+constexpr int SC_THREADS = (SC_EPI_WARP0 + 4 * SC_NUT) * 32;   // 608
+constexpr int SC_KMAX = 24;              // smem: lists k x 512 x 8 B next to A (64 KB), the queues (32 KB) and >= 2 B stages
+constexpr int SC_QCAP = 8;               // queued candidates per user between drains
 constexpr int SC_A_BYTES = SC_BM * 128;               // one 128-user tile, 64 bf16 (128 B) per row
 constexpr int SC_B_BYTES = SC_BN * 128;
+constexpr int SC_SMEM_MAX = 232448;                   // 227 KB opt-in limit
 
 __device__ __forceinline__ float max3_nan(float a, float b, float c) {
     float r;
@@ -49,51 +62,174 @@ __device__ __forceinline__ float max2_nan(float a, float b) {
     return r;
 }
 
-__device__ __forceinline__ bool hist_has(const int32_t* __restrict__ cols, int lo, int hi, int64_t gid) {
-    int l = lo, h = hi;
-    while (l < h) {
-        const int mid = (l + h) >> 1;
-        if ((int64_t)cols[mid] < gid) l = mid + 1; else h = mid;
-    }
-    return l < hi && (int64_t)cols[l] == gid;
-}
-
 struct ScoreParams {
     int64_t Q, N;
-    int k;
+    int k, stages;
     int64_t item_id_offset;
     int mask_pad;
     int64_t seg_lo, seg_hi;             // global ids kept; everything else scores -inf
     const int32_t* hist_rowptr;
-    const int32_t* hist_cols;
+    const int32_t* hist_cols;           // sorted per user
     int64_t tile_begin, tile_end;       // item tiles (of SC_BN local rows) that intersect the kept segment
+    uint32_t* pub;                      // [Q][gridDim.x] j-th best score of each stream (ordered-float key; 0 = none yet)
+    int pub_j, pub_groups;              // j (1..3, or k when P is too small) and G of the threshold-sharing scheme
+    int debug;                          // profiling only (OOV_SCORE_DEBUG): bit 0 = no candidate processing, bit 1 = no threshold sharing
     unsigned long long* partial;        // [gridDim.x][Q][k]
 };
 
+// per-thread (= per-user) epilogue state
+struct UserState {
+    unsigned long long* L;              // list column (UNSORTED): entry e at L[e * SC_UG]; 0 = empty slot
+    unsigned long long* Qe;             // candidate queue column: entry i at Qe[i * SC_UG] = (score bits << 32 | local row)
+    unsigned long long thr_key;         // smallest key of the list (0 while it has an empty slot)
+    float thr_f;                        // score filter: scores strictly below cannot enter the final top-k
+    int min_pos;                        // slot holding thr_key
+    int cnt;                            // queued candidates
+    uint32_t b1, b2, b3;                // three best score keys this stream has seen (b1 >= b2 >= b3)
+    int hpos, hend;                     // history cursor
+    int64_t next_h;                     // next masked global id (INT64_MAX when exhausted)
+    int n_push, n_ins, n_steps;         // profiling counters (OOV_SCORE_DEBUG bit 2)
+};
+
+// replace the smallest list entry with `key` (> thr_key) and find the new smallest: k independent smem loads, no
+// data-dependent branches, so the lanes of a warp (32 users) insert together
+__device__ __forceinline__ void list_insert(const ScoreParams& p, UserState& u, unsigned long long key) {
+    u.L[u.min_pos * SC_UG] = key;
+    ++u.n_ins;
+    const uint32_t hi = (uint32_t)(key >> 32);
+    if (hi > u.b1) { u.b3 = u.b2; u.b2 = u.b1; u.b1 = hi; }
+    else if (hi > u.b2) { u.b3 = u.b2; u.b2 = hi; }
+    else if (hi > u.b3) u.b3 = hi;
+    unsigned long long mn = ~0ull;
+    int pos = 0;
+    const int k = p.k;
+#pragma unroll 4
+    for (int e = 0; e < k; ++e) {
+        const unsigned long long x = u.L[e * SC_UG];
+        if (x < mn) { mn = x; pos = e; }
+    }
+    u.thr_key = mn;
+    u.min_pos = pos;
+    if (mn) u.thr_f = fmaxf(u.thr_f, key64_score(mn));            // a NaN k-th score leaves the filter unchanged
+}
+
+// masks (pad / segment / history cursor) + list insertion of one queued candidate
+__device__ __forceinline__ void consider(const ScoreParams& p, UserState& u, float s, uint32_t li) {
+    if (li >= (uint32_t)p.N) return;                              // zero-filled rows past the end of the shard
+    const int64_t gid = (int64_t)li + p.item_id_offset;
+    while (u.next_h < gid) {                                      // ids arrive in increasing order
+        ++u.hpos;
+        u.next_h = u.hpos < u.hend ? (int64_t)p.hist_cols[u.hpos] : INT64_MAX;
+    }
+    if (u.next_h == gid || (p.mask_pad && gid == 0) || gid < p.seg_lo || gid >= p.seg_hi) s = -INFINITY;
+    const unsigned long long key = make_key64(s, li);
+    if (key > u.thr_key) list_insert(p, u, key);
+}
+
+// all 32 lanes together: every user works through its own queue
+__device__ __forceinline__ void drain(const ScoreParams& p, UserState& u) {
+    const int n = u.cnt;
+    u.n_steps += __reduce_max_sync(0xffffffffu, n);
+    for (int i = 0; i < n; ++i) {
+        const unsigned long long ent = u.Qe[i * SC_UG];
+        consider(p, u, __uint_as_float((uint32_t)(ent >> 32)), (uint32_t)ent);
+    }
+    u.cnt = 0;
+}
+
+// Threshold sharing, one warp for its 32 users: lane l reads the values published by streams l, l + 32, ... of one
+// user ([Q][P] layout, coalesced), so lane = group; T = min over the G groups of the group's best published j-th
+// score (0 while some group has published nothing).  pub_groups == 1: plain max of the published k-th bests.
+__device__ __forceinline__ uint32_t shared_threshold(const ScoreParams& p, int64_t user0, int P, int lane) {
+    uint32_t mine = 0u;
+    const int G = p.pub_groups;
+#pragma unroll 4
+    for (int uu = 0; uu < 32; ++uu) {
+        const int64_t user = user0 + uu;
+        if (user >= p.Q) break;                                   // warp-uniform
+        uint32_t v = 0u;
+        for (int s = lane; s < P; s += 32) {
+            const uint32_t x = __ldcg(p.pub + (size_t)user * P + s);
+            v = x > v ? x : v;
+        }
+        uint32_t T;
+        if (G == 1) T = __reduce_max_sync(0xffffffffu, v);
+        else T = __reduce_min_sync(0xffffffffu, lane < G ? v : 0xFFFFFFFFu);
+        if (lane == uu) mine = T;
+    }
+    return mine;
+}
+
+// one 32-column chunk of one user's scores (registers v[0..31]); `col0` = local item row of column 0.
+// Called by all 32 lanes together (warp votes inside).  Candidates are queued; the queue is drained here only when
+// some lane ran out of space (then the chunk is scanned again for what is left), else at the end of the tile.
+__device__ __forceinline__ void process_chunk(const ScoreParams& p, UserState& u, const uint32_t (&v)[32], uint32_t col0) {
+    float m[11];
+#pragma unroll
+    for (int j = 0; j < 10; ++j)
+        m[j] = max3_nan(__uint_as_float(v[3 * j]), __uint_as_float(v[3 * j + 1]), __uint_as_float(v[3 * j + 2]));
+    m[10] = max2_nan(__uint_as_float(v[30]), __uint_as_float(v[31]));
+    const float m0 = max3_nan(m[0], m[1], m[2]), m1 = max3_nan(m[3], m[4], m[5]);
+    const float m2 = max3_nan(m[6], m[7], m[8]), m3 = max2_nan(m[9], m[10]);
+    const float mx = max2_nan(max3_nan(m0, m1, m2), m3);
+    if (!__any_sync(0xffffffffu, !(mx < u.thr_f))) return;        // NaN compares false -> scanned
+    int done = -1;                                                // last column of this chunk already queued
+    while (true) {
+        bool more = false;
+        if (!(mx < u.thr_f)) {
+#pragma unroll
+            for (int g = 0; g < 11; ++g) {
+                if (m[g] < u.thr_f) continue;
+#pragma unroll
+                for (int e3 = 0; e3 < (g < 10 ? 3 : 2); ++e3) {
+                    const int idx = 3 * g + e3;
+                    const uint32_t bits = v[idx];
+                    if (__uint_as_float(bits) < u.thr_f || idx <= done) continue;
+                    if (u.cnt < SC_QCAP) {
+                        u.Qe[u.cnt * SC_UG] = ((unsigned long long)bits << 32) | (unsigned long long)(col0 + (uint32_t)idx);
+                        ++u.cnt; ++u.n_push;
+                        done = idx;
+                    } else {
+                        more = true;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, more)) break;
+        drain(p, u);
+    }
+}
+
 __global__ void __launch_bounds__(SC_THREADS, 1)
-tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmI, ScoreParams p) {
+tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmI, const ScoreParams p) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* sA = smem;                                        // 2 x 16 KB
-    unsigned char* sB = smem + 2 * SC_A_BYTES;                       // SC_STAGES x 32 KB
-    unsigned long long* lists = reinterpret_cast<unsigned long long*>(sB + SC_STAGES * SC_B_BYTES);   // [k][SC_UG]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(lists + (size_t)p.k * SC_UG);
-    uint64_t* full_bar = bars;                  // [SC_STAGES]
-    uint64_t* empty_bar = bars + SC_STAGES;     // [SC_STAGES]
-    uint64_t* a_full = bars + 2 * SC_STAGES;    // [1]
-    uint64_t* acc_full = a_full + 1;            // [2]
-    uint64_t* acc_empty = acc_full + 2;         // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
+    unsigned char* sA = smem;                                        // SC_NUT x 16 KB
+    unsigned char* sB = smem + SC_NUT * SC_A_BYTES;                  // stages x 16 KB
+    unsigned long long* lists = reinterpret_cast<unsigned long long*>(sB + p.stages * SC_B_BYTES);   // [k][SC_UG]
+    unsigned long long* queues = lists + (size_t)p.k * SC_UG;                                          // [SC_QCAP][SC_UG]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(queues + (size_t)SC_QCAP * SC_UG);
+    uint64_t* full_bar = bars;                          // [SC_MAX_STAGES]
+    uint64_t* empty_bar = bars + SC_MAX_STAGES;         // [SC_MAX_STAGES]
+    uint64_t* a_full = bars + 2 * SC_MAX_STAGES;        // [1]
+    uint64_t* acc_full = a_full + 1;                    // [SC_NUT]
+    uint64_t* acc_empty = acc_full + SC_NUT;            // [SC_NUT]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + SC_NUT);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t q0 = (int64_t)blockIdx.y * SC_UG;
-    const int n_ut = (p.Q - q0 > SC_BM) ? 2 : 1;                     // valid 128-user tiles in this group
+    const int64_t q_left = p.Q - q0;
+    const int n_ut = q_left >= SC_UG ? SC_NUT : (int)((q_left + SC_BM - 1) / SC_BM);   // valid 128-user tiles
+    // contiguous tile range of this CTA
+    const int64_t n_tiles = p.tile_end - p.tile_begin;
+    const int64_t t0 = p.tile_begin + n_tiles * blockIdx.x / gridDim.x;
+    const int64_t t1 = p.tile_begin + n_tiles * (blockIdx.x + 1) / gridDim.x;
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmU); tma_prefetch_desc(&tmI); }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < SC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(a_full, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+        for (int a = 0; a < SC_NUT; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -107,11 +243,11 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
             mbar_arrive_expect_tx(a_full, (uint32_t)(n_ut * SC_A_BYTES));
             for (int ut = 0; ut < n_ut; ++ut) tma_load_2d(sA + ut * SC_A_BYTES, &tmU, a_full, 0, (int)(q0 + ut * SC_BM));
             int stage = 0; uint32_t phase = 0;
-            for (int64_t t = p.tile_begin + blockIdx.x; t < p.tile_end; t += gridDim.x) {
+            for (int64_t t = t0; t < t1; ++t) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 mbar_arrive_expect_tx(&full_bar[stage], SC_B_BYTES);
                 tma_load_2d(sB + stage * SC_B_BYTES, &tmI, &full_bar[stage], 0, (int)(t * SC_BN));
-                if (++stage == SC_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -119,7 +255,7 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
             constexpr uint32_t idesc = make_idesc_bf16_f32(SC_BM, SC_BN);
             mbar_wait(a_full, 0);
             int stage = 0; uint32_t phase = 0, acc_phase = 0;
-            for (int64_t t = p.tile_begin + blockIdx.x; t < p.tile_end; t += gridDim.x) {
+            for (int64_t t = t0; t < t1; ++t) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint64_t bdesc = make_sw128_desc(smem_u32(sB + stage * SC_B_BYTES));
@@ -133,82 +269,83 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
                         tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, kk ? 1u : 0u);
                     tc_commit(&acc_full[ut]);
                 }
-                tc_commit(&empty_bar[stage]);                         // item tile consumed by both user tiles
-                if (++stage == SC_STAGES) { stage = 0; phase ^= 1; }
+                tc_commit(&empty_bar[stage]);                         // item tile consumed by every user tile
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 acc_phase ^= 1;
             }
         }
-    } else if (warp >= 4) {
-        const int ut = (warp - 4) >> 2;                               // which user tile / accumulator
-        const int q = warp & 3;                                       // TMEM lane quarter
+    } else if (warp >= SC_EPI_WARP0) {
+        const int ut = (warp - SC_EPI_WARP0) >> 2;                    // which user tile / accumulator
+        const int q = warp & 3;                                       // TMEM lane quarter this warp may access
         const int u_local = ut * SC_BM + q * 32 + lane;               // column of `lists`
         const int64_t user = q0 + u_local;
-        const bool user_ok = user < p.Q;
-        unsigned long long* L = lists + u_local;                      // entry e at L[e * SC_UG]
+        const bool user_ok = user < p.Q && !(p.debug & 1);
         const int k = p.k;
-        for (int e = 0; e < k; ++e) L[e * SC_UG] = 0ull;
-        unsigned long long thr_key = 0ull;
-        float thr_f = -INFINITY;
-        int hlo = 0, hhi = 0;
-        if (p.hist_rowptr != nullptr && user_ok) { hlo = p.hist_rowptr[user]; hhi = p.hist_rowptr[user + 1]; }
+        UserState u;
+        u.L = lists + u_local;
+        u.Qe = queues + u_local;
+        for (int e = 0; e < k; ++e) u.L[e * SC_UG] = 0ull;
+        u.thr_key = 0ull; u.min_pos = 0; u.cnt = 0;
+        u.b1 = u.b2 = u.b3 = 0u;
+        u.n_push = u.n_ins = u.n_steps = 0;
+        u.thr_f = user_ok ? -INFINITY : INFINITY;                     // padding lanes never take a candidate
+        u.hpos = 0; u.hend = 0; u.next_h = INT64_MAX;
+        uint32_t* pub_user = p.pub + (size_t)(user_ok ? user : 0) * gridDim.x + blockIdx.x;
+        uint32_t last_pub = 0u;
 
         if (ut < n_ut) {
+            if (p.hist_rowptr != nullptr && user_ok) {
+                int lo = p.hist_rowptr[user];
+                u.hend = p.hist_rowptr[user + 1];
+                const int64_t first_gid = t0 * SC_BN + p.item_id_offset;
+                int hi = u.hend;
+                while (lo < hi) {                                     // lower_bound(first id of this CTA's range)
+                    const int mid = (lo + hi) >> 1;
+                    if ((int64_t)p.hist_cols[mid] < first_gid) lo = mid + 1; else hi = mid;
+                }
+                u.hpos = lo;
+                if (lo < u.hend) u.next_h = (int64_t)p.hist_cols[lo];
+            }
             uint32_t acc_phase = 0;
             const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ut * SC_BN);
-            for (int64_t t = p.tile_begin + blockIdx.x; t < p.tile_end; t += gridDim.x) {
+            for (int64_t t = t0; t < t1; ++t) {
+                const int64_t it = t - t0;
+                if (it > 0 && (it & (it - 1)) == 0 && gridDim.x > 1 && !(p.debug & 3)) {      // after tiles 1, 2, 4, 8, ...
+                    const uint32_t T = shared_threshold(p, user - lane, (int)gridDim.x, lane);
+                    if (T != 0u && user_ok) u.thr_f = fmaxf(u.thr_f, float_from_order_key(T));
+                }
                 mbar_wait(&acc_full[ut], acc_phase);
                 tc_fence_after();
-                const int64_t row0 = t * SC_BN;                       // first local item row of the tile
+                const uint32_t row0 = (uint32_t)(t * SC_BN);          // first local item row of the tile
+                uint32_t v[32];
 #pragma unroll 1
                 for (int c = 0; c < SC_BN / 32; ++c) {
-                    uint32_t v[32];
                     tc_ld_32x32(t_lane + (uint32_t)(c * 32), v);
                     tc_wait_ld();
-                    // NaN-propagating max of the 32 scores: 11 + 4 + 1 three-input / two-input max ops
-                    float m[11];
-#pragma unroll
-                    for (int j = 0; j < 10; ++j)
-                        m[j] = max3_nan(__uint_as_float(v[3 * j]), __uint_as_float(v[3 * j + 1]), __uint_as_float(v[3 * j + 2]));
-                    m[10] = max2_nan(__uint_as_float(v[30]), __uint_as_float(v[31]));
-                    const float m0 = max3_nan(m[0], m[1], m[2]), m1 = max3_nan(m[3], m[4], m[5]);
-                    const float m2 = max3_nan(m[6], m[7], m[8]), m3 = max2_nan(m[9], m[10]);
-                    const float mx = max2_nan(max3_nan(m0, m1, m2), m3);
-                    if (!(mx < thr_f) && user_ok) {                   // rare once the list has warmed up
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float s = __uint_as_float(v[j]);
-                            if (s < thr_f) continue;
-                            const int64_t li = row0 + c * 32 + j;
-                            if (li >= p.N) continue;                  // zero-filled rows past the end of the shard
-                            const int64_t gid = li + p.item_id_offset;
-                            if ((p.mask_pad && gid == 0) || gid < p.seg_lo || gid >= p.seg_hi ||
-                                (hhi > hlo && hist_has(p.hist_cols, hlo, hhi, gid)))
-                                s = -INFINITY;
-                            const unsigned long long key = make_key64(s, (uint32_t)li);
-                            if (key > thr_key) {
-                                int e = k - 1;
-                                while (e > 0) {
-                                    const unsigned long long prev = L[(e - 1) * SC_UG];
-                                    if (prev >= key) break;
-                                    L[e * SC_UG] = prev;
-                                    --e;
-                                }
-                                L[e * SC_UG] = key;
-                                thr_key = L[(k - 1) * SC_UG];
-                                thr_f = thr_key ? key64_score(thr_key) : -INFINITY;
-                            }
-                        }
+                    if (c == SC_BN / 32 - 1) {
+                        // the whole accumulator has been read: hand it back to the MMA warp before the last chunk is processed
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[ut]);
                     }
+                    process_chunk(p, u, v, row0 + (uint32_t)(c * 32));
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[ut]);
+                if (__any_sync(0xffffffffu, u.cnt > 0)) drain(p, u);
+                if (user_ok) {                                        // this stream's j-th best so far
+                    const uint32_t jb = p.pub_j == 1 ? u.b1 : (p.pub_j == 2 ? u.b2 : (p.pub_j == 3 ? u.b3 : (uint32_t)(u.thr_key >> 32)));
+                    if (jb > last_pub) { last_pub = jb; __stcg(pub_user, jb); }
+                }
                 acc_phase ^= 1;
             }
+        }
+        if ((p.debug & 4) && blockIdx.x == 0 && blockIdx.y == 0) {
+            const int tp = __reduce_add_sync(0xffffffffu, u.n_push), ti = __reduce_add_sync(0xffffffffu, u.n_ins);
+            const int mp = __reduce_max_sync(0xffffffffu, u.n_push);
+            if (lane == 0) printf("warp %d: tiles %lld pushes %d (max lane %d) inserts %d drain-steps %d\n", warp, (long long)(t1 - t0), tp, mp, ti, u.n_steps);
         }
         if (user_ok) {
             unsigned long long* dst = p.partial + ((size_t)blockIdx.x * p.Q + user) * k;
-            for (int e = 0; e < k; ++e) dst[e] = L[e * SC_UG];
+            for (int e = 0; e < k; ++e) dst[e] = u.L[e * SC_UG];
         }
     }
 
@@ -220,11 +357,18 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
     }
 }
 
-static size_t score_smem_bytes(int k) {
-    return 1024 + 2 * SC_A_BYTES + SC_STAGES * SC_B_BYTES + (size_t)k * SC_UG * 8 + 256;
+static int score_stages(int k) {
+    const int fixed = 1024 + SC_NUT * SC_A_BYTES + (k + SC_QCAP) * SC_UG * 8 + 256;
+    int s = (SC_SMEM_MAX - fixed) / SC_B_BYTES;
+    return s > SC_MAX_STAGES ? SC_MAX_STAGES : s;
+}
+static size_t score_smem_bytes(int k, int stages) {
+    return 1024 + SC_NUT * SC_A_BYTES + (size_t)stages * SC_B_BYTES + (size_t)(k + SC_QCAP) * SC_UG * 8 + 256;
 }
 
-bool score_tc_supported(int dtype, int D, int k) { return dtype == OOV_BF16 && D >= 8 && D <= 64 && D % 8 == 0 && k >= 1 && k <= SC_KMAX; }
+bool score_tc_supported(int dtype, int D, int k) {
+    return dtype == OOV_BF16 && D >= 8 && D <= 64 && D % 8 == 0 && k >= 1 && k <= SC_KMAX && score_stages(k) >= 2;
+}
 
 static int score_grid_x(int64_t Q, int64_t n_tiles) {
     const int64_t groups = cdiv(Q, SC_UG);
@@ -235,9 +379,11 @@ static int score_grid_x(int64_t Q, int64_t n_tiles) {
     return (int)gx;
 }
 
+static size_t score_pub_bytes(int64_t Q, int gx) { return align_up((size_t)gx * Q * 4, 256); }
+
 size_t score_tc_workspace(int64_t Q, int64_t N, int k) {
     const int gx = score_grid_x(Q, cdiv(N > 0 ? N : 1, SC_BN));
-    return align_up((size_t)gx * Q * k * 8, 256);
+    return score_pub_bytes(Q, gx) + align_up((size_t)gx * Q * k * 8, 256);
 }
 
 int score_tc_run(const void* users, const void* items, int64_t Q, int64_t N, int D, int k, int64_t item_id_offset,
@@ -252,23 +398,31 @@ int score_tc_run(const void* users, const void* items, int64_t Q, int64_t N, int
     p.seg_lo = seg_lo; p.seg_hi = seg_hi; p.hist_rowptr = hist_rowptr; p.hist_cols = hist_cols;
     p.tile_begin = hi > lo ? lo / SC_BN : 0;
     p.tile_end = hi > lo ? cdiv(hi, SC_BN) : 0;
+    p.stages = score_stages(k);
+    { const char* dbg = getenv("OOV_SCORE_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
     const int64_t n_tiles = p.tile_end - p.tile_begin;
     const int gx = score_grid_x(Q, n_tiles > 0 ? n_tiles : 1);
-    const size_t need = (size_t)gx * Q * k * 8;
+    const size_t need = score_pub_bytes(Q, gx) + (size_t)gx * Q * k * 8;
     OOV_REQUIRE(workspace && workspace_bytes >= need, OOV_ERR_WORKSPACE, "oov_fullsort_topk (tcgen05): workspace %zu < %zu",
                 workspace_bytes, need);
-    p.partial = reinterpret_cast<unsigned long long*>(workspace);
+    OOV_REQUIRE(aligned(workspace, 8), OOV_ERR_ALIGN, "oov_fullsort_topk (tcgen05): workspace must be 8-byte aligned");
+    p.pub = reinterpret_cast<uint32_t*>(workspace);
+    p.partial = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + score_pub_bytes(Q, gx));
+    p.pub_groups = gx < 32 ? gx : 32;                                // group = streams congruent modulo 32
+    p.pub_j = (k + p.pub_groups - 1) / p.pub_groups;
+    if (p.pub_j > 3) { p.pub_groups = 1; p.pub_j = k; }              // few long streams: share the plain k-th best
+    cudaError_t ce = cudaMemsetAsync(p.pub, 0, (size_t)gx * Q * 4, st);
+    OOV_REQUIRE(ce == cudaSuccess, OOV_ERR_CUDA, "cudaMemsetAsync(threshold array): %s", cudaGetErrorString(ce));
 
     CUtensorMap tmU, tmI;
     int rc = make_tmap_bf16_2d(&tmU, users, (uint64_t)D, (uint64_t)Q, (uint64_t)D * 2, SC_BM);
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&tmI, items, (uint64_t)D, (uint64_t)(N > 0 ? N : 1), (uint64_t)D * 2, SC_BN);
     if (rc) return rc;
-    const size_t smem = score_smem_bytes(k);
+    const size_t smem = score_smem_bytes(k, p.stages);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tc_score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)score_smem_bytes(SC_KMAX));
+        cudaError_t e = cudaFuncSetAttribute(tc_score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM_MAX);
         OOV_REQUIRE(e == cudaSuccess, OOV_ERR_CUDA, "cudaFuncSetAttribute(tc_score_topk_kernel): %s", cudaGetErrorString(e));
         attr_done = true;
     }

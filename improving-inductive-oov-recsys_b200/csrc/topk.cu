@@ -497,7 +497,7 @@ int oov_fullsort_topk(const void* users, const void* items, int32_t dtype, int64
     // bf16 tables take the tensor-core path (tcgen05 GEMM fused with the top-k epilogue); fp32 tables the fp32 FMA path
     const bool tc_ok = tc::score_tc_supported(dtype, D, k) && N >= 1;
     OOV_REQUIRE(path != OOV_PATH_TCGEN05 || tc_ok, OOV_ERR_ARG,
-                "oov_fullsort_topk: tcgen05 path needs bf16 tables, D <= 64 (multiple of 8) and k <= 32");
+                "oov_fullsort_topk: tcgen05 path needs bf16 tables, D <= 64 (multiple of 8) and k <= 24");
     if (tc_ok && path != OOV_PATH_SIMT_FP32)
         return tc::score_tc_run(users, items, Q, N, D, k, item_id_offset, mask_pad, seg_lo, seg_hi, hist_rowptr, hist_cols,
                                 out_scores, out_idx, workspace, workspace_bytes, (cudaStream_t)stream);

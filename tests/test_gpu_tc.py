@@ -142,7 +142,7 @@ def _ref_scores(users, items, off, hist, seg, mask_pad=True):
     return s
 
 
-@pytest.mark.parametrize("Q,N,D,k", [(1, 50, 64, 5), (100, 257, 64, 20), (256, 5000, 64, 20), (300, 5000, 16, 32),
+@pytest.mark.parametrize("Q,N,D,k", [(1, 50, 64, 5), (100, 257, 64, 20), (256, 5000, 64, 20), (300, 5000, 16, 24),
                                      (1024, 70_001, 64, 20), (129, 1024, 32, 1), (64, 200_003, 64, 10)])
 def test_tc_score_topk_vs_fp32_reference(Q, N, D, k):
     from oov_b200 import ops
