@@ -46,6 +46,7 @@ constexpr int SC_MAX_STAGES = 6;
 constexpr int SC_EPI_WARP0 = 3;
 constexpr int SC_THREADS = (SC_EPI_WARP0 + 4 * SC_NUT) * 32;   // 608
 constexpr int SC_KMAX = 24;              // smem: lists k x 512 x 8 B next to A (64 KB), the queues (32 KB) and >= 2 B stages
+constexpr int SC_PUB_MAXP = 160;          // streams per user the threshold refresh reads (>= SM count)
 constexpr int SC_QCAP = 8;               // queued candidates per user between drains
 constexpr int SC_A_BYTES = SC_BM * 128;               // one 128-user tile, 64 bf16 (128 B) per row
 constexpr int SC_B_BYTES = SC_BN * 128;
@@ -100,9 +101,10 @@ __device__ __forceinline__ void list_insert(const ScoreParams& p, UserState& u, 
     if (hi > u.b1) { u.b3 = u.b2; u.b2 = u.b1; u.b1 = hi; }
     else if (hi > u.b2) { u.b3 = u.b2; u.b2 = hi; }
     else if (hi > u.b3) u.b3 = hi;
+    const int k = p.k;
+    if (u.thr_key == 0ull && u.min_pos + 1 < k) { ++u.min_pos; return; }   // still filling: slots are taken in order
     unsigned long long mn = ~0ull;
     int pos = 0;
-    const int k = p.k;
 #pragma unroll 4
     for (int e = 0; e < k; ++e) {
         const unsigned long long x = u.L[e * SC_UG];
@@ -143,21 +145,37 @@ __device__ __forceinline__ void drain(const ScoreParams& p, UserState& u) {
 __device__ __forceinline__ uint32_t shared_threshold(const ScoreParams& p, int64_t user0, int P, int lane) {
     uint32_t mine = 0u;
     const int G = p.pub_groups;
-#pragma unroll 4
-    for (int uu = 0; uu < 32; ++uu) {
-        const int64_t user = user0 + uu;
-        if (user >= p.Q) break;                                   // warp-uniform
-        uint32_t v = 0u;
-        for (int s = lane; s < P; s += 32) {
-            const uint32_t x = __ldcg(p.pub + (size_t)user * P + s);
-            v = x > v ? x : v;
+    for (int uu0 = 0; uu0 < 32; uu0 += 8) {                       // 8 users x up to 5 loads in flight per lane
+        if (user0 + uu0 >= p.Q) break;                            // warp-uniform
+        uint32_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t user = user0 + uu0 + j;
+            const uint32_t* row = p.pub + (size_t)(user < p.Q ? user : user0) * P;
+            uint32_t x = 0u;
+#pragma unroll
+            for (int i = 0; i < SC_PUB_MAXP / 32; ++i) {
+                const int s = lane + 32 * i;
+                const uint32_t y = s < P ? __ldcg(row + s) : 0u;
+                x = y > x ? y : x;
+            }
+            v[j] = x;
         }
-        uint32_t T;
-        if (G == 1) T = __reduce_max_sync(0xffffffffu, v);
-        else T = __reduce_min_sync(0xffffffffu, lane < G ? v : 0xFFFFFFFFu);
-        if (lane == uu) mine = T;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint32_t T;
+            if (G == 1) T = __reduce_max_sync(0xffffffffu, v[j]);
+            else T = __reduce_min_sync(0xffffffffu, lane < G ? v[j] : 0xFFFFFFFFu);
+            if (lane == uu0 + j) mine = T;
+        }
     }
     return mine;
+}
+
+// refresh after tiles 1, 2, 3, 4, 6, 8, 12, 16, 24, ...: the useful threshold moves like 1/n
+__device__ __forceinline__ bool refresh_tile(int64_t it) {
+    const int64_t low = it & (it - 1);                            // `it` without its lowest set bit
+    return low == 0 || ((low & (low - 1)) == 0 && (low >> 1) == (it ^ low));   // 2^a or 3 * 2^a
 }
 
 // one 32-column chunk of one user's scores (registers v[0..31]); `col0` = local item row of column 0.
@@ -227,7 +245,7 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmU); tma_prefetch_desc(&tmI); }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], (uint32_t)n_ut); }
         mbar_init(a_full, 1);
         for (int a = 0; a < SC_NUT; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
         fence_barrier_init();
@@ -254,24 +272,36 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_bf16_f32(SC_BM, SC_BN);
             mbar_wait(a_full, 0);
-            int stage = 0; uint32_t phase = 0, acc_phase = 0;
-            for (int64_t t = t0; t < t1; ++t) {
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                const uint64_t bdesc = make_sw128_desc(smem_u32(sB + stage * SC_B_BYTES));
-                for (int ut = 0; ut < n_ut; ++ut) {
-                    mbar_wait(&acc_empty[ut], acc_phase ^ 1);         // this user tile's epilogue drained the accumulator
+            // Each user tile advances through the item tiles on its own: whichever accumulator has been drained gets
+            // its next MMA, so one slow epilogue (a burst of candidates) does not stall the other three.  The B ring
+            // bounds the drift: a stage is released when every user tile has consumed it (empty_bar counts n_ut).
+            int64_t nxt[SC_NUT];
+            int stg[SC_NUT];
+            uint32_t ph[SC_NUT], aph[SC_NUT];
+#pragma unroll
+            for (int ut = 0; ut < SC_NUT; ++ut) { nxt[ut] = t0; stg[ut] = 0; ph[ut] = 0; aph[ut] = 0; }
+            int remaining = n_ut;
+            if (t1 <= t0) remaining = 0;
+            while (remaining > 0) {
+#pragma unroll
+                for (int ut = 0; ut < SC_NUT; ++ut) {
+                    if (ut >= n_ut || nxt[ut] >= t1) continue;
+                    if (!mbar_try_wait(&acc_empty[ut], aph[ut] ^ 1)) continue;     // epilogue still draining this accumulator
+                    if (!mbar_try_wait(&full_bar[stg[ut]], ph[ut])) continue;      // item tile not landed yet (never block: the
+                                                                                   // slowest user tile frees the stage it needs)
                     tc_fence_after();
+                    const uint64_t bdesc = make_sw128_desc(smem_u32(sB + stg[ut] * SC_B_BYTES));
                     const uint64_t adesc = make_sw128_desc(smem_u32(sA + ut * SC_A_BYTES));
                     const uint32_t d_tmem = tmem_base + (uint32_t)(ut * SC_BN);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
                         tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, kk ? 1u : 0u);
                     tc_commit(&acc_full[ut]);
+                    tc_commit(&empty_bar[stg[ut]]);                               // one of n_ut arrivals for this stage
+                    aph[ut] ^= 1;
+                    if (++stg[ut] == p.stages) { stg[ut] = 0; ph[ut] ^= 1; }
+                    if (++nxt[ut] == t1) --remaining;
                 }
-                tc_commit(&empty_bar[stage]);                         // item tile consumed by every user tile
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
-                acc_phase ^= 1;
             }
         }
     } else if (warp >= SC_EPI_WARP0) {
@@ -310,7 +340,7 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
             const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ut * SC_BN);
             for (int64_t t = t0; t < t1; ++t) {
                 const int64_t it = t - t0;
-                if (it > 0 && (it & (it - 1)) == 0 && gridDim.x > 1 && !(p.debug & 3)) {      // after tiles 1, 2, 4, 8, ...
+                if (it > 0 && refresh_tile(it) && gridDim.x > 1 && !(p.debug & 3)) {
                     const uint32_t T = shared_threshold(p, user - lane, (int)gridDim.x, lane);
                     if (T != 0u && user_ok) u.thr_f = fmaxf(u.thr_f, float_from_order_key(T));
                 }
@@ -375,6 +405,7 @@ static int score_grid_x(int64_t Q, int64_t n_tiles) {
     int64_t gx = num_sms() / groups;
     if (gx < 1) gx = 1;
     if (gx > n_tiles) gx = n_tiles;
+    if (gx > SC_PUB_MAXP) gx = SC_PUB_MAXP;
     if (gx < 1) gx = 1;
     return (int)gx;
 }
