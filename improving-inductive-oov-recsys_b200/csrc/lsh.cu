@@ -331,6 +331,14 @@ int launch_lsh_bits_simt(const float* feat, int64_t n_feat_rows, int F, const fl
 
 int check_rows_public(const oov_rows* r, const char* who) { return check_rows(r, who); }
 
+namespace tc {
+bool lsh_tc_supported(int F, int B, int D);
+size_t lsh_tc_workspace(int B);
+int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* planes, int B, const void* W, int w_dtype,
+               const oov_rows* rows, float tie_eps, uint32_t* bits_out, unsigned long long* tie_count, void* workspace,
+               size_t workspace_bytes, cudaStream_t st);
+}  // namespace tc
+
 }  // namespace oov
 
 using namespace oov;
@@ -350,9 +358,14 @@ int oov_lsh_bits(const float* feat, int64_t n_feat_rows, int32_t F, const float*
 }
 
 size_t oov_lsh_embed_workspace(int64_t n, int32_t B, int32_t D, int32_t path) {
-    (void)D; (void)path;
     const int64_t chunk = n < (1 << 20) ? n : (1 << 20);
-    return align_up((size_t)chunk * ((B + 31) / 32) * 4, 256);
+    size_t a = align_up((size_t)chunk * ((B + 31) / 32) * 4, 256);
+    if (path != OOV_PATH_SIMT_FP32 && B > 0) {                 // F is not known here: reserve for the tensor-core path too
+        const size_t b = tc::lsh_tc_workspace(B);
+        if (b > a) a = b;
+    }
+    (void)D;
+    return a;
 }
 
 int oov_lsh_embed(const float* feat, int64_t n_feat_rows, int32_t F, const float* planes, int32_t B,
@@ -363,9 +376,15 @@ int oov_lsh_embed(const float* feat, int64_t n_feat_rows, int32_t F, const float
     if (rc) return rc;
     OOV_REQUIRE(feat && planes && W && dtype_ok(w_dtype), OOV_ERR_ARG, "oov_lsh_embed: NULL pointer / bad dtype");
     OOV_REQUIRE(F > 0 && B > 0 && n_feat_rows > 0, OOV_ERR_ARG, "oov_lsh_embed: bad shape F=%d B=%d", F, B);
-    OOV_REQUIRE(path == OOV_PATH_AUTO || path == OOV_PATH_SIMT_FP32, OOV_ERR_ARG, "oov_lsh_embed: unsupported path %d", path);
+    OOV_REQUIRE(path >= OOV_PATH_AUTO && path <= OOV_PATH_TCGEN05, OOV_ERR_ARG, "oov_lsh_embed: unsupported path %d", path);
     if (rows->n == 0) return OOV_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    // tensor cores (split-bf16 exact-sign GEMM fused with the bucket-mean GEMM) when the tile shapes allow
+    const bool tc_ok = tc::lsh_tc_supported(F, B, rows->D);
+    OOV_REQUIRE(path != OOV_PATH_TCGEN05 || tc_ok, OOV_ERR_ARG, "oov_lsh_embed: tcgen05 path needs F <= 32 and D <= 64 (F=%d D=%d)", F, rows->D);
+    if (tc_ok && path != OOV_PATH_SIMT_FP32)
+        return tc::lsh_tc_run(feat, n_feat_rows, F, planes, B, W, w_dtype, rows, tie_eps, bits_out, tie_count, workspace,
+                              workspace_bytes, st);
     const int words = (B + 31) / 32;
     const int64_t chunk = bits_out ? rows->n : (rows->n < (1 << 20) ? rows->n : (1 << 20));
     if (!bits_out) {

@@ -1,0 +1,482 @@
+// LSH OOV embedder on the tensor cores: sign-projection GEMM -> bit-pack -> multi-hot x bucket-table GEMM -> mean.
+//
+// Replaces inductive/torch_hash.py:55-60 (R = X P^T, bit = !(R < 0)) and inductive/lsh_embedder.py:141-179
+// (out = (H W) / H.sum(1)) in ONE kernel: neither R [n, B] fp32 nor H [n, B] ever exist in HBM.
+//
+// Exact signs from bf16 tensor cores: every fp32 operand is split into three bf16 pieces (8 + 8 + 8 significand
+// bits, an exact split), and the six products that matter are laid side by side along K:
+//     A' = [x0 | x0 | x1 | x0 | x1 | x2]      B' = [p0 | p1 | p0 | p2 | p1 | p0]        (K' = 6 F, F <= 32 -> 192)
+// so one K' = 192 GEMM with fp32 accumulation reproduces the fp32 projection to ~1e-7.  Projections that land within
+// 1e-5 of zero (about 8 per million) are recomputed by the epilogue thread with the same fp32 FMA chain the CUDA-core
+// path uses (csrc/lsh.cu), so both paths give identical bits; |R| < tie_eps events are counted like there.
+//
+// Per CTA (608 threads), persistent over 128-row tiles of the id list:
+//   warps 3-18  workers : gather the tile's feature rows, split, write A' into 128B-swizzled K-major smem; per 128-plane
+//                         N tile: tcgen05.ld the projections (lane = row), pack the sign bits (bits_out word = one
+//                         32-column load), count them, write the 0/1 tile H as the next GEMM's bf16 A operand; at the
+//                         end divide the accumulated H W by the count (0/0 -> NaN like lsh_embedder.py:158) and store.
+//   warp 0      TMA     : B' tiles (128 planes x 64 K) through a 4-stage ring
+//   warp 2      TMEM alloc, then TMA of the transposed bucket-table tiles (64 d x 64 planes) through a 4-stage ring
+//   warp 1      MMA     : GEMM1 (M128 N128 K16 x 12) into one of two TMEM accumulators, GEMM2 (M128 N64 K16 x 8) one
+//                         N tile behind, accumulating H W over all N tiles in a third TMEM region.
+// The fp32 bucket table is split hi + lo bf16 (two GEMM2 passes) so the sums are fp32-grade for every output dtype.
+// Row tiles without any OOV id skip the GEMMs (every role derives that from the ids with one warp vote).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace oov {
+namespace tc {
+
+constexpr int L_BM = 128;                 // rows per tile
+constexpr int L_BN = 128;                 // planes per N tile
+constexpr int L_FMAX = 32;                // features (K' = 192 = 3 K blocks of 64)
+constexpr int L_KB = 3;
+constexpr int L_DMAX = 64;
+constexpr int L_BSTAGES = 4, L_WSTAGES = 4;
+constexpr int L_WORK_WARP0 = 3, L_WORKERS = 16;
+constexpr int L_THREADS = (L_WORK_WARP0 + L_WORKERS) * 32;     // 608
+constexpr int L_A_BYTES = L_KB * L_BM * 128;                   // 48 KB
+constexpr int L_BT_BYTES = L_BN * 128;                         // 16 KB: one K block of one N tile of B'
+constexpr int L_H_BYTES = 2 * L_BM * 128;                      // 32 KB: H tile = 2 K blocks
+constexpr int L_WT_BYTES = L_DMAX * 128;                       // 8 KB: 64 d-rows x 64 planes
+constexpr int L_SMEM = 1024 + L_A_BYTES + L_BSTAGES * L_BT_BYTES + 2 * L_H_BYTES + L_WSTAGES * L_WT_BYTES + 5120;
+constexpr float L_NEAR = 1e-5f;           // projections closer to zero than this are recomputed in exact fp32 order
+
+struct LshParams {
+    const float* feat; int64_t n_feat_rows; int F;
+    const float* planes; int B; int NT;               // NT = ceil(B / 128)
+    const int64_t* ids; int64_t ids_stride; int64_t n; int64_t n_old; int64_t prime_pad;
+    const void* iv_table; int iv_dtype;
+    void* out; int out_dtype; int64_t out_stride; int D;
+    int wsplit;                                        // 1: bf16 bucket table, 2: hi + lo
+    float tie_eps;
+    uint32_t* bits_out; int words;
+    unsigned long long* tie_count;
+};
+
+// ---------------------------------------------------------------- operand packing (once per call)
+// Bp [NT*128, 192] bf16: row b = [p0 | p1 | p0 | p2 | p1 | p0] (32 columns each; zero for f >= F and b >= B)
+// Wt [wsplit*64, NT*128] bf16: Wt[s*64 + d][b] = piece s of W[b][d] (zero padding)
+__global__ void lsh_pack_kernel(const float* __restrict__ planes, int B, int F, int NT, const void* __restrict__ W, int w_dtype,
+                                int D, int wsplit, __nv_bfloat16* __restrict__ Bp, __nv_bfloat16* __restrict__ Wt) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nb = (int64_t)NT * L_BN;
+    if (t < nb * 32) {
+        const int b = (int)(t >> 5), f = (int)(t & 31);
+        float p = (b < B && f < F) ? planes[(size_t)b * F + f] : 0.f;
+        const __nv_bfloat16 p0 = __float2bfloat16_rn(p);
+        const float r1 = p - __bfloat162float(p0);
+        const __nv_bfloat16 p1 = __float2bfloat16_rn(r1);
+        const __nv_bfloat16 p2 = __float2bfloat16_rn(r1 - __bfloat162float(p1));
+        __nv_bfloat16* row = Bp + (size_t)b * 192;
+        row[f] = p0; row[32 + f] = p1; row[64 + f] = p0; row[96 + f] = p2; row[128 + f] = p1; row[160 + f] = p0;
+    }
+    if (t < nb * L_DMAX) {
+        const int d = (int)(t / nb);
+        const int64_t b = t - (int64_t)d * nb;
+        const float w = (b < B && d < D) ? load_elem(W, w_dtype, b * D + d) : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+        Wt[(size_t)d * nb + b] = hi;
+        if (wsplit == 2) Wt[(size_t)(L_DMAX + d) * nb + b] = __float2bfloat16_rn(w - __bfloat162float(hi));
+    }
+}
+
+// warp-uniform: does tile `t` (128 list positions) hold at least one OOV id?  Every role asks the same question.
+__device__ __forceinline__ bool tile_has_oov(const LshParams& p, int64_t t, int lane) {
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < L_BM / 32; ++i) {
+        const int64_t r = t * L_BM + i * 32 + lane;
+        if (r < p.n) any |= p.ids[r * p.ids_stride] >= p.n_old;
+    }
+    return __any_sync(0xffffffffu, any);
+}
+
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(L_WORKERS * 32) : "memory"); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void tc_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(L_THREADS, 1)
+tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmW, const LshParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* sA = smem;                                        // 3 K blocks x [128 x 64] bf16
+    unsigned char* sB = sA + L_A_BYTES;                              // ring of [128 planes x 64] tiles
+    unsigned char* sH = sB + L_BSTAGES * L_BT_BYTES;                 // 2 x (2 K blocks x [128 x 64])
+    unsigned char* sW = sH + 2 * L_H_BYTES;                          // ring of [64 d x 64 planes] tiles
+    unsigned char* tail = sW + L_WSTAGES * L_WT_BYTES;
+    int64_t* srow = reinterpret_cast<int64_t*>(tail);                // [128] feature row or -1
+    int64_t* sid = srow + L_BM;                                      // [128] id, INT64_MIN = no such row
+    int* scnt = reinterpret_cast<int*>(sid + L_BM);                  // [4][128] popcounts per column quarter
+    uint64_t* bars = reinterpret_cast<uint64_t*>(scnt + 4 * L_BM);
+    uint64_t* a_full = bars;            uint64_t* a_empty = bars + 1;
+    uint64_t* b_full = bars + 2;        uint64_t* b_empty = b_full + L_BSTAGES;
+    uint64_t* w_full = b_empty + L_BSTAGES;  uint64_t* w_empty = w_full + L_WSTAGES;
+    uint64_t* acc1_full = w_empty + L_WSTAGES;  uint64_t* acc1_empty = acc1_full + 2;
+    uint64_t* h_full = acc1_empty + 2;  uint64_t* h_empty = h_full + 2;
+    uint64_t* acc2_full = h_empty + 2;  uint64_t* acc2_empty = acc2_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_tiles = (p.n + L_BM - 1) / L_BM;
+    const int NT = p.NT;
+    const int WK = 2 * p.wsplit;                                     // Wt tiles per N tile
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmW); }
+    if (warp == 1 && lane == 0) {
+        mbar_init(a_full, L_WORKERS); mbar_init(a_empty, 1);
+        for (int s = 0; s < L_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < L_WSTAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc1_full[a], 1); mbar_init(&acc1_empty[a], L_WORKERS);
+            mbar_init(&h_full[a], L_WORKERS); mbar_init(&h_empty[a], 1);
+        }
+        mbar_init(acc2_full, 1); mbar_init(acc2_empty, L_WORKERS);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t ACC2_COL = 256;
+
+    if (warp == 0) {
+        // ===================== TMA: B' tiles =====================
+        int stage = 0; uint32_t phase = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            if (!tile_has_oov(p, t, lane)) continue;
+            if (lane == 0)
+                for (int nt = 0; nt < NT; ++nt)
+                    for (int kb = 0; kb < L_KB; ++kb) {
+                        mbar_wait(&b_empty[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&b_full[stage], L_BT_BYTES);
+                        tma_load_2d(sB + stage * L_BT_BYTES, &tmB, &b_full[stage], kb * 64, nt * L_BN);
+                        if (++stage == L_BSTAGES) { stage = 0; phase ^= 1; }
+                    }
+            __syncwarp();
+        }
+    } else if (warp == 2) {
+        // ===================== TMA: transposed bucket-table tiles =====================
+        int stage = 0; uint32_t phase = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            if (!tile_has_oov(p, t, lane)) continue;
+            if (lane == 0)
+                for (int nt = 0; nt < NT; ++nt)
+                    for (int kk = 0; kk < WK; ++kk) {
+                        mbar_wait(&w_empty[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&w_full[stage], L_WT_BYTES);
+                        tma_load_2d(sW + stage * L_WT_BYTES, &tmW, &w_full[stage], nt * L_BN + (kk & 1) * 64, (kk >> 1) * L_DMAX);
+                        if (++stage == L_WSTAGES) { stage = 0; phase ^= 1; }
+                    }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        {
+            constexpr uint32_t idesc1 = make_idesc_bf16_f32(L_BM, L_BN);
+            constexpr uint32_t idesc2 = make_idesc_bf16_f32(L_BM, L_DMAX);
+            int bs = 0; uint32_t bph = 0; int ws = 0; uint32_t wph = 0;
+            int64_t g1 = 0, g2 = 0;            // N tiles issued to GEMM1 / GEMM2 since kernel start
+            int64_t T = 0;                     // row tiles with OOV ids done by this CTA
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                if (!tile_has_oov(p, t, lane)) continue;
+                if (lane != 0) { ++T; __syncwarp(); continue; }
+                mbar_wait(a_full, (uint32_t)(T & 1));
+                tc_fence_after();
+                for (int nt = 0; nt <= NT; ++nt) {
+                    if (nt < NT) {                                    // GEMM1(nt): projections of 128 planes
+                        const int buf = (int)(g1 & 1);
+                        mbar_wait(&acc1_empty[buf], (uint32_t)(((g1 >> 1) & 1) ^ 1));
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * L_BN);
+                        for (int kb = 0; kb < L_KB; ++kb) {
+                            mbar_wait(&b_full[bs], bph);
+                            tc_fence_after();
+                            const uint64_t adesc = make_sw128_desc(smem_u32(sA + kb * L_BM * 128));
+                            const uint64_t bdesc = make_sw128_desc(smem_u32(sB + bs * L_BT_BYTES));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, (kb | k) ? 1u : 0u);
+                            tc_commit(&b_empty[bs]);
+                            if (++bs == L_BSTAGES) { bs = 0; bph ^= 1; }
+                        }
+                        tc_commit(&acc1_full[buf]);
+                        if (nt == NT - 1) tc_commit(a_empty);         // A' may be rebuilt for the next row tile
+                        ++g1;
+                    }
+                    if (nt >= 1) {                                    // GEMM2(nt - 1): acc2 += H W
+                        const int j = nt - 1;
+                        const int hb = (int)(g2 & 1);
+                        mbar_wait(&h_full[hb], (uint32_t)((g2 >> 1) & 1));
+                        if (j == 0) mbar_wait(acc2_empty, (uint32_t)((T & 1) ^ 1));
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + ACC2_COL;
+                        for (int kk = 0; kk < WK; ++kk) {
+                            mbar_wait(&w_full[ws], wph);
+                            tc_fence_after();
+                            const uint64_t adesc = make_sw128_desc(smem_u32(sH + hb * L_H_BYTES + (kk & 1) * L_BM * 128));
+                            const uint64_t bdesc = make_sw128_desc(smem_u32(sW + ws * L_WT_BYTES));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (j | kk | k) ? 1u : 0u);
+                            tc_commit(&w_empty[ws]);
+                            if (++ws == L_WSTAGES) { ws = 0; wph ^= 1; }
+                        }
+                        tc_commit(&h_empty[hb]);
+                        if (j == NT - 1) tc_commit(acc2_full);
+                        ++g2;
+                    }
+                }
+                ++T;
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===================== workers =====================
+        const int wk = warp - L_WORK_WARP0;
+        const int q = warp & 3;                    // TMEM lane quarter
+        const int cq = wk >> 2;                    // column quarter of every N tile
+        const int row = q * 32 + lane;             // row of the tile this thread owns in the epilogues
+        const int wtid = wk * 32 + lane;           // 0..511
+        unsigned int my_ties = 0;
+        int64_t g = 0, T = 0;
+        const float near = fmaxf(L_NEAR, 4.f * p.tie_eps);
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int64_t row0 = t * L_BM;
+            worker_bar();                                             // previous tile's readers of srow / scnt are done
+            if (wtid < L_BM) {
+                const int64_t r = row0 + wtid;
+                int64_t id = INT64_MIN, fr = -1;
+                if (r < p.n) {
+                    id = p.ids[r * p.ids_stride];
+                    if (id >= p.n_old) {
+                        fr = feature_row(id, p.prime_pad);
+                        if (fr < 0 || fr >= p.n_feat_rows) fr = -1;   // out-of-range ids hash nothing (caller bug)
+                    }
+                }
+                sid[wtid] = id; srow[wtid] = fr;
+            }
+            worker_bar();
+            if (!tile_has_oov(p, t, lane)) {                                           // in-vocab rows only: plain gather, 4 threads per row
+                const int r = wtid >> 2, part = wtid & 3;
+                const int64_t id = sid[r];
+                if (id != INT64_MIN && id >= 0 && p.iv_table != nullptr)
+                    for (int d = part * 16; d < p.D && d < part * 16 + 16; ++d)
+                        store_elem(p.out, p.out_dtype, (row0 + r) * p.out_stride + d, load_elem(p.iv_table, p.iv_dtype, id * (int64_t)p.D + d));
+                if (p.bits_out != nullptr && row0 + r < p.n)
+                    for (int w = part; w < p.words; w += 4) p.bits_out[(row0 + r) * p.words + w] = 0u;
+                continue;
+            }
+            // ---- gather + split: thread = (row r, 8 features)
+            {
+                const int r = wtid >> 2, part = wtid & 3;
+                const int64_t fr = srow[r];
+                float x[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int f = part * 8 + j;
+                    x[j] = (fr >= 0 && f < p.F) ? __ldg(p.feat + fr * p.F + f) : 0.f;
+                }
+                uint32_t c0[4], c1[4], c2[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float a = x[2 * j], b = x[2 * j + 1];
+                    const __nv_bfloat16 a0 = __float2bfloat16_rn(a), b0 = __float2bfloat16_rn(b);
+                    const float ra = a - __bfloat162float(a0), rb = b - __bfloat162float(b0);
+                    const __nv_bfloat16 a1 = __float2bfloat16_rn(ra), b1 = __float2bfloat16_rn(rb);
+                    const float sa = ra - __bfloat162float(a1), sb = rb - __bfloat162float(b1);
+                    c0[j] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(b0) << 16);
+                    c1[j] = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+                    c2[j] = pack_bf16x2(sa, sb);
+                }
+                mbar_wait(a_empty, (uint32_t)((T & 1) ^ 1));          // previous tile's GEMM1s have read A'
+                const uint4 v0 = make_uint4(c0[0], c0[1], c0[2], c0[3]);
+                const uint4 v1 = make_uint4(c1[0], c1[1], c1[2], c1[3]);
+                const uint4 v2 = make_uint4(c2[0], c2[1], c2[2], c2[3]);
+                // K block 0 = [x0 | x0], 1 = [x1 | x0], 2 = [x1 | x2]; 16-byte chunk (4 s + part) of row r, swizzled
+                *reinterpret_cast<uint4*>(sA + 0 * L_BM * 128 + sw128_offset(r, part)) = v0;
+                *reinterpret_cast<uint4*>(sA + 0 * L_BM * 128 + sw128_offset(r, 4 + part)) = v0;
+                *reinterpret_cast<uint4*>(sA + 1 * L_BM * 128 + sw128_offset(r, part)) = v1;
+                *reinterpret_cast<uint4*>(sA + 1 * L_BM * 128 + sw128_offset(r, 4 + part)) = v0;
+                *reinterpret_cast<uint4*>(sA + 2 * L_BM * 128 + sw128_offset(r, part)) = v1;
+                *reinterpret_cast<uint4*>(sA + 2 * L_BM * 128 + sw128_offset(r, 4 + part)) = v2;
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full);
+            }
+            const int64_t my_fr = srow[row];
+            const bool my_oov = my_fr >= 0;
+            int cnt = 0;
+            // ---- per N tile: projections -> bits -> H
+            for (int nt = 0; nt < NT; ++nt, ++g) {
+                const int buf = (int)(g & 1);
+                const uint32_t par = (uint32_t)((g >> 1) & 1);
+                mbar_wait(&acc1_full[buf], par);
+                tc_fence_after();
+                uint32_t v[32];
+                tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * L_BN + cq * 32), v);
+                tc_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc1_empty[buf]);
+                const int b0 = nt * L_BN + cq * 32;                   // plane of column 0
+                uint32_t word = 0u;
+                bool any_near = false;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float r = __uint_as_float(v[j]);
+                    word |= (r < 0.f ? 0u : 1u) << j;                 // torch_hash.py:57-59: -0, +0, NaN -> 1
+                    any_near |= fabsf(r) < near;
+                }
+                if (any_near && my_oov) {                             // rare: redo in the fp32 FMA order of csrc/lsh.cu
+                    for (int j = 0; j < 32; ++j) {
+                        const int b = b0 + j;
+                        if (b >= p.B || !(fabsf(__uint_as_float(v[j])) < near)) continue;
+                        const float* xr = p.feat + my_fr * p.F;
+                        const float* pr = p.planes + (size_t)b * p.F;
+                        float a = 0.f;
+                        for (int f = 0; f < p.F; ++f) a = fmaf(__ldg(xr + f), __ldg(pr + f), a);
+                        word = (word & ~(1u << j)) | ((a < 0.f ? 0u : 1u) << j);
+                        if (fabsf(a) < p.tie_eps) ++my_ties;
+                    }
+                }
+                if (b0 + 32 > p.B) word &= (b0 >= p.B) ? 0u : ((1u << (p.B - b0)) - 1u);   // planes past B do not exist
+                if (!my_oov) word = 0u;
+                cnt += __popc(word);
+                if (p.bits_out != nullptr && row0 + row < p.n && nt * 4 + cq < p.words)
+                    p.bits_out[(row0 + row) * p.words + nt * 4 + cq] = word;
+                // H tile: 32 bf16 0/1 values = 4 chunks of 16 B at K block (cq >> 1), chunks (cq & 1) * 4 ..
+                mbar_wait(&h_empty[buf], par ^ 1);                    // GEMM2 of the previous use of this buffer is done
+                unsigned char* hk = sH + buf * L_H_BYTES + (cq >> 1) * L_BM * 128;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t w4[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t two = (word >> (c * 8 + i * 2)) & 3u;
+                        w4[i] = ((two & 1u) ? 0x3F80u : 0u) | ((two & 2u) ? 0x3F800000u : 0u);
+                    }
+                    *reinterpret_cast<uint4*>(hk + sw128_offset(row, (cq & 1) * 4 + c)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&h_full[buf]);
+            }
+            // ---- final: out = (H W) / count
+            scnt[cq * L_BM + row] = cnt;
+            mbar_wait(acc2_full, (uint32_t)(T & 1));
+            tc_fence_after();
+            ++T;
+            uint32_t a[16];
+            tc_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + ACC2_COL + (uint32_t)(cq * 16), a);
+            tc_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc2_empty);
+            worker_bar();                                             // all four popcount partials are in smem
+            const int64_t r = row0 + row;
+            if (r < p.n) {
+                const int d0 = cq * 16;
+                const size_t osz = p.out_dtype == OOV_F32 ? 4 : 2;
+                char* orow = reinterpret_cast<char*>(p.out) + (size_t)r * p.out_stride * osz;
+                if (my_oov) {
+                    const float den = (float)(scnt[row] + scnt[L_BM + row] + scnt[2 * L_BM + row] + scnt[3 * L_BM + row]);
+                    if (p.out_dtype == OOV_BF16 && d0 + 16 <= p.D && ((reinterpret_cast<uintptr_t>(orow) + d0 * 2) & 15) == 0) {
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            pk[i] = pack_bf16x2(__uint_as_float(a[2 * i]) / den, __uint_as_float(a[2 * i + 1]) / den);
+                        uint4* o = reinterpret_cast<uint4*>(orow + d0 * 2);
+                        o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (d0 + i < p.D) store_elem(p.out, p.out_dtype, r * p.out_stride + d0 + i, __uint_as_float(a[i]) / den);
+                    }
+                } else {
+                    const int64_t id = sid[row];
+                    if (id != INT64_MIN && id >= 0 && id < p.n_old && p.iv_table != nullptr) {   // in-vocab gather (bpr.py:111-112)
+                        for (int i = 0; i < 16; ++i)
+                            if (d0 + i < p.D)
+                                store_elem(p.out, p.out_dtype, r * p.out_stride + d0 + i, load_elem(p.iv_table, p.iv_dtype, id * (int64_t)p.D + d0 + i));
+                    }
+                }
+            }
+        }
+        if (p.tie_count != nullptr) {
+            for (int o = 16; o; o >>= 1) my_ties += __shfl_xor_sync(0xffffffffu, my_ties, o);
+            if (lane == 0 && my_ties) atomicAdd(p.tie_count, (unsigned long long)my_ties);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------- host
+bool lsh_tc_supported(int F, int B, int D) { return F >= 1 && F <= L_FMAX && D >= 1 && D <= L_DMAX && B >= 1; }
+
+static size_t lsh_bp_bytes(int B) { return align_up((size_t)cdiv(B, L_BN) * L_BN * 192 * 2, 1024); }
+size_t lsh_tc_workspace(int B) { return lsh_bp_bytes(B) + align_up((size_t)2 * L_DMAX * cdiv(B, L_BN) * L_BN * 2, 1024) + 1024; }
+
+int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* planes, int B, const void* W, int w_dtype,
+               const oov_rows* rows, float tie_eps, uint32_t* bits_out, unsigned long long* tie_count, void* workspace,
+               size_t workspace_bytes, cudaStream_t st) {
+    OOV_REQUIRE(workspace && workspace_bytes >= lsh_tc_workspace(B), OOV_ERR_WORKSPACE, "oov_lsh_embed (tcgen05): workspace %zu < %zu",
+                workspace_bytes, lsh_tc_workspace(B));
+    char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+    __nv_bfloat16* Bp = reinterpret_cast<__nv_bfloat16*>(ws);
+    __nv_bfloat16* Wt = reinterpret_cast<__nv_bfloat16*>(ws + lsh_bp_bytes(B));
+    const int NT = (int)cdiv(B, L_BN);
+    const int64_t nb = (int64_t)NT * L_BN;
+    LshParams p{};
+    p.feat = feat; p.n_feat_rows = n_feat_rows; p.F = F; p.planes = planes; p.B = B; p.NT = NT;
+    p.ids = rows->ids; p.ids_stride = rows->ids_stride; p.n = rows->n; p.n_old = rows->n_old; p.prime_pad = rows->prime_pad;
+    p.iv_table = rows->iv_table; p.iv_dtype = rows->iv_dtype; p.out = rows->out; p.out_dtype = rows->out_dtype;
+    p.out_stride = rows->out_stride; p.D = rows->D;
+    p.wsplit = 2;                     // hi + lo bf16 pieces of the fp32 bucket table: fp32-grade sums for every output dtype
+    p.tie_eps = tie_eps; p.bits_out = bits_out; p.words = (B + 31) / 32; p.tie_count = tie_count;
+
+    const int64_t pack_threads = nb * L_DMAX > nb * 32 ? nb * L_DMAX : nb * 32;
+    lsh_pack_kernel<<<(unsigned)cdiv(pack_threads, 256), 256, 0, st>>>(planes, B, F, NT, W, w_dtype, rows->D, p.wsplit, Bp, Wt);
+    OOV_LAUNCH_CHECK("lsh_pack_kernel");
+
+    CUtensorMap tmB, tmW;
+    int rc = make_tmap_bf16_2d(&tmB, Bp, 192, (uint64_t)nb, 192 * 2, L_BN);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tmW, Wt, (uint64_t)nb, (uint64_t)(p.wsplit * L_DMAX), (uint64_t)nb * 2, L_DMAX);
+    if (rc) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tc_lsh_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM);
+        OOV_REQUIRE(e == cudaSuccess, OOV_ERR_CUDA, "cudaFuncSetAttribute(tc_lsh_embed_kernel): %s", cudaGetErrorString(e));
+        attr_done = true;
+    }
+    const int64_t n_tiles = cdiv(rows->n, L_BM);
+    const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
+    tc_lsh_embed_kernel<<<grid, L_THREADS, L_SMEM, st>>>(tmB, tmW, p);
+    OOV_LAUNCH_CHECK("tc_lsh_embed_kernel");
+    return OOV_OK;
+}
+
+}  // namespace tc
+}  // namespace oov

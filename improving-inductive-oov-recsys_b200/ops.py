@@ -143,7 +143,7 @@ def lsh_embed(feat, planes, oov_weight, ids, out=None, out_dtype=torch.float32, 
     rows, out, keep = make_rows(ids, D, out, out_dtype, n_old, iv_table, prime_pad)
     lib = _lib.load()
     bits = torch.empty((rows.n, (B + 31) // 32), dtype=torch.int32, device=feat.device) if return_bits else None
-    ws_bytes = 0 if return_bits else lib.oov_lsh_embed_workspace(rows.n, B, D, path)
+    ws_bytes = lib.oov_lsh_embed_workspace(rows.n, B, D, path)
     ws = _workspace(ws_bytes, feat.device) if ws_bytes else None
     _lib.check(lib.oov_lsh_embed(_p(feat), feat.shape[0], F, _p(planes), B, _p(oov_weight), _dt(oov_weight),
                                  C.byref(rows), float(tie_eps), _p(bits), _p(tie_count), _p(ws),

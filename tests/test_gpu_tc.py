@@ -214,3 +214,42 @@ def test_tc_score_shard_merge_equals_global():
     ref[hu, hi] = -float("inf")
     ok, msg = o.topk_sets_match(ref.cpu().numpy(), i_all.cpu().numpy(), k, rtol=1e-5, atol=1e-4)
     assert ok, msg
+
+
+@pytest.mark.parametrize("n,F,B,D,dtype", [(1000, 32, 1000, 64, torch.float32), (70_001, 24, 1000, 64, torch.bfloat16),
+                                           (513, 4, 100, 16, torch.float32), (300, 13, 3, 10, torch.float32),
+                                           (20_000, 32, 129, 64, torch.float32)])
+def test_tc_lsh_matches_simt_bits_and_embeddings(n, F, B, D, dtype):
+    """Tensor-core LSH (split-bf16 sign-projection GEMM + multi-hot x bucket-table GEMM) against the fp32 CUDA-core
+    path: identical multi-hot bits (both resolve near-zero projections with the same fp32 FMA chain), embeddings within
+    fp32 / bf16 tolerance, in-vocab rows gathered, all-zero rows NaN (lsh_embedder.py:158)."""
+    from oov_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(n + F + B + D)
+    n_old = n // 3
+    feat = torch.nn.functional.normalize(torch.randn(n, F, generator=g), dim=-1).to(DEV)
+    planes = torch.randn(B, F, generator=g).to(DEV)
+    W = (torch.randn(B, D, generator=g) * 0.1).to(DEV)
+    table = (torch.randn(n_old, D, generator=g) * 0.1).to(DEV)
+    ids = torch.randperm(n, generator=g).to(DEV)              # in-vocab and OOV rows interleaved
+    tc_t = torch.zeros(1, dtype=torch.int64, device=DEV)
+    tc_s = torch.zeros(1, dtype=torch.int64, device=DEV)
+    o_tc, b_tc = ops.lsh_embed(feat, planes, W, ids, out_dtype=dtype, n_old=n_old, iv_table=table, return_bits=True,
+                               tie_count=tc_t, path=ops.PATH_TCGEN05)
+    o_si, b_si = ops.lsh_embed(feat, planes, W, ids, out_dtype=dtype, n_old=n_old, iv_table=table, return_bits=True,
+                               tie_count=tc_s, path=ops.PATH_SIMT_FP32)
+    torch.cuda.synchronize()
+    oov = (ids >= n_old)
+    assert torch.equal(b_tc[oov], b_si[oov]), f"{(b_tc[oov] != b_si[oov]).sum().item()} words differ"
+    assert int(tc_t.item()) == int(tc_s.item())
+    a, b = o_tc.float(), o_si.float()
+    assert torch.equal(torch.isnan(a), torch.isnan(b))
+    tol = dict(rtol=1e-5, atol=1e-6) if dtype == torch.float32 else dict(rtol=2 ** -7, atol=1e-4)
+    assert torch.allclose(a[~torch.isnan(a)], b[~torch.isnan(b)], **tol), (a - b).abs().nan_to_num().max().item()
+    assert torch.equal(o_tc[~oov], o_si[~oov])                 # in-vocab rows are plain copies
+    # and against the oracle on a sample
+    sel = torch.nonzero(oov).flatten()[:64].cpu().numpy()
+    want = o.lsh_embed(feat.cpu().numpy(), ids.cpu().numpy()[sel], planes.cpu().numpy(), W.cpu().numpy())
+    got = a.cpu().numpy()[sel]
+    both = ~np.isnan(want)
+    pu.assert_close(got[both], want[both], rtol=1e-4 if dtype == torch.float32 else 2 ** -6, atol=1e-5 if dtype == torch.float32 else 1e-3,
+                    what="tc lsh vs oracle")
