@@ -6,21 +6,24 @@
 // Exact signs from bf16 tensor cores: every fp32 operand is split into three bf16 pieces (8 + 8 + 8 significand
 // bits, an exact split), and the six products that matter are laid side by side along K:
 //     A' = [x0 | x0 | x1 | x0 | x1 | x2]      B' = [p0 | p1 | p0 | p2 | p1 | p0]        (K' = 6 F, F <= 32 -> 192)
-// so one K' = 192 GEMM with fp32 accumulation reproduces the fp32 projection to ~1e-7.  Projections that land within
-// 1e-5 of zero (about 8 per million) are recomputed by the epilogue thread with the same fp32 FMA chain the CUDA-core
-// path uses (csrc/lsh.cu), so both paths give identical bits; |R| < tie_eps events are counted like there.
+// so one K' = 192 GEMM with fp32 accumulation reproduces the fp32 projection to ~1e-7 |x||p|.  Projections closer to
+// zero than 2^-17 |x| max|p| (a few per 100 000) are recomputed by the epilogue thread with the same fp32 FMA chain the
+// CUDA-core path uses (csrc/lsh.cu), so both paths give identical bits; |R| < tie_eps events are counted like there.
 //
-// Per CTA (608 threads), persistent over 128-row tiles of the id list:
-//   warps 3-18  workers : gather the tile's feature rows, split, write A' into 128B-swizzled K-major smem; per 128-plane
-//                         N tile: tcgen05.ld the projections (lane = row), pack the sign bits (bits_out word = one
-//                         32-column load), count them, write the 0/1 tile H as the next GEMM's bf16 A operand; at the
-//                         end divide the accumulated H W by the count (0/0 -> NaN like lsh_embedder.py:158) and store.
-//   warp 0      TMA     : B' tiles (128 planes x 64 K) through a 4-stage ring
-//   warp 2      TMEM alloc, then TMA of the transposed bucket-table tiles (64 d x 64 planes) through a 4-stage ring
-//   warp 1      MMA     : GEMM1 (M128 N128 K16 x 12) into one of two TMEM accumulators, GEMM2 (M128 N64 K16 x 8) one
-//                         N tile behind, accumulating H W over all N tiles in a third TMEM region.
+// Per CTA (608 threads), persistent over 128-row tiles of the id list (tiles without OOV ids are plain row copies and
+// skip the GEMMs — every role derives that from the ids with one warp vote):
+//   warps 3-18  workers : fetch the NEXT tile's feature rows into registers, then per 128-plane N tile: tcgen05.ld the
+//                         projections (lane = row), pack the sign bits (one bits_out word per 32-column load), count
+//                         them, write the 0/1 tile H back into TENSOR MEMORY (tcgen05.st, bf16 pairs) as the A operand
+//                         of the second GEMM; after the last projection split the prefetched rows into A' (128B-swizzled
+//                         K-major smem) so the tensor core starts the next tile while this one is finished:
+//                         out = (H W) / count (0/0 -> NaN like lsh_embedder.py:158).
+//   warp 0      TMA     : B' tiles (128 planes x 64 K) through a 6-stage ring (two N tiles ahead)
+//   warp 2      TMEM alloc, then TMA of the transposed bucket-table tiles (64 d x 64 planes) through an 8-stage ring
+//   warp 1      MMA     : GEMM1 (SS: M128 N128 K16 x 12) into one of two TMEM accumulators; GEMM2 (TS: A = H from TMEM,
+//                         M128 N64 K16 x 16) one N tile behind, accumulating H W over all N tiles in a third region.
+// TMEM columns: 0-255 projections (2 buffers), 256-319 H W, 320-447 H (2 buffers).
 // The fp32 bucket table is split hi + lo bf16 (two GEMM2 passes) so the sums are fp32-grade for every output dtype.
-// Row tiles without any OOV id skip the GEMMs (every role derives that from the ids with one warp vote).
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -34,15 +37,14 @@ constexpr int L_BN = 128;                 // planes per N tile
 constexpr int L_FMAX = 32;                // features (K' = 192 = 3 K blocks of 64)
 constexpr int L_KB = 3;
 constexpr int L_DMAX = 64;
-constexpr int L_BSTAGES = 4, L_WSTAGES = 4;
+constexpr int L_BSTAGES = 6, L_WSTAGES = 8;
 constexpr int L_WORK_WARP0 = 3, L_WORKERS = 16;
 constexpr int L_THREADS = (L_WORK_WARP0 + L_WORKERS) * 32;     // 608
 constexpr int L_A_BYTES = L_KB * L_BM * 128;                   // 48 KB
 constexpr int L_BT_BYTES = L_BN * 128;                         // 16 KB: one K block of one N tile of B'
-constexpr int L_H_BYTES = 2 * L_BM * 128;                      // 32 KB: H tile = 2 K blocks
 constexpr int L_WT_BYTES = L_DMAX * 128;                       // 8 KB: 64 d-rows x 64 planes
-constexpr int L_SMEM = 1024 + L_A_BYTES + L_BSTAGES * L_BT_BYTES + 2 * L_H_BYTES + L_WSTAGES * L_WT_BYTES + 5120;
-constexpr float L_NEAR = 1e-5f;           // projections closer to zero than this are recomputed in exact fp32 order
+constexpr int L_SMEM = 1024 + L_A_BYTES + L_BSTAGES * L_BT_BYTES + L_WSTAGES * L_WT_BYTES + 4096;
+constexpr float L_NEAR_REL = 7.62939453125e-6f;   // 2^-17 |x| max|p|: projections closer to zero are recomputed in exact fp32 order
 
 struct LshParams {
     const float* feat; int64_t n_feat_rows; int F;
@@ -54,13 +56,15 @@ struct LshParams {
     float tie_eps;
     uint32_t* bits_out; int words;
     unsigned long long* tie_count;
+    const float* pn_max;                               // largest plane norm (device scalar written by the pack kernel)
 };
 
 // ---------------------------------------------------------------- operand packing (once per call)
 // Bp [NT*128, 192] bf16: row b = [p0 | p1 | p0 | p2 | p1 | p0] (32 columns each; zero for f >= F and b >= B)
 // Wt [wsplit*64, NT*128] bf16: Wt[s*64 + d][b] = piece s of W[b][d] (zero padding)
 __global__ void lsh_pack_kernel(const float* __restrict__ planes, int B, int F, int NT, const void* __restrict__ W, int w_dtype,
-                                int D, int wsplit, __nv_bfloat16* __restrict__ Bp, __nv_bfloat16* __restrict__ Wt) {
+                                int D, int wsplit, __nv_bfloat16* __restrict__ Bp, __nv_bfloat16* __restrict__ Wt,
+                                float* __restrict__ pn_max) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nb = (int64_t)NT * L_BN;
     if (t < nb * 32) {
@@ -72,6 +76,9 @@ __global__ void lsh_pack_kernel(const float* __restrict__ planes, int B, int F, 
         const __nv_bfloat16 p2 = __float2bfloat16_rn(r1 - __bfloat162float(p1));
         __nv_bfloat16* row = Bp + (size_t)b * 192;
         row[f] = p0; row[32 + f] = p1; row[64 + f] = p0; row[96 + f] = p2; row[128 + f] = p1; row[160 + f] = p0;
+        float s2 = p * p;                                           // the 32 lanes of a warp hold one plane
+        for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        if (f == 0 && s2 == s2) atomicMax(reinterpret_cast<unsigned int*>(pn_max), __float_as_uint(sqrtf(s2)));
     }
     if (t < nb * L_DMAX) {
         const int d = (int)(t / nb);
@@ -109,18 +116,101 @@ __device__ __forceinline__ void tc_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
         : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (the 0/1 tile H, bf16 pairs packed along K, lane = row) comes from
+// tensor memory, where the workers put it with tcgen05.st — no shared-memory round trip for H
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// one row's 8 features (thread = (row r, part)), fetched one tile ahead
+struct Gather {
+    float x[8];
+    float n2;          // squared norm of the whole row (after the 4-lane reduction)
+};
+
+__device__ __forceinline__ void gather_load(const LshParams& p, int64_t tile, int r, int part, Gather& gth) {
+    const int64_t rr = tile * L_BM + r;
+    int64_t fr = -1;
+    if (rr < p.n) {
+        const int64_t id = p.ids[rr * p.ids_stride];
+        if (id >= p.n_old) {
+            fr = feature_row(id, p.prime_pad);
+            if (fr < 0 || fr >= p.n_feat_rows) fr = -1;               // out-of-range ids hash nothing (caller bug)
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int f = part * 8 + j;
+        gth.x[j] = (fr >= 0 && f < p.F) ? __ldg(p.feat + fr * p.F + f) : 0.f;
+        s = fmaf(gth.x[j], gth.x[j], s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    gth.n2 = s;
+}
+
+// split into three bf16 pieces and write the row's slice of A' (K block 0 = [x0 | x0], 1 = [x1 | x0], 2 = [x1 | x2])
+__device__ __forceinline__ void gather_store(unsigned char* sA, float* snorm, int r, int part, const Gather& gth) {
+    uint32_t c0[4], c1[4], c2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float a = gth.x[2 * j], b = gth.x[2 * j + 1];
+        const __nv_bfloat16 a0 = __float2bfloat16_rn(a), b0 = __float2bfloat16_rn(b);
+        const float ra = a - __bfloat162float(a0), rb = b - __bfloat162float(b0);
+        const __nv_bfloat16 a1 = __float2bfloat16_rn(ra), b1 = __float2bfloat16_rn(rb);
+        const float sa = ra - __bfloat162float(a1), sb = rb - __bfloat162float(b1);
+        c0[j] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(b0) << 16);
+        c1[j] = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+        c2[j] = pack_bf16x2(sa, sb);
+    }
+    const uint4 v0 = make_uint4(c0[0], c0[1], c0[2], c0[3]);
+    const uint4 v1 = make_uint4(c1[0], c1[1], c1[2], c1[3]);
+    const uint4 v2 = make_uint4(c2[0], c2[1], c2[2], c2[3]);
+    *reinterpret_cast<uint4*>(sA + 0 * L_BM * 128 + sw128_offset(r, part)) = v0;
+    *reinterpret_cast<uint4*>(sA + 0 * L_BM * 128 + sw128_offset(r, 4 + part)) = v0;
+    *reinterpret_cast<uint4*>(sA + 1 * L_BM * 128 + sw128_offset(r, part)) = v1;
+    *reinterpret_cast<uint4*>(sA + 1 * L_BM * 128 + sw128_offset(r, 4 + part)) = v0;
+    *reinterpret_cast<uint4*>(sA + 2 * L_BM * 128 + sw128_offset(r, part)) = v1;
+    *reinterpret_cast<uint4*>(sA + 2 * L_BM * 128 + sw128_offset(r, 4 + part)) = v2;
+    if (part == 0) snorm[r] = sqrtf(gth.n2);
+}
+
+// in-vocab-only tile: plain gather (bpr.py:111-112), 4 threads per row
+__device__ __forceinline__ void copy_iv_tile(const LshParams& p, int64_t tile, int r, int part) {
+    const int64_t rr = tile * L_BM + r;
+    if (rr >= p.n) return;
+    const int64_t id = p.ids[rr * p.ids_stride];
+    if (id >= 0 && id < p.n_old && p.iv_table != nullptr)
+        for (int d = part * 16; d < p.D && d < part * 16 + 16; ++d)
+            store_elem(p.out, p.out_dtype, rr * p.out_stride + d, load_elem(p.iv_table, p.iv_dtype, id * (int64_t)p.D + d));
+    if (p.bits_out != nullptr)
+        for (int w = part; w < p.words; w += 4) p.bits_out[rr * p.words + w] = 0u;
+}
+
 __global__ void __launch_bounds__(L_THREADS, 1)
 tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmW, const LshParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* sA = smem;                                        // 3 K blocks x [128 x 64] bf16
     unsigned char* sB = sA + L_A_BYTES;                              // ring of [128 planes x 64] tiles
-    unsigned char* sH = sB + L_BSTAGES * L_BT_BYTES;                 // 2 x (2 K blocks x [128 x 64])
-    unsigned char* sW = sH + 2 * L_H_BYTES;                          // ring of [64 d x 64 planes] tiles
+    unsigned char* sW = sB + L_BSTAGES * L_BT_BYTES;                 // ring of [64 d x 64 planes] tiles
     unsigned char* tail = sW + L_WSTAGES * L_WT_BYTES;
-    int64_t* srow = reinterpret_cast<int64_t*>(tail);                // [128] feature row or -1
-    int64_t* sid = srow + L_BM;                                      // [128] id, INT64_MIN = no such row
-    int* scnt = reinterpret_cast<int*>(sid + L_BM);                  // [4][128] popcounts per column quarter
+    float* snorm = reinterpret_cast<float*>(tail);                   // [128] feature-row norms of the current tile
+    int* scnt = reinterpret_cast<int*>(snorm + L_BM);                // [4][128] popcounts per column quarter
     uint64_t* bars = reinterpret_cast<uint64_t*>(scnt + 4 * L_BM);
     uint64_t* a_full = bars;            uint64_t* a_empty = bars + 1;
     uint64_t* b_full = bars + 2;        uint64_t* b_empty = b_full + L_BSTAGES;
@@ -152,7 +242,8 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t ACC2_COL = 256;
+    constexpr uint32_t ACC2_COL = 256;                               // 64 fp32 columns
+    constexpr uint32_t H_COL = 320;                                  // 2 x 64 columns: [128 x 128] bf16, two per column
 
     if (warp == 0) {
         // ===================== TMA: B' tiles =====================
@@ -186,15 +277,14 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        {
-            constexpr uint32_t idesc1 = make_idesc_bf16_f32(L_BM, L_BN);
-            constexpr uint32_t idesc2 = make_idesc_bf16_f32(L_BM, L_DMAX);
-            int bs = 0; uint32_t bph = 0; int ws = 0; uint32_t wph = 0;
-            int64_t g1 = 0, g2 = 0;            // N tiles issued to GEMM1 / GEMM2 since kernel start
-            int64_t T = 0;                     // row tiles with OOV ids done by this CTA
-            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                if (!tile_has_oov(p, t, lane)) continue;
-                if (lane != 0) { ++T; __syncwarp(); continue; }
+        constexpr uint32_t idesc1 = make_idesc_bf16_f32(L_BM, L_BN);
+        constexpr uint32_t idesc2 = make_idesc_bf16_f32(L_BM, L_DMAX);
+        int bs = 0; uint32_t bph = 0; int ws = 0; uint32_t wph = 0;
+        int64_t g1 = 0, g2 = 0;            // N tiles issued to GEMM1 / GEMM2 since kernel start
+        int64_t T = 0;                     // row tiles with OOV ids done by this CTA
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            if (!tile_has_oov(p, t, lane)) continue;
+            if (lane == 0) {
                 mbar_wait(a_full, (uint32_t)(T & 1));
                 tc_fence_after();
                 for (int nt = 0; nt <= NT; ++nt) {
@@ -218,7 +308,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                         if (nt == NT - 1) tc_commit(a_empty);         // A' may be rebuilt for the next row tile
                         ++g1;
                     }
-                    if (nt >= 1) {                                    // GEMM2(nt - 1): acc2 += H W
+                    if (nt >= 1) {                                    // GEMM2(nt - 1): acc2 += H W, H read from TMEM
                         const int j = nt - 1;
                         const int hb = (int)(g2 & 1);
                         mbar_wait(&h_full[hb], (uint32_t)((g2 >> 1) & 1));
@@ -228,11 +318,11 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                         for (int kk = 0; kk < WK; ++kk) {
                             mbar_wait(&w_full[ws], wph);
                             tc_fence_after();
-                            const uint64_t adesc = make_sw128_desc(smem_u32(sH + hb * L_H_BYTES + (kk & 1) * L_BM * 128));
+                            const uint32_t a_tmem = tmem_base + H_COL + (uint32_t)(hb * 64 + (kk & 1) * 32);
                             const uint64_t bdesc = make_sw128_desc(smem_u32(sW + ws * L_WT_BYTES));
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (j | kk | k) ? 1u : 0u);
+                            for (int k = 0; k < 4; ++k)               // K = 16 bf16 = 8 TMEM columns / 32 B of smem
+                                tc_mma_bf16_ts(d_tmem, a_tmem + (uint32_t)(8 * k), bdesc + (uint64_t)(2 * k), idesc2, (j | kk | k) ? 1u : 0u);
                             tc_commit(&w_empty[ws]);
                             if (++ws == L_WSTAGES) { ws = 0; wph ^= 1; }
                         }
@@ -241,9 +331,9 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                         ++g2;
                     }
                 }
-                ++T;
-                __syncwarp();
             }
+            ++T;
+            __syncwarp();
         }
     } else {
         // ===================== workers =====================
@@ -252,74 +342,41 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         const int cq = wk >> 2;                    // column quarter of every N tile
         const int row = q * 32 + lane;             // row of the tile this thread owns in the epilogues
         const int wtid = wk * 32 + lane;           // 0..511
+        const int gr = wtid >> 2, gpart = wtid & 3;   // gather role: row, 8-feature slice
         unsigned int my_ties = 0;
         int64_t g = 0, T = 0;
-        const float near = fmaxf(L_NEAR, 4.f * p.tie_eps);
-        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const float pn_max = *p.pn_max;
+
+        // first tile with OOV ids (in-vocab-only tiles on the way are plain copies)
+        int64_t t = blockIdx.x;
+        while (t < n_tiles && !tile_has_oov(p, t, lane)) { copy_iv_tile(p, t, gr, gpart); t += gridDim.x; }
+        Gather gth;
+        if (t < n_tiles) {
+            gather_load(p, t, gr, gpart, gth);
+            gather_store(sA, snorm, gr, gpart, gth);                  // a_empty: nothing has read A' yet
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+        }
+        while (t < n_tiles) {
             const int64_t row0 = t * L_BM;
-            worker_bar();                                             // previous tile's readers of srow / scnt are done
-            if (wtid < L_BM) {
-                const int64_t r = row0 + wtid;
-                int64_t id = INT64_MIN, fr = -1;
-                if (r < p.n) {
-                    id = p.ids[r * p.ids_stride];
-                    if (id >= p.n_old) {
-                        fr = feature_row(id, p.prime_pad);
-                        if (fr < 0 || fr >= p.n_feat_rows) fr = -1;   // out-of-range ids hash nothing (caller bug)
-                    }
+            worker_bar();                                             // snorm of this tile is complete; scnt of the previous one is free
+            // next tile with OOV ids: issue its gather now, it is consumed after this tile's last projection
+            int64_t tn = t + gridDim.x;
+            while (tn < n_tiles && !tile_has_oov(p, tn, lane)) { copy_iv_tile(p, tn, gr, gpart); tn += gridDim.x; }
+            if (tn < n_tiles) gather_load(p, tn, gr, gpart, gth);
+
+            int64_t my_fr = -1, my_id = INT64_MIN;
+            if (row0 + row < p.n) {
+                my_id = p.ids[(row0 + row) * p.ids_stride];
+                if (my_id >= p.n_old) {
+                    my_fr = feature_row(my_id, p.prime_pad);
+                    if (my_fr < 0 || my_fr >= p.n_feat_rows) my_fr = -1;
                 }
-                sid[wtid] = id; srow[wtid] = fr;
             }
-            worker_bar();
-            if (!tile_has_oov(p, t, lane)) {                                           // in-vocab rows only: plain gather, 4 threads per row
-                const int r = wtid >> 2, part = wtid & 3;
-                const int64_t id = sid[r];
-                if (id != INT64_MIN && id >= 0 && p.iv_table != nullptr)
-                    for (int d = part * 16; d < p.D && d < part * 16 + 16; ++d)
-                        store_elem(p.out, p.out_dtype, (row0 + r) * p.out_stride + d, load_elem(p.iv_table, p.iv_dtype, id * (int64_t)p.D + d));
-                if (p.bits_out != nullptr && row0 + r < p.n)
-                    for (int w = part; w < p.words; w += 4) p.bits_out[(row0 + r) * p.words + w] = 0u;
-                continue;
-            }
-            // ---- gather + split: thread = (row r, 8 features)
-            {
-                const int r = wtid >> 2, part = wtid & 3;
-                const int64_t fr = srow[r];
-                float x[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int f = part * 8 + j;
-                    x[j] = (fr >= 0 && f < p.F) ? __ldg(p.feat + fr * p.F + f) : 0.f;
-                }
-                uint32_t c0[4], c1[4], c2[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float a = x[2 * j], b = x[2 * j + 1];
-                    const __nv_bfloat16 a0 = __float2bfloat16_rn(a), b0 = __float2bfloat16_rn(b);
-                    const float ra = a - __bfloat162float(a0), rb = b - __bfloat162float(b0);
-                    const __nv_bfloat16 a1 = __float2bfloat16_rn(ra), b1 = __float2bfloat16_rn(rb);
-                    const float sa = ra - __bfloat162float(a1), sb = rb - __bfloat162float(b1);
-                    c0[j] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(b0) << 16);
-                    c1[j] = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
-                    c2[j] = pack_bf16x2(sa, sb);
-                }
-                mbar_wait(a_empty, (uint32_t)((T & 1) ^ 1));          // previous tile's GEMM1s have read A'
-                const uint4 v0 = make_uint4(c0[0], c0[1], c0[2], c0[3]);
-                const uint4 v1 = make_uint4(c1[0], c1[1], c1[2], c1[3]);
-                const uint4 v2 = make_uint4(c2[0], c2[1], c2[2], c2[3]);
-                // K block 0 = [x0 | x0], 1 = [x1 | x0], 2 = [x1 | x2]; 16-byte chunk (4 s + part) of row r, swizzled
-                *reinterpret_cast<uint4*>(sA + 0 * L_BM * 128 + sw128_offset(r, part)) = v0;
-                *reinterpret_cast<uint4*>(sA + 0 * L_BM * 128 + sw128_offset(r, 4 + part)) = v0;
-                *reinterpret_cast<uint4*>(sA + 1 * L_BM * 128 + sw128_offset(r, part)) = v1;
-                *reinterpret_cast<uint4*>(sA + 1 * L_BM * 128 + sw128_offset(r, 4 + part)) = v0;
-                *reinterpret_cast<uint4*>(sA + 2 * L_BM * 128 + sw128_offset(r, part)) = v1;
-                *reinterpret_cast<uint4*>(sA + 2 * L_BM * 128 + sw128_offset(r, 4 + part)) = v2;
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(a_full);
-            }
-            const int64_t my_fr = srow[row];
             const bool my_oov = my_fr >= 0;
+            // |tensor-core projection - fp32 projection| stays far below this; anything closer to zero is redone exactly
+            const float near = fmaxf(L_NEAR_REL * snorm[row] * pn_max, 4.f * p.tie_eps);
             int cnt = 0;
             // ---- per N tile: projections -> bits -> H
             for (int nt = 0; nt < NT; ++nt, ++g) {
@@ -334,47 +391,53 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc1_empty[buf]);
                 const int b0 = nt * L_BN + cq * 32;                   // plane of column 0
-                uint32_t word = 0u;
-                bool any_near = false;
+                uint32_t word = 0u, nearw = 0u;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float r = __uint_as_float(v[j]);
                     word |= (r < 0.f ? 0u : 1u) << j;                 // torch_hash.py:57-59: -0, +0, NaN -> 1
-                    any_near |= fabsf(r) < near;
+                    nearw |= (fabsf(r) < near ? 1u : 0u) << j;
                 }
-                if (any_near && my_oov) {                             // rare: redo in the fp32 FMA order of csrc/lsh.cu
-                    for (int j = 0; j < 32; ++j) {
-                        const int b = b0 + j;
-                        if (b >= p.B || !(fabsf(__uint_as_float(v[j])) < near)) continue;
-                        const float* xr = p.feat + my_fr * p.F;
-                        const float* pr = p.planes + (size_t)b * p.F;
-                        float a = 0.f;
-                        for (int f = 0; f < p.F; ++f) a = fmaf(__ldg(xr + f), __ldg(pr + f), a);
-                        word = (word & ~(1u << j)) | ((a < 0.f ? 0u : 1u) << j);
-                        if (fabsf(a) < p.tie_eps) ++my_ties;
-                    }
+                if (b0 + 32 > p.B) {                                  // planes past B do not exist
+                    const uint32_t valid = (b0 >= p.B) ? 0u : ((1u << (p.B - b0)) - 1u);
+                    word &= valid; nearw &= valid;
                 }
-                if (b0 + 32 > p.B) word &= (b0 >= p.B) ? 0u : ((1u << (p.B - b0)) - 1u);   // planes past B do not exist
-                if (!my_oov) word = 0u;
+                if (!my_oov) { word = 0u; nearw = 0u; }
+                while (nearw) {                                       // rare: redo in the fp32 FMA order of csrc/lsh.cu
+                    const int j = __ffs(nearw) - 1;
+                    nearw &= nearw - 1;
+                    const float* xr = p.feat + my_fr * p.F;
+                    const float* pr = p.planes + (size_t)(b0 + j) * p.F;
+                    float a = 0.f;
+                    for (int f = 0; f < p.F; ++f) a = fmaf(__ldg(xr + f), __ldg(pr + f), a);
+                    word = (word & ~(1u << j)) | ((a < 0.f ? 0u : 1u) << j);
+                    if (fabsf(a) < p.tie_eps) ++my_ties;
+                }
                 cnt += __popc(word);
                 if (p.bits_out != nullptr && row0 + row < p.n && nt * 4 + cq < p.words)
                     p.bits_out[(row0 + row) * p.words + nt * 4 + cq] = word;
-                // H tile: 32 bf16 0/1 values = 4 chunks of 16 B at K block (cq >> 1), chunks (cq & 1) * 4 ..
-                mbar_wait(&h_empty[buf], par ^ 1);                    // GEMM2 of the previous use of this buffer is done
-                unsigned char* hk = sH + buf * L_H_BYTES + (cq >> 1) * L_BM * 128;
+                // H: 32 bf16 0/1 values = 16 TMEM columns of this row
+                uint32_t hw[16];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t w4[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint32_t two = (word >> (c * 8 + i * 2)) & 3u;
-                        w4[i] = ((two & 1u) ? 0x3F80u : 0u) | ((two & 2u) ? 0x3F800000u : 0u);
-                    }
-                    *reinterpret_cast<uint4*>(hk + sw128_offset(row, (cq & 1) * 4 + c)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                for (int i = 0; i < 16; ++i) {
+                    const uint32_t two = (word >> (2 * i)) & 3u;
+                    hw[i] = ((two & 1u) ? 0x3F80u : 0u) | ((two & 2u) ? 0x3F800000u : 0u);
                 }
-                fence_proxy_async_smem();
+                mbar_wait(&h_empty[buf], par ^ 1);                    // GEMM2 of the previous use of this buffer is done
+                tc_fence_after();
+                tc_st_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + H_COL + (uint32_t)(buf * 64 + cq * 16), hw);
+                tc_wait_st();
+                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&h_full[buf]);
+            }
+            // ---- A' of the next tile (its features arrived long ago), so the tensor core can go on while we finish
+            if (tn < n_tiles) {
+                mbar_wait(a_empty, (uint32_t)(T & 1));                // this tile's GEMM1s have read A'
+                gather_store(sA, snorm, gr, gpart, gth);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full);
             }
             // ---- final: out = (H W) / count
             scnt[cq * L_BM + row] = cnt;
@@ -408,15 +471,13 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                         for (int i = 0; i < 16; ++i)
                             if (d0 + i < p.D) store_elem(p.out, p.out_dtype, r * p.out_stride + d0 + i, __uint_as_float(a[i]) / den);
                     }
-                } else {
-                    const int64_t id = sid[row];
-                    if (id != INT64_MIN && id >= 0 && id < p.n_old && p.iv_table != nullptr) {   // in-vocab gather (bpr.py:111-112)
-                        for (int i = 0; i < 16; ++i)
-                            if (d0 + i < p.D)
-                                store_elem(p.out, p.out_dtype, r * p.out_stride + d0 + i, load_elem(p.iv_table, p.iv_dtype, id * (int64_t)p.D + d0 + i));
-                    }
+                } else if (my_id != INT64_MIN && my_id >= 0 && my_id < p.n_old && p.iv_table != nullptr) {
+                    for (int i = 0; i < 16; ++i)                      // in-vocab gather (bpr.py:111-112)
+                        if (d0 + i < p.D)
+                            store_elem(p.out, p.out_dtype, r * p.out_stride + d0 + i, load_elem(p.iv_table, p.iv_dtype, my_id * (int64_t)p.D + d0 + i));
                 }
             }
+            t = tn;
         }
         if (p.tie_count != nullptr) {
             for (int o = 16; o; o >>= 1) my_ties += __shfl_xor_sync(0xffffffffu, my_ties, o);
@@ -436,7 +497,8 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
 bool lsh_tc_supported(int F, int B, int D) { return F >= 1 && F <= L_FMAX && D >= 1 && D <= L_DMAX && B >= 1; }
 
 static size_t lsh_bp_bytes(int B) { return align_up((size_t)cdiv(B, L_BN) * L_BN * 192 * 2, 1024); }
-size_t lsh_tc_workspace(int B) { return lsh_bp_bytes(B) + align_up((size_t)2 * L_DMAX * cdiv(B, L_BN) * L_BN * 2, 1024) + 1024; }
+static size_t lsh_wt_bytes(int B) { return align_up((size_t)2 * L_DMAX * cdiv(B, L_BN) * L_BN * 2, 1024); }
+size_t lsh_tc_workspace(int B) { return lsh_bp_bytes(B) + lsh_wt_bytes(B) + 256 + 1024; }
 
 int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* planes, int B, const void* W, int w_dtype,
                const oov_rows* rows, float tie_eps, uint32_t* bits_out, unsigned long long* tie_count, void* workspace,
@@ -446,6 +508,9 @@ int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* plane
     char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
     __nv_bfloat16* Bp = reinterpret_cast<__nv_bfloat16*>(ws);
     __nv_bfloat16* Wt = reinterpret_cast<__nv_bfloat16*>(ws + lsh_bp_bytes(B));
+    float* pn_max = reinterpret_cast<float*>(ws + lsh_bp_bytes(B) + lsh_wt_bytes(B));
+    cudaError_t ce = cudaMemsetAsync(pn_max, 0, 4, st);
+    OOV_REQUIRE(ce == cudaSuccess, OOV_ERR_CUDA, "cudaMemsetAsync(pn_max): %s", cudaGetErrorString(ce));
     const int NT = (int)cdiv(B, L_BN);
     const int64_t nb = (int64_t)NT * L_BN;
     LshParams p{};
@@ -454,10 +519,10 @@ int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* plane
     p.iv_table = rows->iv_table; p.iv_dtype = rows->iv_dtype; p.out = rows->out; p.out_dtype = rows->out_dtype;
     p.out_stride = rows->out_stride; p.D = rows->D;
     p.wsplit = 2;                     // hi + lo bf16 pieces of the fp32 bucket table: fp32-grade sums for every output dtype
-    p.tie_eps = tie_eps; p.bits_out = bits_out; p.words = (B + 31) / 32; p.tie_count = tie_count;
+    p.tie_eps = tie_eps; p.bits_out = bits_out; p.words = (B + 31) / 32; p.tie_count = tie_count; p.pn_max = pn_max;
 
     const int64_t pack_threads = nb * L_DMAX > nb * 32 ? nb * L_DMAX : nb * 32;
-    lsh_pack_kernel<<<(unsigned)cdiv(pack_threads, 256), 256, 0, st>>>(planes, B, F, NT, W, w_dtype, rows->D, p.wsplit, Bp, Wt);
+    lsh_pack_kernel<<<(unsigned)cdiv(pack_threads, 256), 256, 0, st>>>(planes, B, F, NT, W, w_dtype, rows->D, p.wsplit, Bp, Wt, pn_max);
     OOV_LAUNCH_CHECK("lsh_pack_kernel");
 
     CUtensorMap tmB, tmW;
