@@ -25,6 +25,7 @@
 // TMEM columns: 0-255 projections (2 buffers), 256-319 H W, 320-447 H (2 buffers).
 // The fp32 bucket table is split hi + lo bf16 (two GEMM2 passes) so the sums are fp32-grade for every output dtype.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -34,17 +35,17 @@ namespace tc {
 
 constexpr int L_BM = 128;                 // rows per tile
 constexpr int L_BN = 128;                 // planes per N tile
-constexpr int L_FMAX = 32;                // features (K' = 192 = 3 K blocks of 64)
-constexpr int L_KB = 3;
+constexpr int L_FMAX = 32;                // features (K' = 4 F = 128 = 2 K blocks of 64)
+constexpr int L_KB = 2;
 constexpr int L_DMAX = 64;
-constexpr int L_BSTAGES = 6, L_WSTAGES = 8;
+constexpr int L_BSTAGES = 8, L_WSTAGES = 8;
 constexpr int L_WORK_WARP0 = 3, L_WORKERS = 16;
 constexpr int L_THREADS = (L_WORK_WARP0 + L_WORKERS) * 32;     // 608
-constexpr int L_A_BYTES = L_KB * L_BM * 128;                   // 48 KB
 constexpr int L_BT_BYTES = L_BN * 128;                         // 16 KB: one K block of one N tile of B'
 constexpr int L_WT_BYTES = L_DMAX * 128;                       // 8 KB: 64 d-rows x 64 planes
-constexpr int L_SMEM = 1024 + L_A_BYTES + L_BSTAGES * L_BT_BYTES + L_WSTAGES * L_WT_BYTES + 4096;
-constexpr float L_NEAR_REL = 7.62939453125e-6f;   // 2^-17 |x| max|p|: projections closer to zero are recomputed in exact fp32 order
+constexpr int L_SMEM = 1024 + L_BSTAGES * L_BT_BYTES + L_WSTAGES * L_WT_BYTES + 6144;
+constexpr float L_NEAR_REL = 3.0517578125e-5f;    // 2^-15 |x| max|p| (4 x the bound on the dropped split terms): projections
+                                                  // closer to zero are recomputed in exact fp32 order
 
 struct LshParams {
     const float* feat; int64_t n_feat_rows; int F;
@@ -60,10 +61,10 @@ struct LshParams {
 };
 
 // ---------------------------------------------------------------- operand packing (once per call)
-// Bp [NT*128, 192] bf16: row b = [p0 | p1 | p0 | p2 | p1 | p0] (32 columns each; zero for f >= F and b >= B)
-// Wt [wsplit*64, NT*128] bf16: Wt[s*64 + d][b] = piece s of W[b][d] (zero padding)
+// Bp [NT*128, 128] bf16: row b = [p0 | p1 | p0 | p1] (32 columns each; zero for f >= F and b >= B)
+// Wt [wsplit*64, NT*128] fp16: Wt[s*64 + d][b] = piece s of W[b][d] (zero padding)
 __global__ void lsh_pack_kernel(const float* __restrict__ planes, int B, int F, int NT, const void* __restrict__ W, int w_dtype,
-                                int D, int wsplit, __nv_bfloat16* __restrict__ Bp, __nv_bfloat16* __restrict__ Wt,
+                                int D, int wsplit, __nv_bfloat16* __restrict__ Bp, __half* __restrict__ Wt,
                                 float* __restrict__ pn_max) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nb = (int64_t)NT * L_BN;
@@ -73,9 +74,8 @@ __global__ void lsh_pack_kernel(const float* __restrict__ planes, int B, int F, 
         const __nv_bfloat16 p0 = __float2bfloat16_rn(p);
         const float r1 = p - __bfloat162float(p0);
         const __nv_bfloat16 p1 = __float2bfloat16_rn(r1);
-        const __nv_bfloat16 p2 = __float2bfloat16_rn(r1 - __bfloat162float(p1));
-        __nv_bfloat16* row = Bp + (size_t)b * 192;
-        row[f] = p0; row[32 + f] = p1; row[64 + f] = p0; row[96 + f] = p2; row[128 + f] = p1; row[160 + f] = p0;
+        __nv_bfloat16* row = Bp + (size_t)b * 128;
+        row[f] = p0; row[32 + f] = p1; row[64 + f] = p0; row[96 + f] = p1;
         float s2 = p * p;                                           // the 32 lanes of a warp hold one plane
         for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
         if (f == 0 && s2 == s2) atomicMax(reinterpret_cast<unsigned int*>(pn_max), __float_as_uint(sqrtf(s2)));
@@ -84,9 +84,9 @@ __global__ void lsh_pack_kernel(const float* __restrict__ planes, int B, int F, 
         const int d = (int)(t / nb);
         const int64_t b = t - (int64_t)d * nb;
         const float w = (b < B && d < D) ? load_elem(W, w_dtype, b * D + d) : 0.f;
-        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+        const __half hi = __float2half_rn(w);
         Wt[(size_t)d * nb + b] = hi;
-        if (wsplit == 2) Wt[(size_t)(L_DMAX + d) * nb + b] = __float2bfloat16_rn(w - __bfloat162float(hi));
+        if (wsplit == 2) Wt[(size_t)(L_DMAX + d) * nb + b] = __float2half_rn(w - __half2float(hi));
     }
 }
 
@@ -135,10 +135,14 @@ __device__ __forceinline__ void tc_st_32x16(uint32_t taddr, const uint32_t (&v)[
 }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// one row's 8 features (thread = (row r, part)), fetched one tile ahead
+__device__ __forceinline__ void tc_st_32x4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// 8 features of one row (thread = (row, slice)), fetched one tile ahead
 struct Gather {
     float x[8];
-    float n2;          // squared norm of the whole row (after the 4-lane reduction)
+    float n2;          // this slice's share of the squared row norm
 };
 
 __device__ __forceinline__ void gather_load(const LshParams& p, int64_t tile, int r, int part, Gather& gth) {
@@ -158,35 +162,25 @@ __device__ __forceinline__ void gather_load(const LshParams& p, int64_t tile, in
         gth.x[j] = (fr >= 0 && f < p.F) ? __ldg(p.feat + fr * p.F + f) : 0.f;
         s = fmaf(gth.x[j], gth.x[j], s);
     }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
     gth.n2 = s;
 }
 
-// split into three bf16 pieces and write the row's slice of A' (K block 0 = [x0 | x0], 1 = [x1 | x0], 2 = [x1 | x2])
-__device__ __forceinline__ void gather_store(unsigned char* sA, float* snorm, int r, int part, const Gather& gth) {
-    uint32_t c0[4], c1[4], c2[4];
+// split into two bf16 pieces and write the slice of A' = [x0 | x0 | x1 | x1] into this row's TMEM lane:
+// K element k lives in column k / 2, so the 8 features are 4 columns at offset 4 * part of each 16-column segment
+__device__ __forceinline__ void gather_store(uint32_t a_lane, float* sn2, int r, int part, const Gather& gth) {
+    uint32_t c0[4], c1[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const float a = gth.x[2 * j], b = gth.x[2 * j + 1];
         const __nv_bfloat16 a0 = __float2bfloat16_rn(a), b0 = __float2bfloat16_rn(b);
-        const float ra = a - __bfloat162float(a0), rb = b - __bfloat162float(b0);
-        const __nv_bfloat16 a1 = __float2bfloat16_rn(ra), b1 = __float2bfloat16_rn(rb);
-        const float sa = ra - __bfloat162float(a1), sb = rb - __bfloat162float(b1);
         c0[j] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(b0) << 16);
-        c1[j] = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
-        c2[j] = pack_bf16x2(sa, sb);
+        c1[j] = pack_bf16x2(a - __bfloat162float(a0), b - __bfloat162float(b0));
     }
-    const uint4 v0 = make_uint4(c0[0], c0[1], c0[2], c0[3]);
-    const uint4 v1 = make_uint4(c1[0], c1[1], c1[2], c1[3]);
-    const uint4 v2 = make_uint4(c2[0], c2[1], c2[2], c2[3]);
-    *reinterpret_cast<uint4*>(sA + 0 * L_BM * 128 + sw128_offset(r, part)) = v0;
-    *reinterpret_cast<uint4*>(sA + 0 * L_BM * 128 + sw128_offset(r, 4 + part)) = v0;
-    *reinterpret_cast<uint4*>(sA + 1 * L_BM * 128 + sw128_offset(r, part)) = v1;
-    *reinterpret_cast<uint4*>(sA + 1 * L_BM * 128 + sw128_offset(r, 4 + part)) = v0;
-    *reinterpret_cast<uint4*>(sA + 2 * L_BM * 128 + sw128_offset(r, part)) = v1;
-    *reinterpret_cast<uint4*>(sA + 2 * L_BM * 128 + sw128_offset(r, 4 + part)) = v2;
-    if (part == 0) snorm[r] = sqrtf(gth.n2);
+    tc_st_32x4(a_lane + 0 * 16 + part * 4, c0[0], c0[1], c0[2], c0[3]);
+    tc_st_32x4(a_lane + 1 * 16 + part * 4, c0[0], c0[1], c0[2], c0[3]);
+    tc_st_32x4(a_lane + 2 * 16 + part * 4, c1[0], c1[1], c1[2], c1[3]);
+    tc_st_32x4(a_lane + 3 * 16 + part * 4, c1[0], c1[1], c1[2], c1[3]);
+    sn2[part * L_BM + r] = gth.n2;
 }
 
 // in-vocab-only tile: plain gather (bpr.py:111-112), 4 threads per row
@@ -205,12 +199,11 @@ __global__ void __launch_bounds__(L_THREADS, 1)
 tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmW, const LshParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char* sA = smem;                                        // 3 K blocks x [128 x 64] bf16
-    unsigned char* sB = sA + L_A_BYTES;                              // ring of [128 planes x 64] tiles
+    unsigned char* sB = smem;                                        // ring of [128 planes x 64] tiles
     unsigned char* sW = sB + L_BSTAGES * L_BT_BYTES;                 // ring of [64 d x 64 planes] tiles
     unsigned char* tail = sW + L_WSTAGES * L_WT_BYTES;
-    float* snorm = reinterpret_cast<float*>(tail);                   // [128] feature-row norms of the current tile
-    int* scnt = reinterpret_cast<int*>(snorm + L_BM);                // [4][128] popcounts per column quarter
+    float* sn2 = reinterpret_cast<float*>(tail);                     // [4][128] squared-norm shares of the current tile's rows
+    int* scnt = reinterpret_cast<int*>(sn2 + 4 * L_BM);              // [4][128] popcounts per column quarter
     uint64_t* bars = reinterpret_cast<uint64_t*>(scnt + 4 * L_BM);
     uint64_t* a_full = bars;            uint64_t* a_empty = bars + 1;
     uint64_t* b_full = bars + 2;        uint64_t* b_empty = b_full + L_BSTAGES;
@@ -243,7 +236,8 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     constexpr uint32_t ACC2_COL = 256;                               // 64 fp32 columns
-    constexpr uint32_t H_COL = 320;                                  // 2 x 64 columns: [128 x 128] bf16, two per column
+    constexpr uint32_t H_COL = 320;                                  // 2 x 64 columns: [128 x 128] fp16, two per column
+    constexpr uint32_t A_COL = 448;                                  // 64 columns: A' [128 x 128] bf16, two per column
 
     if (warp == 0) {
         // ===================== TMA: B' tiles =====================
@@ -278,7 +272,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc1 = make_idesc_bf16_f32(L_BM, L_BN);
-        constexpr uint32_t idesc2 = make_idesc_bf16_f32(L_BM, L_DMAX);
+        constexpr uint32_t idesc2 = make_idesc_bf16_f32(L_BM, L_DMAX) & ~((7u << 7) | (7u << 10));   // A, B = fp16 (format 0)
         int bs = 0; uint32_t bph = 0; int ws = 0; uint32_t wph = 0;
         int64_t g1 = 0, g2 = 0;            // N tiles issued to GEMM1 / GEMM2 since kernel start
         int64_t T = 0;                     // row tiles with OOV ids done by this CTA
@@ -296,11 +290,11 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                         for (int kb = 0; kb < L_KB; ++kb) {
                             mbar_wait(&b_full[bs], bph);
                             tc_fence_after();
-                            const uint64_t adesc = make_sw128_desc(smem_u32(sA + kb * L_BM * 128));
+                            const uint32_t a_tmem = tmem_base + A_COL + (uint32_t)(kb * 32);
                             const uint64_t bdesc = make_sw128_desc(smem_u32(sB + bs * L_BT_BYTES));
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, (kb | k) ? 1u : 0u);
+                            for (int k = 0; k < 4; ++k)               // A' from TMEM: K = 16 bf16 = 8 columns
+                                tc_mma_bf16_ts(d_tmem, a_tmem + (uint32_t)(8 * k), bdesc + (uint64_t)(2 * k), idesc1, (kb | k) ? 1u : 0u);
                             tc_commit(&b_empty[bs]);
                             if (++bs == L_BSTAGES) { bs = 0; bph ^= 1; }
                         }
@@ -342,7 +336,8 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         const int cq = wk >> 2;                    // column quarter of every N tile
         const int row = q * 32 + lane;             // row of the tile this thread owns in the epilogues
         const int wtid = wk * 32 + lane;           // 0..511
-        const int gr = wtid >> 2, gpart = wtid & 3;   // gather role: row, 8-feature slice
+        const int gr = wtid >> 2, gpart = wtid & 3;   // in-vocab copy role: row, 16-column slice
+        const uint32_t a_lane = tmem_base + ((uint32_t)(q * 32) << 16) + A_COL;
         unsigned int my_ties = 0;
         int64_t g = 0, T = 0;
         const float pn_max = *p.pn_max;
@@ -352,19 +347,20 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         while (t < n_tiles && !tile_has_oov(p, t, lane)) { copy_iv_tile(p, t, gr, gpart); t += gridDim.x; }
         Gather gth;
         if (t < n_tiles) {
-            gather_load(p, t, gr, gpart, gth);
-            gather_store(sA, snorm, gr, gpart, gth);                  // a_empty: nothing has read A' yet
-            fence_proxy_async_smem();
+            gather_load(p, t, row, cq, gth);
+            gather_store(a_lane, sn2, row, cq, gth);                  // a_empty: nothing has read A' yet
+            tc_wait_st();
+            tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(a_full);
         }
         while (t < n_tiles) {
             const int64_t row0 = t * L_BM;
-            worker_bar();                                             // snorm of this tile is complete; scnt of the previous one is free
+            worker_bar();                                             // sn2 of this tile is complete; scnt of the previous one is free
             // next tile with OOV ids: issue its gather now, it is consumed after this tile's last projection
             int64_t tn = t + gridDim.x;
             while (tn < n_tiles && !tile_has_oov(p, tn, lane)) { copy_iv_tile(p, tn, gr, gpart); tn += gridDim.x; }
-            if (tn < n_tiles) gather_load(p, tn, gr, gpart, gth);
+            if (tn < n_tiles) gather_load(p, tn, row, cq, gth);
 
             int64_t my_fr = -1, my_id = INT64_MIN;
             if (row0 + row < p.n) {
@@ -376,7 +372,8 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             }
             const bool my_oov = my_fr >= 0;
             // |tensor-core projection - fp32 projection| stays far below this; anything closer to zero is redone exactly
-            const float near = fmaxf(L_NEAR_REL * snorm[row] * pn_max, 4.f * p.tie_eps);
+            const float xnorm = sqrtf(sn2[row] + sn2[L_BM + row] + sn2[2 * L_BM + row] + sn2[3 * L_BM + row]);
+            const float near = fmaxf(L_NEAR_REL * xnorm * pn_max, 4.f * p.tie_eps);
             int cnt = 0;
             // ---- per N tile: projections -> bits -> H
             for (int nt = 0; nt < NT; ++nt, ++g) {
@@ -416,12 +413,12 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                 cnt += __popc(word);
                 if (p.bits_out != nullptr && row0 + row < p.n && nt * 4 + cq < p.words)
                     p.bits_out[(row0 + row) * p.words + nt * 4 + cq] = word;
-                // H: 32 bf16 0/1 values = 16 TMEM columns of this row
+                // H: 32 fp16 0/1 values = 16 TMEM columns of this row
                 uint32_t hw[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const uint32_t two = (word >> (2 * i)) & 3u;
-                    hw[i] = ((two & 1u) ? 0x3F80u : 0u) | ((two & 2u) ? 0x3F800000u : 0u);
+                    hw[i] = ((two & 1u) ? 0x3C00u : 0u) | ((two & 2u) ? 0x3C000000u : 0u);
                 }
                 mbar_wait(&h_empty[buf], par ^ 1);                    // GEMM2 of the previous use of this buffer is done
                 tc_fence_after();
@@ -434,8 +431,10 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             // ---- A' of the next tile (its features arrived long ago), so the tensor core can go on while we finish
             if (tn < n_tiles) {
                 mbar_wait(a_empty, (uint32_t)(T & 1));                // this tile's GEMM1s have read A'
-                gather_store(sA, snorm, gr, gpart, gth);
-                fence_proxy_async_smem();
+                tc_fence_after();
+                gather_store(a_lane, sn2, row, cq, gth);
+                tc_wait_st();
+                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a_full);
             }
@@ -496,7 +495,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
 // ---------------------------------------------------------------- host
 bool lsh_tc_supported(int F, int B, int D) { return F >= 1 && F <= L_FMAX && D >= 1 && D <= L_DMAX && B >= 1; }
 
-static size_t lsh_bp_bytes(int B) { return align_up((size_t)cdiv(B, L_BN) * L_BN * 192 * 2, 1024); }
+static size_t lsh_bp_bytes(int B) { return align_up((size_t)cdiv(B, L_BN) * L_BN * 128 * 2, 1024); }
 static size_t lsh_wt_bytes(int B) { return align_up((size_t)2 * L_DMAX * cdiv(B, L_BN) * L_BN * 2, 1024); }
 size_t lsh_tc_workspace(int B) { return lsh_bp_bytes(B) + lsh_wt_bytes(B) + 256 + 1024; }
 
@@ -507,7 +506,7 @@ int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* plane
                 workspace_bytes, lsh_tc_workspace(B));
     char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
     __nv_bfloat16* Bp = reinterpret_cast<__nv_bfloat16*>(ws);
-    __nv_bfloat16* Wt = reinterpret_cast<__nv_bfloat16*>(ws + lsh_bp_bytes(B));
+    __half* Wt = reinterpret_cast<__half*>(ws + lsh_bp_bytes(B));
     float* pn_max = reinterpret_cast<float*>(ws + lsh_bp_bytes(B) + lsh_wt_bytes(B));
     cudaError_t ce = cudaMemsetAsync(pn_max, 0, 4, st);
     OOV_REQUIRE(ce == cudaSuccess, OOV_ERR_CUDA, "cudaMemsetAsync(pn_max): %s", cudaGetErrorString(ce));
@@ -518,7 +517,7 @@ int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* plane
     p.ids = rows->ids; p.ids_stride = rows->ids_stride; p.n = rows->n; p.n_old = rows->n_old; p.prime_pad = rows->prime_pad;
     p.iv_table = rows->iv_table; p.iv_dtype = rows->iv_dtype; p.out = rows->out; p.out_dtype = rows->out_dtype;
     p.out_stride = rows->out_stride; p.D = rows->D;
-    p.wsplit = 2;                     // hi + lo bf16 pieces of the fp32 bucket table: fp32-grade sums for every output dtype
+    p.wsplit = rows->out_dtype == OOV_F32 ? 2 : 1;   // fp16 hi (+ lo) pieces of the fp32 bucket table: 2^-12 (2^-23) relative
     p.tie_eps = tie_eps; p.bits_out = bits_out; p.words = (B + 31) / 32; p.tie_count = tie_count; p.pn_max = pn_max;
 
     const int64_t pack_threads = nb * L_DMAX > nb * 32 ? nb * L_DMAX : nb * 32;
@@ -526,7 +525,7 @@ int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* plane
     OOV_LAUNCH_CHECK("lsh_pack_kernel");
 
     CUtensorMap tmB, tmW;
-    int rc = make_tmap_bf16_2d(&tmB, Bp, 192, (uint64_t)nb, 192 * 2, L_BN);
+    int rc = make_tmap_bf16_2d(&tmB, Bp, 128, (uint64_t)nb, 128 * 2, L_BN);
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&tmW, Wt, (uint64_t)nb, (uint64_t)(p.wsplit * L_DMAX), (uint64_t)nb * 2, L_DMAX);
     if (rc) return rc;
