@@ -1,29 +1,33 @@
-// LSH OOV embedder on the tensor cores: sign-projection GEMM -> bit-pack -> multi-hot x bucket-table GEMM -> mean.
+// LSH OOV embedder on the tensor cores: sign-projection GEMM -> signs -> multi-hot x bucket-table GEMM -> mean.
 //
 // Replaces inductive/torch_hash.py:55-60 (R = X P^T, bit = !(R < 0)) and inductive/lsh_embedder.py:141-179
-// (out = (H W) / H.sum(1)) in ONE kernel: neither R [n, B] fp32 nor H [n, B] ever exist in HBM.
+// (out = (H W) / H.sum(1)) in ONE kernel: neither R [n, B] fp32 nor H [n, B] ever exist in HBM or shared memory.
 //
-// Exact signs from bf16 tensor cores: every fp32 operand is split into three bf16 pieces (8 + 8 + 8 significand
-// bits, an exact split), and the six products that matter are laid side by side along K:
-//     A' = [x0 | x0 | x1 | x0 | x1 | x2]      B' = [p0 | p1 | p0 | p2 | p1 | p0]        (K' = 6 F, F <= 32 -> 192)
-// so one K' = 192 GEMM with fp32 accumulation reproduces the fp32 projection to ~1e-7 |x||p|.  Projections closer to
-// zero than 2^-17 |x| max|p| (a few per 100 000) are recomputed by the epilogue thread with the same fp32 FMA chain the
-// CUDA-core path uses (csrc/lsh.cu), so both paths give identical bits; |R| < tie_eps events are counted like there.
+// Exact signs from bf16 tensor cores: x = x0 + x1 + (<= 2^-18 |x|), p likewise (bf16 pieces), and the three products
+// that matter sit side by side along K:
+//     A' = [x0 | x0 | x1]      B' = [p0 | p1 | p0]        (K' = 3 F, F <= 32 -> 96)
+// The dropped terms are bounded by 1.5 * 2^-17 |x||p|; projections closer to zero than 2^-16 |x| max|p| (about 1 per
+// 10 000) are recomputed by the epilogue thread with the fp32 FMA chain of the CUDA-core path (csrc/lsh.cu), so both
+// paths give identical bits, and |R| < tie_eps events are counted like there.
 //
-// Per CTA (608 threads), persistent over 128-row tiles of the id list (tiles without OOV ids are plain row copies and
+// Second GEMM without popcounts or masks: the epilogue writes S' = 2H - 1 (+-1 in fp16: the sign bit of R under a
+// constant) and the bucket table gets one extra column of ones (zero for planes >= B), so
+//     S' [W | 1] = [2 H W - colsum(W) | 2 count - B]   ->   out = (acc + colsum(W)) / (acc_ones + B)
+// with 0 / 0 -> NaN like lsh_embedder.py:158.  W is split into fp16 hi (+ lo for fp32 outputs) pieces.
+//
+// Per CTA (640 threads), persistent over 128-row tiles of the id list (tiles without OOV ids are plain row copies and
 // skip the GEMMs — every role derives that from the ids with one warp vote):
-//   warps 3-18  workers : fetch the NEXT tile's feature rows into registers, then per 128-plane N tile: tcgen05.ld the
-//                         projections (lane = row), pack the sign bits (one bits_out word per 32-column load), count
-//                         them, write the 0/1 tile H back into TENSOR MEMORY (tcgen05.st, bf16 pairs) as the A operand
-//                         of the second GEMM; after the last projection split the prefetched rows into A' (128B-swizzled
-//                         K-major smem) so the tensor core starts the next tile while this one is finished:
-//                         out = (H W) / count (0/0 -> NaN like lsh_embedder.py:158).
-//   warp 0      TMA     : B' tiles (128 planes x 64 K) through a 6-stage ring (two N tiles ahead)
-//   warp 2      TMEM alloc, then TMA of the transposed bucket-table tiles (64 d x 64 planes) through an 8-stage ring
-//   warp 1      MMA     : GEMM1 (SS: M128 N128 K16 x 12) into one of two TMEM accumulators; GEMM2 (TS: A = H from TMEM,
-//                         M128 N64 K16 x 16) one N tile behind, accumulating H W over all N tiles in a third region.
-// TMEM columns: 0-255 projections (2 buffers), 256-319 H W, 320-447 H (2 buffers).
-// The fp32 bucket table is split hi + lo bf16 (two GEMM2 passes) so the sums are fp32-grade for every output dtype.
+//   warps 4-19  workers : fetch the NEXT tile's feature rows into registers; per 128-plane N tile: tcgen05.ld the
+//                         projections (lane = row), min|R| tree against the near-zero threshold, two instructions
+//                         per pair of scores (PRMT + LOP3) to form the fp16 +-1 words, tcgen05.st them back into
+//                         TENSOR MEMORY as the A operand of the second GEMM; after the last projection split the
+//                         prefetched rows into A' (also in TMEM) so the tensor core starts the next tile at once.
+//   warp 0      TMA     : B' tiles (128 planes x 128 K) through a 4-stage ring (one mbarrier per N tile)
+//   warp 2      TMEM alloc, then TMA of the transposed bucket-table tiles (80 rows x 128 planes) through a 3-stage ring
+//   warp 1      MMA 1   : GEMM1 (TS: A' from TMEM, M128 N128 K16 x 6) into one of two TMEM accumulators
+//   warp 3      MMA 2   : GEMM2 (TS: A = S' from TMEM, M128 N80 K16 x 8 per piece), accumulating over all N tiles.
+//                         Two issuing threads: each spends ~100 cycles per mbarrier wait, one thread could not keep up.
+// TMEM columns: 0-255 projections (2 buffers), 256-335 [S' W | S' 1], 336-463 S' (2 buffers), 464-511 A'.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -35,17 +39,16 @@ namespace tc {
 
 constexpr int L_BM = 128;                 // rows per tile
 constexpr int L_BN = 128;                 // planes per N tile
-constexpr int L_FMAX = 32;                // features (K' = 4 F = 128 = 2 K blocks of 64)
-constexpr int L_KB = 2;
+constexpr int L_FMAX = 32;                // features (K' = 3 F = 96: K block 0 full, K block 1 half used)
 constexpr int L_DMAX = 64;
-constexpr int L_BSTAGES = 8, L_WSTAGES = 8;
-constexpr int L_WORK_WARP0 = 3, L_WORKERS = 16;
-constexpr int L_THREADS = (L_WORK_WARP0 + L_WORKERS) * 32;     // 608
-constexpr int L_BT_BYTES = L_BN * 128;                         // 16 KB: one K block of one N tile of B'
-constexpr int L_WT_BYTES = L_DMAX * 128;                       // 8 KB: 64 d-rows x 64 planes
-constexpr int L_SMEM = 1024 + L_BSTAGES * L_BT_BYTES + L_WSTAGES * L_WT_BYTES + 6144;
-constexpr float L_NEAR_REL = 3.0517578125e-5f;    // 2^-15 |x| max|p| (4 x the bound on the dropped split terms): projections
-                                                  // closer to zero are recomputed in exact fp32 order
+constexpr int L_WROWS = 80;               // bucket-table tile rows: 64 d + the ones row + padding to a multiple of 16
+constexpr int L_BSTAGES = 4, L_WSTAGES = 3;   // one stage = one N tile of B' (2 K blocks) / one piece of the bucket tile (2 halves)
+constexpr int L_WORK_WARP0 = 4, L_WORKERS = 16;
+constexpr int L_THREADS = (L_WORK_WARP0 + L_WORKERS) * 32;     // 640
+constexpr int L_BT_BYTES = 2 * L_BN * 128;                     // 32 KB: both K blocks of one N tile of B'
+constexpr int L_WT_BYTES = 2 * L_WROWS * 128;                  // 20 KB: 80 rows x 128 planes (two 64-plane halves)
+constexpr int L_SMEM = 1024 + L_BSTAGES * L_BT_BYTES + L_WSTAGES * L_WT_BYTES + 4096;
+constexpr float L_NEAR_REL = 1.52587890625e-5f;   // 2^-16 |x| max|p|: projections closer to zero are recomputed in fp32 order
 
 struct LshParams {
     const float* feat; int64_t n_feat_rows; int F;
@@ -53,16 +56,17 @@ struct LshParams {
     const int64_t* ids; int64_t ids_stride; int64_t n; int64_t n_old; int64_t prime_pad;
     const void* iv_table; int iv_dtype;
     void* out; int out_dtype; int64_t out_stride; int D;
-    int wsplit;                                        // 1: bf16 bucket table, 2: hi + lo
+    int wsplit;                                        // 1: fp16 bucket table, 2: hi + lo
     float tie_eps;
     uint32_t* bits_out; int words;
     unsigned long long* tie_count;
     const float* pn_max;                               // largest plane norm (device scalar written by the pack kernel)
+    const float* wsum;                                 // [64] column sums of the packed bucket table
 };
 
 // ---------------------------------------------------------------- operand packing (once per call)
-// Bp [NT*128, 128] bf16: row b = [p0 | p1 | p0 | p1] (32 columns each; zero for f >= F and b >= B)
-// Wt [wsplit*64, NT*128] fp16: Wt[s*64 + d][b] = piece s of W[b][d] (zero padding)
+// Bp [NT*128, 128] bf16: row b = [p0 | p1 | p0 | 0] (32 columns each; zero for f >= F and b >= B)
+// Wt [wsplit*80, NT*128] fp16: rows s*80 + d = piece s of W[., d]; row 64 of piece 0 = 1 for b < B; zero padding
 __global__ void lsh_pack_kernel(const float* __restrict__ planes, int B, int F, int NT, const void* __restrict__ W, int w_dtype,
                                 int D, int wsplit, __nv_bfloat16* __restrict__ Bp, __half* __restrict__ Wt,
                                 float* __restrict__ pn_max) {
@@ -72,22 +76,34 @@ __global__ void lsh_pack_kernel(const float* __restrict__ planes, int B, int F, 
         const int b = (int)(t >> 5), f = (int)(t & 31);
         float p = (b < B && f < F) ? planes[(size_t)b * F + f] : 0.f;
         const __nv_bfloat16 p0 = __float2bfloat16_rn(p);
-        const float r1 = p - __bfloat162float(p0);
-        const __nv_bfloat16 p1 = __float2bfloat16_rn(r1);
+        const __nv_bfloat16 p1 = __float2bfloat16_rn(p - __bfloat162float(p0));
         __nv_bfloat16* row = Bp + (size_t)b * 128;
-        row[f] = p0; row[32 + f] = p1; row[64 + f] = p0; row[96 + f] = p1;
+        row[f] = p0; row[32 + f] = p1; row[64 + f] = p0; row[96 + f] = __float2bfloat16_rn(0.f);
         float s2 = p * p;                                           // the 32 lanes of a warp hold one plane
         for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
         if (f == 0 && s2 == s2) atomicMax(reinterpret_cast<unsigned int*>(pn_max), __float_as_uint(sqrtf(s2)));
     }
-    if (t < nb * L_DMAX) {
+    if (t < nb * L_WROWS) {
         const int d = (int)(t / nb);
         const int64_t b = t - (int64_t)d * nb;
-        const float w = (b < B && d < D) ? load_elem(W, w_dtype, b * D + d) : 0.f;
+        float w = 0.f;
+        if (b < B) w = d < D ? load_elem(W, w_dtype, b * D + d) : (d == L_DMAX ? 1.f : 0.f);
         const __half hi = __float2half_rn(w);
         Wt[(size_t)d * nb + b] = hi;
-        if (wsplit == 2) Wt[(size_t)(L_DMAX + d) * nb + b] = __float2half_rn(w - __half2float(hi));
+        if (wsplit == 2) Wt[(size_t)(L_WROWS + d) * nb + b] = __float2half_rn(w - __half2float(hi));
     }
+}
+// wsum[d] = sum over b of the packed pieces of W[b, d], fixed order (one warp per column, fp32 tree over 32 partial sums)
+__global__ void lsh_wsum_kernel(const __half* __restrict__ Wt, int64_t nb, int wsplit, float* __restrict__ wsum) {
+    const int d = blockIdx.x, lane = threadIdx.x;
+    float s = 0.f;
+    for (int64_t b = lane; b < nb; b += 32) {
+        float w = __half2float(Wt[(size_t)d * nb + b]);
+        if (wsplit == 2) w += __half2float(Wt[(size_t)(L_WROWS + d) * nb + b]);
+        s += w;
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) wsum[d] = s;
 }
 
 // warp-uniform: does tile `t` (128 list positions) hold at least one OOV id?  Every role asks the same question.
@@ -115,10 +131,14 @@ __device__ __forceinline__ void tc_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
-
-// D[tmem] (+)= A[tmem] * B[smem]: the A operand (the 0/1 tile H, bf16 pairs packed along K, lane = row) comes from
-// tensor memory, where the workers put it with tcgen05.st — no shared-memory round trip for H
-__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ uint32_t tc_ld_32x1(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+    return v;
+}
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (16-bit pairs packed along K, lane = row) comes from tensor memory,
+// where the workers put it with tcgen05.st — no shared-memory round trip
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
@@ -133,11 +153,10 @@ __device__ __forceinline__ void tc_st_32x16(uint32_t taddr, const uint32_t (&v)[
           "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
 }
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
 __device__ __forceinline__ void tc_st_32x4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // 8 features of one row (thread = (row, slice)), fetched one tile ahead
 struct Gather {
@@ -165,7 +184,7 @@ __device__ __forceinline__ void gather_load(const LshParams& p, int64_t tile, in
     gth.n2 = s;
 }
 
-// split into two bf16 pieces and write the slice of A' = [x0 | x0 | x1 | x1] into this row's TMEM lane:
+// split into two bf16 pieces and write the slice of A' = [x0 | x0 | x1] into this row's TMEM lane:
 // K element k lives in column k / 2, so the 8 features are 4 columns at offset 4 * part of each 16-column segment
 __device__ __forceinline__ void gather_store(uint32_t a_lane, float* sn2, int r, int part, const Gather& gth) {
     uint32_t c0[4], c1[4];
@@ -179,7 +198,6 @@ __device__ __forceinline__ void gather_store(uint32_t a_lane, float* sn2, int r,
     tc_st_32x4(a_lane + 0 * 16 + part * 4, c0[0], c0[1], c0[2], c0[3]);
     tc_st_32x4(a_lane + 1 * 16 + part * 4, c0[0], c0[1], c0[2], c0[3]);
     tc_st_32x4(a_lane + 2 * 16 + part * 4, c1[0], c1[1], c1[2], c1[3]);
-    tc_st_32x4(a_lane + 3 * 16 + part * 4, c1[0], c1[1], c1[2], c1[3]);
     sn2[part * L_BM + r] = gth.n2;
 }
 
@@ -200,11 +218,11 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* sB = smem;                                        // ring of [128 planes x 64] tiles
-    unsigned char* sW = sB + L_BSTAGES * L_BT_BYTES;                 // ring of [64 d x 64 planes] tiles
+    unsigned char* sW = sB + L_BSTAGES * L_BT_BYTES;                 // ring of [80 rows x 64 planes] tiles
     unsigned char* tail = sW + L_WSTAGES * L_WT_BYTES;
     float* sn2 = reinterpret_cast<float*>(tail);                     // [4][128] squared-norm shares of the current tile's rows
-    int* scnt = reinterpret_cast<int*>(sn2 + 4 * L_BM);              // [4][128] popcounts per column quarter
-    uint64_t* bars = reinterpret_cast<uint64_t*>(scnt + 4 * L_BM);
+    float* swsum = sn2 + 4 * L_BM;                                   // [64] column sums of the bucket table
+    uint64_t* bars = reinterpret_cast<uint64_t*>(swsum + L_DMAX);
     uint64_t* a_full = bars;            uint64_t* a_empty = bars + 1;
     uint64_t* b_full = bars + 2;        uint64_t* b_empty = b_full + L_BSTAGES;
     uint64_t* w_full = b_empty + L_BSTAGES;  uint64_t* w_empty = w_full + L_WSTAGES;
@@ -216,7 +234,6 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_tiles = (p.n + L_BM - 1) / L_BM;
     const int NT = p.NT;
-    const int WK = 2 * p.wsplit;                                     // Wt tiles per N tile
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmW); }
     if (warp == 1 && lane == 0) {
@@ -231,13 +248,14 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x >= 128 && threadIdx.x < 128 + L_DMAX) swsum[threadIdx.x - 128] = p.wsum[threadIdx.x - 128];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t ACC2_COL = 256;                               // 64 fp32 columns
-    constexpr uint32_t H_COL = 320;                                  // 2 x 64 columns: [128 x 128] fp16, two per column
-    constexpr uint32_t A_COL = 448;                                  // 64 columns: A' [128 x 128] bf16, two per column
+    constexpr uint32_t ACC2_COL = 256;                               // 80 fp32 columns: [S' W | S' 1 | padding]
+    constexpr uint32_t H_COL = 336;                                  // 2 x 64 columns: S' [128 x 128] fp16, two per column
+    constexpr uint32_t A_COL = 464;                                  // 48 columns: A' [128 x 96] bf16, two per column
 
     if (warp == 0) {
         // ===================== TMA: B' tiles =====================
@@ -245,13 +263,13 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             if (!tile_has_oov(p, t, lane)) continue;
             if (lane == 0)
-                for (int nt = 0; nt < NT; ++nt)
-                    for (int kb = 0; kb < L_KB; ++kb) {
-                        mbar_wait(&b_empty[stage], phase ^ 1);
-                        mbar_arrive_expect_tx(&b_full[stage], L_BT_BYTES);
-                        tma_load_2d(sB + stage * L_BT_BYTES, &tmB, &b_full[stage], kb * 64, nt * L_BN);
-                        if (++stage == L_BSTAGES) { stage = 0; phase ^= 1; }
-                    }
+                for (int nt = 0; nt < NT; ++nt) {
+                    mbar_wait(&b_empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&b_full[stage], L_BT_BYTES);
+                    tma_load_2d(sB + stage * L_BT_BYTES, &tmB, &b_full[stage], 0, nt * L_BN);
+                    tma_load_2d(sB + stage * L_BT_BYTES + L_BT_BYTES / 2, &tmB, &b_full[stage], 64, nt * L_BN);
+                    if (++stage == L_BSTAGES) { stage = 0; phase ^= 1; }
+                }
             __syncwarp();
         }
     } else if (warp == 2) {
@@ -261,69 +279,76 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             if (!tile_has_oov(p, t, lane)) continue;
             if (lane == 0)
                 for (int nt = 0; nt < NT; ++nt)
-                    for (int kk = 0; kk < WK; ++kk) {
+                    for (int pc = 0; pc < p.wsplit; ++pc) {
                         mbar_wait(&w_empty[stage], phase ^ 1);
                         mbar_arrive_expect_tx(&w_full[stage], L_WT_BYTES);
-                        tma_load_2d(sW + stage * L_WT_BYTES, &tmW, &w_full[stage], nt * L_BN + (kk & 1) * 64, (kk >> 1) * L_DMAX);
+                        tma_load_2d(sW + stage * L_WT_BYTES, &tmW, &w_full[stage], nt * L_BN, pc * L_WROWS);
+                        tma_load_2d(sW + stage * L_WT_BYTES + L_WT_BYTES / 2, &tmW, &w_full[stage], nt * L_BN + 64, pc * L_WROWS);
                         if (++stage == L_WSTAGES) { stage = 0; phase ^= 1; }
                     }
             __syncwarp();
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuer 1: projections =====================
         constexpr uint32_t idesc1 = make_idesc_bf16_f32(L_BM, L_BN);
-        constexpr uint32_t idesc2 = make_idesc_bf16_f32(L_BM, L_DMAX) & ~((7u << 7) | (7u << 10));   // A, B = fp16 (format 0)
-        int bs = 0; uint32_t bph = 0; int ws = 0; uint32_t wph = 0;
-        int64_t g1 = 0, g2 = 0;            // N tiles issued to GEMM1 / GEMM2 since kernel start
+        int bs = 0; uint32_t bph = 0;
+        int64_t g1 = 0;                    // N tiles issued since kernel start
         int64_t T = 0;                     // row tiles with OOV ids done by this CTA
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             if (!tile_has_oov(p, t, lane)) continue;
             if (lane == 0) {
                 mbar_wait(a_full, (uint32_t)(T & 1));
-                tc_fence_after();
-                for (int nt = 0; nt <= NT; ++nt) {
-                    if (nt < NT) {                                    // GEMM1(nt): projections of 128 planes
-                        const int buf = (int)(g1 & 1);
-                        mbar_wait(&acc1_empty[buf], (uint32_t)(((g1 >> 1) & 1) ^ 1));
-                        tc_fence_after();
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * L_BN);
-                        for (int kb = 0; kb < L_KB; ++kb) {
-                            mbar_wait(&b_full[bs], bph);
-                            tc_fence_after();
-                            const uint32_t a_tmem = tmem_base + A_COL + (uint32_t)(kb * 32);
-                            const uint64_t bdesc = make_sw128_desc(smem_u32(sB + bs * L_BT_BYTES));
+                for (int nt = 0; nt < NT; ++nt, ++g1) {
+                    const int buf = (int)(g1 & 1);
+                    mbar_wait(&acc1_empty[buf], (uint32_t)(((g1 >> 1) & 1) ^ 1));
+                    mbar_wait(&b_full[bs], bph);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * L_BN);
+                    const uint32_t a_tmem = tmem_base + A_COL;
+                    const uint64_t bdesc0 = make_sw128_desc(smem_u32(sB + bs * L_BT_BYTES));
+                    const uint64_t bdesc1 = make_sw128_desc(smem_u32(sB + bs * L_BT_BYTES + L_BT_BYTES / 2));
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)               // A' from TMEM: K = 16 bf16 = 8 columns
-                                tc_mma_bf16_ts(d_tmem, a_tmem + (uint32_t)(8 * k), bdesc + (uint64_t)(2 * k), idesc1, (kb | k) ? 1u : 0u);
-                            tc_commit(&b_empty[bs]);
-                            if (++bs == L_BSTAGES) { bs = 0; bph ^= 1; }
-                        }
-                        tc_commit(&acc1_full[buf]);
-                        if (nt == NT - 1) tc_commit(a_empty);         // A' may be rebuilt for the next row tile
-                        ++g1;
-                    }
-                    if (nt >= 1) {                                    // GEMM2(nt - 1): acc2 += H W, H read from TMEM
-                        const int j = nt - 1;
-                        const int hb = (int)(g2 & 1);
-                        mbar_wait(&h_full[hb], (uint32_t)((g2 >> 1) & 1));
-                        if (j == 0) mbar_wait(acc2_empty, (uint32_t)((T & 1) ^ 1));
+                    for (int k = 0; k < 6; ++k)                       // A' from TMEM: K = 16 bf16 = 8 columns; K' = 96 -> 6 steps
+                        tc_mma_f16_ts(d_tmem, a_tmem + (uint32_t)(8 * k), (k < 4 ? bdesc0 + (uint64_t)(2 * k) : bdesc1 + (uint64_t)(2 * (k - 4))),
+                                      idesc1, k ? 1u : 0u);
+                    tc_commit(&b_empty[bs]);
+                    tc_commit(&acc1_full[buf]);
+                    if (nt == NT - 1) tc_commit(a_empty);             // A' may be rebuilt for the next row tile
+                    if (++bs == L_BSTAGES) { bs = 0; bph ^= 1; }
+                }
+            }
+            ++T;
+            __syncwarp();
+        }
+    } else if (warp == 3) {
+        // ===================== MMA issuer 2: acc2 += S' [W | 1], S' read from TMEM =====================
+        constexpr uint32_t idesc2 = make_idesc_bf16_f32(L_BM, L_WROWS) & ~((7u << 7) | (7u << 10));   // A, B = fp16 (format 0)
+        int ws = 0; uint32_t wph = 0;
+        int64_t g2 = 0;
+        int64_t T = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            if (!tile_has_oov(p, t, lane)) continue;
+            if (lane == 0) {
+                const uint32_t d_tmem = tmem_base + ACC2_COL;
+                for (int j = 0; j < NT; ++j, ++g2) {
+                    const int hb = (int)(g2 & 1);
+                    mbar_wait(&h_full[hb], (uint32_t)((g2 >> 1) & 1));
+                    if (j == 0) mbar_wait(acc2_empty, (uint32_t)((T & 1) ^ 1));
+                    for (int pc = 0; pc < p.wsplit; ++pc) {
+                        mbar_wait(&w_full[ws], wph);
                         tc_fence_after();
-                        const uint32_t d_tmem = tmem_base + ACC2_COL;
-                        for (int kk = 0; kk < WK; ++kk) {
-                            mbar_wait(&w_full[ws], wph);
-                            tc_fence_after();
-                            const uint32_t a_tmem = tmem_base + H_COL + (uint32_t)(hb * 64 + (kk & 1) * 32);
-                            const uint64_t bdesc = make_sw128_desc(smem_u32(sW + ws * L_WT_BYTES));
+                        const uint32_t a_tmem = tmem_base + H_COL + (uint32_t)(hb * 64);
+                        const uint64_t bdesc0 = make_sw128_desc(smem_u32(sW + ws * L_WT_BYTES));
+                        const uint64_t bdesc1 = make_sw128_desc(smem_u32(sW + ws * L_WT_BYTES + L_WT_BYTES / 2));
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)               // K = 16 bf16 = 8 TMEM columns / 32 B of smem
-                                tc_mma_bf16_ts(d_tmem, a_tmem + (uint32_t)(8 * k), bdesc + (uint64_t)(2 * k), idesc2, (j | kk | k) ? 1u : 0u);
-                            tc_commit(&w_empty[ws]);
-                            if (++ws == L_WSTAGES) { ws = 0; wph ^= 1; }
-                        }
-                        tc_commit(&h_empty[hb]);
-                        if (j == NT - 1) tc_commit(acc2_full);
-                        ++g2;
+                        for (int k = 0; k < 8; ++k)                   // K = 16 fp16 = 8 TMEM columns / 32 B of smem
+                            tc_mma_f16_ts(d_tmem, a_tmem + (uint32_t)(8 * k), (k < 4 ? bdesc0 + (uint64_t)(2 * k) : bdesc1 + (uint64_t)(2 * (k - 4))),
+                                          idesc2, (j | pc | k) ? 1u : 0u);
+                        tc_commit(&w_empty[ws]);
+                        if (++ws == L_WSTAGES) { ws = 0; wph ^= 1; }
                     }
+                    tc_commit(&h_empty[hb]);
+                    if (j == NT - 1) tc_commit(acc2_full);
                 }
             }
             ++T;
@@ -333,14 +358,16 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         // ===================== workers =====================
         const int wk = warp - L_WORK_WARP0;
         const int q = warp & 3;                    // TMEM lane quarter
-        const int cq = wk >> 2;                    // column quarter of every N tile
-        const int row = q * 32 + lane;             // row of the tile this thread owns in the epilogues
+        const int cq = wk >> 2;                    // column quarter of every N tile / 8-feature slice / 16-column output slice
+        const int row = q * 32 + lane;             // row of the tile this thread owns
         const int wtid = wk * 32 + lane;           // 0..511
         const int gr = wtid >> 2, gpart = wtid & 3;   // in-vocab copy role: row, 16-column slice
-        const uint32_t a_lane = tmem_base + ((uint32_t)(q * 32) << 16) + A_COL;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t a_lane = lane_base + A_COL;
         unsigned int my_ties = 0;
         int64_t g = 0, T = 0;
         const float pn_max = *p.pn_max;
+        const uint32_t SIGNS = 0x80008000u, ONES = 0x3C003C00u;       // fp16 pair: sign bits / (+1, +1)
 
         // first tile with OOV ids (in-vocab-only tiles on the way are plain copies)
         int64_t t = blockIdx.x;
@@ -356,10 +383,11 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         }
         while (t < n_tiles) {
             const int64_t row0 = t * L_BM;
-            worker_bar();                                             // sn2 of this tile is complete; scnt of the previous one is free
+            worker_bar();                                             // sn2 of this tile is complete
             // next tile with OOV ids: issue its gather now, it is consumed after this tile's last projection
             int64_t tn = t + gridDim.x;
             while (tn < n_tiles && !tile_has_oov(p, tn, lane)) { copy_iv_tile(p, tn, gr, gpart); tn += gridDim.x; }
+            const float xnorm = sqrtf(sn2[row] + sn2[L_BM + row] + sn2[2 * L_BM + row] + sn2[3 * L_BM + row]);
             if (tn < n_tiles) gather_load(p, tn, row, cq, gth);
 
             int64_t my_fr = -1, my_id = INT64_MIN;
@@ -372,57 +400,65 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             }
             const bool my_oov = my_fr >= 0;
             // |tensor-core projection - fp32 projection| stays far below this; anything closer to zero is redone exactly
-            const float xnorm = sqrtf(sn2[row] + sn2[L_BM + row] + sn2[2 * L_BM + row] + sn2[3 * L_BM + row]);
             const float near = fmaxf(L_NEAR_REL * xnorm * pn_max, 4.f * p.tie_eps);
-            int cnt = 0;
-            // ---- per N tile: projections -> bits -> H
+            // ---- per N tile: projections -> signs -> S'
             for (int nt = 0; nt < NT; ++nt, ++g) {
                 const int buf = (int)(g & 1);
                 const uint32_t par = (uint32_t)((g >> 1) & 1);
                 mbar_wait(&acc1_full[buf], par);
                 tc_fence_after();
                 uint32_t v[32];
-                tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * L_BN + cq * 32), v);
+                tc_ld_32x32(lane_base + (uint32_t)(buf * L_BN + cq * 32), v);
                 tc_wait_ld();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc1_empty[buf]);
-                const int b0 = nt * L_BN + cq * 32;                   // plane of column 0
-                uint32_t word = 0u, nearw = 0u;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float r = __uint_as_float(v[j]);
-                    word |= (r < 0.f ? 0u : 1u) << j;                 // torch_hash.py:57-59: -0, +0, NaN -> 1
-                    nearw |= (fabsf(r) < near ? 1u : 0u) << j;
-                }
-                if (b0 + 32 > p.B) {                                  // planes past B do not exist
-                    const uint32_t valid = (b0 >= p.B) ? 0u : ((1u << (p.B - b0)) - 1u);
-                    word &= valid; nearw &= valid;
-                }
-                if (!my_oov) { word = 0u; nearw = 0u; }
-                while (nearw) {                                       // rare: redo in the fp32 FMA order of csrc/lsh.cu
-                    const int j = __ffs(nearw) - 1;
-                    nearw &= nearw - 1;
-                    const float* xr = p.feat + my_fr * p.F;
-                    const float* pr = p.planes + (size_t)(b0 + j) * p.F;
-                    float a = 0.f;
-                    for (int f = 0; f < p.F; ++f) a = fmaf(__ldg(xr + f), __ldg(pr + f), a);
-                    word = (word & ~(1u << j)) | ((a < 0.f ? 0u : 1u) << j);
-                    if (fabsf(a) < p.tie_eps) ++my_ties;
-                }
-                cnt += __popc(word);
-                if (p.bits_out != nullptr && row0 + row < p.n && nt * 4 + cq < p.words)
-                    p.bits_out[(row0 + row) * p.words + nt * 4 + cq] = word;
-                // H: 32 fp16 0/1 values = 16 TMEM columns of this row
+                // fast path: S' pair = (+1, +1) with the sign bits of the two projections (2 instructions per pair)
                 uint32_t hw[16];
+                float mn = INFINITY;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const uint32_t two = (word >> (2 * i)) & 3u;
-                    hw[i] = ((two & 1u) ? 0x3C00u : 0u) | ((two & 2u) ? 0x3C000000u : 0u);
+                    hw[i] = (__byte_perm(v[2 * i], v[2 * i + 1], 0x7030) & SIGNS) ^ ONES;
+                    mn = fminf(mn, fminf(fabsf(__uint_as_float(v[2 * i])), fabsf(__uint_as_float(v[2 * i + 1]))));
+                }
+                const int b0 = nt * L_BN + cq * 32;                   // plane of column 0
+                if ((mn < near || p.bits_out != nullptr) && my_oov) {
+                    // slow path (about 1 chunk in 200, or when the caller wants the multi-hot words): exact bits.
+                    // -0 has the sign bit but is not < 0 (torch_hash.py:57-59), near-zero projections are redone in
+                    // the fp32 FMA order of csrc/lsh.cu
+                    uint32_t word = 0u, nearw = 0u;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float r = __uint_as_float(v[j]);
+                        word |= (r < 0.f ? 0u : 1u) << j;
+                        nearw |= (fabsf(r) < near ? 1u : 0u) << j;
+                    }
+                    const uint32_t valid = (b0 + 32 <= p.B) ? 0xffffffffu : ((b0 >= p.B) ? 0u : ((1u << (p.B - b0)) - 1u));
+                    nearw &= valid;
+                    while (nearw) {
+                        const int j = __ffs(nearw) - 1;
+                        nearw &= nearw - 1;
+                        const float* xr = p.feat + my_fr * p.F;
+                        const float* pr = p.planes + (size_t)(b0 + j) * p.F;
+                        float a = 0.f;
+                        for (int f = 0; f < p.F; ++f) a = fmaf(__ldg(xr + f), __ldg(pr + f), a);
+                        word = (word & ~(1u << j)) | ((a < 0.f ? 0u : 1u) << j);
+                        if (fabsf(a) < p.tie_eps) ++my_ties;
+                    }
+                    word &= valid;
+                    if (p.bits_out != nullptr && row0 + row < p.n && nt * 4 + cq < p.words)
+                        p.bits_out[(row0 + row) * p.words + nt * 4 + cq] = word;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {                    // planes >= B meet zero bucket rows: any sign will do
+                        const uint32_t two = (word >> (2 * i)) & 3u;
+                        hw[i] = ((two & 1u) ? 0x3C00u : 0xBC00u) | ((two & 2u) ? 0x3C000000u : 0xBC000000u);
+                    }
+                } else if (p.bits_out != nullptr && row0 + row < p.n && nt * 4 + cq < p.words) {
+                    p.bits_out[(row0 + row) * p.words + nt * 4 + cq] = 0u;
                 }
                 mbar_wait(&h_empty[buf], par ^ 1);                    // GEMM2 of the previous use of this buffer is done
                 tc_fence_after();
-                tc_st_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + H_COL + (uint32_t)(buf * 64 + cq * 16), hw);
+                tc_st_32x16(lane_base + H_COL + (uint32_t)(buf * 64 + cq * 16), hw);
                 tc_wait_st();
                 tc_fence_before();
                 __syncwarp();
@@ -438,37 +474,39 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a_full);
             }
-            // ---- final: out = (H W) / count
-            scnt[cq * L_BM + row] = cnt;
+            // ---- final: out = (S' W + colsum W) / (S' 1 + B)   [= 2 H W / 2 count]
             mbar_wait(acc2_full, (uint32_t)(T & 1));
             tc_fence_after();
             ++T;
             uint32_t a[16];
-            tc_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + ACC2_COL + (uint32_t)(cq * 16), a);
+            tc_ld_32x16(lane_base + ACC2_COL + (uint32_t)(cq * 16), a);
+            const uint32_t ones_acc = tc_ld_32x1(lane_base + ACC2_COL + L_DMAX);
             tc_wait_ld();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc2_empty);
-            worker_bar();                                             // all four popcount partials are in smem
             const int64_t r = row0 + row;
             if (r < p.n) {
                 const int d0 = cq * 16;
                 const size_t osz = p.out_dtype == OOV_F32 ? 4 : 2;
                 char* orow = reinterpret_cast<char*>(p.out) + (size_t)r * p.out_stride * osz;
                 if (my_oov) {
-                    const float den = (float)(scnt[row] + scnt[L_BM + row] + scnt[2 * L_BM + row] + scnt[3 * L_BM + row]);
+                    const float den = __uint_as_float(ones_acc) + (float)p.B;          // 2 x count, exact
+                    float o[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        o[i] = den == 0.f ? __uint_as_float(0x7FC00000u) : (__uint_as_float(a[i]) + swsum[d0 + i]) / den;
                     if (p.out_dtype == OOV_BF16 && d0 + 16 <= p.D && ((reinterpret_cast<uintptr_t>(orow) + d0 * 2) & 15) == 0) {
                         uint32_t pk[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            pk[i] = pack_bf16x2(__uint_as_float(a[2 * i]) / den, __uint_as_float(a[2 * i + 1]) / den);
-                        uint4* o = reinterpret_cast<uint4*>(orow + d0 * 2);
-                        o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
+                        uint4* op = reinterpret_cast<uint4*>(orow + d0 * 2);
+                        op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
-                            if (d0 + i < p.D) store_elem(p.out, p.out_dtype, r * p.out_stride + d0 + i, __uint_as_float(a[i]) / den);
+                            if (d0 + i < p.D) store_elem(p.out, p.out_dtype, r * p.out_stride + d0 + i, o[i]);
                     }
                 } else if (my_id != INT64_MIN && my_id >= 0 && my_id < p.n_old && p.iv_table != nullptr) {
                     for (int i = 0; i < 16; ++i)                      // in-vocab gather (bpr.py:111-112)
@@ -496,8 +534,8 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
 bool lsh_tc_supported(int F, int B, int D) { return F >= 1 && F <= L_FMAX && D >= 1 && D <= L_DMAX && B >= 1; }
 
 static size_t lsh_bp_bytes(int B) { return align_up((size_t)cdiv(B, L_BN) * L_BN * 128 * 2, 1024); }
-static size_t lsh_wt_bytes(int B) { return align_up((size_t)2 * L_DMAX * cdiv(B, L_BN) * L_BN * 2, 1024); }
-size_t lsh_tc_workspace(int B) { return lsh_bp_bytes(B) + lsh_wt_bytes(B) + 256 + 1024; }
+static size_t lsh_wt_bytes(int B) { return align_up((size_t)2 * L_WROWS * cdiv(B, L_BN) * L_BN * 2, 1024); }
+size_t lsh_tc_workspace(int B) { return lsh_bp_bytes(B) + lsh_wt_bytes(B) + 512 + 1024; }
 
 int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* planes, int B, const void* W, int w_dtype,
                const oov_rows* rows, float tie_eps, uint32_t* bits_out, unsigned long long* tie_count, void* workspace,
@@ -508,6 +546,7 @@ int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* plane
     __nv_bfloat16* Bp = reinterpret_cast<__nv_bfloat16*>(ws);
     __half* Wt = reinterpret_cast<__half*>(ws + lsh_bp_bytes(B));
     float* pn_max = reinterpret_cast<float*>(ws + lsh_bp_bytes(B) + lsh_wt_bytes(B));
+    float* wsum = pn_max + 16;
     cudaError_t ce = cudaMemsetAsync(pn_max, 0, 4, st);
     OOV_REQUIRE(ce == cudaSuccess, OOV_ERR_CUDA, "cudaMemsetAsync(pn_max): %s", cudaGetErrorString(ce));
     const int NT = (int)cdiv(B, L_BN);
@@ -518,16 +557,17 @@ int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* plane
     p.iv_table = rows->iv_table; p.iv_dtype = rows->iv_dtype; p.out = rows->out; p.out_dtype = rows->out_dtype;
     p.out_stride = rows->out_stride; p.D = rows->D;
     p.wsplit = rows->out_dtype == OOV_F32 ? 2 : 1;   // fp16 hi (+ lo) pieces of the fp32 bucket table: 2^-12 (2^-23) relative
-    p.tie_eps = tie_eps; p.bits_out = bits_out; p.words = (B + 31) / 32; p.tie_count = tie_count; p.pn_max = pn_max;
+    p.tie_eps = tie_eps; p.bits_out = bits_out; p.words = (B + 31) / 32; p.tie_count = tie_count; p.pn_max = pn_max; p.wsum = wsum;
 
-    const int64_t pack_threads = nb * L_DMAX > nb * 32 ? nb * L_DMAX : nb * 32;
-    lsh_pack_kernel<<<(unsigned)cdiv(pack_threads, 256), 256, 0, st>>>(planes, B, F, NT, W, w_dtype, rows->D, p.wsplit, Bp, Wt, pn_max);
+    lsh_pack_kernel<<<(unsigned)cdiv(nb * L_WROWS, 256), 256, 0, st>>>(planes, B, F, NT, W, w_dtype, rows->D, p.wsplit, Bp, Wt, pn_max);
     OOV_LAUNCH_CHECK("lsh_pack_kernel");
+    lsh_wsum_kernel<<<L_DMAX, 32, 0, st>>>(Wt, nb, p.wsplit, wsum);
+    OOV_LAUNCH_CHECK("lsh_wsum_kernel");
 
     CUtensorMap tmB, tmW;
     int rc = make_tmap_bf16_2d(&tmB, Bp, 128, (uint64_t)nb, 128 * 2, L_BN);
     if (rc) return rc;
-    rc = make_tmap_bf16_2d(&tmW, Wt, (uint64_t)nb, (uint64_t)(p.wsplit * L_DMAX), (uint64_t)nb * 2, L_DMAX);
+    rc = make_tmap_bf16_2d(&tmW, Wt, (uint64_t)nb, (uint64_t)(p.wsplit * L_WROWS), (uint64_t)nb * 2, L_WROWS);   // fp16: same 2-byte boxes
     if (rc) return rc;
     static bool attr_done = false;
     if (!attr_done) {
