@@ -78,63 +78,92 @@ struct ScoreParams {
     unsigned long long* partial;        // [gridDim.x][Q][k]
 };
 
-// per-thread (= per-user) epilogue state
+// per-thread (= per-user) epilogue state.  The list is UNSORTED and split in two u32 arrays (ordered score / ~row):
+// entries [0, n) are valid.  While n < k new candidates are appended; when it is full the smallest entry (tracked in
+// thr_hi / thr_lo / min_pos) is replaced and the minimum is searched again with short independent chains.
 struct UserState {
-    unsigned long long* L;              // list column (UNSORTED): entry e at L[e * SC_UG]; 0 = empty slot
+    uint32_t* Lh;                       // ordered score keys: entry e at Lh[e * SC_UG]
+    uint32_t* Ll;                       // ~local row:         entry e at Ll[e * SC_UG]
     unsigned long long* Qe;             // candidate queue column: entry i at Qe[i * SC_UG] = (score bits << 32 | local row)
-    unsigned long long thr_key;         // smallest key of the list (0 while it has an empty slot)
+    uint32_t thr_hi, thr_lo;            // smallest (score key, ~row) of a FULL list, else 0
     float thr_f;                        // score filter: scores strictly below cannot enter the final top-k
-    int min_pos;                        // slot holding thr_key
+    int n;                              // valid list entries
+    int min_pos;                        // slot of the smallest entry (full list only)
     int cnt;                            // queued candidates
     uint32_t b1, b2, b3;                // three best score keys this stream has seen (b1 >= b2 >= b3)
     int hpos, hend;                     // history cursor
-    int64_t next_h;                     // next masked global id (INT64_MAX when exhausted)
+    uint32_t next_h;                    // next masked LOCAL row (0xFFFFFFFF when exhausted)
     int n_push, n_ins, n_steps;         // profiling counters (OOV_SCORE_DEBUG bit 2)
 };
 
-// replace the smallest list entry with `key` (> thr_key) and find the new smallest: k independent smem loads, no
-// data-dependent branches, so the lanes of a warp (32 users) insert together
-__device__ __forceinline__ void list_insert(const ScoreParams& p, UserState& u, unsigned long long key) {
-    u.L[u.min_pos * SC_UG] = key;
-    ++u.n_ins;
-    const uint32_t hi = (uint32_t)(key >> 32);
-    if (hi > u.b1) { u.b3 = u.b2; u.b2 = u.b1; u.b1 = hi; }
-    else if (hi > u.b2) { u.b3 = u.b2; u.b2 = hi; }
-    else if (hi > u.b3) u.b3 = hi;
+// per-CTA constants of the mask tests, all as local rows (uint32)
+struct MaskRows {
+    uint32_t n_rows;                    // rows >= this are TMA zero fill
+    uint32_t pad_row;                   // local row of global id 0 when it is masked, else 0xFFFFFFFF
+    uint32_t seg_lo, seg_hi;            // local rows kept: [seg_lo, seg_hi)
+};
+
+// smallest entry of a full list by (score key, ~row): the kept set is exactly the (score desc, row asc) top-k
+__device__ __forceinline__ void list_find_min(const ScoreParams& p, UserState& u) {
     const int k = p.k;
-    if (u.thr_key == 0ull && u.min_pos + 1 < k) { ++u.min_pos; return; }   // still filling: slots are taken in order
     unsigned long long mn = ~0ull;
     int pos = 0;
 #pragma unroll 4
     for (int e = 0; e < k; ++e) {
-        const unsigned long long x = u.L[e * SC_UG];
+        const unsigned long long x = ((unsigned long long)u.Lh[e * SC_UG] << 32) | (unsigned long long)u.Ll[e * SC_UG];
         if (x < mn) { mn = x; pos = e; }
     }
-    u.thr_key = mn;
-    u.min_pos = pos;
-    if (mn) u.thr_f = fmaxf(u.thr_f, key64_score(mn));            // a NaN k-th score leaves the filter unchanged
+    u.thr_hi = (uint32_t)(mn >> 32); u.thr_lo = (uint32_t)mn; u.min_pos = pos;
+    u.thr_f = fmaxf(u.thr_f, float_from_order_key(u.thr_hi));     // a NaN k-th score leaves the filter unchanged
+}
+
+__device__ __forceinline__ void list_insert(const ScoreParams& p, UserState& u, uint32_t hi, uint32_t lo) {
+    ++u.n_ins;
+    if (hi > u.b1) { u.b3 = u.b2; u.b2 = u.b1; u.b1 = hi; }
+    else if (hi > u.b2) { u.b3 = u.b2; u.b2 = hi; }
+    else if (hi > u.b3) u.b3 = hi;
+    if (u.n < p.k) {                                              // room left: append
+        u.Lh[u.n * SC_UG] = hi; u.Ll[u.n * SC_UG] = lo;
+        if (++u.n == p.k) list_find_min(p, u);
+        return;
+    }
+    u.Lh[u.min_pos * SC_UG] = hi; u.Ll[u.min_pos * SC_UG] = lo;   // replace the smallest
+    list_find_min(p, u);
+}
+
+// drop list entries whose score is strictly below the shared threshold T (they cannot be in the final top-k)
+__device__ __forceinline__ void list_compact(UserState& u, uint32_t T) {
+    int w = 0;
+    for (int e = 0; e < u.n; ++e) {
+        const uint32_t h = u.Lh[e * SC_UG], l = u.Ll[e * SC_UG];
+        if (h >= T) { u.Lh[w * SC_UG] = h; u.Ll[w * SC_UG] = l; ++w; }
+    }
+    if (w < u.n) { u.n = w; u.thr_hi = 0u; u.thr_lo = 0u; }
 }
 
 // masks (pad / segment / history cursor) + list insertion of one queued candidate
-__device__ __forceinline__ void consider(const ScoreParams& p, UserState& u, float s, uint32_t li) {
-    if (li >= (uint32_t)p.N) return;                              // zero-filled rows past the end of the shard
-    const int64_t gid = (int64_t)li + p.item_id_offset;
-    while (u.next_h < gid) {                                      // ids arrive in increasing order
+__device__ __forceinline__ void consider(const ScoreParams& p, const MaskRows& mr, UserState& u, float s, uint32_t li) {
+    if (li >= mr.n_rows) return;                                  // zero-filled rows past the end of the shard
+    while (u.next_h < li) {                                       // rows arrive in increasing order
         ++u.hpos;
-        u.next_h = u.hpos < u.hend ? (int64_t)p.hist_cols[u.hpos] : INT64_MAX;
+        u.next_h = 0xFFFFFFFFu;
+        if (u.hpos < u.hend) {
+            const int64_t loc = (int64_t)p.hist_cols[u.hpos] - p.item_id_offset;
+            u.next_h = loc < (int64_t)mr.n_rows ? (uint32_t)loc : 0xFFFFFFFFu;      // loc >= first row of this CTA > 0
+        }
     }
-    if (u.next_h == gid || (p.mask_pad && gid == 0) || gid < p.seg_lo || gid >= p.seg_hi) s = -INFINITY;
-    const unsigned long long key = make_key64(s, li);
-    if (key > u.thr_key) list_insert(p, u, key);
+    if (u.next_h == li || li == mr.pad_row || li < mr.seg_lo || li >= mr.seg_hi) s = -INFINITY;
+    const uint32_t hi = float_order_key(s), lo = ~li;
+    if (u.n < p.k || hi > u.thr_hi || (hi == u.thr_hi && lo > u.thr_lo)) list_insert(p, u, hi, lo);
 }
 
 // all 32 lanes together: every user works through its own queue
-__device__ __forceinline__ void drain(const ScoreParams& p, UserState& u) {
+__device__ __forceinline__ void drain(const ScoreParams& p, const MaskRows& mr, UserState& u) {
     const int n = u.cnt;
     u.n_steps += __reduce_max_sync(0xffffffffu, n);
     for (int i = 0; i < n; ++i) {
         const unsigned long long ent = u.Qe[i * SC_UG];
-        consider(p, u, __uint_as_float((uint32_t)(ent >> 32)), (uint32_t)ent);
+        consider(p, mr, u, __uint_as_float((uint32_t)(ent >> 32)), (uint32_t)ent);
     }
     u.cnt = 0;
 }
@@ -181,7 +210,7 @@ __device__ __forceinline__ bool refresh_tile(int64_t it) {
 // one 32-column chunk of one user's scores (registers v[0..31]); `col0` = local item row of column 0.
 // Called by all 32 lanes together (warp votes inside).  Candidates are queued; the queue is drained here only when
 // some lane ran out of space (then the chunk is scanned again for what is left), else at the end of the tile.
-__device__ __forceinline__ void process_chunk(const ScoreParams& p, UserState& u, const uint32_t (&v)[32], uint32_t col0) {
+__device__ __forceinline__ void process_chunk(const ScoreParams& p, const MaskRows& mr, UserState& u, const uint32_t (&v)[32], uint32_t col0) {
     float m[11];
 #pragma unroll
     for (int j = 0; j < 10; ++j)
@@ -191,6 +220,23 @@ __device__ __forceinline__ void process_chunk(const ScoreParams& p, UserState& u
     const float m2 = max3_nan(m[6], m[7], m[8]), m3 = max2_nan(m[9], m[10]);
     const float mx = max2_nan(max3_nan(m0, m1, m2), m3);
     if (!__any_sync(0xffffffffu, !(mx < u.thr_f))) return;        // NaN compares false -> scanned
+    // Common case (a lane or two with one candidate): no branches.  Upper bound of this thread's candidates = 3 x
+    // groups at or above the threshold; if every lane's queue has room for that, push with predicated stores.
+    int hits = 0;
+#pragma unroll
+    for (int g = 0; g < 11; ++g) hits += (m[g] < u.thr_f) ? 0 : 1;
+    if (!__any_sync(0xffffffffu, u.cnt + 3 * hits > SC_QCAP)) {
+        const float thr = u.thr_f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (!(__uint_as_float(v[j]) < thr)) {
+                u.Qe[u.cnt * SC_UG] = ((unsigned long long)v[j] << 32) | (unsigned long long)(col0 + (uint32_t)j);
+                ++u.cnt; ++u.n_push;
+            }
+        }
+        return;
+    }
+    // Crowded chunk (the first tiles of a stream): queue what fits, drain, scan again for the rest.
     int done = -1;                                                // last column of this chunk already queued
     while (true) {
         bool more = false;
@@ -214,7 +260,7 @@ __device__ __forceinline__ void process_chunk(const ScoreParams& p, UserState& u
             }
         }
         if (!__any_sync(0xffffffffu, more)) break;
-        drain(p, u);
+        drain(p, mr, u);
     }
 }
 
@@ -224,8 +270,9 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     unsigned char* sA = smem;                                        // SC_NUT x 16 KB
     unsigned char* sB = smem + SC_NUT * SC_A_BYTES;                  // stages x 16 KB
-    unsigned long long* lists = reinterpret_cast<unsigned long long*>(sB + p.stages * SC_B_BYTES);   // [k][SC_UG]
-    unsigned long long* queues = lists + (size_t)p.k * SC_UG;                                          // [SC_QCAP][SC_UG]
+    uint32_t* lists_hi = reinterpret_cast<uint32_t*>(sB + p.stages * SC_B_BYTES);                     // [k][SC_UG]
+    uint32_t* lists_lo = lists_hi + (size_t)p.k * SC_UG;                                               // [k][SC_UG]
+    unsigned long long* queues = reinterpret_cast<unsigned long long*>(lists_lo + (size_t)p.k * SC_UG);   // [SC_QCAP][SC_UG]
     uint64_t* bars = reinterpret_cast<uint64_t*>(queues + (size_t)SC_QCAP * SC_UG);
     uint64_t* full_bar = bars;                          // [SC_MAX_STAGES]
     uint64_t* empty_bar = bars + SC_MAX_STAGES;         // [SC_MAX_STAGES]
@@ -312,14 +359,23 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
         const bool user_ok = user < p.Q && !(p.debug & 1);
         const int k = p.k;
         UserState u;
-        u.L = lists + u_local;
+        u.Lh = lists_hi + u_local;
+        u.Ll = lists_lo + u_local;
         u.Qe = queues + u_local;
-        for (int e = 0; e < k; ++e) u.L[e * SC_UG] = 0ull;
-        u.thr_key = 0ull; u.min_pos = 0; u.cnt = 0;
+        u.thr_hi = 0u; u.thr_lo = 0u; u.n = 0; u.min_pos = 0; u.cnt = 0;
         u.b1 = u.b2 = u.b3 = 0u;
         u.n_push = u.n_ins = u.n_steps = 0;
         u.thr_f = user_ok ? -INFINITY : INFINITY;                     // padding lanes never take a candidate
-        u.hpos = 0; u.hend = 0; u.next_h = INT64_MAX;
+        u.hpos = 0; u.hend = 0; u.next_h = 0xFFFFFFFFu;
+        // mask tests on local rows (uint32): [0, N) holds global ids item_id_offset ..
+        MaskRows mr;
+        mr.n_rows = (uint32_t)p.N;
+        mr.pad_row = (p.mask_pad && p.item_id_offset <= 0 && -p.item_id_offset < p.N) ? (uint32_t)(-p.item_id_offset) : 0xFFFFFFFFu;
+        {
+            const int64_t lo = p.seg_lo - p.item_id_offset, hi = p.seg_hi - p.item_id_offset;
+            mr.seg_lo = lo <= 0 ? 0u : (lo >= p.N ? (uint32_t)p.N : (uint32_t)lo);
+            mr.seg_hi = hi <= 0 ? 0u : (hi >= p.N ? (uint32_t)p.N : (uint32_t)hi);
+        }
         uint32_t* pub_user = p.pub + (size_t)(user_ok ? user : 0) * gridDim.x + blockIdx.x;
         uint32_t last_pub = 0u;
 
@@ -334,7 +390,10 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
                     if ((int64_t)p.hist_cols[mid] < first_gid) lo = mid + 1; else hi = mid;
                 }
                 u.hpos = lo;
-                if (lo < u.hend) u.next_h = (int64_t)p.hist_cols[lo];
+                if (lo < u.hend) {
+                    const int64_t loc = (int64_t)p.hist_cols[lo] - p.item_id_offset;
+                    u.next_h = loc < p.N ? (uint32_t)loc : 0xFFFFFFFFu;
+                }
             }
             uint32_t acc_phase = 0;
             const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ut * SC_BN);
@@ -342,7 +401,10 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
                 const int64_t it = t - t0;
                 if (it > 0 && refresh_tile(it) && gridDim.x > 1 && !(p.debug & 3)) {
                     const uint32_t T = shared_threshold(p, user - lane, (int)gridDim.x, lane);
-                    if (T != 0u && user_ok) u.thr_f = fmaxf(u.thr_f, float_from_order_key(T));
+                    if (T != 0u && user_ok) {
+                        u.thr_f = fmaxf(u.thr_f, float_from_order_key(T));
+                        if (T != 0xFFFFFFFFu && T > u.thr_hi && !(p.debug & 8)) list_compact(u, T);      // most of a short stream's list is below T
+                    }
                 }
                 mbar_wait(&acc_full[ut], acc_phase);
                 tc_fence_after();
@@ -358,11 +420,11 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&acc_empty[ut]);
                     }
-                    process_chunk(p, u, v, row0 + (uint32_t)(c * 32));
+                    process_chunk(p, mr, u, v, row0 + (uint32_t)(c * 32));
                 }
-                if (__any_sync(0xffffffffu, u.cnt > 0)) drain(p, u);
+                if (__any_sync(0xffffffffu, u.cnt > 0)) drain(p, mr, u);
                 if (user_ok) {                                        // this stream's j-th best so far
-                    const uint32_t jb = p.pub_j == 1 ? u.b1 : (p.pub_j == 2 ? u.b2 : (p.pub_j == 3 ? u.b3 : (uint32_t)(u.thr_key >> 32)));
+                    const uint32_t jb = p.pub_j == 1 ? u.b1 : (p.pub_j == 2 ? u.b2 : (p.pub_j == 3 ? u.b3 : u.thr_hi));
                     if (jb > last_pub) { last_pub = jb; __stcg(pub_user, jb); }
                 }
                 acc_phase ^= 1;
@@ -375,7 +437,8 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
         }
         if (user_ok) {
             unsigned long long* dst = p.partial + ((size_t)blockIdx.x * p.Q + user) * k;
-            for (int e = 0; e < k; ++e) dst[e] = u.L[e * SC_UG];
+            for (int e = 0; e < k; ++e)
+                dst[e] = e < u.n ? (((unsigned long long)u.Lh[e * SC_UG] << 32) | (unsigned long long)u.Ll[e * SC_UG]) : 0ull;
         }
     }
 
