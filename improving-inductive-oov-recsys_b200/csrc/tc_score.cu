@@ -430,10 +430,10 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
                 acc_phase ^= 1;
             }
         }
-        if ((p.debug & 4) && blockIdx.x == 0 && blockIdx.y == 0) {
+        if ((p.debug & 4) && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && blockIdx.y == 0 && (warp & 3) == 0) {
             const int tp = __reduce_add_sync(0xffffffffu, u.n_push), ti = __reduce_add_sync(0xffffffffu, u.n_ins);
             const int mp = __reduce_max_sync(0xffffffffu, u.n_push);
-            if (lane == 0) printf("warp %d: tiles %lld pushes %d (max lane %d) inserts %d drain-steps %d\n", warp, (long long)(t1 - t0), tp, mp, ti, u.n_steps);
+            if (lane == 0) printf("cta %d warp %d: tiles %lld pushes %d (max lane %d) inserts %d drain-steps %d\n", (int)blockIdx.x, warp, (long long)(t1 - t0), tp, mp, ti, u.n_steps);
         }
         if (user_ok) {
             unsigned long long* dst = p.partial + ((size_t)blockIdx.x * p.Q + user) * k;
