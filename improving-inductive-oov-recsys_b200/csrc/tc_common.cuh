@@ -43,12 +43,38 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
+// non-blocking probe (try_wait may park the thread for a system-dependent time before it reports "not yet")
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// try_wait with a suspend-time hint (ns): the hardware parks the thread until the phase completes or the time is up,
+// so a waiting warp does not spend issue slots the working warps of the same scheduler need
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.  The clock is only
+// read every 256 polls (the poll loop used to be a fifth of all instructions the scoring kernel executed).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) __trap();      // ~2 s at 2 GHz
+    uint32_t polls = 0;
+    long long t0 = 0;
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+        if ((++polls & 255u) == 0u) {
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 4000000000ll) __trap();      // ~2 s at 2 GHz
+        }
     }
 }
 
@@ -62,6 +88,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+
+// ask L2 to fetch a tile (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+                 : "memory");
 }
 
 // ---------------------------------------------------------------- tcgen05

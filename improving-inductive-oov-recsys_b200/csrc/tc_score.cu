@@ -5,13 +5,12 @@
 // only ever exists as 128 x 128 fp32 tiles in TMEM.
 //
 // grid = (item ranges, user groups of 512).  Every CTA owns a CONTIGUOUS range of 128-item tiles.  608 threads:
-//   warp 0       TMA producer : the group's four 128-user tiles once (A, resident), then 128-item tiles (B) through
+//   warp 16      TMA producer : the group's four 128-user tiles once (A, resident), then 128-item tiles (B) through
 //                               an mbarrier ring — K-major, 128B-swizzled, straight from the bf16 tables
-//   warp 1       MMA issuer   : per item tile and user tile `ut`, 4 x tcgen05.mma (M 128, N 128, K 16) into
+//   warps 17-18  MMA issuers  : two user tiles `ut` each; per item tile and user tile 4 x tcgen05.mma (M 128, N 128, K 16) into
 //                               accumulator `ut` (TMEM columns ut*128 ..); the tensor core works on the other
 //                               three user tiles while one is being drained
-//   warp 2       TMEM alloc (512 columns)
-//   warps 3-18   epilogue     : thread = one user (TMEM lane).  Per 32-column tcgen05.ld (double-buffered in
+//   warps 0-15   epilogue     : thread = one user (TMEM lane).  Per 32-column tcgen05.ld (double-buffered in
 //                               registers) a NaN-propagating 3-input max tree is compared ONCE with the user's
 //                               threshold; only groups that beat it are scanned, masked (pad / segment / history)
 //                               and inserted into the user's sorted list (smem, thread-private column).
@@ -25,6 +24,15 @@
 // cursor (one register holds the next masked id) instead of searching.
 // Every CTA writes its per-user lists as key64 = (ordered score << 32 | ~local_row); merge_keys_kernel (topk.cu)
 // reduces the per-CTA lists to the final (score desc, id asc) top-k.
+//
+// Sampled pre-pass (large shards): the same TMA / tcgen05 pipeline first visits every `stride`-th FULL item tile with a
+// divergence-free epilogue that only records each user's maximum score of the tile (MODE 1).  score_threshold_kernel
+// then takes, per user, the R-th largest tile maximum with R = k + (masked items of that user inside sampled tiles):
+// every masked item is the maximum of at most one tile, so at least k sampled tiles have an UNMASKED item at or above
+// that value and no score strictly below it can be in the top-k.  The main pass (MODE 0) starts from this threshold
+// (pass rate ~ R / sampled items, e.g. 2e-4 for 1 M items at stride 8) instead of -inf: the fill phase, most list
+// maintenance and the cross-CTA threshold exchange disappear, for `1 / stride` extra MMA work.  Both passes issue the
+// identical MMA sequence for a (user tile, item tile) pair, so a score has the same bits in both.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -42,9 +50,17 @@ constexpr int SC_BM = 128;            // users per MMA (TMEM lanes)
 constexpr int SC_BN = 128;            // items per tile (TMEM columns per accumulator)
 constexpr int SC_NUT = 4;             // user tiles (accumulators) per CTA
 constexpr int SC_UG = SC_BM * SC_NUT; // users per CTA
-constexpr int SC_MAX_STAGES = 6;
-constexpr int SC_EPI_WARP0 = 3;
-constexpr int SC_THREADS = (SC_EPI_WARP0 + 4 * SC_NUT) * 32;   // 608
+constexpr int SC_MAX_STAGES = 10;
+constexpr int SC_L2_AHEAD = 12;          // item tiles the producer asks L2 to fetch ahead of the TMA ring
+// Warp roles.  The SM sub-partition schedulers favour the highest warp id among eligible warps, so the two latency-
+// critical single-thread roles (TMA producer, MMA issuer) take the HIGHEST ids: as warps 0 / 1 they were starved by
+// the sixteen epilogue warps whenever those had work or polled a barrier.
+constexpr int SC_EPI_WARP0 = 0;
+constexpr int SC_EPI_WARPS = 4 * SC_NUT;
+constexpr int SC_W_TMA = SC_EPI_WARPS;                         // 16: TMEM alloc / dealloc + TMA producer
+constexpr int SC_W_ALLOC = SC_W_TMA;
+constexpr int SC_W_MMA = SC_EPI_WARPS + 1;                     // 17, 18: MMA issuers, two user tiles each
+constexpr int SC_THREADS = (SC_EPI_WARPS + 3) * 32;            // 608
 constexpr int SC_KMAX = 24;              // smem: lists k x 512 x 8 B next to A (64 KB), the queues (32 KB) and >= 2 B stages
 constexpr int SC_PUB_MAXP = 160;          // streams per user the threshold refresh reads (>= SM count)
 constexpr int SC_QCAP = 8;               // queued candidates per user between drains
@@ -76,6 +92,11 @@ struct ScoreParams {
     int pub_j, pub_groups;              // j (1..3, or k when P is too small) and G of the threshold-sharing scheme
     int debug;                          // profiling only (OOV_SCORE_DEBUG): bit 0 = no candidate processing, bit 1 = no threshold sharing
     unsigned long long* partial;        // [gridDim.x][Q][k]
+    int64_t tile_stride;                // MODE 1: tiles tile_begin + i * tile_stride, i in [0, n_visit)
+    int64_t n_visit;                    // tiles visited by the whole grid (MODE 0: tile_end - tile_begin)
+    uint32_t* tile_max;                 // MODE 1 out: [Q][n_visit] ordered-float key of the user's best score in tile i
+    const uint32_t* thr_init;           // MODE 0 in (optional): [Q] key no top-k score is below (0 = none)
+    int share;                          // MODE 0: exchange thresholds between the CTAs of a user
 };
 
 // per-thread (= per-user) epilogue state.  The list is UNSORTED and split in two u32 arrays (ordered score / ~row):
@@ -227,11 +248,17 @@ __device__ __forceinline__ void process_chunk(const ScoreParams& p, const MaskRo
     for (int g = 0; g < 11; ++g) hits += (m[g] < u.thr_f) ? 0 : 1;
     if (!__any_sync(0xffffffffu, u.cnt + 3 * hits > SC_QCAP)) {
         const float thr = u.thr_f;
+        // second vote per quarter of the chunk (columns 0-8, 9-17, 18-26, 27-31): usually one quarter of one lane hits
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            if (!(__uint_as_float(v[j]) < thr)) {
-                u.Qe[u.cnt * SC_UG] = ((unsigned long long)v[j] << 32) | (unsigned long long)(col0 + (uint32_t)j);
-                ++u.cnt; ++u.n_push;
+        for (int qq = 0; qq < 4; ++qq) {
+            const float mq = qq == 0 ? m0 : (qq == 1 ? m1 : (qq == 2 ? m2 : m3));
+            if (!__any_sync(0xffffffffu, !(mq < thr))) continue;
+#pragma unroll
+            for (int j = 9 * qq; j < (qq < 3 ? 9 * qq + 9 : 32); ++j) {
+                if (!(__uint_as_float(v[j]) < thr)) {
+                    u.Qe[u.cnt * SC_UG] = ((unsigned long long)v[j] << 32) | (unsigned long long)(col0 + (uint32_t)j);
+                    ++u.cnt; ++u.n_push;
+                }
             }
         }
         return;
@@ -264,6 +291,8 @@ __device__ __forceinline__ void process_chunk(const ScoreParams& p, const MaskRo
     }
 }
 
+// MODE 0: scoring + masks + top-k lists.  MODE 1: sampled pre-pass, per-user maximum of every visited tile.
+template <int MODE>
 __global__ void __launch_bounds__(SC_THREADS, 1)
 tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmI, const ScoreParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -271,9 +300,10 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
     unsigned char* sA = smem;                                        // SC_NUT x 16 KB
     unsigned char* sB = smem + SC_NUT * SC_A_BYTES;                  // stages x 16 KB
     uint32_t* lists_hi = reinterpret_cast<uint32_t*>(sB + p.stages * SC_B_BYTES);                     // [k][SC_UG]
-    uint32_t* lists_lo = lists_hi + (size_t)p.k * SC_UG;                                               // [k][SC_UG]
-    unsigned long long* queues = reinterpret_cast<unsigned long long*>(lists_lo + (size_t)p.k * SC_UG);   // [SC_QCAP][SC_UG]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(queues + (size_t)SC_QCAP * SC_UG);
+    const size_t list_rows = MODE == 1 ? 0 : (size_t)p.k, queue_rows = MODE == 1 ? 0 : (size_t)SC_QCAP;   // the pre-pass keeps no lists
+    uint32_t* lists_lo = lists_hi + list_rows * SC_UG;                                                 // [k][SC_UG]
+    unsigned long long* queues = reinterpret_cast<unsigned long long*>(lists_lo + list_rows * SC_UG);     // [SC_QCAP][SC_UG]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(queues + queue_rows * SC_UG);
     uint64_t* full_bar = bars;                          // [SC_MAX_STAGES]
     uint64_t* empty_bar = bars + SC_MAX_STAGES;         // [SC_MAX_STAGES]
     uint64_t* a_full = bars + 2 * SC_MAX_STAGES;        // [1]
@@ -285,73 +315,110 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
     const int64_t q0 = (int64_t)blockIdx.y * SC_UG;
     const int64_t q_left = p.Q - q0;
     const int n_ut = q_left >= SC_UG ? SC_NUT : (int)((q_left + SC_BM - 1) / SC_BM);   // valid 128-user tiles
-    // contiguous tile range of this CTA
-    const int64_t n_tiles = p.tile_end - p.tile_begin;
-    const int64_t t0 = p.tile_begin + n_tiles * blockIdx.x / gridDim.x;
-    const int64_t t1 = p.tile_begin + n_tiles * (blockIdx.x + 1) / gridDim.x;
+    // contiguous range of visit indices of this CTA; visit i is item tile tile_begin + i * stride
+    const int64_t stride = MODE == 1 ? p.tile_stride : 1;
+    const int64_t t0 = p.n_visit * blockIdx.x / gridDim.x;
+    const int64_t t1 = p.n_visit * (blockIdx.x + 1) / gridDim.x;
 
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmU); tma_prefetch_desc(&tmI); }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], (uint32_t)n_ut); }
+    if (warp == SC_W_TMA && lane == 0) { tma_prefetch_desc(&tmU); tma_prefetch_desc(&tmI); }
+    if (warp == SC_W_MMA && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], n_ut > 2 ? 2u : 1u); }
         mbar_init(a_full, 1);
         for (int a = 0; a < SC_NUT; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (warp == SC_W_ALLOC) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == SC_W_TMA) {
         if (lane == 0) {
             mbar_arrive_expect_tx(a_full, (uint32_t)(n_ut * SC_A_BYTES));
             for (int ut = 0; ut < n_ut; ++ut) tma_load_2d(sA + ut * SC_A_BYTES, &tmU, a_full, 0, (int)(q0 + ut * SC_BM));
             int stage = 0; uint32_t phase = 0;
+            // The ring holds only a few 16 KB tiles (the lists take the shared memory), less than HBM latency x the
+            // rate the MMAs consume them: tiles are requested into L2 well ahead, so the ring loads are L2 hits.
+            for (int64_t t = t0; t < t1 && t < t0 + SC_L2_AHEAD; ++t)
+                tma_prefetch_l2_2d(&tmI, 0, (int)((p.tile_begin + t * stride) * SC_BN));
             for (int64_t t = t0; t < t1; ++t) {
+                if (t + SC_L2_AHEAD < t1) tma_prefetch_l2_2d(&tmI, 0, (int)((p.tile_begin + (t + SC_L2_AHEAD) * stride) * SC_BN));
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 mbar_arrive_expect_tx(&full_bar[stage], SC_B_BYTES);
-                tma_load_2d(sB + stage * SC_B_BYTES, &tmI, &full_bar[stage], 0, (int)(t * SC_BN));
+                tma_load_2d(sB + stage * SC_B_BYTES, &tmI, &full_bar[stage], 0, (int)((p.tile_begin + t * stride) * SC_BN));
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {
+    } else if (warp >= SC_W_MMA) {
+        // Two issuer warps, each serving two user tiles in turn.  A single issuer for the four accumulators was the
+        // bottleneck of the whole kernel: every hand-over costs it two barrier reads (~90-150 cycles each) on top of the
+        // issue itself, four times per item tile, in series — more than the 4 x 256 cycles the MMAs take.  The waits
+        // park the thread (try_wait), they do not poll.  (One issuer per user tile is no faster and its 672 threads
+        // leave the epilogue 80 registers instead of 96.  Splitting the accumulators into 64-column halves to overlap
+        // drain and MMA was tried and lost: N = 64 MMAs are shared-memory bound in SS mode.)
+        const int iw = warp - SC_W_MMA;
+        if (lane == 0 && 2 * iw < n_ut) {
             constexpr uint32_t idesc = make_idesc_bf16_f32(SC_BM, SC_BN);
             mbar_wait(a_full, 0);
-            // Each user tile advances through the item tiles on its own: whichever accumulator has been drained gets
-            // its next MMA, so one slow epilogue (a burst of candidates) does not stall the other three.  The B ring
-            // bounds the drift: a stage is released when every user tile has consumed it (empty_bar counts n_ut).
-            int64_t nxt[SC_NUT];
-            int stg[SC_NUT];
-            uint32_t ph[SC_NUT], aph[SC_NUT];
-#pragma unroll
-            for (int ut = 0; ut < SC_NUT; ++ut) { nxt[ut] = t0; stg[ut] = 0; ph[ut] = 0; aph[ut] = 0; }
-            int remaining = n_ut;
-            if (t1 <= t0) remaining = 0;
-            while (remaining > 0) {
-#pragma unroll
-                for (int ut = 0; ut < SC_NUT; ++ut) {
-                    if (ut >= n_ut || nxt[ut] >= t1) continue;
-                    if (!mbar_try_wait(&acc_empty[ut], aph[ut] ^ 1)) continue;     // epilogue still draining this accumulator
-                    if (!mbar_try_wait(&full_bar[stg[ut]], ph[ut])) continue;      // item tile not landed yet (never block: the
-                                                                                   // slowest user tile frees the stage it needs)
+            const int n_mine = n_ut - 2 * iw >= 2 ? 2 : 1;
+            int stage = 0; uint32_t phase = 0, acc_phase = 0;
+            for (int64_t t = t0; t < t1; ++t) {
+                for (int j = 0; j < n_mine; ++j) {
+                    const int ut = 2 * iw + j;
+                    mbar_wait(&acc_empty[ut], acc_phase ^ 1);                     // epilogue has drained the accumulator
+                    if (j == 0) mbar_wait(&full_bar[stage], phase);               // item tile has landed
                     tc_fence_after();
-                    const uint64_t bdesc = make_sw128_desc(smem_u32(sB + stg[ut] * SC_B_BYTES));
                     const uint64_t adesc = make_sw128_desc(smem_u32(sA + ut * SC_A_BYTES));
+                    const uint64_t bdesc = make_sw128_desc(smem_u32(sB + stage * SC_B_BYTES));
                     const uint32_t d_tmem = tmem_base + (uint32_t)(ut * SC_BN);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
                         tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, kk ? 1u : 0u);
                     tc_commit(&acc_full[ut]);
-                    tc_commit(&empty_bar[stg[ut]]);                               // one of n_ut arrivals for this stage
-                    aph[ut] ^= 1;
-                    if (++stg[ut] == p.stages) { stg[ut] = 0; ph[ut] ^= 1; }
-                    if (++nxt[ut] == t1) --remaining;
                 }
+                tc_commit(&empty_bar[stage]);                                     // one arrival per issuer for this stage
+                acc_phase ^= 1;
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp >= SC_EPI_WARP0) {
+    } else if (warp < SC_EPI_WARPS && MODE == 1) {
+        // pre-pass epilogue: the user's maximum score of every visited tile, no masks, no divergence
+        const int ut = (warp - SC_EPI_WARP0) >> 2;
+        const int q = warp & 3;
+        const int64_t user = q0 + ut * SC_BM + q * 32 + lane;
+        if (ut < n_ut) {
+            uint32_t acc_phase = 0;
+            const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ut * SC_BN);
+            uint32_t* dst = p.tile_max + (size_t)(user < p.Q ? user : 0) * p.n_visit;
+            for (int64_t t = t0; t < t1; ++t) {
+                mbar_wait(&acc_full[ut], acc_phase);
+                tc_fence_after();
+                uint32_t v[32];
+                float mx = -INFINITY;
+#pragma unroll 1
+                for (int c = 0; c < SC_BN / 32; ++c) {
+                    tc_ld_32x32(t_lane + (uint32_t)(c * 32), v);
+                    tc_wait_ld();
+                    if (c == SC_BN / 32 - 1) {                         // the accumulator is in registers: hand it back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[ut]);
+                    }
+                    float m[11];
+#pragma unroll
+                    for (int j = 0; j < 10; ++j)
+                        m[j] = max3_nan(__uint_as_float(v[3 * j]), __uint_as_float(v[3 * j + 1]), __uint_as_float(v[3 * j + 2]));
+                    m[10] = max2_nan(__uint_as_float(v[30]), __uint_as_float(v[31]));
+                    const float m0 = max3_nan(m[0], m[1], m[2]), m1 = max3_nan(m[3], m[4], m[5]);
+                    const float m2 = max3_nan(m[6], m[7], m[8]), m3 = max3_nan(m[9], m[10], mx);
+                    mx = max2_nan(max3_nan(m0, m1, m2), m3);
+                }
+                if (user < p.Q) dst[t] = float_order_key(mx);
+                acc_phase ^= 1;
+            }
+        }
+    } else if (warp < SC_EPI_WARPS) {
         const int ut = (warp - SC_EPI_WARP0) >> 2;                    // which user tile / accumulator
         const int q = warp & 3;                                       // TMEM lane quarter this warp may access
         const int u_local = ut * SC_BM + q * 32 + lane;               // column of `lists`
@@ -366,6 +433,11 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
         u.b1 = u.b2 = u.b3 = 0u;
         u.n_push = u.n_ins = u.n_steps = 0;
         u.thr_f = user_ok ? -INFINITY : INFINITY;                     // padding lanes never take a candidate
+        if (user_ok && p.thr_init != nullptr) {
+            const uint32_t T = p.thr_init[user];
+            if (T != 0u) u.thr_f = float_from_order_key(T);           // NaN (k NaN tiles): nothing is filtered
+        }
+        const bool share = p.share && gridDim.x > 1 && !(p.debug & 3);
         u.hpos = 0; u.hend = 0; u.next_h = 0xFFFFFFFFu;
         // mask tests on local rows (uint32): [0, N) holds global ids item_id_offset ..
         MaskRows mr;
@@ -376,14 +448,14 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
             mr.seg_lo = lo <= 0 ? 0u : (lo >= p.N ? (uint32_t)p.N : (uint32_t)lo);
             mr.seg_hi = hi <= 0 ? 0u : (hi >= p.N ? (uint32_t)p.N : (uint32_t)hi);
         }
-        uint32_t* pub_user = p.pub + (size_t)(user_ok ? user : 0) * gridDim.x + blockIdx.x;
+        uint32_t* pub_user = share ? p.pub + (size_t)(user_ok ? user : 0) * gridDim.x + blockIdx.x : nullptr;
         uint32_t last_pub = 0u;
 
         if (ut < n_ut) {
             if (p.hist_rowptr != nullptr && user_ok) {
                 int lo = p.hist_rowptr[user];
                 u.hend = p.hist_rowptr[user + 1];
-                const int64_t first_gid = t0 * SC_BN + p.item_id_offset;
+                const int64_t first_gid = (p.tile_begin + t0) * SC_BN + p.item_id_offset;
                 int hi = u.hend;
                 while (lo < hi) {                                     // lower_bound(first id of this CTA's range)
                     const int mid = (lo + hi) >> 1;
@@ -399,7 +471,7 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
             const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ut * SC_BN);
             for (int64_t t = t0; t < t1; ++t) {
                 const int64_t it = t - t0;
-                if (it > 0 && refresh_tile(it) && gridDim.x > 1 && !(p.debug & 3)) {
+                if (share && it > 0 && refresh_tile(it)) {
                     const uint32_t T = shared_threshold(p, user - lane, (int)gridDim.x, lane);
                     if (T != 0u && user_ok) {
                         u.thr_f = fmaxf(u.thr_f, float_from_order_key(T));
@@ -408,7 +480,7 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
                 }
                 mbar_wait(&acc_full[ut], acc_phase);
                 tc_fence_after();
-                const uint32_t row0 = (uint32_t)(t * SC_BN);          // first local item row of the tile
+                const uint32_t row0 = (uint32_t)((p.tile_begin + t) * SC_BN);   // first local item row of the tile
                 uint32_t v[32];
 #pragma unroll 1
                 for (int c = 0; c < SC_BN / 32; ++c) {
@@ -423,7 +495,7 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
                     process_chunk(p, mr, u, v, row0 + (uint32_t)(c * 32));
                 }
                 if (__any_sync(0xffffffffu, u.cnt > 0)) drain(p, mr, u);
-                if (user_ok) {                                        // this stream's j-th best so far
+                if (user_ok && share) {                               // this stream's j-th best so far
                     const uint32_t jb = p.pub_j == 1 ? u.b1 : (p.pub_j == 2 ? u.b2 : (p.pub_j == 3 ? u.b3 : u.thr_hi));
                     if (jb > last_pub) { last_pub = jb; __stcg(pub_user, jb); }
                 }
@@ -444,19 +516,88 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == SC_W_ALLOC) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
 }
 
+// Pre-pass threshold: one warp per user.  R = k + (masked items of the user that lie in sampled tiles); the R-th
+// largest of the user's n_s tile maxima (ordered keys, radix select 4 x 8 bits over a warp-private histogram) is a
+// bound no top-k score is below.  0 = no bound (fewer than R sampled tiles).
+constexpr int THR_WARPS = 8;
+__global__ void __launch_bounds__(THR_WARPS * 32)
+score_threshold_kernel(const uint32_t* __restrict__ tile_max, int64_t n_s, int64_t Q, int k, int64_t tile_first,
+                       int64_t tile_stride, int64_t item_id_offset, int64_t N, int mask_pad,
+                       const int32_t* __restrict__ hist_rowptr, const int32_t* __restrict__ hist_cols,
+                       uint32_t* __restrict__ thr_out) {
+    __shared__ uint32_t hist_s[THR_WARPS][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t user = (int64_t)blockIdx.x * THR_WARPS + warp;
+    if (user >= Q) return;
+    uint32_t* hist = hist_s[warp];
+    auto sampled = [&](int64_t loc) -> bool {                         // local row inside a sampled tile?
+        if (loc < 0 || loc >= N) return false;
+        const int64_t d = loc / SC_BN - tile_first;
+        return d >= 0 && d % tile_stride == 0 && d / tile_stride < n_s;
+    };
+    int h = 0;
+    if (hist_rowptr != nullptr) {
+        const int e = hist_rowptr[user + 1];
+        for (int j = hist_rowptr[user] + lane; j < e; j += 32) h += sampled((int64_t)hist_cols[j] - item_id_offset) ? 1 : 0;
+    }
+    h = __reduce_add_sync(0xffffffffu, h);
+    if (mask_pad && sampled(-item_id_offset)) ++h;
+    int64_t remaining = (int64_t)k + h;                               // rank (1 = largest) still to find
+    if (remaining > n_s) { if (lane == 0) thr_out[user] = 0u; return; }
+    const uint32_t* row = tile_max + (size_t)user * n_s;
+    uint32_t prefix = 0u, mask = 0u;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hist[lane * 8 + j] = 0u;
+        __syncwarp();
+        for (int64_t i = lane; i < n_s; i += 32) {
+            const uint32_t v = row[i];
+            if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255u], 1u);
+        }
+        __syncwarp();
+        uint32_t c[8], lane_sum = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { c[j] = hist[lane * 8 + j]; lane_sum += c[j]; }
+        // values in bins above this lane's eight bins
+        uint32_t incl = lane_sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_down_sync(0xffffffffu, incl, d);
+            if (lane + d < 32) incl += y;
+        }
+        uint32_t acc = incl - lane_sum;
+        int found = -1;
+        uint32_t rem_new = 0u;
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {
+            if (found < 0 && (int64_t)acc < remaining && (int64_t)(acc + c[j]) >= remaining) { found = lane * 8 + j; rem_new = (uint32_t)(remaining - acc); }
+            acc += c[j];
+        }
+        const unsigned who = __ballot_sync(0xffffffffu, found >= 0);  // exactly one lane
+        const int src = __ffs(who) - 1;
+        found = __shfl_sync(0xffffffffu, found, src);
+        rem_new = __shfl_sync(0xffffffffu, rem_new, src);
+        prefix |= (uint32_t)found << shift;
+        mask |= 255u << shift;
+        remaining = rem_new;
+        __syncwarp();
+    }
+    if (lane == 0) thr_out[user] = prefix;
+}
+
 static int score_stages(int k) {
-    const int fixed = 1024 + SC_NUT * SC_A_BYTES + (k + SC_QCAP) * SC_UG * 8 + 256;
+    const int fixed = 1024 + SC_NUT * SC_A_BYTES + (k + SC_QCAP) * SC_UG * 8 + 512;
     int s = (SC_SMEM_MAX - fixed) / SC_B_BYTES;
     return s > SC_MAX_STAGES ? SC_MAX_STAGES : s;
 }
 static size_t score_smem_bytes(int k, int stages) {
-    return 1024 + SC_NUT * SC_A_BYTES + (size_t)stages * SC_B_BYTES + (size_t)(k + SC_QCAP) * SC_UG * 8 + 256;
+    return 1024 + SC_NUT * SC_A_BYTES + (size_t)stages * SC_B_BYTES + (size_t)(k + SC_QCAP) * SC_UG * 8 + 512;
 }
 
 bool score_tc_supported(int dtype, int D, int k) {
@@ -475,9 +616,40 @@ static int score_grid_x(int64_t Q, int64_t n_tiles) {
 
 static size_t score_pub_bytes(int64_t Q, int gx) { return align_up((size_t)gx * Q * 4, 256); }
 
+// sampled pre-pass: every `stride`-th full tile once the shard has enough tiles for a useful threshold
+constexpr int64_t SC_PRE_MIN_TILES = 256;
+static int64_t score_pre_stride(int64_t n_full_tiles) {
+    if (n_full_tiles < SC_PRE_MIN_TILES) return 0;
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("OOV_SCORE_STRIDE"); forced = e ? atoi(e) : 0; }   // profiling only; 1 = no pre-pass
+    if (forced == 1) return 0;
+    if (forced > 1) return forced;
+    int64_t s = 2;
+    while (s < 16 && n_full_tiles / (2 * s) >= 512) s *= 2;          // keep >= 512 sampled tiles, at most 1/2 .. 1/16 extra work
+    return s;
+}
+// most tiles any kept segment of an N-row shard can sample (the stride grows with the segment)
+static int64_t score_pre_max_visits(int64_t N) {
+    const int64_t nf = N / SC_BN;
+    if (score_pre_stride(nf) == 0) return 0;
+    int64_t best = 0;
+    for (int64_t s = 2; s <= 16; s *= 2) {                            // segments whose stride is s have < 1024 s tiles (s < 16)
+        const int64_t top = s < 16 ? (nf < 1024 * s ? nf : 1024 * s) : nf;
+        if (cdiv(top, s) > best) best = cdiv(top, s);
+    }
+    const int64_t f = score_pre_stride(nf);
+    if (f > 0 && cdiv(nf, f) > best) best = cdiv(nf, f);
+    return best;
+}
+static size_t score_thr_bytes(int64_t Q) { return align_up((size_t)Q * 4, 256); }
+static size_t score_pre_bytes(int64_t Q, int64_t N) {
+    const int64_t nv = score_pre_max_visits(N);
+    return nv == 0 ? 0 : score_thr_bytes(Q) + align_up((size_t)Q * (size_t)nv * 4, 256);
+}
+
 size_t score_tc_workspace(int64_t Q, int64_t N, int k) {
     const int gx = score_grid_x(Q, cdiv(N > 0 ? N : 1, SC_BN));
-    return score_pub_bytes(Q, gx) + align_up((size_t)gx * Q * k * 8, 256);
+    return score_pub_bytes(Q, gx) + align_up((size_t)gx * Q * k * 8, 256) + score_pre_bytes(Q, N);
 }
 
 int score_tc_run(const void* users, const void* items, int64_t Q, int64_t N, int D, int k, int64_t item_id_offset,
@@ -505,8 +677,30 @@ int score_tc_run(const void* users, const void* items, int64_t Q, int64_t N, int
     p.pub_groups = gx < 32 ? gx : 32;                                // group = streams congruent modulo 32
     p.pub_j = (k + p.pub_groups - 1) / p.pub_groups;
     if (p.pub_j > 3) { p.pub_groups = 1; p.pub_j = k; }              // few long streams: share the plain k-th best
-    cudaError_t ce = cudaMemsetAsync(p.pub, 0, (size_t)gx * Q * 4, st);
-    OOV_REQUIRE(ce == cudaSuccess, OOV_ERR_CUDA, "cudaMemsetAsync(threshold array): %s", cudaGetErrorString(ce));
+    p.n_visit = n_tiles; p.tile_stride = 1; p.share = 1;
+
+    // sampled pre-pass over the FULL tiles of the kept segment (no zero-filled or segment-masked rows inside)
+    const int64_t full_begin = hi > lo ? cdiv(lo, SC_BN) : 0, full_end = hi > lo ? hi / SC_BN : 0;
+    const int64_t pre_stride = score_pre_stride(full_end - full_begin);
+    ScoreParams pa = p;
+    if (pre_stride > 0) {
+        pa.stages = SC_MAX_STAGES;                                    // no lists in the pre-pass: the whole shared memory is TMA ring
+        pa.tile_begin = full_begin;
+        pa.tile_stride = pre_stride;
+        pa.n_visit = cdiv(full_end - full_begin, pre_stride);
+        unsigned char* w = reinterpret_cast<unsigned char*>(workspace) + score_pub_bytes(Q, gx) + align_up((size_t)gx * Q * k * 8, 256);
+        uint32_t* thr = reinterpret_cast<uint32_t*>(w);
+        pa.tile_max = reinterpret_cast<uint32_t*>(w + score_thr_bytes(Q));
+        const size_t need_pre = (size_t)(w - reinterpret_cast<unsigned char*>(workspace)) + score_thr_bytes(Q) + (size_t)Q * pa.n_visit * 4;
+        OOV_REQUIRE(workspace_bytes >= need_pre, OOV_ERR_WORKSPACE, "oov_fullsort_topk (tcgen05): workspace %zu < %zu (pre-pass)",
+                    workspace_bytes, need_pre);
+        p.thr_init = thr;
+        p.share = (p.debug & 16) ? 1 : 0;                            // the sampled threshold beats the exchanged one from the first tile
+    }
+    if (p.share) {
+        cudaError_t ce = cudaMemsetAsync(p.pub, 0, (size_t)gx * Q * 4, st);
+        OOV_REQUIRE(ce == cudaSuccess, OOV_ERR_CUDA, "cudaMemsetAsync(threshold array): %s", cudaGetErrorString(ce));
+    }
 
     CUtensorMap tmU, tmI;
     int rc = make_tmap_bf16_2d(&tmU, users, (uint64_t)D, (uint64_t)Q, (uint64_t)D * 2, SC_BM);
@@ -516,12 +710,22 @@ int score_tc_run(const void* users, const void* items, int64_t Q, int64_t N, int
     const size_t smem = score_smem_bytes(k, p.stages);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tc_score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM_MAX);
-        OOV_REQUIRE(e == cudaSuccess, OOV_ERR_CUDA, "cudaFuncSetAttribute(tc_score_topk_kernel): %s", cudaGetErrorString(e));
+        cudaError_t e = cudaFuncSetAttribute(tc_score_topk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM_MAX);
+        OOV_REQUIRE(e == cudaSuccess, OOV_ERR_CUDA, "cudaFuncSetAttribute(tc_score_topk_kernel<0>): %s", cudaGetErrorString(e));
+        e = cudaFuncSetAttribute(tc_score_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM_MAX);
+        OOV_REQUIRE(e == cudaSuccess, OOV_ERR_CUDA, "cudaFuncSetAttribute(tc_score_topk_kernel<1>): %s", cudaGetErrorString(e));
         attr_done = true;
     }
     const dim3 grid((unsigned)gx, (unsigned)cdiv(Q, SC_UG));
-    tc_score_topk_kernel<<<grid, SC_THREADS, smem, st>>>(tmU, tmI, p);
+    if (pre_stride > 0) {
+        tc_score_topk_kernel<1><<<grid, SC_THREADS, score_smem_bytes(-SC_QCAP, pa.stages), st>>>(tmU, tmI, pa);
+        OOV_LAUNCH_CHECK("tc_score_topk_kernel<1> (pre-pass)");
+        score_threshold_kernel<<<(unsigned)cdiv(Q, THR_WARPS), THR_WARPS * 32, 0, st>>>(
+            pa.tile_max, pa.n_visit, Q, k, pa.tile_begin, pa.tile_stride, item_id_offset, N, mask_pad, hist_rowptr, hist_cols,
+            const_cast<uint32_t*>(p.thr_init));
+        OOV_LAUNCH_CHECK("score_threshold_kernel");
+    }
+    tc_score_topk_kernel<0><<<grid, SC_THREADS, smem, st>>>(tmU, tmI, p);
     OOV_LAUNCH_CHECK("tc_score_topk_kernel");
     return launch_merge_keys(p.partial, gx, Q, k, item_id_offset, out_scores, out_idx, st);
 }

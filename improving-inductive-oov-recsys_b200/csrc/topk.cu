@@ -211,20 +211,28 @@ merge_keys_kernel(const unsigned long long* __restrict__ partial, int P, int64_t
     WarpList<KR> fin;
     fin.clear();
     unsigned long long t = 0ull;
-    const int64_t total = (int64_t)P * k;
-    for (int64_t i0 = 0; i0 < total; i0 += 32) {
-        const int64_t i = i0 + lane;
-        unsigned long long key = 0ull;
-        if (i < total) {
-            const int64_t p = i / k, j = i - p * k;
-            key = partial[((size_t)p * Q + q) * k + j];
+    const int total = P * k;
+    constexpr int MU = 8;                                   // loads in flight per lane: the loop is latency-bound otherwise
+    for (int i0 = 0; i0 < total; i0 += 32 * MU) {
+        unsigned long long key[MU];
+#pragma unroll
+        for (int u = 0; u < MU; ++u) {
+            const int i = i0 + u * 32 + lane;
+            key[u] = 0ull;
+            if (i < total) {
+                const int p = i / k, j = i - p * k;
+                key[u] = __ldcs(partial + ((size_t)p * Q + q) * k + j);
+            }
         }
-        unsigned m = __ballot_sync(0xffffffffu, key > t);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const unsigned long long x = __shfl_sync(0xffffffffu, key, src);
-            if (x > t) { fin.insert(x, lane); t = fin.kth(k); }
+#pragma unroll
+        for (int u = 0; u < MU; ++u) {
+            unsigned m = __ballot_sync(0xffffffffu, key[u] > t);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const unsigned long long x = __shfl_sync(0xffffffffu, key[u], src);
+                if (x > t) { fin.insert(x, lane); t = fin.kth(k); }
+            }
         }
     }
 #pragma unroll

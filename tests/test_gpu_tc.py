@@ -176,6 +176,39 @@ def test_tc_score_topk_vs_fp32_reference(Q, N, D, k):
             assert (i_.cpu().numpy()[:, :-1][tie] < i_.cpu().numpy()[:, 1:][tie]).all(), nm
 
 
+def test_tc_score_prepass_history_holds_the_top_items():
+    """Adversarial case for the sampled pre-pass threshold (tc_score.cu): every user's history is exactly the user's
+    40 best items, so most sampled tile maxima belong to masked items; plus NaN items and a pad row in a sampled tile."""
+    from oov_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(7)
+    Q, N, D, k = 96, 100_000, 64, 20
+    users = torch.randn(Q, D, generator=g).to(torch.bfloat16).to(DEV)
+    items = torch.randn(N, D, generator=g).to(torch.bfloat16).to(DEV)
+    items[[77, 50_000]] = float("nan")
+    full = users.float() @ items.float().T
+    top = torch.topk(torch.nan_to_num(full, nan=-1e30), 40, dim=1).indices          # [Q, 40]
+    hu = torch.arange(Q, device=DEV).repeat_interleave(40)
+    hi = top.reshape(-1)
+    hist = ops.pairs_to_csr(hu, hi, Q)
+    ref = full.clone()
+    ref[:, 0] = -float("inf")
+    ref[hu, hi] = -float("inf")
+    for seg in ((0, 1 << 62), (1000, 90_000)):
+        r = ref.clone()
+        r[:, :seg[0]] = -float("inf")
+        r[:, min(seg[1], N):] = -float("inf")
+        r = torch.nan_to_num(r, nan=float("inf"), posinf=float("inf"), neginf=-float("inf"))    # NaN ranks first
+        s_tc, i_tc = ops.fullsort_topk(users, items, k, hist=hist, seg=seg, path=ops.PATH_TCGEN05)
+        s_si, i_si = ops.fullsort_topk(users, items, k, hist=hist, seg=seg, path=ops.PATH_SIMT_FP32)
+        ok, msg = o.topk_sets_match(r.cpu().numpy(), i_tc.cpu().numpy(), k, rtol=1e-5, atol=1e-4)
+        assert ok, f"seg={seg}: {msg}"
+        want = [77, 50_000] if seg[0] == 0 else [50_000]
+        assert torch.equal(i_tc[:, :len(want)].cpu(), torch.tensor(want).expand(Q, len(want)))   # NaN first, id ascending
+        # SIMT fp32 accumulates in a different order: index sets agree up to near-ties, checked against ref above
+        ok, msg = o.topk_sets_match(r.cpu().numpy(), i_si.cpu().numpy(), k, rtol=1e-5, atol=1e-4)
+        assert ok, f"simt seg={seg}: {msg}"
+
+
 def test_tc_score_nan_rows_rank_first():
     """An all-zero LSH multi-hot row gives a NaN item embedding (lsh_embedder.py:158); torch.topk ranks NaN first."""
     from oov_b200 import ops
