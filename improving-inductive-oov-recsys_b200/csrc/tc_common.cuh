@@ -71,6 +71,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t polls = 0;
     long long t0 = 0;
     while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+        // try_wait comes back after a few tens of cycles whatever the hint says; a short sleep keeps the waiting warps
+        // of the scoring epilogue from taking a third of the issue slots of the warps that still have work
+        if (polls >= 4u) __nanosleep(32);
         if ((++polls & 255u) == 0u) {
             if (t0 == 0) t0 = clock64();
             else if (clock64() - t0 > 4000000000ll) __trap();      // ~2 s at 2 GHz

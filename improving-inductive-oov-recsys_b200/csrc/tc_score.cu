@@ -41,8 +41,8 @@
 
 namespace oov {
 
-int launch_merge_keys(const unsigned long long* partial, int P, int64_t Q, int k, int64_t off, float* out_scores,
-                      int64_t* out_idx, cudaStream_t st);
+int launch_merge_keys(const unsigned long long* partial, const uint8_t* partial_n, int P, int64_t Q, int k, int64_t off,
+                      float* out_scores, int64_t* out_idx, cudaStream_t st);
 
 namespace tc {
 
@@ -91,7 +91,8 @@ struct ScoreParams {
     uint32_t* pub;                      // [Q][gridDim.x] j-th best score of each stream (ordered-float key; 0 = none yet)
     int pub_j, pub_groups;              // j (1..3, or k when P is too small) and G of the threshold-sharing scheme
     int debug;                          // profiling only (OOV_SCORE_DEBUG): bit 0 = no candidate processing, bit 1 = no threshold sharing
-    unsigned long long* partial;        // [gridDim.x][Q][k]
+    unsigned long long* partial;        // [gridDim.x][Q][k]: the first partial_n[stream][user] entries are valid
+    uint8_t* partial_n;                 // [gridDim.x][Q]
     int64_t tile_stride;                // MODE 1: tiles tile_begin + i * tile_stride, i in [0, n_visit)
     int64_t n_visit;                    // tiles visited by the whole grid (MODE 0: tile_end - tile_begin)
     uint32_t* tile_max;                 // MODE 1 out: [Q][n_visit] ordered-float key of the user's best score in tile i
@@ -509,8 +510,11 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
         }
         if (user_ok) {
             unsigned long long* dst = p.partial + ((size_t)blockIdx.x * p.Q + user) * k;
-            for (int e = 0; e < k; ++e)
-                dst[e] = e < u.n ? (((unsigned long long)u.Lh[e * SC_UG] << 32) | (unsigned long long)u.Ll[e * SC_UG]) : 0ull;
+            for (int e = 0; e < u.n; ++e)
+                dst[e] = ((unsigned long long)u.Lh[e * SC_UG] << 32) | (unsigned long long)u.Ll[e * SC_UG];
+            p.partial_n[(size_t)blockIdx.x * p.Q + user] = (uint8_t)u.n;
+        } else if (user < p.Q) {
+            p.partial_n[(size_t)blockIdx.x * p.Q + user] = 0;                     // OOV_SCORE_DEBUG bit 0
         }
     }
 
@@ -556,9 +560,16 @@ score_threshold_kernel(const uint32_t* __restrict__ tile_max, int64_t n_s, int64
 #pragma unroll
         for (int j = 0; j < 8; ++j) hist[lane * 8 + j] = 0u;
         __syncwarp();
-        for (int64_t i = lane; i < n_s; i += 32) {
-            const uint32_t v = row[i];
-            if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255u], 1u);
+        for (int64_t i0 = 0; i0 < n_s; i0 += 32 * 8) {                 // 8 loads in flight per lane: the pass is latency-bound
+            uint32_t v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int64_t i = i0 + j * 32 + lane;
+                v[j] = i < n_s ? __ldg(row + i) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (i0 + j * 32 + lane < n_s && (v[j] & mask) == prefix) atomicAdd(&hist[(v[j] >> shift) & 255u], 1u);
         }
         __syncwarp();
         uint32_t c[8], lane_sum = 0u;
@@ -615,6 +626,7 @@ static int score_grid_x(int64_t Q, int64_t n_tiles) {
 }
 
 static size_t score_pub_bytes(int64_t Q, int gx) { return align_up((size_t)gx * Q * 4, 256); }
+static size_t score_partial_bytes(int64_t Q, int gx, int k) { return align_up((size_t)gx * Q * k * 8, 256) + align_up((size_t)gx * Q, 256); }
 
 // sampled pre-pass: every `stride`-th full tile once the shard has enough tiles for a useful threshold
 constexpr int64_t SC_PRE_MIN_TILES = 256;
@@ -649,7 +661,7 @@ static size_t score_pre_bytes(int64_t Q, int64_t N) {
 
 size_t score_tc_workspace(int64_t Q, int64_t N, int k) {
     const int gx = score_grid_x(Q, cdiv(N > 0 ? N : 1, SC_BN));
-    return score_pub_bytes(Q, gx) + align_up((size_t)gx * Q * k * 8, 256) + score_pre_bytes(Q, N);
+    return score_pub_bytes(Q, gx) + score_partial_bytes(Q, gx, k) + score_pre_bytes(Q, N);
 }
 
 int score_tc_run(const void* users, const void* items, int64_t Q, int64_t N, int D, int k, int64_t item_id_offset,
@@ -668,12 +680,13 @@ int score_tc_run(const void* users, const void* items, int64_t Q, int64_t N, int
     { const char* dbg = getenv("OOV_SCORE_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
     const int64_t n_tiles = p.tile_end - p.tile_begin;
     const int gx = score_grid_x(Q, n_tiles > 0 ? n_tiles : 1);
-    const size_t need = score_pub_bytes(Q, gx) + (size_t)gx * Q * k * 8;
+    const size_t need = score_pub_bytes(Q, gx) + score_partial_bytes(Q, gx, k);
     OOV_REQUIRE(workspace && workspace_bytes >= need, OOV_ERR_WORKSPACE, "oov_fullsort_topk (tcgen05): workspace %zu < %zu",
                 workspace_bytes, need);
     OOV_REQUIRE(aligned(workspace, 8), OOV_ERR_ALIGN, "oov_fullsort_topk (tcgen05): workspace must be 8-byte aligned");
     p.pub = reinterpret_cast<uint32_t*>(workspace);
     p.partial = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + score_pub_bytes(Q, gx));
+    p.partial_n = reinterpret_cast<uint8_t*>(p.partial) + align_up((size_t)gx * Q * k * 8, 256);
     p.pub_groups = gx < 32 ? gx : 32;                                // group = streams congruent modulo 32
     p.pub_j = (k + p.pub_groups - 1) / p.pub_groups;
     if (p.pub_j > 3) { p.pub_groups = 1; p.pub_j = k; }              // few long streams: share the plain k-th best
@@ -688,7 +701,7 @@ int score_tc_run(const void* users, const void* items, int64_t Q, int64_t N, int
         pa.tile_begin = full_begin;
         pa.tile_stride = pre_stride;
         pa.n_visit = cdiv(full_end - full_begin, pre_stride);
-        unsigned char* w = reinterpret_cast<unsigned char*>(workspace) + score_pub_bytes(Q, gx) + align_up((size_t)gx * Q * k * 8, 256);
+        unsigned char* w = reinterpret_cast<unsigned char*>(workspace) + score_pub_bytes(Q, gx) + score_partial_bytes(Q, gx, k);
         uint32_t* thr = reinterpret_cast<uint32_t*>(w);
         pa.tile_max = reinterpret_cast<uint32_t*>(w + score_thr_bytes(Q));
         const size_t need_pre = (size_t)(w - reinterpret_cast<unsigned char*>(workspace)) + score_thr_bytes(Q) + (size_t)Q * pa.n_visit * 4;
@@ -727,7 +740,7 @@ int score_tc_run(const void* users, const void* items, int64_t Q, int64_t N, int
     }
     tc_score_topk_kernel<0><<<grid, SC_THREADS, smem, st>>>(tmU, tmI, p);
     OOV_LAUNCH_CHECK("tc_score_topk_kernel");
-    return launch_merge_keys(p.partial, gx, Q, k, item_id_offset, out_scores, out_idx, st);
+    return launch_merge_keys(p.partial, p.partial_n, gx, Q, k, item_id_offset, out_scores, out_idx, st);
 }
 
 }  // namespace tc

@@ -200,38 +200,72 @@ fullsort_topk_simt(const T* __restrict__ users, const T* __restrict__ items, int
     }
 }
 
-// one warp per user: merge P partial lists of k key64 entries; decode to (score, global id)
+// one warp per user: merge P partial lists of up to k key64 entries; decode to (score, global id).
+// `partial_n` (optional): [P][Q] valid entries per list — the tensor-core kernel's lists are mostly short, and only
+// the valid entries are read (and were written).
 template <int KR>
 __global__ void __launch_bounds__(256)
-merge_keys_kernel(const unsigned long long* __restrict__ partial, int P, int64_t Q, int k, int64_t item_id_offset,
-                  float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+merge_keys_kernel(const unsigned long long* __restrict__ partial, const uint8_t* __restrict__ partial_n, int P, int64_t Q, int k,
+                  int64_t item_id_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
     const int lane = threadIdx.x & 31;
     const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= Q) return;
     WarpList<KR> fin;
     fin.clear();
     unsigned long long t = 0ull;
-    const int total = P * k;
     constexpr int MU = 8;                                   // loads in flight per lane: the loop is latency-bound otherwise
-    for (int i0 = 0; i0 < total; i0 += 32 * MU) {
-        unsigned long long key[MU];
+    if (partial_n != nullptr) {
+        // lane l owns lists l, l + 32, ...: walk them entry by entry, MU lists at a time
+        for (int p0 = 0; p0 < P; p0 += 32 * MU) {
+            int n[MU], nmax = 0;
 #pragma unroll
-        for (int u = 0; u < MU; ++u) {
-            const int i = i0 + u * 32 + lane;
-            key[u] = 0ull;
-            if (i < total) {
-                const int p = i / k, j = i - p * k;
-                key[u] = __ldcs(partial + ((size_t)p * Q + q) * k + j);
+            for (int u = 0; u < MU; ++u) {
+                const int p = p0 + u * 32 + lane;
+                n[u] = p < P ? (int)partial_n[(size_t)p * Q + q] : 0;
+                nmax = n[u] > nmax ? n[u] : nmax;
+            }
+            nmax = __reduce_max_sync(0xffffffffu, nmax);
+            for (int e = 0; e < nmax; ++e) {
+                unsigned long long key[MU];
+#pragma unroll
+                for (int u = 0; u < MU; ++u) {
+                    const int p = p0 + u * 32 + lane;
+                    key[u] = e < n[u] ? __ldcs(partial + ((size_t)p * Q + q) * k + e) : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < MU; ++u) {
+                    unsigned m = __ballot_sync(0xffffffffu, key[u] > t);
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        const unsigned long long x = __shfl_sync(0xffffffffu, key[u], src);
+                        if (x > t) { fin.insert(x, lane); t = fin.kth(k); }
+                    }
+                }
             }
         }
+    } else {
+        const int total = P * k;
+        for (int i0 = 0; i0 < total; i0 += 32 * MU) {
+            unsigned long long key[MU];
 #pragma unroll
-        for (int u = 0; u < MU; ++u) {
-            unsigned m = __ballot_sync(0xffffffffu, key[u] > t);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const unsigned long long x = __shfl_sync(0xffffffffu, key[u], src);
-                if (x > t) { fin.insert(x, lane); t = fin.kth(k); }
+            for (int u = 0; u < MU; ++u) {
+                const int i = i0 + u * 32 + lane;
+                key[u] = 0ull;
+                if (i < total) {
+                    const int p = i / k, j = i - p * k;
+                    key[u] = __ldcs(partial + ((size_t)p * Q + q) * k + j);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < MU; ++u) {
+                unsigned m = __ballot_sync(0xffffffffu, key[u] > t);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const unsigned long long x = __shfl_sync(0xffffffffu, key[u], src);
+                    if (x > t) { fin.insert(x, lane); t = fin.kth(k); }
+                }
             }
         }
     }
@@ -441,7 +475,7 @@ static int launch_fullsort_simt(const T* users, const T* items, int64_t Q, int64
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
         kern<<<grid, FS_THREADS, smem, st>>>(users, items, Q, N, D, k, off, mask_pad, seg_lo, seg_hi, hr, hc, partial); \
         OOV_LAUNCH_CHECK("fullsort_topk_simt");                                                                       \
-        merge_keys_kernel<KR_><<<(unsigned)cdiv(Q * 32, 256), 256, 0, st>>>(partial, P, Q, k, off, out_scores, out_idx); \
+        merge_keys_kernel<KR_><<<(unsigned)cdiv(Q * 32, 256), 256, 0, st>>>(partial, nullptr, P, Q, k, off, out_scores, out_idx); \
         OOV_LAUNCH_CHECK("merge_keys_kernel");                                                                        \
     }
     if (c.KR == 1) OOV_FS_CASE(16, 1)
@@ -452,12 +486,12 @@ static int launch_fullsort_simt(const T* users, const T* items, int64_t Q, int64
 }
 
 // shared with the tcgen05 scoring kernel (tc_score.cu): merge P partial key lists per user
-int launch_merge_keys(const unsigned long long* partial, int P, int64_t Q, int k, int64_t off, float* out_scores,
-                      int64_t* out_idx, cudaStream_t st) {
+int launch_merge_keys(const unsigned long long* partial, const uint8_t* partial_n, int P, int64_t Q, int k, int64_t off,
+                      float* out_scores, int64_t* out_idx, cudaStream_t st) {
     const unsigned blocks = (unsigned)cdiv(Q * 32, 256);
-    if (k <= 32) merge_keys_kernel<1><<<blocks, 256, 0, st>>>(partial, P, Q, k, off, out_scores, out_idx);
-    else if (k <= 64) merge_keys_kernel<2><<<blocks, 256, 0, st>>>(partial, P, Q, k, off, out_scores, out_idx);
-    else merge_keys_kernel<4><<<blocks, 256, 0, st>>>(partial, P, Q, k, off, out_scores, out_idx);
+    if (k <= 32) merge_keys_kernel<1><<<blocks, 256, 0, st>>>(partial, partial_n, P, Q, k, off, out_scores, out_idx);
+    else if (k <= 64) merge_keys_kernel<2><<<blocks, 256, 0, st>>>(partial, partial_n, P, Q, k, off, out_scores, out_idx);
+    else merge_keys_kernel<4><<<blocks, 256, 0, st>>>(partial, partial_n, P, Q, k, off, out_scores, out_idx);
     OOV_LAUNCH_CHECK("merge_keys_kernel");
     return OOV_OK;
 }
