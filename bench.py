@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--workload", default="dhe1m", choices=list(WORKLOADS))
     ap.add_argument("--Q", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     ap.add_argument("--cpu-sample-div", type=int, default=None, help="item subsampling factor of the CPU arm")
     return ap.parse_args()
 
@@ -298,7 +299,8 @@ def main():
                 "n_oov_items": wl["n_items"] - wl["n_old_items"], "n_users": wl["n_users"], "embedding_size": wl["D"],
                 "Q_per_step": wl["Q"], "k": wl["k"], "max_history": wl["max_hist"],
                 "step": "embed Q users + embed all N items + score + mask + top-k (un-amortised, as bpr.py:151-156)",
-                "l2": "per-step working set (tables + activations) > 126 MB L2; no explicit flush"}
+                "l2": "per-step working set (tables + activations) > 126 MB L2; no explicit flush",
+                "launch": "eager (one Python call per kernel)" if args.eager else "whole step replayed from one CUDA graph (GraphedTopK)"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -332,17 +334,23 @@ def main():
     dev_batches = []
     for users, hu, hi in batches:
         u = torch.from_numpy(users).to(device)
-        csr = ops.pairs_to_csr(torch.from_numpy(hu).to(device), torch.from_numpy(hi).to(device), Q)
-        dev_batches.append((u, csr))
+        dhu, dhi = torch.from_numpy(hu).to(device), torch.from_numpy(hi).to(device)
+        csr = ops.pairs_to_csr(dhu, dhi, Q)
+        dev_batches.append((u, csr, dhu, dhi))
     pin = [(torch.from_numpy(u).pin_memory(), torch.from_numpy(hu).pin_memory(), torch.from_numpy(hi).pin_memory())
            for u, hu, hi in batches]
     out_s_host = torch.empty((Q, k), dtype=torch.float32).pin_memory()
     out_i_host = torch.empty((Q, k), dtype=torch.int64).pin_memory()
 
     sr = sharded.ShardedRetrieval(model, N) if world > 1 else None
+    # the public serving call: the whole step (history CSR build, user embed, item-table assembly, scoring, masks,
+    # top-k, candidate all-gather + merge when sharded) captured once in a CUDA graph and replayed per batch
+    gstep = None if args.eager else oov_b200.GraphedTopK(model, Q, k, N, Q * wl["max_hist"], sharded=sr)
 
     def step_resident(b):
-        u, csr = dev_batches[b % n_batches]
+        u, csr, dhu, dhi = dev_batches[b % n_batches]
+        if gstep is not None:
+            return gstep(u, dhu, dhi)
         if sr is None:
             return model.full_sort_topk(u, k, n_total_items=N, hist_csr=csr)
         user_e = model._assemble("user", u, out_dtype=model.table_dtype)
@@ -351,16 +359,19 @@ def main():
 
     def step_e2e(b):
         hu_, hhu, hhi = pin[b % n_batches]
-        u = hu_.to(device, non_blocking=True)
-        hu = hhu.to(device, non_blocking=True)
-        hi = hhi.to(device, non_blocking=True)
-        if sr is None:
-            s, i = model.full_sort_topk({"user_id": u}, k, n_total_items=N, history_index=(hu, hi))
+        if gstep is not None:
+            s, i = gstep(hu_, hhu, hhi)                       # pinned host -> static device buffers, then the graph
         else:
-            csr = ops.pairs_to_csr(hu, hi, Q)
-            user_e = model._assemble("user", u, out_dtype=model.table_dtype)
-            sr.build_shard()
-            s, i = sr.topk(user_e, k, hist=csr)
+            u = hu_.to(device, non_blocking=True)
+            hu = hhu.to(device, non_blocking=True)
+            hi = hhi.to(device, non_blocking=True)
+            if sr is None:
+                s, i = model.full_sort_topk({"user_id": u}, k, n_total_items=N, history_index=(hu, hi))
+            else:
+                csr = ops.pairs_to_csr(hu, hi, Q)
+                user_e = model._assemble("user", u, out_dtype=model.table_dtype)
+                sr.build_shard()
+                s, i = sr.topk(user_e, k, hist=csr)
         out_s_host.copy_(s, non_blocking=True)
         out_i_host.copy_(i, non_blocking=True)
         torch.cuda.current_stream().synchronize()          # the caller consumes the result every step
@@ -394,7 +405,7 @@ def main():
     t_w0 = time.time()
     ms_total = timed(step_resident, args.steps)
     t_w1 = time.time()
-    launches = ops.launch_count() - l0
+    launches = ops.launch_count() - l0 if gstep is None else gstep.launches_per_replay * args.steps
     clocks = sampler.window(t_w0, t_w1) if sampler else None
     h2d = d2h = 0
 
@@ -428,8 +439,7 @@ def main():
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / reps
 
-        u, csr = dev_batches[0]
-        lo, hi_ = (0, N) if sr is None else (sr.segments[1][0], sr.segments[1][1])
+        u, csr = dev_batches[0][0], dev_batches[0][1]
         table = model.build_item_table(N)
         user_e = model._assemble("user", u, out_dtype=model.table_dtype)
         stages["user_embed_ms"] = ev_time(lambda: model._assemble("user", u, out_dtype=model.table_dtype))
@@ -456,7 +466,7 @@ def main():
         if wl["embedder"] == "dhe":
             ids_oov = torch.arange(wl["n_old_items"], N, device=device)
             keys_dev = emb._keys_dev
-            stages["item_hash_ms"] = ev_time(lambda: ops.dhe_hash(ids_oov, keys_dev), reps=3)
+            stages["dhe_hash_u32_ms"] = ev_time(lambda: ops.dhe_hash(ids_oov, keys_dev), reps=3)   # generic oov_dhe_hash; the step uses the byte-plane kernel inside oov_dhe_embed
             M = min(n_oov, 1 << 18)
             A = torch.randn(M, wl["hidden"], device=device).to(torch.bfloat16)
             Wt = torch.randn(wl["hidden"], wl["hidden"], device=device).to(torch.bfloat16)
@@ -497,8 +507,17 @@ def main():
             "gpu_launches": int(lt.item()), "roofline": roofline, "cpu_baseline": cpu_base, "stages": stages}))
     if sampler:
         sampler.stop()
+    sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # A captured graph that contains the NCCL all-gather keeps the communicator busy at teardown
+        # (destroy_process_group did not return on the 2-GPU box): drop the graph, quiesce, leave without the
+        # interpreter's teardown.  Every rank has finished its work and rank 0 has printed by now.
+        gstep = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

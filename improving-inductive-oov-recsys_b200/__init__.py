@@ -9,11 +9,12 @@ Layout
     model/                   BPR / DirectAU (fused assemble + full_sort_topk), context token gather
     evaluator.py             InductiveEvaluator / Collector on the fused path
     sharded.py               row-sharded retrieval, NCCL all-gather top-k merge
+    graphed.py               the whole retrieval step captured in one CUDA graph (static shapes)
 
 The directory name contains '-', so import it as `import oov_b200` (alias module at the repo root)
 or `importlib.import_module("improving-inductive-oov-recsys_b200")`.
 """
-from . import _lib, ops, sharded, evaluator, interaction        # noqa: F401
+from . import _lib, ops, sharded, graphed, evaluator, interaction        # noqa: F401
 from .interaction import Interaction                             # noqa: F401
 from .inductive import (abstract_embedder, feature_cache, torch_hash, lsh_embedder, single_lsh_embedder,   # noqa: F401
                         dh_embedder, mean_embedder, zero_embedder, random_mapper, get_inductive)
@@ -21,5 +22,6 @@ from .model import general, context                              # noqa: F401
 from .inductive.get_inductive import get_inductive_embedder, get_inductive_mapper   # noqa: F401
 from .model.general import BPR, DirectAU                         # noqa: F401
 from .evaluator import InductiveEvaluator, Collector            # noqa: F401
+from .graphed import GraphedTopK                                 # noqa: F401
 
 __version__ = "0.1.0"

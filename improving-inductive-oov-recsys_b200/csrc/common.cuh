@@ -72,6 +72,18 @@ __device__ __forceinline__ void copy_row(const void* src, int sdt, void* dst, in
             return;
         }
     }
+    if (sdt == OOV_F32 && ddt == OOV_BF16 && (D & 3) == 0 &&
+        ((reinterpret_cast<uintptr_t>(src) & 15) | (reinterpret_cast<uintptr_t>(dst) & 7)) == 0) {
+        // fp32 table row -> bf16 table row (the in-vocab half of every assembled bf16 item table): 16 B in, 8 B out per lane
+        const float4* s = reinterpret_cast<const float4*>(src);
+        uint2* d = reinterpret_cast<uint2*>(dst);
+        for (int i = lane; i < (D >> 2); i += nlanes) {
+            const float4 v = __ldg(s + i);
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            d[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        }
+        return;
+    }
     for (int i = lane; i < D; i += nlanes) store_elem(dst, ddt, i, load_elem(src, sdt, i));
 }
 

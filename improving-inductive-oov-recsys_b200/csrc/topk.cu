@@ -485,6 +485,119 @@ static int launch_fullsort_simt(const T* users, const T* items, int64_t Q, int64
     return OOV_OK;
 }
 
+// (row, item) pairs -> CSR with ascending columns per row, in ONE launch and without cross-CTA communication: every CTA
+// owns a contiguous block of rows and reads ALL pairs twice (they stay in L2): pass 1 counts its rows' entries and the
+// valid pairs that sort before its block (its rowptr base), pass 2 collects its rows' columns in shared memory, then one
+// warp per row rank-sorts and writes the row out.  Replaces a torch.sort over 64-bit keys (several radix passes) on the
+// per-batch path; rows outside [0, Q) are padding.
+constexpr int CSR_THREADS = 1024;
+constexpr int CSR_MAX_ROWS = 512;               // rows per CTA
+constexpr int CSR_STAGE = 10240;                // staged columns per CTA (40 KB); more take the in-place global path
+
+__device__ __forceinline__ void csr_sort_row(int* buf, int m, int* dst, int lane) {
+    // rank sort of buf[0, m) into dst[0, m) (buf and dst may alias only if m <= 128: values are read first)
+    if (m <= 128) {
+        int v[4], rk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { v[u] = u * 32 + lane < m ? buf[u * 32 + lane] : 0x7fffffff; rk[u] = 0; }
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            if (w * 32 >= m) break;                                       // warp-uniform
+            const int jn = m - w * 32 < 32 ? m - w * 32 : 32;
+            for (int jj = 0; jj < jn; ++jj) {
+                const int o = __shfl_sync(0xffffffffu, v[w], jj);
+                const int j = w * 32 + jj;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) rk[u] += (o < v[u] || (o == v[u] && j < u * 32 + lane)) ? 1 : 0;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (u * 32 + lane < m) dst[rk[u]] = v[u];
+    } else {
+        // very long rows (more than 128 history items of one user in the batch): odd-even transposition in place
+        for (int pass = 0; pass < m; ++pass) {
+            for (int i = (pass & 1) + 2 * lane; i + 1 < m; i += 64) {
+                const int a = buf[i], c = buf[i + 1];
+                if (a > c) { buf[i] = c; buf[i + 1] = a; }
+            }
+            __syncwarp();
+        }
+        if (dst != buf)
+            for (int i = lane; i < m; i += 32) dst[i] = buf[i];
+    }
+}
+
+__global__ void __launch_bounds__(CSR_THREADS)
+pairs_to_csr_kernel(const int64_t* __restrict__ rows, const int64_t* __restrict__ cols, int64_t n, int Q, int rows_per,
+                    int32_t* __restrict__ rowptr, int32_t* __restrict__ cols_out) {
+    __shared__ int cnt[CSR_MAX_ROWS + 1];       // counts -> exclusive offsets inside this CTA's block of rows
+    __shared__ int cur[CSR_MAX_ROWS];           // scatter cursors
+    __shared__ int warp_red[CSR_THREADS / 32];
+    __shared__ int stage[CSR_STAGE];
+    __shared__ int s_base, s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r0 = blockIdx.x * rows_per, r1 = r0 + rows_per < Q ? r0 + rows_per : Q, nr = r1 - r0;
+    for (int i = tid; i <= nr; i += CSR_THREADS) cnt[i] = 0;
+    __syncthreads();
+    int below = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += CSR_THREADS * 8) {                // 8 loads in flight per thread
+        int64_t r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int64_t i = i0 + u * CSR_THREADS + tid; r[u] = i < n ? __ldg(rows + i) : -1; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (r[u] < 0 || r[u] >= Q) continue;
+            if (r[u] < r0) ++below;
+            else if (r[u] < r1) atomicAdd(&cnt[(int)r[u] - r0], 1);
+        }
+    }
+    below = __reduce_add_sync(0xffffffffu, below);
+    if (lane == 0) warp_red[warp] = below;
+    __syncthreads();
+    if (warp == 0) {
+        const int b = __reduce_add_sync(0xffffffffu, warp_red[lane]);
+        // exclusive scan of this block's <= 512 row counts: 16 per lane
+        int c[CSR_MAX_ROWS / 32], local = 0;
+#pragma unroll
+        for (int u = 0; u < CSR_MAX_ROWS / 32; ++u) { const int i = lane * (CSR_MAX_ROWS / 32) + u; c[u] = i < nr ? cnt[i] : 0; local += c[u]; }
+        int incl = local;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+        int run = incl - local;
+#pragma unroll
+        for (int u = 0; u < CSR_MAX_ROWS / 32; ++u) {
+            const int i = lane * (CSR_MAX_ROWS / 32) + u;
+            if (i < nr) { cnt[i] = run; cur[i] = run; }
+            run += c[u];
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 0) { s_base = b; s_total = total; cnt[nr] = total; }
+    }
+    __syncthreads();
+    const int base = s_base, total = s_total;
+    for (int i = tid; i < nr; i += CSR_THREADS) rowptr[r0 + i] = base + cnt[i];
+    if (r1 == Q && tid == 0) rowptr[Q] = base + total;
+    const bool staged = total <= CSR_STAGE;
+    int* buf = staged ? stage : cols_out + base;
+    for (int64_t i0 = 0; i0 < n && total > 0; i0 += CSR_THREADS * 8) {
+        int64_t r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int64_t i = i0 + u * CSR_THREADS + tid; r[u] = i < n ? __ldg(rows + i) : -1; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (r[u] >= r0 && r[u] < r1) buf[atomicAdd(&cur[(int)r[u] - r0], 1)] = (int32_t)__ldg(cols + i0 + u * CSR_THREADS + tid);
+    }
+    __syncthreads();                            // (global path: a CTA sees its own writes after the barrier)
+    for (int i = warp; i < nr; i += CSR_THREADS / 32) {
+        const int lo = cnt[i], m = cnt[i + 1] - lo;
+        if (m == 0) continue;
+        if (staged) csr_sort_row(stage + lo, m, cols_out + base + lo, lane);
+        else if (m > 1) csr_sort_row(cols_out + base + lo, m, cols_out + base + lo, lane);
+    }
+}
+
 // shared with the tcgen05 scoring kernel (tc_score.cu): merge P partial key lists per user
 int launch_merge_keys(const unsigned long long* partial, const uint8_t* partial_n, int P, int64_t Q, int k, int64_t off,
                       float* out_scores, int64_t* out_idx, cudaStream_t st) {
@@ -520,6 +633,20 @@ size_t oov_fullsort_topk_workspace(int64_t Q, int64_t N, int32_t D, int32_t k, i
         if (b > a) a = b;
     }
     return a;
+}
+
+int oov_pairs_to_csr(const int64_t* rows, const int64_t* cols, int64_t n_pairs, int64_t Q, int32_t* rowptr_out,
+                     int32_t* cols_out, void* stream) {
+    OOV_REQUIRE(Q >= 1 && Q <= 16 * CSR_MAX_ROWS && n_pairs >= 0 && n_pairs <= (1ll << 20), OOV_ERR_ARG,
+                "oov_pairs_to_csr: Q=%lld (1..%d), n_pairs=%lld (max 2^20)", (long long)Q, 16 * CSR_MAX_ROWS, (long long)n_pairs);
+    OOV_REQUIRE(rowptr_out && (n_pairs == 0 || (rows && cols && cols_out)), OOV_ERR_ARG, "oov_pairs_to_csr: NULL pointer");
+    // 64-512 rows per CTA, at most 16 CTAs: each one streams all the pairs, so more CTAs only add L2 traffic
+    int rows_per = (int)cdiv(Q, 16);
+    if (rows_per < 64) rows_per = 64;
+    const unsigned grid = (unsigned)cdiv(Q, rows_per);
+    pairs_to_csr_kernel<<<grid, CSR_THREADS, 0, (cudaStream_t)stream>>>(rows, cols, n_pairs, (int)Q, rows_per, rowptr_out, cols_out);
+    OOV_LAUNCH_CHECK("pairs_to_csr_kernel");
+    return OOV_OK;
 }
 
 int oov_fullsort_topk(const void* users, const void* items, int32_t dtype, int64_t Q, int64_t N, int32_t D, int32_t k,

@@ -1,0 +1,82 @@
+"""Static-shape full-sort top-k step captured in ONE CUDA graph.
+
+A retrieval step is ~25-60 kernel launches (user embed, item-table assembly, pre-pass / threshold / scoring /
+merge per segment, the candidate all-gather when sharded).  On a small shard (1M items over 8 GPUs) the kernels are
+tens of microseconds each and the host enqueue time (~0.45 ms) is close to the GPU time, so the whole step is
+captured once and replayed: the host cost per step drops to the input copies plus one `cudaGraphLaunch`.
+
+No reference counterpart (the reference evaluates eagerly, trainer.py:526-545); the inputs and outputs are the same
+as `model.full_sort_topk`: user ids [Q] and the dataloader's history_index pairs (general_dataloader.py:270-292).
+History pairs are padded to `max_pairs` with row = Q (dropped by the CSR build), so every shape is static.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+
+class GraphedTopK:
+    """`scores, ids = g(users, hist_rows, hist_cols)` — replays the captured step.
+
+    model         BPR / DirectAU (model/general.py)
+    Q, k          static query batch size and list length
+    n_total_items N of `get_item_embedding(arange(N))`
+    max_pairs     capacity of the history pair buffers
+    sharded       optional `ShardedRetrieval` (row-sharded step with the NCCL all-gather inside the graph)
+    """
+
+    def __init__(self, model, Q: int, k: int, n_total_items: int, max_pairs: int, sharded=None, warmup: int = 3):
+        self.model, self.Q, self.k, self.N, self.max_pairs, self.sr = model, Q, k, n_total_items, max(int(max_pairs), 1), sharded
+        dev = model.device
+        self.users = torch.zeros(Q, dtype=torch.int64, device=dev)
+        self.hist_rows = torch.full((self.max_pairs,), Q, dtype=torch.int64, device=dev)
+        self.hist_cols = torch.zeros(self.max_pairs, dtype=torch.int64, device=dev)
+        self.scores: Optional[torch.Tensor] = None
+        self.ids: Optional[torch.Tensor] = None
+        self.launches_per_replay = 0
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):                        # allocator, workspaces, function attributes, NCCL
+                self._step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = ops.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.scores, self.ids = self._step()
+        self.launches_per_replay = ops.launch_count() - l0
+        torch.cuda.synchronize(dev)
+
+    def _step(self):
+        csr = ops.pairs_to_csr(self.hist_rows, self.hist_cols, self.Q)      # padding rows (= Q) are dropped
+        m = self.model
+        user_e = m._assemble("user", self.users, out_dtype=m.table_dtype)
+        if self.sr is None:
+            table = m.build_item_table(self.N)
+            s, i = ops.fullsort_topk(user_e, table, self.k, mask_pad=True, hist=csr)
+        else:
+            self.sr.build_shard()
+            s, i = self.sr.topk(user_e, self.k, hist=csr)
+        self.hist_rows.fill_(self.Q)                               # padding for the next call's shorter pair list
+        return s, i
+
+    def load(self, users: torch.Tensor, hist_rows: Optional[torch.Tensor], hist_cols: Optional[torch.Tensor]) -> None:
+        """Copy one batch into the static buffers (host pinned or device tensors; async on the current stream)."""
+        if users.shape[0] != self.Q:
+            raise ValueError(f"graph was captured for Q={self.Q}, got {users.shape[0]} users")
+        self.users.copy_(users, non_blocking=True)
+        n = 0 if hist_rows is None else int(hist_rows.shape[0])
+        if n > self.max_pairs:
+            raise ValueError(f"{n} history pairs exceed the captured capacity {self.max_pairs}")
+        if n:
+            self.hist_rows[:n].copy_(hist_rows, non_blocking=True)
+            self.hist_cols[:n].copy_(hist_cols, non_blocking=True)
+
+    def __call__(self, users, hist_rows=None, hist_cols=None):
+        self.load(users, hist_rows, hist_cols)
+        self.graph.replay()
+        return self.scores, self.ids

@@ -428,20 +428,38 @@ def topk_hits(topk_idx: torch.Tensor, pos_rowptr: torch.Tensor, pos_cols: torch.
     return out
 
 
+CSR_MAX_Q, CSR_MAX_PAIRS = 8192, 1 << 20
+
+
 def pairs_to_csr(rows_idx: torch.Tensor, cols_idx: torch.Tensor, Q: int):
     """(row, item) index pairs (general_dataloader.py:270-292 history_index / positive_u,i) -> CSR
-    with ascending columns per row.  Pure index plumbing, done with torch ops on the device."""
+    (int32 rowptr [Q + 1], int32 cols ascending per row).  Rows outside [0, Q) are padding and are dropped; cols has
+    the length of the input and is only meaningful up to rowptr[Q].  One kernel, no host sync (graph-capturable)."""
     if rows_idx is None or rows_idx.numel() == 0:
         dev = rows_idx.device if rows_idx is not None else "cuda"
         return torch.zeros(Q + 1, dtype=torch.int32, device=dev), torch.zeros(0, dtype=torch.int32, device=dev)
-    key = rows_idx.to(torch.int64) * (1 << 32) + cols_idx.to(torch.int64)
+    n = rows_idx.numel()
+    if not rows_idx.is_cuda or Q > CSR_MAX_Q or n > CSR_MAX_PAIRS:          # host-side index plumbing (tests, gloo) or huge batches
+        return _pairs_to_csr_torch(rows_idx, cols_idx, Q)
+    _cuda(rows_idx, "rows_idx", torch.int64)
+    _cuda(cols_idx, "cols_idx", torch.int64)
+    rows_idx, cols_idx = rows_idx.contiguous(), cols_idx.contiguous()
+    rowptr = torch.empty(Q + 1, dtype=torch.int32, device=rows_idx.device)
+    cols = torch.empty(n, dtype=torch.int32, device=rows_idx.device)
+    _lib.check(_lib.load().oov_pairs_to_csr(_p(rows_idx), _p(cols_idx), n, Q, _p(rowptr), _p(cols), _stream()))
+    return rowptr, cols
+
+
+def _pairs_to_csr_torch(rows_idx: torch.Tensor, cols_idx: torch.Tensor, Q: int):
+    """Index plumbing with torch ops for batches beyond the one-CTA kernel's limits (sync-free as well)."""
+    rows_idx = rows_idx.to(torch.int64)
+    rows_idx = torch.where((rows_idx < 0) | (rows_idx >= Q), torch.full_like(rows_idx, Q), rows_idx)
+    key = rows_idx * (1 << 32) + cols_idx.to(torch.int64)
     key, _ = torch.sort(key)
-    r = torch.div(key, 1 << 32, rounding_mode="floor")
-    c = key - r * (1 << 32)
-    counts = torch.bincount(r, minlength=Q)
-    rowptr = torch.zeros(Q + 1, dtype=torch.int64, device=key.device)
-    rowptr[1:] = torch.cumsum(counts, 0)
-    return rowptr.to(torch.int32), c.to(torch.int32)
+    r = key >> 32
+    c = (key & 0xFFFFFFFF).to(torch.int32)
+    rowptr = torch.searchsorted(r, torch.arange(Q + 1, device=key.device, dtype=torch.int64))
+    return rowptr.to(torch.int32), c
 
 
 # ------------------------------------------------------------------------------------ context models

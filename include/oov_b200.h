@@ -204,6 +204,14 @@ int oov_topk_hits(const int64_t* topk_idx, int64_t Q, int32_t k,
                   const int32_t* pos_rowptr, const int32_t* pos_cols,
                   int32_t* out_hits /* [Q, k+1] */, void* stream);
 
+/* (row, item) index pairs — the `history_index` / `positive_u, positive_i` tensors FullSortEvalDataLoader.collate_fn
+ * yields (data/dataloader/general_dataloader.py:270-292) — to the CSR the kernels above read: rowptr [Q + 1] int32,
+ * cols [n_pairs] int32 ascending within a row (duplicates kept).  Pairs whose row is outside [0, Q) are padding and
+ * are dropped (cols_out past rowptr[Q] is left untouched).  One launch, asynchronous, no workspace: n_pairs <= 2^20,
+ * 1 <= Q <= 8192. */
+int oov_pairs_to_csr(const int64_t* rows, const int64_t* cols, int64_t n_pairs, int64_t Q,
+                     int32_t* rowptr_out, int32_t* cols_out, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Context models — replaces model/abstract_recommender.py:794-842 (embed_token_fields)
  * with model/layers.py:150-153 (FMEmbedding), and model/layers.py:1634-1693.

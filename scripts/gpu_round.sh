@@ -1,9 +1,15 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-bash scripts/gpu_check.sh tests/test_gpu_tc.py tests/test_gpu_retrieval.py
-timeout 300 python scripts/prof_score.py 2>&1 | tee gpurun_out/score_sweep.log
-timeout 300 python scripts/prof_small.py 2>&1 | tee gpurun_out/score_small.log
-timeout 300 python scripts/prof_dhe.py 2>&1 | tee gpurun_out/dhe.log
-timeout 300 python scripts/prof_lsh.py 2000000 2>&1 | tee gpurun_out/lsh.log
-ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_score_one.csv python scripts/prof_score.py one > /dev/null 2>&1
+show() { python - "$1" <<'PY'
+import json,sys
+f=sys.argv[1]
+try:
+    d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, d["n_gpus"], "value", round(d["value"]), "ms/step", round(d["ms_per_step"],3), "e2e", round(d["e2e"]["value"]), "e2e ms", round(d["e2e"]["ms_per_step"],3), "launches", d["gpu_launches"], d.get("stages"))
+except Exception as e: print(f, "ERR", e)
+PY
+}
+bash scripts/gpu_check.sh tests/test_gpu_tc.py
+timeout 300 python bench.py --no-cpu-baseline > gpurun_out/b1.json 2> gpurun_out/b1.err; echo rc=$?; tail -3 gpurun_out/b1.err; show gpurun_out/b1.json
+timeout 300 python bench.py --no-cpu-baseline --eager > gpurun_out/b1e.json 2> gpurun_out/b1e.err; echo rc=$?; tail -3 gpurun_out/b1e.err; show gpurun_out/b1e.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r01_launches_bench_dhe1m.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo rc=$?

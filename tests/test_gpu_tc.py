@@ -209,6 +209,52 @@ def test_tc_score_prepass_history_holds_the_top_items():
         assert ok, f"simt seg={seg}: {msg}"
 
 
+def test_pairs_to_csr_kernel_matches_torch_path():
+    """oov_pairs_to_csr (one CTA: count, scan, scatter, per-row sort) against the torch index plumbing, including
+    padding rows (>= Q or negative), duplicate pairs, rows of 33-128 and of more than 128 entries, and an empty batch."""
+    from oov_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for Q, n, hot in ((1024, 25_600, 0), (1, 50, 0), (300, 5000, 200), (4096, 100_000, 150), (7, 3, 0), (64, 30_000, 0),
+                      (8192, 51_200, 0)):
+        rows = torch.randint(-2, Q + 3, (n,), generator=g)
+        if hot:
+            rows[: hot] = 5 % Q                                      # one long row
+        cols = torch.randint(0, 1_000_000, (n,), generator=g)
+        cols[: n // 10] = cols[n // 10: 2 * (n // 10)]              # duplicates
+        rp_k, c_k = ops.pairs_to_csr(rows.to(DEV), cols.to(DEV), Q)
+        rp_t, c_t = ops._pairs_to_csr_torch(rows.to(DEV), cols.to(DEV), Q)
+        assert torch.equal(rp_k, rp_t), (Q, n)
+        m = int(rp_t[-1])
+        assert torch.equal(c_k[:m], c_t[:m]), (Q, n)
+    rp, c = ops.pairs_to_csr(torch.zeros(0, dtype=torch.int64, device=DEV), torch.zeros(0, dtype=torch.int64, device=DEV), 5)
+    assert rp.tolist() == [0] * 6 and c.numel() == 0
+
+
+def test_graphed_topk_equals_eager(tmp_path):
+    """GraphedTopK (the whole step in one CUDA graph, padded history pairs) returns exactly what the eager
+    model.full_sort_topk returns, for two different batches replayed through the same graph."""
+    import cases
+    import gpu_util as gu
+    import oov_b200
+    case = cases.CASES["bpr_lsh_ml100k"]
+    inp = cases.retrieval_inputs(case)
+    cfg, emb, model = gu.build_retrieval(case, inp, table_dtype="bfloat16")
+    N = case.n_all_items
+    Q, k = 64, 10
+    gq = oov_b200.GraphedTopK(model, Q, k, N, max_pairs=Q * 8)
+    g = torch.Generator(device="cpu").manual_seed(11)
+    for trial in range(2):
+        users = torch.randint(1, case.n_all_users, (Q,), generator=g).to(DEV)
+        n_pairs = 100 + 200 * trial
+        hu = torch.randint(0, Q, (n_pairs,), generator=g).to(DEV)
+        hi = torch.randint(1, N, (n_pairs,), generator=g).to(DEV)
+        s_g, i_g = gq(users, hu, hi)
+        s_g, i_g = s_g.clone(), i_g.clone()
+        s_e, i_e = model.full_sort_topk(users, k, n_total_items=N, history_index=(hu, hi))
+        torch.cuda.synchronize()
+        assert torch.equal(i_g, i_e) and torch.equal(s_g, s_e), trial
+
+
 def test_tc_score_nan_rows_rank_first():
     """An all-zero LSH multi-hot row gives a NaN item embedding (lsh_embedder.py:158); torch.topk ranks NaN first."""
     from oov_b200 import ops
