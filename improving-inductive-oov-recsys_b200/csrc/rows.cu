@@ -215,9 +215,21 @@ __global__ void map_ids_kernel(const int64_t* __restrict__ ids, int64_t n, int64
     }
 }
 
-static unsigned grid_for(int64_t work_items, int per_block) {
+// Grid of a grid-stride kernel: enough blocks for the work, capped at ONE resident wave (blocks per SM from the
+// occupancy calculator).  A fixed cap of 8 blocks per SM left kernels that fit 4-5 blocks per SM with a partial second
+// wave that ran on a fraction of the machine.
+template <typename K>
+static unsigned grid_for(K kernel, int64_t work_items, int per_block) {
+    static int per_sm = 0;                       // one instantiation (and one cache slot) per kernel type
+    static const void* cached_for = nullptr;
+    if (cached_for != reinterpret_cast<const void*>(kernel)) {
+        int v = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, 256, 0) != cudaSuccess || v < 1) v = 4;
+        per_sm = v;
+        cached_for = reinterpret_cast<const void*>(kernel);
+    }
     int64_t b = cdiv(work_items, per_block);
-    const int64_t cap = (int64_t)num_sms() * 8;
+    const int64_t cap = (int64_t)num_sms() * per_sm;
     if (b > cap) b = cap;
     if (b < 1) b = 1;
     return (unsigned)b;
@@ -257,7 +269,7 @@ int oov_const_embed(const float* vec, const oov_rows* rows, void* stream) {
     int rc = check_rows_public(rows, "oov_const_embed");
     if (rc) return rc;
     if (rows->n == 0) return OOV_OK;
-    const_embed_kernel<<<grid_for(rows->n, 16), 256, 0, (cudaStream_t)stream>>>(
+    const_embed_kernel<<<grid_for(const_embed_kernel, rows->n, 16), 256, 0, (cudaStream_t)stream>>>(
         vec, rows->ids, rows->ids_stride, rows->n, rows->n_old, rows->iv_table, rows->iv_dtype, rows->out, rows->out_dtype,
         rows->out_stride, rows->D);
     OOV_LAUNCH_CHECK("const_embed_kernel");
@@ -272,13 +284,13 @@ int oov_gather_rows(const void* table, int32_t dtype, int64_t table_rows, int32_
     if (n == 0) return OOV_OK;
     OOV_REQUIRE(idx && out, OOV_ERR_ARG, "oov_gather_rows: NULL pointer");
     if (dtype == OOV_F32 && out_dtype == OOV_BF16 && D % 4 == 0 && out_stride % 4 == 0 && aligned(table, 16) && aligned(out, 8)) {
-        gather_rows_f32_bf16_kernel<<<grid_for(n, 64), 256, 0, (cudaStream_t)stream>>>(
+        gather_rows_f32_bf16_kernel<<<grid_for(gather_rows_f32_bf16_kernel, n, 64), 256, 0, (cudaStream_t)stream>>>(
             reinterpret_cast<const float*>(table), table_rows, D, idx, idx_stride, n, idx_offset,
             reinterpret_cast<__nv_bfloat16*>(out), out_stride);
         OOV_LAUNCH_CHECK("gather_rows_f32_bf16_kernel");
         return OOV_OK;
     }
-    gather_rows_kernel<<<grid_for(n, 16), 256, 0, (cudaStream_t)stream>>>(table, dtype, table_rows, D, idx, idx_stride, n,
+    gather_rows_kernel<<<grid_for(gather_rows_kernel, n, 16), 256, 0, (cudaStream_t)stream>>>(table, dtype, table_rows, D, idx, idx_stride, n,
                                                                           idx_offset, out, out_dtype, out_stride);
     OOV_LAUNCH_CHECK("gather_rows_kernel");
     return OOV_OK;
@@ -295,11 +307,11 @@ int oov_token_gather(const int64_t* tokens, int64_t Bn, int32_t fields, const in
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t total = Bn * fields;
     if (D <= 16)
-        token_gather_kernel<4><<<grid_for(total, 64), 256, 0, st>>>(tokens, Bn, fields, offsets, table, dtype, table_rows, D,
+        token_gather_kernel<4><<<grid_for(token_gather_kernel<4>, total, 64), 256, 0, st>>>(tokens, Bn, fields, offsets, table, dtype, table_rows, D,
                                                                     n_users, n_items, uid_idx, iid_idx, user_const,
                                                                     item_const, out, out_dtype);
     else
-        token_gather_kernel<16><<<grid_for(total, 16), 256, 0, st>>>(tokens, Bn, fields, offsets, table, dtype, table_rows, D,
+        token_gather_kernel<16><<<grid_for(token_gather_kernel<16>, total, 16), 256, 0, st>>>(tokens, Bn, fields, offsets, table, dtype, table_rows, D,
                                                                      n_users, n_items, uid_idx, iid_idx, user_const,
                                                                      item_const, out, out_dtype);
     OOV_LAUNCH_CHECK("token_gather_kernel");
@@ -312,7 +324,7 @@ int oov_first_order_sum(const int64_t* tokens, int64_t Bn, int32_t fields, const
     OOV_REQUIRE(table1 && offsets && Bn >= 0 && fields > 0 && table_rows > 0, OOV_ERR_ARG, "oov_first_order_sum: bad argument");
     if (Bn == 0) return OOV_OK;
     OOV_REQUIRE(tokens && out, OOV_ERR_ARG, "oov_first_order_sum: NULL pointer");
-    first_order_sum_kernel<<<grid_for(Bn, 256), 256, 0, (cudaStream_t)stream>>>(
+    first_order_sum_kernel<<<grid_for(first_order_sum_kernel, Bn, 256), 256, 0, (cudaStream_t)stream>>>(
         tokens, Bn, fields, offsets, table1, table_rows, n_users, n_items, uid_idx, iid_idx, oov_user_val, oov_item_val, out);
     OOV_LAUNCH_CHECK("first_order_sum_kernel");
     return OOV_OK;
@@ -322,7 +334,7 @@ int oov_map_ids(const int64_t* ids, int64_t n, int64_t n_old, int64_t n_buckets,
     OOV_REQUIRE(n >= 0 && n_buckets > 0 && fn >= 0 && fn <= 3, OOV_ERR_ARG, "oov_map_ids: bad argument");
     if (n == 0) return OOV_OK;
     OOV_REQUIRE(ids && out, OOV_ERR_ARG, "oov_map_ids: NULL pointer");
-    map_ids_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(ids, n, n_old, n_buckets, fn, out);
+    map_ids_kernel<<<grid_for(map_ids_kernel, n, 256), 256, 0, (cudaStream_t)stream>>>(ids, n, n_old, n_buckets, fn, out);
     OOV_LAUNCH_CHECK("map_ids_kernel");
     return OOV_OK;
 }

@@ -9,7 +9,6 @@ try:
 except Exception as e: print(f, "ERR", e)
 PY
 }
-bash scripts/gpu_check.sh tests/test_gpu_tc.py
+bash scripts/gpu_check.sh tests/test_gpu_dhe_context.py tests/test_gpu_tc.py
+timeout 300 python scripts/prof_dhe.py 2>&1 | tail -1
 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/b1.json 2> gpurun_out/b1.err; echo rc=$?; tail -3 gpurun_out/b1.err; show gpurun_out/b1.json
-timeout 300 python bench.py --no-cpu-baseline --eager > gpurun_out/b1e.json 2> gpurun_out/b1e.err; echo rc=$?; tail -3 gpurun_out/b1e.err; show gpurun_out/b1e.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r01_launches_bench_dhe1m.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo rc=$?
