@@ -529,9 +529,18 @@ __device__ __forceinline__ void csr_sort_row(int* buf, int m, int* dst, int lane
     }
 }
 
+// optional column map of a row shard made of two id ranges: [lo0, hi0) -> local rows 0.., [lo1, hi1) -> local rows
+// (hi0 - lo0)..; every other column is dropped.  lo0 = hi0 = lo1 = 0, hi1 = INT64_MAX is the identity.
+struct CsrColMap { int64_t lo0, hi0, lo1, hi1; };
+__device__ __forceinline__ int64_t csr_map_col(const CsrColMap& m, int64_t c) {
+    if (c >= m.lo0 && c < m.hi0) return c - m.lo0;
+    if (c >= m.lo1 && c < m.hi1) return c - m.lo1 + (m.hi0 - m.lo0);
+    return -1;
+}
+
 __global__ void __launch_bounds__(CSR_THREADS)
 pairs_to_csr_kernel(const int64_t* __restrict__ rows, const int64_t* __restrict__ cols, int64_t n, int Q, int rows_per,
-                    int32_t* __restrict__ rowptr, int32_t* __restrict__ cols_out) {
+                    const CsrColMap cmap, int32_t* __restrict__ rowptr, int32_t* __restrict__ cols_out) {
     __shared__ int cnt[CSR_MAX_ROWS + 1];       // counts -> exclusive offsets inside this CTA's block of rows
     __shared__ int cur[CSR_MAX_ROWS];           // scatter cursors
     __shared__ int warp_red[CSR_THREADS / 32];
@@ -543,12 +552,16 @@ pairs_to_csr_kernel(const int64_t* __restrict__ rows, const int64_t* __restrict_
     __syncthreads();
     int below = 0;
     for (int64_t i0 = 0; i0 < n; i0 += CSR_THREADS * 8) {                // 8 loads in flight per thread
-        int64_t r[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { const int64_t i = i0 + u * CSR_THREADS + tid; r[u] = i < n ? __ldg(rows + i) : -1; }
+        int64_t r[8], c[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            if (r[u] < 0 || r[u] >= Q) continue;
+            const int64_t i = i0 + u * CSR_THREADS + tid;
+            r[u] = i < n ? __ldg(rows + i) : -1;
+            c[u] = i < n ? __ldg(cols + i) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (r[u] < 0 || r[u] >= Q || csr_map_col(cmap, c[u]) < 0) continue;
             if (r[u] < r0) ++below;
             else if (r[u] < r1) atomicAdd(&cnt[(int)r[u] - r0], 1);
         }
@@ -586,8 +599,11 @@ pairs_to_csr_kernel(const int64_t* __restrict__ rows, const int64_t* __restrict_
 #pragma unroll
         for (int u = 0; u < 8; ++u) { const int64_t i = i0 + u * CSR_THREADS + tid; r[u] = i < n ? __ldg(rows + i) : -1; }
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (r[u] >= r0 && r[u] < r1) buf[atomicAdd(&cur[(int)r[u] - r0], 1)] = (int32_t)__ldg(cols + i0 + u * CSR_THREADS + tid);
+        for (int u = 0; u < 8; ++u) {
+            if (r[u] < r0 || r[u] >= r1) continue;
+            const int64_t c = csr_map_col(cmap, __ldg(cols + i0 + u * CSR_THREADS + tid));
+            if (c >= 0) buf[atomicAdd(&cur[(int)r[u] - r0], 1)] = (int32_t)c;
+        }
     }
     __syncthreads();                            // (global path: a CTA sees its own writes after the barrier)
     for (int i = warp; i < nr; i += CSR_THREADS / 32) {
@@ -635,8 +651,8 @@ size_t oov_fullsort_topk_workspace(int64_t Q, int64_t N, int32_t D, int32_t k, i
     return a;
 }
 
-int oov_pairs_to_csr(const int64_t* rows, const int64_t* cols, int64_t n_pairs, int64_t Q, int32_t* rowptr_out,
-                     int32_t* cols_out, void* stream) {
+int oov_pairs_to_csr(const int64_t* rows, const int64_t* cols, int64_t n_pairs, int64_t Q, const int64_t* col_ranges,
+                     int32_t* rowptr_out, int32_t* cols_out, void* stream) {
     OOV_REQUIRE(Q >= 1 && Q <= 16 * CSR_MAX_ROWS && n_pairs >= 0 && n_pairs <= (1ll << 20), OOV_ERR_ARG,
                 "oov_pairs_to_csr: Q=%lld (1..%d), n_pairs=%lld (max 2^20)", (long long)Q, 16 * CSR_MAX_ROWS, (long long)n_pairs);
     OOV_REQUIRE(rowptr_out && (n_pairs == 0 || (rows && cols && cols_out)), OOV_ERR_ARG, "oov_pairs_to_csr: NULL pointer");
@@ -644,7 +660,13 @@ int oov_pairs_to_csr(const int64_t* rows, const int64_t* cols, int64_t n_pairs, 
     int rows_per = (int)cdiv(Q, 16);
     if (rows_per < 64) rows_per = 64;
     const unsigned grid = (unsigned)cdiv(Q, rows_per);
-    pairs_to_csr_kernel<<<grid, CSR_THREADS, 0, (cudaStream_t)stream>>>(rows, cols, n_pairs, (int)Q, rows_per, rowptr_out, cols_out);
+    CsrColMap cmap{0, 0, 0, INT64_MAX};                               // identity
+    if (col_ranges != nullptr) {
+        cmap = CsrColMap{col_ranges[0], col_ranges[1], col_ranges[2], col_ranges[3]};
+        OOV_REQUIRE(cmap.lo0 <= cmap.hi0 && cmap.hi0 <= cmap.lo1 && cmap.lo1 <= cmap.hi1, OOV_ERR_ARG,
+                    "oov_pairs_to_csr: col_ranges must be two ascending, disjoint ranges");
+    }
+    pairs_to_csr_kernel<<<grid, CSR_THREADS, 0, (cudaStream_t)stream>>>(rows, cols, n_pairs, (int)Q, rows_per, cmap, rowptr_out, cols_out);
     OOV_LAUNCH_CHECK("pairs_to_csr_kernel");
     return OOV_OK;
 }

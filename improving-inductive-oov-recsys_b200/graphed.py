@@ -52,15 +52,15 @@ class GraphedTopK:
         torch.cuda.synchronize(dev)
 
     def _step(self):
-        csr = ops.pairs_to_csr(self.hist_rows, self.hist_cols, self.Q)      # padding rows (= Q) are dropped
         m = self.model
         user_e = m._assemble("user", self.users, out_dtype=m.table_dtype)
         if self.sr is None:
+            csr = ops.pairs_to_csr(self.hist_rows, self.hist_cols, self.Q)  # padding rows (= Q) are dropped
             table = m.build_item_table(self.N)
             s, i = ops.fullsort_topk(user_e, table, self.k, mask_pad=True, hist=csr)
         else:
             self.sr.build_shard()
-            s, i = self.sr.topk(user_e, self.k, hist=csr)
+            s, i = self.sr.topk(user_e, self.k, hist_pairs=(self.hist_rows, self.hist_cols))
         self.hist_rows.fill_(self.Q)                               # padding for the next call's shorter pair list
         return s, i
 

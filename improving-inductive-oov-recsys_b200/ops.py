@@ -431,30 +431,46 @@ def topk_hits(topk_idx: torch.Tensor, pos_rowptr: torch.Tensor, pos_cols: torch.
 CSR_MAX_Q, CSR_MAX_PAIRS = 8192, 1 << 20
 
 
-def pairs_to_csr(rows_idx: torch.Tensor, cols_idx: torch.Tensor, Q: int):
+def pairs_to_csr(rows_idx: torch.Tensor, cols_idx: torch.Tensor, Q: int, col_ranges=None):
     """(row, item) index pairs (general_dataloader.py:270-292 history_index / positive_u,i) -> CSR
     (int32 rowptr [Q + 1], int32 cols ascending per row).  Rows outside [0, Q) are padding and are dropped; cols has
-    the length of the input and is only meaningful up to rowptr[Q].  One kernel, no host sync (graph-capturable)."""
+    the length of the input and is only meaningful up to rowptr[Q].  One kernel, no host sync (graph-capturable).
+
+    col_ranges = ((lo0, hi0), (lo1, hi1)): keep only items of these two id ranges and rewrite them as LOCAL rows of a
+    shard table laid out [range 0 | range 1] (sharded.py)."""
     if rows_idx is None or rows_idx.numel() == 0:
         dev = rows_idx.device if rows_idx is not None else "cuda"
         return torch.zeros(Q + 1, dtype=torch.int32, device=dev), torch.zeros(0, dtype=torch.int32, device=dev)
     n = rows_idx.numel()
     if not rows_idx.is_cuda or Q > CSR_MAX_Q or n > CSR_MAX_PAIRS:          # host-side index plumbing (tests, gloo) or huge batches
-        return _pairs_to_csr_torch(rows_idx, cols_idx, Q)
+        return _pairs_to_csr_torch(rows_idx, cols_idx, Q, col_ranges)
     _cuda(rows_idx, "rows_idx", torch.int64)
     _cuda(cols_idx, "cols_idx", torch.int64)
     rows_idx, cols_idx = rows_idx.contiguous(), cols_idx.contiguous()
     rowptr = torch.empty(Q + 1, dtype=torch.int32, device=rows_idx.device)
     cols = torch.empty(n, dtype=torch.int32, device=rows_idx.device)
-    _lib.check(_lib.load().oov_pairs_to_csr(_p(rows_idx), _p(cols_idx), n, Q, _p(rowptr), _p(cols), _stream()))
+    cr = None
+    if col_ranges is not None:
+        (a0, b0), (a1, b1) = col_ranges
+        cr = (C.c_int64 * 4)(int(a0), int(b0), int(a1), int(b1))
+    _lib.check(_lib.load().oov_pairs_to_csr(_p(rows_idx), _p(cols_idx), n, Q, cr, _p(rowptr), _p(cols), _stream()))
     return rowptr, cols
 
 
-def _pairs_to_csr_torch(rows_idx: torch.Tensor, cols_idx: torch.Tensor, Q: int):
-    """Index plumbing with torch ops for batches beyond the one-CTA kernel's limits (sync-free as well)."""
+def _pairs_to_csr_torch(rows_idx: torch.Tensor, cols_idx: torch.Tensor, Q: int, col_ranges=None):
+    """Index plumbing with torch ops for batches beyond the kernel's limits and for CPU tensors (sync-free as well)."""
     rows_idx = rows_idx.to(torch.int64)
-    rows_idx = torch.where((rows_idx < 0) | (rows_idx >= Q), torch.full_like(rows_idx, Q), rows_idx)
-    key = rows_idx * (1 << 32) + cols_idx.to(torch.int64)
+    cols_idx = cols_idx.to(torch.int64)
+    drop = (rows_idx < 0) | (rows_idx >= Q)
+    if col_ranges is not None:
+        (a0, b0), (a1, b1) = col_ranges
+        in0 = (cols_idx >= a0) & (cols_idx < b0)
+        in1 = (cols_idx >= a1) & (cols_idx < b1)
+        cols_idx = torch.where(in0, cols_idx - a0, cols_idx - a1 + (b0 - a0))
+        drop = drop | ~(in0 | in1)
+    rows_idx = torch.where(drop, torch.full_like(rows_idx, Q), rows_idx)
+    cols_idx = torch.where(drop, torch.zeros_like(cols_idx), cols_idx)
+    key = rows_idx * (1 << 32) + cols_idx
     key, _ = torch.sort(key)
     r = key >> 32
     c = (key & 0xFFFFFFFF).to(torch.int32)

@@ -66,6 +66,11 @@ class ShardedRetrieval:
         self.world = world_size if world_size is not None else (dist.get_world_size(group) if inited else 1)
         self.n_total = n_total_items
         self.segments = [s for s in shard_segments(model.n_items, n_total_items, self.rank, self.world, balanced)]
+        # With the stock kernels the two segments live in ONE table [in-vocab slice | OOV slice] and are scored by ONE
+        # fused launch in local-row space (history columns are rewritten to local rows by the CSR build, the winning
+        # rows are mapped back to global ids afterwards): half the launches of the per-segment path.
+        self.fused = local_topk_fn is None and build_table_fn is None and len(self.segments) == 2
+        self.table: Optional[torch.Tensor] = None
         if local_topk_fn is None or merge_fn is None:
             from . import ops
             local_topk_fn = local_topk_fn or (lambda ue, tab, k, off, seg, hist: ops.fullsort_topk(
@@ -77,8 +82,52 @@ class ShardedRetrieval:
 
     def build_shard(self) -> List[torch.Tensor]:
         """Embed this rank's rows (in-vocab gather + OOV embed); no communication."""
+        if self.fused:
+            m = self.model
+            n0 = self.segments[0][1] - self.segments[0][0]
+            n1 = self.segments[1][1] - self.segments[1][0]
+            self.table = torch.empty((n0 + n1, m.embedding_size), dtype=m.table_dtype, device=m.device)
+            self.tables = [self.table[:n0], self.table[n0:]]
+            for (lo, hi), out in zip(self.segments, self.tables):
+                if hi > lo:
+                    m.build_item_table(self.n_total, row_range=(lo, hi), out=out)
+            return self.tables
         self.tables = [self._build(lo, hi) for lo, hi in self.segments]
         return self.tables
+
+    def _local_seg(self, seg) -> Optional[Tuple[int, int]]:
+        """Global id filter [a, b) as ONE range of local rows of the fused table, or None if it is not contiguous there."""
+        (lo0, hi0), (lo1, hi1) = self.segments
+        n0 = hi0 - lo0
+        a, b = seg
+        a0, b0 = max(a, lo0), min(b, hi0)
+        a1, b1 = max(a, lo1), min(b, hi1)
+        e0, e1 = b0 > a0, b1 > a1
+        if e0 and e1:
+            return (a0 - lo0, n0 + b1 - lo1) if (b0 == hi0 and a1 == lo1) else None
+        if e0:
+            return (a0 - lo0, b0 - lo0)
+        if e1:
+            return (n0 + a1 - lo1, n0 + b1 - lo1)
+        return (0, 0)
+
+    def fused_candidates(self, user_e: torch.Tensor, k: int, hist_pairs=None, seg=(0, INT64_MAX)) -> Optional[torch.Tensor]:
+        """[1, Q, k, 2] candidates from one launch over the fused table; None if `seg` needs the per-segment path."""
+        from . import ops
+        lseg = self._local_seg(seg)
+        if lseg is None:
+            return None
+        if self.table is None:
+            self.build_shard()
+        (lo0, hi0), (lo1, hi1) = self.segments
+        n0 = hi0 - lo0
+        csr = None
+        if hist_pairs is not None and hist_pairs[0] is not None:
+            csr = ops.pairs_to_csr(hist_pairs[0], hist_pairs[1], user_e.shape[0], col_ranges=self.segments)
+        s, rows = ops.fullsort_topk(user_e, self.table, k, item_id_offset=0, mask_pad=(lo0 == 0 and hi0 > 0), seg=lseg, hist=csr)
+        ids = torch.where(rows < n0, rows + lo0, rows + (lo1 - n0))
+        ids = torch.where(rows < 0, rows, ids)                      # empty slots stay -1
+        return pack_candidates(s, ids).unsqueeze(0)
 
     def local_candidates(self, user_e: torch.Tensor, k: int, hist=None, seg=(0, INT64_MAX)) -> torch.Tensor:
         if self.tables is None:
@@ -89,9 +138,17 @@ class ShardedRetrieval:
             packed.append(pack_candidates(s, i))
         return torch.stack(packed, dim=0)                       # [S, Q, k, 2]
 
-    def topk(self, user_e: torch.Tensor, k: int, hist=None, seg=(0, INT64_MAX)):
-        """Global (scores [Q,k], ids [Q,k]) — identical on every rank."""
-        local = self.local_candidates(user_e, k, hist, seg)
+    def topk(self, user_e: torch.Tensor, k: int, hist=None, seg=(0, INT64_MAX), hist_pairs=None):
+        """Global (scores [Q,k], ids [Q,k]) — identical on every rank.  History either as a CSR over GLOBAL item ids
+        (`hist`, per-segment path) or as the dataloader's (row, item) pairs (`hist_pairs`, fused one-launch path)."""
+        local = None
+        if self.fused and hist is None:
+            local = self.fused_candidates(user_e, k, hist_pairs, seg)
+        if local is None:
+            if hist is None and hist_pairs is not None and hist_pairs[0] is not None:
+                from . import ops
+                hist = ops.pairs_to_csr(hist_pairs[0], hist_pairs[1], user_e.shape[0])
+            local = self.local_candidates(user_e, k, hist, seg)
         if self.world > 1:
             cand = torch.empty((self.world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype,
                                device=local.device)              # ranks concatenated along dim 0

@@ -14,7 +14,8 @@ cfg, emb, model = bench.build_gpu(wl, dev, 0)
 Q, k, N = wl["Q"], wl["k"], wl["n_items"]
 users, hu, hi = bench.query_batch(wl, 100)
 u = torch.from_numpy(users).to(dev)
-csr = ops.pairs_to_csr(torch.from_numpy(hu).to(dev), torch.from_numpy(hi).to(dev), Q)
+dhu, dhi = torch.from_numpy(hu).to(dev), torch.from_numpy(hi).to(dev)
+csr = ops.pairs_to_csr(dhu, dhi, Q)
 sr = sharded.ShardedRetrieval(model, N, rank=0, world_size=world)
 sr.world = 1                     # no process group here: skip the all-gather, keep the 1/world segments
 print("segments", sr.segments)
@@ -22,7 +23,7 @@ print("segments", sr.segments)
 def step():
     user_e = model._assemble("user", u, out_dtype=model.table_dtype)
     sr.build_shard()
-    return sr.topk(user_e, k, hist=csr)
+    return sr.topk(user_e, k, hist_pairs=(dhu, dhi))
 
 def timed(fn, reps=20):
     for _ in range(3): fn()
@@ -41,8 +42,10 @@ for name, fn in (("user_embed", lambda: model._assemble("user", u, out_dtype=mod
     g, c = timed(fn)
     print(f"  {name}: GPU {g:.3f} ms, CPU {c:.3f} ms")
 ue = model._assemble("user", u, out_dtype=model.table_dtype)
+g, c = timed(lambda: sr.topk(ue, k, hist_pairs=(dhu, dhi)))
+print(f"  topk (CSR build + one fused launch over both segments + merge): GPU {g:.3f} ms, CPU {c:.3f} ms")
 g, c = timed(lambda: sr.topk(ue, k, hist=csr))
-print(f"  topk (2 segments + merge): GPU {g:.3f} ms, CPU {c:.3f} ms")
+print(f"  topk (per-segment path, prebuilt CSR): GPU {g:.3f} ms, CPU {c:.3f} ms")
 
 s = torch.cuda.Stream()
 s.wait_stream(torch.cuda.current_stream())

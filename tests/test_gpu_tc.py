@@ -221,11 +221,12 @@ def test_pairs_to_csr_kernel_matches_torch_path():
             rows[: hot] = 5 % Q                                      # one long row
         cols = torch.randint(0, 1_000_000, (n,), generator=g)
         cols[: n // 10] = cols[n // 10: 2 * (n // 10)]              # duplicates
-        rp_k, c_k = ops.pairs_to_csr(rows.to(DEV), cols.to(DEV), Q)
-        rp_t, c_t = ops._pairs_to_csr_torch(rows.to(DEV), cols.to(DEV), Q)
-        assert torch.equal(rp_k, rp_t), (Q, n)
-        m = int(rp_t[-1])
-        assert torch.equal(c_k[:m], c_t[:m]), (Q, n)
+        for cr in (None, ((1000, 300_000), (500_000, 777_777)), ((0, 0), (999_000, 1_000_000))):
+            rp_k, c_k = ops.pairs_to_csr(rows.to(DEV), cols.to(DEV), Q, col_ranges=cr)
+            rp_t, c_t = ops._pairs_to_csr_torch(rows.to(DEV), cols.to(DEV), Q, col_ranges=cr)
+            assert torch.equal(rp_k, rp_t), (Q, n, cr)
+            m = int(rp_t[-1])
+            assert torch.equal(c_k[:m], c_t[:m]), (Q, n, cr)
     rp, c = ops.pairs_to_csr(torch.zeros(0, dtype=torch.int64, device=DEV), torch.zeros(0, dtype=torch.int64, device=DEV), 5)
     assert rp.tolist() == [0] * 6 and c.numel() == 0
 
@@ -253,6 +254,40 @@ def test_graphed_topk_equals_eager(tmp_path):
         s_e, i_e = model.full_sort_topk(users, k, n_total_items=N, history_index=(hu, hi))
         torch.cuda.synchronize()
         assert torch.equal(i_g, i_e) and torch.equal(s_g, s_e), trial
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_fused_table_equals_global(world):
+    """ShardedRetrieval on one GPU, rank by rank (no process group): every rank scores its [in-vocab slice | OOV slice]
+    table with ONE launch in local-row space (history rewritten by oov_pairs_to_csr's column map); merging the ranks'
+    candidates reproduces the un-sharded full_sort_topk bit for bit, for the three collector segments."""
+    import gpu_util as gu
+    import oov_b200
+    from oov_b200 import ops, sharded
+    case = cases.CASES["bpr_lsh_ml100k"]
+    inp = cases.retrieval_inputs(case)
+    cfg, emb, model = gu.build_retrieval(case, inp, table_dtype="bfloat16")
+    N, n_old = case.n_all_items, case.n_old_items
+    Q, k = 96, 10
+    g = torch.Generator(device="cpu").manual_seed(world)
+    users = torch.randint(1, case.n_all_users, (Q,), generator=g).to(DEV)
+    hu = torch.randint(0, Q, (900,), generator=g).to(DEV)
+    hi = torch.randint(0, N, (900,), generator=g).to(DEV)
+    user_e = model._assemble("user", users, out_dtype=model.table_dtype)
+    for seg in ((0, 1 << 62), (0, n_old), (n_old, 1 << 62)):
+        s_ref, i_ref = model.full_sort_topk(users, k, n_total_items=N, history_index=(hu, hi), seg=seg)
+        cands = []
+        for r in range(world):
+            sr = sharded.ShardedRetrieval(model, N, rank=r, world_size=world)
+            assert sr.fused
+            sr.build_shard()
+            c = sr.fused_candidates(user_e, k, hist_pairs=(hu, hi), seg=seg)
+            assert c is not None and c.shape == (1, Q, k, 2)
+            cands.append(c)
+        cs, ci = sharded.unpack_candidates(torch.cat(cands, dim=0))
+        s_m, i_m = ops.topk_merge(cs, ci)
+        torch.cuda.synchronize()
+        assert torch.equal(i_m, i_ref) and torch.equal(s_m, s_ref), (world, seg)
 
 
 def test_tc_score_nan_rows_rank_first():
