@@ -305,7 +305,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        div = args.cpu_sample_div or (50 if wl["n_items"] >= 1_000_000 else 5)
+        div = args.cpu_sample_div or (50 if wl["n_items"] >= 5_000_000 else (10 if wl["n_items"] >= 1_000_000 else 5))
         qps, desc, threads, ms = cpu_reference(wl, args.steps, args.warmup, div, budget_s=120.0)
         print(json.dumps({"impl": "reference", "metric": "full_sort_topk_queries_per_s", "value": qps, "unit": "queries/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -460,9 +460,11 @@ def main():
             cands.append((t_ms * launches_per_step, d))
 
         # fused score + mask + top-k: algorithmic flops 2 Q N D
-        tensor_entry("tc_score_topk_kernel + merge_keys_kernel (tcgen05 scoring fused with masks and top-k)",
+        tensor_entry("tc_score_topk_kernel<1> + score_threshold_kernel + tc_score_topk_kernel<0> + merge_keys_kernel "
+                     "(tcgen05 scoring fused with masks and top-k; sampled pre-pass threshold)",
                      stages["score_topk_ms"], 2.0 * Q * N * wl["D"],
-                     note="epilogue (threshold filter + candidate lists), not the MMA, bounds this kernel")
+                     note="algorithmic flops 2 Q N D over the time of all four launches; the accumulator hand-over "
+                          "(D = 64: four MMAs per 128 x 128 tile) and the epilogue bound it, not the MMA rate")
         if wl["embedder"] == "dhe":
             ids_oov = torch.arange(wl["n_old_items"], N, device=device)
             keys_dev = emb._keys_dev
@@ -475,6 +477,11 @@ def main():
             stages["dhe_hidden_layer_ms_per_262144_rows"] = t_ms
             tensor_entry("tc_linear_kernel<256,GELU,FAST> (DHE hidden layer 512x512, tcgen05)", t_ms,
                          2.0 * M * wl["hidden"] * wl["hidden"], launches_per_step=2 * max(1, -(-n_oov // M)))
+            if M == 1 << 18 and wl["hidden"] == 512:
+                # dram__bytes_read.sum + dram__bytes_write.sum of this launch shape, ncu --set full capture
+                # (profiles/r01_linear_ncu.txt): 269.0 MB + 229.4 MB; algorithmic bytes 2 x 268.4 MB + 0.5 MB weights
+                cands[-1][1]["traffic"] = 498.4e6
+                cands[-1][1]["traffic_source"] = "profiles/r01_linear_ncu.txt (ncu --set full, same launch shape)"
         else:
             ids_oov = torch.arange(wl["n_old_items"], N, device=device)
             feat_i = emb.item_feature_mat
@@ -491,8 +498,9 @@ def main():
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        div = args.cpu_sample_div or (50 if N >= 1_000_000 else 5)
-        qps, desc, threads, _ = cpu_reference(wl, 3, 1, div, budget_s=25.0)
+        # bounded sample: ~12 s of CPU work on 1/10 (1M-item workloads) or 1/50 (10M) of the item axis
+        div = args.cpu_sample_div or (50 if N >= 5_000_000 else (10 if N >= 1_000_000 else 5))
+        qps, desc, threads, _ = cpu_reference(wl, 1000, 1, div, budget_s=12.0)
         cpu_base = {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": desc}
 
     if rank == 0:
