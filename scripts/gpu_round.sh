@@ -1,15 +1,5 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-show() { python - "$1" <<'PY'
-import json,sys
-f=sys.argv[1]
-try:
-    d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, d["n_gpus"], "value", round(d["value"]), "ms/step", round(d["ms_per_step"],3), "e2e", round(d["e2e"]["value"]), "e2e ms", round(d["e2e"].get("ms_per_step",0),3), "launches", d.get("gpu_launches"), d.get("stages"), "roofline", (d.get("roofline") or {}).get("kernel"), (d.get("roofline") or {}).get("frac"), "cpu", d.get("cpu_baseline"))
-except Exception as e: print(f, "ERR", e)
-PY
-}
-timeout 600 python bench.py > gpurun_out/r01_bench_dhe1m.json 2> gpurun_out/r01_bench_dhe1m.err; echo rc=$?; tail -3 gpurun_out/r01_bench_dhe1m.err; show gpurun_out/r01_bench_dhe1m.json
-timeout 600 python bench.py --workload lsh10m --steps 10 > gpurun_out/r01_bench_lsh10m.json 2> gpurun_out/r01_bench_lsh10m.err; echo rc=$?; tail -3 gpurun_out/r01_bench_lsh10m.err; show gpurun_out/r01_bench_lsh10m.json
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r01_bench_ref_dhe1m.json 2> gpurun_out/r01_bench_ref.err; echo rc=$?; show gpurun_out/r01_bench_ref_dhe1m.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r01_launches_bench_dhe1m.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo rc=$?
+timeout 600 python -c "import __graft_entry__ as g; g.build(); g.smoke()" 2>&1 | tail -5
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
