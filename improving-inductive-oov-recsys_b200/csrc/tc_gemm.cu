@@ -165,7 +165,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int64_t mt = t / n_tiles; const int nt = (int)(t - mt * n_tiles);
                 for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
                     unsigned char* sa = smem + stage * S::STAGE_BYTES;
                     tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, (int)(mt * BM));
@@ -208,8 +208,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int cq = (warp - EPI_WARP0) >> 2;     // column quarter: 64 of the tile's 256 columns
             unsigned char* stg = staging + (warp - EPI_WARP0) * (32 * 128);
             for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int64_t mt = t / n_tiles; const int nt = (int)(t - mt * n_tiles);
-                mbar_wait(&tmem_full[acc], acc_phase);
+                // 32-bit split when it fits (a 64-bit division is ~40 instructions per tile and warp)
+                const int64_t mt = total_tiles < (1ll << 31) ? (int64_t)((uint32_t)t / (uint32_t)n_tiles) : t / n_tiles;
+                const int nt = (int)(t - mt * n_tiles);
+                mbar_wait_relaxed(&tmem_full[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cq * 64);
                 uint32_t v0[32], v1[32];
@@ -253,14 +255,23 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 if (epi.debug & 1) continue;
                 __syncwarp();
-                const int64_t row_base = mt * BM + q * 32;
-                __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(epi.out) + col0;
+                // 4 rows x 128 B per store instruction; pointer, stride, swizzle offsets and the row bound are hoisted
+                // (the straightforward indexing spent 16 integer instructions per store on 64-bit address arithmetic)
+                const int r0 = lane >> 3, c = lane & 7;
+                const int64_t row0 = mt * BM + q * 32 + r0;
+                char* gp = reinterpret_cast<char*>(reinterpret_cast<__nv_bfloat16*>(epi.out) + col0 + row0 * epi.ld + c * 8);
+                const int64_t gstep = epi.ld * 8;                 // four rows of bf16
+                const unsigned char* sp = stg + r0 * 128;
+                const int off_even = (c ^ r0) << 4, off_odd = (c ^ (r0 + 4)) << 4;    // row & 7 = r0 + 4 (i & 1)
+                const int64_t left = M - row0;                    // rows r0, r0 + 4, ... below M
+                const int n_it = left <= 0 ? 0 : (left >= 29 ? 8 : (int)((left + 3) >> 2));
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {                    // 4 rows x 128 B per instruction
-                    const int r = i * 4 + (lane >> 3), c = lane & 7;
-                    const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 128 + ((c ^ (r & 7)) << 4));
-                    if (row_base + r < M)
-                        *reinterpret_cast<uint4*>(obase + (row_base + r) * epi.ld + c * 8) = val;
+                for (int i = 0; i < 8; ++i) {
+                    if (i < n_it) {
+                        const uint4 val = *reinterpret_cast<const uint4*>(sp + i * 512 + ((i & 1) ? off_odd : off_even));
+                        *reinterpret_cast<uint4*>(gp) = val;
+                    }
+                    gp += gstep;
                 }
                 __syncwarp();
             }

@@ -143,6 +143,41 @@ def test_pairs_to_csr():
     assert rp.tolist() == w_rp.tolist() and cols.tolist() == w_c.tolist()
 
 
+def test_pairs_to_csr_column_map_and_padding():
+    """Host restatement of oov_pairs_to_csr's contract: padding rows dropped, two-range column map to local rows."""
+    from oov_b200 import ops
+    hu = torch.tensor([2, 0, 2, 4, 2, 0, -1, 1])          # 4 and -1 are padding for Q = 4
+    hi = torch.tensor([9, 4, 1, 7, 25, 3, 2, 30])
+    rp, cols = ops.pairs_to_csr(hu, hi, 4)
+    assert rp.tolist() == [0, 2, 3, 6, 6] and cols[:6].tolist() == [3, 4, 30, 1, 9, 25]
+    # shard = items [0, 5) and [20, 40): local rows 0..4 and 5..24; items 7, 9 belong to other ranks
+    rp, cols = ops.pairs_to_csr(hu, hi, 4, col_ranges=((0, 5), (20, 40)))
+    assert rp.tolist() == [0, 2, 3, 5, 5] and cols[:5].tolist() == [3, 4, 15, 1, 10]
+
+
+def test_sharded_local_segments():
+    """ShardedRetrieval._local_seg: a global id filter as one range of local rows of [in-vocab slice | OOV slice]."""
+    from oov_b200 import sharded
+
+    class M:
+        n_items = 100
+    sr = sharded.ShardedRetrieval(M(), 260, rank=1, world_size=4, local_topk_fn=None, merge_fn=lambda a, b: (a, b))
+    assert sr.segments == [(25, 50), (140, 180)] and sr.fused
+    assert sr._local_seg((0, 1 << 62)) == (0, 65)
+    assert sr._local_seg((0, 100)) == (0, 25)              # old items only
+    assert sr._local_seg((100, 1 << 62)) == (25, 65)       # new items only
+    assert sr._local_seg((30, 150)) == (5, 35)             # tail of range 0 + head of range 1: contiguous locally
+    assert sr._local_seg((30, 45)) == (5, 20)
+    assert sr._local_seg((0, 45)) == (0, 20)
+    assert sr._local_seg((60, 120)) == (0, 0)              # nothing of this rank
+    assert sr._local_seg((26, 40)) == (1, 15)
+    assert sr._local_seg((10, 49)) == (0, 24) and sr._local_seg((30, 49)) == (5, 24)
+    assert sr._local_seg((26, 175)) is not None and sr._local_seg((26, 175)) == (1, 60)
+    # not contiguous in local rows: stops short of the end of range 0 but continues into range 1
+    assert sr._local_seg((30, 49 + 100)) == (5, 34)        # 49 + 100 = 149 -> [30, 50) and [140, 149): contiguous
+    assert sr._local_seg((0, 1 << 62)) == (0, 65)
+
+
 def test_shard_arithmetic_and_packing():
     from oov_b200 import sharded
     for n, world in ((10, 4), (7, 8), (1_000_003, 8), (0, 2)):
