@@ -475,7 +475,7 @@ def main():
             bias = torch.zeros(wl["hidden"], device=device)
             t_ms = ev_time(lambda: ops.tc_linear(A, Wt, bias, act="gelu", out_dtype=torch.bfloat16), reps=10)
             stages["dhe_hidden_layer_ms_per_262144_rows"] = t_ms
-            tensor_entry("tc_linear_kernel<256,GELU,FAST> (DHE hidden layer 512x512, tcgen05)", t_ms,
+            tensor_entry("tc_linear2_kernel<GELU> (DHE hidden layer 512x512, tcgen05 cta_group::2 CTA pairs)", t_ms,
                          2.0 * M * wl["hidden"] * wl["hidden"], launches_per_step=2 * max(1, -(-n_oov // M)))
             if M == 1 << 18 and wl["hidden"] == 512:
                 # dram__bytes_read.sum + dram__bytes_write.sum of this launch shape, ncu --set full capture
