@@ -479,9 +479,9 @@ def main():
                          2.0 * M * wl["hidden"] * wl["hidden"], launches_per_step=2 * max(1, -(-n_oov // M)))
             if M == 1 << 18 and wl["hidden"] == 512:
                 # dram__bytes_read.sum + dram__bytes_write.sum of this launch shape, ncu --set full capture
-                # (profiles/r01_linear_ncu.txt): 269.0 MB + 229.4 MB; algorithmic bytes 2 x 268.4 MB + 0.5 MB weights
-                cands[-1][1]["traffic"] = 498.4e6
-                cands[-1][1]["traffic_source"] = "profiles/r01_linear_ncu.txt (ncu --set full, same launch shape)"
+                # (profiles/r01_linear2_ncu.txt): 269.1 MB + 222.5 MB; algorithmic bytes 2 x 268.4 MB + 0.5 MB weights
+                cands[-1][1]["traffic"] = 491.6e6
+                cands[-1][1]["traffic_source"] = "profiles/r01_linear2_ncu.txt (ncu --set full, same launch shape)"
         else:
             ids_oov = torch.arange(wl["n_old_items"], N, device=device)
             feat_i = emb.item_feature_mat
