@@ -644,6 +644,8 @@ static int launch_linear(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat1
 template <int ACT>
 static int tc_linear_act(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, int64_t M, int N, int K,
                          const LinearEpi& epi, cudaStream_t st) {
+    // (N = 64, the last DHE layer, through this 256-wide kernel was measured: 6 % SLOWER than the generic 64-wide one —
+    // three quarters of the MMA columns and of the weight tile would be TMA zero fill)
     const bool fast = epi.out_dtype == OOV_BF16 && N > 64 && N % 64 == 0 && N <= 1024 && epi.ids == nullptr &&
                       epi.ld % 8 == 0 && aligned(epi.out, 16);
     // CTA pairs need full 256-column weight blocks (each CTA loads 128 of them) and more than one 256-row tile to pay
@@ -984,7 +986,8 @@ int dhe_tc_run(const uint8_t* keys, uint64_t mod, const oov_dhe_net* net, const 
         LinearEpi f{};
         f.bias = net->b[3]; f.act = ACT_SIGMOID; f.out_dtype = out_dtype; f.ld = out_stride;
         f.out = reinterpret_cast<char*>(out) + (size_t)r0 * out_stride * osz;
-        f.ids = ids ? ids + r0 * ids_stride : nullptr; f.ids_stride = ids_stride; f.n_old = n_old;
+        // per-row assemble (rows whose id < n_old take the in-vocab row) only when there can be such rows
+        f.ids = (ids && n_old > 0) ? ids + r0 * ids_stride : nullptr; f.ids_stride = ids_stride; f.n_old = n_old;
         f.iv_table = iv_table; f.iv_dtype = iv_dtype;
         if (hashes_u32 != nullptr) f.ids = nullptr;
         rc = tc_linear((const __nv_bfloat16*)act0, hid, (const __nv_bfloat16*)(packed + L.off[3]), hid, cn, net->D, hid, f, st);
