@@ -37,6 +37,7 @@ class GraphedTopK:
         self.scores: Optional[torch.Tensor] = None
         self.ids: Optional[torch.Tensor] = None
         self.launches_per_replay = 0
+        self._side = torch.cuda.Stream(device=dev)                 # query-side branch of the step
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -52,15 +53,29 @@ class GraphedTopK:
         torch.cuda.synchronize(dev)
 
     def _step(self):
+        """One step on the current stream, with the query side (history CSR + user embed: a dozen small kernels that
+        fill a few SMs) forked onto a second stream so that it runs under the item-table assembly instead of in front
+        of it; the streams join before the scoring launch.  Captured as two branches of the graph."""
         m = self.model
-        user_e = m._assemble("user", self.users, out_dtype=m.table_dtype)
+        cur = torch.cuda.current_stream(m.device)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            if self.sr is not None and self.sr.fused:
+                csr = self.sr.local_history_csr((self.hist_rows, self.hist_cols), self.Q)
+            else:
+                csr = ops.pairs_to_csr(self.hist_rows, self.hist_cols, self.Q)      # padding rows (= Q) are dropped
+            user_e = m._assemble("user", self.users, out_dtype=m.table_dtype)
         if self.sr is None:
-            csr = ops.pairs_to_csr(self.hist_rows, self.hist_cols, self.Q)  # padding rows (= Q) are dropped
             table = m.build_item_table(self.N)
+            cur.wait_stream(self._side)
             s, i = ops.fullsort_topk(user_e, table, self.k, mask_pad=True, hist=csr)
         else:
             self.sr.build_shard()
-            s, i = self.sr.topk(user_e, self.k, hist_pairs=(self.hist_rows, self.hist_cols))
+            cur.wait_stream(self._side)
+            if self.sr.fused:
+                s, i = self.sr.topk(user_e, self.k, local_csr=csr)
+            else:
+                s, i = self.sr.topk(user_e, self.k, hist=csr)
         self.hist_rows.fill_(self.Q)                               # padding for the next call's shorter pair list
         return s, i
 

@@ -111,8 +111,16 @@ class ShardedRetrieval:
             return (n0 + a1 - lo1, n0 + b1 - lo1)
         return (0, 0)
 
-    def fused_candidates(self, user_e: torch.Tensor, k: int, hist_pairs=None, seg=(0, INT64_MAX)) -> Optional[torch.Tensor]:
-        """[1, Q, k, 2] candidates from one launch over the fused table; None if `seg` needs the per-segment path."""
+    def local_history_csr(self, hist_pairs, Q: int):
+        """History pairs -> CSR over the LOCAL rows of the fused table (items of other ranks dropped)."""
+        from . import ops
+        if hist_pairs is None or hist_pairs[0] is None:
+            return None
+        return ops.pairs_to_csr(hist_pairs[0], hist_pairs[1], Q, col_ranges=self.segments)
+
+    def fused_candidates(self, user_e: torch.Tensor, k: int, hist_pairs=None, seg=(0, INT64_MAX), local_csr=None) -> Optional[torch.Tensor]:
+        """[1, Q, k, 2] candidates from one launch over the fused table; None if `seg` needs the per-segment path.
+        `local_csr` = a CSR already built by `local_history_csr` (e.g. on another stream)."""
         from . import ops
         lseg = self._local_seg(seg)
         if lseg is None:
@@ -121,9 +129,7 @@ class ShardedRetrieval:
             self.build_shard()
         (lo0, hi0), (lo1, hi1) = self.segments
         n0 = hi0 - lo0
-        csr = None
-        if hist_pairs is not None and hist_pairs[0] is not None:
-            csr = ops.pairs_to_csr(hist_pairs[0], hist_pairs[1], user_e.shape[0], col_ranges=self.segments)
+        csr = local_csr if local_csr is not None else self.local_history_csr(hist_pairs, user_e.shape[0])
         s, rows = ops.fullsort_topk(user_e, self.table, k, item_id_offset=0, mask_pad=(lo0 == 0 and hi0 > 0), seg=lseg, hist=csr)
         ids = torch.where(rows < n0, rows + lo0, rows + (lo1 - n0))
         ids = torch.where(rows < 0, rows, ids)                      # empty slots stay -1
@@ -138,12 +144,12 @@ class ShardedRetrieval:
             packed.append(pack_candidates(s, i))
         return torch.stack(packed, dim=0)                       # [S, Q, k, 2]
 
-    def topk(self, user_e: torch.Tensor, k: int, hist=None, seg=(0, INT64_MAX), hist_pairs=None):
+    def topk(self, user_e: torch.Tensor, k: int, hist=None, seg=(0, INT64_MAX), hist_pairs=None, local_csr=None):
         """Global (scores [Q,k], ids [Q,k]) — identical on every rank.  History either as a CSR over GLOBAL item ids
         (`hist`, per-segment path) or as the dataloader's (row, item) pairs (`hist_pairs`, fused one-launch path)."""
         local = None
         if self.fused and hist is None:
-            local = self.fused_candidates(user_e, k, hist_pairs, seg)
+            local = self.fused_candidates(user_e, k, hist_pairs, seg, local_csr)
         if local is None:
             if hist is None and hist_pairs is not None and hist_pairs[0] is not None:
                 from . import ops
