@@ -493,6 +493,9 @@ def main():
             tensor_entry("tc_lsh_embed_kernel (sign-projection GEMM + bucket-mean GEMM, tcgen05, operands in TMEM)", t_ms,
                          2.0 * n_oov * wl["B"] * (wl["F"] + wl["D"]),
                          note="algorithmic flops = 2 B (F + D) per OOV id (SURVEY 8d); the kernel issues 3 F + D (+16) wide MMAs")
+        # throughput when the item table is embedded once per weight version and reused by every query
+        # batch (only the query side and the scoring run per step) — derived from the stage timings above
+        stages["amortised_queries_per_s_item_table_reused"] = Q / ((stages["user_embed_ms"] + stages["score_topk_ms"]) * 1e-3)
         roofline = max(cands, key=lambda c: c[0])[1]
         roofline["others"] = [c[1] for c in cands if c[1] is not roofline]
 
