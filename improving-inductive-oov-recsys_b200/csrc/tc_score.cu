@@ -10,12 +10,12 @@
 //   warps 17-18  MMA issuers  : two user tiles `ut` each; per item tile and user tile 4 x tcgen05.mma (M 128, N 128, K 16) into
 //                               accumulator `ut` (TMEM columns ut*128 ..); the tensor core works on the other
 //                               three user tiles while one is being drained
-//   warps 0-15   epilogue     : thread = one user (TMEM lane).  Per 32-column tcgen05.ld (double-buffered in
-//                               registers) a NaN-propagating 3-input max tree is compared ONCE with the user's
-//                               threshold; only groups that beat it are scanned, masked (pad / segment / history)
-//                               and inserted into the user's sorted list (smem, thread-private column).
-// Threshold sharing: a user is scored by P = gridDim.x CTAs ("streams"), and a short stream's own k-th best is a
-// weak filter.  Every stream publishes its j-th best score (j = ceil(k / G), G = min(P, k)) with a plain store;
+//   warps 0-15   epilogue     : thread = one user (TMEM lane).  Per 32-column tcgen05.ld a NaN-propagating 3-input max
+//                               tree is compared ONCE with the user's threshold (one warp vote, a second vote per
+//                               quarter chunk); only what beats it is queued, masked (pad / segment / history) and
+//                               inserted into the user's list (smem, thread-private column).
+// Threshold sharing (shards below 256 full tiles; larger shards take the sampled pre-pass described below): a user is
+// scored by P = gridDim.x CTAs ("streams"), and a short stream's own k-th best is a weak filter.  Every stream publishes its j-th best score (j = ceil(k / G), G = min(P, k)) with a plain store;
 // the streams are dealt into G groups and T = min over groups of (max over the group's streams of the published
 // value) has at least G * j >= k distinct scores at or above it, so dropping scores strictly below T is exact.
 // Threads refresh T on a doubling schedule (after tiles 1, 2, 4, 8, ...): total candidates per user stay near
