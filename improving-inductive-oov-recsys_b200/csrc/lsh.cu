@@ -276,6 +276,126 @@ slsh_embed_simt(const float* __restrict__ feat, int64_t n_feat_rows, int F,
     if (tie_count != nullptr && lane == 0 && my_ties) atomicAdd(tie_count, (unsigned long long)my_ties);
 }
 
+// lane = id variant (bits_req <= NP planes): the warp-per-id kernel above keeps 10 of 32 lanes busy and walks a
+// dependent chain per id (623 us per 1 M ids = 10-16 % of the HBM rate of its algorithmic bytes).  Here every lane
+// projects ITS id's feature row on all planes (plane values are warp-uniform shared-memory broadcasts, the row comes
+// in 16-byte loads), same f-ascending fmaf chain per plane as above -> identical bits; the bucket rows are then copied
+// by the whole warp, one list position after the other, so the stores are full lines.
+template <int NP>
+__global__ void __launch_bounds__(SLSH_THREADS)
+slsh_embed_lane(const float* __restrict__ feat, int64_t n_feat_rows, int F,
+                const float* __restrict__ planes, int bits_req, int n_buckets,
+                const void* __restrict__ W, int w_dtype,
+                const int64_t* __restrict__ ids, int64_t ids_stride, int64_t n,
+                int64_t n_old, int64_t prime_pad,
+                const void* __restrict__ iv_table, int iv_dtype,
+                void* __restrict__ out, int out_dtype, int64_t out_stride, int D,
+                float tie_eps, int64_t* __restrict__ bucket_out, unsigned long long* __restrict__ tie_count) {
+    extern __shared__ float Pt[];            // [F][NP], plane p of feature f at Pt[f * NP + p]; planes >= bits_req are 0
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < F * NP; i += SLSH_THREADS) {
+        const int f = i / NP, p = i - f * NP;
+        Pt[i] = p < bits_req ? __ldg(planes + (size_t)p * F + f) : 0.f;
+    }
+    __syncthreads();
+    const int warps_per_block = SLSH_THREADS / 32;
+    const size_t osz = out_dtype == OOV_F32 ? 4 : 2, wsz = w_dtype == OOV_F32 ? 4 : 2, isz = iv_dtype == OOV_F32 ? 4 : 2;
+    const bool vec4 = (F & 3) == 0 && aligned_dev(feat, 16);
+    unsigned int my_ties = 0;
+    for (int64_t base = ((int64_t)blockIdx.x * warps_per_block + warp) * 32; base < n;
+         base += (int64_t)gridDim.x * warps_per_block * 32) {
+        const int64_t r = base + lane;
+        const bool valid = r < n;
+        const int64_t id = valid ? ids[r * ids_stride] : 0;
+        const bool oov = valid && id >= n_old;
+        const int64_t fr = feature_row(id, prime_pad);
+        const bool inrange = oov && fr >= 0 && fr < n_feat_rows;
+        const float* x = feat + (inrange ? fr : 0) * F;
+        float acc[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) acc[p] = 0.f;
+        if (vec4) {
+            for (int f = 0; f < F; f += 4) {
+                float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (inrange) xv = __ldg(reinterpret_cast<const float4*>(x + f));
+                const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4* pr = reinterpret_cast<const float4*>(Pt + (f + i) * NP);
+#pragma unroll
+                    for (int p4 = 0; p4 < NP / 4; ++p4) {
+                        const float4 pv = pr[p4];
+                        acc[4 * p4 + 0] = fmaf(xs[i], pv.x, acc[4 * p4 + 0]);
+                        acc[4 * p4 + 1] = fmaf(xs[i], pv.y, acc[4 * p4 + 1]);
+                        acc[4 * p4 + 2] = fmaf(xs[i], pv.z, acc[4 * p4 + 2]);
+                        acc[4 * p4 + 3] = fmaf(xs[i], pv.w, acc[4 * p4 + 3]);
+                    }
+                }
+            }
+        } else {
+            for (int f = 0; f < F; ++f) {
+                const float xf = inrange ? __ldg(x + f) : 0.f;
+#pragma unroll
+                for (int p = 0; p < NP; ++p) acc[p] = fmaf(xf, Pt[f * NP + p], acc[p]);
+            }
+        }
+        unsigned word = 0u;
+        int ties = 0;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            if (p < bits_req) {
+                word |= (!(acc[p] < 0.f)) ? (1u << p) : 0u;
+                ties += (fabsf(acc[p]) < tie_eps) ? 1 : 0;
+            }
+        }
+        if (oov) my_ties += (unsigned)ties;
+        // (2 ** H).sum(1) % n_buckets with H in {0,1}  ==  (bits_req + popcount) % n_buckets
+        const int bucket = (bits_req + __popc(word)) % n_buckets;
+        if (bucket_out && valid) bucket_out[r] = oov ? bucket : -1;
+        if (out == nullptr) continue;
+        const int cnt = (int)((n - base) < 32 ? (n - base) : 32);
+        // fast copy: bucket table and output in the same dtype, rows of 64 / 128 / 256 / 512 bytes, nothing in-vocab in
+        // this group of 32: LPR lanes move one row in 16-byte pieces, 32 / LPR rows per step, four steps of loads in
+        // flight before their stores
+        const int row_bytes = D * (int)osz;
+        const bool fast_rows = W != nullptr && w_dtype == out_dtype && out_stride == D &&
+                               (row_bytes == 64 || row_bytes == 128 || row_bytes == 256 || row_bytes == 512) &&
+                               aligned_dev(W, 16) && aligned_dev(out, 16) && __all_sync(0xffffffffu, oov || !valid);
+        if (fast_rows) {
+            const int lpr = row_bytes >> 4, rpi = 32 / lpr;           // lanes per row, rows per step
+            const int piece = lane % lpr, slot = lane / lpr;
+            char* obase = reinterpret_cast<char*>(out) + (size_t)base * row_bytes;
+            for (int j0 = 0; j0 < cnt; j0 += 4 * rpi) {
+                uint4 v[4];
+                int jj[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    jj[u] = j0 + u * rpi + slot;
+                    const int bj = __shfl_sync(0xffffffffu, bucket, jj[u] & 31);
+                    if (jj[u] < cnt) v[u] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(W) + (size_t)bj * row_bytes) + piece);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (jj[u] < cnt) reinterpret_cast<uint4*>(obase + (size_t)jj[u] * row_bytes)[piece] = v[u];
+            }
+            continue;
+        }
+        for (int j = 0; j < cnt; ++j) {
+            const int64_t idj = __shfl_sync(0xffffffffu, id, j);
+            const int oovj = __shfl_sync(0xffffffffu, (int)oov, j), bj = __shfl_sync(0xffffffffu, bucket, j);
+            char* orow = reinterpret_cast<char*>(out) + (size_t)(base + j) * out_stride * osz;
+            if (oovj) {
+                if (W != nullptr)
+                    copy_row(reinterpret_cast<const char*>(W) + (size_t)bj * D * wsz, w_dtype, orow, out_dtype, D, lane, 32);
+            } else if (iv_table != nullptr && idj >= 0) {
+                copy_row(reinterpret_cast<const char*>(iv_table) + (size_t)idj * D * isz, iv_dtype, orow, out_dtype, D, lane, 32);
+            }
+        }
+    }
+    my_ties = __reduce_add_sync(0xffffffffu, my_ties);
+    if (tie_count != nullptr && lane == 0 && my_ties) atomicAdd(tie_count, (unsigned long long)my_ties);
+}
+
 // bucket ids from packed words (F > SLSH_MAXF fallback): one thread per row
 __global__ void slsh_finish(const uint32_t* __restrict__ bits, int bits_req, int n_buckets,
                             const void* __restrict__ W, int w_dtype,
@@ -422,6 +542,27 @@ int oov_slsh_embed(const float* feat, int64_t n_feat_rows, int32_t F, const floa
     if (rows->n == 0) return OOV_OK;
     cudaStream_t st = (cudaStream_t)stream;
     OOV_REQUIRE(F <= SLSH_MAXF, OOV_ERR_ARG, "oov_slsh_embed: F=%d > %d (use oov_lsh_bits + bucket gather)", F, SLSH_MAXF);
+    if (bits_req <= 16 && F <= 512) {
+        constexpr int NP = 16;
+        const size_t smem16 = (size_t)F * NP * sizeof(float);
+        static bool attr16 = false;
+        if (!attr16) {
+            cudaFuncSetAttribute(slsh_embed_lane<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * NP * 4);
+            attr16 = true;
+        }
+        static int per_sm = 0;
+        if (per_sm == 0 &&
+            (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, slsh_embed_lane<NP>, SLSH_THREADS, smem16) != cudaSuccess || per_sm < 1))
+            per_sm = 2;
+        int64_t blocks16 = cdiv(rows->n, (int64_t)(SLSH_THREADS / 32) * 32);
+        if (blocks16 > (int64_t)num_sms() * per_sm) blocks16 = (int64_t)num_sms() * per_sm;
+        slsh_embed_lane<NP><<<(unsigned)blocks16, SLSH_THREADS, smem16, st>>>(
+            feat, n_feat_rows, F, planes, bits_req, n_buckets, W, w_dtype, rows->ids, rows->ids_stride, rows->n, rows->n_old,
+            rows->prime_pad, rows->iv_table, rows->iv_dtype, rows->out, rows->out_dtype, rows->out_stride, rows->D, tie_eps,
+            bucket_out, tie_count);
+        OOV_LAUNCH_CHECK("slsh_embed_lane");
+        return OOV_OK;
+    }
     const size_t smem = (size_t)F * 32 * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
