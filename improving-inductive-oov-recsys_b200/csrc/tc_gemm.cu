@@ -426,7 +426,7 @@ struct Gemm2Smem {
 template <int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Smem::THREADS, 1)
 tc_linear2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  int64_t M, int N, int K, LinearEpi epi) {
+                  const __grid_constant__ CUtensorMap tmO, int64_t M, int N, int K, LinearEpi epi) {
     using S = Gemm2Smem;
     constexpr int BN = 256;
     extern __shared__ unsigned char smem_raw[];
@@ -450,7 +450,7 @@ tc_linear2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int k_blocks = (K + BK - 1) / BK;
     constexpr uint32_t TMEM_COLS = 2 * BN;
 
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmO); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < S::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * S::NEPI); }
@@ -530,6 +530,10 @@ tc_linear2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             const int col0 = nt * BN + cq * 64;
             if (col0 >= N || (epi.debug & 2)) continue;      // warp-uniform
+            if (epi.debug & 8) {                             // TMA store path: the previous tile's store must have read the staging
+                if (lane == 0) bulk_wait_group_read0();
+                __syncwarp();
+            }
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 uint32_t pk[16];
@@ -560,6 +564,17 @@ tc_linear2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
             }
             if (epi.debug & 1) continue;
+            if (epi.debug & 8) {
+                // the staging tile is exactly a 32-row x 64-column SWIZZLE_128B box: one bulk tensor store per warp, issued by
+                // one lane, asynchronous (rows >= M are clipped by the tensor map)
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmO, stg, col0, (int)(mt * 2 * BM + (int64_t)rank * BM + q * 32));
+                    bulk_commit_group();
+                }
+                continue;
+            }
             __syncwarp();
             const int r0 = lane >> 3, c = lane & 7;
             const int64_t row0 = mt * 2 * BM + (int64_t)rank * BM + q * 32 + r0;
@@ -579,6 +594,7 @@ tc_linear2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             __syncwarp();
         }
+        if ((epi.debug & 8) && lane == 0) bulk_wait_group0();
     }
 
     tc_fence_before();
@@ -605,6 +621,15 @@ static int launch_linear2(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, 128);
     if (rc) return rc;
+    CUtensorMap tmO;                                       // output as 32-row x 64-column boxes (one per epilogue warp)
+    rc = make_tmap_bf16_2d(&tmO, epi.out, (uint64_t)N, (uint64_t)M, (uint64_t)epi.ld * 2, 32);
+    if (rc) return rc;
+    LinearEpi e2 = epi;
+    {
+        static int tma_store = -1;
+        if (tma_store < 0) { const char* e = getenv("OOV_LINEAR_TMASTORE"); tma_store = e ? atoi(e) : 1; }
+        if (tma_store) e2.debug |= 8;                      // bit 3: epilogue stores through TMA
+    }
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tc_linear2_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
@@ -614,7 +639,7 @@ static int launch_linear2(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat
     const int64_t tiles = cdiv(M, 2 * BM) * cdiv(N, 256);
     const int pairs_max = num_sms() / 2;
     const int grid = 2 * (int)(tiles < pairs_max ? tiles : pairs_max);
-    tc_linear2_kernel<ACT><<<grid, S::THREADS, S::TOTAL, st>>>(tmA, tmB, M, N, K, epi);
+    tc_linear2_kernel<ACT><<<grid, S::THREADS, S::TOTAL, st>>>(tmA, tmB, tmO, M, N, K, e2);
     OOV_LAUNCH_CHECK("tc_linear2_kernel");
     return OOV_OK;
 }
