@@ -66,7 +66,16 @@ class GraphedTopK:
                 csr = ops.pairs_to_csr(self.hist_rows, self.hist_cols, self.Q)      # padding rows (= Q) are dropped
             user_e = m._assemble("user", self.users, out_dtype=m.table_dtype)
         if self.sr is None:
-            table = m.build_item_table(self.N)
+            split = min(m.n_items, self.N)
+            if m.inductive_embedder is not None and m.inductive_mapper is None and 0 < split < self.N:
+                # the in-vocab half of the table (a memory-bound gather-cast) joins the query-side branch, the OOV half
+                # (SipHash + MLP / LSH GEMMs) is the main branch
+                table = torch.empty((self.N, m.embedding_size), dtype=m.table_dtype, device=m.device)
+                with torch.cuda.stream(self._side):
+                    m.build_item_table(self.N, row_range=(0, split), out=table[:split])
+                m.build_item_table(self.N, row_range=(split, self.N), out=table[split:])
+            else:
+                table = m.build_item_table(self.N)
             cur.wait_stream(self._side)
             s, i = ops.fullsort_topk(user_e, table, self.k, mask_pad=True, hist=csr)
         else:
