@@ -79,7 +79,10 @@ class GraphedTopK:
             cur.wait_stream(self._side)
             s, i = ops.fullsort_topk(user_e, table, self.k, mask_pad=True, hist=csr)
         else:
-            self.sr.build_shard()
+            if self.sr.fused:
+                self.sr.build_shard(iv_stream=self._side)          # in-vocab slice on the query-side branch
+            else:
+                self.sr.build_shard()
             cur.wait_stream(self._side)
             if self.sr.fused:
                 s, i = self.sr.topk(user_e, self.k, local_csr=csr)

@@ -80,16 +80,22 @@ class ShardedRetrieval:
         self._build = build_table_fn or (lambda lo, hi: model.build_item_table(n_total_items, row_range=(lo, hi)))
         self.tables: Optional[List[torch.Tensor]] = None
 
-    def build_shard(self) -> List[torch.Tensor]:
-        """Embed this rank's rows (in-vocab gather + OOV embed); no communication."""
+    def build_shard(self, iv_stream: Optional[torch.cuda.Stream] = None) -> List[torch.Tensor]:
+        """Embed this rank's rows (in-vocab gather + OOV embed); no communication.  `iv_stream`: run the in-vocab
+        segment (a memory-bound gather) on that stream, concurrently with the OOV segment; the caller joins the streams."""
         if self.fused:
             m = self.model
             n0 = self.segments[0][1] - self.segments[0][0]
             n1 = self.segments[1][1] - self.segments[1][0]
             self.table = torch.empty((n0 + n1, m.embedding_size), dtype=m.table_dtype, device=m.device)
             self.tables = [self.table[:n0], self.table[n0:]]
-            for (lo, hi), out in zip(self.segments, self.tables):
-                if hi > lo:
+            for i, ((lo, hi), out) in enumerate(zip(self.segments, self.tables)):
+                if hi <= lo:
+                    continue
+                if i == 0 and iv_stream is not None:
+                    with torch.cuda.stream(iv_stream):
+                        m.build_item_table(self.n_total, row_range=(lo, hi), out=out)
+                else:
                     m.build_item_table(self.n_total, row_range=(lo, hi), out=out)
             return self.tables
         self.tables = [self._build(lo, hi) for lo, hi in self.segments]
