@@ -229,6 +229,18 @@ __device__ __forceinline__ bool refresh_tile(int64_t it) {
     return low == 0 || ((low & (low - 1)) == 0 && (low >> 1) == (it ^ low));   // 2^a or 3 * 2^a
 }
 
+// NaN-propagating maximum of a 32-column chunk
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32]) {
+    float m[11];
+#pragma unroll
+    for (int j = 0; j < 10; ++j)
+        m[j] = max3_nan(__uint_as_float(v[3 * j]), __uint_as_float(v[3 * j + 1]), __uint_as_float(v[3 * j + 2]));
+    m[10] = max2_nan(__uint_as_float(v[30]), __uint_as_float(v[31]));
+    const float m0 = max3_nan(m[0], m[1], m[2]), m1 = max3_nan(m[3], m[4], m[5]);
+    const float m2 = max3_nan(m[6], m[7], m[8]), m3 = max2_nan(m[9], m[10]);
+    return max2_nan(max3_nan(m0, m1, m2), m3);
+}
+
 // one 32-column chunk of one user's scores (registers v[0..31]); `col0` = local item row of column 0.
 // Called by all 32 lanes together (warp votes inside).  Candidates are queued; the queue is drained here only when
 // some lane ran out of space (then the chunk is scanned again for what is left), else at the end of the tile.
@@ -483,17 +495,49 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
                 tc_fence_after();
                 const uint32_t row0 = (uint32_t)((p.tile_begin + t) * SC_BN);   // first local item row of the tile
                 uint32_t v[32];
+                if (p.thr_init != nullptr && !(p.debug & 64)) {
+                    // With the pre-pass threshold most tiles hold nothing for these 32 users: scan the four chunks first
+                    // (load, max tree, one vote each — a tcgen05.ld costs ~22 cycles) and hand the accumulator back at once
+                    // when no chunk has a hit, so the next tile's MMAs start ~1000 cycles earlier; chunks with hits are
+                    // loaded again and processed, the accumulator goes back after the last of them is in registers.
+                    unsigned hitmask = 0u;
 #pragma unroll 1
-                for (int c = 0; c < SC_BN / 32; ++c) {
-                    tc_ld_32x32(t_lane + (uint32_t)(c * 32), v);
-                    tc_wait_ld();
-                    if (c == SC_BN / 32 - 1) {
-                        // the whole accumulator has been read: hand it back to the MMA warp before the last chunk is processed
+                    for (int c = 0; c < SC_BN / 32; ++c) {
+                        tc_ld_32x32(t_lane + (uint32_t)(c * 32), v);
+                        tc_wait_ld();
+                        const float mx = chunk_max(v);
+                        if (__any_sync(0xffffffffu, !(mx < u.thr_f))) hitmask |= 1u << c;
+                    }
+                    if (hitmask == 0u) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&acc_empty[ut]);
                     }
-                    process_chunk(p, mr, u, v, row0 + (uint32_t)(c * 32));
+                    while (hitmask != 0u) {
+                        const int c = __ffs(hitmask) - 1;
+                        hitmask &= hitmask - 1u;
+                        tc_ld_32x32(t_lane + (uint32_t)(c * 32), v);
+                        tc_wait_ld();
+                        if (hitmask == 0u) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&acc_empty[ut]);
+                        }
+                        process_chunk(p, mr, u, v, row0 + (uint32_t)(c * 32));
+                    }
+                } else {
+#pragma unroll 1
+                    for (int c = 0; c < SC_BN / 32; ++c) {
+                        tc_ld_32x32(t_lane + (uint32_t)(c * 32), v);
+                        tc_wait_ld();
+                        if (c == SC_BN / 32 - 1) {
+                            // the whole accumulator has been read: hand it back to the MMA warp before the last chunk is processed
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&acc_empty[ut]);
+                        }
+                        process_chunk(p, mr, u, v, row0 + (uint32_t)(c * 32));
+                    }
                 }
                 if (__any_sync(0xffffffffu, u.cnt > 0)) drain(p, mr, u);
                 if (user_ok && share) {                               // this stream's j-th best so far
