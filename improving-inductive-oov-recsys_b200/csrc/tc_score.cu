@@ -30,7 +30,7 @@
 // then takes, per user, the R-th largest tile maximum with R = k + (masked items of that user inside sampled tiles):
 // every masked item is the maximum of at most one tile, so at least k sampled tiles have an UNMASKED item at or above
 // that value and no score strictly below it can be in the top-k.  The main pass (MODE 0) starts from this threshold
-// (pass rate ~ R / sampled items, e.g. 2e-4 for 1 M items at stride 8) instead of -inf: the fill phase, most list
+// (pass rate ~ R / sampled items, e.g. 1e-4 for 1 M items at stride 4) instead of -inf: the fill phase, most list
 // maintenance and the cross-CTA threshold exchange disappear, for `1 / stride` extra MMA work.  Both passes issue the
 // identical MMA sequence for a (user tile, item tile) pair, so a score has the same bits in both.
 #include <cuda_bf16.h>
@@ -681,7 +681,7 @@ static int64_t score_pre_stride(int64_t n_full_tiles) {
     if (forced == 1) return 0;
     if (forced > 1) return forced;
     int64_t s = 2;
-    while (s < 16 && n_full_tiles / (2 * s) >= 512) s *= 2;          // keep >= 512 sampled tiles, at most 1/2 .. 1/16 extra work
+    while (s < 16 && n_full_tiles / (2 * s) >= 1024) s *= 2;         // keep >= 1024 sampled tiles, at most 1/2 .. 1/16 extra work
     return s;
 }
 // most tiles any kept segment of an N-row shard can sample (the stride grows with the segment)
@@ -689,8 +689,8 @@ static int64_t score_pre_max_visits(int64_t N) {
     const int64_t nf = N / SC_BN;
     if (score_pre_stride(nf) == 0) return 0;
     int64_t best = 0;
-    for (int64_t s = 2; s <= 16; s *= 2) {                            // segments whose stride is s have < 1024 s tiles (s < 16)
-        const int64_t top = s < 16 ? (nf < 1024 * s ? nf : 1024 * s) : nf;
+    for (int64_t s = 2; s <= 16; s *= 2) {                            // segments whose stride is s have < 2048 s tiles (s < 16)
+        const int64_t top = s < 16 ? (nf < 2048 * s ? nf : 2048 * s) : nf;
         if (cdiv(top, s) > best) best = cdiv(top, s);
     }
     const int64_t f = score_pre_stride(nf);
