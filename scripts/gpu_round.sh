@@ -1,8 +1,5 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_tc.py -q -x -m gpu -k "graphed or sharded" -p no:cacheprovider 2>&1 | tail -3
-timeout 300 python scripts/prof_shard_step.py 8 dhe1m 2>&1 | tail -7
-timeout 300 python bench.py --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('dhe1m', round(d['value']), d['ms_per_step'], 'e2e', round(d['e2e']['value']), d['gpu_launches'])"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:tc_score_topk_kernel -c 2 -o gpurun_out/r01_score_v4 -f python scripts/prof_score_10m.py 10000000 > gpurun_out/ncu_score_v4.log 2>&1; echo rc=$?
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:tc_linear2_kernel -s 4 -c 1 -o gpurun_out/r01_linear2_gelu -f python scripts/prof_linear_gelu.py > gpurun_out/ncu_linear2_gelu.log 2>&1; echo rc=$?
