@@ -177,10 +177,9 @@ class InductiveGeneralRecommender(nn.Module):
         key = (lo, hi, str(self.device))
         t = cache.get(key)
         if t is None:
-            if len(cache) >= 8:
-                cache.clear()
             t = torch.arange(lo, hi, device=self.device, dtype=torch.int64)
-            cache[key] = t
+            if len(cache) < 8:                  # never evict: a captured CUDA graph may hold the address of an entry
+                cache[key] = t
         return t
 
     def full_sort_topk(self, interaction, k: int, n_total_items: Optional[int] = None, history_index=None,
