@@ -51,6 +51,10 @@ class GraphedTopK:
             self.scores, self.ids = self._step()
         self.launches_per_replay = ops.launch_count() - l0
         torch.cuda.synchronize(dev)
+        # the graph holds raw addresses of the per-stream kernel workspaces (ops._workspace) used while it was captured:
+        # keep them alive even if the cache later replaces them with bigger buffers for some other caller of that stream
+        streams = {side.cuda_stream, self._side.cuda_stream}
+        self._keep_alive = [buf for key, buf in ops._ws_cache.items() if key[1] in streams]
 
     def _step(self):
         """One step on the current stream, with the query side (history CSR + user embed: a dozen small kernels that
