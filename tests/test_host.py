@@ -178,6 +178,31 @@ def test_sharded_local_segments():
     assert sr._local_seg((0, 1 << 62)) == (0, 65)
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_local_history_partitions_the_pairs(world):
+    """Host logic of the fused shard path: every rank rewrites the history pairs to LOCAL rows of its
+    [in-vocab slice | OOV slice] table and drops the others; mapping the local columns back to global ids and taking the
+    union over the ranks must give back exactly the original pairs (each once)."""
+    from oov_b200 import ops, sharded
+    g = torch.Generator().manual_seed(world)
+    Q, n_old, n_total = 37, 1000, 2600
+    hu = torch.randint(0, Q, (900,), generator=g)
+    hi = torch.randint(0, n_total, (900,), generator=g)
+    want = sorted(zip(hu.tolist(), hi.tolist()))
+    got = []
+    for r in range(world):
+        (lo0, hi0), (lo1, hi1) = sharded.shard_segments(n_old, n_total, r, world)
+        rp, cols = ops.pairs_to_csr(hu, hi, Q, col_ranges=((lo0, hi0), (lo1, hi1)))
+        n0 = hi0 - lo0
+        for q in range(Q):
+            row = cols[rp[q]:rp[q + 1]].tolist()
+            assert row == sorted(row)                          # ascending per row: the scoring kernel's cursor relies on it
+            for c in row:
+                assert 0 <= c < n0 + (hi1 - lo1)
+                got.append((q, c + lo0 if c < n0 else c - n0 + lo1))
+    assert sorted(got) == want
+
+
 def test_shard_arithmetic_and_packing():
     from oov_b200 import sharded
     for n, world in ((10, 4), (7, 8), (1_000_003, 8), (0, 2)):
