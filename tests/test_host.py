@@ -232,3 +232,24 @@ def test_topk_metrics():
     dcg0 = 1 + 1 / np.log2(5)
     idcg0 = 1 + 1 / np.log2(3)
     assert m["ndcg@4"] == pytest.approx((dcg0 / idcg0 + 0 + (1 / np.log2(3)) / (1 + 1 / np.log2(3) + 1 / np.log2(4))) / 3)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm: oracle port of the reference step on the host cores) prints ONE JSON
+    line with the keys the driver reads; a second rank of a torchrun launch prints nothing and exits 0."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "dhe100k", "--steps", "1", "--warmup", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "full_sort_topk_queries_per_s" and d["unit"] == "queries/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["config"]["workload"] == "dhe100k"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out2 = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=120, cwd=root, env=env)
+    assert out2.returncode == 0 and not [ln for ln in out2.stdout.splitlines() if ln.startswith("{")]
