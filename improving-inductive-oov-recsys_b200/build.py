@@ -34,19 +34,43 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _headers() -> list[str]:
+    return glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(os.path.dirname(PKG_DIR), "include", "*.h"))
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu under csrc/ into one shared library.  Raises on failure."""
+    """Compile every .cu under csrc/ (one object per file, stale ones only, in parallel) and link them into one shared
+    library.  Raises on failure."""
     if not force and not is_stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build liboov_b200.so (no CPU fallback exists)")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
-    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + proc.stdout)
+    obj_dir = os.path.join(PKG_DIR, "build")
+    os.makedirs(obj_dir, exist_ok=True)
+    hdr_t = max([os.path.getmtime(h) for h in _headers()] + [os.path.getmtime(__file__)])
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src: str):
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+            return obj, 0, ""
+        proc = subprocess.run([nvcc] + compile_flags + ["-c", src, "-o", obj], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True)
+        return obj, proc.returncode, proc.stdout
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, sources()))
+    failed = [out for _, rc, out in results if rc != 0]
+    if failed:
+        raise RuntimeError("nvcc failed:\n" + "\n".join(failed))
     if verbose:
-        print(proc.stdout)
+        print("\n".join(out for _, _, out in results if out))
+    link = subprocess.run([nvcc, "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH]
+                          + [o for o, _, _ in results], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if link.returncode != 0:
+        raise RuntimeError("link failed:\n" + link.stdout)
     return LIB_PATH
 
 

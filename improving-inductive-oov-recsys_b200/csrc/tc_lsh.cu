@@ -3,31 +3,39 @@
 // Replaces inductive/torch_hash.py:55-60 (R = X P^T, bit = !(R < 0)) and inductive/lsh_embedder.py:141-179
 // (out = (H W) / H.sum(1)) in ONE kernel: neither R [n, B] fp32 nor H [n, B] ever exist in HBM or shared memory.
 //
-// Exact signs from bf16 tensor cores: x = x0 + x1 + (<= 2^-18 |x|), p likewise (bf16 pieces), and the three products
-// that matter sit side by side along K:
-//     A' = [x0 | x0 | x1]      B' = [p0 | p1 | p0]        (K' = 3 F, F <= 32 -> 96)
-// The dropped terms are bounded by 1.5 * 2^-17 |x||p|; projections closer to zero than 2^-16 |x| max|p| (about 1 per
-// 10 000) are recomputed by the epilogue thread with the fp32 FMA chain of the CUDA-core path (csrc/lsh.cu), so both
-// paths give identical bits, and |R| < tie_eps events are counted like there.
+// Exact signs from fp16 tensor cores.  Only the SIGN of x . p matters, so both operands are rescaled freely: every
+// plane to length 2^8 (p^ = 256 p / |p|), every feature row by a power of two (largest |x_i| -> [2^13, 2^14)), which
+// keeps every fp16 piece in the normal range.  With x = x0 + x1 (+ <= 2^-22 |x|) and p^ = p0 + p1 (+ <= 2^-22 |p^|)
+//     A' = [x0 | x1] in TMEM,   B' row = [p0 | p1],   R' = x0 p0 + x1 p0 + x0 p1      (six K = 16 steps, x0 reused)
+// and  |R' - x . p^| <= 3 * 2^-22 |x||p^| + the tensor core's accumulation error.  A projection closer to zero than
+// 2^-16 |x||p^| (about 7 in 100 000) is NOT trusted: its (row, plane) goes into a shared-memory queue and the worker warps go on.  At
+// the end of the row tile all 512 worker threads re-evaluate the queued projections with the fp32 FMA chain of the
+// CUDA-core path (csrc/lsh.cu: the original planes, f ascending) — so both paths give identical bits and count the same
+// |R| < tie_eps events — and the few signs that really differ are applied to the finished accumulator as rank-one
+// corrections (+-2 W[b, :]).  No warp ever leaves the pipeline for a long recomputation (the round-1 kernel lost 80 % of
+// its time to exactly that: one slow lane held up all sixteen warps of every hand-over).
 //
-// Second GEMM without popcounts or masks: the epilogue writes S' = 2H - 1 (+-1 in fp16: the sign bit of R under a
-// constant) and the bucket table gets one extra column of ones (zero for planes >= B), so
-//     S' [W | 1] = [2 H W - colsum(W) | 2 count - B]   ->   out = (acc + colsum(W)) / (acc_ones + B)
-// with 0 / 0 -> NaN like lsh_embedder.py:158.  W is split into fp16 hi (+ lo for fp32 outputs) pieces.
+// Second GEMM without masks: the epilogue writes S' = 2H - 1 (+-1 in fp16: the sign bit of R under a constant), so
+//     S' W = 2 H W - colsum(W)   ->   out = (acc + colsum(W)) / (sum(S') + B)        [sum(S') + B = 2 count]
+// with 0 / 0 -> NaN like lsh_embedder.py:158.  sum(S') is accumulated by the workers with packed-half adds on the very
+// words they store (exact: |sum| <= 2048).  W is split into fp16 hi (+ lo for fp32 outputs) pieces.
+//
+// Operands: B' (16 KB per 128 planes) is loaded ONCE per CTA when it fits its 8 stages (B <= 1024), the transposed
+// bucket table (16 KB per 128 planes and piece) streams through a 4-stage TMA ring (resident when it fits); otherwise the
+// same stages work as TMA rings.  (Streaming both per row tile would need ~50 B/clk/SM of L2 bandwidth at full speed;
+// the chip delivers ~42.)
 //
 // Per CTA (640 threads), persistent over 128-row tiles of the id list (tiles without OOV ids are plain row copies and
 // skip the GEMMs — every role derives that from the ids with one warp vote):
 //   warps 4-19  workers : fetch the NEXT tile's feature rows into registers; per 128-plane N tile: tcgen05.ld the
 //                         projections (lane = row), min|R| tree against the near-zero threshold, two instructions
-//                         per pair of scores (PRMT + LOP3) to form the fp16 +-1 words, tcgen05.st them back into
-//                         TENSOR MEMORY as the A operand of the second GEMM; after the last projection split the
-//                         prefetched rows into A' (also in TMEM) so the tensor core starts the next tile at once.
-//   warp 0      TMA     : B' tiles (128 planes x 128 K) through a 4-stage ring (one mbarrier per N tile)
-//   warp 2      TMEM alloc, then TMA of the transposed bucket-table tiles (80 rows x 128 planes) through a 3-stage ring
+//                         per pair of scores (PRMT + LOP3) to form the fp16 +-1 words, one HADD2 per word for the
+//                         count, tcgen05.st them back into TENSOR MEMORY as the A operand of the second GEMM.
+//   warp 0      TMA     : B' tiles
+//   warp 2      TMEM alloc, then TMA of the transposed bucket-table tiles
 //   warp 1      MMA 1   : GEMM1 (TS: A' from TMEM, M128 N128 K16 x 6) into one of two TMEM accumulators
-//   warp 3      MMA 2   : GEMM2 (TS: A = S' from TMEM, M128 N80 K16 x 8 per piece), accumulating over all N tiles.
-//                         Two issuing threads: each spends ~100 cycles per mbarrier wait, one thread could not keep up.
-// TMEM columns: 0-255 projections (2 buffers), 256-335 [S' W | S' 1], 336-463 S' (2 buffers), 464-511 A'.
+//   warp 3      MMA 2   : GEMM2 (TS: A = S' from TMEM, M128 N64 K16 x 8 per piece), accumulating over all N tiles.
+// TMEM columns: 0-255 projections (2 buffers), 256-319 S' W, 320-447 S' (2 buffers), 448-479 A'.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -39,16 +47,19 @@ namespace tc {
 
 constexpr int L_BM = 128;                 // rows per tile
 constexpr int L_BN = 128;                 // planes per N tile
-constexpr int L_FMAX = 32;                // features (K' = 3 F = 96: K block 0 full, K block 1 half used)
+constexpr int L_FMAX = 32;                // features (K' = 3 * 32 = 96 fp16)
 constexpr int L_DMAX = 64;
-constexpr int L_WROWS = 80;               // bucket-table tile rows: 64 d + the ones row + padding to a multiple of 16
-constexpr int L_BSTAGES = 4, L_WSTAGES = 3;   // one stage = one N tile of B' (2 K blocks) / one piece of the bucket tile (2 halves)
+constexpr int L_BSTAGES = 8, L_WSTAGES = 4;   // stages of the B' / bucket-table rings (resident when everything fits)
 constexpr int L_WORK_WARP0 = 4, L_WORKERS = 16;
 constexpr int L_THREADS = (L_WORK_WARP0 + L_WORKERS) * 32;     // 640
-constexpr int L_BT_BYTES = 2 * L_BN * 128;                     // 32 KB: both K blocks of one N tile of B'
-constexpr int L_WT_BYTES = 2 * L_WROWS * 128;                  // 20 KB: 80 rows x 128 planes (two 64-plane halves)
-constexpr int L_SMEM = 1024 + L_BSTAGES * L_BT_BYTES + L_WSTAGES * L_WT_BYTES + 4096;
-constexpr float L_NEAR_REL = 1.52587890625e-5f;   // 2^-16 |x| max|p|: projections closer to zero are recomputed in fp32 order
+constexpr int L_BT_BYTES = L_BN * 128;                         // 16 KB: row r = [p0 | p1] of plane r of one N tile
+constexpr int L_WT_BYTES = 2 * L_DMAX * 128;                   // 16 KB: 64 d-rows x 128 planes (two 64-plane K blocks)
+constexpr int L_QCAP = 1024;                                   // queued near-zero projections per row tile
+constexpr int L_TAIL_BYTES = 2 * 4 * L_BM * 4 + 4 * L_BM * 4 + 2 * L_BM * 8 + 4 * L_QCAP * 4 + L_DMAX * 4 + 1024;
+constexpr int L_SMEM = 1024 + L_BSTAGES * L_BT_BYTES + L_WSTAGES * L_WT_BYTES + L_TAIL_BYTES;
+static_assert(L_SMEM <= 232448, "tc_lsh shared memory");
+constexpr float L_PSCALE = 256.f;                 // length of the rescaled planes
+constexpr float L_NEAR_REL = 1.52587890625e-5f * L_PSCALE;   // 2^-16 |p^|: |R' - x.p^| stays far below this times |x|
 
 struct LshParams {
     const float* feat; int64_t n_feat_rows; int F;
@@ -57,40 +68,48 @@ struct LshParams {
     const void* iv_table; int iv_dtype;
     void* out; int out_dtype; int64_t out_stride; int D;
     int wsplit;                                        // 1: fp16 bucket table, 2: hi + lo
+    int res_b, res_w;                                  // operand tiles resident in shared memory (loaded once per CTA)
     float tie_eps;
     uint32_t* bits_out; int words;
     unsigned long long* tie_count;
-    const float* pn_max;                               // largest plane norm (device scalar written by the pack kernel)
+    const float* pn_min;                               // smallest non-zero plane norm (device scalar written by the pack kernel)
     const float* wsum;                                 // [64] column sums of the packed bucket table
+    const __half* Wt; int64_t nb;                      // packed bucket table [wsplit * 64, nb] (rank-one sign corrections)
 };
 
 // ---------------------------------------------------------------- operand packing (once per call)
-// Bp [NT*128, 128] bf16: row b = [p0 | p1 | p0 | 0] (32 columns each; zero for f >= F and b >= B)
-// Wt [wsplit*80, NT*128] fp16: rows s*80 + d = piece s of W[., d]; row 64 of piece 0 = 1 for b < B; zero padding
+// Bp [NT*128, 64] fp16: row b = [p0 | p1] (32 columns each) of p^ = 256 p / |p|
+//                      (zero for f >= F, b >= B and planes without a finite non-zero norm: those are always re-evaluated)
+// Wt [wsplit*64, NT*128] fp16: rows s*64 + d = piece s of W[., d]; zero padding
 __global__ void lsh_pack_kernel(const float* __restrict__ planes, int B, int F, int NT, const void* __restrict__ W, int w_dtype,
-                                int D, int wsplit, __nv_bfloat16* __restrict__ Bp, __half* __restrict__ Wt,
-                                float* __restrict__ pn_max) {
+                                int D, int wsplit, __half* __restrict__ Bp, __half* __restrict__ Wt,
+                                float* __restrict__ pn_min) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nb = (int64_t)NT * L_BN;
     if (t < nb * 32) {
         const int b = (int)(t >> 5), f = (int)(t & 31);
-        float p = (b < B && f < F) ? planes[(size_t)b * F + f] : 0.f;
-        const __nv_bfloat16 p0 = __float2bfloat16_rn(p);
-        const __nv_bfloat16 p1 = __float2bfloat16_rn(p - __bfloat162float(p0));
-        __nv_bfloat16* row = Bp + (size_t)b * 128;
-        row[f] = p0; row[32 + f] = p1; row[64 + f] = p0; row[96 + f] = __float2bfloat16_rn(0.f);
-        float s2 = p * p;                                           // the 32 lanes of a warp hold one plane
-        for (int o = 16; o; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-        if (f == 0 && s2 == s2) atomicMax(reinterpret_cast<unsigned int*>(pn_max), __float_as_uint(sqrtf(s2)));
+        float v = 0.f;
+        if (b < B) {
+            float s2 = 0.f;
+            for (int j = 0; j < F; ++j) { const float pj = planes[(size_t)b * F + j]; s2 = fmaf(pj, pj, s2); }
+            const float nrm = sqrtf(s2);
+            if (nrm > 0.f && nrm < INFINITY) {
+                if (f < F) v = planes[(size_t)b * F + f] / nrm * L_PSCALE;
+                if (f == 0) atomicMin(reinterpret_cast<unsigned int*>(pn_min), __float_as_uint(nrm));
+            }
+        }
+        const __half p0 = __float2half_rn(v);
+        Bp[(size_t)b * 64 + f] = p0;
+        Bp[(size_t)b * 64 + 32 + f] = __float2half_rn(v - __half2float(p0));
     }
-    if (t < nb * L_WROWS) {
+    if (t < nb * L_DMAX) {
         const int d = (int)(t / nb);
         const int64_t b = t - (int64_t)d * nb;
         float w = 0.f;
-        if (b < B) w = d < D ? load_elem(W, w_dtype, b * D + d) : (d == L_DMAX ? 1.f : 0.f);
+        if (b < B && d < D) w = load_elem(W, w_dtype, b * D + d);
         const __half hi = __float2half_rn(w);
         Wt[(size_t)d * nb + b] = hi;
-        if (wsplit == 2) Wt[(size_t)(L_WROWS + d) * nb + b] = __float2half_rn(w - __half2float(hi));
+        if (wsplit == 2) Wt[(size_t)(L_DMAX + d) * nb + b] = __float2half_rn(w - __half2float(hi));
     }
 }
 // wsum[d] = sum over b of the packed pieces of W[b, d], fixed order (one warp per column, fp32 tree over 32 partial sums)
@@ -99,7 +118,7 @@ __global__ void lsh_wsum_kernel(const __half* __restrict__ Wt, int64_t nb, int w
     float s = 0.f;
     for (int64_t b = lane; b < nb; b += 32) {
         float w = __half2float(Wt[(size_t)d * nb + b]);
-        if (wsplit == 2) w += __half2float(Wt[(size_t)(L_WROWS + d) * nb + b]);
+        if (wsplit == 2) w += __half2float(Wt[(size_t)(L_DMAX + d) * nb + b]);
         s += w;
     }
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -122,6 +141,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ void tc_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -131,11 +154,6 @@ __device__ __forceinline__ void tc_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ uint32_t tc_ld_32x1(uint32_t taddr) {
-    uint32_t v;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
-    return v;
-}
 // D[tmem] (+)= A[tmem] * B[smem]: the A operand (16-bit pairs packed along K, lane = row) comes from tensor memory,
 // where the workers put it with tcgen05.st — no shared-memory round trip
 __device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -144,6 +162,12 @@ __device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, 
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
 }
 __device__ __forceinline__ void tc_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
     asm volatile(
@@ -158,47 +182,45 @@ __device__ __forceinline__ void tc_st_32x4(uint32_t taddr, uint32_t a, uint32_t 
 }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// the fp32 FMA chain of csrc/lsh.cu (f ascending, original planes): the value that decides a bit on every path
+__device__ __forceinline__ float exact_projection(const LshParams& p, int64_t fr, int b) {
+    const float* xr = p.feat + fr * p.F;
+    const float* pr = p.planes + (size_t)b * p.F;
+    float a = 0.f;
+    int f = 0;
+    for (; f + 8 <= p.F; f += 8) {
+        float xv[8], pv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { xv[j] = __ldg(xr + f + j); pv[j] = __ldg(pr + f + j); }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a = fmaf(xv[j], pv[j], a);
+    }
+    for (; f < p.F; ++f) a = fmaf(__ldg(xr + f), __ldg(pr + f), a);
+    return a;
+}
+
 // 8 features of one row (thread = (row, slice)), fetched one tile ahead
 struct Gather {
     float x[8];
-    float n2;          // this slice's share of the squared row norm
+    int64_t id, fr;    // list id of the row (INT64_MIN past the end) and its feature row (-1: not hashed)
 };
 
 __device__ __forceinline__ void gather_load(const LshParams& p, int64_t tile, int r, int part, Gather& gth) {
     const int64_t rr = tile * L_BM + r;
-    int64_t fr = -1;
+    int64_t fr = -1, id = INT64_MIN;
     if (rr < p.n) {
-        const int64_t id = p.ids[rr * p.ids_stride];
+        id = p.ids[rr * p.ids_stride];
         if (id >= p.n_old) {
             fr = feature_row(id, p.prime_pad);
             if (fr < 0 || fr >= p.n_feat_rows) fr = -1;               // out-of-range ids hash nothing (caller bug)
         }
     }
-    float s = 0.f;
+    gth.id = id; gth.fr = fr;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int f = part * 8 + j;
         gth.x[j] = (fr >= 0 && f < p.F) ? __ldg(p.feat + fr * p.F + f) : 0.f;
-        s = fmaf(gth.x[j], gth.x[j], s);
     }
-    gth.n2 = s;
-}
-
-// split into two bf16 pieces and write the slice of A' = [x0 | x0 | x1] into this row's TMEM lane:
-// K element k lives in column k / 2, so the 8 features are 4 columns at offset 4 * part of each 16-column segment
-__device__ __forceinline__ void gather_store(uint32_t a_lane, float* sn2, int r, int part, const Gather& gth) {
-    uint32_t c0[4], c1[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float a = gth.x[2 * j], b = gth.x[2 * j + 1];
-        const __nv_bfloat16 a0 = __float2bfloat16_rn(a), b0 = __float2bfloat16_rn(b);
-        c0[j] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(b0) << 16);
-        c1[j] = pack_bf16x2(a - __bfloat162float(a0), b - __bfloat162float(b0));
-    }
-    tc_st_32x4(a_lane + 0 * 16 + part * 4, c0[0], c0[1], c0[2], c0[3]);
-    tc_st_32x4(a_lane + 1 * 16 + part * 4, c0[0], c0[1], c0[2], c0[3]);
-    tc_st_32x4(a_lane + 2 * 16 + part * 4, c1[0], c1[1], c1[2], c1[3]);
-    sn2[part * L_BM + r] = gth.n2;
 }
 
 // in-vocab-only tile: plain gather (bpr.py:111-112), 4 threads per row
@@ -217,12 +239,19 @@ __global__ void __launch_bounds__(L_THREADS, 1)
 tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmW, const LshParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char* sB = smem;                                        // ring of [128 planes x 64] tiles
-    unsigned char* sW = sB + L_BSTAGES * L_BT_BYTES;                 // ring of [80 rows x 64 planes] tiles
+    unsigned char* sB = smem;                                        // stages of [128 planes x 128 B] B' tiles
+    unsigned char* sW = sB + L_BSTAGES * L_BT_BYTES;                 // stages of 2 x [64 d-rows x 128 B] bucket-table tiles
     unsigned char* tail = sW + L_WSTAGES * L_WT_BYTES;
-    float* sn2 = reinterpret_cast<float*>(tail);                     // [4][128] squared-norm shares of the current tile's rows
-    float* swsum = sn2 + 4 * L_BM;                                   // [64] column sums of the bucket table
-    uint64_t* bars = reinterpret_cast<uint64_t*>(swsum + L_DMAX);
+    float* s_mx = reinterpret_cast<float*>(tail);                    // [4][128] largest |x_i| of the NEXT tile's row slices
+    float* s_n2 = s_mx + 4 * L_BM;                                   // [4][128] squared-norm shares of the same
+    float* s_cnt = s_n2 + 4 * L_BM;                                  // [4][128] sum of S' over this tile's column quarters
+    int64_t* s_fr = reinterpret_cast<int64_t*>(s_cnt + 4 * L_BM);    // [2][128] feature row of every tile row (by tile parity)
+    uint32_t* q_ent = reinterpret_cast<uint32_t*>(s_fr + 2 * L_BM);  // [2][QCAP] near-zero projections: row << 24 | plane << 1 | bit
+    uint32_t* f_ent = q_ent + 2 * L_QCAP;                            // [2][QCAP] signs that differ: row << 24 | plane << 1 | exact bit
+    float* swsum = reinterpret_cast<float*>(f_ent + 2 * L_QCAP);     // [64] column sums of the bucket table
+    uint32_t* s_qn = reinterpret_cast<uint32_t*>(swsum + L_DMAX);    // [2] queue lengths, [2] flip-list lengths
+    uint32_t* s_fn = s_qn + 2;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_fn + 2);
     uint64_t* a_full = bars;            uint64_t* a_empty = bars + 1;
     uint64_t* b_full = bars + 2;        uint64_t* b_empty = b_full + L_BSTAGES;
     uint64_t* w_full = b_empty + L_BSTAGES;  uint64_t* w_empty = w_full + L_WSTAGES;
@@ -237,6 +266,9 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
     const int warp = (int)((threadIdx.x >> 5) + L_WORK_WARP0) % (int)(L_THREADS / 32), lane = threadIdx.x & 31;
     const int64_t n_tiles = (p.n + L_BM - 1) / L_BM;
     const int NT = p.NT;
+    const int SB = p.res_b ? NT : L_BSTAGES;                         // stages in use
+    const int NW = NT * p.wsplit;                                    // bucket-table tiles per row tile
+    const int SW = p.res_w ? NW : L_WSTAGES;
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmW); }
     if (warp == 1 && lane == 0) {
@@ -248,6 +280,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             mbar_init(&h_full[a], L_WORKERS); mbar_init(&h_empty[a], 1);
         }
         mbar_init(acc2_full, 1); mbar_init(acc2_empty, L_WORKERS);
+        s_qn[0] = s_qn[1] = s_fn[0] = s_fn[1] = 0u;
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -256,9 +289,9 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t ACC2_COL = 256;                               // 80 fp32 columns: [S' W | S' 1 | padding]
-    constexpr uint32_t H_COL = 336;                                  // 2 x 64 columns: S' [128 x 128] fp16, two per column
-    constexpr uint32_t A_COL = 464;                                  // 48 columns: A' [128 x 96] bf16, two per column
+    constexpr uint32_t ACC2_COL = 256;                               // 64 fp32 columns: S' W
+    constexpr uint32_t H_COL = 320;                                  // 2 x 64 columns: S' [128 x 128] fp16, two per column
+    constexpr uint32_t A_COL = 448;                                  // 32 columns: A' [128 x 64] fp16, two per column
 
     if (warp == 0) {
         // ===================== TMA: B' tiles =====================
@@ -267,13 +300,13 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             if (!tile_has_oov(p, t, lane)) continue;
             if (lane == 0)
                 for (int nt = 0; nt < NT; ++nt) {
-                    mbar_wait(&b_empty[stage], phase ^ 1);
+                    if (!p.res_b) mbar_wait(&b_empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&b_full[stage], L_BT_BYTES);
                     tma_load_2d(sB + stage * L_BT_BYTES, &tmB, &b_full[stage], 0, nt * L_BN);
-                    tma_load_2d(sB + stage * L_BT_BYTES + L_BT_BYTES / 2, &tmB, &b_full[stage], 64, nt * L_BN);
-                    if (++stage == L_BSTAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == SB) { stage = 0; phase ^= 1; }
                 }
             __syncwarp();
+            if (p.res_b) break;                                       // resident: loaded once
         }
     } else if (warp == 2) {
         // ===================== TMA: transposed bucket-table tiles =====================
@@ -283,17 +316,18 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             if (lane == 0)
                 for (int nt = 0; nt < NT; ++nt)
                     for (int pc = 0; pc < p.wsplit; ++pc) {
-                        mbar_wait(&w_empty[stage], phase ^ 1);
+                        if (!p.res_w) mbar_wait(&w_empty[stage], phase ^ 1);
                         mbar_arrive_expect_tx(&w_full[stage], L_WT_BYTES);
-                        tma_load_2d(sW + stage * L_WT_BYTES, &tmW, &w_full[stage], nt * L_BN, pc * L_WROWS);
-                        tma_load_2d(sW + stage * L_WT_BYTES + L_WT_BYTES / 2, &tmW, &w_full[stage], nt * L_BN + 64, pc * L_WROWS);
-                        if (++stage == L_WSTAGES) { stage = 0; phase ^= 1; }
+                        tma_load_2d(sW + stage * L_WT_BYTES, &tmW, &w_full[stage], nt * L_BN, pc * L_DMAX);
+                        tma_load_2d(sW + stage * L_WT_BYTES + L_WT_BYTES / 2, &tmW, &w_full[stage], nt * L_BN + 64, pc * L_DMAX);
+                        if (++stage == SW) { stage = 0; phase ^= 1; }
                     }
             __syncwarp();
+            if (p.res_w) break;
         }
     } else if (warp == 1) {
         // ===================== MMA issuer 1: projections =====================
-        constexpr uint32_t idesc1 = make_idesc_bf16_f32(L_BM, L_BN);
+        constexpr uint32_t idesc1 = make_idesc_bf16_f32(L_BM, L_BN) & ~((7u << 7) | (7u << 10));   // A, B = fp16 (format 0)
         int bs = 0; uint32_t bph = 0;
         int64_t g1 = 0;                    // N tiles issued since kernel start
         int64_t T = 0;                     // row tiles with OOV ids done by this CTA
@@ -304,28 +338,29 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                 for (int nt = 0; nt < NT; ++nt, ++g1) {
                     const int buf = (int)(g1 & 1);
                     mbar_wait(&acc1_empty[buf], (uint32_t)(((g1 >> 1) & 1) ^ 1));
-                    mbar_wait(&b_full[bs], bph);
+                    mbar_wait(&b_full[bs], p.res_b ? 0u : bph);       // resident: phase 0 completed once and for all
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * L_BN);
                     const uint32_t a_tmem = tmem_base + A_COL;
-                    const uint64_t bdesc0 = make_sw128_desc(smem_u32(sB + bs * L_BT_BYTES));
-                    const uint64_t bdesc1 = make_sw128_desc(smem_u32(sB + bs * L_BT_BYTES + L_BT_BYTES / 2));
-#pragma unroll
-                    for (int k = 0; k < 6; ++k)                       // A' from TMEM: K = 16 bf16 = 8 columns; K' = 96 -> 6 steps
-                        tc_mma_f16_ts(d_tmem, a_tmem + (uint32_t)(8 * k), (k < 4 ? bdesc0 + (uint64_t)(2 * k) : bdesc1 + (uint64_t)(2 * (k - 4))),
-                                      idesc1, k ? 1u : 0u);
-                    tc_commit(&b_empty[bs]);
+                    const uint64_t bdesc = make_sw128_desc(smem_u32(sB + bs * L_BT_BYTES));
+                    // K = 16 fp16 = 8 TMEM columns of A' (x0: columns 0-15, x1: 16-31) / 32 B of a B' row (p0: bytes 0-63, p1: 64-127)
+                    tc_mma_f16_ts(tmem_base + (uint32_t)(buf * L_BN), a_tmem + 0, bdesc + 0, idesc1, 0u);    // x0 p0
+                    tc_mma_f16_ts(tmem_base + (uint32_t)(buf * L_BN), a_tmem + 8, bdesc + 2, idesc1, 1u);
+                    tc_mma_f16_ts(tmem_base + (uint32_t)(buf * L_BN), a_tmem + 16, bdesc + 0, idesc1, 1u);   // x1 p0
+                    tc_mma_f16_ts(tmem_base + (uint32_t)(buf * L_BN), a_tmem + 24, bdesc + 2, idesc1, 1u);
+                    tc_mma_f16_ts(tmem_base + (uint32_t)(buf * L_BN), a_tmem + 0, bdesc + 4, idesc1, 1u);    // x0 p1
+                    tc_mma_f16_ts(tmem_base + (uint32_t)(buf * L_BN), a_tmem + 8, bdesc + 6, idesc1, 1u);
+                    if (!p.res_b) tc_commit(&b_empty[bs]);
                     tc_commit(&acc1_full[buf]);
                     if (nt == NT - 1) tc_commit(a_empty);             // A' may be rebuilt for the next row tile
-                    if (++bs == L_BSTAGES) { bs = 0; bph ^= 1; }
+                    if (++bs == SB) { bs = 0; bph ^= 1; }
                 }
             }
             ++T;
             __syncwarp();
         }
     } else if (warp == 3) {
-        // ===================== MMA issuer 2: acc2 += S' [W | 1], S' read from TMEM =====================
-        constexpr uint32_t idesc2 = make_idesc_bf16_f32(L_BM, L_WROWS) & ~((7u << 7) | (7u << 10));   // A, B = fp16 (format 0)
+        // ===================== MMA issuer 2: acc2 += S' W, S' read from TMEM =====================
+        constexpr uint32_t idesc2 = make_idesc_bf16_f32(L_BM, L_DMAX) & ~((7u << 7) | (7u << 10));   // A, B = fp16 (format 0)
         int ws = 0; uint32_t wph = 0;
         int64_t g2 = 0;
         int64_t T = 0;
@@ -338,7 +373,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                     mbar_wait(&h_full[hb], (uint32_t)((g2 >> 1) & 1));
                     if (j == 0) mbar_wait(acc2_empty, (uint32_t)((T & 1) ^ 1));
                     for (int pc = 0; pc < p.wsplit; ++pc) {
-                        mbar_wait(&w_full[ws], wph);
+                        mbar_wait(&w_full[ws], p.res_w ? 0u : wph);
                         tc_fence_after();
                         const uint32_t a_tmem = tmem_base + H_COL + (uint32_t)(hb * 64);
                         const uint64_t bdesc0 = make_sw128_desc(smem_u32(sW + ws * L_WT_BYTES));
@@ -347,8 +382,8 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                         for (int k = 0; k < 8; ++k)                   // K = 16 fp16 = 8 TMEM columns / 32 B of smem
                             tc_mma_f16_ts(d_tmem, a_tmem + (uint32_t)(8 * k), (k < 4 ? bdesc0 + (uint64_t)(2 * k) : bdesc1 + (uint64_t)(2 * (k - 4))),
                                           idesc2, (j | pc | k) ? 1u : 0u);
-                        tc_commit(&w_empty[ws]);
-                        if (++ws == L_WSTAGES) { ws = 0; wph ^= 1; }
+                        if (!p.res_w) tc_commit(&w_empty[ws]);
+                        if (++ws == SW) { ws = 0; wph ^= 1; }
                     }
                     tc_commit(&h_empty[hb]);
                     if (j == NT - 1) tc_commit(acc2_full);
@@ -369,8 +404,60 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         const uint32_t a_lane = lane_base + A_COL;
         unsigned int my_ties = 0;
         int64_t g = 0, T = 0;
-        const float pn_max = *p.pn_max;
+        const float pn_min = __uint_as_float(*reinterpret_cast<const unsigned int*>(p.pn_min));
         const uint32_t SIGNS = 0x80008000u, ONES = 0x3C003C00u;       // fp16 pair: sign bits / (+1, +1)
+        const bool exact_inline = p.bits_out != nullptr;              // the caller wants the multi-hot words: no deferral
+
+        // The row state of the tile being projected (set by stage_tile from the prefetched features)
+        int64_t my_id = INT64_MIN, my_fr = -1;
+        float near = 0.f;
+        bool force = false;
+
+        // Turn the prefetched features of tile `Tn` (its parity selects the s_fr bank) into A' = [x0 | x1] in TMEM and the
+        // row's near-zero threshold.  Called by every worker thread (it holds a worker barrier).
+        auto stage_tile = [&](const Gather& gth, int64_t Tn, bool wait_a_empty) {
+            float mx = 0.f, n2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { mx = fmaxf(mx, fabsf(gth.x[j])); n2 = fmaf(gth.x[j], gth.x[j], n2); }
+            bool bad = false;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bad |= !(fabsf(gth.x[j]) < INFINITY);      // Inf / NaN features: every bit is re-evaluated
+            s_mx[cq * L_BM + row] = bad ? INFINITY : mx;
+            s_n2[cq * L_BM + row] = n2;
+            if (cq == 0) s_fr[(Tn & 1) * L_BM + row] = gth.fr;
+            worker_bar();                                              // also: this tile's queue, counts and s_cnt are complete
+            if (wtid == 0) { s_qn[Tn & 1] = 0u; s_fn[Tn & 1] = 0u; }   // the bank of tile Tn (last used by Tn - 2, long done)
+            const float m4 = fmaxf(fmaxf(s_mx[row], s_mx[L_BM + row]), fmaxf(s_mx[2 * L_BM + row], s_mx[3 * L_BM + row]));
+            const float nn = (s_n2[row] + s_n2[L_BM + row]) + (s_n2[2 * L_BM + row] + s_n2[3 * L_BM + row]);
+            // power-of-two row scale: largest |x_i| -> [2^13, 2^14) (exact; the sign of the projection does not change)
+            const uint32_t e = (__float_as_uint(m4) >> 23) & 0xffu;
+            const float sc = __uint_as_float((e >= 13u ? (e <= 254u ? 267u - e : 1u) : 254u) << 23);
+            // |sc x|: from the squared norm unless that may have under- / overflowed, then from sqrt(F) max|x_i| (looser)
+            const float xn = ((m4 > 1e-15f) & (m4 < 1e15f)) ? sqrtf(nn) * sc : 5.6568542f * m4 * sc;
+            my_id = gth.id; my_fr = gth.fr;
+            force = !(m4 < INFINITY) || !(xn < INFINITY);
+            // |R' - sc x.p^| < L_NEAR_REL |sc x|; |x.p| < tie_eps (the reported ties) lies inside 256 sc tie_eps / |p|
+            near = fmaxf(L_NEAR_REL * xn, 2.f * L_PSCALE * p.tie_eps * sc / pn_min);
+            uint32_t c0[4], c1[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float a = gth.x[2 * j] * sc, b = gth.x[2 * j + 1] * sc;
+                const __half a0 = __float2half_rn(a), b0 = __float2half_rn(b);
+                c0[j] = (uint32_t)__half_as_ushort(a0) | ((uint32_t)__half_as_ushort(b0) << 16);
+                c1[j] = pack_f16x2(a - __half2float(a0), b - __half2float(b0));
+            }
+            if (wait_a_empty) {
+                mbar_wait(a_empty, (uint32_t)((Tn - 1) & 1));          // the previous tile's GEMM1s have read A'
+                tc_fence_after();
+            }
+            // K element k lives in column k / 2: the 8 features are 4 columns at offset 4 * cq of each 16-column piece
+            tc_st_32x4(a_lane + 0 * 16 + cq * 4, c0[0], c0[1], c0[2], c0[3]);
+            tc_st_32x4(a_lane + 1 * 16 + cq * 4, c1[0], c1[1], c1[2], c1[3]);
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+        };
 
         // first tile with OOV ids (in-vocab-only tiles on the way are plain copies)
         int64_t t = blockIdx.x;
@@ -378,88 +465,148 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         Gather gth;
         if (t < n_tiles) {
             gather_load(p, t, row, cq, gth);
-            gather_store(a_lane, sn2, row, cq, gth);                  // a_empty: nothing has read A' yet
-            tc_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a_full);
+            stage_tile(gth, 0, false);                                // a_empty: nothing has read A' yet
         }
         while (t < n_tiles) {
             const int64_t row0 = t * L_BM;
-            worker_bar();                                             // sn2 of this tile is complete
+            const int par = (int)(T & 1);
             // next tile with OOV ids: issue its gather now, it is consumed after this tile's last projection
             int64_t tn = t + gridDim.x;
             while (tn < n_tiles && !tile_has_oov(p, tn, lane)) { copy_iv_tile(p, tn, gr, gpart); tn += gridDim.x; }
-            const float xnorm = sqrtf(sn2[row] + sn2[L_BM + row] + sn2[2 * L_BM + row] + sn2[3 * L_BM + row]);
+            const int64_t cur_id = my_id, cur_fr = my_fr;
+            const bool my_oov = cur_fr >= 0;
+            const float cur_near = near;
+            const bool cur_force = force;
             if (tn < n_tiles) gather_load(p, tn, row, cq, gth);
 
-            int64_t my_fr = -1, my_id = INT64_MIN;
-            if (row0 + row < p.n) {
-                my_id = p.ids[(row0 + row) * p.ids_stride];
-                if (my_id >= p.n_old) {
-                    my_fr = feature_row(my_id, p.prime_pad);
-                    if (my_fr < 0 || my_fr >= p.n_feat_rows) my_fr = -1;
-                }
-            }
-            const bool my_oov = my_fr >= 0;
-            // |tensor-core projection - fp32 projection| stays far below this; anything closer to zero is redone exactly
-            const float near = fmaxf(L_NEAR_REL * xnorm * pn_max, 4.f * p.tie_eps);
+            __half2 cn0 = __float2half2_rn(0.f), cn1 = cn0;           // sum of this thread's S' words (two chains)
+            int padc = 0;                                             // planes >= B among them (forced to +1)
             // ---- per N tile: projections -> signs -> S'
             for (int nt = 0; nt < NT; ++nt, ++g) {
                 const int buf = (int)(g & 1);
-                const uint32_t par = (uint32_t)((g >> 1) & 1);
-                mbar_wait(&acc1_full[buf], par);
+                const uint32_t bpar = (uint32_t)((g >> 1) & 1);
+                mbar_wait(&acc1_full[buf], bpar);
                 tc_fence_after();
                 uint32_t v[32];
-                tc_ld_32x32(lane_base + (uint32_t)(buf * L_BN + cq * 32), v);
+                const uint32_t acc_addr = lane_base + (uint32_t)(buf * L_BN + cq * 32);
+                tc_ld_32x32(acc_addr, v);
                 tc_wait_ld();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc1_empty[buf]);
-                // fast path: S' pair = (+1, +1) with the sign bits of the two projections (2 instructions per pair)
+                // fast path: S' pair = (+1, +1) with the sign bits of the two projections (2 instructions per pair) and the
+                // smallest |R| of every 8-column group (one 3-input min per pair)
                 uint32_t hw[16];
-                float mn = INFINITY;
+                float gm[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     hw[i] = (__byte_perm(v[2 * i], v[2 * i + 1], 0x7030) & SIGNS) ^ ONES;
-                    mn = fminf(mn, fminf(fabsf(__uint_as_float(v[2 * i])), fabsf(__uint_as_float(v[2 * i + 1]))));
+                    gm[i >> 2] = fminf(gm[i >> 2], fminf(fabsf(__uint_as_float(v[2 * i])), fabsf(__uint_as_float(v[2 * i + 1]))));
                 }
+                const float mn = fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3]));
                 const int b0 = nt * L_BN + cq * 32;                   // plane of column 0
-                if ((mn < near || p.bits_out != nullptr) && my_oov) {
-                    // slow path (about 1 chunk in 200, or when the caller wants the multi-hot words): exact bits.
-                    // -0 has the sign bit but is not < 0 (torch_hash.py:57-59), near-zero projections are redone in
-                    // the fp32 FMA order of csrc/lsh.cu
-                    uint32_t word = 0u, nearw = 0u;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float r = __uint_as_float(v[j]);
-                        word |= (r < 0.f ? 0u : 1u) << j;
-                        nearw |= (fabsf(r) < near ? 1u : 0u) << j;
-                    }
+                const bool partial = b0 + 32 > p.B;                   // warp-uniform: the chunk holds planes >= B
+                // (votes: the rare paths read the projections again with warp-collective tcgen05.ld — the values are not kept
+                // in registers past the loop above — so every branch around such a load is warp-uniform)
+                if (partial | exact_inline | __any_sync(0xffffffffu, ((mn < cur_near) | cur_force) & my_oov)) {
                     const uint32_t valid = (b0 + 32 <= p.B) ? 0xffffffffu : ((b0 >= p.B) ? 0u : ((1u << (p.B - b0)) - 1u));
-                    nearw &= valid;
-                    while (nearw) {
-                        const int j = __ffs(nearw) - 1;
-                        nearw &= nearw - 1;
-                        const float* xr = p.feat + my_fr * p.F;
-                        const float* pr = p.planes + (size_t)(b0 + j) * p.F;
-                        float a = 0.f;
-                        for (int f = 0; f < p.F; ++f) a = fmaf(__ldg(xr + f), __ldg(pr + f), a);
-                        word = (word & ~(1u << j)) | ((a < 0.f ? 0u : 1u) << j);
-                        if (fabsf(a) < p.tie_eps) ++my_ties;
-                    }
-                    word &= valid;
-                    if (p.bits_out != nullptr && row0 + row < p.n && nt * 4 + cq < p.words)
-                        p.bits_out[(row0 + row) * p.words + nt * 4 + cq] = word;
+                    uint32_t setw = 0u, clrw = 0u;                    // bits to force to 1 / 0 in the S' words
+                    if (exact_inline | __any_sync(0xffffffffu, cur_force & my_oov)) {
+                        uint32_t nearw = 0u, posw = 0u;               // near-zero projections / sign bit clear (the bit S' carries)
+                        uint32_t word = 0u;                           // !(R < 0)
+                        {
+                            uint32_t u[32];
+                            tc_ld_32x32(acc_addr, u);
+                            tc_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {                    // planes >= B meet zero bucket rows: any sign will do
-                        const uint32_t two = (word >> (2 * i)) & 3u;
-                        hw[i] = ((two & 1u) ? 0x3C00u : 0xBC00u) | ((two & 2u) ? 0x3C000000u : 0xBC000000u);
+                            for (int j = 0; j < 32; ++j) {
+                                nearw |= (fabsf(__uint_as_float(u[j])) >= cur_near ? 0u : 1u) << j;   // NaN counts as near
+                                posw |= ((u[j] >> 31) ^ 1u) << j;
+                                word |= (__uint_as_float(u[j]) < 0.f ? 0u : 1u) << j;
+                            }
+                        }
+                        asm volatile("mov.b32 %0, %0;" : "+r"(posw)); // opaque: keeps ptxas from re-deriving bit j from v[j] through local memory
+                        if (cur_force) nearw = 0xffffffffu;
+                        nearw &= my_oov ? valid : 0u;
+                        if (exact_inline) {
+                            // exact bits now: -0 has the sign bit but is not < 0 (torch_hash.py:57-59), near-zero projections
+                            // are redone in the fp32 FMA order of csrc/lsh.cu
+                            while (nearw) {
+                                const int j = __ffs(nearw) - 1;
+                                nearw &= nearw - 1;
+                                const float a = exact_projection(p, cur_fr, b0 + j);
+                                word = (word & ~(1u << j)) | ((a < 0.f ? 0u : 1u) << j);
+                                if (fabsf(a) < p.tie_eps) ++my_ties;
+                            }
+                            word &= my_oov ? valid : 0u;
+                            if (row0 + row < p.n && nt * 4 + cq < p.words) p.bits_out[(row0 + row) * p.words + nt * 4 + cq] = word;
+                            setw = word; clrw = ~word & valid;
+                        } else {
+                            while (nearw) {                           // a row with Inf / NaN features: every plane is queued
+                                const int j = __ffs(nearw) - 1;
+                                nearw &= nearw - 1;
+                                const uint32_t slot = atomicAdd(&s_qn[par], 1u);
+                                if (slot < (uint32_t)L_QCAP) {
+                                    q_ent[par * L_QCAP + slot] = ((uint32_t)row << 24) | ((uint32_t)(b0 + j) << 1) | ((posw >> j) & 1u);
+                                } else {                              // queue full: settle it here
+                                    const float a = exact_projection(p, cur_fr, b0 + j);
+                                    if (a < 0.f) clrw |= 1u << j; else setw |= 1u << j;
+                                    if (fabsf(a) < p.tie_eps) ++my_ties;
+                                }
+                            }
+                        }
+                    } else {
+                        // the usual case: one projection of one 8-column group is close to zero.  Queue it and go on.
+#pragma unroll
+                        for (int gi = 0; gi < 4; ++gi) {
+                            const uint32_t vg = (valid >> (8 * gi)) & 0xffu;          // warp-uniform
+                            if (vg != 0u && __any_sync(0xffffffffu, (gm[gi] < cur_near) & my_oov)) {
+                                uint32_t nw = 0u, pw = 0u;
+                                {
+                                    uint32_t u[8];
+                                    tc_ld_32x8(acc_addr + (uint32_t)(8 * gi), u);
+                                    tc_wait_ld();
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        nw |= (fabsf(__uint_as_float(u[j])) >= cur_near ? 0u : 1u) << j;
+                                        pw |= ((u[j] >> 31) ^ 1u) << j;
+                                    }
+                                }
+                                nw &= my_oov ? vg : 0u;
+                                while (nw) {
+                                    const int j = __ffs(nw) - 1;
+                                    nw &= nw - 1;
+                                    const uint32_t slot = atomicAdd(&s_qn[par], 1u);
+                                    if (slot < (uint32_t)L_QCAP) {
+                                        q_ent[par * L_QCAP + slot] = ((uint32_t)row << 24) | ((uint32_t)(b0 + 8 * gi + j) << 1) | ((pw >> j) & 1u);
+                                    } else {                          // queue full (degenerate rows): settle it here
+                                        const float a = exact_projection(p, cur_fr, b0 + 8 * gi + j);
+                                        if (a < 0.f) clrw |= 1u << (8 * gi + j); else setw |= 1u << (8 * gi + j);
+                                        if (fabsf(a) < p.tie_eps) ++my_ties;
+                                    }
+                                }
+                            }
+                        }
                     }
-                } else if (p.bits_out != nullptr && row0 + row < p.n && nt * 4 + cq < p.words) {
-                    p.bits_out[(row0 + row) * p.words + nt * 4 + cq] = 0u;
+                    setw |= ~valid;                                   // planes >= B meet zero bucket rows: +1, taken out of the count below
+                    if (setw | clrw) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const uint32_t s2 = (setw >> (2 * i)) & 3u, c2 = (clrw >> (2 * i)) & 3u;
+                            uint32_t w = hw[i];
+                            w &= ~(((s2 & 1u) ? 0x8000u : 0u) | ((s2 & 2u) ? 0x80000000u : 0u));
+                            w |= ((c2 & 1u) ? 0x8000u : 0u) | ((c2 & 2u) ? 0x80000000u : 0u);
+                            hw[i] = w;
+                        }
+                    }
+                    padc += __popc(~valid);
                 }
-                mbar_wait(&h_empty[buf], par ^ 1);                    // GEMM2 of the previous use of this buffer is done
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc1_empty[buf]);         // the projections of this N tile are no longer needed
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    cn0 = __hadd2(cn0, *reinterpret_cast<const __half2*>(&hw[i]));
+                    cn1 = __hadd2(cn1, *reinterpret_cast<const __half2*>(&hw[i + 1]));
+                }
+                mbar_wait(&h_empty[buf], bpar ^ 1);                   // GEMM2 of the previous use of this buffer is done
                 tc_fence_after();
                 tc_st_32x16(lane_base + H_COL + (uint32_t)(buf * 64 + cq * 16), hw);
                 tc_wait_st();
@@ -467,23 +614,31 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&h_full[buf]);
             }
-            // ---- A' of the next tile (its features arrived long ago), so the tensor core can go on while we finish
-            if (tn < n_tiles) {
-                mbar_wait(a_empty, (uint32_t)(T & 1));                // this tile's GEMM1s have read A'
-                tc_fence_after();
-                gather_store(a_lane, sn2, row, cq, gth);
-                tc_wait_st();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(a_full);
+            {
+                const __half2 c = __hadd2(cn0, cn1);
+                s_cnt[cq * L_BM + row] = (__low2float(c) + __high2float(c)) - (float)padc;
             }
-            // ---- final: out = (S' W + colsum W) / (S' 1 + B)   [= 2 H W / 2 count]
+            // ---- A' of the next tile (its features arrived long ago), so the tensor core can go on while we finish
+            if (tn < n_tiles) stage_tile(gth, T + 1, true);
+            else worker_bar();
+            // ---- re-evaluate the queued near-zero projections exactly; keep the signs that differ
+            {
+                const uint32_t nq = min(s_qn[par], (uint32_t)L_QCAP);
+                for (uint32_t e = (uint32_t)wtid; e < nq; e += L_WORKERS * 32) {
+                    const uint32_t ent = q_ent[par * L_QCAP + e];
+                    const int r = (int)(ent >> 24), b = (int)((ent >> 1) & 0x7fffffu);
+                    const float a = exact_projection(p, s_fr[par * L_BM + r], b);
+                    const uint32_t bit = a < 0.f ? 0u : 1u;
+                    if (fabsf(a) < p.tie_eps) ++my_ties;
+                    if (bit != (ent & 1u)) f_ent[par * L_QCAP + atomicAdd(&s_fn[par], 1u)] = (ent & ~1u) | bit;
+                }
+            }
+            worker_bar();                                             // the flip list is complete
+            // ---- final: out = (S' W + colsum W + corrections) / (sum S' + B)   [= 2 H W / 2 count]
             mbar_wait(acc2_full, (uint32_t)(T & 1));
             tc_fence_after();
-            ++T;
             uint32_t a[16];
             tc_ld_32x16(lane_base + ACC2_COL + (uint32_t)(cq * 16), a);
-            const uint32_t ones_acc = tc_ld_32x1(lane_base + ACC2_COL + L_DMAX);
             tc_wait_ld();
             tc_fence_before();
             __syncwarp();
@@ -494,11 +649,27 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                 const size_t osz = p.out_dtype == OOV_F32 ? 4 : 2;
                 char* orow = reinterpret_cast<char*>(p.out) + (size_t)r * p.out_stride * osz;
                 if (my_oov) {
-                    const float den = __uint_as_float(ones_acc) + (float)p.B;          // 2 x count, exact
+                    float num[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) num[i] = __uint_as_float(a[i]) + swsum[d0 + i];
+                    float den = ((s_cnt[row] + s_cnt[L_BM + row]) + (s_cnt[2 * L_BM + row] + s_cnt[3 * L_BM + row])) + (float)p.B;   // 2 x count, exact
+                    const uint32_t nf = s_fn[par];
+                    for (uint32_t e = 0; e < nf; ++e) {
+                        const uint32_t ent = f_ent[par * L_QCAP + e];
+                        if ((int)(ent >> 24) != row) continue;
+                        const int64_t b = (int64_t)((ent >> 1) & 0x7fffffu);
+                        const float sg = (ent & 1u) ? 2.f : -2.f;     // S' goes from -1 to +1 or back
+                        den += sg;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float w = __half2float(p.Wt[(size_t)(d0 + i) * p.nb + b]);
+                            if (p.wsplit == 2) w += __half2float(p.Wt[(size_t)(L_DMAX + d0 + i) * p.nb + b]);
+                            num[i] = fmaf(sg, w, num[i]);
+                        }
+                    }
                     float o[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        o[i] = den == 0.f ? __uint_as_float(0x7FC00000u) : (__uint_as_float(a[i]) + swsum[d0 + i]) / den;
+                    for (int i = 0; i < 16; ++i) o[i] = den == 0.f ? __uint_as_float(0x7FC00000u) : num[i] / den;
                     if (p.out_dtype == OOV_BF16 && d0 + 16 <= p.D && ((reinterpret_cast<uintptr_t>(orow) + d0 * 2) & 15) == 0) {
                         uint32_t pk[8];
 #pragma unroll
@@ -511,12 +682,13 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                         for (int i = 0; i < 16; ++i)
                             if (d0 + i < p.D) store_elem(p.out, p.out_dtype, r * p.out_stride + d0 + i, o[i]);
                     }
-                } else if (my_id != INT64_MIN && my_id >= 0 && my_id < p.n_old && p.iv_table != nullptr) {
+                } else if (cur_id != INT64_MIN && cur_id >= 0 && cur_id < p.n_old && p.iv_table != nullptr) {
                     for (int i = 0; i < 16; ++i)                      // in-vocab gather (bpr.py:111-112)
                         if (d0 + i < p.D)
-                            store_elem(p.out, p.out_dtype, r * p.out_stride + d0 + i, load_elem(p.iv_table, p.iv_dtype, my_id * (int64_t)p.D + d0 + i));
+                            store_elem(p.out, p.out_dtype, r * p.out_stride + d0 + i, load_elem(p.iv_table, p.iv_dtype, cur_id * (int64_t)p.D + d0 + i));
                 }
             }
+            ++T;
             t = tn;
         }
         if (p.tie_count != nullptr) {
@@ -534,10 +706,10 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
 }
 
 // ---------------------------------------------------------------- host
-bool lsh_tc_supported(int F, int B, int D) { return F >= 1 && F <= L_FMAX && D >= 1 && D <= L_DMAX && B >= 1; }
+bool lsh_tc_supported(int F, int B, int D) { return F >= 1 && F <= L_FMAX && D >= 1 && D <= L_DMAX && B >= 1 && B <= (1 << 22); }
 
-static size_t lsh_bp_bytes(int B) { return align_up((size_t)cdiv(B, L_BN) * L_BN * 128 * 2, 1024); }
-static size_t lsh_wt_bytes(int B) { return align_up((size_t)2 * L_WROWS * cdiv(B, L_BN) * L_BN * 2, 1024); }
+static size_t lsh_bp_bytes(int B) { return align_up((size_t)cdiv(B, L_BN) * L_BN * 64 * 2, 1024); }
+static size_t lsh_wt_bytes(int B) { return align_up((size_t)2 * L_DMAX * cdiv(B, L_BN) * L_BN * 2, 1024); }
 size_t lsh_tc_workspace(int B) { return lsh_bp_bytes(B) + lsh_wt_bytes(B) + 512 + 1024; }
 
 int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* planes, int B, const void* W, int w_dtype,
@@ -546,12 +718,12 @@ int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* plane
     OOV_REQUIRE(workspace && workspace_bytes >= lsh_tc_workspace(B), OOV_ERR_WORKSPACE, "oov_lsh_embed (tcgen05): workspace %zu < %zu",
                 workspace_bytes, lsh_tc_workspace(B));
     char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
-    __nv_bfloat16* Bp = reinterpret_cast<__nv_bfloat16*>(ws);
+    __half* Bp = reinterpret_cast<__half*>(ws);
     __half* Wt = reinterpret_cast<__half*>(ws + lsh_bp_bytes(B));
-    float* pn_max = reinterpret_cast<float*>(ws + lsh_bp_bytes(B) + lsh_wt_bytes(B));
-    float* wsum = pn_max + 16;
-    cudaError_t ce = cudaMemsetAsync(pn_max, 0, 4, st);
-    OOV_REQUIRE(ce == cudaSuccess, OOV_ERR_CUDA, "cudaMemsetAsync(pn_max): %s", cudaGetErrorString(ce));
+    float* pn_min = reinterpret_cast<float*>(ws + lsh_bp_bytes(B) + lsh_wt_bytes(B));
+    float* wsum = pn_min + 16;
+    cudaError_t ce = cudaMemsetAsync(pn_min, 0x7f, 4, st);           // 0x7f7f7f7f = 3.4e38: "no plane seen"
+    OOV_REQUIRE(ce == cudaSuccess, OOV_ERR_CUDA, "cudaMemsetAsync(pn_min): %s", cudaGetErrorString(ce));
     const int NT = (int)cdiv(B, L_BN);
     const int64_t nb = (int64_t)NT * L_BN;
     LshParams p{};
@@ -560,24 +732,24 @@ int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* plane
     p.iv_table = rows->iv_table; p.iv_dtype = rows->iv_dtype; p.out = rows->out; p.out_dtype = rows->out_dtype;
     p.out_stride = rows->out_stride; p.D = rows->D;
     p.wsplit = rows->out_dtype == OOV_F32 ? 2 : 1;   // fp16 hi (+ lo) pieces of the fp32 bucket table: 2^-12 (2^-23) relative
-    p.tie_eps = tie_eps; p.bits_out = bits_out; p.words = (B + 31) / 32; p.tie_count = tie_count; p.pn_max = pn_max; p.wsum = wsum;
+    p.res_b = NT <= L_BSTAGES ? 1 : 0;
+    p.res_w = NT * p.wsplit <= L_WSTAGES ? 1 : 0;
+    p.tie_eps = tie_eps; p.bits_out = bits_out; p.words = (B + 31) / 32; p.tie_count = tie_count; p.pn_min = pn_min; p.wsum = wsum;
+    p.Wt = Wt; p.nb = nb;
 
-    lsh_pack_kernel<<<(unsigned)cdiv(nb * L_WROWS, 256), 256, 0, st>>>(planes, B, F, NT, W, w_dtype, rows->D, p.wsplit, Bp, Wt, pn_max);
+    const int64_t pack_threads = nb * L_DMAX;                        // >= nb * 32
+    lsh_pack_kernel<<<(unsigned)cdiv(pack_threads, 256), 256, 0, st>>>(planes, B, F, NT, W, w_dtype, rows->D, p.wsplit, Bp, Wt, pn_min);
     OOV_LAUNCH_CHECK("lsh_pack_kernel");
     lsh_wsum_kernel<<<L_DMAX, 32, 0, st>>>(Wt, nb, p.wsplit, wsum);
     OOV_LAUNCH_CHECK("lsh_wsum_kernel");
 
     CUtensorMap tmB, tmW;
-    int rc = make_tmap_bf16_2d(&tmB, Bp, 128, (uint64_t)nb, 128 * 2, L_BN);
+    int rc = make_tmap_bf16_2d(&tmB, Bp, 64, (uint64_t)nb, 64 * 2, L_BN);                                     // fp16: same 2-byte boxes
     if (rc) return rc;
-    rc = make_tmap_bf16_2d(&tmW, Wt, (uint64_t)nb, (uint64_t)(p.wsplit * L_WROWS), (uint64_t)nb * 2, L_WROWS);   // fp16: same 2-byte boxes
+    rc = make_tmap_bf16_2d(&tmW, Wt, (uint64_t)nb, (uint64_t)(p.wsplit * L_DMAX), (uint64_t)nb * 2, L_DMAX);
     if (rc) return rc;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tc_lsh_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM);
-        OOV_REQUIRE(e == cudaSuccess, OOV_ERR_CUDA, "cudaFuncSetAttribute(tc_lsh_embed_kernel): %s", cudaGetErrorString(e));
-        attr_done = true;
-    }
+    cudaError_t e = cudaFuncSetAttribute(tc_lsh_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM);
+    OOV_REQUIRE(e == cudaSuccess, OOV_ERR_CUDA, "cudaFuncSetAttribute(tc_lsh_embed_kernel): %s", cudaGetErrorString(e));
     const int64_t n_tiles = cdiv(rows->n, L_BM);
     const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
     tc_lsh_embed_kernel<<<grid, L_THREADS, L_SMEM, st>>>(tmB, tmW, p);

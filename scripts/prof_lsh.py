@@ -25,5 +25,5 @@ for name, path in paths:
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
     dense = 2.0 * n * B * (F + D)
-    issued = 2.0 * n * 1024 * (192 + 128)
+    issued = 2.0 * n * 1024 * (64 + 64)
     print(f"lsh_embed {name} n={n}: {ms:.3f} ms  {n / ms / 1e3:.2f} M ids/s  dense-equivalent {dense / ms / 1e9:.1f} TFLOP/s  issued-MMA {issued / ms / 1e9:.1f} TFLOP/s")

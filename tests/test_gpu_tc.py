@@ -367,3 +367,44 @@ def test_tc_lsh_matches_simt_bits_and_embeddings(n, F, B, D, dtype):
     both = ~np.isnan(want)
     pu.assert_close(got[both], want[both], rtol=1e-4 if dtype == torch.float32 else 2 ** -6, atol=1e-5 if dtype == torch.float32 else 1e-3,
                     what="tc lsh vs oracle")
+
+
+@pytest.mark.parametrize("n,F,B,D,dtype", [(40_000, 32, 1000, 64, torch.float32), (40_000, 32, 1000, 64, torch.bfloat16),
+                                           (9_000, 32, 1500, 64, torch.bfloat16), (5_000, 20, 2100, 48, torch.float32),
+                                           (3_000, 7, 37, 16, torch.float32)])
+def test_tc_lsh_deferred_sign_fix_matches_simt(n, F, B, D, dtype):
+    """The product path of the tensor-core LSH (no multi-hot words requested): near-zero projections are queued, settled
+    with the fp32 FMA chain at the end of the row tile and applied as rank-one corrections.  One wrong sign moves an
+    fp32 output by ~2 |W| / count (1e-3 relative and more), so rtol 1e-5 against the CUDA-core path pins every bit;
+    the reported tie counts must agree too.  Covers resident operands (B <= 1024, bf16), the bucket-table ring (fp32
+    output: two pieces), both rings (B > 1024), unscaled features and degenerate rows (all-zero, NaN, Inf, tiny)."""
+    from oov_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(7 * n + F + B + D)
+    n_old = n // 4
+    feat = torch.randn(n, F, generator=g)
+    feat[n_old:n_old + n // 8] *= 1e4                                   # unnormalised rows ('none' normalisation)
+    feat[n_old + n // 8:n_old + n // 4] *= 1e-9
+    feat[n_old + 5] = 0.0                                              # every projection is an exact tie
+    feat[n_old + 6, 1] = float("nan")
+    feat[n_old + 7, 0] = float("inf")
+    feat[n_old + 8] = 1e-30
+    feat = feat.to(DEV)
+    planes = torch.randn(B, F, generator=g)
+    planes[min(3, B - 1)] *= 1e-3                                       # a short plane widens the tie band
+    planes = planes.to(DEV)
+    W = (torch.randn(B, D, generator=g) * 0.1).to(DEV)
+    table = (torch.randn(n_old, D, generator=g) * 0.1).to(DEV)
+    ids = torch.randperm(n, generator=g).to(DEV)
+    tc_t = torch.zeros(1, dtype=torch.int64, device=DEV)
+    tc_s = torch.zeros(1, dtype=torch.int64, device=DEV)
+    o_tc = ops.lsh_embed(feat, planes, W, ids, out_dtype=dtype, n_old=n_old, iv_table=table, tie_count=tc_t, path=ops.PATH_TCGEN05)
+    o_si = ops.lsh_embed(feat, planes, W, ids, out_dtype=dtype, n_old=n_old, iv_table=table, tie_count=tc_s, path=ops.PATH_SIMT_FP32)
+    torch.cuda.synchronize()
+    assert int(tc_t.item()) == int(tc_s.item()) and int(tc_t.item()) >= B      # the all-zero row alone gives B ties
+    a, b = o_tc.float(), o_si.float()
+    assert torch.equal(torch.isnan(a), torch.isnan(b))
+    ok = ~torch.isnan(a)
+    tol = dict(rtol=1e-5, atol=2e-7) if dtype == torch.float32 else dict(rtol=2 ** -7, atol=1e-5)
+    assert torch.allclose(a[ok], b[ok], **tol), (a - b).abs().nan_to_num().max().item()
+    oov = ids >= n_old
+    assert torch.equal(o_tc[~oov], o_si[~oov])
