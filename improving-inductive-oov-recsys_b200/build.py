@@ -50,6 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(obj_dir, exist_ok=True)
     hdr_t = max([os.path.getmtime(h) for h in _headers()] + [os.path.getmtime(__file__)])
     compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    compile_flags += os.environ.get("OOV_NVCC_EXTRA", "").split()       # e.g. -DOOV_LSH_TRACE for scripts/trace_lsh.py
 
     def compile_one(src: str):
         obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")

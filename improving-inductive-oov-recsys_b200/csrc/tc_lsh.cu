@@ -39,6 +39,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -75,7 +77,18 @@ struct LshParams {
     const float* pn_min;                               // smallest non-zero plane norm (device scalar written by the pack kernel)
     const float* wsum;                                 // [64] column sums of the packed bucket table
     const __half* Wt; int64_t nb;                      // packed bucket table [wsplit * 64, nb] (rank-one sign corrections)
+    unsigned long long* trace;                         // profiling only (OOV_LSH_TRACE_PTR): [4 roles][4096] event << 56 | clock of CTA 0
 };
+// one timestamp of CTA 0 (roles: 0 MMA1, 1 MMA2, 2 worker warp 0, 3 worker warp 15); a no-op unless a trace buffer is set
+#ifdef OOV_LSH_TRACE
+#define LTRACE(role, ev)                                                                                         \
+    do {                                                                                                         \
+        if (p.trace != nullptr && blockIdx.x == 0 && trace_n < 4096)                                              \
+            p.trace[(role) * 4096 + trace_n++] = ((unsigned long long)(ev) << 56) | (unsigned long long)clock64(); \
+    } while (0)
+#else
+#define LTRACE(role, ev) do { (void)trace_n; } while (0)
+#endif
 
 // ---------------------------------------------------------------- operand packing (once per call)
 // Bp [NT*128, 64] fp16: row b = [p0 | p1] (32 columns each) of p^ = 256 p / |p|
@@ -293,19 +306,26 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
     constexpr uint32_t H_COL = 320;                                  // 2 x 64 columns: S' [128 x 128] fp16, two per column
     constexpr uint32_t A_COL = 448;                                  // 32 columns: A' [128 x 64] fp16, two per column
 
+    // The single-thread roles run with ALL 32 lanes of their warp in uniform control flow and only predicate the TMA / MMA /
+    // commit instructions on one elected lane.  Under a divergent `if (lane == 0)` ptxas cannot keep descriptors and
+    // addresses in uniform registers and wraps every UTCHMMA / UTMALDG in a vote loop (ELECT + 3 R2UR.BROADCAST +
+    // BRA.U.ANY, ~14 dependent instructions): 125-200 cycles per MMA next to four busy worker warps on the same
+    // scheduler, which left the tensor pipe idle 80 % of the time (trace: scripts/trace_lsh.py).
+    const bool leader = elect_one();
     if (warp == 0) {
         // ===================== TMA: B' tiles =====================
         int stage = 0; uint32_t phase = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             if (!tile_has_oov(p, t, lane)) continue;
-            if (lane == 0)
-                for (int nt = 0; nt < NT; ++nt) {
-                    if (!p.res_b) mbar_wait(&b_empty[stage], phase ^ 1);
+            for (int nt = 0; nt < NT; ++nt) {
+                if (!p.res_b) mbar_wait_spin(&b_empty[stage], phase ^ 1);
+                if (leader) {
                     mbar_arrive_expect_tx(&b_full[stage], L_BT_BYTES);
                     tma_load_2d(sB + stage * L_BT_BYTES, &tmB, &b_full[stage], 0, nt * L_BN);
-                    if (++stage == SB) { stage = 0; phase ^= 1; }
                 }
-            __syncwarp();
+                __syncwarp();
+                if (++stage == SB) { stage = 0; phase ^= 1; }
+            }
             if (p.res_b) break;                                       // resident: loaded once
         }
     } else if (warp == 2) {
@@ -313,16 +333,17 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         int stage = 0; uint32_t phase = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             if (!tile_has_oov(p, t, lane)) continue;
-            if (lane == 0)
-                for (int nt = 0; nt < NT; ++nt)
-                    for (int pc = 0; pc < p.wsplit; ++pc) {
-                        if (!p.res_w) mbar_wait(&w_empty[stage], phase ^ 1);
+            for (int nt = 0; nt < NT; ++nt)
+                for (int pc = 0; pc < p.wsplit; ++pc) {
+                    if (!p.res_w) mbar_wait_spin(&w_empty[stage], phase ^ 1);
+                    if (leader) {
                         mbar_arrive_expect_tx(&w_full[stage], L_WT_BYTES);
                         tma_load_2d(sW + stage * L_WT_BYTES, &tmW, &w_full[stage], nt * L_BN, pc * L_DMAX);
                         tma_load_2d(sW + stage * L_WT_BYTES + L_WT_BYTES / 2, &tmW, &w_full[stage], nt * L_BN + 64, pc * L_DMAX);
-                        if (++stage == SW) { stage = 0; phase ^= 1; }
                     }
-            __syncwarp();
+                    __syncwarp();
+                    if (++stage == SW) { stage = 0; phase ^= 1; }
+                }
             if (p.res_w) break;
         }
     } else if (warp == 1) {
@@ -331,32 +352,38 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         int bs = 0; uint32_t bph = 0;
         int64_t g1 = 0;                    // N tiles issued since kernel start
         int64_t T = 0;                     // row tiles with OOV ids done by this CTA
+        int trace_n = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             if (!tile_has_oov(p, t, lane)) continue;
-            if (lane == 0) {
-                mbar_wait(a_full, (uint32_t)(T & 1));
-                for (int nt = 0; nt < NT; ++nt, ++g1) {
-                    const int buf = (int)(g1 & 1);
-                    mbar_wait(&acc1_empty[buf], (uint32_t)(((g1 >> 1) & 1) ^ 1));
-                    mbar_wait(&b_full[bs], p.res_b ? 0u : bph);       // resident: phase 0 completed once and for all
-                    tc_fence_after();
-                    const uint32_t a_tmem = tmem_base + A_COL;
-                    const uint64_t bdesc = make_sw128_desc(smem_u32(sB + bs * L_BT_BYTES));
+            if (leader) LTRACE(0, 0);
+            mbar_wait_spin(a_full, (uint32_t)(T & 1));
+            for (int nt = 0; nt < NT; ++nt, ++g1) {
+                const int buf = (int)(g1 & 1);
+                if (leader) LTRACE(0, 1);
+                mbar_wait_spin(&acc1_empty[buf], (uint32_t)(((g1 >> 1) & 1) ^ 1));
+                mbar_wait_spin(&b_full[bs], p.res_b ? 0u : bph);           // resident: phase 0 completed once and for all
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * L_BN);
+                const uint32_t a_tmem = tmem_base + A_COL;
+                const uint64_t bdesc = make_sw128_desc(smem_u32(sB + bs * L_BT_BYTES));
+                if (leader) {
+                    LTRACE(0, 2);
                     // K = 16 fp16 = 8 TMEM columns of A' (x0: columns 0-15, x1: 16-31) / 32 B of a B' row (p0: bytes 0-63, p1: 64-127)
-                    tc_mma_f16_ts(tmem_base + (uint32_t)(buf * L_BN), a_tmem + 0, bdesc + 0, idesc1, 0u);    // x0 p0
-                    tc_mma_f16_ts(tmem_base + (uint32_t)(buf * L_BN), a_tmem + 8, bdesc + 2, idesc1, 1u);
-                    tc_mma_f16_ts(tmem_base + (uint32_t)(buf * L_BN), a_tmem + 16, bdesc + 0, idesc1, 1u);   // x1 p0
-                    tc_mma_f16_ts(tmem_base + (uint32_t)(buf * L_BN), a_tmem + 24, bdesc + 2, idesc1, 1u);
-                    tc_mma_f16_ts(tmem_base + (uint32_t)(buf * L_BN), a_tmem + 0, bdesc + 4, idesc1, 1u);    // x0 p1
-                    tc_mma_f16_ts(tmem_base + (uint32_t)(buf * L_BN), a_tmem + 8, bdesc + 6, idesc1, 1u);
+                    tc_mma_f16_ts(d_tmem, a_tmem + 0, bdesc + 0, idesc1, 0u);    // x0 p0
+                    tc_mma_f16_ts(d_tmem, a_tmem + 8, bdesc + 2, idesc1, 1u);
+                    tc_mma_f16_ts(d_tmem, a_tmem + 16, bdesc + 0, idesc1, 1u);   // x1 p0
+                    tc_mma_f16_ts(d_tmem, a_tmem + 24, bdesc + 2, idesc1, 1u);
+                    tc_mma_f16_ts(d_tmem, a_tmem + 0, bdesc + 4, idesc1, 1u);    // x0 p1
+                    tc_mma_f16_ts(d_tmem, a_tmem + 8, bdesc + 6, idesc1, 1u);
                     if (!p.res_b) tc_commit(&b_empty[bs]);
                     tc_commit(&acc1_full[buf]);
                     if (nt == NT - 1) tc_commit(a_empty);             // A' may be rebuilt for the next row tile
-                    if (++bs == SB) { bs = 0; bph ^= 1; }
+                    LTRACE(0, 3);
                 }
+                __syncwarp();
+                if (++bs == SB) { bs = 0; bph ^= 1; }
             }
             ++T;
-            __syncwarp();
         }
     } else if (warp == 3) {
         // ===================== MMA issuer 2: acc2 += S' W, S' read from TMEM =====================
@@ -364,33 +391,40 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         int ws = 0; uint32_t wph = 0;
         int64_t g2 = 0;
         int64_t T = 0;
+        int trace_n = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             if (!tile_has_oov(p, t, lane)) continue;
-            if (lane == 0) {
-                const uint32_t d_tmem = tmem_base + ACC2_COL;
-                for (int j = 0; j < NT; ++j, ++g2) {
-                    const int hb = (int)(g2 & 1);
-                    mbar_wait(&h_full[hb], (uint32_t)((g2 >> 1) & 1));
-                    if (j == 0) mbar_wait(acc2_empty, (uint32_t)((T & 1) ^ 1));
-                    for (int pc = 0; pc < p.wsplit; ++pc) {
-                        mbar_wait(&w_full[ws], p.res_w ? 0u : wph);
-                        tc_fence_after();
-                        const uint32_t a_tmem = tmem_base + H_COL + (uint32_t)(hb * 64);
-                        const uint64_t bdesc0 = make_sw128_desc(smem_u32(sW + ws * L_WT_BYTES));
-                        const uint64_t bdesc1 = make_sw128_desc(smem_u32(sW + ws * L_WT_BYTES + L_WT_BYTES / 2));
+            const uint32_t d_tmem = tmem_base + ACC2_COL;
+            for (int j = 0; j < NT; ++j, ++g2) {
+                const int hb = (int)(g2 & 1);
+                if (leader) LTRACE(1, 4);
+                mbar_wait_spin(&h_full[hb], (uint32_t)((g2 >> 1) & 1));
+                if (j == 0) mbar_wait_spin(acc2_empty, (uint32_t)((T & 1) ^ 1));
+                if (leader) LTRACE(1, 5);
+                for (int pc = 0; pc < p.wsplit; ++pc) {
+                    mbar_wait_spin(&w_full[ws], p.res_w ? 0u : wph);
+                    tc_fence_after();
+                    const uint32_t a_tmem = tmem_base + H_COL + (uint32_t)(hb * 64);
+                    const uint64_t bdesc0 = make_sw128_desc(smem_u32(sW + ws * L_WT_BYTES));
+                    const uint64_t bdesc1 = make_sw128_desc(smem_u32(sW + ws * L_WT_BYTES + L_WT_BYTES / 2));
+                    if (leader) {
 #pragma unroll
                         for (int k = 0; k < 8; ++k)                   // K = 16 fp16 = 8 TMEM columns / 32 B of smem
                             tc_mma_f16_ts(d_tmem, a_tmem + (uint32_t)(8 * k), (k < 4 ? bdesc0 + (uint64_t)(2 * k) : bdesc1 + (uint64_t)(2 * (k - 4))),
                                           idesc2, (j | pc | k) ? 1u : 0u);
                         if (!p.res_w) tc_commit(&w_empty[ws]);
-                        if (++ws == SW) { ws = 0; wph ^= 1; }
                     }
+                    __syncwarp();
+                    if (++ws == SW) { ws = 0; wph ^= 1; }
+                }
+                if (leader) {
                     tc_commit(&h_empty[hb]);
                     if (j == NT - 1) tc_commit(acc2_full);
+                    LTRACE(1, 6);
                 }
+                __syncwarp();
             }
             ++T;
-            __syncwarp();
         }
     } else {
         // ===================== workers =====================
@@ -404,8 +438,20 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         const uint32_t a_lane = lane_base + A_COL;
         unsigned int my_ties = 0;
         int64_t g = 0, T = 0;
+        int trace_n = 0;
+        const int trole = (lane == 0 && wk == 0) ? 2 : ((lane == 0 && wk == L_WORKERS - 1) ? 3 : -1);
+#ifdef OOV_LSH_TRACE
+#define WTRACE(ev) do { if (trole >= 0) LTRACE(trole, ev); } while (0)
+#else
+#define WTRACE(ev) do { (void)trole; } while (0)
+#endif
         const float pn_min = __uint_as_float(*reinterpret_cast<const unsigned int*>(p.pn_min));
-        const uint32_t SIGNS = 0x80008000u, ONES = 0x3C003C00u;       // fp16 pair: sign bits / (+1, +1)
+        // fp16 pair: sign bits / (+1, +1).  Kept in registers (opaque to the compiler) so that (x & SIGNS) ^ ONES is ONE
+        // three-register LOP3 instead of two with an immediate each: the alu pipe (PRMT / LOP3 / FMNMX, one warp
+        // instruction per two cycles per scheduler) is what bounds the workers.
+        uint32_t SIGNS, ONES;
+        asm volatile("mov.b32 %0, 0x80008000;" : "=r"(SIGNS));
+        asm volatile("mov.b32 %0, 0x3C003C00;" : "=r"(ONES));
         const bool exact_inline = p.bits_out != nullptr;              // the caller wants the multi-hot words: no deferral
 
         // The row state of the tile being projected (set by stage_tile from the prefetched features)
@@ -485,19 +531,22 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             for (int nt = 0; nt < NT; ++nt, ++g) {
                 const int buf = (int)(g & 1);
                 const uint32_t bpar = (uint32_t)((g >> 1) & 1);
+                WTRACE(7);
                 mbar_wait(&acc1_full[buf], bpar);
                 tc_fence_after();
+                WTRACE(8);
                 uint32_t v[32];
                 const uint32_t acc_addr = lane_base + (uint32_t)(buf * L_BN + cq * 32);
                 tc_ld_32x32(acc_addr, v);
                 tc_wait_ld();
+                WTRACE(9);
                 // fast path: S' pair = (+1, +1) with the sign bits of the two projections (2 instructions per pair) and the
                 // smallest |R| of every 8-column group (one 3-input min per pair)
                 uint32_t hw[16];
                 float gm[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    hw[i] = (__byte_perm(v[2 * i], v[2 * i + 1], 0x7030) & SIGNS) ^ ONES;
+                    asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(hw[i]) : "r"(__byte_perm(v[2 * i], v[2 * i + 1], 0x7030)), "r"(SIGNS), "r"(ONES));
                     gm[i >> 2] = fminf(gm[i >> 2], fminf(fabsf(__uint_as_float(v[2 * i])), fabsf(__uint_as_float(v[2 * i + 1]))));
                 }
                 const float mn = fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3]));
@@ -606,13 +655,16 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                     cn0 = __hadd2(cn0, *reinterpret_cast<const __half2*>(&hw[i]));
                     cn1 = __hadd2(cn1, *reinterpret_cast<const __half2*>(&hw[i + 1]));
                 }
+                WTRACE(10);
                 mbar_wait(&h_empty[buf], bpar ^ 1);                   // GEMM2 of the previous use of this buffer is done
                 tc_fence_after();
+                WTRACE(11);
                 tc_st_32x16(lane_base + H_COL + (uint32_t)(buf * 64 + cq * 16), hw);
                 tc_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&h_full[buf]);
+                WTRACE(12);
             }
             {
                 const __half2 c = __hadd2(cn0, cn1);
@@ -621,6 +673,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             // ---- A' of the next tile (its features arrived long ago), so the tensor core can go on while we finish
             if (tn < n_tiles) stage_tile(gth, T + 1, true);
             else worker_bar();
+            WTRACE(13);
             // ---- re-evaluate the queued near-zero projections exactly; keep the signs that differ
             {
                 const uint32_t nq = min(s_qn[par], (uint32_t)L_QCAP);
@@ -633,10 +686,12 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                     if (bit != (ent & 1u)) f_ent[par * L_QCAP + atomicAdd(&s_fn[par], 1u)] = (ent & ~1u) | bit;
                 }
             }
+            WTRACE(14);
             worker_bar();                                             // the flip list is complete
             // ---- final: out = (S' W + colsum W + corrections) / (sum S' + B)   [= 2 H W / 2 count]
             mbar_wait(acc2_full, (uint32_t)(T & 1));
             tc_fence_after();
+            WTRACE(15);
             uint32_t a[16];
             tc_ld_32x16(lane_base + ACC2_COL + (uint32_t)(cq * 16), a);
             tc_wait_ld();
@@ -668,8 +723,9 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                         }
                     }
                     float o[16];
+                    const float rden = den == 0.f ? __uint_as_float(0x7FC00000u) : __frcp_rn(den);   // 0 / 0 -> NaN (lsh_embedder.py:158)
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) o[i] = den == 0.f ? __uint_as_float(0x7FC00000u) : num[i] / den;
+                    for (int i = 0; i < 16; ++i) o[i] = num[i] * rden;
                     if (p.out_dtype == OOV_BF16 && d0 + 16 <= p.D && ((reinterpret_cast<uintptr_t>(orow) + d0 * 2) & 15) == 0) {
                         uint32_t pk[8];
 #pragma unroll
@@ -688,6 +744,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                             store_elem(p.out, p.out_dtype, r * p.out_stride + d0 + i, load_elem(p.iv_table, p.iv_dtype, cur_id * (int64_t)p.D + d0 + i));
                 }
             }
+            WTRACE(16);
             ++T;
             t = tn;
         }
@@ -736,6 +793,9 @@ int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* plane
     p.res_w = NT * p.wsplit <= L_WSTAGES ? 1 : 0;
     p.tie_eps = tie_eps; p.bits_out = bits_out; p.words = (B + 31) / 32; p.tie_count = tie_count; p.pn_min = pn_min; p.wsum = wsum;
     p.Wt = Wt; p.nb = nb;
+#ifdef OOV_LSH_TRACE
+    if (const char* tp = getenv("OOV_LSH_TRACE_PTR")) p.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0));   // profiling only
+#endif
 
     const int64_t pack_threads = nb * L_DMAX;                        // >= nb * 32
     lsh_pack_kernel<<<(unsigned)cdiv(pack_threads, 256), 256, 0, st>>>(planes, B, F, NT, W, w_dtype, rows->D, p.wsplit, Bp, Wt, pn_min);
