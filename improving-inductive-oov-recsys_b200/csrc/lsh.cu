@@ -453,7 +453,7 @@ int check_rows_public(const oov_rows* r, const char* who) { return check_rows(r,
 
 namespace tc {
 bool lsh_tc_supported(int F, int B, int D);
-size_t lsh_tc_workspace(int B);
+size_t lsh_tc_workspace(int64_t n, int B);
 int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* planes, int B, const void* W, int w_dtype,
                const oov_rows* rows, float tie_eps, uint32_t* bits_out, unsigned long long* tie_count, void* workspace,
                size_t workspace_bytes, cudaStream_t st);
@@ -481,7 +481,7 @@ size_t oov_lsh_embed_workspace(int64_t n, int32_t B, int32_t D, int32_t path) {
     const int64_t chunk = n < (1 << 20) ? n : (1 << 20);
     size_t a = align_up((size_t)chunk * ((B + 31) / 32) * 4, 256);
     if (path != OOV_PATH_SIMT_FP32 && B > 0) {                 // F is not known here: reserve for the tensor-core path too
-        const size_t b = tc::lsh_tc_workspace(B);
+        const size_t b = tc::lsh_tc_workspace(n, B);
         if (b > a) a = b;
     }
     (void)D;

@@ -82,15 +82,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // Wait of a single-thread role (TMA producer / MMA issuer) whose warp runs in uniform control flow (all 32 lanes execute
-// the wait, the role's instructions are issued under elect_one() with uniform-register operands).  Polls with the
-// non-blocking test_wait and never sleeps: the wake-up latency of these warps is on the critical path of every tile,
-// and a converged warp parked in try_wait was seen to wake up 1500+ cycles late (scripts/trace_lsh.py).
+// the wait, the role's instructions are issued under elect_one() with uniform-register operands).  The warp is parked
+// in try_wait (hardware suspend, woken by the phase flip): a role warp has the highest warp id of its scheduler, so a
+// spinning one takes issue slots from the four worker warps next to it exactly when they are the critical path
+// (test_wait spinning cost 27 % of those schedulers' slots, scripts/trace_lsh.py showed their workers as stragglers).
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
-    if (mbar_test_wait(bar, parity)) return;
+    if (mbar_try_wait(bar, parity)) return;
     uint32_t polls = 0;
     long long t0 = 0;
-    while (!mbar_test_wait(bar, parity)) {
-        if ((++polls & 4095u) == 0u) {
+    while (!mbar_try_wait_hint(bar, parity, 1000000u)) {
+        if ((++polls & 255u) == 0u) {
             if (t0 == 0) t0 = clock64();
             else if (clock64() - t0 > 4000000000ll) __trap();      // ~2 s at 2 GHz
         }

@@ -198,45 +198,51 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int64_t mt = t / n_tiles; const int nt = (int)(t - mt * n_tiles);
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
+        // (single-thread roles: all 32 lanes in uniform control flow, the TMA / MMA / commit instructions predicated on one
+        // elected lane — under `if (lane == 0)` ptxas wraps every UTMALDG / UTCHMMA in an ELECT + R2UR + BRA.U.ANY vote loop)
+        const bool issue = elect_one();
+        int stage = 0; uint32_t phase = 0;
+        for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int64_t mt = t / n_tiles; const int nt = (int)(t - mt * n_tiles);
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
+                unsigned char* sa = smem + stage * S::STAGE_BYTES;
+                if (issue) {
                     mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-                    unsigned char* sa = smem + stage * S::STAGE_BYTES;
                     tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, (int)(mt * BM));
                     tma_load_2d(sa + S::A_BYTES, &tmB, &full_bar[stage], kb * BK, nt * BN);
-                    if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN);
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);           // epilogue has drained this accumulator
+        const bool issue = elect_one();
+        constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);               // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                mbar_wait(&full_bar[stage], phase);                   // TMA bytes have landed
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);               // TMA bytes have landed
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
-                    const uint64_t adesc = make_sw128_desc(sa);
-                    const uint64_t bdesc = make_sw128_desc(sa + S::A_BYTES);
+                const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+                const uint64_t adesc = make_sw128_desc(sa);
+                const uint64_t bdesc = make_sw128_desc(sa + S::A_BYTES);
+                if (issue) {
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)                 // +32 B along K per UMMA_K = 16 bf16
                         tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
                     tc_commit(&empty_bar[stage]);                     // frees the smem slot when the MMAs retire
-                    if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+                    if (kb == k_blocks - 1) tc_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
                 }
-                tc_commit(&tmem_full[acc]);                           // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
             }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue =====================
@@ -466,24 +472,29 @@ tc_linear2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs: own A rows, own half of the weight rows) =====================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int64_t t = pair; t < total_tiles; t += n_pairs) {
-                const int64_t mt = t / n_tiles; const int nt = (int)(t - mt * n_tiles);
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
+        // (single-thread roles: all 32 lanes in uniform control flow, the TMA / MMA / commit instructions predicated on one
+        // elected lane — under `if (lane == 0)` ptxas wraps every UTMALDG / UTCHMMA in an ELECT + R2UR + BRA.U.ANY vote loop)
+        const bool issue = elect_one();
+        int stage = 0; uint32_t phase = 0;
+        for (int64_t t = pair; t < total_tiles; t += n_pairs) {
+            const int64_t mt = t / n_tiles; const int nt = (int)(t - mt * n_tiles);
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
+                const uint32_t fb = mapa_u32(&full_bar[stage], 0);
+                unsigned char* sa = smem + stage * S::STAGE_BYTES;
+                if (issue) {
                     if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
-                    const uint32_t fb = mapa_u32(&full_bar[stage], 0);
-                    unsigned char* sa = smem + stage * S::STAGE_BYTES;
                     tma_load_2d_cg2(sa, &tmA, fb, kb * BK, (int)(mt * 2 * BM + rank * BM));
                     tma_load_2d_cg2(sa + S::A_BYTES, &tmB, fb, kb * BK, nt * BN + (int)rank * 128);
-                    if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
-        if (lane == 0 && leader) {
+        const bool issue = elect_one();
+        if (leader) {
             constexpr uint32_t idesc = make_idesc_bf16_f32(2 * BM, BN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -497,13 +508,16 @@ tc_linear2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
                     const uint64_t adesc = make_sw128_desc(sa);
                     const uint64_t bdesc = make_sw128_desc(sa + S::A_BYTES);
+                    if (issue) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        tc_mma_bf16_cg2(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-                    tc_commit_cg2(&empty_bar[stage], 3);              // frees the stage in both CTAs
+                        for (int k = 0; k < BK / 16; ++k)
+                            tc_mma_bf16_cg2(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                        tc_commit_cg2(&empty_bar[stage], 3);          // frees the stage in both CTAs
+                        if (kb == k_blocks - 1) tc_commit_cg2(&tmem_full[acc], 3);   // accumulator complete -> both epilogues
+                    }
+                    __syncwarp();
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc_commit_cg2(&tmem_full[acc], 3);                    // accumulator complete -> both epilogues
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -531,7 +545,7 @@ tc_linear2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int col0 = nt * BN + cq * 64;
             if (col0 >= N || (epi.debug & 2)) continue;      // warp-uniform
             if (epi.debug & 8) {                             // TMA store path: the previous tile's store must have read the staging
-                if (lane == 0) bulk_wait_group_read0();
+                if (elect_one()) bulk_wait_group_read0();       // the lane that issued the stores (elect.sync is deterministic)
                 __syncwarp();
             }
 #pragma unroll
@@ -569,7 +583,7 @@ tc_linear2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 // one lane, asynchronous (rows >= M are clipped by the tensor map)
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) {
+                if (elect_one()) {                                    // (uniform operands: no vote loop around the UTMASTG)
                     tma_store_2d(&tmO, stg, col0, (int)(mt * 2 * BM + (int64_t)rank * BM + q * 32));
                     bulk_commit_group();
                 }
@@ -594,7 +608,7 @@ tc_linear2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             __syncwarp();
         }
-        if ((epi.debug & 8) && lane == 0) bulk_wait_group0();
+        if ((epi.debug & 8) && elect_one()) bulk_wait_group0();
     }
 
     tc_fence_before();

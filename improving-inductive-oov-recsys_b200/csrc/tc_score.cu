@@ -346,22 +346,31 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // The single-thread roles (TMA producer, MMA issuers) run with all 32 lanes of their warp in uniform control flow and
+    // predicate only the TMA / MMA / commit instructions on one elected lane: under a divergent `if (lane == 0)` ptxas
+    // cannot keep descriptors in uniform registers and wraps every UTCHMMA / UTMALDG in a vote loop (ELECT + R2UR.BROADCAST
+    // + BRA.U.ANY, ~14 dependent instructions each — 125-200 cycles per MMA next to busy epilogue warps).
     if (warp == SC_W_TMA) {
-        if (lane == 0) {
+        const bool leader = elect_one();
+        if (leader) {
             mbar_arrive_expect_tx(a_full, (uint32_t)(n_ut * SC_A_BYTES));
             for (int ut = 0; ut < n_ut; ++ut) tma_load_2d(sA + ut * SC_A_BYTES, &tmU, a_full, 0, (int)(q0 + ut * SC_BM));
-            int stage = 0; uint32_t phase = 0;
             // The ring holds only a few 16 KB tiles (the lists take the shared memory), less than HBM latency x the
             // rate the MMAs consume them: tiles are requested into L2 well ahead, so the ring loads are L2 hits.
             for (int64_t t = t0; t < t1 && t < t0 + SC_L2_AHEAD; ++t)
                 tma_prefetch_l2_2d(&tmI, 0, (int)((p.tile_begin + t * stride) * SC_BN));
-            for (int64_t t = t0; t < t1; ++t) {
+        }
+        __syncwarp();
+        int stage = 0; uint32_t phase = 0;
+        for (int64_t t = t0; t < t1; ++t) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (leader) {
                 if (t + SC_L2_AHEAD < t1) tma_prefetch_l2_2d(&tmI, 0, (int)((p.tile_begin + (t + SC_L2_AHEAD) * stride) * SC_BN));
-                mbar_wait(&empty_bar[stage], phase ^ 1);
                 mbar_arrive_expect_tx(&full_bar[stage], SC_B_BYTES);
                 tma_load_2d(sB + stage * SC_B_BYTES, &tmI, &full_bar[stage], 0, (int)((p.tile_begin + t * stride) * SC_BN));
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
     } else if (warp >= SC_W_MMA) {
         // Two issuer warps, each serving two user tiles in turn.  A single issuer for the four accumulators was the
@@ -371,7 +380,8 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
         // leave the epilogue 80 registers instead of 96.  Splitting the accumulators into 64-column halves to overlap
         // drain and MMA was tried and lost: N = 64 MMAs are shared-memory bound in SS mode.)
         const int iw = warp - SC_W_MMA;
-        if (lane == 0 && 2 * iw < n_ut) {
+        const bool leader = elect_one();
+        if (2 * iw < n_ut) {
             constexpr uint32_t idesc = make_idesc_bf16_f32(SC_BM, SC_BN);
             mbar_wait(a_full, 0);
             const int n_mine = n_ut - 2 * iw >= 2 ? 2 : 1;
@@ -385,12 +395,15 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
                     const uint64_t adesc = make_sw128_desc(smem_u32(sA + ut * SC_A_BYTES));
                     const uint64_t bdesc = make_sw128_desc(smem_u32(sB + stage * SC_B_BYTES));
                     const uint32_t d_tmem = tmem_base + (uint32_t)(ut * SC_BN);
+                    if (leader) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, kk ? 1u : 0u);
-                    tc_commit(&acc_full[ut]);
+                        for (int kk = 0; kk < 4; ++kk)
+                            tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, kk ? 1u : 0u);
+                        tc_commit(&acc_full[ut]);
+                        if (j == n_mine - 1) tc_commit(&empty_bar[stage]);        // one arrival per issuer for this stage
+                    }
+                    __syncwarp();
                 }
-                tc_commit(&empty_bar[stage]);                                     // one arrival per issuer for this stage
                 acc_phase ^= 1;
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }

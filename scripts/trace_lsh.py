@@ -27,9 +27,9 @@ for role in range(4):
         if x == 0:
             continue
         x &= (1 << 64) - 1
-        ev.append((x & ((1 << 56) - 1), role, x >> 56))
+        ev.append((x & ((1 << 48) - 1), role, x >> 56, (x >> 48) & 255))
 ev.sort()
 t0 = ev[0][0]
 lim = int(sys.argv[1]) if len(sys.argv) > 1 else 400
-for t, role, e in ev[:lim]:
-    print(f"{t - t0:9d}  {'  ' * role * 6}{['MMA1', 'MMA2', 'W0', 'W15'][role]} {names.get(e, e)}")
+for t, role, e, tag in ev[:lim]:
+    print(f"{t - t0:9d}  {'  ' * role * 6}{['MMA1', 'MMA2', 'W0', 'W15'][role]} {names.get(e, e)} #{tag}")
