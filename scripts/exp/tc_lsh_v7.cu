@@ -8,7 +8,7 @@
 // keeps every fp16 piece in the normal range.  With x = x0 + x1 (+ <= 2^-22 |x|) and p^ = p0 + p1 (+ <= 2^-22 |p^|)
 //     A' = [x0 | x1] in TMEM,   B' row = [p0 | p1],   R' = x0 p0 + x1 p0 + x0 p1      (six K = 16 steps, x0 reused)
 // and  |R' - x . p^| <= 3 * 2^-22 |x||p^| + the tensor core's accumulation error.  A projection closer to zero than
-// 2^-18 |x||p^| (about 2 in 100 000) is NOT trusted: its (row, plane) goes into a shared-memory queue and the worker warps go on.  At
+// 2^-16 |x||p^| (about 7 in 100 000) is NOT trusted: its (row, plane) goes into a shared-memory queue and the worker warps go on.  At
 // the end of the row tile all 512 worker threads re-evaluate the queued projections with the fp32 FMA chain of the
 // CUDA-core path (csrc/lsh.cu: the original planes, f ascending) — so both paths give identical bits and count the same
 // |R| < tie_eps events — and the few signs that really differ are applied to the finished accumulator as rank-one
@@ -27,13 +27,11 @@
 //
 // Per CTA (640 threads), persistent over 128-row tiles of the id list (tiles without OOV ids are plain row copies and
 // skip the GEMMs — one flag byte per tile, written by lsh_flags_kernel):
-//   warps 0-15  workers : per 128-plane N tile (lane = row, warp = 32 of the 128 columns): tcgen05.ld the projections,
-//                         min|R| tree against the near-zero threshold, two instructions per pair of scores (PRMT +
-//                         LOP3) to form the fp16 +-1 words, one HADD2 per word for the count, tcgen05.st them back
-//                         into TENSOR MEMORY as the A operand of the second GEMM.  Everything rare (a near-zero
-//                         projection, planes >= B, the caller wants the bits) is one out-of-line call, so the loop stays
-//                         a few hundred bytes of code (the inlined version lost a third of its time to it: instruction
-//                         fetch stalls and the slowest of sixteen warps holding up every hand-over).
+//   warps 0-15  workers : fetch the NEXT tile's feature rows into registers; per 128-plane N tile (even tiles: warps
+//                         0-7, odd tiles: warps 8-15): tcgen05.ld the projections (lane = row), min|R| tree against the
+//                         near-zero threshold, two instructions per pair of scores (PRMT + LOP3) to form the fp16 +-1
+//                         words, one HADD2 per word for the count, tcgen05.st them back into TENSOR MEMORY as the A
+//                         operand of the second GEMM.
 //   warp 16     TMA     : B' tiles and the transposed bucket-table tiles
 //   warp 17     MMA 1   : GEMM1 (TS: A' from TMEM, M128 N128 K16 x 6) into one of two TMEM accumulators
 //   warp 18     TMEM alloc, then fixer: re-evaluates the queued near-zero projections of a finished row tile while the
@@ -66,7 +64,7 @@ constexpr int L_TAIL_BYTES = 2 * 4 * L_BM * 4 + 4 * L_BM * 4 + 2 * L_BM * 8 + 4 
 constexpr int L_SMEM = 1024 + L_BSTAGES * L_BT_BYTES + L_WSTAGES * L_WT_BYTES + L_TAIL_BYTES;
 static_assert(L_SMEM <= 232448, "tc_lsh shared memory");
 constexpr float L_PSCALE = 256.f;                 // length of the rescaled planes
-constexpr float L_NEAR_REL = 3.814697265625e-6f * L_PSCALE;  // 2^-18 |p^|: |R' - x.p^| stays below a quarter of this times |x|
+constexpr float L_NEAR_REL = 1.52587890625e-5f * L_PSCALE;   // 2^-16 |p^|: |R' - x.p^| stays far below this times |x|
 
 struct LshParams {
     const float* feat; int64_t n_feat_rows; int F;
@@ -286,75 +284,6 @@ __device__ __forceinline__ void copy_iv_tile(const LshParams& p, int64_t tile, i
         for (int w = part; w < p.words; w += 4) p.bits_out[rr * p.words + w] = 0u;
 }
 
-// Everything that is not the common case of a 32-column chunk, out of line and warp-uniform (all 32 lanes call it; the
-// projections are read again from tensor memory, 8 columns at a time): near-zero projections are queued for the fixer
-// warp (or settled here when the queue is full / the caller wants exact bits), planes >= B are forced to +1.
-// Returns the S' bits to force to 1 (x) / to 0 (y), and the number of |R| < tie_eps events seen (z).
-struct RareArgs {
-    uint32_t acc_addr;            // TMEM address of column 0 of the chunk (this warp's lane quarter)
-    uint32_t valid;               // columns < B
-    float near; int force, my_oov, exact_inline;
-    int b0, row, par;
-    int64_t out_row;              // list position of the row (bits_out), -1: past the end
-    int64_t fr;                   // feature row
-    uint32_t* s_qn; uint32_t* q_ent;
-    const float* feat; const float* planes; int F; float tie_eps;
-    uint32_t* bits_out; int words;
-};
-__device__ __noinline__ uint3 lsh_rare_chunk(const RareArgs a) {
-    uint32_t setw = 0u, clrw = 0u, ties = 0u, word = 0u;
-    const bool any_force = __any_sync(0xffffffffu, a.force && a.my_oov);      // a row with Inf / NaN features
-#pragma unroll 1
-    for (int gi = 0; gi < 4; ++gi) {
-        const uint32_t vg = (a.valid >> (8 * gi)) & 0xffu;                   // warp-uniform
-        if (vg == 0u) continue;
-        uint32_t u[8];
-        tc_ld_32x8(a.acc_addr + (uint32_t)(8 * gi), u);
-        tc_wait_ld();
-        uint32_t nw = 0u, pw = 0u, wd = 0u;                                  // near zero / sign bit clear (the bit S' carries) / !(R < 0)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            nw |= (fabsf(__uint_as_float(u[j])) >= a.near ? 0u : 1u) << j;    // NaN counts as near
-            pw |= ((u[j] >> 31) ^ 1u) << j;
-            wd |= (__uint_as_float(u[j]) < 0.f ? 0u : 1u) << j;
-        }
-        if (a.force) nw = 0xffu;
-        nw &= a.my_oov ? vg : 0u;
-        (void)any_force;
-        if (a.exact_inline) {
-            // exact bits now: -0 has the sign bit but is not < 0 (torch_hash.py:57-59), near-zero projections are redone in
-            // the fp32 FMA order of csrc/lsh.cu
-            while (nw) {
-                const int j = __ffs(nw) - 1;
-                nw &= nw - 1;
-                const float r = exact_projection(a.feat, a.planes, a.F, a.fr, a.b0 + 8 * gi + j);
-                wd = (wd & ~(1u << j)) | ((r < 0.f ? 0u : 1u) << j);
-                if (fabsf(r) < a.tie_eps) ++ties;
-            }
-            wd &= a.my_oov ? vg : 0u;
-            word |= wd << (8 * gi);
-            setw |= wd << (8 * gi); clrw |= (~wd & vg) << (8 * gi);
-        } else {
-            while (nw) {
-                const int j = __ffs(nw) - 1;
-                nw &= nw - 1;
-                const uint32_t qs = atomicAdd(a.s_qn, 1u);
-                if (qs < (uint32_t)L_QCAP) {
-                    a.q_ent[qs] = ((uint32_t)a.row << 24) | ((uint32_t)(a.b0 + 8 * gi + j) << 1) | ((pw >> j) & 1u);
-                } else {                                                     // queue full (degenerate rows): settle it here
-                    const float r = exact_projection(a.feat, a.planes, a.F, a.fr, a.b0 + 8 * gi + j);
-                    if (r < 0.f) clrw |= 1u << (8 * gi + j); else setw |= 1u << (8 * gi + j);
-                    if (fabsf(r) < a.tie_eps) ++ties;
-                }
-            }
-        }
-    }
-    if (a.exact_inline && a.out_row >= 0 && (a.b0 >> 5) < a.words) a.bits_out[a.out_row * a.words + (a.b0 >> 5)] = word;
-    setw |= ~a.valid;                                                        // planes >= B meet zero bucket rows: +1, taken out of the count by the caller
-    return make_uint3(setw, clrw, ties);
-}
-
-
 __global__ void __launch_bounds__(L_THREADS, 1)
 tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmW, const LshParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -399,8 +328,8 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         for (int s = 0; s < L_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int s = 0; s < L_WSTAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
         for (int a = 0; a < 2; ++a) {
-            mbar_init(&acc1_full[a], 1); mbar_init(&acc1_empty[a], L_WORKERS);
-            mbar_init(&h_full[a], L_WORKERS); mbar_init(&h_empty[a], 1);
+            mbar_init(&acc1_full[a], 1); mbar_init(&acc1_empty[a], L_WORKERS / 2);
+            mbar_init(&h_full[a], L_WORKERS / 2); mbar_init(&h_empty[a], 1);
             mbar_init(&q_full[a], 1); mbar_init(&f_full[a], 1);
         }
         mbar_init(acc2_full, 1); mbar_init(acc2_empty, L_WORKERS);
@@ -561,9 +490,14 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
     } else {
 #define trace_tag g
         // ===================== workers =====================
+        // Two groups of eight warps: group 0 converts the even N tiles (projection buffer 0, S' buffer 0), group 1 the odd
+        // ones.  A warp's per-tile latencies (barrier round trips, TMEM load / store, hand-over) overlap with the other
+        // group's sign arithmetic instead of idling all four warps of a scheduler at the same time.
         const int wk = warp;
         const int q = wk & 3;                      // TMEM lane quarter
-        const int slot = wk >> 2;                  // column quarter of every N tile / 8-feature slice / count slot / 16-column output slice
+        const int grp = wk >> 3;                   // N-tile parity this warp converts
+        const int ch = (wk >> 2) & 1;              // 64-column half of those N tiles
+        const int slot = grp * 2 + ch;             // 8-feature slice / count slot / 16-column output slice
         const int row = q * 32 + lane;             // row of the tile this thread owns
         const int wtid = wk * 32 + lane;           // 0..511
         const int gr = wtid >> 2, gpart = wtid & 3;   // in-vocab copy role: row, 16-column slice
@@ -658,84 +592,129 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
 
             __half2 cn0 = __float2half2_rn(0.f), cn1 = cn0;           // sum of this thread's S' words (two chains)
             int padc = 0;                                             // planes >= B among them (forced to +1)
-            // ---- per N tile: projections -> signs -> S'
+            // ---- this group's N tiles: projections -> signs -> S'
             for (int nt = 0; nt < NT; ++nt, ++g) {
-                const int buf = g & 1;
+                if ((int)(g & 1) != grp) continue;
                 const uint32_t bpar = (uint32_t)((g >> 1) & 1);
-                const uint32_t acc_addr = lane_base + (uint32_t)(buf * L_BN + slot * 32);
                 WTRACE(7);
-                mbar_wait(&acc1_full[buf], bpar);
+                mbar_wait(&acc1_full[grp], bpar);
                 tc_fence_after();
                 WTRACE(8);
-                // asked now, needed before the store below: the barrier round trip hides under the load and the conversion
-                const bool h_ok = mbar_try_wait(&h_empty[buf], bpar ^ 1);
-                // S' pair = (+1, +1) with the sign bits of the two projections (2 instructions per pair) and the smallest |R|
-                // of every 8-column group (one 3-input min per pair); 16 columns at a time (registers)
-                uint32_t hw[16];
-                float gm[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    const int col0 = ch * 64 + half * 32;             // first of this thread's 32 columns of the N tile
+                    const uint32_t acc_addr = lane_base + (uint32_t)(grp * L_BN + col0);
+                    // fast path: S' pair = (+1, +1) with the sign bits of the two projections (2 instructions per pair) and
+                    // the smallest |R| of every 8-column group (one 3-input min per pair); 16 columns at a time (registers)
+                    uint32_t hw[16];
+                    float gm[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
 #pragma unroll
-                for (int qq = 0; qq < 2; ++qq) {
-                    uint32_t v[16];
-                    tc_ld_32x16(acc_addr + (uint32_t)(16 * qq), v);
-                    tc_wait_ld();
+                    for (int qq = 0; qq < 2; ++qq) {
+                        uint32_t v[16];
+                        tc_ld_32x16(acc_addr + (uint32_t)(16 * qq), v);
+                        tc_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(hw[8 * qq + i]) : "r"(__byte_perm(v[2 * i], v[2 * i + 1], 0x7030)), "r"(SIGNS), "r"(ONES));
-                        gm[2 * qq + (i >> 2)] = fminf(gm[2 * qq + (i >> 2)], fminf(fabsf(__uint_as_float(v[2 * i])), fabsf(__uint_as_float(v[2 * i + 1]))));
-                    }
-                }
-                WTRACE(9);
-                const float mn = fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3]));
-                const int b0 = nt * L_BN + slot * 32;                 // plane of column 0
-                // rare (warp-uniform: the out-of-line path reads tensor memory with warp-collective loads): a projection
-                // too close to zero to trust its sign, a row with Inf / NaN features, planes >= B in the chunk (their
-                // projections are exact zeros), or the caller wants the multi-hot words
-#ifdef OOV_LSH_NORARE   /* timing experiment only: results are wrong without this path */
-                if (false) {
-#else
-                if ((b0 + 32 > p.B) | exact_inline | __any_sync(0xffffffffu, ((mn < near) | force) & my_oov)) {
-#endif
-                    RareArgs ra;
-                    ra.acc_addr = acc_addr;
-                    ra.valid = (b0 + 32 <= p.B) ? 0xffffffffu : ((b0 >= p.B) ? 0u : ((1u << (p.B - b0)) - 1u));
-                    ra.near = near; ra.force = force; ra.my_oov = my_oov; ra.exact_inline = exact_inline;
-                    ra.b0 = b0; ra.row = row; ra.par = par;
-                    ra.out_row = row0 + row < p.n ? row0 + row : -1;
-                    ra.fr = s_fr[par * L_BM + row];
-                    ra.s_qn = &s_qn[par]; ra.q_ent = q_ent + par * L_QCAP;
-                    ra.feat = p.feat; ra.planes = p.planes; ra.F = p.F; ra.tie_eps = p.tie_eps;
-                    ra.bits_out = p.bits_out; ra.words = p.words;
-                    const uint3 fx = lsh_rare_chunk(ra);
-                    my_ties += fx.z;
-                    if (fx.x | fx.y) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const uint32_t s2 = (fx.x >> (2 * i)) & 3u, c2 = (fx.y >> (2 * i)) & 3u;
-                            uint32_t w = hw[i];
-                            w &= ~(((s2 & 1u) ? 0x8000u : 0u) | ((s2 & 2u) ? 0x80000000u : 0u));
-                            w |= ((c2 & 1u) ? 0x8000u : 0u) | ((c2 & 2u) ? 0x80000000u : 0u);
-                            hw[i] = w;
+                        for (int i = 0; i < 8; ++i) {
+                            asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(hw[8 * qq + i]) : "r"(__byte_perm(v[2 * i], v[2 * i + 1], 0x7030)), "r"(SIGNS), "r"(ONES));
+                            gm[2 * qq + (i >> 2)] = fminf(gm[2 * qq + (i >> 2)], fminf(fabsf(__uint_as_float(v[2 * i])), fabsf(__uint_as_float(v[2 * i + 1]))));
                         }
                     }
-                    padc += __popc(~ra.valid);
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc1_empty[buf]);         // the projections of this N tile are no longer needed
+                    const float mn = fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3]));
+                    const int b0 = nt * L_BN + col0;                  // plane of column 0
+                    const bool partial = b0 + 32 > p.B;               // warp-uniform: the chunk holds planes >= B
+                    // (votes: the rare paths read the projections again with warp-collective tcgen05.ld — the values are not
+                    // kept in registers past the loop above — so every branch around such a load is warp-uniform)
+                    #ifdef OOV_LSH_NORARE
+ if (false) {
+#else
+if (partial | exact_inline | __any_sync(0xffffffffu, ((mn < near) | force) & my_oov)) {
+#endif
+                        const uint32_t valid = (b0 + 32 <= p.B) ? 0xffffffffu : ((b0 >= p.B) ? 0u : ((1u << (p.B - b0)) - 1u));
+                        uint32_t setw = 0u, clrw = 0u;                // bits to force to 1 / 0 in the S' words
+                        uint32_t word = 0u;                           // exact multi-hot bits (only when the caller wants them)
+                        const bool any_force = __any_sync(0xffffffffu, force & my_oov);   // a row with Inf / NaN features
 #pragma unroll
-                for (int i = 0; i < 16; i += 2) {
-                    cn0 = __hadd2(cn0, *reinterpret_cast<const __half2*>(&hw[i]));
-                    cn1 = __hadd2(cn1, *reinterpret_cast<const __half2*>(&hw[i + 1]));
+                        for (int gi = 0; gi < 4; ++gi) {
+                            const uint32_t vg = (valid >> (8 * gi)) & 0xffu;              // warp-uniform
+                            // the usual case: one projection of one 8-column group is close to zero.  Queue it and go on.
+                            if (vg != 0u && (exact_inline | any_force | __any_sync(0xffffffffu, (gm[gi] < near) & my_oov))) {
+                                uint32_t nw = 0u, pw = 0u, wd = 0u;   // near zero / sign bit clear (the bit S' carries) / !(R < 0)
+                                {
+                                    uint32_t u[8];
+                                    tc_ld_32x8(acc_addr + (uint32_t)(8 * gi), u);
+                                    tc_wait_ld();
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        nw |= (fabsf(__uint_as_float(u[j])) >= near ? 0u : 1u) << j;          // NaN counts as near
+                                        pw |= ((u[j] >> 31) ^ 1u) << j;
+                                        wd |= (__uint_as_float(u[j]) < 0.f ? 0u : 1u) << j;
+                                    }
+                                }
+                                if (force) nw = 0xffu;
+                                nw &= my_oov ? vg : 0u;
+                                if (exact_inline) {
+                                    // exact bits now: -0 has the sign bit but is not < 0 (torch_hash.py:57-59), near-zero
+                                    // projections are redone in the fp32 FMA order of csrc/lsh.cu
+                                    while (nw) {
+                                        const int j = __ffs(nw) - 1;
+                                        nw &= nw - 1;
+                                        const float a = exact_projection(p.feat, p.planes, p.F, s_fr[par * L_BM + row], b0 + 8 * gi + j);
+                                        wd = (wd & ~(1u << j)) | ((a < 0.f ? 0u : 1u) << j);
+                                        if (fabsf(a) < p.tie_eps) ++my_ties;
+                                    }
+                                    wd &= my_oov ? vg : 0u;
+                                    word |= wd << (8 * gi);
+                                    setw |= wd << (8 * gi); clrw |= (~wd & vg) << (8 * gi);
+                                } else {
+                                    while (nw) {
+                                        const int j = __ffs(nw) - 1;
+                                        nw &= nw - 1;
+                                        const uint32_t qs = atomicAdd(&s_qn[par], 1u);
+                                        if (qs < (uint32_t)L_QCAP) {
+                                            q_ent[par * L_QCAP + qs] = ((uint32_t)row << 24) | ((uint32_t)(b0 + 8 * gi + j) << 1) | ((pw >> j) & 1u);
+                                        } else {                      // queue full (degenerate rows): settle it here
+                                            const float a = exact_projection(p.feat, p.planes, p.F, s_fr[par * L_BM + row], b0 + 8 * gi + j);
+                                            if (a < 0.f) clrw |= 1u << (8 * gi + j); else setw |= 1u << (8 * gi + j);
+                                            if (fabsf(a) < p.tie_eps) ++my_ties;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        if (exact_inline && row0 + row < p.n && (b0 >> 5) < p.words) p.bits_out[(row0 + row) * p.words + (b0 >> 5)] = word;
+                        setw |= ~valid;                               // planes >= B meet zero bucket rows: +1, taken out of the count below
+                        if (setw | clrw) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const uint32_t s2 = (setw >> (2 * i)) & 3u, c2 = (clrw >> (2 * i)) & 3u;
+                                uint32_t w = hw[i];
+                                w &= ~(((s2 & 1u) ? 0x8000u : 0u) | ((s2 & 2u) ? 0x80000000u : 0u));
+                                w |= ((c2 & 1u) ? 0x8000u : 0u) | ((c2 & 2u) ? 0x80000000u : 0u);
+                                hw[i] = w;
+                            }
+                        }
+                        padc += __popc(~valid);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        cn0 = __hadd2(cn0, *reinterpret_cast<const __half2*>(&hw[i]));
+                        cn1 = __hadd2(cn1, *reinterpret_cast<const __half2*>(&hw[i + 1]));
+                    }
+                    if (half == 0) {
+                        WTRACE(10);
+                        mbar_wait(&h_empty[grp], bpar ^ 1);           // GEMM2 of the previous use of this S' buffer is done
+                        tc_fence_after();
+                        WTRACE(11);
+                    }
+                    tc_st_32x16(lane_base + H_COL + (uint32_t)(grp * 64 + (col0 >> 1)), hw);
                 }
-                WTRACE(10);
-                if (!h_ok) mbar_wait(&h_empty[buf], bpar ^ 1);        // GEMM2 of the previous use of this S' buffer is done
-                tc_fence_after();
-                WTRACE(11);
-                tc_st_32x16(lane_base + H_COL + (uint32_t)(buf * 64 + slot * 16), hw);
                 tc_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&h_full[buf]);
+                if (lane == 0) {
+                    mbar_arrive(&acc1_empty[grp]);                    // the projections of this N tile are no longer needed
+                    mbar_arrive(&h_full[grp]);
+                }
                 WTRACE(12);
             }
             {
