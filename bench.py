@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench.py — full-sort top-k queries/s with DHE / LSH OOV embedding on N B200s.
+"""bench.py — full-sort top-k queries/s with LSH / DHE OOV embedding on N B200s.
 
     python bench.py --gpus 1 --steps 20 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
@@ -9,7 +9,10 @@
 A *step* is one pass of the hot path over one batch of Q query users, un-amortised like the reference
 (bpr.py:151-156 re-embeds every item per batch): embed the Q users (in-vocab gather + OOV embed), embed ALL N
 items (in-vocab gather + OOV embed) into the bf16 item table, score Q x N, mask pad + history, top-k.
-Default workload = BASELINE.json configs[1]: DirectAU + dhe, 1M items (500k OOV) / 100k users, D = 64, bf16.
+Default workload `lsh10m` = BASELINE.json configs[4], the configuration the metric's target is quoted on (BPR + lsh,
+10M items of which 5M OOV, F = 32, B = 1000, D = 64, Q = 1024, k = 20; it fits one B200).  The same JSON line carries
+a second block `workloads.dhe1m` = configs[1] (DirectAU + dhe, 1M items / 100k users, bf16) with its own value / e2e /
+roofline, measured in the same process (`--single` skips it).
 With N > 1 the item rows are sharded over the ranks (strong scaling: total work fixed), each rank embeds and
 scores its shard, one NCCL all-gather moves the [S, Q, k] candidates and every rank merges.
 Prints ONE JSON line on rank 0.
@@ -51,11 +54,13 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="dhe1m", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="lsh10m", choices=list(WORKLOADS))
+    ap.add_argument("--second", default="dhe1m", choices=list(WORKLOADS), help="second workload reported under `workloads`")
+    ap.add_argument("--single", action="store_true", help="measure only --workload")
     ap.add_argument("--Q", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
-    ap.add_argument("--cpu-sample-div", type=int, default=None, help="item subsampling factor of the CPU arm")
+    ap.add_argument("--cpu-slices", type=int, default=None, help="CPU arm: item-axis slices per query batch (one slice = one step)")
     return ap.parse_args()
 
 
@@ -92,71 +97,118 @@ def query_batch(wl, seed):
 
 
 # --------------------------------------------------------------------------------------- CPU arm (oracle port)
-def cpu_reference(wl, steps, warmup, sample_div, budget_s=25.0):
-    """The reference's CPU path, restated by the oracle (the reference itself is Python on torch and does not
-    travel to the GPU box): same step, item axis subsampled by `sample_div`, time scaled back (cost is linear
-    in N).  Returns (queries/s at the full workload size, description, threads)."""
-    import torch
-    from oracle import oracle as o
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    n_items = max(wl["n_items"] // sample_div, 2000)
-    n_old = n_items // 2
-    D, Q, k = wl["D"], wl["Q"], wl["k"]
-    g = np.random.Generator(np.random.PCG64(7))
-    item_table = (g.standard_normal((n_old, D)) * 0.05).astype(np.float32)
-    user_table = (g.standard_normal((wl["n_old_users"], D)) * 0.05).astype(np.float32)
-    users, hu, hi = query_batch(wl, 99)
-    hi = hi % n_items
-    if wl["embedder"] == "dhe":
-        keys = o.keys_to_array(dhe_keys(wl["H"]))
-        ws, bs = dhe_weights(wl["H"], wl["hidden"], D, 5)
-        tws = [torch.from_numpy(w) for w in ws]
-        tbs = [torch.from_numpy(b) for b in bs]
+class CpuReference:
+    """The reference's CPU path, restated by the oracle (the reference itself is Python on torch with absent
+    dependencies and does not travel to the GPU box), at the FULL workload size: no sub-sampling, no scaled times.
 
-        def mlp(h):          # fp32 torch CPU GEMMs (multi-threaded), like the reference's nn.Sequential on CPU
-            x = torch.from_numpy(h.astype(np.float32))
-            for l in range(4):
-                x = torch.nn.functional.linear(x, tws[l], tbs[l])
-                x = torch.nn.functional.gelu(x) if l < 3 else torch.sigmoid(x)
-            return x.numpy()
+    One query batch = embed the Q users, embed ALL N items, score, mask pad + history, top-k.  The reference
+    materialises [N, B] multi-hot and [Q, N] score matrices (40 GB each at 10M items), so the item axis is walked in
+    `slices` equal slices with a running top-k merge; ONE SLICE IS ONE STEP, `slices` steps complete one query batch:
+    queries/s = Q / (slices x seconds per step), every number is measured."""
 
-        embed_items = lambda ids: mlp(o.dhe_hashes(ids, keys))
-        embed_users = embed_items
-    else:
-        F_, B = wl["F"], wl["B"]
-        feat = o.l2_normalize(g.standard_normal((n_items, F_)).astype(np.float32))
-        ufeat = o.l2_normalize(g.standard_normal((wl["n_users"], F_)).astype(np.float32))
-        planes = g.standard_normal((B, F_)).astype(np.float32)
-        W = (g.standard_normal((B, D)) * 0.05).astype(np.float32)
-        embed_items = lambda ids: o.lsh_embed(feat, ids, planes, W)
-        embed_users = lambda ids: o.lsh_embed(ufeat, ids, planes, W)
+    def __init__(self, wl, slices):
+        import torch
+        from oracle import oracle as o
+        self.o, self.torch, self.wl, self.slices = o, torch, wl, max(1, int(slices))
+        self.threads = os.cpu_count() or 1
+        torch.set_num_threads(self.threads)
+        N, D = wl["n_items"], wl["D"]
+        self.n_old = wl["n_old_items"]
+        g = np.random.Generator(np.random.PCG64(7))
+        self.item_table = (g.standard_normal((self.n_old, D), dtype=np.float32) * np.float32(0.05))
+        self.user_table = (g.standard_normal((wl["n_old_users"], D), dtype=np.float32) * np.float32(0.05))
+        self.users, self.hu, self.hi = query_batch(wl, 99)
+        if wl["embedder"] == "dhe":
+            keys = o.keys_to_array(dhe_keys(wl["H"]))
+            ws, bs = dhe_weights(wl["H"], wl["hidden"], D, 5)
+            tws = [torch.from_numpy(w) for w in ws]
+            tbs = [torch.from_numpy(b) for b in bs]
 
-    def step():
-        ue = o.assemble_rows(users, wl["n_old_users"], user_table, embed_users)
-        ie = o.assemble_rows(np.arange(n_items), n_old, item_table, embed_items)
-        s = torch.from_numpy(ue) @ torch.from_numpy(ie).T
-        s[:, 0] = -np.inf
-        s[torch.from_numpy(hu), torch.from_numpy(hi)] = -np.inf
-        return torch.topk(s, k, dim=-1)
+            def mlp(h):          # fp32 torch CPU GEMMs (multi-threaded), like the reference's nn.Sequential on CPU
+                x = torch.from_numpy(h.astype(np.float32))
+                for l in range(4):
+                    x = torch.nn.functional.linear(x, tws[l], tbs[l])
+                    x = torch.nn.functional.gelu(x) if l < 3 else torch.sigmoid(x)
+                return x.numpy()
 
-    t_all = time.perf_counter()
-    for _ in range(max(1, min(warmup, 1))):
-        step()
-    times = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        step()
-        times.append(time.perf_counter() - t0)
-        if time.perf_counter() - t_all > budget_s and len(times) >= 2:
-            break
-    t = float(np.mean(times))
-    scale = wl["n_items"] / n_items
-    qps = Q / (t * scale)
-    desc = (f"oracle port of the reference step on {threads} host threads: Q={Q}, items subsampled to {n_items} "
-            f"(1/{scale:.0f} of {wl['n_items']}), {len(times)} steps of {t * 1e3:.1f} ms, time scaled x{scale:.0f} "
-            f"(cost linear in N); hashing = C SipHash loop (the reference loops per id in Python, dh_embedder.py:165-170)")
-    return qps, desc, threads, t * scale * 1e3
+            self.embed_items = lambda ids: mlp(o.dhe_hashes(ids, keys))
+            self.embed_users = self.embed_items
+            self.hashing = "C SipHash loop (the reference loops per id in Python, dh_embedder.py:165-170)"
+        else:
+            F_, B = wl["F"], wl["B"]
+            n_oov = N - self.n_old
+            feat = np.empty((N, F_), dtype=np.float32)          # rows < n_old are never hashed
+            feat[self.n_old:] = o.l2_normalize(g.standard_normal((n_oov, F_), dtype=np.float32))
+            ufeat = o.l2_normalize(g.standard_normal((wl["n_users"], F_), dtype=np.float32))
+            planes = g.standard_normal((B, F_), dtype=np.float32)
+            W = (g.standard_normal((B, D), dtype=np.float32) * np.float32(0.05))
+            chunk = 131072                                       # rows per [n, B] multi-hot block (0.5 GB fp32)
+
+            def emb(fm, ids):
+                out = np.empty((len(ids), D), dtype=np.float32)
+                for c0 in range(0, len(ids), chunk):
+                    out[c0:c0 + chunk] = o.lsh_embed(fm, ids[c0:c0 + chunk], planes, W)
+                return out
+
+            self.embed_items = lambda ids: emb(feat, ids)
+            self.embed_users = lambda ids: emb(ufeat, ids)
+            self.hashing = "torch_hash.py:55-60 restated with numpy GEMMs"
+        self.bounds = [N * i // self.slices for i in range(self.slices + 1)]
+        self.i = 0
+        self.ue = None
+        self.best = None
+
+    def step(self):
+        """One slice of the item axis (slice 0 also embeds the query users); returns True when a batch completed."""
+        o, torch, wl = self.o, self.torch, self.wl
+        k = wl["k"]
+        sl = self.i % self.slices
+        if sl == 0:
+            self.ue = torch.from_numpy(o.assemble_rows(self.users, wl["n_old_users"], self.user_table, self.embed_users))
+            self.best = None
+        lo, hi = self.bounds[sl], self.bounds[sl + 1]
+        ie = o.assemble_rows(np.arange(lo, hi), self.n_old, self.item_table, self.embed_items)
+        s = self.ue @ torch.from_numpy(ie).T
+        if lo == 0:
+            s[:, 0] = -np.inf
+        m = (self.hi >= lo) & (self.hi < hi)
+        s[torch.from_numpy(self.hu[m]), torch.from_numpy(self.hi[m] - lo)] = -np.inf
+        v, ix = torch.topk(s, min(k, hi - lo), dim=-1)
+        ix = ix + lo
+        if self.best is not None:
+            v = torch.cat([self.best[0], v], dim=1)
+            ix = torch.cat([self.best[1], ix], dim=1)
+            v, sel = torch.topk(v, k, dim=-1)
+            ix = torch.gather(ix, 1, sel)
+        self.best = (v, ix)
+        self.i += 1
+        return sl == self.slices - 1
+
+    def run(self, steps, warmup, budget_s=None):
+        """Times `steps` slices after `warmup` untimed ones (stops early after `budget_s` seconds, never mid-batch when
+        a budget is given).  Returns (queries/s, ms per step, steps timed)."""
+        for _ in range(warmup):
+            self.step()
+        t_all = time.perf_counter()
+        times = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            done = self.step()
+            times.append(time.perf_counter() - t0)
+            if budget_s is not None and done and time.perf_counter() - t_all > budget_s:
+                break
+        t = float(np.mean(times))
+        return self.wl["Q"] / (t * self.slices), t * 1e3, len(times)
+
+    def describe(self, n_steps, ms):
+        wl = self.wl
+        return (f"oracle port of the reference step on {self.threads} host threads at the full size (N={wl['n_items']}, Q={wl['Q']}): "
+                f"{self.slices} item-axis slice(s) per query batch with a running top-k merge, one slice per step, {n_steps} steps of "
+                f"{ms:.0f} ms measured, nothing extrapolated; hashing = {self.hashing}")
+
+
+def default_slices(wl):
+    return 8 if wl["n_items"] >= 5_000_000 else 1
 
 
 # --------------------------------------------------------------------------------------- clocks
@@ -271,12 +323,6 @@ def build_gpu(wl, device, rank):
             emb = oov_b200.get_inductive_embedder(cfg, Dataset(wl["n_old_users"], wl["n_old_items"], uf, itf), mode="bench")
         finally:
             os.chdir(cwd)
-        ws, bs = dhe_weights(wl["H"], wl["hidden"], D, 5)
-        with torch.no_grad():
-            for net in (emb.user_hash_net, emb.item_hash_net):
-                for l, li in enumerate((0, 2, 4, 6)):
-                    net[li].weight.copy_(torch.from_numpy(ws[l]))
-                    net[li].bias.copy_(torch.from_numpy(bs[l]))
     else:
         F_ = wl["F"]
         uf = oov_b200.Interaction({"user_id": torch.arange(wl["n_users"]), "f0": torch.randn(wl["n_users"], F_, generator=g)})
@@ -284,49 +330,63 @@ def build_gpu(wl, device, rank):
         emb = oov_b200.get_inductive_embedder(cfg, Dataset(wl["n_old_users"], wl["n_old_items"], uf, itf), mode=f"bench-{rank}")
     cls = oov_b200.BPR if wl["model"] == "BPR" else oov_b200.DirectAU
     model = cls(cfg, Dataset(wl["n_old_users"], wl["n_old_items"], uf, itf), inductive_embedder=emb).to(device).eval()
+    if wl["embedder"] == "dhe":
+        # 'trained-looking' hash nets, set AFTER the model is built: the model's constructor re-initialises every Linear of
+        # its sub-modules, the embedder's nets included (bpr.py:46 self.apply(xavier_normal_initialization)), which with
+        # 24-bit hash inputs saturates every output to exactly 0 or 1
+        ws, bs = dhe_weights(wl["H"], wl["hidden"], D, 5)
+        with torch.no_grad():
+            for net in (emb.user_hash_net, emb.item_hash_net):
+                for l, li in enumerate((0, 2, 4, 6)):
+                    net[li].weight.copy_(torch.from_numpy(ws[l]))
+                    net[li].bias.copy_(torch.from_numpy(bs[l]))
     return cfg, emb, model
 
 
-def main():
-    args = parse_args()
-    wl = dict(WORKLOADS[args.workload])
-    if args.Q:
-        wl["Q"] = args.Q
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    cfg_json = {"workload": args.workload, "model": wl["model"], "embedder": wl["embedder"], "n_items": wl["n_items"],
-                "n_oov_items": wl["n_items"] - wl["n_old_items"], "n_users": wl["n_users"], "embedding_size": wl["D"],
-                "Q_per_step": wl["Q"], "k": wl["k"], "max_history": wl["max_hist"],
-                "step": "embed Q users + embed all N items + score + mask + top-k (un-amortised, as bpr.py:151-156)",
-                "l2": "per-step working set (tables + activations) > 126 MB L2; no explicit flush",
-                "launch": "eager (one Python call per kernel)" if args.eager else "whole step replayed from one CUDA graph (GraphedTopK)"}
+def config_json(name, wl, args, world):
+    return {"workload": name, "model": wl["model"], "embedder": wl["embedder"], "n_items": wl["n_items"],
+            "n_oov_items": wl["n_items"] - wl["n_old_items"], "n_users": wl["n_users"], "embedding_size": wl["D"],
+            "Q_per_step": wl["Q"], "k": wl["k"], "max_history": wl["max_hist"],
+            "step": "embed Q users + embed all N items + score + mask + top-k (un-amortised, as bpr.py:151-156)",
+            "l2": "per-step working set (tables + activations) > 126 MB L2; no explicit flush",
+            "launch": "eager (one Python call per kernel)" if args.eager else "whole step replayed from one CUDA graph (GraphedTopK)",
+            "parallelism": "single GPU" if world == 1 else f"item rows sharded over {world} ranks, all-gather top-k merge"}
 
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        div = args.cpu_sample_div or (50 if wl["n_items"] >= 5_000_000 else (10 if wl["n_items"] >= 1_000_000 else 5))
-        qps, desc, threads, ms = cpu_reference(wl, args.steps, args.warmup, div, budget_s=120.0)
-        print(json.dumps({"impl": "reference", "metric": "full_sort_topk_queries_per_s", "value": qps, "unit": "queries/s",
-                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                          "data": "synthetic", "config": cfg_json,
-                          "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": desc},
-                          "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return
 
+def traffic_of(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel / launch shape, taken from the committed
+    `ncu --set full` summaries (profiles/traffic.json names the source file of every entry)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        e = t.get(kernel_key)
+        return (float(e["bytes"]), e["source"]) if e else (None, None)
+    except Exception:
+        return None, None
+
+
+def run_reference(args, name, wl):
+    """`--impl reference`: the CPU arm alone (rank 0), same metric / unit / config keys as the GPU arm."""
+    slices = args.cpu_slices or default_slices(wl)
+    ref = CpuReference(wl, slices)
+    qps, ms, n = ref.run(args.steps, args.warmup)
+    desc = ref.describe(n, ms)
+    return {"impl": "reference", "metric": "full_sort_topk_queries_per_s", "value": qps, "unit": "queries/s",
+            "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_json(name, wl, args, max(args.gpus, 1)),
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": ref.threads, "kind": "port", "sample": desc,
+                             "steps_per_query_batch": slices},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def run_gpu(args, name, wl, rank, world, local_rank, with_cpu_baseline):
+    """One workload on this rank's GPU (all ranks call it); returns the result dict on rank 0, None elsewhere."""
     import torch
     import torch.distributed as dist
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local_rank)
-    device = f"cuda:{local_rank}"
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(device))
     import oov_b200
     from oov_b200 import ops, sharded
-    oov_b200._lib.check(oov_b200._lib.load().oov_check_device(local_rank))
-
+    device = f"cuda:{local_rank}"
+    cfg_json = config_json(name, wl, args, world)
     cfg, emb, model = build_gpu(wl, device, rank)
     Q, k, N = wl["Q"], wl["k"], wl["n_items"]
     n_batches = 8
@@ -450,18 +510,21 @@ def main():
         src = "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1590 (of fallback)"
         cands = []          # (per-step ms, roofline dict)
 
-        def tensor_entry(name, t_ms, flops, launches_per_step=1, note=None):
+        def tensor_entry(name_, key, t_ms, flops, launches_per_step=1, note=None):
             ach = flops / (t_ms * 1e-3) / 1e12
-            d = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                 "traffic": None, "launch_ms": t_ms, "flops_per_launch": flops, "launches_per_step": launches_per_step,
+            tr, tr_src = traffic_of(key)
+            d = {"kernel": name_, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                 "traffic": tr, "launch_ms": t_ms, "flops_per_launch": flops, "launches_per_step": launches_per_step,
                  "peak_source": src}
+            if tr_src:
+                d["traffic_source"] = tr_src
             if note:
                 d["note"] = note
             cands.append((t_ms * launches_per_step, d))
 
         # fused score + mask + top-k: algorithmic flops 2 Q N D
         tensor_entry("tc_score_topk_kernel<1> + score_threshold_kernel + tc_score_topk_kernel<0> + merge_keys_kernel "
-                     "(tcgen05 scoring fused with masks and top-k; sampled pre-pass threshold)",
+                     "(tcgen05 scoring fused with masks and top-k; sampled pre-pass threshold)", f"score_topk:{name}",
                      stages["score_topk_ms"], 2.0 * Q * N * wl["D"],
                      note="algorithmic flops 2 Q N D over the time of all four launches; the accumulator hand-over "
                           "(D = 64: four MMAs per 128 x 128 tile) and the epilogue bound it, not the MMA rate")
@@ -475,13 +538,9 @@ def main():
             bias = torch.zeros(wl["hidden"], device=device)
             t_ms = ev_time(lambda: ops.tc_linear(A, Wt, bias, act="gelu", out_dtype=torch.bfloat16), reps=10)
             stages["dhe_hidden_layer_ms_per_262144_rows"] = t_ms
-            tensor_entry("tc_linear2_kernel<GELU> (DHE hidden layer 512x512, tcgen05 cta_group::2 CTA pairs)", t_ms,
+            tensor_entry("tc_linear2_kernel<GELU> (DHE hidden layer 512x512, tcgen05 cta_group::2 CTA pairs)",
+                         f"tc_linear2_gelu:M{M}:N{wl['hidden']}:K{wl['hidden']}", t_ms,
                          2.0 * M * wl["hidden"] * wl["hidden"], launches_per_step=2 * max(1, -(-n_oov // M)))
-            if M == 1 << 18 and wl["hidden"] == 512:
-                # dram__bytes_read.sum + dram__bytes_write.sum of this launch shape, ncu --set full capture
-                # (profiles/r01_linear2_ncu.txt): 269.1 MB + 222.5 MB; algorithmic bytes 2 x 268.4 MB + 0.5 MB weights
-                cands[-1][1]["traffic"] = 491.6e6
-                cands[-1][1]["traffic_source"] = "profiles/r01_linear2_ncu.txt (ncu --set full, same launch shape)"
         else:
             ids_oov = torch.arange(wl["n_old_items"], N, device=device)
             feat_i = emb.item_feature_mat
@@ -490,40 +549,92 @@ def main():
             out_b = torch.empty((n_oov, wl["D"]), dtype=torch.bfloat16, device=device)
             t_ms = ev_time(lambda: ops.lsh_embed(feat_i, planes_i, Wb, ids_oov, out=out_b, n_old=0), reps=3)
             stages["lsh_embed_oov_ms"] = t_ms
-            tensor_entry("tc_lsh_embed_kernel (sign-projection GEMM + bucket-mean GEMM, tcgen05, operands in TMEM)", t_ms,
+            tensor_entry("tc_lsh_embed_kernel (sign-projection GEMM + bucket-mean GEMM, tcgen05, operands in TMEM)",
+                         f"tc_lsh_embed:n{n_oov}:F{wl['F']}:B{wl['B']}:D{wl['D']}", t_ms,
                          2.0 * n_oov * wl["B"] * (wl["F"] + wl["D"]),
-                         note="algorithmic flops = 2 B (F + D) per OOV id (SURVEY 8d); the kernel issues 3 F + D (+16) wide MMAs")
+                         note="algorithmic flops = 2 B (F + D) per OOV id (SURVEY 8d); the kernel issues 3 F + D wide fp16 MMAs (exact-sign split)")
         # throughput when the item table is embedded once per weight version and reused by every query
         # batch (only the query side and the scoring run per step) — derived from the stage timings above
         stages["amortised_queries_per_s_item_table_reused"] = Q / ((stages["user_embed_ms"] + stages["score_topk_ms"]) * 1e-3)
         roofline = max(cands, key=lambda c: c[0])[1]
         roofline["others"] = [c[1] for c in cands if c[1] is not roofline]
+        del table, user_e
 
     cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # bounded sample: ~12 s of CPU work on 1/10 (1M-item workloads) or 1/50 (10M) of the item axis
-        div = args.cpu_sample_div or (50 if N >= 5_000_000 else (10 if N >= 1_000_000 else 5))
-        qps, desc, threads, _ = cpu_reference(wl, 1000, 1, div, budget_s=12.0)
-        cpu_base = {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": desc}
+    if rank == 0 and with_cpu_baseline:
+        # bounded: at most one full query batch beyond ~15 s of CPU work, at the full workload size (nothing extrapolated)
+        slices = args.cpu_slices or default_slices(wl)
+        ref = CpuReference(wl, slices)
+        qps, ms_c, n_c = ref.run(1000 * slices, 0, budget_s=15.0)
+        cpu_base = {"value": qps, "unit": "queries/s", "cores": ref.threads, "kind": "port", "sample": ref.describe(n_c, ms_c),
+                    "steps_per_query_batch": slices, "ms_per_step": ms_c}
+        del ref
 
+    result = None
     if rank == 0:
-        cfg_json["parallelism"] = "single GPU" if world == 1 else f"item rows sharded over {world} ranks, all-gather top-k merge"
-        print(json.dumps({
+        result = {
             "metric": "full_sort_topk_queries_per_s", "value": value, "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": cfg_json, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(lt.item()), "roofline": roofline, "cpu_baseline": cpu_base, "stages": stages}))
+            "gpu_launches": int(lt.item()), "roofline": roofline, "cpu_baseline": cpu_base, "stages": stages}
     if sampler:
         sampler.stop()
+    # free this workload's device memory before the next one (a captured graph holds its pool until it is dropped)
+    gstep = None
+    del dev_batches, model, emb, sr
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return result
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    names = [args.workload] + ([] if args.single or args.second == args.workload else [args.second])
+
+    def workload(name):
+        wl = dict(WORKLOADS[name])
+        if args.Q:
+            wl["Q"] = args.Q
+        return wl
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        print(json.dumps(run_reference(args, names[0], workload(names[0]))))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    import oov_b200
+    oov_b200._lib.check(oov_b200._lib.load().oov_check_device(local_rank))
+
+    results = [run_gpu(args, n, workload(n), rank, world, local_rank, with_cpu_baseline=(world == 1 and not args.no_cpu_baseline))
+               for n in names]
+    if rank == 0:
+        line = results[0]
+        if len(results) > 1:
+            line["workloads"] = {n: {key: r[key] for key in ("value", "unit", "ms_per_step", "e2e", "gpu_launches", "roofline",
+                                                           "cpu_baseline", "stages", "config", "clocks", "steps", "warmup")}
+                                 for n, r in zip(names[1:], results[1:])}
+        print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:
         # A captured graph that contains the NCCL all-gather keeps the communicator busy at teardown
-        # (destroy_process_group did not return on the 2-GPU box): drop the graph, quiesce, leave without the
-        # interpreter's teardown.  Every rank has finished its work and rank 0 has printed by now.
-        gstep = None
+        # (destroy_process_group did not return on the 2-GPU box): quiesce, leave without the interpreter's teardown.
+        # Every rank has finished its work and rank 0 has printed by now.
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()

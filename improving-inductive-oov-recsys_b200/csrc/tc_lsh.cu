@@ -238,25 +238,16 @@ __device__ __forceinline__ float exact_projection(const float* __restrict__ feat
     return a;
 }
 
-// 8 features of one row (thread = (row, slice)).  The row is requested into L2 one tile ahead (no registers held across
-// the N loop) and loaded when the tile is staged.
+// 8 features of one row (thread = (row, slice)).  The workers look two tiles ahead: a tile's ids (-> feature rows) are
+// loaded while the tile before the previous one is projected, its feature rows are requested into L2 one tile ahead
+// (no registers) and loaded (L2 hits) when the tile is staged — no chain of dependent global loads between two tiles.
 struct Gather {
     float x[8];
     int64_t fr;        // feature row of the list row (-1: not hashed — in-vocab, past the end, or out of range)
 };
 
-__device__ __forceinline__ void gather_prefetch(const LshParams& p, int64_t tile, int r, int part) {
-    const int64_t rr = tile * L_BM + r;
-    if (rr < p.n) {
-        const int64_t id = p.ids[rr * p.ids_stride];
-        if (id >= p.n_old) {
-            const int64_t fr = feature_row(id, p.prime_pad);
-            if (fr >= 0 && fr < p.n_feat_rows && part * 8 < p.F)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.feat + fr * p.F + part * 8));
-        }
-    }
-}
-__device__ __forceinline__ void gather_load(const LshParams& p, int64_t tile, int r, int part, Gather& gth) {
+// feature row of list position (tile, r): -1 = not hashed (in-vocab id, past the end of the list, out of range)
+__device__ __forceinline__ int64_t gather_fr(const LshParams& p, int64_t tile, int r) {
     const int64_t rr = tile * L_BM + r;
     int64_t fr = -1;
     if (rr < p.n) {
@@ -266,6 +257,9 @@ __device__ __forceinline__ void gather_load(const LshParams& p, int64_t tile, in
             if (fr < 0 || fr >= p.n_feat_rows) fr = -1;               // out-of-range ids hash nothing (caller bug)
         }
     }
+    return fr;
+}
+__device__ __forceinline__ void gather_load(const LshParams& p, int64_t fr, int part, Gather& gth) {
     gth.fr = fr;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -594,9 +588,9 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
 
         // Turn the prefetched features of tile `Tn` (its parity selects the s_fr bank) into A' = [x0 | x1] in TMEM and the
         // row's near-zero threshold.  Called by every worker thread (it holds a worker barrier).
-        auto stage_tile = [&](int64_t tile, int Tn, bool wait_a_empty) {
+        auto stage_tile = [&](int64_t fr, int Tn, bool wait_a_empty) {
             Gather gth;
-            gather_load(p, tile, row, slot, gth);
+            gather_load(p, fr, slot, gth);
             float mx = 0.f, n2 = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) { mx = fmaxf(mx, fabsf(gth.x[j])); n2 = fmaf(gth.x[j], gth.x[j], n2); }
@@ -643,18 +637,23 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             if (lane == 0) mbar_arrive(a_full);
         };
 
-        // first tile with OOV ids (in-vocab-only tiles on the way are plain copies)
+        // first two tiles with OOV ids (in-vocab-only tiles on the way are plain copies); later ones are found while projecting
         int64_t t = blockIdx.x;
         while (t < n_tiles && p.flags[t] == 0) { copy_iv_tile(p, t, gr, gpart); t += gridDim.x; }
-        if (t < n_tiles) stage_tile(t, 0, false);                     // a_empty: nothing has read A' yet
+        int64_t tn = t + gridDim.x;
+        while (tn < n_tiles && p.flags[tn] == 0) { copy_iv_tile(p, tn, gr, gpart); tn += gridDim.x; }
+        int64_t fr_n = tn < n_tiles ? gather_fr(p, tn, row) : -1;     // feature row of this thread's row in tile tn
+        if (t < n_tiles) stage_tile(gather_fr(p, t, row), 0, false);  // a_empty: nothing has read A' yet
         while (t < n_tiles) {
             const int64_t row0 = t * L_BM;
             const int par = (int)(T & 1);
-            // next tile with OOV ids: issue its gather now, it is consumed after this tile's last projection
-            int64_t tn = t + gridDim.x;
-            while (tn < n_tiles && p.flags[tn] == 0) { copy_iv_tile(p, tn, gr, gpart); tn += gridDim.x; }
             const bool cur_oov = my_oov;                              // (stage_tile moves my_oov / near / force on to the next tile)
-            if (tn < n_tiles) gather_prefetch(p, tn, row, slot);
+            // look ahead: request tile tn's feature rows into L2, load the flag and the ids of the tile after it (consumed at
+            // the end of this tile: the loads fly while this tile is projected)
+            if (fr_n >= 0 && slot * 8 < p.F) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.feat + fr_n * p.F + slot * 8));
+            int64_t tnn = tn + gridDim.x;
+            const uint8_t flag_nn = tnn < n_tiles ? p.flags[tnn] : (uint8_t)1;
+            int64_t fr_nn = tnn < n_tiles ? gather_fr(p, tnn, row) : -1;
 
             __half2 cn0 = __float2half2_rn(0.f), cn1 = cn0;           // sum of this thread's S' words (two chains)
             int padc = 0;                                             // planes >= B among them (forced to +1)
@@ -744,7 +743,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             }
             // ---- A' of the next tile (its features arrived long ago), so the tensor core can go on while we finish; the
             //      barrier inside also completes this tile's queue and hands it to the fixer warp
-            if (tn < n_tiles) stage_tile(tn, T + 1, true);
+            if (tn < n_tiles) stage_tile(fr_n, T + 1, true);
             else {
                 worker_bar();
                 if (wtid == 0) mbar_arrive(&q_full[par]);
@@ -810,9 +809,13 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                                 store_elem(p.out, p.out_dtype, r * p.out_stride + d0 + i, load_elem(p.iv_table, p.iv_dtype, id * (int64_t)p.D + d0 + i));
                 }
             }
+            if (flag_nn == 0) {                                       // rare: in-vocab-only tiles ahead — find the next OOV tile the slow way
+                while (tnn < n_tiles && p.flags[tnn] == 0) { copy_iv_tile(p, tnn, gr, gpart); tnn += gridDim.x; }
+                fr_nn = tnn < n_tiles ? gather_fr(p, tnn, row) : -1;
+            }
             WTRACE(16);
             ++T;
-            t = tn;
+            t = tn; tn = tnn; fr_n = fr_nn;
         }
         if (p.tie_count != nullptr) {
             for (int o = 16; o; o >>= 1) my_ties += __shfl_xor_sync(0xffffffffu, my_ties, o);
