@@ -51,6 +51,9 @@ SIGNATURES = {
     "oov_dhe_mlp": (c_i32, [c_vp, c_i64, C.POINTER(OovDheNet), c_vp, c_i32, c_i64, c_vp, c_sz, c_i32, c_vp]),
     "oov_dhe_embed": (c_i32, [c_vp, c_u64, C.POINTER(OovDheNet), C.POINTER(OovRows), c_vp, c_sz, c_i32, c_vp]),
     "oov_dhe_workspace": (c_sz, [c_i64, C.POINTER(OovDheNet), c_i32]),
+    "oov_dhe_planes_ld": (c_i64, [c_i32]),
+    "oov_dhe_hash_planes": (c_i32, [c_vp, c_i64, c_i64, c_vp, c_i32, c_u64, c_vp, c_vp]),
+    "oov_dhe_embed_planes": (c_i32, [c_vp, C.POINTER(OovDheNet), C.POINTER(OovRows), c_vp, c_sz, c_vp]),
     "oov_tc_linear": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_i32, c_vp, c_i32, c_i64, c_vp]),
     "oov_col_mean": (c_i32, [c_vp, c_i32, c_i64, c_i32, c_vp, c_vp, c_sz, c_vp]),
     "oov_col_mean_workspace": (c_sz, [c_i64, c_i32]),

@@ -162,7 +162,11 @@ size_t dhe_tc_workspace(int64_t n, const oov_dhe_net* net);
 bool dhe_tc_supported(const oov_dhe_net* net, uint64_t mod);
 int dhe_tc_run(const uint8_t* keys, uint64_t mod, const oov_dhe_net* net, const uint32_t* hashes_u32,
                const int64_t* ids, int64_t ids_stride, int64_t n, int64_t n_old, const void* iv_table, int iv_dtype,
-               void* out, int out_dtype, int64_t out_stride, void* workspace, size_t workspace_bytes, cudaStream_t st);
+               void* out, int out_dtype, int64_t out_stride, void* workspace, size_t workspace_bytes, cudaStream_t st,
+               const __nv_bfloat16* planes_in = nullptr);
+int64_t dhe_planes_ld(int H);
+int dhe_tc_hash_planes(const int64_t* ids, int64_t ids_stride, int64_t n, const uint8_t* keys, int H, uint64_t mod,
+                       __nv_bfloat16* planes, cudaStream_t st);
 }  // namespace tc
 // OOV_PATH_AUTO: bf16 outputs take the tensor-core path (bf16 operands, fp32 accumulate, rtol 1e-3 contract),
 // fp32 outputs take the CUDA-core fp32 path (rtol 1e-5 contract).
@@ -310,6 +314,32 @@ int oov_dhe_embed(const uint8_t* keys, uint64_t mod, const oov_dhe_net* net, con
         if (rc) return rc;
     }
     return OOV_OK;
+}
+
+int64_t oov_dhe_planes_ld(int32_t H) { return tc::dhe_planes_ld(H); }
+
+int oov_dhe_hash_planes(const int64_t* ids, int64_t ids_stride, int64_t n, const uint8_t* keys, int32_t H, uint64_t mod,
+                        void* planes, void* stream) {
+    OOV_REQUIRE(keys && (n == 0 || (ids && planes)), OOV_ERR_ARG, "oov_dhe_hash_planes: NULL pointer");
+    OOV_REQUIRE(H > 0 && n >= 0 && ids_stride >= 1, OOV_ERR_ARG, "oov_dhe_hash_planes: bad shape H=%d n=%lld", H, (long long)n);
+    OOV_REQUIRE(mod >= 1 && mod <= (1ull << 24), OOV_ERR_ARG, "oov_dhe_hash_planes: mod must be in [1, 2^24] (three byte planes)");
+    OOV_REQUIRE(aligned(planes, 16), OOV_ERR_ALIGN, "oov_dhe_hash_planes: planes must be 16-byte aligned");
+    return tc::dhe_tc_hash_planes(ids, ids_stride, n, keys, H, mod, reinterpret_cast<__nv_bfloat16*>(planes), (cudaStream_t)stream);
+}
+
+int oov_dhe_embed_planes(const void* planes, const oov_dhe_net* net, const oov_rows* rows, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+    int rc = check_net(net, "oov_dhe_embed_planes");
+    if (rc) return rc;
+    rc = check_rows_public(rows, "oov_dhe_embed_planes");
+    if (rc) return rc;
+    OOV_REQUIRE(planes && aligned(planes, 16), OOV_ERR_ARG, "oov_dhe_embed_planes: planes is NULL or not 16-byte aligned");
+    OOV_REQUIRE(rows->D == net->D, OOV_ERR_ARG, "oov_dhe_embed_planes: rows->D=%d != net->D=%d", rows->D, net->D);
+    OOV_REQUIRE(tc::dhe_tc_supported(net, 1ull << 24), OOV_ERR_ARG, "oov_dhe_embed_planes: net shape not supported by the tcgen05 path");
+    if (rows->n == 0) return OOV_OK;
+    return tc::dhe_tc_run(nullptr, 1ull << 24, net, nullptr, rows->ids, rows->ids_stride, rows->n, rows->n_old, rows->iv_table,
+                          rows->iv_dtype, rows->out, rows->out_dtype, rows->out_stride, workspace, workspace_bytes,
+                          (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(planes));
 }
 
 }  // extern "C"

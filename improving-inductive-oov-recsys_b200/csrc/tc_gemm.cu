@@ -959,10 +959,12 @@ int dhe_tc_pack(const oov_dhe_net* net, void* packed, cudaStream_t st) {
     return OOV_OK;
 }
 
-// hash -> 4 tcgen05 linear layers.  `hashes_u32` (optional) replaces the hash step (oov_dhe_mlp).
+// hash -> 4 tcgen05 linear layers.  `hashes_u32` (optional) replaces the hash step (oov_dhe_mlp); `planes_in` (optional,
+// row stride dhe_planes_ld(H)) are memoised byte planes of the ids (oov_dhe_embed_planes).
 int dhe_tc_run(const uint8_t* keys, uint64_t mod, const oov_dhe_net* net, const uint32_t* hashes_u32,
                const int64_t* ids, int64_t ids_stride, int64_t n, int64_t n_old, const void* iv_table, int iv_dtype,
-               void* out, int out_dtype, int64_t out_stride, void* workspace, size_t workspace_bytes, cudaStream_t st);
+               void* out, int out_dtype, int64_t out_stride, void* workspace, size_t workspace_bytes, cudaStream_t st,
+               const __nv_bfloat16* planes_in = nullptr);
 
 __global__ void split_u32_kernel(const uint32_t* __restrict__ h, int64_t n, int H, __nv_bfloat16* __restrict__ A1, int64_t lda) {
     const int64_t total = n * (int64_t)H;
@@ -977,9 +979,34 @@ __global__ void split_u32_kernel(const uint32_t* __restrict__ h, int64_t n, int 
     }
 }
 
+int64_t dhe_planes_ld(int H) { return (3 * (int64_t)H + 7) / 8 * 8; }
+
+// the three bf16 byte planes of every id (memoised by the caller: they depend on (id, keys) only)
+int dhe_tc_hash_planes(const int64_t* ids, int64_t ids_stride, int64_t n, const uint8_t* keys, int H, uint64_t mod,
+                       __nv_bfloat16* planes, cudaStream_t st) {
+    const int64_t ld = dhe_planes_ld(H);
+    if (n == 0) return OOV_OK;
+    if (ld != 3 * H) {
+        cudaError_t e = cudaMemsetAsync(planes, 0, (size_t)n * ld * 2, st);
+        OOV_REQUIRE(e == cudaSuccess, OOV_ERR_CUDA, "cudaMemsetAsync(planes): %s", cudaGetErrorString(e));
+    }
+    if (hash_fast_ok(H, mod, ld) && hash_variant() >= 0) {
+        launch_hash_fast(ids, ids_stride, n, keys, H, planes, ld, st);
+        OOV_LAUNCH_CHECK("dhe_hash_split_fast_kernel");
+    } else {
+        int64_t blocks = cdiv(n * (int64_t)H, 256);
+        const int64_t cap = (int64_t)num_sms() * 16;
+        if (blocks > cap) blocks = cap;
+        dhe_hash_split_kernel<<<(unsigned)blocks, 256, (size_t)H * 32, st>>>(ids, ids_stride, n, keys, H, mod, planes, ld);
+        OOV_LAUNCH_CHECK("dhe_hash_split_kernel");
+    }
+    return OOV_OK;
+}
+
 int dhe_tc_run(const uint8_t* keys, uint64_t mod, const oov_dhe_net* net, const uint32_t* hashes_u32,
                const int64_t* ids, int64_t ids_stride, int64_t n, int64_t n_old, const void* iv_table, int iv_dtype,
-               void* out, int out_dtype, int64_t out_stride, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+               void* out, int out_dtype, int64_t out_stride, void* workspace, size_t workspace_bytes, cudaStream_t st,
+               const __nv_bfloat16* planes_in) {
     const DhePackedLayout L = packed_layout(net);
     OOV_REQUIRE(workspace && workspace_bytes >= dhe_tc_workspace(n, net), OOV_ERR_WORKSPACE, "dhe (tcgen05): workspace %zu < %zu",
                 workspace_bytes, dhe_tc_workspace(n, net));
@@ -996,11 +1023,16 @@ int dhe_tc_run(const uint8_t* keys, uint64_t mod, const oov_dhe_net* net, const 
     for (int64_t r0 = 0; r0 < n; r0 += c) {
         const int64_t cn = n - r0 < c ? n - r0 : c;
         __nv_bfloat16* A1 = reinterpret_cast<__nv_bfloat16*>(a1);
-        if (L.K1p != 3 * H) cudaMemsetAsync(A1, 0, (size_t)cn * L.K1p * 2, st);
         int64_t blocks = cdiv(cn * (int64_t)H, 256);
         const int64_t cap = (int64_t)num_sms() * 16;
         if (blocks > cap) blocks = cap;
-        if (hashes_u32 != nullptr) {
+        if (planes_in != nullptr) {
+            A1 = const_cast<__nv_bfloat16*>(planes_in) + r0 * (int64_t)L.K1p;       // memoised: no hashing at all
+        } else if (L.K1p != 3 * H) {
+            cudaMemsetAsync(A1, 0, (size_t)cn * L.K1p * 2, st);
+        }
+        if (planes_in != nullptr) {
+        } else if (hashes_u32 != nullptr) {
             split_u32_kernel<<<(unsigned)blocks, 256, 0, st>>>(hashes_u32 + r0 * H, cn, H, A1, L.K1p);
             OOV_LAUNCH_CHECK("split_u32_kernel");
         } else if (hash_fast_ok(H, mod, L.K1p) && hash_variant() >= 0) {

@@ -57,6 +57,7 @@ class DeepHashEmbedder(AbstractInductiveEmbedder):
         self.hash_keys = self.get_hash_keys()
         self._keys_dev = ops.keys_tensor(self.hash_keys, self.device)
         self.compute_path = ops.PATH_AUTO
+        self._planes_cache = {}            # (lo, hi, device) -> bf16 byte planes of arange(lo, hi)
 
     def get_hash_keys(self):
         os.makedirs(DeepHashEmbedder.HASH_KEY_PATH, exist_ok=True)
@@ -88,9 +89,30 @@ class DeepHashEmbedder(AbstractInductiveEmbedder):
     def _hash_items(self, items):
         return self.assemble_rows("item", items, None, 0, None)
 
-    def assemble_rows(self, side, ids, model, n_old, iv_table, out=None, out_dtype=torch.float32):
-        return ops.dhe_embed(ids, self._keys_dev, self._net(side), out=out, out_dtype=out_dtype, n_old=n_old,
+    def assemble_rows(self, side, ids, model, n_old, iv_table, out=None, out_dtype=torch.float32, id_range=None):
+        """`id_range=(lo, hi)`: the caller states that `ids` is arange(lo, hi) (the all-item table, a row shard of it).
+        The hashes of an id depend on the id and the keys only — the reference memoises them per id (dh_embedder.py:139
+        `@cache` on _get_hashes) — so the byte planes of such a range are computed once and kept (768 B per id); later
+        calls run the MLP alone.  Arbitrary id tensors (query batches) are hashed on every call."""
+        net = self._net(side)
+        use_tc = out_dtype == torch.bfloat16 or self.compute_path == ops.PATH_TCGEN05
+        if id_range is not None and use_tc and self.compute_path != ops.PATH_SIMT_FP32 and net.hidden % 8 == 0 and net.D >= 8:
+            key = (int(id_range[0]), int(id_range[1]), ids.device.index)
+            planes = self._planes_cache.get(key)
+            if planes is None:
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("DHE hash planes must be memoised before a CUDA graph is captured (run the step once eagerly)")
+                planes = ops.dhe_hash_planes(ids, self._keys_dev, DeepHashEmbedder.MAX_HASH)
+                while len(self._planes_cache) >= 4:                      # a few shards at most
+                    self._planes_cache.pop(next(iter(self._planes_cache)))
+                self._planes_cache[key] = planes
+            return ops.dhe_embed_planes(planes, ids, net, out=out, out_dtype=out_dtype, n_old=n_old, iv_table=iv_table)
+        return ops.dhe_embed(ids, self._keys_dev, net, out=out, out_dtype=out_dtype, n_old=n_old,
                              iv_table=iv_table, mod=DeepHashEmbedder.MAX_HASH, path=self.compute_path)
+
+    def clear_hash_cache(self):
+        """Drop the memoised hash planes (call after changing `hash_keys` / `_keys_dev`)."""
+        self._planes_cache.clear()
 
     def embed_user_ids(self, user_ids, model) -> torch.Tensor:
         return self._hash_users(user_ids)

@@ -166,8 +166,9 @@ class InductiveGeneralRecommender(nn.Module):
             ops.gather_rows(self.item_embedding.weight.detach(), ids_iv, out=out[: split - lo])
         if hi > split:
             ids_oov = self._id_range(split, hi)
+            kw = {"id_range": (split, hi)} if getattr(self.inductive_embedder, "_planes_cache", None) is not None else {}
             self.inductive_embedder.assemble_rows("item", ids_oov, self, 0, None, out=out[split - lo:],
-                                                  out_dtype=self.table_dtype)
+                                                  out_dtype=self.table_dtype, **kw)
         return out
 
     def _id_range(self, lo: int, hi: int) -> torch.Tensor:

@@ -258,6 +258,32 @@ def dhe_embed(ids, keys: torch.Tensor, net: DheNet, out=None, out_dtype=torch.fl
     return out
 
 
+def dhe_hash_planes(ids, keys: torch.Tensor, mod: int = MAX_HASH) -> torch.Tensor:
+    """bf16 [n, ld]: the three exact byte planes of every 24-bit hash (h = 65536 a + 256 b + c), the layout the
+    tensor-core MLP consumes.  The hashes depend on (id, keys) only — the reference memoises them per id
+    (dh_embedder.py:139 `@cache`) — so a caller that embeds the same ids again keeps this tensor."""
+    ids, stride = _ids_1d(ids)
+    _cuda(keys, "keys", torch.uint8)
+    keys = keys.contiguous()
+    lib = _lib.load()
+    ld = int(lib.oov_dhe_planes_ld(keys.shape[0]))
+    planes = torch.empty((ids.shape[0], ld), dtype=torch.bfloat16, device=ids.device)
+    _lib.check(lib.oov_dhe_hash_planes(_p(ids), stride, ids.shape[0], _p(keys), keys.shape[0], int(mod), _p(planes), _stream()))
+    return planes
+
+
+def dhe_embed_planes(planes: torch.Tensor, ids, net: DheNet, out=None, out_dtype=torch.bfloat16, n_old: int = 0, iv_table=None):
+    """MLP + assemble from memoised byte planes (`dhe_hash_planes` of the same ids)."""
+    _cuda(planes, "planes", torch.bfloat16)
+    rows, out, keep = make_rows(ids, net.D, out, out_dtype, n_old, iv_table, 0)
+    lib = _lib.load()
+    if planes.dim() != 2 or planes.shape[0] != rows.n or planes.shape[1] != int(lib.oov_dhe_planes_ld(net.H)) or not planes.is_contiguous():
+        raise ValueError(f"planes must be contiguous [n={rows.n}, {int(lib.oov_dhe_planes_ld(net.H))}] (got {tuple(planes.shape)})")
+    ws = _workspace(lib.oov_dhe_workspace(rows.n, C.byref(net.struct), PATH_TCGEN05), planes.device)
+    _lib.check(lib.oov_dhe_embed_planes(_p(planes), C.byref(net.struct), C.byref(rows), _p(ws), ws.numel(), _stream()))
+    return out
+
+
 def tc_linear(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, act: str = "none",
               out_dtype=torch.float32, _debug: int = 0) -> torch.Tensor:
     """act(A @ W.T + bias) on the tensor cores: A [M, K], W [N, K] bf16, fp32 accumulate (tcgen05 + TMEM)."""

@@ -132,6 +132,18 @@ int oov_dhe_embed(const uint8_t* keys, uint64_t mod, const oov_dhe_net* net,
                   const oov_rows* rows, void* workspace, size_t workspace_bytes,
                   int32_t path, void* stream);
 size_t oov_dhe_workspace(int64_t n, const oov_dhe_net* net, int32_t path);
+/* The reference memoises the hashes of an id (dh_embedder.py:139 `@cache` on _get_hashes): they depend on (id, keys)
+ * only, never on the weights.  oov_dhe_hash_planes writes them once in the layout the tensor-core MLP consumes — three
+ * exact bf16 byte planes per id, h = 65536 a + 256 b + c: planes[i, j] = a, planes[i, H + j] = b, planes[i, 2H + j] = c,
+ * row stride oov_dhe_planes_ld(H) elements (padding columns zero) — and oov_dhe_embed_planes runs the MLP + assemble
+ * from the memoised planes (rows->ids is only read for the in-vocab / OOV decision when rows->n_old > 0).
+ * mod must be <= 2^24; tcgen05 path only. */
+int64_t oov_dhe_planes_ld(int32_t H);
+int oov_dhe_hash_planes(const int64_t* ids, int64_t ids_stride, int64_t n,
+                        const uint8_t* keys, int32_t H, uint64_t mod,
+                        void* planes /* bf16 [n, ld] */, void* stream);
+int oov_dhe_embed_planes(const void* planes, const oov_dhe_net* net, const oov_rows* rows,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* One bf16 linear layer on the tensor cores (the building block of the tcgen05 DHE path):
  * out[M, N] = act(A[M, K] . W[N, K]^T + bias); A, W bf16 row-major (lda, ldw in elements, multiples of 8),

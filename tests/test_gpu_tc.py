@@ -408,3 +408,30 @@ def test_tc_lsh_deferred_sign_fix_matches_simt(n, F, B, D, dtype):
     assert torch.allclose(a[ok], b[ok], **tol), (a - b).abs().nan_to_num().max().item()
     oov = ids >= n_old
     assert torch.equal(o_tc[~oov], o_si[~oov])
+
+
+def test_dhe_memoised_hash_planes_equal_hashing_every_call(tmp_path):
+    """dh_embedder.py:139 memoises the hashes of an id; here the byte planes of a known id range are kept by the embedder
+    and later calls run the MLP alone.  Same bits as hashing on every call, also after the weights change (the planes
+    depend on ids and keys only), in-vocab rows still gathered; the planes equal the generic uint32 hashes."""
+    import gpu_util as G
+    from oov_b200 import ops
+    case = cases.DHE_CASES["dhe_scaled"]
+    emb, keys, ws, bs = _dhe(case, tmp_path, ops.PATH_AUTO)
+    lo, hi, n_old = 1000, 1000 + 30_011, 7000
+    ids = torch.arange(lo, hi, device=DEV)
+    table = (torch.randn(n_old, case.D, device=DEV) * 0.1).to(torch.bfloat16)
+    for trial in range(2):
+        a = emb.assemble_rows("item", ids, None, n_old, table, out_dtype=torch.bfloat16)
+        b = emb.assemble_rows("item", ids, None, n_old, table, out_dtype=torch.bfloat16, id_range=(lo, hi))
+        c = emb.assemble_rows("item", ids, None, n_old, table, out_dtype=torch.bfloat16, id_range=(lo, hi))     # from the cache
+        torch.cuda.synchronize()
+        assert len(emb._planes_cache) == 1
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16)) and torch.equal(b.view(torch.int16), c.view(torch.int16))
+        assert torch.equal(a[: n_old - lo], table[lo:n_old])
+        with torch.no_grad():                                           # new weights, same planes
+            emb.item_hash_net[2].weight.mul_(1.25)
+    planes = next(iter(emb._planes_cache.values())).float()
+    H = case.n_hashes
+    h = ops.dhe_hash(ids, emb._keys_dev).to(torch.int64)
+    assert torch.equal((planes[:, :H] * 65536 + planes[:, H:2 * H] * 256 + planes[:, 2 * H:3 * H]).to(torch.int64), h)
