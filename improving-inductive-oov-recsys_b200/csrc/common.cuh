@@ -14,6 +14,8 @@ namespace oov {
 extern std::atomic<uint64_t> g_launches;
 void set_error(const char* fmt, ...);
 int num_sms();
+int cur_device();        // current CUDA device clamped to [0, 64): index of per-device caches (function attributes and
+                         // occupancy are per device / context, a process may drive several GPUs)
 
 #define OOV_REQUIRE(cond, code, ...)         \
     do {                                     \

@@ -16,6 +16,12 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+int cur_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    return dev;
+}
+
 int num_sms() {
     static int cached[64] = {0};
     int dev = 0;

@@ -545,12 +545,10 @@ int oov_slsh_embed(const float* feat, int64_t n_feat_rows, int32_t F, const floa
     if (bits_req <= 16 && F <= 512) {
         constexpr int NP = 16;
         const size_t smem16 = (size_t)F * NP * sizeof(float);
-        static bool attr16 = false;
-        if (!attr16) {
-            cudaFuncSetAttribute(slsh_embed_lane<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * NP * 4);
-            attr16 = true;
-        }
-        static int per_sm = 0;
+        // (function attributes are per device: set on every call — cheap and idempotent; occupancy cached per device)
+        cudaFuncSetAttribute(slsh_embed_lane<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * NP * 4);
+        static int per_sm_dev[64] = {0};
+        int& per_sm = per_sm_dev[cur_device()];
         if (per_sm == 0 &&
             (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, slsh_embed_lane<NP>, SLSH_THREADS, smem16) != cudaSuccess || per_sm < 1))
             per_sm = 2;
@@ -564,11 +562,7 @@ int oov_slsh_embed(const float* feat, int64_t n_feat_rows, int32_t F, const floa
         return OOV_OK;
     }
     const size_t smem = (size_t)F * 32 * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(slsh_embed_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, SLSH_MAXF * 32 * 4);
-        attr_set = true;
-    }
+    cudaFuncSetAttribute(slsh_embed_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, SLSH_MAXF * 32 * 4);
     const int warps_per_block = SLSH_THREADS / 32;
     int64_t blocks = cdiv(rows->n, warps_per_block);
     const int64_t max_blocks = (int64_t)num_sms() * (smem > 64 * 1024 ? 1 : (smem > 24 * 1024 ? 2 : 8));

@@ -323,14 +323,16 @@ __global__ void map_ids_kernel(const int64_t* __restrict__ ids, int64_t n, int64
 // wave that ran on a fraction of the machine.
 template <typename K>
 static unsigned grid_for(K kernel, int64_t work_items, int per_block) {
-    static int per_sm = 0;                       // one instantiation (and one cache slot) per kernel type
-    static const void* cached_for = nullptr;
-    if (cached_for != reinterpret_cast<const void*>(kernel)) {
+    static int per_sm_dev[64] = {0};             // one instantiation (and one cache slot per device) per kernel type
+    static const void* cached_for[64] = {nullptr};
+    const int dev = cur_device();
+    if (cached_for[dev] != reinterpret_cast<const void*>(kernel)) {
         int v = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, 256, 0) != cudaSuccess || v < 1) v = 4;
-        per_sm = v;
-        cached_for = reinterpret_cast<const void*>(kernel);
+        per_sm_dev[dev] = v;
+        cached_for[dev] = reinterpret_cast<const void*>(kernel);
     }
+    const int per_sm = per_sm_dev[dev];
     int64_t b = cdiv(work_items, per_block);
     const int64_t cap = (int64_t)num_sms() * per_sm;
     if (b > cap) b = cap;

@@ -644,11 +644,9 @@ static int launch_linear2(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat
         if (tma_store < 0) { const char* e = getenv("OOV_LINEAR_TMASTORE"); tma_store = e ? atoi(e) : 1; }
         if (tma_store) e2.debug |= 8;                      // bit 3: epilogue stores through TMA
     }
-    static bool attr_done = false;
-    if (!attr_done) {
+    {   // per device / context, cheap and idempotent: set on every call (a process may drive several GPUs)
         cudaError_t e = cudaFuncSetAttribute(tc_linear2_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         OOV_REQUIRE(e == cudaSuccess, OOV_ERR_CUDA, "cudaFuncSetAttribute(tc_linear2_kernel): %s", cudaGetErrorString(e));
-        attr_done = true;
     }
     const int64_t tiles = cdiv(M, 2 * BM) * cdiv(N, 256);
     const int pairs_max = num_sms() / 2;
@@ -667,11 +665,9 @@ static int launch_linear(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat1
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, BN);
     if (rc) return rc;
-    static bool attr_done = false;
-    if (!attr_done) {
+    {
         cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<BN, ACT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         OOV_REQUIRE(e == cudaSuccess, OOV_ERR_CUDA, "cudaFuncSetAttribute(tc_linear_kernel): %s", cudaGetErrorString(e));
-        attr_done = true;
     }
     const int64_t tiles = cdiv(M, BM) * cdiv(N, BN);
     const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
@@ -867,7 +863,8 @@ static void launch_hash_fast_v(const int64_t* ids, int64_t ids_stride, int64_t n
     const int slots = 256 / (H / 2);
     // exactly one resident wave: every block walks an equal share of the ids, so a partial second wave (8 blocks per
     // SM requested, 6 resident at 40 registers) ran at a third of the machine for half of the kernel
-    static int per_sm = 0;
+    static int per_sm_dev[64] = {0};
+    int& per_sm = per_sm_dev[cur_device()];
     if (per_sm == 0) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dhe_hash_split_fast_kernel<VARIANT>, 256, 0) != cudaSuccess || per_sm < 1)
             per_sm = 4;

@@ -778,13 +778,11 @@ int score_tc_run(const void* users, const void* items, int64_t Q, int64_t N, int
     rc = make_tmap_bf16_2d(&tmI, items, (uint64_t)D, (uint64_t)(N > 0 ? N : 1), (uint64_t)D * 2, SC_BN);
     if (rc) return rc;
     const size_t smem = score_smem_bytes(k, p.stages);
-    static bool attr_done = false;
-    if (!attr_done) {
+    {   // per device / context, cheap and idempotent: set on every call (a process may drive several GPUs)
         cudaError_t e = cudaFuncSetAttribute(tc_score_topk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM_MAX);
         OOV_REQUIRE(e == cudaSuccess, OOV_ERR_CUDA, "cudaFuncSetAttribute(tc_score_topk_kernel<0>): %s", cudaGetErrorString(e));
         e = cudaFuncSetAttribute(tc_score_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM_MAX);
         OOV_REQUIRE(e == cudaSuccess, OOV_ERR_CUDA, "cudaFuncSetAttribute(tc_score_topk_kernel<1>): %s", cudaGetErrorString(e));
-        attr_done = true;
     }
     const dim3 grid((unsigned)gx, (unsigned)cdiv(Q, SC_UG));
     if (pre_stride > 0) {

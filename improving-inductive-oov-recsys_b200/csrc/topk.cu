@@ -653,12 +653,14 @@ size_t oov_fullsort_topk_workspace(int64_t Q, int64_t N, int32_t D, int32_t k, i
 
 int oov_pairs_to_csr(const int64_t* rows, const int64_t* cols, int64_t n_pairs, int64_t Q, const int64_t* col_ranges,
                      int32_t* rowptr_out, int32_t* cols_out, void* stream) {
-    OOV_REQUIRE(Q >= 1 && Q <= 16 * CSR_MAX_ROWS && n_pairs >= 0 && n_pairs <= (1ll << 20), OOV_ERR_ARG,
-                "oov_pairs_to_csr: Q=%lld (1..%d), n_pairs=%lld (max 2^20)", (long long)Q, 16 * CSR_MAX_ROWS, (long long)n_pairs);
+    OOV_REQUIRE(Q >= 1 && Q <= (1ll << 24) && n_pairs >= 0 && n_pairs < (1ll << 31), OOV_ERR_ARG,
+                "oov_pairs_to_csr: Q=%lld (1..2^24), n_pairs=%lld (< 2^31)", (long long)Q, (long long)n_pairs);
     OOV_REQUIRE(rowptr_out && (n_pairs == 0 || (rows && cols && cols_out)), OOV_ERR_ARG, "oov_pairs_to_csr: NULL pointer");
-    // 64-512 rows per CTA, at most 16 CTAs: each one streams all the pairs, so more CTAs only add L2 traffic
+    // 64-512 rows per CTA: every CTA streams all the pairs (L2-resident after the first), so up to 8192 rows use at most 16
+    // CTAs; larger query batches take ceil(Q / 512) CTAs
     int rows_per = (int)cdiv(Q, 16);
     if (rows_per < 64) rows_per = 64;
+    if (rows_per > CSR_MAX_ROWS) rows_per = CSR_MAX_ROWS;
     const unsigned grid = (unsigned)cdiv(Q, rows_per);
     CsrColMap cmap{0, 0, 0, INT64_MAX};                               // identity
     if (col_ranges != nullptr) {

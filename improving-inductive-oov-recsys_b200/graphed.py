@@ -47,14 +47,17 @@ class GraphedTopK:
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         l0 = ops.launch_count()
-        with torch.cuda.graph(self.graph):
+        # capture on the SAME stream the warm-up ran on: the per-(device, stream) kernel workspaces (ops._workspace) the
+        # graph bakes in are then exactly the ones the warm-up sized, owned by this object's two streams
+        with torch.cuda.graph(self.graph, stream=side):
             self.scores, self.ids = self._step()
         self.launches_per_replay = ops.launch_count() - l0
         torch.cuda.synchronize(dev)
-        # the graph holds raw addresses of the per-stream kernel workspaces (ops._workspace) used while it was captured:
-        # keep them alive even if the cache later replaces them with bigger buffers for some other caller of that stream
+        # the graph holds raw addresses of those workspaces: keep them alive even if the cache later replaces them with
+        # bigger buffers for some other caller of the same stream
         streams = {side.cuda_stream, self._side.cuda_stream}
         self._keep_alive = [buf for key, buf in ops._ws_cache.items() if key[1] in streams]
+        self._capture_stream = side
 
     def _step(self):
         """One step on the current stream, with the query side (history CSR + user embed: a dozen small kernels that

@@ -158,6 +158,10 @@ def slsh_embed(feat, planes, n_buckets: int, oov_weight, ids, out=None, out_dtyp
     (single_lsh_embedder.py:82-109).  `oov_weight=None` computes bucket ids only."""
     feat, planes = _feat_planes(feat, planes)
     bits_req, F = planes.shape
+    if bits_req == 0:
+        # n_buckets == 1: ceil(log2(1)) = 0 planes, every id lands in bucket (0 + 0) % 1 = 0 like the reference
+        # (single_lsh_embedder.py:77-87); an empty tensor has a NULL data pointer, the C-ABI wants a valid one
+        planes = torch.zeros((1, F), dtype=torch.float32, device=feat.device)
     lib = _lib.load()
     buckets = None
     if oov_weight is None:
@@ -333,6 +337,12 @@ def gather_rows(table: torch.Tensor, idx, idx_offset: int = 0, out=None, out_dty
     n, D = idx.shape[0], table.shape[1]
     if out is None:
         out = torch.empty((n, D), dtype=table.dtype if out_dtype is None else _torch_dtype(out_dtype), device=table.device)
+    else:
+        _cuda(out, "out")
+        _dt(out)
+        if out.device != table.device or out.dim() != 2 or out.shape[0] != n or out.shape[1] != D or (D > 1 and out.stride(1) != 1):
+            raise ValueError(f"out must be [n={n}, D={D}] on {table.device} with unit inner stride "
+                             f"(got {tuple(out.shape)}, strides {out.stride()}, {out.device})")
     _lib.check(_lib.load().oov_gather_rows(_p(table), _dt(table), table.shape[0], D, _p(idx), stride, n, int(idx_offset),
                                            _p(out), _dt(out), out.stride(0) if n > 1 else D, _stream()))
     return out
@@ -454,22 +464,20 @@ def topk_hits(topk_idx: torch.Tensor, pos_rowptr: torch.Tensor, pos_cols: torch.
     return out
 
 
-CSR_MAX_Q, CSR_MAX_PAIRS = 8192, 1 << 20
-
-
 def pairs_to_csr(rows_idx: torch.Tensor, cols_idx: torch.Tensor, Q: int, col_ranges=None):
     """(row, item) index pairs (general_dataloader.py:270-292 history_index / positive_u,i) -> CSR
     (int32 rowptr [Q + 1], int32 cols ascending per row).  Rows outside [0, Q) are padding and are dropped; cols has
-    the length of the input and is only meaningful up to rowptr[Q].  One kernel, no host sync (graph-capturable).
+    the length of the input and is only meaningful up to rowptr[Q].  One kernel, no host sync (graph-capturable), any Q
+    and up to 2^31 - 1 pairs (ceil(Q / 512) CTAs, each streams the pair list).  CUDA tensors only.
 
     col_ranges = ((lo0, hi0), (lo1, hi1)): keep only items of these two id ranges and rewrite them as LOCAL rows of a
     shard table laid out [range 0 | range 1] (sharded.py)."""
     if rows_idx is None or rows_idx.numel() == 0:
-        dev = rows_idx.device if rows_idx is not None else "cuda"
+        dev = rows_idx.device if rows_idx is not None else torch.device("cuda")
+        if dev.type != "cuda":
+            raise RuntimeError("pairs_to_csr: index tensors must live on a CUDA device; oov_b200 has no CPU fallback")
         return torch.zeros(Q + 1, dtype=torch.int32, device=dev), torch.zeros(0, dtype=torch.int32, device=dev)
     n = rows_idx.numel()
-    if not rows_idx.is_cuda or Q > CSR_MAX_Q or n > CSR_MAX_PAIRS:          # host-side index plumbing (tests, gloo) or huge batches
-        return _pairs_to_csr_torch(rows_idx, cols_idx, Q, col_ranges)
     _cuda(rows_idx, "rows_idx", torch.int64)
     _cuda(cols_idx, "cols_idx", torch.int64)
     rows_idx, cols_idx = rows_idx.contiguous(), cols_idx.contiguous()
@@ -481,27 +489,6 @@ def pairs_to_csr(rows_idx: torch.Tensor, cols_idx: torch.Tensor, Q: int, col_ran
         cr = (C.c_int64 * 4)(int(a0), int(b0), int(a1), int(b1))
     _lib.check(_lib.load().oov_pairs_to_csr(_p(rows_idx), _p(cols_idx), n, Q, cr, _p(rowptr), _p(cols), _stream()))
     return rowptr, cols
-
-
-def _pairs_to_csr_torch(rows_idx: torch.Tensor, cols_idx: torch.Tensor, Q: int, col_ranges=None):
-    """Index plumbing with torch ops for batches beyond the kernel's limits and for CPU tensors (sync-free as well)."""
-    rows_idx = rows_idx.to(torch.int64)
-    cols_idx = cols_idx.to(torch.int64)
-    drop = (rows_idx < 0) | (rows_idx >= Q)
-    if col_ranges is not None:
-        (a0, b0), (a1, b1) = col_ranges
-        in0 = (cols_idx >= a0) & (cols_idx < b0)
-        in1 = (cols_idx >= a1) & (cols_idx < b1)
-        cols_idx = torch.where(in0, cols_idx - a0, cols_idx - a1 + (b0 - a0))
-        drop = drop | ~(in0 | in1)
-    rows_idx = torch.where(drop, torch.full_like(rows_idx, Q), rows_idx)
-    cols_idx = torch.where(drop, torch.zeros_like(cols_idx), cols_idx)
-    key = rows_idx * (1 << 32) + cols_idx
-    key, _ = torch.sort(key)
-    r = key >> 32
-    c = (key & 0xFFFFFFFF).to(torch.int32)
-    rowptr = torch.searchsorted(r, torch.arange(Q + 1, device=key.device, dtype=torch.int64))
-    return rowptr.to(torch.int32), c
 
 
 # ------------------------------------------------------------------------------------ context models

@@ -221,8 +221,8 @@ int oov_topk_hits(const int64_t* topk_idx, int64_t Q, int32_t k,
  * cols [n_pairs] int32 ascending within a row (duplicates kept).  Pairs whose row is outside [0, Q) are padding and
  * are dropped (cols_out past rowptr[Q] is left untouched).  col_ranges = {lo0, hi0, lo1, hi1} (host array, optional)
  * maps item ids to the LOCAL rows of a two-range row shard — [lo0, hi0) -> 0.., [lo1, hi1) -> (hi0 - lo0).. — and drops
- * every other item: the history of a shard that holds one slice of the in-vocab ids and one of the OOV ids.  One launch, asynchronous, no workspace: n_pairs <= 2^20,
- * 1 <= Q <= 8192. */
+ * every other item: the history of a shard that holds one slice of the in-vocab ids and one of the OOV ids.  One launch, asynchronous, no workspace:
+ * n_pairs < 2^31, 1 <= Q <= 2^24 (ceil(Q / 512) CTAs beyond 8192 rows, each streams the pair list). */
 int oov_pairs_to_csr(const int64_t* rows, const int64_t* cols, int64_t n_pairs, int64_t Q,
                      const int64_t* col_ranges /* HOST, 4 values or NULL */,
                      int32_t* rowptr_out, int32_t* cols_out, void* stream);

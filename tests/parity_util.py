@@ -121,3 +121,29 @@ def history_csr(hist_u: np.ndarray, hist_i: np.ndarray, q: int):
     np.add.at(rowptr, hu + 1, 1)
     rowptr = np.cumsum(rowptr)
     return rowptr.astype(np.int32), hi.astype(np.int32)
+
+
+def pairs_to_csr_host(rows_idx, cols_idx, Q, col_ranges=None):
+    """Host restatement (torch index ops, any device) of the contract of oov_pairs_to_csr / ops.pairs_to_csr — test
+    infrastructure: int32 rowptr [Q + 1], int32 cols ascending per row; rows outside [0, Q) are padding and dropped;
+    col_ranges = ((lo0, hi0), (lo1, hi1)) keeps the items of the two ranges and rewrites them to local shard rows."""
+    import torch
+    rows_idx = rows_idx.to(torch.int64)
+    cols_idx = cols_idx.to(torch.int64)
+    if rows_idx.numel() == 0:
+        return torch.zeros(Q + 1, dtype=torch.int32, device=rows_idx.device), torch.zeros(0, dtype=torch.int32, device=rows_idx.device)
+    drop = (rows_idx < 0) | (rows_idx >= Q)
+    if col_ranges is not None:
+        (a0, b0), (a1, b1) = col_ranges
+        in0 = (cols_idx >= a0) & (cols_idx < b0)
+        in1 = (cols_idx >= a1) & (cols_idx < b1)
+        cols_idx = torch.where(in0, cols_idx - a0, cols_idx - a1 + (b0 - a0))
+        drop = drop | ~(in0 | in1)
+    rows_idx = torch.where(drop, torch.full_like(rows_idx, Q), rows_idx)
+    cols_idx = torch.where(drop, torch.zeros_like(cols_idx), cols_idx)
+    key = rows_idx * (1 << 32) + cols_idx
+    key, _ = torch.sort(key)
+    r = key >> 32
+    c = (key & 0xFFFFFFFF).to(torch.int32)
+    rowptr = torch.searchsorted(r, torch.arange(Q + 1, device=key.device, dtype=torch.int64))
+    return rowptr.to(torch.int32), c

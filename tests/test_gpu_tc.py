@@ -215,7 +215,7 @@ def test_pairs_to_csr_kernel_matches_torch_path():
     from oov_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(3)
     for Q, n, hot in ((1024, 25_600, 0), (1, 50, 0), (300, 5000, 200), (4096, 100_000, 150), (7, 3, 0), (64, 30_000, 0),
-                      (8192, 51_200, 0)):
+                      (8192, 51_200, 0), (20_000, 300_000, 0), (65_536, 1_500_000, 90)):   # beyond 8192 rows / 2^20 pairs: more CTAs, same kernel
         rows = torch.randint(-2, Q + 3, (n,), generator=g)
         if hot:
             rows[: hot] = 5 % Q                                      # one long row
@@ -223,7 +223,7 @@ def test_pairs_to_csr_kernel_matches_torch_path():
         cols[: n // 10] = cols[n // 10: 2 * (n // 10)]              # duplicates
         for cr in (None, ((1000, 300_000), (500_000, 777_777)), ((0, 0), (999_000, 1_000_000))):
             rp_k, c_k = ops.pairs_to_csr(rows.to(DEV), cols.to(DEV), Q, col_ranges=cr)
-            rp_t, c_t = ops._pairs_to_csr_torch(rows.to(DEV), cols.to(DEV), Q, col_ranges=cr)
+            rp_t, c_t = pu.pairs_to_csr_host(rows.to(DEV), cols.to(DEV), Q, col_ranges=cr)
             assert torch.equal(rp_k, rp_t), (Q, n, cr)
             m = int(rp_t[-1])
             assert torch.equal(c_k[:m], c_t[:m]), (Q, n, cr)
@@ -435,3 +435,24 @@ def test_dhe_memoised_hash_planes_equal_hashing_every_call(tmp_path):
     H = case.n_hashes
     h = ops.dhe_hash(ids, emb._keys_dev).to(torch.int64)
     assert torch.equal((planes[:, :H] * 65536 + planes[:, H:2 * H] * 256 + planes[:, 2 * H:3 * H]).to(torch.int64), h)
+
+
+def test_slsh_single_bucket_and_gather_rows_out_validation():
+    """n_buckets == 1: ceil(log2(1)) = 0 planes, every OOV id takes bucket 0 (single_lsh_embedder.py:77-87).
+    gather_rows refuses an `out` of the wrong shape / stride / device instead of writing out of bounds."""
+    from oov_b200 import ops
+    feat = torch.randn(50, 6, device=DEV)
+    planes = torch.zeros((0, 6), device=DEV)
+    W = torch.randn(1, 8, device=DEV)
+    ids = torch.arange(10, 40, device=DEV)
+    out, buckets = ops.slsh_embed(feat, planes, 1, W, ids, return_buckets=True)
+    torch.cuda.synchronize()
+    assert (buckets == 0).all() and torch.equal(out, W.expand(30, 8))
+    table = torch.randn(20, 8, device=DEV)
+    idx = torch.arange(0, 20, 2, device=DEV)
+    good = torch.empty((10, 8), device=DEV)
+    assert torch.equal(ops.gather_rows(table, idx, out=good), table[idx])
+    for bad in (torch.empty((9, 8), device=DEV), torch.empty((10, 7), device=DEV), torch.empty((10, 16), device=DEV)[:, ::2],
+                torch.empty((10, 8))):
+        with pytest.raises((ValueError, RuntimeError)):
+            ops.gather_rows(table, idx, out=bad)

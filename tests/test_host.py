@@ -135,9 +135,11 @@ def test_pairs_to_csr():
     from oov_b200 import ops
     hu = torch.tensor([2, 0, 2, 2, 0])
     hi = torch.tensor([9, 4, 1, 5, 3])
-    rp, cols = ops.pairs_to_csr(hu, hi, 4)
+    rp, cols = pu.pairs_to_csr_host(hu, hi, 4)
     assert rp.tolist() == [0, 2, 2, 5, 5] and cols.tolist() == [3, 4, 1, 5, 9]
-    rp0, c0 = ops.pairs_to_csr(torch.zeros(0, dtype=torch.int64), torch.zeros(0, dtype=torch.int64), 3)
+    rp0, c0 = pu.pairs_to_csr_host(torch.zeros(0, dtype=torch.int64), torch.zeros(0, dtype=torch.int64), 3)
+    with pytest.raises(RuntimeError):                    # the product has no CPU path
+        ops.pairs_to_csr(hu, hi, 4)
     assert rp0.tolist() == [0, 0, 0, 0] and c0.numel() == 0
     w_rp, w_c = pu.history_csr(hu.numpy(), hi.numpy(), 4)
     assert rp.tolist() == w_rp.tolist() and cols.tolist() == w_c.tolist()
@@ -148,10 +150,10 @@ def test_pairs_to_csr_column_map_and_padding():
     from oov_b200 import ops
     hu = torch.tensor([2, 0, 2, 4, 2, 0, -1, 1])          # 4 and -1 are padding for Q = 4
     hi = torch.tensor([9, 4, 1, 7, 25, 3, 2, 30])
-    rp, cols = ops.pairs_to_csr(hu, hi, 4)
+    rp, cols = pu.pairs_to_csr_host(hu, hi, 4)
     assert rp.tolist() == [0, 2, 3, 6, 6] and cols[:6].tolist() == [3, 4, 30, 1, 9, 25]
     # shard = items [0, 5) and [20, 40): local rows 0..4 and 5..24; items 7, 9 belong to other ranks
-    rp, cols = ops.pairs_to_csr(hu, hi, 4, col_ranges=((0, 5), (20, 40)))
+    rp, cols = pu.pairs_to_csr_host(hu, hi, 4, col_ranges=((0, 5), (20, 40)))
     assert rp.tolist() == [0, 2, 3, 5, 5] and cols[:5].tolist() == [3, 4, 15, 1, 10]
 
 
@@ -192,7 +194,7 @@ def test_sharded_local_history_partitions_the_pairs(world):
     got = []
     for r in range(world):
         (lo0, hi0), (lo1, hi1) = sharded.shard_segments(n_old, n_total, r, world)
-        rp, cols = ops.pairs_to_csr(hu, hi, Q, col_ranges=((lo0, hi0), (lo1, hi1)))
+        rp, cols = pu.pairs_to_csr_host(hu, hi, Q, col_ranges=((lo0, hi0), (lo1, hi1)))
         n0 = hi0 - lo0
         for q in range(Q):
             row = cols[rp[q]:rp[q + 1]].tolist()
