@@ -331,6 +331,48 @@ __global__ void topk_hits_kernel(const int64_t* __restrict__ topk_idx, int64_t Q
     out[t] = sorted_contains(pos_cols, lo, hi, topk_idx[q * k + j]) ? 1 : 0;
 }
 
+// The seven collectors of inductive/evaluator.py:29-56 in one launch, one thread per (collector, user, column):
+//   c: 0 overall, 1 old_users, 2 new_users, 3 old_old, 4 old_new, 5 new_old, 6 new_new   (user filter x item filter)
+// out[c][q] = [hit flags of the collector's k-list | pos_len | keep].  keep = the row belongs to the collector's
+// 'rec.topk' (filtered_collector.py:32-62 keeps the users that pass the user filter and still own a positive).
+// The k-lists are the all / old-items-only / new-items-only top-k of ONE scoring pass (items are split at n_old_items).
+// compat = 1 reproduces two quirks of collector_filter.py: :172-175 picks the blanked item segment from
+// return_old_USERS instead of return_old_items, and :249-250 shifts new-item positives by -n_old_items while the
+// score columns stay global.
+__global__ void topk_hits_collectors_kernel(const int64_t* __restrict__ idx_all, const int64_t* __restrict__ idx_old,
+                                            const int64_t* __restrict__ idx_new, int64_t Q, int k,
+                                            const int64_t* __restrict__ user_ids, int64_t n_old_users, int64_t n_old_items,
+                                            const int32_t* __restrict__ pos_rowptr, const int32_t* __restrict__ pos_cols,
+                                            int compat, int32_t* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = k + 2;
+    if (t >= 7 * Q * w) return;
+    const int c = (int)(t / (Q * w));
+    const int64_t q = (t - (int64_t)c * Q * w) / w;
+    const int j = (int)(t - ((int64_t)c * Q + q) * w);
+    // user filter: -1 none, 1 old users, 0 new users; item filter likewise
+    const int ru = c == 0 ? -1 : (c == 1 || c == 3 || c == 4 ? 1 : 0);
+    const int ri = c <= 2 ? -1 : (c == 3 || c == 5 ? 1 : 0);
+    const int lo = pos_rowptr[q], hi = pos_rowptr[q + 1];
+    // the positives are ascending: [lo, mid) are old items, [mid, hi) new ones
+    int a = lo, b = hi;
+    while (a < b) { const int m = (a + b) >> 1; if ((int64_t)pos_cols[m] < n_old_items) a = m + 1; else b = m; }
+    const int mid = a;
+    const int plo = ri == 0 ? mid : lo, phi = ri == 1 ? mid : hi;            // considered positives
+    if (j == k) { out[t] = phi - plo; return; }                               // pos_len (collector.py:163)
+    if (j == k + 1) {
+        const bool old_user = user_ids[q] < n_old_users;
+        const bool user_ok = ru < 0 || (ru == 1) == old_user;
+        out[t] = (user_ok && (c == 0 || phi > plo)) ? 1 : 0;
+        return;
+    }
+    const int keep_old = compat ? ru : ri;                                    // which k-list the collector reads
+    const int64_t* list = ri < 0 ? idx_all : (keep_old == 1 ? idx_old : idx_new);
+    int64_t id = list[q * k + j];
+    if (id >= 0 && compat && ri == 0) id += n_old_items;                      // (positives shifted by -n_old_items)
+    out[t] = (id >= 0 && id <= 0x7fffffffll && sorted_contains(pos_cols, plo, phi, id)) ? 1 : 0;
+}
+
 // dense scores (the reference's materialised matrix) — one warp per 32 items x TQ users
 template <typename T, int TQ>
 __global__ void __launch_bounds__(FS_THREADS)
@@ -778,6 +820,19 @@ int oov_topk_hits(const int64_t* topk_idx, int64_t Q, int32_t k, const int32_t* 
     topk_hits_kernel<<<(unsigned)cdiv(Q * (k + 1), 256), 256, 0, (cudaStream_t)stream>>>(topk_idx, Q, k, pos_rowptr,
                                                                                         pos_cols, out_hits);
     OOV_LAUNCH_CHECK("topk_hits_kernel");
+    return OOV_OK;
+}
+
+int oov_topk_hits_collectors(const int64_t* idx_all, const int64_t* idx_old, const int64_t* idx_new, int64_t Q, int32_t k,
+                             const int64_t* user_ids, int64_t n_old_users, int64_t n_old_items, const int32_t* pos_rowptr,
+                             const int32_t* pos_cols, int32_t reference_compat, int32_t* out, void* stream) {
+    OOV_REQUIRE(Q >= 0 && k > 0, OOV_ERR_ARG, "oov_topk_hits_collectors: bad shape");
+    if (Q == 0) return OOV_OK;
+    OOV_REQUIRE(idx_all && idx_old && idx_new && user_ids && pos_rowptr && pos_cols && out, OOV_ERR_ARG,
+                "oov_topk_hits_collectors: NULL pointer");
+    topk_hits_collectors_kernel<<<(unsigned)cdiv(7 * Q * (k + 2), 256), 256, 0, (cudaStream_t)stream>>>(
+        idx_all, idx_old, idx_new, Q, k, user_ids, n_old_users, n_old_items, pos_rowptr, pos_cols, reference_compat ? 1 : 0, out);
+    OOV_LAUNCH_CHECK("topk_hits_collectors_kernel");
     return OOV_OK;
 }
 

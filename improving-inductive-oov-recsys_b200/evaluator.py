@@ -3,15 +3,18 @@
 (Collector.eval_batch_collect, 'rec.topk') and inductive/filtered_collector.py:18-80 +
 collector_filter.py:128-256 (the six old/new user x old/new item collectors).
 
-The reference materialises scores [Q, N], masks them in place and runs torch.topk up to 7 times per
-batch.  Here one fused kernel pass per item segment (all / old / new) yields top-k ids directly and
-the hit matrix [hits | pos_len] is built from CSR positives — three passes serve all seven
-collectors, and each collector sees un-aliased scores (the reference's in-place `-inf` writes leak
-from one filtered collector into the next, collector_filter.py:172-175).
+The reference materialises scores [Q, N], masks them in place and runs torch.topk up to 7 times per batch.  Here ONE
+scoring pass over the items — split at n_old_items into two fused launches, so every item is scored once — yields the
+old-items-only and new-items-only top-k lists, their merge is the all-items list, and one kernel turns the three lists
+and the CSR positives into the [hits | pos_len | keep] rows of all seven collectors.  Nothing in `eval_batch`
+synchronises with the host (no boolean-mask indexing, no unique, no per-collector .cpu()): results stay on the device
+until they are read, and `evaluate_model` copies them to the host once.  Each collector sees un-aliased scores (the
+reference's in-place `-inf` writes leak from one filtered collector into the next, collector_filter.py:172-175;
+SURVEY §8f row 1).
 """
 from __future__ import annotations
 
-from typing import Dict, Optional, Sequence
+from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 import torch
@@ -29,19 +32,21 @@ COLLECTORS = {          # name -> (return_old_users, return_old_items); None = n
 
 class Collector:
     """Accumulates 'rec.topk' rows; `eval_batch_collect` keeps the reference signature for callers
-    that still hold a dense score matrix (collector.py:137-167)."""
+    that still hold a dense score matrix (collector.py:137-167).  Rows stay on the device until
+    `get_data_struct()` is called (one host copy for all batches)."""
 
     def __init__(self, config):
         self.config = config
         self.topk = list(config["topk"])
         self.k = max(self.topk)
-        self._rows = []
+        self._rows: List[torch.Tensor] = []          # host rows already materialised
+        self._pending: List = []                     # callables returning device/host rows, resolved on read
 
     def collect_topk(self, topk_idx: torch.Tensor, positive_u: torch.Tensor, positive_i: torch.Tensor) -> torch.Tensor:
         Q = topk_idx.shape[0]
         rowptr, cols = ops.pairs_to_csr(positive_u.to(topk_idx.device), positive_i.to(topk_idx.device), Q)
         res = ops.topk_hits(topk_idx, rowptr, cols)
-        self._rows.append(res.cpu())                         # collector.py:44-52: results leave the GPU per batch
+        self._pending.append(lambda r=res: r)
         return res
 
     def eval_batch_collect(self, scores_tensor: torch.Tensor, interaction, positive_u, positive_i):
@@ -50,7 +55,43 @@ class Collector:
         return self.collect_topk(topk_idx, positive_u, positive_i)
 
     def get_data_struct(self) -> Dict[str, torch.Tensor]:
+        for fn in self._pending:
+            r = fn()
+            if r is not None and r.shape[0]:
+                self._rows.append(r.cpu())
+        self._pending = []
         return {"rec.topk": torch.cat(self._rows, dim=0) if self._rows else torch.zeros((0, self.k + 1), dtype=torch.int32)}
+
+
+class BatchResult:
+    """`{collector name: 'rec.topk' rows of this batch}` — read lazily: the first access copies the batch's
+    [7, Q, k + 2] result tensor to the host (the only synchronisation) and splits it by the `keep` column.  A collector
+    without rows is absent, like a reference FilteredCollector that returns early (filtered_collector.py:34-35)."""
+
+    def __init__(self, dev_rows: torch.Tensor):
+        self.device_rows = dev_rows                  # int32 [7, Q, k + 2]: hits | pos_len | keep
+        self._host: Optional[Dict[str, torch.Tensor]] = None
+
+    def _materialise(self) -> Dict[str, torch.Tensor]:
+        if self._host is None:
+            rows = self.device_rows.cpu()
+            out = {}
+            for c, name in enumerate(COLLECTORS):
+                keep = rows[c, :, -1] != 0
+                if name == "overall" or bool(keep.any()):
+                    out[name] = rows[c][keep][:, :-1].contiguous()
+            self._host = out
+        return self._host
+
+    def rows_of(self, name: str) -> Optional[torch.Tensor]:
+        return self._materialise().get(name)
+
+    def __contains__(self, name): return name in self._materialise()
+    def __getitem__(self, name): return self._materialise()[name]
+    def __iter__(self): return iter(self._materialise())
+    def keys(self): return self._materialise().keys()
+    def items(self): return self._materialise().items()
+    def __len__(self): return len(self._materialise())
 
 
 def topk_metrics(rec_topk: np.ndarray, topk: Sequence[int]) -> Dict[str, float]:
@@ -80,9 +121,18 @@ def topk_metrics(rec_topk: np.ndarray, topk: Sequence[int]) -> Dict[str, float]:
 
 
 class InductiveEvaluator:
-    """Drop-in for reference inductive/evaluator.py: same constructor, `eval_batch`, `evaluate_model`."""
+    """Drop-in for reference inductive/evaluator.py: same constructor, `eval_batch`, `evaluate_model`.
 
-    def __init__(self, model, config, n_old_users, n_old_items, feature_extractor=None, reference_compat=True):
+    reference_compat=False (default): a collector with an item filter reads the k-list of ITS item segment
+    (return_old_items) and hits are compared in global item ids.
+    reference_compat=True reproduces two quirks of collector_filter.py bit for bit (opt-in; the golden fixtures of the
+    reference's FilteredCollector are checked in this mode):
+      * :172-175 picks the masked item segment from `return_old_USERS` (old users -> new items blanked, new users ->
+        old items blanked), whatever `return_old_items` says;
+      * :249-250 shifts new-item positives by -n_old_items while the score columns stay global.
+    It does not reproduce the in-place -inf leak from one collector into the next (each collector sees clean scores)."""
+
+    def __init__(self, model, config, n_old_users, n_old_items, feature_extractor=None, reference_compat=False):
         self.model = model
         self.config = config
         self.device = model.device
@@ -94,15 +144,12 @@ class InductiveEvaluator:
         self.collectors = {name: Collector(config) for name in COLLECTORS}
         self.tot_item_num: Optional[int] = None
         self.item_range = None
-        # reference_compat=True reproduces two quirks of collector_filter.py bit for bit:
-        #   * :172-175 picks the masked item segment from `return_old_USERS` (old users -> new items blanked,
-        #     new users -> old items blanked), whatever `return_old_items` says;
-        #   * :249-250 shifts new-item positives by -n_old_items while the score columns stay global.
-        # reference_compat=False masks by `return_old_items` and compares in global ids.
         self.reference_compat = reference_compat
 
-    def eval_batch(self, batched_data, item_table: Optional[torch.Tensor] = None):
-        """(interaction, history_index, positive_u, positive_i) -> {collector: 'rec.topk' rows of this batch}."""
+    def eval_batch(self, batched_data, item_table: Optional[torch.Tensor] = None) -> BatchResult:
+        """(interaction, history_index, positive_u, positive_i) -> {collector: 'rec.topk' rows of this batch} (lazy).
+        Launches: two CSR builds, the user embed, two fused score + mask + top-k launches that together visit every item
+        once (old items, new items), one merge, one 7-collector hits kernel.  No host synchronisation."""
         interaction, history_index, positive_u, positive_i = batched_data
         users = interaction[self.USER_ID].to(self.device)
         Q = users.shape[0]
@@ -111,33 +158,19 @@ class InductiveEvaluator:
             hist = ops.pairs_to_csr(history_index[0].to(self.device), history_index[1].to(self.device), Q)
         if item_table is None:
             item_table = self.model.build_item_table(self.tot_item_num)
-        positive_u, positive_i = positive_u.to(self.device), positive_i.to(self.device)
-        passes = {}
-        for seg_name, seg in (("all", (0, INT64_MAX)), ("old", (0, self.n_old_items)), ("new", (self.n_old_items, INT64_MAX))):
-            passes[seg_name] = self.model.full_sort_topk(users, self.k, item_table=item_table, hist_csr=hist, seg=seg)[1]
-        old_user_rows = users < self.n_old_users
-        results = {}
-        for name, (ru, ri) in COLLECTORS.items():
-            keep_old_segment = ru if self.reference_compat else ri
-            idx = passes["all" if ri is None else ("old" if keep_old_segment else "new")]
-            pmask = torch.ones_like(positive_u, dtype=torch.bool)
-            if ri is not None:
-                pmask &= (positive_i < self.n_old_items) if ri else (positive_i >= self.n_old_items)
-            if ru is not None:
-                pmask &= old_user_rows[positive_u] if ru else ~old_user_rows[positive_u]
-            pu, pi = positive_u[pmask], positive_i[pmask]
-            if name != "overall":
-                if pu.numel() == 0:
-                    continue                                   # filtered_collector.py:34-35
-                keep = torch.unique(pu, sorted=True)           # rows = users that still own a positive
-                remap = torch.full((Q,), -1, dtype=torch.int64, device=self.device)
-                remap[keep] = torch.arange(keep.numel(), device=self.device)
-                pu = remap[pu]
-                idx = idx[keep]
-                if ri is False and self.reference_compat:
-                    pi = pi - self.n_old_items
-            results[name] = self.collectors[name].collect_topk(idx, pu, pi)
-        return results
+        m = self.model
+        user_e = m._assemble("user", users, out_dtype=m.table_dtype)
+        s_old, i_old = ops.fullsort_topk(user_e, item_table, self.k, mask_pad=True, seg=(0, self.n_old_items), hist=hist)
+        s_new, i_new = ops.fullsort_topk(user_e, item_table, self.k, mask_pad=True, seg=(self.n_old_items, INT64_MAX), hist=hist)
+        # the two segments partition the items, so the all-items list is the merge of their lists (same total order)
+        _, i_all = ops.topk_merge(torch.stack([s_old, s_new]), torch.stack([i_old, i_new]))
+        rowptr, cols = ops.pairs_to_csr(positive_u.to(self.device), positive_i.to(self.device), Q)
+        rows = ops.topk_hits_collectors(i_all, i_old, i_new, users, self.n_old_users, self.n_old_items, rowptr, cols,
+                                        reference_compat=self.reference_compat)
+        res = BatchResult(rows)
+        for name in COLLECTORS:
+            self.collectors[name]._pending.append(lambda r=res, n=name: r.rows_of(n))
+        return res
 
     def evaluate_model(self, eval_data, config=None, show_progress=False, inductive=True, n_total_items=None):
         self.model.eval()

@@ -464,6 +464,27 @@ def topk_hits(topk_idx: torch.Tensor, pos_rowptr: torch.Tensor, pos_cols: torch.
     return out
 
 
+def topk_hits_collectors(idx_all, idx_old, idx_new, user_ids, n_old_users: int, n_old_items: int, pos_rowptr, pos_cols,
+                         reference_compat: bool = False) -> torch.Tensor:
+    """int32 [7, Q, k + 2] = hits | pos_len | keep for the seven collectors of inductive/evaluator.py:29-56 (order of
+    evaluator.COLLECTORS) from the all / old-items / new-items k-lists of one scoring pass.  No host sync."""
+    for t, nm in ((idx_all, "idx_all"), (idx_old, "idx_old"), (idx_new, "idx_new"), (user_ids, "user_ids")):
+        _cuda(t, nm, torch.int64)
+    _cuda(pos_rowptr, "pos_rowptr", torch.int32)
+    _cuda(pos_cols, "pos_cols", torch.int32)
+    idx_all, idx_old, idx_new, user_ids = idx_all.contiguous(), idx_old.contiguous(), idx_new.contiguous(), user_ids.contiguous()
+    Q, k = idx_all.shape
+    if idx_old.shape != (Q, k) or idx_new.shape != (Q, k) or user_ids.shape != (Q,) or pos_rowptr.numel() != Q + 1:
+        raise ValueError("topk_hits_collectors: the three lists must be [Q, k], user_ids [Q], pos_rowptr [Q + 1]")
+    if pos_cols.numel() == 0:
+        pos_cols = torch.zeros(1, dtype=torch.int32, device=idx_all.device)
+    out = torch.empty((7, Q, k + 2), dtype=torch.int32, device=idx_all.device)
+    _lib.check(_lib.load().oov_topk_hits_collectors(_p(idx_all), _p(idx_old), _p(idx_new), Q, k, _p(user_ids), int(n_old_users),
+                                                    int(n_old_items), _p(pos_rowptr.contiguous()), _p(pos_cols.contiguous()),
+                                                    int(bool(reference_compat)), _p(out), _stream()))
+    return out
+
+
 def pairs_to_csr(rows_idx: torch.Tensor, cols_idx: torch.Tensor, Q: int, col_ranges=None):
     """(row, item) index pairs (general_dataloader.py:270-292 history_index / positive_u,i) -> CSR
     (int32 rowptr [Q + 1], int32 cols ascending per row).  Rows outside [0, Q) are padding and are dropped; cols has

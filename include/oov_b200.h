@@ -216,6 +216,21 @@ int oov_topk_hits(const int64_t* topk_idx, int64_t Q, int32_t k,
                   const int32_t* pos_rowptr, const int32_t* pos_cols,
                   int32_t* out_hits /* [Q, k+1] */, void* stream);
 
+/* The seven collectors of inductive/evaluator.py:29-56 (overall, old_users, new_users, old_old, old_new, new_old,
+ * new_new — in this order) from the three k-lists of ONE scoring pass over items split at n_old_items (all / old items
+ * only / new items only; the "all" list is the merge of the other two).  Replaces collector_filter.py:128-256 +
+ * filtered_collector.py:18-80 (seven masked copies of the score matrix, seven top-k) without boolean indexing or host
+ * synchronisation: out [7, Q, k + 2] int32 = hit flags of the collector's list | pos_len | keep, where keep = 1 marks
+ * the rows the reference's collector would hold (users passing the user filter that own a positive after the item
+ * filter; every user for "overall").  user_ids [Q]; positives as in oov_topk_hits.  reference_compat = 1 reproduces two
+ * quirks of collector_filter.py (:172-175 blanks the item segment chosen by return_old_USERS; :249-250 shifts new-item
+ * positives by -n_old_items while score columns stay global); 0 filters by return_old_items and compares global ids. */
+int oov_topk_hits_collectors(const int64_t* idx_all, const int64_t* idx_old, const int64_t* idx_new,
+                             int64_t Q, int32_t k, const int64_t* user_ids,
+                             int64_t n_old_users, int64_t n_old_items,
+                             const int32_t* pos_rowptr, const int32_t* pos_cols,
+                             int32_t reference_compat, int32_t* out, void* stream);
+
 /* (row, item) index pairs — the `history_index` / `positive_u, positive_i` tensors FullSortEvalDataLoader.collate_fn
  * yields (data/dataloader/general_dataloader.py:270-292) — to the CSR the kernels above read: rowptr [Q + 1] int32,
  * cols [n_pairs] int32 ascending within a row (duplicates kept).  Pairs whose row is outside [0, Q) are padding and

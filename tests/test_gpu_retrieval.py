@@ -135,18 +135,28 @@ def test_retrieval_fp32(name, G):
 
 @pytest.mark.parametrize("name", ["bpr_lsh_ml100k", "directau_slsh", "bpr_mean"])
 def test_inductive_evaluator_collectors(name, G):
-    """The 7 collectors of inductive/evaluator.py:39-56 from 3 fused passes vs the reference's
-    FilteredCollector outputs (each fed un-aliased scores)."""
+    """The 7 collectors of inductive/evaluator.py:39-56 from ONE scoring pass (old-items + new-items launches, merged for
+    the all-items list) and one hits kernel, vs the reference's FilteredCollector outputs (each fed un-aliased scores),
+    in reference_compat mode; eval_batch runs under torch's sync-debug mode: no host synchronisation."""
     import oov_b200
     case = cases.CASES[name]
     inp = cases.retrieval_inputs(case)
     g = pu.load_golden(name)
     ora = pu.oracle_retrieval(case, inp)
     cfg, emb, model = G.build_retrieval(case, inp)
-    ev = oov_b200.InductiveEvaluator(model, cfg, case.n_old_users, case.n_old_items)
+    ev = oov_b200.InductiveEvaluator(model, cfg, case.n_old_users, case.n_old_items, reference_compat=True)
     ev.tot_item_num = case.n_all_items
     batch = ({"user_id": G.t(inp["users"])}, (G.t(inp["hist_u"]), G.t(inp["hist_i"])), G.t(inp["pos_u"]), G.t(inp["pos_i"]))
-    res = ev.eval_batch(batch)
+    table = model.build_item_table(case.n_all_items)
+    ev.eval_batch(batch, item_table=table)                     # warm-up: workspaces, lazy initialisation
+    ev = oov_b200.InductiveEvaluator(model, cfg, case.n_old_users, case.n_old_items, reference_compat=True)
+    ev.tot_item_num = case.n_all_items
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")                    # eval_batch must not synchronise with the host
+    try:
+        res = ev.eval_batch(batch, item_table=table)
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
     scale = float(np.abs(ora["scores_raw"][np.isfinite(ora["scores_raw"])]).max())
     for cname in oov_b200.evaluator.COLLECTORS:
         key = f"collector_{cname}"
@@ -240,3 +250,49 @@ def test_empty_and_error_behaviour(G):
     # fewer items than k: tail is (-inf, -1)
     s, i = ops.fullsort_topk(torch.randn(4, 32, device=G.DEV), torch.randn(3, 32, device=G.DEV), 5, mask_pad=False)
     assert (i[:, 3:] == -1).all() and torch.isinf(s[:, 3:]).all() and (i[:, :3] >= 0).all()
+
+
+@pytest.mark.parametrize("name", ["bpr_lsh_ml100k", "directau_slsh"])
+def test_inductive_evaluator_default_mode_vs_oracle(name, G):
+    """reference_compat=False (the default): a collector with an item filter ranks ITS item segment and hits are compared
+    in global ids.  Expected rows from the oracle's masked scores: segment mask by return_old_items, top-k, hit flags
+    against the item-filtered positives, rows = users passing the user filter that own such a positive.  Also checks that
+    the accumulated collectors return the same rows (one host copy at read time)."""
+    import oov_b200
+    case = cases.CASES[name]
+    inp = cases.retrieval_inputs(case)
+    ora = pu.oracle_retrieval(case, inp)
+    cfg, emb, model = G.build_retrieval(case, inp)
+    ev = oov_b200.InductiveEvaluator(model, cfg, case.n_old_users, case.n_old_items)
+    assert ev.reference_compat is False
+    ev.tot_item_num = case.n_all_items
+    batch = ({"user_id": G.t(inp["users"])}, (G.t(inp["hist_u"]), G.t(inp["hist_i"])), G.t(inp["pos_u"]), G.t(inp["pos_i"]))
+    res = ev.eval_batch(batch)
+    scale = float(np.abs(ora["scores_raw"][np.isfinite(ora["scores_raw"])]).max())
+    users, pos_u, pos_i = inp["users"], inp["pos_u"], inp["pos_i"]
+    old_user = users < case.n_old_users
+    for cname, (ru, ri) in oov_b200.evaluator.COLLECTORS.items():
+        seg = o.segment_mask(ora["scores_masked"], case.n_old_items, ri)
+        pm = np.ones_like(pos_u, dtype=bool)
+        if ri is not None:
+            pm &= (pos_i < case.n_old_items) if ri else (pos_i >= case.n_old_items)
+        urow = np.ones(case.Q, dtype=bool) if ru is None else (old_user if ru else ~old_user)
+        pos_len = np.bincount(pos_u[pm], minlength=case.Q)
+        rows = np.nonzero(urow & ((pos_len > 0) | (cname == "overall")))[0]
+        if cname != "overall" and rows.size == 0:
+            assert cname not in res
+            continue
+        got = res[cname].cpu().numpy()
+        assert got.shape == (rows.size, case.k + 1), (cname, got.shape, rows.size)
+        assert (got[:, -1] == pos_len[rows]).all(), cname
+        srt = -np.sort(-o.order_key(seg[rows]), axis=1)
+        with np.errstate(invalid="ignore"):
+            clear = (srt[:, case.k - 1] - srt[:, case.k]) > 1e-5 * scale
+        _, idx = o.topk(seg[rows], case.k)
+        pos_set = set(zip(pos_u[pm].tolist(), pos_i[pm].tolist()))
+        want = np.array([[1 if (int(u), int(i)) in pos_set else 0 for i in idx[r]] for r, u in enumerate(rows)], dtype=np.int32)
+        finite = np.isfinite(np.take_along_axis(seg[rows], idx, axis=1))
+        want = np.where(finite, want, 0)                        # -inf slots (fewer than k candidates) are empty: no hit
+        assert (got[clear][:, :-1] == want[clear]).all(), cname
+        acc = ev.collectors[cname].get_data_struct()["rec.topk"].numpy()
+        assert (acc == got).all(), cname
