@@ -66,6 +66,9 @@ SIGNATURES = {
                                     c_vp, c_i64, c_vp]),
     "oov_dense_topk": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "oov_topk_merge": (c_i32, [c_vp, c_vp, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp]),
+    "oov_fullsort_topk_keys": (c_i32, [c_vp, c_vp, c_i32, c_i64, c_i64, c_i32, c_i32, c_i32, c_i64, c_i64, c_vp, c_vp,
+                                       c_i64, c_i64, c_i64, c_vp, c_vp, c_sz, c_i32, c_vp]),
+    "oov_topk_merge_keys": (c_i32, [c_vp, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "oov_topk_hits": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "oov_topk_hits_collectors": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp]),
     "oov_pairs_to_csr": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),

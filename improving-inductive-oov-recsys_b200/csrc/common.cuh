@@ -121,6 +121,12 @@ __host__ __device__ __forceinline__ float float_from_order_key(uint32_t k) {
     return f;
 #endif
 }
+// Optional output mode of the final per-user merge: packed 8-byte candidates in GLOBAL item ids instead of (score, id)
+// arrays — what a row shard laid out [ids lo0.. (n0 rows) | ids lo1..] sends to the other ranks (sharded.py).
+struct KeyOut {
+    unsigned long long* keys = nullptr;     // [Q, k]; nullptr: write out_scores / out_idx
+    int64_t n0 = 0, lo0 = 0, lo1 = 0;       // local row r -> r < n0 ? lo0 + r : lo1 + (r - n0)
+};
 __device__ __forceinline__ unsigned long long make_key64(float score, uint32_t local_idx) {
     return ((unsigned long long)float_order_key(score) << 32) | (unsigned long long)(~local_idx);
 }

@@ -42,7 +42,7 @@
 namespace oov {
 
 int launch_merge_keys(const unsigned long long* partial, const uint8_t* partial_n, int P, int64_t Q, int k, int64_t off,
-                      float* out_scores, int64_t* out_idx, cudaStream_t st);
+                      float* out_scores, int64_t* out_idx, cudaStream_t st, const KeyOut ko);
 
 namespace tc {
 
@@ -723,7 +723,7 @@ size_t score_tc_workspace(int64_t Q, int64_t N, int k) {
 
 int score_tc_run(const void* users, const void* items, int64_t Q, int64_t N, int D, int k, int64_t item_id_offset,
                  int mask_pad, int64_t seg_lo, int64_t seg_hi, const int32_t* hist_rowptr, const int32_t* hist_cols,
-                 float* out_scores, int64_t* out_idx, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                 float* out_scores, int64_t* out_idx, void* workspace, size_t workspace_bytes, cudaStream_t st, const KeyOut ko) {
     // only item tiles that intersect the kept segment are visited
     int64_t lo = seg_lo - item_id_offset, hi = seg_hi > item_id_offset + N ? N : seg_hi - item_id_offset;
     if (lo < 0) lo = 0;
@@ -795,7 +795,7 @@ int score_tc_run(const void* users, const void* items, int64_t Q, int64_t N, int
     }
     tc_score_topk_kernel<0><<<grid, SC_THREADS, smem, st>>>(tmU, tmI, p);
     OOV_LAUNCH_CHECK("tc_score_topk_kernel");
-    return launch_merge_keys(p.partial, p.partial_n, gx, Q, k, item_id_offset, out_scores, out_idx, st);
+    return launch_merge_keys(p.partial, p.partial_n, gx, Q, k, item_id_offset, out_scores, out_idx, st, ko);
 }
 
 }  // namespace tc

@@ -206,7 +206,7 @@ fullsort_topk_simt(const T* __restrict__ users, const T* __restrict__ items, int
 template <int KR>
 __global__ void __launch_bounds__(256)
 merge_keys_kernel(const unsigned long long* __restrict__ partial, const uint8_t* __restrict__ partial_n, int P, int64_t Q, int k,
-                  int64_t item_id_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+                  int64_t item_id_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_idx, const KeyOut ko) {
     const int lane = threadIdx.x & 31;
     const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= Q) return;
@@ -274,8 +274,15 @@ merge_keys_kernel(const unsigned long long* __restrict__ partial, const uint8_t*
         const int j = r * 32 + lane;
         if (j < k) {
             const unsigned long long key = fin.e[r];
-            out_scores[q * k + j] = key ? key64_score(key) : -INFINITY;
-            out_idx[q * k + j] = key ? (int64_t)key64_idx(key) + item_id_offset : -1;
+            if (ko.keys != nullptr) {
+                // packed candidate in global ids (score bits unchanged): 8 bytes per entry for the shard exchange
+                const int64_t row = (int64_t)key64_idx(key);
+                const int64_t gid = row < ko.n0 ? ko.lo0 + row : ko.lo1 + (row - ko.n0);
+                ko.keys[q * k + j] = key ? ((key & 0xFFFFFFFF00000000ull) | (unsigned long long)(~(uint32_t)gid)) : 0ull;
+            } else {
+                out_scores[q * k + j] = key ? key64_score(key) : -INFINITY;
+                out_idx[q * k + j] = key ? (int64_t)key64_idx(key) + item_id_offset : -1;
+            }
         }
     }
 }
@@ -507,7 +514,7 @@ template <typename T>
 static int launch_fullsort_simt(const T* users, const T* items, int64_t Q, int64_t N, int D, int k,
                                 int64_t off, int mask_pad, int64_t seg_lo, int64_t seg_hi,
                                 const int32_t* hr, const int32_t* hc, float* out_scores, int64_t* out_idx,
-                                unsigned long long* partial, int P, cudaStream_t st) {
+                                unsigned long long* partial, int P, cudaStream_t st, const KeyOut ko = KeyOut{}) {
     const TopkCfg c = topk_cfg(k);
     const dim3 grid((unsigned)P, (unsigned)cdiv(Q, c.TQ));
     const size_t smem = (size_t)c.TQ * D * 4 + (size_t)FS_WARPS * c.TQ * c.KR * 32 * 8;
@@ -517,7 +524,7 @@ static int launch_fullsort_simt(const T* users, const T* items, int64_t Q, int64
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
         kern<<<grid, FS_THREADS, smem, st>>>(users, items, Q, N, D, k, off, mask_pad, seg_lo, seg_hi, hr, hc, partial); \
         OOV_LAUNCH_CHECK("fullsort_topk_simt");                                                                       \
-        merge_keys_kernel<KR_><<<(unsigned)cdiv(Q * 32, 256), 256, 0, st>>>(partial, nullptr, P, Q, k, off, out_scores, out_idx); \
+        merge_keys_kernel<KR_><<<(unsigned)cdiv(Q * 32, 256), 256, 0, st>>>(partial, nullptr, P, Q, k, off, out_scores, out_idx, ko); \
         OOV_LAUNCH_CHECK("merge_keys_kernel");                                                                        \
     }
     if (c.KR == 1) OOV_FS_CASE(16, 1)
@@ -658,11 +665,11 @@ pairs_to_csr_kernel(const int64_t* __restrict__ rows, const int64_t* __restrict_
 
 // shared with the tcgen05 scoring kernel (tc_score.cu): merge P partial key lists per user
 int launch_merge_keys(const unsigned long long* partial, const uint8_t* partial_n, int P, int64_t Q, int k, int64_t off,
-                      float* out_scores, int64_t* out_idx, cudaStream_t st) {
+                      float* out_scores, int64_t* out_idx, cudaStream_t st, const KeyOut ko) {
     const unsigned blocks = (unsigned)cdiv(Q * 32, 256);
-    if (k <= 32) merge_keys_kernel<1><<<blocks, 256, 0, st>>>(partial, partial_n, P, Q, k, off, out_scores, out_idx);
-    else if (k <= 64) merge_keys_kernel<2><<<blocks, 256, 0, st>>>(partial, partial_n, P, Q, k, off, out_scores, out_idx);
-    else merge_keys_kernel<4><<<blocks, 256, 0, st>>>(partial, partial_n, P, Q, k, off, out_scores, out_idx);
+    if (k <= 32) merge_keys_kernel<1><<<blocks, 256, 0, st>>>(partial, partial_n, P, Q, k, off, out_scores, out_idx, ko);
+    else if (k <= 64) merge_keys_kernel<2><<<blocks, 256, 0, st>>>(partial, partial_n, P, Q, k, off, out_scores, out_idx, ko);
+    else merge_keys_kernel<4><<<blocks, 256, 0, st>>>(partial, partial_n, P, Q, k, off, out_scores, out_idx, ko);
     OOV_LAUNCH_CHECK("merge_keys_kernel");
     return OOV_OK;
 }
@@ -672,7 +679,8 @@ bool score_tc_supported(int dtype, int D, int k);
 size_t score_tc_workspace(int64_t Q, int64_t N, int k);
 int score_tc_run(const void* users, const void* items, int64_t Q, int64_t N, int D, int k, int64_t item_id_offset,
                  int mask_pad, int64_t seg_lo, int64_t seg_hi, const int32_t* hist_rowptr, const int32_t* hist_cols,
-                 float* out_scores, int64_t* out_idx, void* workspace, size_t workspace_bytes, cudaStream_t st);
+                 float* out_scores, int64_t* out_idx, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                 const KeyOut ko = KeyOut{});
 }  // namespace tc
 
 }  // namespace oov
@@ -715,10 +723,10 @@ int oov_pairs_to_csr(const int64_t* rows, const int64_t* cols, int64_t n_pairs, 
     return OOV_OK;
 }
 
-int oov_fullsort_topk(const void* users, const void* items, int32_t dtype, int64_t Q, int64_t N, int32_t D, int32_t k,
-                      int64_t item_id_offset, int32_t mask_pad, int64_t seg_lo, int64_t seg_hi,
-                      const int32_t* hist_rowptr, const int32_t* hist_cols, float* out_scores, int64_t* out_idx,
-                      void* workspace, size_t workspace_bytes, int32_t path, void* stream) {
+static int fullsort_topk_impl(const void* users, const void* items, int32_t dtype, int64_t Q, int64_t N, int32_t D, int32_t k,
+                              int64_t item_id_offset, int32_t mask_pad, int64_t seg_lo, int64_t seg_hi,
+                              const int32_t* hist_rowptr, const int32_t* hist_cols, float* out_scores, int64_t* out_idx,
+                              void* workspace, size_t workspace_bytes, int32_t path, void* stream, const KeyOut ko) {
     OOV_REQUIRE(dtype_ok(dtype), OOV_ERR_ARG, "oov_fullsort_topk: bad dtype %d", dtype);
     OOV_REQUIRE(Q >= 0 && N >= 0 && D > 0 && k > 0 && k <= 128, OOV_ERR_ARG,
                 "oov_fullsort_topk: bad shape Q=%lld N=%lld D=%d k=%d (k <= 128)", (long long)Q, (long long)N, D, k);
@@ -727,7 +735,7 @@ int oov_fullsort_topk(const void* users, const void* items, int32_t dtype, int64
     OOV_REQUIRE((hist_rowptr == nullptr) == (hist_cols == nullptr), OOV_ERR_ARG, "oov_fullsort_topk: rowptr/cols mismatch");
     OOV_REQUIRE(path >= OOV_PATH_AUTO && path <= OOV_PATH_TCGEN05, OOV_ERR_ARG, "oov_fullsort_topk: unsupported path %d", path);
     if (Q == 0) return OOV_OK;
-    OOV_REQUIRE(users && out_scores && out_idx && (N == 0 || items), OOV_ERR_ARG, "oov_fullsort_topk: NULL pointer");
+    OOV_REQUIRE(users && ((out_scores && out_idx) || ko.keys) && (N == 0 || items), OOV_ERR_ARG, "oov_fullsort_topk: NULL pointer");
     OOV_REQUIRE(aligned(users, 16) && aligned(items, 16), OOV_ERR_ALIGN, "oov_fullsort_topk: tables must be 16-byte aligned");
     // bf16 tables take the tensor-core path (tcgen05 GEMM fused with the top-k epilogue); fp32 tables the fp32 FMA path
     const bool tc_ok = tc::score_tc_supported(dtype, D, k) && N >= 1;
@@ -735,7 +743,7 @@ int oov_fullsort_topk(const void* users, const void* items, int32_t dtype, int64
                 "oov_fullsort_topk: tcgen05 path needs bf16 tables, D <= 64 (multiple of 8) and k <= 24");
     if (tc_ok && path != OOV_PATH_SIMT_FP32)
         return tc::score_tc_run(users, items, Q, N, D, k, item_id_offset, mask_pad, seg_lo, seg_hi, hist_rowptr, hist_cols,
-                                out_scores, out_idx, workspace, workspace_bytes, (cudaStream_t)stream);
+                                out_scores, out_idx, workspace, workspace_bytes, (cudaStream_t)stream, ko);
     const TopkCfg c = topk_cfg(k);
     const int P = pick_item_ctas(N > 0 ? N : 1, cdiv(Q, c.TQ));
     const size_t need = (size_t)P * Q * k * 8;
@@ -745,10 +753,40 @@ int oov_fullsort_topk(const void* users, const void* items, int32_t dtype, int64
     unsigned long long* partial = reinterpret_cast<unsigned long long*>(workspace);
     if (dtype == OOV_F32)
         return launch_fullsort_simt<float>((const float*)users, (const float*)items, Q, N, D, k, item_id_offset, mask_pad,
-                                           seg_lo, seg_hi, hist_rowptr, hist_cols, out_scores, out_idx, partial, P, st);
+                                           seg_lo, seg_hi, hist_rowptr, hist_cols, out_scores, out_idx, partial, P, st, ko);
     return launch_fullsort_simt<__nv_bfloat16>((const __nv_bfloat16*)users, (const __nv_bfloat16*)items, Q, N, D, k,
                                                item_id_offset, mask_pad, seg_lo, seg_hi, hist_rowptr, hist_cols,
-                                               out_scores, out_idx, partial, P, st);
+                                               out_scores, out_idx, partial, P, st, ko);
+}
+
+int oov_fullsort_topk(const void* users, const void* items, int32_t dtype, int64_t Q, int64_t N, int32_t D, int32_t k,
+                      int64_t item_id_offset, int32_t mask_pad, int64_t seg_lo, int64_t seg_hi,
+                      const int32_t* hist_rowptr, const int32_t* hist_cols, float* out_scores, int64_t* out_idx,
+                      void* workspace, size_t workspace_bytes, int32_t path, void* stream) {
+    return fullsort_topk_impl(users, items, dtype, Q, N, D, k, item_id_offset, mask_pad, seg_lo, seg_hi, hist_rowptr, hist_cols,
+                              out_scores, out_idx, workspace, workspace_bytes, path, stream, KeyOut{});
+}
+
+int oov_fullsort_topk_keys(const void* users, const void* items, int32_t dtype, int64_t Q, int64_t N, int32_t D, int32_t k,
+                           int32_t mask_pad, int64_t seg_lo, int64_t seg_hi, const int32_t* hist_rowptr, const int32_t* hist_cols,
+                           int64_t n0, int64_t lo0, int64_t lo1, uint64_t* keys_out,
+                           void* workspace, size_t workspace_bytes, int32_t path, void* stream) {
+    OOV_REQUIRE(keys_out != nullptr || Q == 0, OOV_ERR_ARG, "oov_fullsort_topk_keys: keys_out is NULL");
+    OOV_REQUIRE(n0 >= 0 && n0 <= N && lo0 >= 0 && lo1 >= 0 && lo0 + n0 < (1ll << 32) && lo1 + (N - n0) < (1ll << 32), OOV_ERR_ARG,
+                "oov_fullsort_topk_keys: row map n0=%lld lo0=%lld lo1=%lld does not fit 32-bit global ids", (long long)n0,
+                (long long)lo0, (long long)lo1);
+    KeyOut ko;
+    ko.keys = reinterpret_cast<unsigned long long*>(keys_out); ko.n0 = n0; ko.lo0 = lo0; ko.lo1 = lo1;
+    return fullsort_topk_impl(users, items, dtype, Q, N, D, k, 0, mask_pad, seg_lo, seg_hi, hist_rowptr, hist_cols, nullptr, nullptr,
+                              workspace, workspace_bytes, path, stream, ko);
+}
+
+int oov_topk_merge_keys(const uint64_t* keys, int32_t G, int64_t Q, int32_t k, float* out_scores, int64_t* out_idx, void* stream) {
+    OOV_REQUIRE(G > 0 && Q >= 0 && k > 0 && k <= 128, OOV_ERR_ARG, "oov_topk_merge_keys: bad shape G=%d Q=%lld k=%d", G, (long long)Q, k);
+    if (Q == 0) return OOV_OK;
+    OOV_REQUIRE(keys && out_scores && out_idx, OOV_ERR_ARG, "oov_topk_merge_keys: NULL pointer");
+    return launch_merge_keys(reinterpret_cast<const unsigned long long*>(keys), nullptr, G, Q, k, 0, out_scores, out_idx,
+                             (cudaStream_t)stream, KeyOut{});
 }
 
 int oov_fullsort_scores(const void* users, const void* items, int32_t dtype, int64_t Q, int64_t N, int32_t D,

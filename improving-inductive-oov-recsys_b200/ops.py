@@ -409,6 +409,43 @@ def fullsort_topk(users: torch.Tensor, items: torch.Tensor, k: int, item_id_offs
     return out_s, out_i
 
 
+def fullsort_topk_keys(users: torch.Tensor, items: torch.Tensor, k: int, row_map: Tuple[int, int, int], mask_pad: bool = True,
+                       seg: Tuple[int, int] = (0, INT64_MAX), hist=None, path: int = PATH_AUTO) -> torch.Tensor:
+    """`fullsort_topk` over a shard table laid out [ids lo0.. (n0 rows) | ids lo1..] (row_map = (n0, lo0, lo1)) that
+    returns the lists as packed 8-byte candidates in GLOBAL ids: int64 [Q, k] holding uint64 keys
+    (score bits << 32 | ~id; 0 = empty), the payload of the row-shard all-gather.  `seg` and `hist` are in local rows."""
+    _cuda(users, "users")
+    _cuda(items, "items")
+    if users.dtype != items.dtype:
+        raise ValueError("users and items must share a dtype")
+    users, items = users.contiguous(), items.contiguous()
+    Q, D = users.shape
+    N = items.shape[0]
+    if N and items.shape[1] != D:
+        raise ValueError("users / items embedding size mismatch")
+    users, items = _pad16(users, items)
+    D = users.shape[1]
+    rowptr, cols = _hist(hist, Q, users.device)
+    keys = torch.empty((Q, k), dtype=torch.int64, device=users.device)
+    lib = _lib.load()
+    ws = _workspace(lib.oov_fullsort_topk_workspace(Q, max(N, 1), D, k, path), users.device)
+    n0, lo0, lo1 = (int(v) for v in row_map)
+    _lib.check(lib.oov_fullsort_topk_keys(_p(users), _p(items), _dt(users), Q, N, D, k, int(bool(mask_pad)), int(seg[0]), int(seg[1]),
+                                          _p(rowptr), _p(cols), n0, lo0, lo1, _p(keys), _p(ws), ws.numel(), path, _stream()))
+    return keys
+
+
+def topk_merge_keys(keys: torch.Tensor):
+    """[G, Q, k] packed candidates (`fullsort_topk_keys` of G shards) -> global (scores fp32, ids int64) [Q, k]."""
+    _cuda(keys, "keys", torch.int64)
+    keys = keys.contiguous()
+    G, Q, k = keys.shape
+    out_s = torch.empty((Q, k), dtype=torch.float32, device=keys.device)
+    out_i = torch.empty((Q, k), dtype=torch.int64, device=keys.device)
+    _lib.check(_lib.load().oov_topk_merge_keys(_p(keys), G, Q, k, _p(out_s), _p(out_i), _stream()))
+    return out_s, out_i
+
+
 def fullsort_scores(users, items, item_id_offset: int = 0, mask_pad: bool = False, seg=(0, INT64_MAX), hist=None):
     """Dense fp32 [Q, N] scores (what the reference materialises); masks optional."""
     _cuda(users, "users")

@@ -124,8 +124,9 @@ class ShardedRetrieval:
             return None
         return ops.pairs_to_csr(hist_pairs[0], hist_pairs[1], Q, col_ranges=self.segments)
 
-    def fused_candidates(self, user_e: torch.Tensor, k: int, hist_pairs=None, seg=(0, INT64_MAX), local_csr=None) -> Optional[torch.Tensor]:
-        """[1, Q, k, 2] candidates from one launch over the fused table; None if `seg` needs the per-segment path.
+    def fused_keys(self, user_e: torch.Tensor, k: int, hist_pairs=None, seg=(0, INT64_MAX), local_csr=None) -> Optional[torch.Tensor]:
+        """[Q, k] packed 8-byte candidates in global ids from ONE launch over the fused table (the final merge of the fused
+        kernel writes them directly: no pack / id-remap ops); None if `seg` needs the per-segment path.
         `local_csr` = a CSR already built by `local_history_csr` (e.g. on another stream)."""
         from . import ops
         lseg = self._local_seg(seg)
@@ -136,9 +137,16 @@ class ShardedRetrieval:
         (lo0, hi0), (lo1, hi1) = self.segments
         n0 = hi0 - lo0
         csr = local_csr if local_csr is not None else self.local_history_csr(hist_pairs, user_e.shape[0])
-        s, rows = ops.fullsort_topk(user_e, self.table, k, item_id_offset=0, mask_pad=(lo0 == 0 and hi0 > 0), seg=lseg, hist=csr)
-        ids = torch.where(rows < n0, rows + lo0, rows + (lo1 - n0))
-        ids = torch.where(rows < 0, rows, ids)                      # empty slots stay -1
+        return ops.fullsort_topk_keys(user_e, self.table, k, (n0, lo0, lo1), mask_pad=(lo0 == 0 and hi0 > 0), seg=lseg, hist=csr)
+
+    def fused_candidates(self, user_e: torch.Tensor, k: int, hist_pairs=None, seg=(0, INT64_MAX), local_csr=None) -> Optional[torch.Tensor]:
+        """[1, Q, k, 2] (score bits, global id) candidates of the fused table, the 16-byte format of the per-segment path
+        (kept for callers that mix both); the exchange itself uses `fused_keys`."""
+        keys = self.fused_keys(user_e, k, hist_pairs, seg, local_csr)
+        if keys is None:
+            return None
+        from . import ops
+        s, ids = ops.topk_merge_keys(keys.unsqueeze(0))
         return pack_candidates(s, ids).unsqueeze(0)
 
     def local_candidates(self, user_e: torch.Tensor, k: int, hist=None, seg=(0, INT64_MAX)) -> torch.Tensor:
@@ -153,14 +161,20 @@ class ShardedRetrieval:
     def topk(self, user_e: torch.Tensor, k: int, hist=None, seg=(0, INT64_MAX), hist_pairs=None, local_csr=None):
         """Global (scores [Q,k], ids [Q,k]) — identical on every rank.  History either as a CSR over GLOBAL item ids
         (`hist`, per-segment path) or as the dataloader's (row, item) pairs (`hist_pairs`, fused one-launch path)."""
-        local = None
         if self.fused and hist is None:
-            local = self.fused_candidates(user_e, k, hist_pairs, seg, local_csr)
-        if local is None:
-            if hist is None and hist_pairs is not None and hist_pairs[0] is not None:
+            keys = self.fused_keys(user_e, k, hist_pairs, seg, local_csr)
+            if keys is not None:
                 from . import ops
-                hist = ops.pairs_to_csr(hist_pairs[0], hist_pairs[1], user_e.shape[0])
-            local = self.local_candidates(user_e, k, hist, seg)
+                if self.world > 1:
+                    cand = torch.empty((self.world,) + tuple(keys.shape), dtype=keys.dtype, device=keys.device)
+                    dist.all_gather_into_tensor(cand, keys, group=self.group)      # 8 bytes per candidate
+                else:
+                    cand = keys.unsqueeze(0)
+                return ops.topk_merge_keys(cand)
+        if hist is None and hist_pairs is not None and hist_pairs[0] is not None:
+            from . import ops
+            hist = ops.pairs_to_csr(hist_pairs[0], hist_pairs[1], user_e.shape[0])
+        local = self.local_candidates(user_e, k, hist, seg)
         if self.world > 1:
             cand = torch.empty((self.world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype,
                                device=local.device)              # ranks concatenated along dim 0

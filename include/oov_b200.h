@@ -210,6 +210,21 @@ int oov_topk_merge(const float* cand_scores, const int64_t* cand_idx,
                    int32_t G, int64_t Q, int32_t k,
                    float* out_scores, int64_t* out_idx, void* stream);
 
+/* Row-sharded exchange with 8-byte candidates: oov_fullsort_topk_keys is oov_fullsort_topk for a shard
+ * table laid out [global ids lo0 .. lo0 + n0 | global ids lo1 ..] (one slice of the in-vocab ids, one of the OOV ids)
+ * that writes every list entry as ONE packed key in GLOBAL item ids, keys_out [Q, k] uint64 =
+ * (order-preserving score bits << 32) | ~uint32(global id), 0 = empty slot, already ordered (score desc, id asc): what
+ * the ranks all-gather (8·Q·k bytes each).  seg_lo / seg_hi and the history CSR are in LOCAL rows of the shard table.
+ * oov_topk_merge_keys merges G such lists [G, Q, k] into the global (scores, ids).  Global ids must fit 32 bits. */
+int oov_fullsort_topk_keys(const void* users, const void* items, int32_t dtype,
+                           int64_t Q, int64_t N, int32_t D, int32_t k, int32_t mask_pad,
+                           int64_t seg_lo, int64_t seg_hi,
+                           const int32_t* hist_rowptr, const int32_t* hist_cols,
+                           int64_t n0, int64_t lo0, int64_t lo1, uint64_t* keys_out,
+                           void* workspace, size_t workspace_bytes, int32_t path, void* stream);
+int oov_topk_merge_keys(const uint64_t* keys, int32_t G, int64_t Q, int32_t k,
+                        float* out_scores, int64_t* out_idx, void* stream);
+
 /* 'rec.topk' rows of evaluator/collector.py:160-166: hits[q, j] = 1 iff topk_idx[q, j] is a
  * positive of user q (CSR pos_rowptr/pos_cols, ascending), last column = number of positives. */
 int oov_topk_hits(const int64_t* topk_idx, int64_t Q, int32_t k,

@@ -276,7 +276,7 @@ def test_sharded_fused_table_equals_global(world):
     user_e = model._assemble("user", users, out_dtype=model.table_dtype)
     for seg in ((0, 1 << 62), (0, n_old), (n_old, 1 << 62)):
         s_ref, i_ref = model.full_sort_topk(users, k, n_total_items=N, history_index=(hu, hi), seg=seg)
-        cands = []
+        cands, keys = [], []
         for r in range(world):
             sr = sharded.ShardedRetrieval(model, N, rank=r, world_size=world)
             assert sr.fused
@@ -284,10 +284,15 @@ def test_sharded_fused_table_equals_global(world):
             c = sr.fused_candidates(user_e, k, hist_pairs=(hu, hi), seg=seg)
             assert c is not None and c.shape == (1, Q, k, 2)
             cands.append(c)
+            kk = sr.fused_keys(user_e, k, hist_pairs=(hu, hi), seg=seg)      # what the ranks all-gather: 8 bytes per candidate
+            assert kk.shape == (Q, k) and kk.dtype == torch.int64
+            keys.append(kk)
         cs, ci = sharded.unpack_candidates(torch.cat(cands, dim=0))
         s_m, i_m = ops.topk_merge(cs, ci)
+        s_k, i_k = ops.topk_merge_keys(torch.stack(keys))
         torch.cuda.synchronize()
         assert torch.equal(i_m, i_ref) and torch.equal(s_m, s_ref), (world, seg)
+        assert torch.equal(i_k, i_ref) and torch.equal(s_k, s_ref), (world, seg)
 
 
 def test_tc_score_nan_rows_rank_first():
