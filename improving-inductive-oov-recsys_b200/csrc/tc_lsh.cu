@@ -86,6 +86,9 @@ struct LshParams {
     unsigned long long* trace;                         // profiling only (OOV_LSH_TRACE_PTR): [4 roles][4096] event << 56 | clock of CTA 0
 };
 // one timestamp of CTA 0 (roles: 0 MMA1, 1 MMA2, 2 worker warp 0, 3 worker warp 15); a no-op unless a trace buffer is set
+#ifndef OOV_TRACE_W2
+#define OOV_TRACE_W2 (L_WORKERS - 1)      /* second traced worker warp (profiling builds: -DOOV_TRACE_W2=n) */
+#endif
 #ifdef OOV_LSH_TRACE
 #define LTRACE(role, ev)                                                                                         \
     do {                                                                                                         \
@@ -566,7 +569,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         unsigned int my_ties = 0;
         int g = 0, T = 0;
         int trace_n = 0;
-        const int trole = (lane == 0 && wk == 0) ? 2 : ((lane == 0 && wk == L_WORKERS - 1) ? 3 : -1);
+        const int trole = (lane == 0 && wk == 0) ? 2 : ((lane == 0 && wk == OOV_TRACE_W2) ? 3 : -1);
 #ifdef OOV_LSH_TRACE
 #define WTRACE(ev) do { if (trole >= 0) LTRACE(trole, ev); } while (0)
 #else
@@ -600,7 +603,9 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             s_mx[slot * L_BM + row] = bad ? INFINITY : mx;
             s_n2[slot * L_BM + row] = n2;
             if (slot == 0) s_fr[(Tn & 1) * L_BM + row] = gth.fr;
-            worker_bar();                                              // also: the previous tile's queue and counts are complete
+            WTRACE(17);
+            worker_bar();
+            WTRACE(18);                                              // also: the previous tile's queue and counts are complete
             if (wtid == 0) {
                 s_qn[Tn & 1] = 0u; s_fn[Tn & 1] = 0u;                  // the bank of tile Tn (last used by Tn - 2, long settled)
                 if (wait_a_empty) mbar_arrive(&q_full[(Tn - 1) & 1]);  // the fixer may settle tile Tn - 1 now
@@ -628,6 +633,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                 mbar_wait(a_empty, (uint32_t)((Tn - 1) & 1));          // the previous tile's GEMM1s have read A'
                 tc_fence_after();
             }
+            WTRACE(19);
             // K element k lives in column k / 2: the 8 features are 4 columns at offset 4 * slot of each 16-column piece
             tc_st_32x4(a_lane + 0 * 16 + slot * 4, c0[0], c0[1], c0[2], c0[3]);
             tc_st_32x4(a_lane + 1 * 16 + slot * 4, c1[0], c1[1], c1[2], c1[3]);

@@ -20,7 +20,7 @@ torch.cuda.synchronize()
 del os.environ["OOV_LSH_TRACE_PTR"]
 tr = trace.cpu().view(4, 4096)
 names = {0: "m1.tile", 1: "m1.wait", 2: "m1.go", 3: "m1.issued", 4: "m2.wait", 5: "m2.go", 6: "m2.issued", 7: "w.wait_acc1", 8: "w.acc1_ready",
-         9: "w.loaded", 10: "w.signs_done", 11: "w.h_empty", 12: "w.stored", 13: "w.staged_next", 14: "w.queue_done", 15: "w.acc2_ready", 16: "w.tile_done"}
+         9: "w.loaded", 10: "w.signs_done", 11: "w.h_empty", 12: "w.stored", 13: "w.staged_next", 14: "w.queue_done", 15: "w.acc2_ready", 16: "w.tile_done", 17: "w.features_loaded", 18: "w.stage_barrier", 19: "w.a_empty"}
 ev = []
 for role in range(4):
     for x in tr[role].tolist():
