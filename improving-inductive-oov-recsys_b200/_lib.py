@@ -77,6 +77,7 @@ SIGNATURES = {
     "oov_first_order_sum": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_vp, c_vp,
                                     c_vp, c_vp]),
     "oov_map_ids": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp]),
+    "oov_cross_update": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
 }
 
 _lib = None

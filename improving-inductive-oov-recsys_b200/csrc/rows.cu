@@ -340,6 +340,30 @@ static unsigned grid_for(K kernel, int64_t work_items, int per_block) {
     return (unsigned)b;
 }
 
+// DCN-V2 cross layer tail (dcnv2.py:120-144): x_{l+1} = x_0 * (W_l x_l + b_l) + x_l, elementwise on bf16 rows; the
+// matrix-vector part t = W_l x_l + b_l comes from the tensor-core linear.  8 elements (16 bytes) per thread and step.
+__global__ void __launch_bounds__(256)
+cross_update_kernel(const uint4* __restrict__ x0, const uint4* __restrict__ t, const uint4* __restrict__ xl, int64_t n8,
+                    uint4* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 a = __ldg(x0 + i), b = __ldg(t + i), c = __ldg(xl + i);
+        uint4 o;
+        const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
+        const uint32_t* pb = reinterpret_cast<const uint32_t*>(&b);
+        const uint32_t* pc = reinterpret_cast<const uint32_t*>(&c);
+        uint32_t* po = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pa[j]));
+            const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pb[j]));
+            const float2 fc = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pc[j]));
+            __nv_bfloat162 h = __floats2bfloat162_rn(fmaf(fa.x, fb.x, fc.x), fmaf(fa.y, fb.y, fc.y));
+            po[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        out[i] = o;
+    }
+}
+
 }  // namespace oov
 
 using namespace oov;
@@ -471,6 +495,20 @@ int oov_map_ids(const int64_t* ids, int64_t n, int64_t n_old, int64_t n_buckets,
     OOV_REQUIRE(ids && out, OOV_ERR_ARG, "oov_map_ids: NULL pointer");
     map_ids_kernel<<<grid_for(map_ids_kernel, n, 256), 256, 0, (cudaStream_t)stream>>>(ids, n, n_old, n_buckets, fn, out);
     OOV_LAUNCH_CHECK("map_ids_kernel");
+    return OOV_OK;
+}
+
+int oov_cross_update(const void* x0, const void* t, const void* xl, int64_t n_elems, void* out, void* stream) {
+    OOV_REQUIRE(n_elems >= 0 && n_elems % 8 == 0, OOV_ERR_ARG, "oov_cross_update: n_elems=%lld must be a multiple of 8", (long long)n_elems);
+    if (n_elems == 0) return OOV_OK;
+    OOV_REQUIRE(x0 && t && xl && out, OOV_ERR_ARG, "oov_cross_update: NULL pointer");
+    OOV_REQUIRE(aligned(x0, 16) && aligned(t, 16) && aligned(xl, 16) && aligned(out, 16), OOV_ERR_ALIGN,
+                "oov_cross_update: operands must be 16-byte aligned");
+    const int64_t n8 = n_elems / 8;
+    cross_update_kernel<<<grid_for(cross_update_kernel, n8, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(x0), reinterpret_cast<const uint4*>(t), reinterpret_cast<const uint4*>(xl), n8,
+        reinterpret_cast<uint4*>(out));
+    OOV_LAUNCH_CHECK("cross_update_kernel");
     return OOV_OK;
 }
 

@@ -57,7 +57,7 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64
 constexpr int BM = 128, BK = 64;
 constexpr int EPI_WARP0 = 4;
 
-enum { ACT_NONE = 0, ACT_GELU = 1, ACT_SIGMOID = 2 };
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_SIGMOID = 2, ACT_RELU = 3 };
 
 struct LinearEpi {
     const float* bias;       // [N] or NULL
@@ -134,6 +134,7 @@ __device__ __forceinline__ uint32_t gelu_pair_bf16(uint64_t acc, uint64_t bias) 
 template <int ACT> __device__ __forceinline__ float act_apply(float v) {
     if (ACT == ACT_GELU) return gelu_fast(v);
     if (ACT == ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+    if (ACT == ACT_RELU) return fmaxf(v, 0.f);
     return v;
 }
 
@@ -696,6 +697,7 @@ int tc_linear(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64
     if (M == 0) return OOV_OK;
     if (epi.act == ACT_GELU) return tc_linear_act<ACT_GELU>(A, lda, W, ldw, M, N, K, epi, st);
     if (epi.act == ACT_SIGMOID) return tc_linear_act<ACT_SIGMOID>(A, lda, W, ldw, M, N, K, epi, st);
+    if (epi.act == ACT_RELU) return tc_linear_act<ACT_RELU>(A, lda, W, ldw, M, N, K, epi, st);
     return tc_linear_act<ACT_NONE>(A, lda, W, ldw, M, N, K, epi, st);
 }
 
@@ -1075,7 +1077,7 @@ int oov_tc_linear(const void* A, int64_t lda, const void* W, int64_t ldw, int64_
                   const float* bias, int32_t act, void* out, int32_t out_dtype, int64_t ld_out, void* stream) {
     const int debug = act >> 8;      // undocumented profiling bits (see LinearEpi::debug)
     act &= 0xff;
-    OOV_REQUIRE(M >= 0 && N > 0 && K > 0 && lda >= K && ldw >= K && ld_out >= N && dtype_ok(out_dtype) && act >= 0 && act <= 2,
+    OOV_REQUIRE(M >= 0 && N > 0 && K > 0 && lda >= K && ldw >= K && ld_out >= N && dtype_ok(out_dtype) && act >= 0 && act <= 3,
                 OOV_ERR_ARG, "oov_tc_linear: bad argument");
     OOV_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, OOV_ERR_ALIGN, "oov_tc_linear: lda/ldw must be multiples of 8 elements");
     if (M == 0) return OOV_OK;

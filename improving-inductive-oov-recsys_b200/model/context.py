@@ -164,3 +164,129 @@ class InductiveFMFirstOrderLinear(nn.Module, _TokenOOVMixin):
     def forward(self, token_fields: torch.Tensor) -> torch.Tensor:
         """Token part of layers.py:1695-1750: sum over fields + bias -> [B, output_dim]."""
         return self.embed_token_fields(token_fields, 0, 1).sum(dim=1) + self.bias
+
+
+class MLPLayers(nn.Module):
+    """layers.py:33-92 with the DCNV2 settings (bn=True, activation='relu'): the same module tree, hence the same
+    state_dict keys (`mlp_layers.{1,5,...}.weight`, `mlp_layers.{2,6,...}.running_mean`, ...)."""
+
+    def __init__(self, layers: Sequence[int], dropout: float = 0.0, bn: bool = True):
+        super().__init__()
+        mods = []
+        for i, o in zip(layers[:-1], layers[1:]):
+            mods.append(nn.Dropout(p=dropout))
+            mods.append(nn.Linear(i, o))
+            if bn:
+                mods.append(nn.BatchNorm1d(num_features=o))
+            mods.append(nn.ReLU())
+        self.mlp_layers = nn.Sequential(*mods)
+
+    def folded(self):
+        """[(W', b')] with every eval-mode BatchNorm folded into its Linear: W' = W gamma / sigma, b' = (b - mean) gamma / sigma + beta."""
+        out, lin = [], None
+        for m in self.mlp_layers:
+            if isinstance(m, nn.Linear):
+                lin = m
+                out.append([m.weight.detach().float(), m.bias.detach().float()])
+            elif isinstance(m, nn.BatchNorm1d):
+                s = m.weight.detach().float() / torch.sqrt(m.running_var.float() + m.eps)
+                w, b = out[-1]
+                out[-1] = [w * s[:, None], (b - m.running_mean.float()) * s + m.bias.detach().float()]
+        return out
+
+
+class DCNV2(InductiveContextRecommender):
+    """DCN-V2 ranking model on the OOV path (reference model/context_aware_recommender/dcnv2.py:30-250, `mixed: False`):
+    token gather + OOV overwrite (`embed_token_fields`) feeding the cross network and the MLP, evaluated in eval mode on
+    the tensor cores: every matrix product is `oov_tc_linear` (tcgen05, bf16 operands, fp32 accumulate; eval-mode
+    BatchNorm folded into the Linear, ReLU / bias in the epilogue), the cross layers' x_0 * t + x_l tail is one
+    elementwise kernel (`oov_cross_update`), the 1-wide predict layer + sigmoid one more linear.  Same parameter names as the
+    reference (`cross_layer_w.{l}`, `bias.{l}`, `mlp_layers.mlp_layers.*`, `predict_layer.*`).  Token fields only
+    (Criteo-shaped data: BASELINE configs[2]); float / token-sequence fields and training are outside this path."""
+
+    def __init__(self, config, field_dims: Sequence[int], inductive_mapper=None, inductive_embedder=None):
+        super().__init__(config, field_dims, inductive_mapper=inductive_mapper, inductive_embedder=inductive_embedder)
+
+        def cfg(key, default):
+            try:
+                v = config[key]
+            except (KeyError, IndexError):
+                v = None
+            return default if v is None else v
+
+        if cfg("mixed", False):
+            raise NotImplementedError("DCNV2 mixed (MoE low-rank) cross network is not on the accelerated path")
+        self.structure = cfg("structure", "stacked")
+        self.cross_layer_num = int(cfg("cross_layer_num", 3))
+        self.mlp_hidden_size = list(cfg("mlp_hidden_size", [768, 768]))
+        self.dropout_prob = float(cfg("dropout_prob", 0.2))
+        self.num_feature_field = len(field_dims)
+        self.in_feature_num = self.num_feature_field * self.embedding_size
+        self.cross_layer_w = nn.ParameterList(nn.Parameter(torch.randn(self.in_feature_num, self.in_feature_num))
+                                              for _ in range(self.cross_layer_num))
+        self.bias = nn.ParameterList(nn.Parameter(torch.zeros(self.in_feature_num, 1)) for _ in range(self.cross_layer_num))
+        self.mlp_layers = MLPLayers([self.in_feature_num] + self.mlp_hidden_size, dropout=self.dropout_prob, bn=True)
+        top = self.mlp_hidden_size[-1] + (self.in_feature_num if self.structure == "parallel" else 0)
+        self.predict_layer = nn.Linear(top, 1)
+        for m in self.modules():                      # dcnv2.py:110 self.apply(xavier_normal_initialization)
+            if isinstance(m, (nn.Embedding, nn.Linear)):
+                nn.init.xavier_normal_(m.weight.data)
+                if isinstance(m, nn.Linear) and m.bias is not None:
+                    nn.init.constant_(m.bias.data, 0)
+        self._packed = None
+
+    # ---- weights in the layout the tensor-core linear takes (bf16 [N, K] with K padded to 8), rebuilt on demand
+    def pack_tower(self):
+        bf = torch.bfloat16
+
+        def pad_k(w):
+            k = w.shape[1]
+            return torch.nn.functional.pad(w, (0, (-k) % 8)).to(bf).contiguous()
+
+        pad = (-self.in_feature_num) % 8             # cross layers are square: pad rows like columns so x_l keeps x_0's padded width
+        cross = [(pad_k(torch.nn.functional.pad(w.detach().float(), (0, 0, 0, pad))),
+                  torch.nn.functional.pad(b.detach().float().reshape(-1), (0, pad)).contiguous()) for w, b in zip(self.cross_layer_w, self.bias)]
+        mlp = [(pad_k(w), b.contiguous()) for w, b in self.mlp_layers.folded()]
+        # the predict layer is 1 wide: pad its output dimension to 8 rows so it runs through the same kernel
+        pw = self.predict_layer.weight.detach().float()
+        pw8 = torch.zeros((8, pw.shape[1]), dtype=torch.float32, device=pw.device)
+        pw8[0] = pw[0]
+        pb8 = torch.zeros(8, dtype=torch.float32, device=pw.device)
+        pb8[0] = self.predict_layer.bias.detach().float()[0]
+        self._packed = dict(cross=cross, mlp=mlp, pred=(pad_k(pw8), pb8))
+        return self._packed
+
+    def cross_network(self, x0: torch.Tensor) -> torch.Tensor:
+        """dcnv2.py:120-144 on bf16 rows [B, in_feature_num]."""
+        pk = self._packed or self.pack_tower()
+        xl = x0
+        for w, b in pk["cross"]:
+            t = ops.tc_linear(xl, w, b, act="none", out_dtype=torch.bfloat16)
+            xl = ops.cross_update(x0, t, xl)
+        return xl
+
+    def _mlp(self, h: torch.Tensor) -> torch.Tensor:
+        for w, b in (self._packed or self.pack_tower())["mlp"]:
+            h = ops.tc_linear(h, w, b, act="relu", out_dtype=torch.bfloat16)
+        return h
+
+    def tower(self, x0: torch.Tensor) -> torch.Tensor:
+        """[B, in_feature_num] bf16 embeddings -> [B] fp32 click probabilities (dcnv2.py:214-250, eval mode)."""
+        if x0.shape[1] % 8:
+            x0 = torch.nn.functional.pad(x0, (0, (-x0.shape[1]) % 8))
+        pk = self._packed or self.pack_tower()
+        cross = self.cross_network(x0)
+        top = self._mlp(cross) if self.structure == "stacked" else torch.cat([cross[:, : self.in_feature_num], self._mlp(x0)], dim=1)
+        pw, pb = pk["pred"]
+        if self.structure != "stacked" and pw.shape[1] != top.shape[1]:
+            top = torch.nn.functional.pad(top, (0, pw.shape[1] - top.shape[1]))
+        return ops.tc_linear(top.contiguous(), pw, pb, act="sigmoid", out_dtype=torch.float32)[:, 0]
+
+    def forward(self, interaction) -> torch.Tensor:
+        tokens = interaction if isinstance(interaction, torch.Tensor) else interaction["token_fields"]
+        emb = self.embed_token_fields(tokens)                       # [B, fields, D]
+        x0 = emb.reshape(emb.shape[0], -1).to(torch.bfloat16)
+        return self.tower(x0)
+
+    def predict(self, interaction) -> torch.Tensor:
+        return self.forward(interaction)

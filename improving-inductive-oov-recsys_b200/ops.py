@@ -300,7 +300,7 @@ def tc_linear(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = N
     if W.shape[1] != K:
         raise ValueError("A / W inner dimensions differ")
     out = torch.empty((M, N), dtype=_torch_dtype(out_dtype), device=A.device)
-    code = {"none": 0, "gelu": 1, "sigmoid": 2}[act] | (_debug << 8)
+    code = {"none": 0, "gelu": 1, "sigmoid": 2, "relu": 3}[act] | (_debug << 8)
     _lib.check(_lib.load().oov_tc_linear(_p(A), K, _p(W), K, M, N, K, _p(bias), code, _p(out), _dt(out), N, _stream()))
     return out
 
@@ -582,6 +582,19 @@ def first_order_sum(tokens, offsets, table1, n_users: int, n_items: int, oov_use
     _lib.check(_lib.load().oov_first_order_sum(_p(tokens), Bn, fields, _p(offsets), _p(t1), t1.numel(), int(n_users),
                                                int(n_items), uid_idx, iid_idx, _p(oov_user_val), _p(oov_item_val),
                                                _p(out), _stream()))
+    return out
+
+
+def cross_update(x0: torch.Tensor, t: torch.Tensor, xl: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x0 * t + xl elementwise (bf16): the tail of a DCN-V2 cross layer, dcnv2.py:137-142."""
+    for a, nm in ((x0, "x0"), (t, "t"), (xl, "xl")):
+        _cuda(a, nm, torch.bfloat16)
+    if x0.shape != t.shape or x0.shape != xl.shape:
+        raise ValueError("cross_update: shapes differ")
+    x0, t, xl = x0.contiguous(), t.contiguous(), xl.contiguous()
+    if out is None:
+        out = torch.empty_like(x0)
+    _lib.check(_lib.load().oov_cross_update(_p(x0), _p(t), _p(xl), x0.numel(), _p(out), _stream()))
     return out
 
 

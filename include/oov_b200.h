@@ -279,6 +279,15 @@ int oov_first_order_sum(const int64_t* tokens, int64_t Bn, int32_t fields, const
                         const float* oov_user_val, const float* oov_item_val,
                         float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Context dense towers — replaces the eval-mode maths of
+ * model/context_aware_recommender/dcnv2.py:120-144 (cross network) and model/layers.py:33-92 (MLPLayers with eval-mode
+ * BatchNorm folded into the Linear) on top of oov_tc_linear (act: 0 none, 1 GELU, 2 sigmoid, 3 ReLU).
+ * oov_cross_update: out = x0 * t + xl elementwise over bf16 tensors of n_elems elements (multiple of 8, 16-byte
+ * aligned) — the tail x_{l+1} = x_0 * (W_l x_l + b_l) + x_l of a cross layer, t being the tensor-core linear's output.
+ * ------------------------------------------------------------------------------------ */
+int oov_cross_update(const void* x0, const void* t, const void* xl, int64_t n_elems, void* out, void* stream);
+
 /* inductive_mapper=random (inductive/random_mapper.py:70-130): new_id = id (id < n_old) or
  * n_old + hash(id - n_old) % n_buckets.  fn: 0 mod, 1 fast, 2 3round, 3 64bit. */
 int oov_map_ids(const int64_t* ids, int64_t n, int64_t n_old, int64_t n_buckets, int32_t fn,

@@ -468,3 +468,48 @@ def map_ids(ids: np.ndarray, n_old: int, n_buckets: int, fn: str) -> np.ndarray:
     oov = ids >= n_old
     out[oov] = mapper_hash(ids[oov] - n_old, n_buckets, fn) + n_old
     return out
+
+
+# ---------------------------------------------------------------------------------------
+# DCN-V2 dense tower in eval mode
+# ---------------------------------------------------------------------------------------
+def dcnv2_cross(x0: np.ndarray, cross_w: Sequence[np.ndarray], cross_b: Sequence[np.ndarray], bf16_points: bool = False) -> np.ndarray:
+    """model/context_aware_recommender/dcnv2.py:120-144: x_{l+1} = x_0 * (W_l x_l + b_l) + x_l, rows of x0 [B, in].
+    bf16_points: round the linear's output and every x_l to bf16 (the rounding points of the tensor-core path)."""
+    r = round_bf16 if bf16_points else (lambda a: a)
+    x0 = np.asarray(x0, np.float32)
+    xl = x0
+    for w, b in zip(cross_w, cross_b):
+        t = r((xl @ np.asarray(w, np.float32).T + np.asarray(b, np.float32).reshape(1, -1)).astype(np.float32))
+        xl = r((x0 * t + xl).astype(np.float32))
+    return xl
+
+
+def mlp_bn_relu(x: np.ndarray, layers: Sequence[dict], bf16_points: bool = False) -> np.ndarray:
+    """model/layers.py:33-92 MLPLayers(bn=True, activation='relu') in eval mode: Dropout is the identity, BatchNorm1d uses
+    its running statistics: y = relu((x W^T + b - mean) / sqrt(var + eps) * gamma + beta).
+    layers: dicts with w [out, in], b, bn_mean, bn_var, bn_gamma, bn_beta, bn_eps."""
+    r = round_bf16 if bf16_points else (lambda a: a)
+    h = np.asarray(x, np.float32)
+    for L in layers:
+        z = h @ np.asarray(L["w"], np.float32).T + np.asarray(L["b"], np.float32)
+        z = (z - L["bn_mean"]) / np.sqrt(L["bn_var"] + L["bn_eps"]) * L["bn_gamma"] + L["bn_beta"]
+        h = r(np.maximum(z, 0).astype(np.float32))
+    return h
+
+
+def fold_bn(L: dict):
+    """Eval-mode BatchNorm folded into the preceding Linear: W' = W * (gamma / sigma), b' = (b - mean) * gamma / sigma + beta."""
+    s = (L["bn_gamma"] / np.sqrt(L["bn_var"] + L["bn_eps"])).astype(np.float32)
+    return (np.asarray(L["w"], np.float32) * s[:, None]).astype(np.float32), ((L["b"] - L["bn_mean"]) * s + L["bn_beta"]).astype(np.float32)
+
+
+def dcnv2_forward(x0, cross_w, cross_b, mlp_layers, pred_w, pred_b, structure: str = "stacked", bf16_points: bool = False):
+    """dcnv2.py:214-250 (mixed = False): stacked: sigmoid(predict(mlp(cross(x0)))); parallel: sigmoid(predict([cross(x0) | mlp(x0)]))."""
+    c = dcnv2_cross(x0, cross_w, cross_b, bf16_points)
+    if structure == "stacked":
+        top = mlp_bn_relu(c, mlp_layers, bf16_points)
+    else:
+        top = np.concatenate([c, mlp_bn_relu(x0, mlp_layers, bf16_points)], axis=1)
+    z = top @ np.asarray(pred_w, np.float32).reshape(-1) + np.float32(np.asarray(pred_b).reshape(-1)[0])
+    return sigmoid(z.astype(np.float32))

@@ -1,6 +1,7 @@
 """Pin the oracle (numpy/C restatement) against the golden fixtures, i.e. against the
 outputs of the UNMODIFIED reference run through oracle/refshim.py by
 tests/golden/make_golden.py.  CPU only."""
+import os
 import numpy as np
 import pytest
 
@@ -147,3 +148,36 @@ def test_topk_helpers():
     ci = np.stack([idx, idx + 10])
     mv, mi = o.merge_topk(cs, ci, 2)
     assert mi.tolist() == idx.tolist()
+
+
+def _dcnv2_case(g, name):
+    pre = name + "."
+    cw = [g[pre + f"cross_w{l}"] for l in range(3)]
+    cb = [g[pre + f"cross_b{l}"] for l in range(3)]
+    layers = []
+    l = 0
+    while pre + f"mlp_w{l}" in g.files:
+        layers.append(dict(w=g[pre + f"mlp_w{l}"], b=g[pre + f"mlp_b{l}"], bn_mean=g[pre + f"bn_mean{l}"], bn_var=g[pre + f"bn_var{l}"],
+                           bn_gamma=g[pre + f"bn_gamma{l}"], bn_beta=g[pre + f"bn_beta{l}"], bn_eps=float(g[pre + f"bn_eps{l}"])))
+        l += 1
+    return g[pre + "x0"], cw, cb, layers, g[pre + "pred_w"], g[pre + "pred_b"]
+
+
+@pytest.mark.parametrize("structure", ["stacked", "parallel"])
+def test_oracle_dcnv2_tower_vs_reference(structure):
+    """oracle.dcnv2_cross / mlp_bn_relu / dcnv2_forward against the reference's DCNV2.cross_network + MLPLayers(eval) +
+    predict layer (tests/golden/make_golden_dcnv2.py), fp32 rtol 1e-5; BatchNorm folding is exact to fp32 rounding."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "dcnv2_tower.npz"))
+    x0, cw, cb, layers, pw, pb = _dcnv2_case(g, structure)
+    pre = structure + "."
+    cross = o.dcnv2_cross(x0, cw, cb)
+    np.testing.assert_allclose(cross, g[pre + "cross_out"], rtol=1e-5, atol=1e-5)
+    deep_in = cross if structure == "stacked" else x0
+    np.testing.assert_allclose(o.mlp_bn_relu(deep_in, layers), g[pre + "deep_out"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(o.dcnv2_forward(x0, cw, cb, layers, pw, pb, structure), g[pre + "out"], rtol=1e-5, atol=1e-6)
+    # folded BatchNorm == BatchNorm
+    h = deep_in
+    for L in layers:
+        w, b = o.fold_bn(L)
+        h = np.maximum(h @ w.T + b, 0)
+    np.testing.assert_allclose(h, g[pre + "deep_out"], rtol=1e-4, atol=1e-5)
