@@ -12,7 +12,8 @@ items (in-vocab gather + OOV embed) into the bf16 item table, score Q x N, mask 
 Default workload `lsh10m` = BASELINE.json configs[4], the configuration the metric's target is quoted on (BPR + lsh,
 10M items of which 5M OOV, F = 32, B = 1000, D = 64, Q = 1024, k = 20; it fits one B200).  The same JSON line carries
 a second block `workloads.dhe1m` = configs[1] (DirectAU + dhe, 1M items / 100k users, bf16) with its own value / e2e /
-roofline, measured in the same process (`--single` skips it).
+roofline, measured in the same process (`--single` skips it), and at N = 1 a third block `workloads.dcnv2_criteo` =
+configs[2] (DCNV2 ranking tower with slsh OOV buckets, 65536 rows x 26 token fields per step, rows/s).
 With N > 1 the item rows are sharded over the ranks (strong scaling: total work fixed), each rank embeds and
 scores its shard, one NCCL all-gather moves the [S, Q, k] candidates and every rank merges.
 Prints ONE JSON line on rank 0.
@@ -57,6 +58,7 @@ def parse_args():
     ap.add_argument("--workload", default="lsh10m", choices=list(WORKLOADS))
     ap.add_argument("--second", default="dhe1m", choices=list(WORKLOADS), help="second workload reported under `workloads`")
     ap.add_argument("--single", action="store_true", help="measure only --workload")
+    ap.add_argument("--no-dcnv2", dest="dcnv2", action="store_false", help="skip the workloads.dcnv2_criteo block (N = 1 only)")
     ap.add_argument("--Q", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
@@ -592,6 +594,154 @@ def run_gpu(args, name, wl, rank, world, local_rank, with_cpu_baseline):
     return result
 
 
+DCNV2_WL = dict(rows=65536, fields=26, D=16, mlp=[768, 768], cross_layers=3, n_users=100_000, n_old_users=50_000,
+                n_items=100_000, n_old_items=50_000, other_vocab=100_000, F=32, B=1000)
+
+
+def run_dcnv2(args, device):
+    """BASELINE.json configs[2]: DCNV2 ranking with slsh OOV buckets on Criteo-shaped synthetic rows —
+    26 token fields (user, item, 24 more), eval_batch_size 65536, embedding_size 16, cross 3 x 416x416, MLP [768, 768].
+    A step = token gather + slsh OOV overwrite (bf16) + cross network + MLP + predict + sigmoid for one batch of rows.
+    Reported under `workloads.dcnv2_criteo` as rows/s (N = 1 only: the path has no exchange step; replicas only)."""
+    import torch
+    import oov_b200
+    from oov_b200 import ops
+    wl = DCNV2_WL
+    Bn, fields, D = wl["rows"], wl["fields"], wl["D"]
+
+    class Config(dict):
+        def __getitem__(self, key):
+            return dict.get(self, key, None)
+
+    class Dataset:
+        def __init__(self, uf, itf):
+            self._uf, self._if = uf, itf
+            self.user_num, self.item_num = wl["n_old_users"], wl["n_old_items"]
+
+        def num(self, f):
+            return {"user_id": self.user_num, "item_id": self.item_num}[f]
+
+        def get_user_feature(self):
+            return self._uf
+
+        def get_item_feature(self):
+            return self._if
+
+    g = torch.Generator(device="cpu").manual_seed(2021)
+    cfg = Config(USER_ID_FIELD="user_id", ITEM_ID_FIELD="item_id", device=device, embedding_size=D, add_oov_buckets=True,
+                 inductive_embedder="slsh", user_oov_buckets=wl["B"], item_oov_buckets=wl["B"], oov_normalization_type="global",
+                 structure="stacked", cross_layer_num=wl["cross_layers"], mlp_hidden_size=wl["mlp"], dropout_prob=0.2, mixed=False)
+    uf = oov_b200.Interaction({"user_id": torch.arange(wl["n_users"]), "f0": torch.randn(wl["n_users"], wl["F"], generator=g)})
+    itf = oov_b200.Interaction({"item_id": torch.arange(wl["n_items"]), "f0": torch.randn(wl["n_items"], wl["F"], generator=g)})
+    emb = oov_b200.get_inductive_embedder(cfg, Dataset(uf, itf), mode="bench-dcnv2")
+    dims = [wl["n_old_users"], wl["n_old_items"]] + [wl["other_vocab"]] * (fields - 2)
+    model = oov_b200.DCNV2(cfg, dims, inductive_embedder=emb).to(device).eval()
+    with torch.no_grad():                      # keep the cross activations O(1): xavier on a square matrix already is
+        for w in model.cross_layer_w:
+            w.mul_(1.0 / 416 ** 0.5)
+    model.pack_tower()
+    n_batches = 4
+    host = []
+    for b in range(n_batches):
+        gb = torch.Generator(device="cpu").manual_seed(300 + b)
+        t = torch.stack([torch.randint(0, wl["n_users"], (Bn,), generator=gb), torch.randint(0, wl["n_items"], (Bn,), generator=gb)] +
+                        [torch.randint(0, wl["other_vocab"], (Bn,), generator=gb) for _ in range(fields - 2)], dim=1)
+        host.append(t.pin_memory())
+    dev = [t.to(device) for t in host]
+    out_host = torch.empty((Bn,), dtype=torch.float32).pin_memory()
+
+    gstep = None if args.eager else oov_b200.GraphedRanker(model, Bn, fields)
+
+    def step_resident(b):
+        return (gstep or model)(dev[b % n_batches])
+
+    def step_e2e(b):
+        if gstep is not None:
+            out = gstep(host[b % n_batches])                  # pinned host -> the graph's static token buffer
+        else:
+            out = model(host[b % n_batches].to(device, non_blocking=True))
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for b in range(steps):
+            fn(b)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    sampler = ClockSampler(int(str(device).split(":")[-1]))
+    sampler.start()
+    for b in range(max(args.warmup, 3)):
+        step_resident(b)
+        step_e2e(b)
+    l0 = ops.launch_count()
+    t0 = time.time()
+    ms = timed(step_resident, args.steps)
+    t1 = time.time()
+    launches = ops.launch_count() - l0 if gstep is None else gstep.launches_per_replay * args.steps
+    clocks = sampler.window(t0, t1)
+    ms_e2e = timed(step_e2e, args.steps)
+    sampler.stop()
+
+    def ev_time(fn, reps=10):
+        """GPU time of `fn` replayed from a CUDA graph (launched from Python the stages are host-bound)."""
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=side):
+            keep = fn()
+        torch.cuda.synchronize()
+        gr.replay()
+        ms_ = timed(lambda b: gr.replay(), reps) / reps
+        del gr, keep
+        return ms_
+
+    x0 = model.embed_token_fields(dev[0], out_dtype=torch.bfloat16).reshape(Bn, -1)
+    cross = model.cross_network(x0)
+    stages = {"token_gather_oov_ms": ev_time(lambda: model.embed_token_fields(dev[0], out_dtype=torch.bfloat16)),
+              "cross_network_ms": ev_time(lambda: model.cross_network(x0)),
+              "mlp_ms": ev_time(lambda: model._mlp(cross)),
+              "tower_ms": ev_time(lambda: model.tower(x0))}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+    inf = fields * D
+    flops = 2.0 * Bn * (wl["cross_layers"] * inf * inf + inf * wl["mlp"][0] + wl["mlp"][0] * wl["mlp"][1] + wl["mlp"][1])
+    ach = flops / (stages["tower_ms"] * 1e-3) / 1e12
+    roofline = {"kernel": "DCNV2 tower: 3 x (tc_linear 416x416 + cross_update) + tc_linear<ReLU> 416->768->768 + predict (tcgen05)",
+                "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "launch_ms": stages["tower_ms"], "flops_per_launch": flops,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops" if peaks else "fallback 1590",
+                "note": "algorithmic flops 2 B (3 in^2 + in h1 + h1 h2 + h2) over the time of the whole tower (9 launches); "
+                        "the activations (54 - 100 MB per layer) stream through L2 / HBM between launches"}
+    res = {"metric": "dcnv2_eval_rows_per_s", "value": Bn * args.steps / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms / args.steps,
+           "e2e": {"value": Bn * args.steps / (ms_e2e * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": Bn * fields * 8,
+                   "d2h_bytes_per_step": Bn * 4, "ms_per_step": ms_e2e / args.steps},
+           "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None, "stages": stages,
+           "config": {"workload": "dcnv2_criteo", "model": "DCNV2 (stacked, mixed off, eval)", "embedder": "slsh", "rows_per_step": Bn,
+                      "token_fields": fields, "embedding_size": D, "cross_layers": wl["cross_layers"], "mlp_hidden_size": wl["mlp"],
+                      "oov_buckets": wl["B"], "oov_share_user_item": 0.5, "l2": "activations per layer 54-100 MB + 4 rotating batches; no explicit flush",
+                      "launch": "eager" if gstep is None else "whole forward replayed from one CUDA graph (GraphedRanker)",
+                      "parallelism": "single GPU (replicas only: no exchange step)"},
+           "clocks": clocks, "steps": args.steps, "warmup": max(args.warmup, 3)}
+    gstep = None
+    del model, emb, dev
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -623,12 +773,15 @@ def main():
 
     results = [run_gpu(args, n, workload(n), rank, world, local_rank, with_cpu_baseline=(world == 1 and not args.no_cpu_baseline))
                for n in names]
+    dcn = run_dcnv2(args, f"cuda:{local_rank}") if (world == 1 and args.dcnv2 and not args.single) else None
     if rank == 0:
         line = results[0]
         if len(results) > 1:
-            line["workloads"] = {n: {key: r[key] for key in ("value", "unit", "ms_per_step", "e2e", "gpu_launches", "roofline",
+            line.setdefault("workloads", {}).update({n: {key: r[key] for key in ("value", "unit", "ms_per_step", "e2e", "gpu_launches", "roofline",
                                                            "cpu_baseline", "stages", "config", "clocks", "steps", "warmup")}
-                                 for n, r in zip(names[1:], results[1:])}
+                                 for n, r in zip(names[1:], results[1:])})
+        if dcn is not None:
+            line.setdefault("workloads", {})["dcnv2_criteo"] = dcn
         print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:

@@ -151,7 +151,7 @@ template <int BN, bool FAST> struct GemmSmem {
     static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
 };
 
-// FAST = bf16 output, N % 64 == 0, N <= 1024, no assemble: 16 epilogue warps (lane quarter x column quarter), both
+// FAST = bf16 output, N % 8 == 0, 64 < N <= 1024, no assemble: 16 epilogue warps (lane quarter x column quarter), both
 // tcgen05.ld of the warp's 64 columns in flight together, TMEM released as soon as they land, bias from smem,
 // results staged through XOR-swizzled smem so every global store instruction writes four full 128-byte lines.
 template <int BN, int ACT, bool FAST>
@@ -272,10 +272,12 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 const int col0 = nt * BN + cq * 64;
                 if (col0 >= N || (epi.debug & 2)) continue;         // warp-uniform
+                const int n_valid = N - col0;                       // columns of this warp's 64 that exist (N % 8 == 0)
                 // two halves of 32 columns: activation -> bf16 pairs -> staging row `lane`
                 // (16-byte chunk c of the row lives at physical chunk c ^ (row & 7): conflict-free both ways)
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
+                    if (hf * 32 >= n_valid) break;                  // warp-uniform
                     uint32_t pk[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
@@ -317,7 +319,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int n_it = left <= 0 ? 0 : (left >= 29 ? 8 : (int)((left + 3) >> 2));
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    if (i < n_it) {
+                    if (i < n_it && c * 8 < n_valid) {
                         const uint4 val = *reinterpret_cast<const uint4*>(sp + i * 512 + ((i & 1) ? off_odd : off_even));
                         *reinterpret_cast<uint4*>(gp) = val;
                     }
@@ -682,7 +684,7 @@ static int tc_linear_act(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat1
                          const LinearEpi& epi, cudaStream_t st) {
     // (N = 64, the last DHE layer, through this 256-wide kernel was measured: 6 % SLOWER than the generic 64-wide one —
     // three quarters of the MMA columns and of the weight tile would be TMA zero fill)
-    const bool fast = epi.out_dtype == OOV_BF16 && N > 64 && N % 64 == 0 && N <= 1024 && epi.ids == nullptr &&
+    const bool fast = epi.out_dtype == OOV_BF16 && N > 64 && N % 8 == 0 && N <= 1024 && epi.ids == nullptr &&
                       epi.ld % 8 == 0 && aligned(epi.out, 16);
     // CTA pairs need full 256-column weight blocks (each CTA loads 128 of them) and more than one 256-row tile to pay
     if (fast && N % 256 == 0 && M > 256 && linear_cg2_enabled())

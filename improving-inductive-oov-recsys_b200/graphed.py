@@ -114,3 +114,40 @@ class GraphedTopK:
         self.load(users, hist_rows, hist_cols)
         self.graph.replay()
         return self.scores, self.ids
+
+
+class GraphedRanker:
+    """`probs = g(token_fields)` — a context ranking model's forward (token gather + OOV overwrite + dense tower, e.g.
+    `model.context.DCNV2`) for a static batch of `rows` x `fields` token ids, captured once and replayed.  The tower is a
+    dozen launches of 20-60 us each: launched one by one from Python the host enqueue time exceeds the GPU time.
+    A shorter batch is padded with token 0 rows and the result sliced."""
+
+    def __init__(self, model, rows: int, fields: int, warmup: int = 3):
+        self.model, self.rows, self.fields = model, int(rows), int(fields)
+        dev = next(model.parameters()).device
+        self.tokens = torch.zeros((self.rows, self.fields), dtype=torch.int64, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                model(self.tokens)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = ops.launch_count()
+        with torch.cuda.graph(self.graph, stream=side):
+            self.out = model(self.tokens)
+        self.launches_per_replay = ops.launch_count() - l0
+        torch.cuda.synchronize(dev)
+        self._keep_alive = [buf for key, buf in ops._ws_cache.items() if key[1] == side.cuda_stream]
+        self._capture_stream = side
+
+    def __call__(self, token_fields: torch.Tensor) -> torch.Tensor:
+        n = int(token_fields.shape[0])
+        if n > self.rows or token_fields.shape[1] != self.fields:
+            raise ValueError(f"graph was captured for [{self.rows}, {self.fields}] token ids, got {tuple(token_fields.shape)}")
+        self.tokens[:n].copy_(token_fields, non_blocking=True)
+        if n < self.rows:
+            self.tokens[n:].zero_()
+        self.graph.replay()
+        return self.out[:n]

@@ -2,8 +2,9 @@
 model/abstract_recommender.py:715-842 (InductiveContextRecommender.embed_token_fields),
 model/layers.py:130-153 (FMEmbedding) and :1617-1750 (InductiveFMFirstOrderLinear).
 
-Only the gather/OOV-overwrite step is on the accelerated path; the dense towers of
-DCNV2 / WideDeep / xDeepFM that consume these tensors are "next" (§8f row 2) and stay the caller's.
+The gather/OOV-overwrite step feeds the dense towers; of those, DCNV2's cross network + MLP
+(§8f row 2; dcnv2.py:120-144, 214-250) runs on the tensor-core linear here (class `DCNV2` below), the WideDeep /
+xDeepFM towers stay the caller's.
 Column 0 of `token_fields` is the user id, column 1 the item id (abstract_recommender.py:691-692).
 """
 from __future__ import annotations
@@ -39,7 +40,7 @@ class FMEmbedding(nn.Module):
 class _TokenOOVMixin:
     """Shared OOV-overwrite logic of abstract_recommender.py:794-842 and layers.py:1634-1693."""
 
-    def _embed_tokens(self, token_fields: torch.Tensor, uid_idx: int, iid_idx: int) -> torch.Tensor:
+    def _embed_tokens(self, token_fields: torch.Tensor, uid_idx: int, iid_idx: int, out_dtype=None) -> torch.Tensor:
         w = self.token_embedding_table.embedding.weight.detach()
         dev = w.device
         token_fields = token_fields.to(dev)
@@ -50,7 +51,7 @@ class _TokenOOVMixin:
         if mapper is None and emb is None:
             raise RuntimeError("Must provide either self.inductive_mapper or self.inductive_embedder")
         # 1) every in-vocab cell; OOV user/item cells are left for step 2 (only the overwrite is observable)
-        out = ops.token_gather(token_fields, offsets, w, self.n_users, self.n_items, uid_idx=uid_idx, iid_idx=iid_idx)
+        out = ops.token_gather(token_fields, offsets, w, self.n_users, self.n_items, uid_idx=uid_idx, iid_idx=iid_idx, out_dtype=out_dtype)
         # 2) OOV cells, written in place through a strided view (ids_stride = fields, out_stride = fields * D)
         for side, col, n_old in (("user", uid_idx, self.n_users), ("item", iid_idx, self.n_items)):
             ids = token_fields[:, col]
@@ -97,11 +98,12 @@ class InductiveContextRecommender(nn.Module, _TokenOOVMixin):
                                                                   inductive_mapper=first_order_mapper,
                                                                   inductive_embedder=first_order_embedder)
 
-    def embed_token_fields(self, token_fields: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
-        """[B, fields] int64 -> [B, fields, D] (abstract_recommender.py:794-842)."""
+    def embed_token_fields(self, token_fields: Optional[torch.Tensor], out_dtype=None) -> Optional[torch.Tensor]:
+        """[B, fields] int64 -> [B, fields, D] (abstract_recommender.py:794-842); `out_dtype` = the dtype the consumer
+        reads (default: the table's)."""
         if token_fields is None:
             return None
-        return self._embed_tokens(token_fields, 0, 1)
+        return self._embed_tokens(token_fields, 0, 1, out_dtype=out_dtype)
 
 
 class InductiveFMFirstOrderLinear(nn.Module, _TokenOOVMixin):
@@ -261,6 +263,8 @@ class DCNV2(InductiveContextRecommender):
         pk = self._packed or self.pack_tower()
         xl = x0
         for w, b in pk["cross"]:
+            # two launches per layer.  (A one-launch variant with the tail in the linear's store pass was measured on
+            # B200 at in = 416, 65536 rows: 99 us against 43 + 27 us — the x_0 / x_l loads sit exposed in the epilogue.)
             t = ops.tc_linear(xl, w, b, act="none", out_dtype=torch.bfloat16)
             xl = ops.cross_update(x0, t, xl)
         return xl
@@ -284,9 +288,8 @@ class DCNV2(InductiveContextRecommender):
 
     def forward(self, interaction) -> torch.Tensor:
         tokens = interaction if isinstance(interaction, torch.Tensor) else interaction["token_fields"]
-        emb = self.embed_token_fields(tokens)                       # [B, fields, D]
-        x0 = emb.reshape(emb.shape[0], -1).to(torch.bfloat16)
-        return self.tower(x0)
+        emb = self.embed_token_fields(tokens, out_dtype=torch.bfloat16)     # [B, fields, D], written as bf16 by the gather
+        return self.tower(emb.reshape(emb.shape[0], -1))
 
     def predict(self, interaction) -> torch.Tensor:
         return self.forward(interaction)

@@ -473,14 +473,17 @@ def map_ids(ids: np.ndarray, n_old: int, n_buckets: int, fn: str) -> np.ndarray:
 # ---------------------------------------------------------------------------------------
 # DCN-V2 dense tower in eval mode
 # ---------------------------------------------------------------------------------------
-def dcnv2_cross(x0: np.ndarray, cross_w: Sequence[np.ndarray], cross_b: Sequence[np.ndarray], bf16_points: bool = False) -> np.ndarray:
+def dcnv2_cross(x0: np.ndarray, cross_w: Sequence[np.ndarray], cross_b: Sequence[np.ndarray], bf16_points: bool = False,
+                bf16_t: bool = True) -> np.ndarray:
     """model/context_aware_recommender/dcnv2.py:120-144: x_{l+1} = x_0 * (W_l x_l + b_l) + x_l, rows of x0 [B, in].
-    bf16_points: round the linear's output and every x_l to bf16 (the rounding points of the tensor-core path)."""
+    bf16_points: round every x_l to bf16 — and, with bf16_t, the linear's output t too (the rounding points of the
+    tensor-core path: a bf16 linear followed by the elementwise tail)."""
     r = round_bf16 if bf16_points else (lambda a: a)
+    rt = r if bf16_t else (lambda a: a)
     x0 = np.asarray(x0, np.float32)
     xl = x0
     for w, b in zip(cross_w, cross_b):
-        t = r((xl @ np.asarray(w, np.float32).T + np.asarray(b, np.float32).reshape(1, -1)).astype(np.float32))
+        t = rt((xl @ np.asarray(w, np.float32).T + np.asarray(b, np.float32).reshape(1, -1)).astype(np.float32))
         xl = r((x0 * t + xl).astype(np.float32))
     return xl
 
@@ -504,9 +507,10 @@ def fold_bn(L: dict):
     return (np.asarray(L["w"], np.float32) * s[:, None]).astype(np.float32), ((L["b"] - L["bn_mean"]) * s + L["bn_beta"]).astype(np.float32)
 
 
-def dcnv2_forward(x0, cross_w, cross_b, mlp_layers, pred_w, pred_b, structure: str = "stacked", bf16_points: bool = False):
+def dcnv2_forward(x0, cross_w, cross_b, mlp_layers, pred_w, pred_b, structure: str = "stacked", bf16_points: bool = False,
+                  bf16_t: bool = True):
     """dcnv2.py:214-250 (mixed = False): stacked: sigmoid(predict(mlp(cross(x0)))); parallel: sigmoid(predict([cross(x0) | mlp(x0)]))."""
-    c = dcnv2_cross(x0, cross_w, cross_b, bf16_points)
+    c = dcnv2_cross(x0, cross_w, cross_b, bf16_points, bf16_t)
     if structure == "stacked":
         top = mlp_bn_relu(c, mlp_layers, bf16_points)
     else:

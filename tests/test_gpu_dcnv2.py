@@ -91,6 +91,40 @@ def test_dcnv2_cross_update_and_relu_epilogue():
     assert torch.allclose(plain, ref, rtol=1e-4, atol=1e-3)
 
 
+def test_tc_linear_fast_path_widths_not_multiple_of_64():
+    """The staged-store epilogue now takes any N % 8 == 0 in (64, 1024]: compare with fp32 maths for ragged widths."""
+    from oov_b200 import ops
+    gen = torch.Generator(device="cpu").manual_seed(10)
+    for M, N, K in ((257, 72, 64), (1000, 416, 416), (333, 264, 128), (4096, 1016, 96)):
+        A = torch.randn((M, K), generator=gen).to(DEV).to(torch.bfloat16)
+        W = torch.randn((N, K), generator=gen).to(DEV).to(torch.bfloat16)
+        b = torch.randn((N,), generator=gen).to(DEV)
+        for act, fn in (("none", lambda x: x), ("relu", torch.relu), ("gelu", torch.nn.functional.gelu)):
+            got = ops.tc_linear(A, W, b, act=act, out_dtype=torch.bfloat16).float()
+            want = fn(A.float() @ W.float().T + b)
+            assert torch.allclose(got, want, rtol=2.0 ** -7, atol=2e-2), (M, N, K, act, (got - want).abs().max().item())
+
+
+def test_graphed_ranker_replays_the_forward():
+    """GraphedRanker: the captured forward equals the eager one bit for bit, for full and short batches, from host or
+    device token tensors."""
+    import oov_b200
+    g = np.load(GOLD)
+    m = _model("stacked", *_dcnv2_case(g, "stacked"))
+    gen = torch.Generator(device="cpu").manual_seed(4)
+    gr = oov_b200.GraphedRanker(m, 512, 6)
+    assert gr.launches_per_replay >= 6
+    for n in (512, 100, 1):
+        tokens = torch.randint(0, 50, (n, 6), generator=gen)
+        want = m(tokens.to(DEV))
+        got = gr(tokens.pin_memory()).clone()
+        got_dev = gr(tokens.to(DEV)).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(got, want) and torch.equal(got_dev, want)
+    with pytest.raises(ValueError):
+        gr(torch.zeros((513, 6), dtype=torch.int64))
+
+
 def test_dcnv2_forward_through_token_gather_and_oov_overwrite():
     """End to end: token ids (some out of vocabulary) -> embed_token_fields -> tower, against the oracle tower applied to
     the same gathered embeddings."""
@@ -100,10 +134,10 @@ def test_dcnv2_forward_through_token_gather_and_oov_overwrite():
     m = _model("stacked", x0, cw, cb, layers, pw, pb)
     gen = torch.Generator(device="cpu").manual_seed(3)
     tokens = torch.randint(0, 50, (300, 6), generator=gen).to(DEV)
-    emb = m.embed_token_fields(tokens)
+    emb = m.embed_token_fields(tokens, out_dtype=torch.bfloat16)
     oov = tokens[:, 0] >= 40
     assert oov.any() and (emb[oov, 0].float() == 0).all()           # OOV user cells were overwritten by the embedder
-    x = emb.reshape(300, -1).to(torch.bfloat16)
+    x = emb.reshape(300, -1)
     got = m(tokens).cpu().numpy()
     r = o.round_bf16
     folded = [o.fold_bn(L) for L in layers]
