@@ -583,6 +583,371 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Main pass behind a pre-pass threshold ("column-split" epilogue).  With thr_init from the sampled pre-pass a user sees
+// a handful of candidates per CTA (pass rate ~1e-5), so the kernel is the speed of its scan: load, max tree, one vote.
+// In tc_score_topk_kernel<0> a thread owns one USER: the four warps of a user tile read the tile's four 32-column
+// chunks one after the other and the accumulator goes back to the MMA warp only then — drain (4 x ~400 cycles), hand-
+// over, four MMAs and hand-over are one serial chain per accumulator (~2200 cycles per item tile against 1024 cycles of
+// MMA time).  Here a thread owns one (TMEM lane, 32-column chunk) pair of ALL four accumulators: warp w reads lane
+// quarter w & 3, chunk w >> 2, so the sixteen warps empty an accumulator with ONE tcgen05.ld each and it is handed back
+// ~4x sooner; while they scan accumulator ut the tensor core already refills it.
+// The per-user state moves out of the registers: thresholds and lists live in shared memory, every value at or above
+// its user's threshold is pushed on a CTA-wide ring (sequence-stamped 16-byte entries) and ONE collector warp applies the
+// masks and maintains the lists (lane e holds list entry e: minimum search by warp reduction).  The history ranges that
+// fall inside the CTA's item range are found once per user at kernel start (two binary searches), so the collector's
+// history test is an (almost always empty) scan of that range.  Same candidate set, same (score desc, row asc) order
+// and the same per-CTA output lists as MODE 0: merge_keys_kernel is unchanged.
+constexpr int SC2_NCOL = 4;                                 // collector warps: one per TMEM lane quarter (disjoint users)
+constexpr int SC2_THREADS = (SC_EPI_WARPS + 3 + SC2_NCOL) * 32;   // 736: 16 scan warps, TMA, two MMA issuers, 4 collectors
+constexpr int SC2_W_COLLECT = SC_EPI_WARPS + 3;             // 19 .. 22
+constexpr int SC2_RS = 8;                                   // hit-chunk slots per scan warp (single producer ring)
+constexpr int SC2_SLOT_U4 = 9;                              // a slot: 32 scores (128 B) + {user column, first local row, sequence, -}
+constexpr int SC2_RING_BYTES = SC_EPI_WARPS * SC2_RS * SC2_SLOT_U4 * 16;     // 18 KB
+
+// -DOOV_SCORE_TRACE: clock-stamped events of CTA (0, 0) into p.pub (unused by this kernel): per warp 2048 64-bit slots,
+// slot = clock << 24 | event << 20 | ut << 16 | tile.  scripts/trace_score.py prints the timeline.
+#ifdef OOV_SCORE_TRACE
+#define STRACE(ev, ut_, t_)                                                                                       \
+    do {                                                                                                          \
+        if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (t_) - t0 < 96 && tr_n < 2048) {                   \
+            reinterpret_cast<unsigned long long*>(p.pub)[(size_t)warp * 2048 + tr_n++] =                          \
+                ((unsigned long long)clock64() << 24) | ((unsigned long long)(ev) << 20) | ((unsigned long long)(ut_) << 16) | \
+                (unsigned long long)(((t_) - t0) & 0xffff);                                                         \
+        }                                                                                                         \
+    } while (0)
+#else
+#define STRACE(ev, ut_, t_) do {} while (0)
+#endif
+
+__device__ __forceinline__ uint32_t lds_volatile(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_volatile(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_acquire(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_release(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, o);
+        x = y < x ? y : x;
+    }
+    return x;
+}
+
+__global__ void __launch_bounds__(SC2_THREADS, 1)
+tc_score_main2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmI, const ScoreParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* sA = smem;                                        // SC_NUT x 16 KB
+    unsigned char* sB = smem + SC_NUT * SC_A_BYTES;                  // stages x 16 KB
+    uint32_t* lists_hi = reinterpret_cast<uint32_t*>(sB + p.stages * SC_B_BYTES);      // [k][SC_UG]
+    uint32_t* lists_lo = lists_hi + (size_t)p.k * SC_UG;                                // [k][SC_UG]
+    uint4* ring = reinterpret_cast<uint4*>(lists_lo + (size_t)p.k * SC_UG);             // [16 warps][SC2_RS] hit-chunk slots
+    float* thr_s = reinterpret_cast<float*>(ring + SC2_RING_BYTES / 16);                // [SC_UG] score filter per user
+    uint32_t* cnt_s = reinterpret_cast<uint32_t*>(thr_s + SC_UG);                       // [SC_UG] valid list entries
+    int32_t* h_lo = reinterpret_cast<int32_t*>(cnt_s + SC_UG);                          // [SC_UG] history range inside this
+    int32_t* h_hi = h_lo + SC_UG;                                                        //         CTA's item rows
+    uint64_t* bars = reinterpret_cast<uint64_t*>(h_hi + SC_UG);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + SC_MAX_STAGES;
+    uint64_t* a_full = bars + 2 * SC_MAX_STAGES;
+    uint64_t* acc_full = a_full + 1;
+    uint64_t* acc_empty = acc_full + SC_NUT;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + SC_NUT);
+    uint32_t* done_cnt = tmem_slot + 1;
+    uint32_t* head_s = tmem_slot + 4;                                                    // [16] slots the collector has consumed, per scan warp
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t q0 = (int64_t)blockIdx.y * SC_UG;
+    const int64_t q_left = p.Q - q0;
+    const int n_ut = q_left >= SC_UG ? SC_NUT : (int)((q_left + SC_BM - 1) / SC_BM);
+    const int64_t t0 = p.n_visit * blockIdx.x / gridDim.x;
+    const int64_t t1 = p.n_visit * (blockIdx.x + 1) / gridDim.x;
+    const int k = p.k;
+    int tr_n = 0; (void)tr_n;
+
+    if (warp == SC_W_TMA && lane == 0) { tma_prefetch_desc(&tmU); tma_prefetch_desc(&tmI); }
+    if (warp == SC_W_MMA && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], n_ut > 2 ? 2u : 1u); }
+        mbar_init(a_full, 1);
+        for (int a = 0; a < SC_NUT; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], SC_EPI_WARPS); }
+        fence_barrier_init();
+        *done_cnt = 0u;
+        for (int w = 0; w < SC_EPI_WARPS; ++w) head_s[w] = 0u;
+    }
+    if (warp == SC_W_ALLOC) tmem_alloc(tmem_slot, 512);
+    for (int i = threadIdx.x; i < SC2_RING_BYTES / 16; i += SC2_THREADS) ring[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x < SC_UG) {
+        // per-user set-up by thread = user column: threshold, empty list, history entries inside this CTA's rows
+        const int ul = threadIdx.x;
+        const int64_t user = q0 + ul;
+        const bool ok = user < p.Q;
+        float thr = ok ? -INFINITY : INFINITY;
+        if (ok && p.thr_init != nullptr) {
+            const uint32_t T = p.thr_init[user];
+            if (T != 0u) thr = float_from_order_key(T);               // NaN (k NaN tiles): nothing is filtered
+        }
+        thr_s[ul] = thr;
+        cnt_s[ul] = 0u;
+        int lo = 0, hi = 0;
+        if (ok && p.hist_rowptr != nullptr) {
+            const int b = p.hist_rowptr[user], e = p.hist_rowptr[user + 1];
+            const int64_t g_lo = (p.tile_begin + t0) * SC_BN + p.item_id_offset, g_hi = (p.tile_begin + t1) * SC_BN + p.item_id_offset;
+            int l = b, h = e;
+            while (l < h) { const int m = (l + h) >> 1; if ((int64_t)p.hist_cols[m] < g_lo) l = m + 1; else h = m; }
+            lo = l; h = e;
+            while (l < h) { const int m = (l + h) >> 1; if ((int64_t)p.hist_cols[m] < g_hi) l = m + 1; else h = m; }
+            hi = l;
+        }
+        h_lo[ul] = lo; h_hi[ul] = hi;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == SC_W_TMA) {
+        const bool leader = elect_one();
+        if (leader) {
+            mbar_arrive_expect_tx(a_full, (uint32_t)(n_ut * SC_A_BYTES));
+            for (int ut = 0; ut < n_ut; ++ut) tma_load_2d(sA + ut * SC_A_BYTES, &tmU, a_full, 0, (int)(q0 + ut * SC_BM));
+            for (int64_t t = t0; t < t1 && t < t0 + SC_L2_AHEAD; ++t)
+                tma_prefetch_l2_2d(&tmI, 0, (int)((p.tile_begin + t) * SC_BN));
+        }
+        __syncwarp();
+        int stage = 0; uint32_t phase = 0;
+        for (int64_t t = t0; t < t1; ++t) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            STRACE(5, 0, t);
+            if (leader) {
+                if (t + SC_L2_AHEAD < t1) tma_prefetch_l2_2d(&tmI, 0, (int)((p.tile_begin + t + SC_L2_AHEAD) * SC_BN));
+                mbar_arrive_expect_tx(&full_bar[stage], SC_B_BYTES);
+                tma_load_2d(sB + stage * SC_B_BYTES, &tmI, &full_bar[stage], 0, (int)((p.tile_begin + t) * SC_BN));
+            }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == SC_W_MMA || warp == SC_W_MMA + 1) {
+        const int iw = warp - SC_W_MMA;
+        const bool leader = elect_one();
+        if (2 * iw < n_ut) {
+            constexpr uint32_t idesc = make_idesc_bf16_f32(SC_BM, SC_BN);
+            mbar_wait(a_full, 0);
+            const int n_mine = n_ut - 2 * iw >= 2 ? 2 : 1;
+            int stage = 0; uint32_t phase = 0, acc_phase = 0;
+            for (int64_t t = t0; t < t1; ++t) {
+                for (int j = 0; j < n_mine; ++j) {
+                    const int ut = 2 * iw + j;
+                    mbar_wait(&acc_empty[ut], acc_phase ^ 1);
+                    STRACE(0, ut, t);
+                    if (j == 0) { mbar_wait(&full_bar[stage], phase); STRACE(1, ut, t); }
+                    tc_fence_after();
+                    const uint64_t adesc = make_sw128_desc(smem_u32(sA + ut * SC_A_BYTES));
+                    const uint64_t bdesc = make_sw128_desc(smem_u32(sB + stage * SC_B_BYTES));
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(ut * SC_BN);
+                    if (leader) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, kk ? 1u : 0u);
+                        tc_commit(&acc_full[ut]);
+                        if (j == n_mine - 1) tc_commit(&empty_bar[stage]);
+                    }
+                    __syncwarp();
+                    STRACE(2, ut, t);
+                }
+                acc_phase ^= 1;
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp < SC_EPI_WARPS) {
+        // ===================== scan warps: lane quarter q, column chunk c of every accumulator =====================
+        const int q = warp & 3, c = warp >> 2;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+        const int ul0 = q * 32 + lane;                                // user column of accumulator 0; + SC_BM per accumulator
+        uint4* my_ring = ring + warp * (SC2_RS * SC2_SLOT_U4);
+        uint32_t my_tail = 0;                                         // warp-uniform
+        uint32_t acc_phase = 0;
+        for (int64_t t = t0; t < t1; ++t) {
+            const uint32_t col0 = (uint32_t)((p.tile_begin + t) * SC_BN) + (uint32_t)(c * 32);    // local item row of v[0]
+#pragma unroll 1
+            for (int ut = 0; ut < n_ut; ++ut) {
+                const float thr = thr_s[ut * SC_BM + ul0];
+                mbar_wait(&acc_full[ut], acc_phase);
+                STRACE(3, ut, t);
+                tc_fence_after();
+                uint32_t v[32];
+                tc_ld_32x32(t_lane + (uint32_t)(ut * SC_BN), v);
+                tc_wait_ld();
+                STRACE(4, ut, t);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[ut]);           // this warp's share of the accumulator is in registers
+                float m[11];
+#pragma unroll
+                for (int j = 0; j < 10; ++j)
+                    m[j] = max3_nan(__uint_as_float(v[3 * j]), __uint_as_float(v[3 * j + 1]), __uint_as_float(v[3 * j + 2]));
+                m[10] = max2_nan(__uint_as_float(v[30]), __uint_as_float(v[31]));
+                const float m0 = max3_nan(m[0], m[1], m[2]), m1 = max3_nan(m[3], m[4], m[5]);
+                const float m2 = max3_nan(m[6], m[7], m[8]), m3 = max2_nan(m[9], m[10]);
+                const float mx = max2_nan(max3_nan(m0, m1, m2), m3);
+                uint32_t hm = __ballot_sync(0xffffffffu, !(mx < thr));                 // NaN compares false -> a hit
+                // Hit (a few per item tile and CTA): the lane hands its 32 scores to the collector as they are — eight
+                // 16-byte stores into this warp's own ring and one release store; nothing is scanned or masked here, a
+                // late scan warp is late for every accumulator that follows.
+                while (hm != 0u) {
+                    uint32_t take = hm;
+                    int nh = __popc(take);
+                    while (nh > SC2_RS) { take &= ~(0x80000000u >> __clz(take)); --nh; }       // start-up burst: SC2_RS lanes at a time
+                    uint32_t polls = 0;
+                    while (my_tail + (uint32_t)nh - lds_volatile(head_s + warp) > (uint32_t)SC2_RS) {   // warp-uniform
+                        __nanosleep(64);
+                        if (++polls > 20000000u) __trap();
+                    }
+                    if ((take >> lane) & 1u) {
+                        const uint32_t seq = my_tail + (uint32_t)__popc(take & ((1u << lane) - 1u));
+                        uint4* d = my_ring + (seq & (SC2_RS - 1)) * SC2_SLOT_U4;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) d[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        uint32_t* meta = reinterpret_cast<uint32_t*>(d + 8);
+                        meta[0] = (uint32_t)(ut * SC_BM + ul0);
+                        meta[1] = col0;
+                        sts_release(meta + 2, seq / SC2_RS + 1u);
+                    }
+                    my_tail += (uint32_t)nh;
+                    hm &= ~take;
+                }
+            }
+            acc_phase ^= 1;
+        }
+        __syncwarp();
+        if (lane == 0) { asm volatile("fence.acq_rel.cta;" ::: "memory"); atomicAdd(done_cnt, 1u); }
+    } else if (warp >= SC2_W_COLLECT) {
+        // ===================== collectors: masks + list maintenance =====================
+        // Collector cq serves the rings of the four scan warps of lane quarter cq (warps cq, cq + 4, cq + 8, cq + 12): the
+        // users of different collectors are disjoint, so every list has one writer.  One hit chunk at a time, warp-wide:
+        // lane j holds score j of the chunk (one vote finds the candidates), lane e holds list entry e (minimum search by
+        // warp reduction).
+        const int cq = warp - SC2_W_COLLECT;
+        const uint32_t n_rows = (uint32_t)p.N;
+        const uint32_t pad_row = (p.mask_pad && p.item_id_offset <= 0 && -p.item_id_offset < p.N) ? (uint32_t)(-p.item_id_offset) : 0xFFFFFFFFu;
+        uint32_t seg_lo, seg_hi;
+        {
+            const int64_t lo = p.seg_lo - p.item_id_offset, hi = p.seg_hi - p.item_id_offset;
+            seg_lo = lo <= 0 ? 0u : (lo >= p.N ? (uint32_t)p.N : (uint32_t)lo);
+            seg_hi = hi <= 0 ? 0u : (hi >= p.N ? (uint32_t)p.N : (uint32_t)hi);
+        }
+        const int src_warp = cq + 4 * (lane & 3);                    // lanes 0-3 poll one ring each
+        const uint4* src_ring = ring + src_warp * (SC2_RS * SC2_SLOT_U4);
+        uint32_t my_head = 0;                                         // of ring `src_warp` (lanes 0-3)
+        uint32_t idle = 0;
+        while (true) {
+            const uint32_t* my_meta = reinterpret_cast<const uint32_t*>(src_ring + (my_head & (SC2_RS - 1)) * SC2_SLOT_U4 + 8);
+            const bool ready = lane < 4 && lds_acquire(my_meta + 2) == my_head / SC2_RS + 1u;
+            const uint32_t rm = __ballot_sync(0xffffffffu, ready);
+            if (rm == 0u) {
+                if (lds_acquire(done_cnt) == (uint32_t)SC_EPI_WARPS) {
+                    // every producer has finished and its stores are visible: one more look at the rings before leaving
+                    const bool late = lane < 4 && lds_acquire(my_meta + 2) == my_head / SC2_RS + 1u;
+                    if (!__any_sync(0xffffffffu, late)) break;
+                    continue;
+                }
+                __nanosleep(idle < 8u ? 32 : 128);
+                ++idle;
+                continue;
+            }
+            idle = 0;
+            const int r = __ffs(rm) - 1;                              // ring (lane) served now
+            const uint32_t head_r = __shfl_sync(0xffffffffu, my_head, r);
+            const int w_r = cq + 4 * r;
+            const uint4* slot = ring + w_r * (SC2_RS * SC2_SLOT_U4) + (head_r & (SC2_RS - 1)) * SC2_SLOT_U4;
+            const uint32_t bits_l = reinterpret_cast<const uint32_t*>(slot)[lane];       // score `lane` of the chunk
+            const uint32_t ul = reinterpret_cast<const uint32_t*>(slot + 8)[0];
+            const uint32_t col0 = reinterpret_cast<const uint32_t*>(slot + 8)[1];
+            if (lane == r) ++my_head;
+            asm volatile("fence.acq_rel.cta;" ::: "memory");          // the reads above are done before the slot is handed back
+            if (lane == r) sts_volatile(head_s + w_r, my_head);
+            float thr = thr_s[ul];
+            const int h0 = h_lo[ul], h1 = h_hi[ul];
+            uint32_t n = cnt_s[ul];
+            unsigned long long x = lane < (int)n ? (((unsigned long long)lists_hi[lane * SC_UG + ul] << 32) | (unsigned long long)lists_lo[lane * SC_UG + ul])
+                                                 : ~0ull;             // list entry `lane`
+            uint32_t cm = __ballot_sync(0xffffffffu, !(__uint_as_float(bits_l) < thr));
+            while (cm != 0u) {
+                const int j = __ffs(cm) - 1;
+                cm &= cm - 1u;
+                const uint32_t bits = __shfl_sync(0xffffffffu, bits_l, j);
+                if (__uint_as_float(bits) < thr) continue;            // the filter rose since the vote
+                const uint32_t row = col0 + (uint32_t)j;
+                if (row >= n_rows) continue;                          // zero-filled rows past the end of the shard
+                float sc = __uint_as_float(bits);
+                bool masked = row == pad_row || row < seg_lo || row >= seg_hi;
+                if (!masked && h0 < h1) {                             // rare: this user has history inside the CTA's rows
+                    const int64_t gid = (int64_t)row + p.item_id_offset;
+                    bool found = false;
+                    for (int jj = h0 + lane; jj < h1; jj += 32) found |= (int64_t)p.hist_cols[jj] == gid;
+                    masked = __any_sync(0xffffffffu, found);
+                }
+                if (masked) sc = -INFINITY;
+                const unsigned long long cand = ((unsigned long long)float_order_key(sc) << 32) | (unsigned long long)(~row);
+                unsigned long long kth = 0ull;
+                bool moved = false;
+                if ((int)n < k) {
+                    if (lane == (int)n) x = cand;
+                    ++n;
+                    if ((int)n == k) { kth = warp_min_u64(x); moved = true; }
+                } else {
+                    const unsigned long long mn = warp_min_u64(x);
+                    if (cand > mn) {
+                        if (x == mn) x = cand;                        // entries are distinct (the row is part of the key)
+                        kth = warp_min_u64(x);
+                        moved = true;
+                    }
+                }
+                if (moved) thr = fmaxf(thr, float_from_order_key((uint32_t)(kth >> 32)));     // a NaN k-th score leaves the filter unchanged
+            }
+            // write the list back (only the entries that exist), the count and the filter
+            if (lane < (int)n) { lists_hi[lane * SC_UG + ul] = (uint32_t)(x >> 32); lists_lo[lane * SC_UG + ul] = (uint32_t)x; }
+            if (lane == 0) { cnt_s[ul] = n; thr_s[ul] = thr; }
+            __syncwarp();
+        }
+    }
+
+    // scan warps + collector: the lists are final
+    if (warp < SC_EPI_WARPS || warp >= SC2_W_COLLECT) {
+        asm volatile("bar.sync 1, %0;" ::"n"((SC_EPI_WARPS + SC2_NCOL) * 32) : "memory");
+        if (warp < SC_EPI_WARPS) {
+            const int ul = threadIdx.x;
+            const int64_t user = q0 + ul;
+            if (user < p.Q) {
+                const int n = (int)cnt_s[ul];
+                unsigned long long* dst = p.partial + ((size_t)blockIdx.x * p.Q + user) * k;
+                for (int e = 0; e < n; ++e)
+                    dst[e] = ((unsigned long long)lists_hi[e * SC_UG + ul] << 32) | (unsigned long long)lists_lo[e * SC_UG + ul];
+                p.partial_n[(size_t)blockIdx.x * p.Q + user] = (uint8_t)n;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == SC_W_ALLOC) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // Pre-pass threshold: one warp per user.  R = k + (masked items of the user that lie in sampled tiles); the R-th
 // largest of the user's n_s tile maxima (ordered keys, radix select 4 x 8 bits over a warp-private histogram) is a
 // bound no top-k score is below.  0 = no bound (fewer than R sampled tiles).
@@ -666,6 +1031,19 @@ static int score_stages(int k) {
 }
 static size_t score_smem_bytes(int k, int stages) {
     return 1024 + SC_NUT * SC_A_BYTES + (size_t)stages * SC_B_BYTES + (size_t)(k + SC_QCAP) * SC_UG * 8 + 512;
+}
+// column-split main pass: lists, candidate ring, per-user threshold / count / history range
+static size_t score2_fixed_bytes(int k) {
+    return 1024 + SC_NUT * SC_A_BYTES + (size_t)k * SC_UG * 8 + (size_t)SC2_RING_BYTES + (size_t)SC_UG * 16 + 512;
+}
+static int score2_stages(int k) {
+    int s = (int)((SC_SMEM_MAX - score2_fixed_bytes(k)) / SC_B_BYTES);
+    return s > SC_MAX_STAGES ? SC_MAX_STAGES : s;
+}
+static bool score2_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("OOV_SCORE_MAIN2"); v = e ? atoi(e) : 1; }      // profiling only; 0 = MODE 0 main pass
+    return v != 0;
 }
 
 bool score_tc_supported(int dtype, int D, int k) {
@@ -793,8 +1171,16 @@ int score_tc_run(const void* users, const void* items, int64_t Q, int64_t N, int
             const_cast<uint32_t*>(p.thr_init));
         OOV_LAUNCH_CHECK("score_threshold_kernel");
     }
-    tc_score_topk_kernel<0><<<grid, SC_THREADS, smem, st>>>(tmU, tmI, p);
-    OOV_LAUNCH_CHECK("tc_score_topk_kernel");
+    if (pre_stride > 0 && !p.share && !p.debug && score2_enabled() && score2_stages(k) >= 2) {
+        cudaError_t e = cudaFuncSetAttribute(tc_score_main2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM_MAX);
+        OOV_REQUIRE(e == cudaSuccess, OOV_ERR_CUDA, "cudaFuncSetAttribute(tc_score_main2_kernel): %s", cudaGetErrorString(e));
+        p.stages = score2_stages(k);
+        tc_score_main2_kernel<<<grid, SC2_THREADS, score2_fixed_bytes(k) + (size_t)p.stages * SC_B_BYTES, st>>>(tmU, tmI, p);
+        OOV_LAUNCH_CHECK("tc_score_main2_kernel");
+    } else {
+        tc_score_topk_kernel<0><<<grid, SC_THREADS, smem, st>>>(tmU, tmI, p);
+        OOV_LAUNCH_CHECK("tc_score_topk_kernel");
+    }
     return launch_merge_keys(p.partial, p.partial_n, gx, Q, k, item_id_offset, out_scores, out_idx, st, ko);
 }
 
