@@ -598,9 +598,13 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
 // fall inside the CTA's item range are found once per user at kernel start (two binary searches), so the collector's
 // history test is an (almost always empty) scan of that range.  Same candidate set, same (score desc, row asc) order
 // and the same per-CTA output lists as MODE 0: merge_keys_kernel is unchanged.
-constexpr int SC2_NCOL = 4;                                 // collector warps: one per TMEM lane quarter (disjoint users)
-constexpr int SC2_THREADS = (SC_EPI_WARPS + 3 + SC2_NCOL) * 32;   // 736: 16 scan warps, TMA, two MMA issuers, 4 collectors
-constexpr int SC2_W_COLLECT = SC_EPI_WARPS + 3;             // 19 .. 22
+#ifndef OOV_SC2_NCOL
+#define OOV_SC2_NCOL 4
+#endif
+constexpr int SC2_NCOL = OOV_SC2_NCOL;                      // collector warps: lane quarters congruent modulo SC2_NCOL (disjoint users)
+constexpr int SC2_RPC = SC_EPI_WARPS / SC2_NCOL;            // rings per collector
+constexpr int SC2_THREADS = (SC_EPI_WARPS + 1 + SC_NUT + SC2_NCOL) * 32;   // 800: 16 scan warps, TMA, 4 MMA issuers, 4 collectors
+constexpr int SC2_W_COLLECT = SC_EPI_WARPS + 1 + SC_NUT;    // 21 .. 24
 constexpr int SC2_RS = 8;                                   // hit-chunk slots per scan warp (single producer ring)
 constexpr int SC2_SLOT_U4 = 9;                              // a slot: 32 scores (128 B) + {user column, first local row, sequence, -}
 constexpr int SC2_RING_BYTES = SC_EPI_WARPS * SC2_RS * SC2_SLOT_U4 * 16;     // 18 KB
@@ -676,11 +680,11 @@ tc_score_main2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_cons
     const int64_t t0 = p.n_visit * blockIdx.x / gridDim.x;
     const int64_t t1 = p.n_visit * (blockIdx.x + 1) / gridDim.x;
     const int k = p.k;
-    int tr_n = 0; (void)tr_n;
+    [[maybe_unused]] int tr_n = 0;
 
     if (warp == SC_W_TMA && lane == 0) { tma_prefetch_desc(&tmU); tma_prefetch_desc(&tmI); }
     if (warp == SC_W_MMA && lane == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], n_ut > 2 ? 2u : 1u); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], (uint32_t)n_ut); }
         mbar_init(a_full, 1);
         for (int a = 0; a < SC_NUT; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], SC_EPI_WARPS); }
         fence_barrier_init();
@@ -739,34 +743,34 @@ tc_score_main2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_cons
             __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-    } else if (warp == SC_W_MMA || warp == SC_W_MMA + 1) {
-        const int iw = warp - SC_W_MMA;
+    } else if (warp >= SC_W_MMA && warp < SC_W_MMA + SC_NUT) {
+        // One issuer warp per accumulator: wait, descriptors, four MMAs and two commits are ~45 dependent instructions
+        // (~450 cycles next to the scan warps of the same scheduler) — with two accumulators per issuer the issuers'
+        // instruction stream, not the tensor pipe (4 x 4 x 64 cycles per item tile), set the period of the kernel.
+        const int ut = warp - SC_W_MMA;
         const bool leader = elect_one();
-        if (2 * iw < n_ut) {
+        if (ut < n_ut) {
             constexpr uint32_t idesc = make_idesc_bf16_f32(SC_BM, SC_BN);
             mbar_wait(a_full, 0);
-            const int n_mine = n_ut - 2 * iw >= 2 ? 2 : 1;
+            const uint64_t adesc = make_sw128_desc(smem_u32(sA + ut * SC_A_BYTES));
+            const uint32_t d_tmem = tmem_base + (uint32_t)(ut * SC_BN);
             int stage = 0; uint32_t phase = 0, acc_phase = 0;
             for (int64_t t = t0; t < t1; ++t) {
-                for (int j = 0; j < n_mine; ++j) {
-                    const int ut = 2 * iw + j;
-                    mbar_wait(&acc_empty[ut], acc_phase ^ 1);
-                    STRACE(0, ut, t);
-                    if (j == 0) { mbar_wait(&full_bar[stage], phase); STRACE(1, ut, t); }
-                    tc_fence_after();
-                    const uint64_t adesc = make_sw128_desc(smem_u32(sA + ut * SC_A_BYTES));
-                    const uint64_t bdesc = make_sw128_desc(smem_u32(sB + stage * SC_B_BYTES));
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(ut * SC_BN);
-                    if (leader) {
+                mbar_wait(&acc_empty[ut], acc_phase ^ 1);
+                STRACE(0, ut, t);
+                mbar_wait(&full_bar[stage], phase);
+                STRACE(1, ut, t);
+                tc_fence_after();
+                const uint64_t bdesc = make_sw128_desc(smem_u32(sB + stage * SC_B_BYTES));
+                if (leader) {
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, kk ? 1u : 0u);
-                        tc_commit(&acc_full[ut]);
-                        if (j == n_mine - 1) tc_commit(&empty_bar[stage]);
-                    }
-                    __syncwarp();
-                    STRACE(2, ut, t);
+                    for (int kk = 0; kk < 4; ++kk)
+                        tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, kk ? 1u : 0u);
+                    tc_commit(&acc_full[ut]);
+                    tc_commit(&empty_bar[stage]);                     // one arrival per issuer for this stage
                 }
+                __syncwarp();
+                STRACE(2, ut, t);
                 acc_phase ^= 1;
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
@@ -835,8 +839,8 @@ tc_score_main2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_cons
         if (lane == 0) { asm volatile("fence.acq_rel.cta;" ::: "memory"); atomicAdd(done_cnt, 1u); }
     } else if (warp >= SC2_W_COLLECT) {
         // ===================== collectors: masks + list maintenance =====================
-        // Collector cq serves the rings of the four scan warps of lane quarter cq (warps cq, cq + 4, cq + 8, cq + 12): the
-        // users of different collectors are disjoint, so every list has one writer.  One hit chunk at a time, warp-wide:
+        // Collector cq serves the rings of the scan warps w with w % SC2_NCOL == cq, i.e. of the lane quarters congruent to
+        // cq: the users of different collectors are disjoint, so every list has one writer.  One hit chunk at a time, warp-wide:
         // lane j holds score j of the chunk (one vote finds the candidates), lane e holds list entry e (minimum search by
         // warp reduction).
         const int cq = warp - SC2_W_COLLECT;
@@ -848,18 +852,18 @@ tc_score_main2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_cons
             seg_lo = lo <= 0 ? 0u : (lo >= p.N ? (uint32_t)p.N : (uint32_t)lo);
             seg_hi = hi <= 0 ? 0u : (hi >= p.N ? (uint32_t)p.N : (uint32_t)hi);
         }
-        const int src_warp = cq + 4 * (lane & 3);                    // lanes 0-3 poll one ring each
+        const int src_warp = cq + SC2_NCOL * (lane & (SC2_RPC - 1));  // lanes 0 .. SC2_RPC - 1 poll one ring each
         const uint4* src_ring = ring + src_warp * (SC2_RS * SC2_SLOT_U4);
-        uint32_t my_head = 0;                                         // of ring `src_warp` (lanes 0-3)
+        uint32_t my_head = 0;                                         // of ring `src_warp` (lanes < SC2_RPC)
         uint32_t idle = 0;
         while (true) {
             const uint32_t* my_meta = reinterpret_cast<const uint32_t*>(src_ring + (my_head & (SC2_RS - 1)) * SC2_SLOT_U4 + 8);
-            const bool ready = lane < 4 && lds_acquire(my_meta + 2) == my_head / SC2_RS + 1u;
+            const bool ready = lane < SC2_RPC && lds_acquire(my_meta + 2) == my_head / SC2_RS + 1u;
             const uint32_t rm = __ballot_sync(0xffffffffu, ready);
             if (rm == 0u) {
                 if (lds_acquire(done_cnt) == (uint32_t)SC_EPI_WARPS) {
                     // every producer has finished and its stores are visible: one more look at the rings before leaving
-                    const bool late = lane < 4 && lds_acquire(my_meta + 2) == my_head / SC2_RS + 1u;
+                    const bool late = lane < SC2_RPC && lds_acquire(my_meta + 2) == my_head / SC2_RS + 1u;
                     if (!__any_sync(0xffffffffu, late)) break;
                     continue;
                 }
@@ -870,7 +874,7 @@ tc_score_main2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_cons
             idle = 0;
             const int r = __ffs(rm) - 1;                              // ring (lane) served now
             const uint32_t head_r = __shfl_sync(0xffffffffu, my_head, r);
-            const int w_r = cq + 4 * r;
+            const int w_r = cq + SC2_NCOL * r;
             const uint4* slot = ring + w_r * (SC2_RS * SC2_SLOT_U4) + (head_r & (SC2_RS - 1)) * SC2_SLOT_U4;
             const uint32_t bits_l = reinterpret_cast<const uint32_t*>(slot)[lane];       // score `lane` of the chunk
             const uint32_t ul = reinterpret_cast<const uint32_t*>(slot + 8)[0];

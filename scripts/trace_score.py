@@ -16,13 +16,13 @@ ops.fullsort_topk(users, items, k, hist=hist)
 torch.cuda.synchronize()
 ws = [b for key, b in ops._ws_cache.items()]
 ws = max(ws, key=lambda b: b.numel())
-ws.view(torch.uint8)[: 20 * 2048 * 8].zero_()
+ws.view(torch.uint8)[: 25 * 2048 * 8].zero_()
 ops.fullsort_topk(users, items, k, hist=hist)
 torch.cuda.synchronize()
-raw = ws.view(torch.uint8)[: 20 * 2048 * 8].cpu().numpy().view(np.uint64).reshape(20, 2048)
+raw = ws.view(torch.uint8)[: 25 * 2048 * 8].cpu().numpy().view(np.uint64).reshape(25, 2048)
 names = {0: "acc_empty ok", 1: "B full ok", 2: "mma issued", 3: "acc_full ok", 4: "ldtm done", 5: "stage empty ok"}
 ev = []
-for w in range(20):
+for w in range(25):
     for x in raw[w]:
         x = int(x)
         if x == 0:
