@@ -589,15 +589,23 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
 // In tc_score_topk_kernel<0> a thread owns one USER: the four warps of a user tile read the tile's four 32-column
 // chunks one after the other and the accumulator goes back to the MMA warp only then — drain (4 x ~400 cycles), hand-
 // over, four MMAs and hand-over are one serial chain per accumulator (~2200 cycles per item tile against 1024 cycles of
-// MMA time).  Here a thread owns one (TMEM lane, 32-column chunk) pair of ALL four accumulators: warp w reads lane
-// quarter w & 3, chunk w >> 2, so the sixteen warps empty an accumulator with ONE tcgen05.ld each and it is handed back
-// ~4x sooner; while they scan accumulator ut the tensor core already refills it.
-// The per-user state moves out of the registers: thresholds and lists live in shared memory, every value at or above
-// its user's threshold is pushed on a CTA-wide ring (sequence-stamped 16-byte entries) and ONE collector warp applies the
-// masks and maintains the lists (lane e holds list entry e: minimum search by warp reduction).  The history ranges that
-// fall inside the CTA's item range are found once per user at kernel start (two binary searches), so the collector's
-// history test is an (almost always empty) scan of that range.  Same candidate set, same (score desc, row asc) order
-// and the same per-CTA output lists as MODE 0: merge_keys_kernel is unchanged.
+// MMA time), and a thread that finds a candidate (masks, list insertion) is late for everything that follows.
+// Here a thread owns one (TMEM lane, 32-column chunk) pair of ALL four accumulators: scan warp w reads lane quarter
+// w & 3, chunk w >> 2, so the sixteen warps empty an accumulator with ONE tcgen05.ld each and hand it back at once.
+// The per-user state moves out of the registers: thresholds, lists and history ranges live in shared memory.  A lane
+// whose chunk holds a value at or above its user's threshold dumps the 32 scores as they are into its warp's own ring
+// (single producer, sequence-stamped slots: eight 16-byte stores and one release store) and goes on; FOUR collector
+// warps — one per TMEM lane quarter, so every user has exactly one writer — pick the chunks up, find the candidates with
+// one vote, apply the masks (pad / segment / history) and maintain the lists (lane e holds list entry e: minimum search
+// by warp reduction), raising the user's threshold when a list is full.  The history entries that fall inside the CTA's
+// item range are located once per user at kernel start (two binary searches), so the collector's history test is an
+// almost always empty scan.  One MMA issuer warp per accumulator (wait + descriptors + 4 MMAs + 2 commits are ~45
+// dependent instructions: with two accumulators per issuer the issuers' instruction stream set the period).
+// Same candidate set, same (score desc, row asc) order and the same per-CTA output lists as MODE 0: merge_keys_kernel is
+// unchanged.  Measured on B200, Q = 1024, N = 10 M, D = 64, k = 20: main pass 1.39 -> 1.09 ms (all four launches 1.48 ->
+// 1.22 ms).  What bounds it now is a scan warp's own chain: four steps per item tile of tcgen05.ld latency (~200 cycles
+// with sixteen readers) + ~45 instructions, ~500 cycles each; two register buffers per warp would hide the load but
+// need ~96 registers x 25 warps (tried with 16-column halves instead: slower, twice the votes and waits per chunk).
 #ifndef OOV_SC2_NCOL
 #define OOV_SC2_NCOL 4
 #endif
@@ -605,9 +613,10 @@ constexpr int SC2_NCOL = OOV_SC2_NCOL;                      // collector warps: 
 constexpr int SC2_RPC = SC_EPI_WARPS / SC2_NCOL;            // rings per collector
 constexpr int SC2_THREADS = (SC_EPI_WARPS + 1 + SC_NUT + SC2_NCOL) * 32;   // 800: 16 scan warps, TMA, 4 MMA issuers, 4 collectors
 constexpr int SC2_W_COLLECT = SC_EPI_WARPS + 1 + SC_NUT;    // 21 .. 24
-constexpr int SC2_RS = 8;                                   // hit-chunk slots per scan warp (single producer ring)
+constexpr int SC2_RS = 4;                                   // hit-chunk slots per scan warp (single producer ring)
+constexpr int SC2_POOL = 2048;                              // masked local rows of the CTA's 512 users that lie in the CTA's tiles
 constexpr int SC2_SLOT_U4 = 9;                              // a slot: 32 scores (128 B) + {user column, first local row, sequence, -}
-constexpr int SC2_RING_BYTES = SC_EPI_WARPS * SC2_RS * SC2_SLOT_U4 * 16;     // 18 KB
+constexpr int SC2_RING_BYTES = SC_EPI_WARPS * SC2_RS * SC2_SLOT_U4 * 16;     // 9 KB
 
 // -DOOV_SCORE_TRACE: clock-stamped events of CTA (0, 0) into p.pub (unused by this kernel): per warp 2048 64-bit slots,
 // slot = clock << 24 | event << 20 | ut << 16 | tile.  scripts/trace_score.py prints the timeline.
@@ -638,7 +647,7 @@ __device__ __forceinline__ uint32_t lds_acquire(const uint32_t* p) {
     return v;
 }
 __device__ __forceinline__ void sts_release(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");     // (measured: the fence costs nothing here)
 }
 
 __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long x) {
@@ -661,9 +670,10 @@ tc_score_main2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_cons
     uint4* ring = reinterpret_cast<uint4*>(lists_lo + (size_t)p.k * SC_UG);             // [16 warps][SC2_RS] hit-chunk slots
     float* thr_s = reinterpret_cast<float*>(ring + SC2_RING_BYTES / 16);                // [SC_UG] score filter per user
     uint32_t* cnt_s = reinterpret_cast<uint32_t*>(thr_s + SC_UG);                       // [SC_UG] valid list entries
-    int32_t* h_lo = reinterpret_cast<int32_t*>(cnt_s + SC_UG);                          // [SC_UG] history range inside this
-    int32_t* h_hi = h_lo + SC_UG;                                                        //         CTA's item rows
-    uint64_t* bars = reinterpret_cast<uint64_t*>(h_hi + SC_UG);
+    int32_t* h_lo = reinterpret_cast<int32_t*>(cnt_s + SC_UG);                          // [SC_UG] the user's masked rows inside this CTA's
+    int32_t* h_hi = h_lo + SC_UG;                                                        //         tiles: pool[h_lo .. h_hi); h_hi < 0: not pooled
+    uint32_t* pool = reinterpret_cast<uint32_t*>(h_hi + SC_UG);                          // [SC2_POOL] local rows
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pool + SC2_POOL);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + SC_MAX_STAGES;
     uint64_t* a_full = bars + 2 * SC_MAX_STAGES;
@@ -671,14 +681,19 @@ tc_score_main2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_cons
     uint64_t* acc_empty = acc_full + SC_NUT;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + SC_NUT);
     uint32_t* done_cnt = tmem_slot + 1;
+    uint32_t* pool_n = tmem_slot + 2;
     uint32_t* head_s = tmem_slot + 4;                                                    // [16] slots the collector has consumed, per scan warp
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t q0 = (int64_t)blockIdx.y * SC_UG;
     const int64_t q_left = p.Q - q0;
     const int n_ut = q_left >= SC_UG ? SC_NUT : (int)((q_left + SC_BM - 1) / SC_BM);
-    const int64_t t0 = p.n_visit * blockIdx.x / gridDim.x;
-    const int64_t t1 = p.n_visit * (blockIdx.x + 1) / gridDim.x;
+    // Item tiles are dealt to the CTAs of a user group round-robin (visit i of this CTA is tile tile_begin + blockIdx.x +
+    // i * gridDim.x): candidates cluster where the scores are large (e.g. the OOV half of the table), contiguous ranges
+    // left half of the CTAs with 40x the hits of the other half and the kernel as slow as its busiest CTA.
+    const int64_t t0 = 0;
+    const int64_t t1 = (int64_t)blockIdx.x < p.n_visit ? (p.n_visit - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+#define SC2_TILE(t_) (p.tile_begin + (int64_t)blockIdx.x + (t_) * (int64_t)gridDim.x)
     const int k = p.k;
     [[maybe_unused]] int tr_n = 0;
 
@@ -688,13 +703,14 @@ tc_score_main2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_cons
         mbar_init(a_full, 1);
         for (int a = 0; a < SC_NUT; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], SC_EPI_WARPS); }
         fence_barrier_init();
-        *done_cnt = 0u;
+        *done_cnt = 0u; *pool_n = 0u;
         for (int w = 0; w < SC_EPI_WARPS; ++w) head_s[w] = 0u;
     }
     if (warp == SC_W_ALLOC) tmem_alloc(tmem_slot, 512);
     for (int i = threadIdx.x; i < SC2_RING_BYTES / 16; i += SC2_THREADS) ring[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
     if (threadIdx.x < SC_UG) {
-        // per-user set-up by thread = user column: threshold, empty list, history entries inside this CTA's rows
+        // per-user set-up by thread = user column: threshold, empty list, masked rows inside this CTA's tiles
         const int ul = threadIdx.x;
         const int64_t user = q0 + ul;
         const bool ok = user < p.Q;
@@ -707,13 +723,30 @@ tc_score_main2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_cons
         cnt_s[ul] = 0u;
         int lo = 0, hi = 0;
         if (ok && p.hist_rowptr != nullptr) {
+            // the user's history is walked twice (count, then copy): the collector tests a candidate against a handful of
+            // rows in shared memory instead of searching the CSR row in global memory
             const int b = p.hist_rowptr[user], e = p.hist_rowptr[user + 1];
-            const int64_t g_lo = (p.tile_begin + t0) * SC_BN + p.item_id_offset, g_hi = (p.tile_begin + t1) * SC_BN + p.item_id_offset;
-            int l = b, h = e;
-            while (l < h) { const int m = (l + h) >> 1; if ((int64_t)p.hist_cols[m] < g_lo) l = m + 1; else h = m; }
-            lo = l; h = e;
-            while (l < h) { const int m = (l + h) >> 1; if ((int64_t)p.hist_cols[m] < g_hi) l = m + 1; else h = m; }
-            hi = l;
+            const uint32_t gx = gridDim.x, x = blockIdx.x;
+            auto mine = [&](int j, uint32_t& row) {
+                const int64_t loc = (int64_t)p.hist_cols[j] - p.item_id_offset;
+                if (loc < 0 || loc >= p.N) return false;
+                const int64_t vt = (loc >> 7) - p.tile_begin;         // SC_BN = 128 rows per tile
+                row = (uint32_t)loc;
+                return vt >= 0 && vt < p.n_visit && (uint32_t)vt % gx == x;
+            };
+            int cnt = 0;
+            uint32_t row;
+            for (int j = b; j < e; ++j) cnt += mine(j, row) ? 1 : 0;
+            if (cnt > 0) {
+                const uint32_t start = atomicAdd(pool_n, (uint32_t)cnt);
+                if (start + (uint32_t)cnt <= (uint32_t)SC2_POOL) {
+                    uint32_t w = start;
+                    for (int j = b; j < e; ++j) if (mine(j, row)) pool[w++] = row;
+                    lo = (int)start; hi = (int)start + cnt;
+                } else {
+                    hi = -1;                                          // pool exhausted (very long histories): search the CSR row
+                }
+            }
         }
         h_lo[ul] = lo; h_hi[ul] = hi;
     }
@@ -728,7 +761,7 @@ tc_score_main2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_cons
             mbar_arrive_expect_tx(a_full, (uint32_t)(n_ut * SC_A_BYTES));
             for (int ut = 0; ut < n_ut; ++ut) tma_load_2d(sA + ut * SC_A_BYTES, &tmU, a_full, 0, (int)(q0 + ut * SC_BM));
             for (int64_t t = t0; t < t1 && t < t0 + SC_L2_AHEAD; ++t)
-                tma_prefetch_l2_2d(&tmI, 0, (int)((p.tile_begin + t) * SC_BN));
+                tma_prefetch_l2_2d(&tmI, 0, (int)(SC2_TILE(t) * SC_BN));
         }
         __syncwarp();
         int stage = 0; uint32_t phase = 0;
@@ -736,9 +769,9 @@ tc_score_main2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_cons
             mbar_wait(&empty_bar[stage], phase ^ 1);
             STRACE(5, 0, t);
             if (leader) {
-                if (t + SC_L2_AHEAD < t1) tma_prefetch_l2_2d(&tmI, 0, (int)((p.tile_begin + t + SC_L2_AHEAD) * SC_BN));
+                if (t + SC_L2_AHEAD < t1) tma_prefetch_l2_2d(&tmI, 0, (int)(SC2_TILE(t + SC_L2_AHEAD) * SC_BN));
                 mbar_arrive_expect_tx(&full_bar[stage], SC_B_BYTES);
-                tma_load_2d(sB + stage * SC_B_BYTES, &tmI, &full_bar[stage], 0, (int)((p.tile_begin + t) * SC_BN));
+                tma_load_2d(sB + stage * SC_B_BYTES, &tmI, &full_bar[stage], 0, (int)(SC2_TILE(t) * SC_BN));
             }
             __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -784,7 +817,7 @@ tc_score_main2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_cons
         uint32_t my_tail = 0;                                         // warp-uniform
         uint32_t acc_phase = 0;
         for (int64_t t = t0; t < t1; ++t) {
-            const uint32_t col0 = (uint32_t)((p.tile_begin + t) * SC_BN) + (uint32_t)(c * 32);    // local item row of v[0]
+            const uint32_t col0 = (uint32_t)(SC2_TILE(t) * SC_BN) + (uint32_t)(c * 32);    // local item row of v[0]
 #pragma unroll 1
             for (int ut = 0; ut < n_ut; ++ut) {
                 const float thr = thr_s[ut * SC_BM + ul0];
@@ -836,7 +869,11 @@ tc_score_main2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_cons
             acc_phase ^= 1;
         }
         __syncwarp();
-        if (lane == 0) { asm volatile("fence.acq_rel.cta;" ::: "memory"); atomicAdd(done_cnt, 1u); }
+        if (lane == 0) {
+            if (p.debug & 32) atomicAdd(p.pub + blockIdx.y * gridDim.x + blockIdx.x, my_tail);      // OOV_SCORE_DEBUG=32: hit chunks per CTA
+            asm volatile("fence.acq_rel.cta;" ::: "memory");
+            atomicAdd(done_cnt, 1u);
+        }
     } else if (warp >= SC2_W_COLLECT) {
         // ===================== collectors: masks + list maintenance =====================
         // Collector cq serves the rings of the scan warps w with w % SC2_NCOL == cq, i.e. of the lane quarters congruent to
@@ -897,10 +934,15 @@ tc_score_main2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_cons
                 if (row >= n_rows) continue;                          // zero-filled rows past the end of the shard
                 float sc = __uint_as_float(bits);
                 bool masked = row == pad_row || row < seg_lo || row >= seg_hi;
-                if (!masked && h0 < h1) {                             // rare: this user has history inside the CTA's rows
+                if (!masked && h0 < h1) {                             // rare: this user has masked rows inside the CTA's tiles
+                    bool found = false;
+                    for (int jj = h0 + lane; jj < h1; jj += 32) found |= pool[jj] == row;
+                    masked = __any_sync(0xffffffffu, found);
+                } else if (!masked && h1 < 0) {                       // not pooled: the user's CSR row in global memory
+                    const int64_t user = q0 + ul;
                     const int64_t gid = (int64_t)row + p.item_id_offset;
                     bool found = false;
-                    for (int jj = h0 + lane; jj < h1; jj += 32) found |= (int64_t)p.hist_cols[jj] == gid;
+                    for (int jj = p.hist_rowptr[user] + lane; jj < p.hist_rowptr[user + 1]; jj += 32) found |= (int64_t)p.hist_cols[jj] == gid;
                     masked = __any_sync(0xffffffffu, found);
                 }
                 if (masked) sc = -INFINITY;
@@ -1038,16 +1080,24 @@ static size_t score_smem_bytes(int k, int stages) {
 }
 // column-split main pass: lists, candidate ring, per-user threshold / count / history range
 static size_t score2_fixed_bytes(int k) {
-    return 1024 + SC_NUT * SC_A_BYTES + (size_t)k * SC_UG * 8 + (size_t)SC2_RING_BYTES + (size_t)SC_UG * 16 + 512;
+    return 1024 + SC_NUT * SC_A_BYTES + (size_t)k * SC_UG * 8 + (size_t)SC2_RING_BYTES + (size_t)SC_UG * 16 + (size_t)SC2_POOL * 4 + 512;
 }
 static int score2_stages(int k) {
     int s = (int)((SC_SMEM_MAX - score2_fixed_bytes(k)) / SC_B_BYTES);
     return s > SC_MAX_STAGES ? SC_MAX_STAGES : s;
 }
-static bool score2_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("OOV_SCORE_MAIN2"); v = e ? atoi(e) : 1; }      // profiling only; 0 = MODE 0 main pass
-    return v != 0;
+// Which main pass follows the sampled pre-pass.  The column-split kernel wins while hits are rare — every hit chunk makes
+// one scan warp late — and loses to MODE 0 (every thread maintains its own user's list, 512 in parallel) when they are
+// not: a user sees ~(k + masked) x stride items above the sampled threshold, whatever N is, so the hit chunks per item
+// tile and CTA are ~(k + 4) x stride x 512 / tiles.  Measured on B200 (Q = 1024, k = 20): 2.4 per tile (10 M items,
+// stride 16) 1.60 -> 1.34 ms; 6 per tile (1 M items, stride 4, candidates clustered in the OOV half) 0.23 -> 0.36 ms.
+// OOV_SCORE_MAIN2 (read on every call; tests and profiling): 0 = never, 2 = whenever the pre-pass runs, else automatic.
+static bool score2_wanted(int k, int64_t stride, int64_t n_tiles) {
+    const char* e = getenv("OOV_SCORE_MAIN2");
+    const int mode = e ? atoi(e) : 1;
+    if (mode == 0) return false;
+    if (mode == 2) return true;
+    return (int64_t)(k + 4) * stride * SC_UG <= 3 * n_tiles;
 }
 
 bool score_tc_supported(int dtype, int D, int k) {
@@ -1175,7 +1225,11 @@ int score_tc_run(const void* users, const void* items, int64_t Q, int64_t N, int
             const_cast<uint32_t*>(p.thr_init));
         OOV_LAUNCH_CHECK("score_threshold_kernel");
     }
-    if (pre_stride > 0 && !p.share && !p.debug && score2_enabled() && score2_stages(k) >= 2) {
+    if (pre_stride > 0 && !p.share && !(p.debug & ~32) && score2_stages(k) >= 2 && score2_wanted(k, pre_stride, n_tiles)) {
+        if (p.debug & 32) {
+            cudaError_t ce = cudaMemsetAsync(p.pub, 0, (size_t)gx * cdiv(Q, SC_UG) * 4, st);
+            OOV_REQUIRE(ce == cudaSuccess, OOV_ERR_CUDA, "cudaMemsetAsync(hit counters): %s", cudaGetErrorString(ce));
+        }
         cudaError_t e = cudaFuncSetAttribute(tc_score_main2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM_MAX);
         OOV_REQUIRE(e == cudaSuccess, OOV_ERR_CUDA, "cudaFuncSetAttribute(tc_score_main2_kernel): %s", cudaGetErrorString(e));
         p.stages = score2_stages(k);

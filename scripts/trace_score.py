@@ -7,7 +7,7 @@ from oov_b200 import ops
 
 dev = "cuda:0"
 torch.manual_seed(0)
-D, k, Q, N = 64, 20, 1024, 10_000_000
+D, k, Q, N = 64, 20, 1024, int(os.environ.get('N', 10_000_000))
 users = (torch.randn(Q, D, device=dev) * 0.3).to(torch.bfloat16)
 items = (torch.randn(N, D, device=dev) * 0.3).to(torch.bfloat16)
 hu = torch.randint(0, Q, (25 * Q,), device=dev); hi = torch.randint(1, N, (25 * Q,), device=dev)
@@ -30,7 +30,17 @@ for w in range(25):
         ev.append((x >> 24, w, (x >> 20) & 15, (x >> 16) & 15, x & 0xffff))
 ev.sort()
 tmin = ev[0][0] if ev else 0
-only = set(int(a) for a in sys.argv[1].split(",")) if len(sys.argv) > 1 else {0, 15, 16, 17, 18}
+import collections
+done = collections.defaultdict(dict)
 for c, w, e, ut, t in ev:
-    if w in only and 41 <= t < 43:
-        print(f"{c - tmin:9d}  warp {w:2d}  tile {t:3d} ut {ut}  {names.get(e, e)}")
+    if e == 4:
+        done[(t, ut)][w] = c - tmin
+prev_first = None
+for key in sorted(done):
+    d = done[key]
+    if len(d) < 16 or not (30 <= key[0] < 50):
+        continue
+    first = min(d.values())
+    late = {w: v - first for w, v in d.items() if v - first > 350}
+    print(key, "first", first, "" if prev_first is None else f"(+{first - prev_first})", "spread", max(d.values()) - first, "late warps", late)
+    prev_first = first

@@ -209,6 +209,52 @@ def test_tc_score_prepass_history_holds_the_top_items():
         assert ok, f"simt seg={seg}: {msg}"
 
 
+@pytest.fixture
+def main2_env():
+    old = os.environ.get("OOV_SCORE_MAIN2")
+    yield lambda v: os.environ.__setitem__("OOV_SCORE_MAIN2", str(v))
+    if old is None:
+        os.environ.pop("OOV_SCORE_MAIN2", None)
+    else:
+        os.environ["OOV_SCORE_MAIN2"] = old
+
+
+@pytest.mark.parametrize("Q,N,k", [(96, 100_000, 20), (700, 70_001, 24), (1024, 300_000, 20), (513, 40_000, 1)])
+def test_tc_score_column_split_main_pass_equals_thread_per_user_main_pass(Q, N, k, main2_env):
+    """The two main passes behind the sampled threshold (tc_score.cu: MODE 0, thread = user; tc_score_main2_kernel, scan
+    warps + collector warps, round-robin tiles) give the same lists bit for bit — scores, ids and order — on inputs with
+    exact score ties, NaN rows, a pad row, histories made of each user's best items (so sampled maxima are masked items and
+    the collectors' history test is exercised), item-id offsets and kept segments that cut through tiles; and both match
+    the fp32 reference.  OOV_SCORE_MAIN2 = 2 forces the column-split kernel at sizes where the automatic rule would not
+    pick it (it is read on every call)."""
+    from oov_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(Q + N + k)
+    D = 64
+    users = torch.randn(Q, D, generator=g).to(torch.bfloat16).to(DEV)
+    items = torch.randn(N, D, generator=g).to(torch.bfloat16).to(DEV)
+    items[10:20] = items[30:40]                            # exact ties
+    items[N // 2: N // 2 + 300] = items[5:305]             # more ties, in another CTA's tiles
+    items[[77, N - 3]] = float("nan")
+    off = 1000
+    full = users.float() @ items.float().T
+    top = torch.topk(torch.nan_to_num(full, nan=-1e30), 30, dim=1).indices
+    hu = torch.cat([torch.arange(Q, device=DEV).repeat_interleave(30), torch.randint(0, Q, (4 * Q,), generator=g).to(DEV)])
+    hi = torch.cat([top.reshape(-1), torch.randint(0, N, (4 * Q,), generator=g).to(DEV)]) + off
+    hist = ops.pairs_to_csr(hu, hi, Q)
+    for seg in ((0, 1 << 62), (off + N // 5 + 17, off + N - N // 7)):
+        main2_env(0)
+        s0, i0 = ops.fullsort_topk(users, items, k, item_id_offset=off, hist=hist, seg=seg, path=ops.PATH_TCGEN05)
+        main2_env(2)
+        s2, i2 = ops.fullsort_topk(users, items, k, item_id_offset=off, hist=hist, seg=seg, path=ops.PATH_TCGEN05)
+        torch.cuda.synchronize()
+        assert torch.equal(i0, i2), f"seg={seg}: {(i0 != i2).sum().item()} ids differ"
+        assert torch.equal(s0.view(torch.int32), s2.view(torch.int32)), f"seg={seg}: scores differ"
+        ref = _ref_scores(users, items, off, (hu.cpu().numpy(), (hi - 0).cpu().numpy()), seg)
+        ref = np.nan_to_num(ref, nan=np.inf, posinf=np.inf, neginf=-np.inf)             # NaN ranks first
+        ok, msg = o.topk_sets_match(ref, i2.cpu().numpy() - off, k, rtol=1e-5, atol=1e-4)
+        assert ok, f"seg={seg}: {msg}"
+
+
 def test_pairs_to_csr_kernel_matches_torch_path():
     """oov_pairs_to_csr (one CTA: count, scan, scatter, per-row sort) against the torch index plumbing, including
     padding rows (>= Q or negative), duplicate pairs, rows of 33-128 and of more than 128 entries, and an empty batch."""
