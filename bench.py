@@ -155,28 +155,31 @@ class CpuReference:
             self.embed_items = lambda ids: emb(feat, ids)
             self.embed_users = lambda ids: emb(ufeat, ids)
             self.hashing = "torch_hash.py:55-60 restated with numpy GEMMs"
-        self.bounds = [N * i // self.slices for i in range(self.slices + 1)]
+        self.N = N
         self.i = 0
         self.ue = None
         self.best = None
 
     def step(self):
-        """One slice of the item axis (slice 0 also embeds the query users); returns True when a batch completed."""
+        """One slice of the item axis (slice 0 also embeds the query users); returns True when a batch completed.
+        Slice s holds the items s, s + slices, s + 2 slices, ...: every slice has the table's own mix of in-vocab and OOV
+        rows, so every step costs the same and any number of timed steps is an unbiased sample of the batch."""
         o, torch, wl = self.o, self.torch, self.wl
         k = wl["k"]
-        sl = self.i % self.slices
+        S = self.slices
+        sl = self.i % S
         if sl == 0:
             self.ue = torch.from_numpy(o.assemble_rows(self.users, wl["n_old_users"], self.user_table, self.embed_users))
             self.best = None
-        lo, hi = self.bounds[sl], self.bounds[sl + 1]
-        ie = o.assemble_rows(np.arange(lo, hi), self.n_old, self.item_table, self.embed_items)
+        ids = np.arange(sl, self.N, S)
+        ie = o.assemble_rows(ids, self.n_old, self.item_table, self.embed_items)
         s = self.ue @ torch.from_numpy(ie).T
-        if lo == 0:
-            s[:, 0] = -np.inf
-        m = (self.hi >= lo) & (self.hi < hi)
-        s[torch.from_numpy(self.hu[m]), torch.from_numpy(self.hi[m] - lo)] = -np.inf
-        v, ix = torch.topk(s, min(k, hi - lo), dim=-1)
-        ix = ix + lo
+        if sl == 0:
+            s[:, 0] = -np.inf                                   # pad item 0
+        m = (self.hi % S) == sl
+        s[torch.from_numpy(self.hu[m]), torch.from_numpy((self.hi[m] - sl) // S)] = -np.inf
+        v, ix = torch.topk(s, min(k, len(ids)), dim=-1)
+        ix = ix * S + sl
         if self.best is not None:
             v = torch.cat([self.best[0], v], dim=1)
             ix = torch.cat([self.best[1], ix], dim=1)
@@ -184,7 +187,7 @@ class CpuReference:
             ix = torch.gather(ix, 1, sel)
         self.best = (v, ix)
         self.i += 1
-        return sl == self.slices - 1
+        return sl == S - 1
 
     def run(self, steps, warmup, budget_s=None):
         """Times `steps` slices after `warmup` untimed ones (stops early after `budget_s` seconds, never mid-batch when
@@ -205,7 +208,7 @@ class CpuReference:
     def describe(self, n_steps, ms):
         wl = self.wl
         return (f"oracle port of the reference step on {self.threads} host threads at the full size (N={wl['n_items']}, Q={wl['Q']}): "
-                f"{self.slices} item-axis slice(s) per query batch with a running top-k merge, one slice per step, {n_steps} steps of "
+                f"{self.slices} strided item-axis slice(s) (items s, s + {self.slices}, ...: same in-vocab / OOV mix) per query batch with a running top-k merge, one slice per step, {n_steps} steps of "
                 f"{ms:.0f} ms measured, nothing extrapolated; hashing = {self.hashing}")
 
 

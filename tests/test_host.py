@@ -255,3 +255,24 @@ def test_bench_reference_arm_prints_the_contract_line():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     out2 = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=120, cwd=root, env=env)
     assert out2.returncode == 0 and not [ln for ln in out2.stdout.splitlines() if ln.startswith("{")]
+
+
+@pytest.mark.parametrize("name,slices", [("lsh1m", 8), ("dhe100k", 3)])
+def test_bench_cpu_arm_strided_slices_equal_the_unsliced_batch(name, slices):
+    """The CPU arm of bench.py walks the item axis in strided slices (items s, s + S, ...: every slice has the table's
+    mix of in-vocab and OOV rows, so any number of timed steps is representative).  S slices with the running top-k
+    merge give exactly the lists of the unsliced batch."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    wl = dict(b.WORKLOADS[name])
+    wl.update(n_items=20_000, n_old_items=10_000, n_users=2_000, n_old_users=1_000, Q=48)
+    one = b.CpuReference(wl, 1)
+    assert one.step() is True
+    many = b.CpuReference(wl, slices)
+    done = [many.step() for _ in range(slices)]
+    assert done == [False] * (slices - 1) + [True]
+    assert (one.best[1] == many.best[1]).all()
+    np.testing.assert_allclose(one.best[0].numpy(), many.best[0].numpy(), rtol=1e-6, atol=1e-7)
