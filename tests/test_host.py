@@ -261,7 +261,7 @@ def test_bench_reference_arm_prints_the_contract_line():
 def test_bench_cpu_arm_strided_slices_equal_the_unsliced_batch(name, slices):
     """The CPU arm of bench.py walks the item axis in strided slices (items s, s + S, ...: every slice has the table's
     mix of in-vocab and OOV rows, so any number of timed steps is representative).  S slices with the running top-k
-    merge give exactly the lists of the unsliced batch."""
+    merge give the lists of the unsliced batch (ids up to fp32 near-ties)."""
     import importlib.util
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     spec = importlib.util.spec_from_file_location("bench", os.path.join(root, "bench.py"))
@@ -274,5 +274,12 @@ def test_bench_cpu_arm_strided_slices_equal_the_unsliced_batch(name, slices):
     many = b.CpuReference(wl, slices)
     done = [many.step() for _ in range(slices)]
     assert done == [False] * (slices - 1) + [True]
-    assert (one.best[1] == many.best[1]).all()
-    np.testing.assert_allclose(one.best[0].numpy(), many.best[0].numpy(), rtol=1e-6, atol=1e-7)
+    v1, v2 = one.best[0].numpy(), many.best[0].numpy()
+    np.testing.assert_allclose(v1, v2, rtol=1e-5, atol=1e-6)
+    i1, i2 = one.best[1].numpy(), many.best[1].numpy()
+    # the fp32 GEMM blocks a slice differently from the whole table: ids may only differ where neighbouring scores tie
+    diff = i1 != i2
+    if diff.any():
+        gap = np.minimum(np.abs(np.diff(v1, axis=1, prepend=np.inf)), np.abs(np.diff(v1, axis=1, append=-np.inf)))
+        assert (gap[diff] <= 1e-5 * np.abs(v1[diff]) + 1e-6).all()
+        assert diff.mean() < 0.05
