@@ -78,6 +78,7 @@ SIGNATURES = {
                                     c_vp, c_vp]),
     "oov_map_ids": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp]),
     "oov_cross_update": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "oov_pair_topk": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i64, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp]),
 }
 
 _lib = None

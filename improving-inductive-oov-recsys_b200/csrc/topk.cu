@@ -685,6 +685,82 @@ int score_tc_run(const void* users, const void* items, int64_t Q, int64_t N, int
 
 }  // namespace oov
 
+
+// ------------------------------------------------------------------------------------ sampled-candidate evaluation
+// Replaces trainer.py:547-564 / inductive/evaluator.py:116-133 (neg_sample_batch_eval): origin_scores = model.predict(
+// (user, item) pairs) = (user_e * item_e).sum(-1) (bpr.py:146-149), scattered into a [users, N] matrix of -inf, then
+// torch.topk per user.  Here the [users, N] matrix never exists: the pairs arrive as a CSR (row = batch user, cols = the
+// candidate item ids ascending — oov_pairs_to_csr), item_e holds one embedding row per CSR entry, and a row's top-k is
+// selected among ITS candidates only (every other item scores -inf in the reference and can only fill the tail of a row
+// with fewer than k candidates: those slots come back as (-inf, -1)).  Duplicate pairs of a row collapse like the
+// scatter's last-write-wins (equal ids are adjacent in the sorted CSR row).
+//   pair_keys_kernel      : lane = CSR entry of the warp's row: fp32 dot product -> key64 = order_key(score) << 32 | ~id
+//                           (0 for a duplicate).
+//   rows_topk_keys_kernel : warp = row; k rounds of "largest key strictly below the previous winner" among ids inside
+//                           [seg_lo, seg_hi) (keys are distinct within a row, so no entry needs marking) — (score desc,
+//                           id asc), deterministic.
+namespace oov {
+__global__ void __launch_bounds__(256)
+pair_keys_kernel(const void* __restrict__ user_e, int u_dtype, const void* __restrict__ item_e, int i_dtype, int D,
+                 const int32_t* __restrict__ rowptr, const int32_t* __restrict__ cols, int64_t U, int normalize,
+                 unsigned long long* __restrict__ keys) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= U) return;
+    const int b = rowptr[row], e = rowptr[row + 1];
+    for (int j = b + lane; j < e; j += 32) {
+        const int32_t id = cols[j];
+        if (j > b && cols[j - 1] == id) { keys[j] = 0ull; continue; }
+        float acc = 0.f;
+        if (normalize) {
+            // DirectAU.predict (directau.py:75-78,174-181): F.normalize both rows (x / max(|x|_2, 1e-12)), then multiply-sum
+            float su = 0.f, si = 0.f;
+            for (int d = 0; d < D; ++d) {
+                const float u = load_elem(user_e, u_dtype, row * D + d), v = load_elem(item_e, i_dtype, (int64_t)j * D + d);
+                su = fmaf(u, u, su); si = fmaf(v, v, si);
+            }
+            const float nu = fmaxf(sqrtf(su), 1e-12f), ni = fmaxf(sqrtf(si), 1e-12f);
+            for (int d = 0; d < D; ++d)
+                acc += (load_elem(user_e, u_dtype, row * D + d) / nu) * (load_elem(item_e, i_dtype, (int64_t)j * D + d) / ni);
+        } else {
+            for (int d = 0; d < D; ++d)                               // the user row is a broadcast load, the item row this lane's own
+                acc = fmaf(load_elem(user_e, u_dtype, row * D + d), load_elem(item_e, i_dtype, (int64_t)j * D + d), acc);
+        }
+        keys[j] = ((unsigned long long)float_order_key(acc) << 32) | (unsigned long long)(~(uint32_t)id);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+rows_topk_keys_kernel(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ rowptr, int64_t U, int k,
+                      int64_t seg_lo, int64_t seg_hi, float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= U) return;
+    const int b = rowptr[row], e = rowptr[row + 1];
+    unsigned long long last = ~0ull;
+    for (int r = 0; r < k; ++r) {
+        unsigned long long best = 0ull;
+        if (last != 0ull) {
+            for (int j = b + lane; j < e; j += 32) {
+                const unsigned long long x = keys[j];
+                const int64_t id = (int64_t)(~(uint32_t)x);
+                if (x != 0ull && x < last && x > best && id >= seg_lo && id < seg_hi) best = x;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long y = __shfl_xor_sync(0xffffffffu, best, o);
+                best = y > best ? y : best;
+            }
+        }
+        last = best;
+        if (lane == 0) {
+            out_scores[row * k + r] = best ? float_from_order_key((uint32_t)(best >> 32)) : -INFINITY;
+            out_idx[row * k + r] = best ? (int64_t)(~(uint32_t)best) : -1;
+        }
+    }
+}
+}  // namespace oov
+
 using namespace oov;
 
 extern "C" {
@@ -871,6 +947,23 @@ int oov_topk_hits_collectors(const int64_t* idx_all, const int64_t* idx_old, con
     topk_hits_collectors_kernel<<<(unsigned)cdiv(7 * Q * (k + 2), 256), 256, 0, (cudaStream_t)stream>>>(
         idx_all, idx_old, idx_new, Q, k, user_ids, n_old_users, n_old_items, pos_rowptr, pos_cols, reference_compat ? 1 : 0, out);
     OOV_LAUNCH_CHECK("topk_hits_collectors_kernel");
+    return OOV_OK;
+}
+
+int oov_pair_topk(const void* user_e, int32_t u_dtype, const void* item_e, int32_t i_dtype, int32_t D,
+                  const int32_t* rowptr, const int32_t* cols, int64_t U, int64_t n_pairs, int32_t normalize, int32_t k, int64_t seg_lo, int64_t seg_hi,
+                  unsigned long long* keys, int32_t compute_keys, float* out_scores, int64_t* out_idx, void* stream) {
+    OOV_REQUIRE(U >= 0 && n_pairs >= 0 && n_pairs < (1ll << 31) && D > 0 && k > 0 && dtype_ok(u_dtype) && dtype_ok(i_dtype), OOV_ERR_ARG,
+                "oov_pair_topk: bad argument");
+    if (U == 0) return OOV_OK;
+    OOV_REQUIRE(rowptr && out_scores && out_idx && (n_pairs == 0 || (user_e && item_e && cols && keys)), OOV_ERR_ARG, "oov_pair_topk: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (compute_keys && n_pairs > 0) {
+        pair_keys_kernel<<<(unsigned)cdiv(U, 8), 256, 0, st>>>(user_e, u_dtype, item_e, i_dtype, D, rowptr, cols, U, normalize ? 1 : 0, keys);
+        OOV_LAUNCH_CHECK("pair_keys_kernel");
+    }
+    rows_topk_keys_kernel<<<(unsigned)cdiv(U, 8), 256, 0, st>>>(keys, rowptr, U, k, seg_lo, seg_hi, out_scores, out_idx);
+    OOV_LAUNCH_CHECK("rows_topk_keys_kernel");
     return OOV_OK;
 }
 

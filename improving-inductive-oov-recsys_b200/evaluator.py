@@ -172,6 +172,33 @@ class InductiveEvaluator:
             self.collectors[name]._pending.append(lambda r=res, n=name: r.rows_of(n))
         return res
 
+    def neg_sample_batch_eval(self, batched_data) -> BatchResult:
+        """Sampled-negative evaluation (`eval_args.mode: uni250` etc.; reference inductive/evaluator.py:116-133 +
+        the seven collectors): (interaction with USER_ID / ITEM_ID pairs, row_idx, positive_u, positive_i) ->
+        {collector: 'rec.topk' rows} (lazy).  The reference scatters `model.predict` into a [users, N] matrix of -inf and
+        runs topk per collector; here every pair is scored once, the old-items and new-items lists come from the same keys
+        and the all-items list is their merge.  The number of batch users must be passed by the dataloader as
+        `positive_u[-1] + 1` on the HOST (like trainer.py:559 reads it) or as interaction["n_rows"]."""
+        interaction, row_idx, positive_u, positive_i = batched_data
+        users, items = interaction[self.USER_ID], interaction[self.ITEM_ID]
+        try:
+            n_rows = int(interaction["n_rows"])
+        except (KeyError, IndexError, TypeError):
+            n_rows = int(positive_u[-1]) + 1                         # trainer.py:559 (a host read, as in the reference)
+        (s_old, i_old), (s_new, i_new) = self.model.pair_topk(row_idx, users, items, n_rows, self.k,
+                                                              segs=((0, self.n_old_items), (self.n_old_items, INT64_MAX)))
+        _, i_all = ops.topk_merge(torch.stack([s_old, s_new]), torch.stack([i_old, i_new]))
+        dev = self.device
+        users_of_row = torch.zeros(n_rows, dtype=torch.int64, device=dev)
+        users_of_row.index_copy_(0, row_idx.to(dev), users.to(dev))
+        rowptr, cols = ops.pairs_to_csr(positive_u.to(dev), positive_i.to(dev), n_rows)
+        rows = ops.topk_hits_collectors(i_all, i_old, i_new, users_of_row, self.n_old_users, self.n_old_items, rowptr, cols,
+                                        reference_compat=self.reference_compat)
+        res = BatchResult(rows)
+        for name in COLLECTORS:
+            self.collectors[name]._pending.append(lambda r=res, n=name: r.rows_of(n))
+        return res
+
     def evaluate_model(self, eval_data, config=None, show_progress=False, inductive=True, n_total_items=None):
         self.model.eval()
         self.tot_item_num = n_total_items if n_total_items is not None else eval_data._dataset.item_num

@@ -132,6 +132,28 @@ class InductiveGeneralRecommender(nn.Module):
         user_e, item_e = self.forward(interaction[self.USER_ID], interaction[self.ITEM_ID])
         return torch.mul(user_e, item_e).sum(dim=1)
 
+    PREDICT_NORMALIZES = False       # `predict` = plain dot product (bpr.py:146-149); DirectAU L2-normalises both sides
+
+    def pair_topk(self, row_idx: torch.Tensor, user_ids: torch.Tensor, item_ids: torch.Tensor, n_rows: int, k: int, segs=(None,)):
+        """Sampled-candidate evaluation, fused: the (user, item) pairs of a NegSampleEvalDataLoader batch (`row_idx[p]` = the
+        pair's batch user, trainer.py:547-564) -> per batch user the top-k of ITS candidates, without `predict` scores in
+        memory or the [users, N] matrix of -inf.  One CSR build, one embed of the candidate items (in CSR order), one embed of
+        the batch users, one scoring kernel, one selection kernel per segment in `segs` ((lo, hi) item-id ranges, None = all).
+        Returns [(scores [n_rows, k], ids [n_rows, k]) per segment]; missing slots are (-inf, -1).  Every row index must
+        lie in [0, n_rows) (the dataloader numbers the batch users 0 .. n_rows - 1)."""
+        dev = self.device
+        row_idx, user_ids, item_ids = row_idx.to(dev), user_ids.to(dev), item_ids.to(dev)
+        rowptr, cols = ops.pairs_to_csr(row_idx, item_ids, n_rows, zero_tail=True)
+        users_of_row = torch.zeros(n_rows, dtype=torch.int64, device=dev)
+        users_of_row.index_copy_(0, row_idx, user_ids)               # all pairs of a row carry the same user id
+        user_e = self._assemble("user", users_of_row, out_dtype=torch.float32)
+        item_e = self._assemble("item", cols.to(torch.int64), out_dtype=torch.float32)
+        out, keys = [], None
+        for seg in segs:
+            s, i, keys = ops.pair_topk(user_e, item_e, rowptr, cols, k, seg=seg, keys=keys, normalize=self.PREDICT_NORMALIZES)
+            out.append((s, i))
+        return out
+
     # --- full-sort: reference-shaped (dense) and fused ------------------------------------------
     def ind_full_sort_predict(self, interaction, item_ids):
         """bpr.py:151-156: flat [Q * N] raw dot products over `item_ids` (dense, for drop-in use)."""
@@ -223,6 +245,8 @@ class DirectAU(InductiveGeneralRecommender):
         self.restore_item_e = None
         self.other_parameter_name = ["restore_user_e", "restore_item_e"]
         self.apply(xavier_normal_initialization)
+
+    PREDICT_NORMALIZES = True        # directau.py:75-78,174-181
 
     def forward(self, user, item):
         return F.normalize(self.get_user_embedding(user), dim=-1), F.normalize(self.get_item_embedding(item), dim=-1)

@@ -522,7 +522,7 @@ def topk_hits_collectors(idx_all, idx_old, idx_new, user_ids, n_old_users: int, 
     return out
 
 
-def pairs_to_csr(rows_idx: torch.Tensor, cols_idx: torch.Tensor, Q: int, col_ranges=None):
+def pairs_to_csr(rows_idx: torch.Tensor, cols_idx: torch.Tensor, Q: int, col_ranges=None, zero_tail: bool = False):
     """(row, item) index pairs (general_dataloader.py:270-292 history_index / positive_u,i) -> CSR
     (int32 rowptr [Q + 1], int32 cols ascending per row).  Rows outside [0, Q) are padding and are dropped; cols has
     the length of the input and is only meaningful up to rowptr[Q].  One kernel, no host sync (graph-capturable), any Q
@@ -540,13 +540,43 @@ def pairs_to_csr(rows_idx: torch.Tensor, cols_idx: torch.Tensor, Q: int, col_ran
     _cuda(cols_idx, "cols_idx", torch.int64)
     rows_idx, cols_idx = rows_idx.contiguous(), cols_idx.contiguous()
     rowptr = torch.empty(Q + 1, dtype=torch.int32, device=rows_idx.device)
-    cols = torch.empty(n, dtype=torch.int32, device=rows_idx.device)
+    cols = (torch.zeros if zero_tail else torch.empty)(n, dtype=torch.int32, device=rows_idx.device)   # zero_tail: entries past rowptr[Q] are 0
     cr = None
     if col_ranges is not None:
         (a0, b0), (a1, b1) = col_ranges
         cr = (C.c_int64 * 4)(int(a0), int(b0), int(a1), int(b1))
     _lib.check(_lib.load().oov_pairs_to_csr(_p(rows_idx), _p(cols_idx), n, Q, cr, _p(rowptr), _p(cols), _stream()))
     return rowptr, cols
+
+
+def pair_topk(user_e: torch.Tensor, item_e: torch.Tensor, rowptr: torch.Tensor, cols: torch.Tensor, k: int,
+              seg: Optional[Tuple[int, int]] = None, keys: Optional[torch.Tensor] = None, normalize: bool = False):
+    """Sampled-candidate evaluation (trainer.py:547-564 / inductive/evaluator.py:116-133 without the [users, N] matrix):
+    row r's top-k (score desc, id asc) among its distinct candidates cols[rowptr[r]:rowptr[r+1]] with score
+    user_e[r] . item_e[j] (fp32; `normalize`: both rows L2-normalised first, DirectAU.predict), optionally only ids in
+    seg = (lo, hi).  Missing slots are (-inf, -1).
+    Returns (scores [U, k] fp32, ids [U, k] int64, keys) — pass `keys` back in to select another segment of the same
+    batch without recomputing the scores."""
+    _cuda(user_e, "user_e")
+    _cuda(item_e, "item_e")
+    _cuda(rowptr, "rowptr", torch.int32)
+    _cuda(cols, "cols", torch.int32)
+    user_e, item_e, rowptr, cols = user_e.contiguous(), item_e.contiguous(), rowptr.contiguous(), cols.contiguous()
+    U, D = user_e.shape
+    n = cols.numel()
+    if rowptr.numel() != U + 1 or item_e.shape != (n, D):
+        raise ValueError("pair_topk: rowptr must be [U + 1] and item_e [len(cols), D]")
+    compute = keys is None
+    if compute:
+        keys = torch.empty((max(n, 1),), dtype=torch.int64, device=user_e.device)
+    elif keys.numel() < n or keys.dtype != torch.int64:
+        raise ValueError("pair_topk: keys must be the int64 tensor a previous call returned")
+    lo, hi = (0, _lib.INT64_MAX) if seg is None else (int(seg[0]), int(seg[1]))
+    out_s = torch.empty((U, k), dtype=torch.float32, device=user_e.device)
+    out_i = torch.empty((U, k), dtype=torch.int64, device=user_e.device)
+    _lib.check(_lib.load().oov_pair_topk(_p(user_e), _dt(user_e), _p(item_e), _dt(item_e), D, _p(rowptr), _p(cols), U, n, int(bool(normalize)), int(k),
+                                         lo, hi, _p(keys), int(compute), _p(out_s), _p(out_i), _stream()))
+    return out_s, out_i, keys
 
 
 # ------------------------------------------------------------------------------------ context models

@@ -288,6 +288,22 @@ int oov_first_order_sum(const int64_t* tokens, int64_t Bn, int32_t fields, const
  * ------------------------------------------------------------------------------------ */
 int oov_cross_update(const void* x0, const void* t, const void* xl, int64_t n_elems, void* out, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Sampled-candidate evaluation (eval side) — replaces trainer.py:547-564 /
+ * inductive/evaluator.py:116-133 (neg_sample_batch_eval: model.predict on (user, item) pairs, scatter into a
+ * [users, N] matrix of -inf, torch.topk) without the [users, N] matrix.
+ * rowptr [U + 1] / cols [n_pairs]: the pairs as a CSR by batch user, item ids ascending per row (oov_pairs_to_csr);
+ * user_e [U, D]; item_e [n_pairs, D]: the embedding of cols[j] in row j (fp32 or bf16 each).
+ * normalize != 0: both rows are L2-normalised first (DirectAU.predict, directau.py:75-78,174-181); 0: plain dot product
+ * (BPR.predict, bpr.py:146-149).
+ * out [U, k]: (score desc, id asc) among the row's distinct candidates with seg_lo <= id < seg_hi; missing slots are
+ * (-inf, -1).  keys: caller workspace of n_pairs 8-byte words; compute_keys = 0 reuses the keys of a previous call
+ * (another segment of the same batch).
+ * ------------------------------------------------------------------------------------ */
+int oov_pair_topk(const void* user_e, int32_t u_dtype, const void* item_e, int32_t i_dtype, int32_t D,
+                  const int32_t* rowptr, const int32_t* cols, int64_t U, int64_t n_pairs, int32_t normalize, int32_t k, int64_t seg_lo, int64_t seg_hi,
+                  unsigned long long* keys, int32_t compute_keys, float* out_scores, int64_t* out_idx, void* stream);
+
 /* inductive_mapper=random (inductive/random_mapper.py:70-130): new_id = id (id < n_old) or
  * n_old + hash(id - n_old) % n_buckets.  fn: 0 mod, 1 fast, 2 3round, 3 64bit. */
 int oov_map_ids(const int64_t* ids, int64_t n, int64_t n_old, int64_t n_buckets, int32_t fn,

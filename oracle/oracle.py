@@ -517,3 +517,22 @@ def dcnv2_forward(x0, cross_w, cross_b, mlp_layers, pred_w, pred_b, structure: s
         top = np.concatenate([c, mlp_bn_relu(x0, mlp_layers, bf16_points)], axis=1)
     z = top @ np.asarray(pred_w, np.float32).reshape(-1) + np.float32(np.asarray(pred_b).reshape(-1)[0])
     return sigmoid(z.astype(np.float32))
+
+
+# ------------------------------------------------------------------------------------ sampled-negative evaluation
+def pair_scores(user_e: np.ndarray, item_e: np.ndarray, normalize: bool = False) -> np.ndarray:
+    """model/general_recommender/bpr.py:146-149 predict: torch.mul(user_e, item_e).sum(dim=1) for aligned [P, D] rows;
+    normalize: directau.py:75-78,174-181 — F.normalize(x, dim=-1) = x / max(|x|_2, 1e-12) on both sides first."""
+    u, v = np.asarray(user_e, np.float32), np.asarray(item_e, np.float32)
+    if normalize:
+        u = u / np.maximum(np.sqrt((u * u).sum(axis=1, keepdims=True, dtype=np.float32)), np.float32(1e-12))
+        v = v / np.maximum(np.sqrt((v * v).sum(axis=1, keepdims=True, dtype=np.float32)), np.float32(1e-12))
+    return (u * v).sum(axis=1, dtype=np.float32)
+
+
+def neg_sample_scores(origin_scores: np.ndarray, row_idx: np.ndarray, col_idx: np.ndarray, n_rows: int, n_items: int) -> np.ndarray:
+    """trainer/trainer.py:559-564 = inductive/evaluator.py:127-133: scores = full((batch_user_num, tot_item_num), -inf);
+    scores[row_idx, col_idx] = origin_scores (duplicate pairs carry the same score)."""
+    s = np.full((n_rows, n_items), -np.inf, dtype=np.float32)
+    s[np.asarray(row_idx), np.asarray(col_idx)] = np.asarray(origin_scores, np.float32)
+    return s

@@ -107,6 +107,7 @@ def oracle_retrieval(case: cases.RetrievalCase, inp: dict) -> dict:
     out["oov_item_emb"] = ei(oov_items)
     out["user_e"] = o.assemble_rows(inp["users"], case.n_old_users, inp["user_table"], eu)
     out["all_item_e"] = o.assemble_rows(np.arange(case.n_all_items), case.n_old_items, inp["item_table"], ei)
+    out["all_user_e"] = o.assemble_rows(np.arange(case.n_all_users), case.n_old_users, inp["user_table"], eu)
     out["scores_raw"] = o.full_sort_scores(out["user_e"], out["all_item_e"])
     out["scores_masked"] = o.mask_scores(out["scores_raw"], inp["hist_u"], inp["hist_i"])
     out["topk_vals"], out["topk_idx"] = o.topk(out["scores_masked"], case.k)
@@ -147,3 +148,21 @@ def pairs_to_csr_host(rows_idx, cols_idx, Q, col_ranges=None):
     c = (key & 0xFFFFFFFF).to(torch.int32)
     rowptr = torch.searchsorted(r, torch.arange(Q + 1, device=key.device, dtype=torch.int64))
     return rowptr.to(torch.int32), c
+
+
+def sampled_rows_match(dense_seg: np.ndarray, got_s: np.ndarray, got_i: np.ndarray, k: int, rtol=1e-5, atol=1e-6):
+    """Per row of a sampled-candidate top-k: the first n = min(k, #finite candidates) slots are a tie-aware top-n of the
+    row's dense (-inf elsewhere) scores with matching values, the remaining slots are (-inf, -1)."""
+    for r in range(dense_seg.shape[0]):
+        fin = np.isfinite(dense_seg[r]) | np.isnan(dense_seg[r])
+        n = min(k, int(fin.sum()))
+        assert (got_i[r, n:] == -1).all() and np.isneginf(got_s[r, n:]).all(), (r, n, got_i[r])
+        if n == 0:
+            continue
+        ok, msg = o.topk_sets_match(dense_seg[r:r + 1], got_i[r:r + 1, :n], n, rtol=rtol, atol=atol)
+        assert ok, f"row {r}: {msg}"
+        np.testing.assert_allclose(got_s[r, :n], dense_seg[r, got_i[r, :n]], rtol=rtol, atol=atol)
+        key = o.order_key(got_s[r, :n])
+        assert (key[:-1] >= key[1:]).all()
+        tie = key[:-1] == key[1:]
+        assert (got_i[r, :n][:-1][tie] < got_i[r, :n][1:][tie]).all()        # (score desc, id asc)

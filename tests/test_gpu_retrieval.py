@@ -1,6 +1,8 @@
 """GPU parity (B200): LSH / SLSH / mean / zero embedders, fused assemble, dense scores, fused
 score+mask+top-k and the collectors — product path (through the C-ABI) vs the golden fixtures of the
 unmodified reference and vs the oracle on the same seeded inputs."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -296,3 +298,52 @@ def test_inductive_evaluator_default_mode_vs_oracle(name, G):
         assert (got[clear][:, :-1] == want[clear]).all(), cname
         acc = ev.collectors[cname].get_data_struct()["rec.topk"].numpy()
         assert (acc == got).all(), cname
+
+
+@pytest.mark.parametrize("name", ["bpr_lsh_ml100k", "directau_slsh", "bpr_mean"])
+def test_sampled_negative_eval_vs_reference_golden(name, G):
+    """SURVEY §8f row 4 (eval side): `model.pair_topk` — CSR of the (user, item) pairs, one embed of the candidates, fp32
+    dot products, per-row selection — against the reference's neg_sample_batch_eval matrix (tests/golden/sampled_eval.npz:
+    model.predict scattered into [users, N] of -inf) for the all / old-items / new-items segments: tie-aware sets, values
+    rtol 1e-5, (score desc, id asc) order, (-inf, -1) where a row has fewer than k candidates (rows with 5 + positives
+    candidates and duplicate pairs are in the fixture).  Then `InductiveEvaluator.neg_sample_batch_eval`: its seven
+    collectors equal `topk_hits_collectors` on those lists."""
+    import oov_b200
+    from oov_b200 import ops
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sampled_eval.npz"))
+    case = cases.CASES[name]
+    inp = cases.retrieval_inputs(case)
+    cfg, emb, model = G.build_retrieval(case, inp)
+    rows, us, its = g[f"{name}.rows"], g[f"{name}.users"], g[f"{name}.items"]
+    pos_u, pos_i = g[f"{name}.pos_u"], g[f"{name}.pos_i"]
+    n_rows = int(rows.max()) + 1
+    dense = g[f"{name}.scores_dense"]
+    segs = ((0, 1 << 62), (0, case.n_old_items), (case.n_old_items, 1 << 62))
+    # pairs in a shuffled order: the CSR build sorts them
+    perm = np.random.default_rng(3).permutation(rows.size)
+    out = model.pair_topk(G.t(rows[perm]), G.t(us[perm]), G.t(its[perm]), n_rows, case.k, segs=segs)
+    lists = []
+    for (s_, i_), (lo, hi) in zip(out, segs):
+        seg = dense.copy()
+        seg[:, :lo] = -np.inf
+        seg[:, min(hi, case.n_all_items):] = -np.inf
+        pu.sampled_rows_match(seg, s_.cpu().numpy(), i_.cpu().numpy(), case.k)
+        lists.append(i_)
+    # all-items list == merge of the two segment lists
+    ms, mi = ops.topk_merge(torch.stack([out[1][0], out[2][0]]), torch.stack([out[1][1], out[2][1]]))
+    assert torch.equal(mi, out[0][1]) and torch.equal(ms, out[0][0])
+    ev = oov_b200.InductiveEvaluator(model, cfg, case.n_old_users, case.n_old_items)
+    batch = ({"user_id": G.t(us), "item_id": G.t(its)}, G.t(rows), G.t(pos_u), G.t(pos_i))
+    res = ev.neg_sample_batch_eval(batch)
+    users_of_row = torch.zeros(n_rows, dtype=torch.int64, device=G.DEV)
+    users_of_row[G.t(rows)] = G.t(us)
+    rp, pc = ops.pairs_to_csr(G.t(pos_u), G.t(pos_i), n_rows)
+    want = ops.topk_hits_collectors(lists[0], lists[1], lists[2], users_of_row, case.n_old_users, case.n_old_items, rp, pc)
+    assert torch.equal(res.device_rows, want)
+    overall = res["overall"].numpy()
+    assert overall.shape == (n_rows, case.k + 1)
+    pos = set(zip(pos_u.tolist(), pos_i.tolist()))
+    idx_all = lists[0].cpu().numpy()
+    hits = np.array([[1 if (r, int(i)) in pos else 0 for i in idx_all[r]] for r in range(n_rows)])
+    assert (overall[:, :-1] == hits).all() and (overall[:, -1] == np.bincount(pos_u, minlength=n_rows)).all()
+    assert hits.sum() > 0

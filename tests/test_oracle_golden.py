@@ -181,3 +181,30 @@ def test_oracle_dcnv2_tower_vs_reference(structure):
         w, b = o.fold_bn(L)
         h = np.maximum(h @ w.T + b, 0)
     np.testing.assert_allclose(h, g[pre + "deep_out"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["bpr_lsh_ml100k", "directau_slsh", "bpr_mean"])
+def test_oracle_sampled_negative_eval_vs_reference(name):
+    """oracle.pair_scores / neg_sample_scores against the reference's model.predict on (user, item) pairs and
+    InductiveEvaluator.neg_sample_batch_eval (tests/golden/make_golden_sampled.py): origin scores rtol 1e-5, the dense
+    [users, N] matrix equal where finite and -inf elsewhere, per-segment top-k sets tie-aware."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sampled_eval.npz"))
+    case = cases.CASES[name]
+    inp = cases.retrieval_inputs(case)
+    ora = pu.oracle_retrieval(case, inp)
+    rows, us, its = g[f"{name}.rows"], g[f"{name}.users"], g[f"{name}.items"]
+    origin = o.pair_scores(ora["all_user_e"][us], ora["all_item_e"][its], normalize=case.model == "DirectAU")
+    pu.assert_close(origin, g[f"{name}.origin_scores"], what="origin scores")
+    n_rows = int(rows.max()) + 1
+    dense = o.neg_sample_scores(origin, rows, its, n_rows, case.n_all_items)
+    want = g[f"{name}.scores_dense"]
+    assert (np.isneginf(dense) == np.isneginf(want)).all()
+    fin = ~np.isneginf(want)
+    pu.assert_close(dense[fin], want[fin], what="dense scores")
+    for nm, lo, hi in (("all", 0, case.n_all_items), ("old", 0, case.n_old_items), ("new", case.n_old_items, case.n_all_items)):
+        seg = want.copy()
+        seg[:, :lo] = -np.inf
+        seg[:, hi:] = -np.inf
+        vals, idx = o.topk(np.where(np.isneginf(seg), seg, dense), case.k)
+        pu.sampled_rows_match(seg, np.where(np.isfinite(vals) | np.isnan(vals), vals, -np.inf),
+                              np.where(np.isneginf(vals), -1, idx), case.k)
