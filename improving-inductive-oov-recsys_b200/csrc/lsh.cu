@@ -501,7 +501,7 @@ int oov_lsh_embed(const float* feat, int64_t n_feat_rows, int32_t F, const float
     cudaStream_t st = (cudaStream_t)stream;
     // tensor cores (split-bf16 exact-sign GEMM fused with the bucket-mean GEMM) when the tile shapes allow
     const bool tc_ok = tc::lsh_tc_supported(F, B, rows->D);
-    OOV_REQUIRE(path != OOV_PATH_TCGEN05 || tc_ok, OOV_ERR_ARG, "oov_lsh_embed: tcgen05 path needs F <= 32 and D <= 64 (F=%d D=%d)", F, rows->D);
+    OOV_REQUIRE(path != OOV_PATH_TCGEN05 || tc_ok, OOV_ERR_ARG, "oov_lsh_embed: tcgen05 path needs F <= 64 and D <= 64 (F=%d D=%d)", F, rows->D);
     if (tc_ok && path != OOV_PATH_SIMT_FP32)
         return tc::lsh_tc_run(feat, n_feat_rows, F, planes, B, W, w_dtype, rows, tie_eps, bits_out, tie_count, workspace,
                               workspace_bytes, st);

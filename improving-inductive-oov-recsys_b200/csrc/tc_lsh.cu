@@ -53,7 +53,8 @@ namespace tc {
 
 constexpr int L_BM = 128;                 // rows per tile
 constexpr int L_BN = 128;                 // planes per N tile
-constexpr int L_FMAX = 32;                // features (K' = 3 * 32 = 96 fp16)
+constexpr int L_FCH = 32;                 // features per K chunk (K' = 3 * 32 = 96 fp16 per chunk)
+constexpr int L_FMAX = 64;                // features: one or two chunks (A' of two chunks fills tensor-memory columns 448-511)
 constexpr int L_DMAX = 64;
 constexpr int L_BSTAGES = 8, L_WSTAGES = 4;   // stages of the B' / bucket-table rings (resident when everything fits)
 constexpr int L_WORKERS = 16;
@@ -69,7 +70,7 @@ constexpr float L_PSCALE = 256.f;                 // length of the rescaled plan
 constexpr float L_NEAR_REL = 3.814697265625e-6f * L_PSCALE;  // 2^-18 |p^|: |R' - x.p^| stays below a quarter of this times |x|
 
 struct LshParams {
-    const float* feat; int64_t n_feat_rows; int F;
+    const float* feat; int64_t n_feat_rows; int F; int FC;   // FC = ceil(F / 32) feature chunks
     const float* planes; int B; int NT;               // NT = ceil(B / 128)
     const int64_t* ids; int64_t ids_stride; int64_t n; int64_t n_old; int64_t prime_pad;
     const void* iv_table; int iv_dtype;
@@ -100,7 +101,7 @@ struct LshParams {
 #endif
 
 // ---------------------------------------------------------------- operand packing (once per call)
-// Bp [NT*128, 64] fp16: row b = [p0 | p1] (32 columns each) of p^ = 256 p / |p|
+// Bp [NT*FC*128, 64] fp16: row (nt * FC + c) * 128 + b % 128 = [p0 | p1] (32 columns each) of features 32 c .. 32 c + 31 of p^ = 256 p / |p|
 //                      (zero for f >= F, b >= B and planes without a finite non-zero norm: those are always re-evaluated)
 // Wt [wsplit*64, NT*128] fp16: rows s*64 + d = piece s of W[., d]; zero padding
 __global__ void lsh_pack_kernel(const float* __restrict__ planes, int B, int F, int NT, const void* __restrict__ W, int w_dtype,
@@ -108,8 +109,12 @@ __global__ void lsh_pack_kernel(const float* __restrict__ planes, int B, int F, 
                                 float* __restrict__ pn_min) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nb = (int64_t)NT * L_BN;
-    if (t < nb * 32) {
-        const int b = (int)(t >> 5), f = (int)(t & 31);
+    const int FC = (F + L_FCH - 1) / L_FCH;
+    if (t < nb * FC * 32) {
+        // row rb of Bp = row (b % 128) of the 128-plane tile nt = b / 128, feature chunk c: tiles are laid out (nt, c)
+        const int64_t rb = t >> 5;
+        const int tile = (int)(rb / L_BN), bl = (int)(rb % L_BN);
+        const int b = (tile / FC) * L_BN + bl, f = (tile % FC) * L_FCH + (int)(t & 31);
         float v = 0.f;
         if (b < B) {
             float s2 = 0.f;
@@ -121,8 +126,8 @@ __global__ void lsh_pack_kernel(const float* __restrict__ planes, int B, int F, 
             }
         }
         const __half p0 = __float2half_rn(v);
-        Bp[(size_t)b * 64 + f] = p0;
-        Bp[(size_t)b * 64 + 32 + f] = __float2half_rn(v - __half2float(p0));
+        Bp[(size_t)rb * 64 + (t & 31)] = p0;
+        Bp[(size_t)rb * 64 + 32 + (t & 31)] = __float2half_rn(v - __half2float(p0));
     }
     if (t < nb * L_DMAX) {
         const int d = (int)(t / nb);
@@ -216,16 +221,18 @@ __device__ __noinline__ float exact_projection_fast(const float* __restrict__ fe
     const float* pr = planes + (size_t)b * F;
     float a = 0.f;
     if ((F & 3) == 0 && ((reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(pr)) & 15) == 0) {
-        float4 xv[L_FMAX / 4], pv[L_FMAX / 4];
+        for (int f0 = 0; f0 < F; f0 += L_FCH) {                        // one chain, f ascending: 32 features per round of loads
+            float4 xv[L_FCH / 4], pv[L_FCH / 4];
 #pragma unroll
-        for (int j = 0; j < L_FMAX / 4; ++j)
-            if (4 * j < F) { xv[j] = __ldg(reinterpret_cast<const float4*>(xr) + j); pv[j] = __ldg(reinterpret_cast<const float4*>(pr) + j); }
+            for (int j = 0; j < L_FCH / 4; ++j)
+                if (f0 + 4 * j < F) { xv[j] = __ldg(reinterpret_cast<const float4*>(xr + f0) + j); pv[j] = __ldg(reinterpret_cast<const float4*>(pr + f0) + j); }
 #pragma unroll
-        for (int j = 0; j < L_FMAX / 4; ++j)
-            if (4 * j < F) {
-                a = fmaf(xv[j].x, pv[j].x, a); a = fmaf(xv[j].y, pv[j].y, a);
-                a = fmaf(xv[j].z, pv[j].z, a); a = fmaf(xv[j].w, pv[j].w, a);
-            }
+            for (int j = 0; j < L_FCH / 4; ++j)
+                if (f0 + 4 * j < F) {
+                    a = fmaf(xv[j].x, pv[j].x, a); a = fmaf(xv[j].y, pv[j].y, a);
+                    a = fmaf(xv[j].z, pv[j].z, a); a = fmaf(xv[j].w, pv[j].w, a);
+                }
+        }
         return a;
     }
     for (int f = 0; f < F; ++f) a = fmaf(__ldg(xr + f), __ldg(pr + f), a);
@@ -262,11 +269,11 @@ __device__ __forceinline__ int64_t gather_fr(const LshParams& p, int64_t tile, i
     }
     return fr;
 }
-__device__ __forceinline__ void gather_load(const LshParams& p, int64_t fr, int part, Gather& gth) {
+__device__ __forceinline__ void gather_load(const LshParams& p, int64_t fr, int f0, Gather& gth) {
     gth.fr = fr;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int f = part * 8 + j;
+        const int f = f0 + j;
         gth.x[j] = (fr >= 0 && f < p.F) ? __ldg(p.feat + fr * p.F + f) : 0.f;
     }
 }
@@ -384,7 +391,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
     const int warp = (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int64_t n_tiles = (p.n + L_BM - 1) / L_BM;
     const int NT = p.NT;
-    const int SB = p.res_b ? NT : L_BSTAGES;                         // stages in use
+    const int SB = p.res_b ? NT * p.FC : L_BSTAGES;                  // stages in use (one B' tile per N tile and feature chunk)
     const int NW = NT * p.wsplit;                                    // bucket-table tiles per row tile
     const int SW = p.res_w ? NW : L_WSTAGES;
     // next row tile of this CTA (at or after t) that holds an OOV id — one byte per tile, written by lsh_flags_kernel
@@ -412,7 +419,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
     constexpr uint32_t ACC2_COL = 256;                               // 64 fp32 columns: S' W
     constexpr uint32_t H_COL = 320;                                  // 2 x 64 columns: S' [128 x 128] fp16, two per column
-    constexpr uint32_t A_COL = 448;                                  // 32 columns: A' [128 x 64] fp16, two per column
+    constexpr uint32_t A_COL = 448;                                  // 32 columns per feature chunk: A' [128 x 64] fp16, two per column (448-511)
 
     // The single-thread roles run with ALL 32 lanes of their warp in uniform control flow and only predicate the TMA / MMA /
     // commit instructions on one elected lane.  Under a divergent `if (lane == 0)` ptxas cannot keep descriptors and
@@ -426,15 +433,16 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         bool b_done = false, w_done = false;                          // resident operands are loaded once
         for (int64_t t = next_oov(blockIdx.x); t < n_tiles && !(b_done && w_done); t = next_oov(t + gridDim.x)) {
             for (int nt = 0; nt < NT; ++nt) {
-                if (!b_done) {
-                    if (!p.res_b) mbar_wait_spin(&b_empty[bst], bphase ^ 1);
-                    if (leader) {
-                        mbar_arrive_expect_tx(&b_full[bst], L_BT_BYTES);
-                        tma_load_2d(sB + bst * L_BT_BYTES, &tmB, &b_full[bst], 0, nt * L_BN);
+                if (!b_done)
+                    for (int c = 0; c < p.FC; ++c) {                  // one B' tile per feature chunk, in consumption order
+                        if (!p.res_b) mbar_wait_spin(&b_empty[bst], bphase ^ 1);
+                        if (leader) {
+                            mbar_arrive_expect_tx(&b_full[bst], L_BT_BYTES);
+                            tma_load_2d(sB + bst * L_BT_BYTES, &tmB, &b_full[bst], 0, (nt * p.FC + c) * L_BN);
+                        }
+                        __syncwarp();
+                        if (++bst == SB) { bst = 0; bphase ^= 1; }
                     }
-                    __syncwarp();
-                    if (++bst == SB) { bst = 0; bphase ^= 1; }
-                }
                 if (!w_done)
                     for (int pc = 0; pc < p.wsplit; ++pc) {
                         if (!p.res_w) mbar_wait_spin(&w_empty[wst], wphase ^ 1);
@@ -465,27 +473,31 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                 const int buf = (int)(g1 & 1);
                 if (leader) LTRACE(0, 1);
                 mbar_wait_spin(&acc1_empty[buf], (uint32_t)(((g1 >> 1) & 1) ^ 1));
-                mbar_wait_spin(&b_full[bs], p.res_b ? 0u : bph);      // resident: phase 0 completed once and for all
-                tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * L_BN);
-                const uint32_t a_tmem = tmem_base + A_COL;
-                const uint64_t bdesc = make_sw128_desc(smem_u32(sB + bs * L_BT_BYTES));
-                if (leader) {
-                    LTRACE(0, 2);
-                    // K = 16 fp16 = 8 TMEM columns of A' (x0: columns 0-15, x1: 16-31) / 32 B of a B' row (p0: bytes 0-63, p1: 64-127)
-                    tc_mma_f16_ts(d_tmem, a_tmem + 0, bdesc + 0, idesc1, 0u);    // x0 p0
-                    tc_mma_f16_ts(d_tmem, a_tmem + 8, bdesc + 2, idesc1, 1u);
-                    tc_mma_f16_ts(d_tmem, a_tmem + 16, bdesc + 0, idesc1, 1u);   // x1 p0
-                    tc_mma_f16_ts(d_tmem, a_tmem + 24, bdesc + 2, idesc1, 1u);
-                    tc_mma_f16_ts(d_tmem, a_tmem + 0, bdesc + 4, idesc1, 1u);    // x0 p1
-                    tc_mma_f16_ts(d_tmem, a_tmem + 8, bdesc + 6, idesc1, 1u);
-                    if (!p.res_b) tc_commit(&b_empty[bs]);
-                    tc_commit(&acc1_full[buf]);
-                    if (nt == NT - 1) tc_commit(a_empty);             // A' may be rebuilt for the next row tile
-                    LTRACE(0, 3);
+                for (int c = 0; c < p.FC; ++c) {                      // K loop over 32-feature chunks (F <= 32: one round)
+                    mbar_wait_spin(&b_full[bs], p.res_b ? 0u : bph);  // resident: phase 0 completed once and for all
+                    tc_fence_after();
+                    const uint32_t a_tmem = tmem_base + A_COL + (uint32_t)(c * 32);
+                    const uint64_t bdesc = make_sw128_desc(smem_u32(sB + bs * L_BT_BYTES));
+                    if (leader) {
+                        LTRACE(0, 2);
+                        // K = 16 fp16 = 8 TMEM columns of A' (x0: columns 0-15, x1: 16-31) / 32 B of a B' row (p0: bytes 0-63, p1: 64-127)
+                        tc_mma_f16_ts(d_tmem, a_tmem + 0, bdesc + 0, idesc1, c ? 1u : 0u);    // x0 p0
+                        tc_mma_f16_ts(d_tmem, a_tmem + 8, bdesc + 2, idesc1, 1u);
+                        tc_mma_f16_ts(d_tmem, a_tmem + 16, bdesc + 0, idesc1, 1u);   // x1 p0
+                        tc_mma_f16_ts(d_tmem, a_tmem + 24, bdesc + 2, idesc1, 1u);
+                        tc_mma_f16_ts(d_tmem, a_tmem + 0, bdesc + 4, idesc1, 1u);    // x0 p1
+                        tc_mma_f16_ts(d_tmem, a_tmem + 8, bdesc + 6, idesc1, 1u);
+                        if (!p.res_b) tc_commit(&b_empty[bs]);
+                        if (c == p.FC - 1) {
+                            tc_commit(&acc1_full[buf]);
+                            if (nt == NT - 1) tc_commit(a_empty);     // A' may be rebuilt for the next row tile
+                        }
+                        LTRACE(0, 3);
+                    }
+                    __syncwarp();
+                    if (++bs == SB) { bs = 0; bph ^= 1; }
                 }
-                __syncwarp();
-                if (++bs == SB) { bs = 0; bph ^= 1; }
             }
             ++T;
         }
@@ -593,11 +605,20 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         // row's near-zero threshold.  Called by every worker thread (it holds a worker barrier).
         auto stage_tile = [&](int64_t fr, int Tn, bool wait_a_empty) {
             Gather gth;
-            gather_load(p, fr, slot, gth);
+            gather_load(p, fr, slot * 8, gth);
             float mx = 0.f, n2 = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) { mx = fmaxf(mx, fabsf(gth.x[j])); n2 = fmaf(gth.x[j], gth.x[j], n2); }
-            bool bad = false;
+            bool bad2 = false;
+            if (p.FC > 1) {
+                // second feature chunk (F > 32): only its maximum and squared norm are needed before the row scale is known;
+                // the values are loaded again (L1 / L2 hits) when they are converted — no registers held across the barrier
+                Gather g2;
+                gather_load(p, fr, L_FCH + slot * 8, g2);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { mx = fmaxf(mx, fabsf(g2.x[j])); n2 = fmaf(g2.x[j], g2.x[j], n2); bad2 |= !(fabsf(g2.x[j]) < INFINITY); }
+            }
+            bool bad = bad2;
 #pragma unroll
             for (int j = 0; j < 8; ++j) bad |= !(fabsf(gth.x[j]) < INFINITY);      // Inf / NaN features: every bit is re-evaluated
             s_mx[slot * L_BM + row] = bad ? INFINITY : mx;
@@ -616,7 +637,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             const uint32_t e = (__float_as_uint(m4) >> 23) & 0xffu;
             const float sc = __uint_as_float((e >= 13u ? (e <= 254u ? 267u - e : 1u) : 254u) << 23);
             // |sc x|: from the squared norm unless that may have under- / overflowed, then from sqrt(F) max|x_i| (looser)
-            const float xn = ((m4 > 1e-15f) & (m4 < 1e15f)) ? sqrtf(nn) * sc : 5.6568542f * m4 * sc;
+            const float xn = ((m4 > 1e-15f) & (m4 < 1e15f)) ? sqrtf(nn) * sc : (p.FC > 1 ? 8.f : 5.6568542f) * m4 * sc;
             my_oov = gth.fr >= 0;
             force = !(m4 < INFINITY) || !(xn < INFINITY);
             // |R' - sc x.p^| < L_NEAR_REL |sc x|; |x.p| < tie_eps (the reported ties) lies inside 256 sc tie_eps / |p|
@@ -637,6 +658,18 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             // K element k lives in column k / 2: the 8 features are 4 columns at offset 4 * slot of each 16-column piece
             tc_st_32x4(a_lane + 0 * 16 + slot * 4, c0[0], c0[1], c0[2], c0[3]);
             tc_st_32x4(a_lane + 1 * 16 + slot * 4, c1[0], c1[1], c1[2], c1[3]);
+            if (p.FC > 1) {                                           // chunk 1 of A': columns 32-63, same layout
+                gather_load(p, gth.fr, L_FCH + slot * 8, gth);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float a = gth.x[2 * j] * sc, b = gth.x[2 * j + 1] * sc;
+                    const __half a0 = __float2half_rn(a), b0 = __float2half_rn(b);
+                    c0[j] = (uint32_t)__half_as_ushort(a0) | ((uint32_t)__half_as_ushort(b0) << 16);
+                    c1[j] = pack_f16x2(a - __half2float(a0), b - __half2float(b0));
+                }
+                tc_st_32x4(a_lane + 32 + 0 * 16 + slot * 4, c0[0], c0[1], c0[2], c0[3]);
+                tc_st_32x4(a_lane + 32 + 1 * 16 + slot * 4, c1[0], c1[1], c1[2], c1[3]);
+            }
             tc_wait_st();
             tc_fence_before();
             __syncwarp();
@@ -657,6 +690,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             // look ahead: request tile tn's feature rows into L2, load the flag and the ids of the tile after it (consumed at
             // the end of this tile: the loads fly while this tile is projected)
             if (fr_n >= 0 && slot * 8 < p.F) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.feat + fr_n * p.F + slot * 8));
+            if (fr_n >= 0 && L_FCH + slot * 8 < p.F) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.feat + fr_n * p.F + L_FCH + slot * 8));
             int64_t tnn = tn + gridDim.x;
             const uint8_t flag_nn = tnn < n_tiles ? p.flags[tnn] : (uint8_t)1;
             int64_t fr_nn = tnn < n_tiles ? gather_fr(p, tnn, row) : -1;
@@ -841,7 +875,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
 // ---------------------------------------------------------------- host
 bool lsh_tc_supported(int F, int B, int D) { return F >= 1 && F <= L_FMAX && D >= 1 && D <= L_DMAX && B >= 1 && B <= (1 << 22); }
 
-static size_t lsh_bp_bytes(int B) { return align_up((size_t)cdiv(B, L_BN) * L_BN * 64 * 2, 1024); }
+static size_t lsh_bp_bytes(int B) { return align_up((size_t)(L_FMAX / L_FCH) * cdiv(B, L_BN) * L_BN * 64 * 2, 1024); }   // sized for two feature chunks
 static size_t lsh_wt_bytes(int B) { return align_up((size_t)2 * L_DMAX * cdiv(B, L_BN) * L_BN * 2, 1024); }
 static size_t lsh_flag_bytes(int64_t n) { return align_up((size_t)cdiv(n, L_BM), 256); }
 size_t lsh_tc_workspace(int64_t n, int B) { return lsh_bp_bytes(B) + lsh_wt_bytes(B) + 512 + lsh_flag_bytes(n) + 1024; }
@@ -862,12 +896,12 @@ int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* plane
     const int NT = (int)cdiv(B, L_BN);
     const int64_t nb = (int64_t)NT * L_BN;
     LshParams p{};
-    p.feat = feat; p.n_feat_rows = n_feat_rows; p.F = F; p.planes = planes; p.B = B; p.NT = NT;
+    p.feat = feat; p.n_feat_rows = n_feat_rows; p.F = F; p.FC = (F + L_FCH - 1) / L_FCH; p.planes = planes; p.B = B; p.NT = NT;
     p.ids = rows->ids; p.ids_stride = rows->ids_stride; p.n = rows->n; p.n_old = rows->n_old; p.prime_pad = rows->prime_pad;
     p.iv_table = rows->iv_table; p.iv_dtype = rows->iv_dtype; p.out = rows->out; p.out_dtype = rows->out_dtype;
     p.out_stride = rows->out_stride; p.D = rows->D;
     p.wsplit = rows->out_dtype == OOV_F32 ? 2 : 1;   // fp16 hi (+ lo) pieces of the fp32 bucket table: 2^-12 (2^-23) relative
-    p.res_b = NT <= L_BSTAGES ? 1 : 0;
+    p.res_b = NT * p.FC <= L_BSTAGES ? 1 : 0;
     p.res_w = NT * p.wsplit <= L_WSTAGES ? 1 : 0;
     p.tie_eps = tie_eps; p.bits_out = bits_out; p.words = (B + 31) / 32; p.tie_count = tie_count; p.pn_min = pn_min; p.wsum = wsum;
     p.Wt = Wt; p.nb = nb; p.flags = flags;
@@ -878,14 +912,14 @@ int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* plane
     const int64_t n_tiles = cdiv(rows->n, L_BM);
     lsh_flags_kernel<<<(unsigned)cdiv(n_tiles, 8), 256, 0, st>>>(rows->ids, rows->ids_stride, rows->n, rows->n_old, flags);
     OOV_LAUNCH_CHECK("lsh_flags_kernel");
-    const int64_t pack_threads = nb * L_DMAX;                        // >= nb * 32
+    const int64_t pack_threads = nb * L_DMAX;                        // >= nb * FC * 32 (FC <= 2)
     lsh_pack_kernel<<<(unsigned)cdiv(pack_threads, 256), 256, 0, st>>>(planes, B, F, NT, W, w_dtype, rows->D, p.wsplit, Bp, Wt, pn_min);
     OOV_LAUNCH_CHECK("lsh_pack_kernel");
     lsh_wsum_kernel<<<L_DMAX, 32, 0, st>>>(Wt, nb, p.wsplit, wsum);
     OOV_LAUNCH_CHECK("lsh_wsum_kernel");
 
     CUtensorMap tmB, tmW;
-    int rc = make_tmap_bf16_2d(&tmB, Bp, 64, (uint64_t)nb, 64 * 2, L_BN);                                     // fp16: same 2-byte boxes
+    int rc = make_tmap_bf16_2d(&tmB, Bp, 64, (uint64_t)nb * p.FC, 64 * 2, L_BN);                                     // fp16: same 2-byte boxes
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&tmW, Wt, (uint64_t)nb, (uint64_t)(p.wsplit * L_DMAX), (uint64_t)nb * 2, L_DMAX);
     if (rc) return rc;

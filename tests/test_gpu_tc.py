@@ -383,7 +383,11 @@ def test_tc_score_shard_merge_equals_global():
 
 @pytest.mark.parametrize("n,F,B,D,dtype", [(1000, 32, 1000, 64, torch.float32), (70_001, 24, 1000, 64, torch.bfloat16),
                                            (513, 4, 100, 16, torch.float32), (300, 13, 3, 10, torch.float32),
-                                           (20_000, 32, 129, 64, torch.float32)])
+                                           (20_000, 32, 129, 64, torch.float32),
+                                           # F > 32: two 32-feature K chunks on the tensor cores (B' ring mode at B = 1000)
+                                           (20_000, 64, 1000, 64, torch.float32), (30_001, 64, 1000, 64, torch.bfloat16),
+                                           (777, 48, 300, 64, torch.float32), (2_000, 33, 1000, 32, torch.float32),
+                                           (1_500, 64, 1100, 64, torch.float32), (900, 40, 500, 16, torch.bfloat16)])
 def test_tc_lsh_matches_simt_bits_and_embeddings(n, F, B, D, dtype):
     """Tensor-core LSH (split-bf16 sign-projection GEMM + multi-hot x bucket-table GEMM) against the fp32 CUDA-core
     path: identical multi-hot bits (both resolve near-zero projections with the same fp32 FMA chain), embeddings within
@@ -422,7 +426,8 @@ def test_tc_lsh_matches_simt_bits_and_embeddings(n, F, B, D, dtype):
 
 @pytest.mark.parametrize("n,F,B,D,dtype", [(40_000, 32, 1000, 64, torch.float32), (40_000, 32, 1000, 64, torch.bfloat16),
                                            (9_000, 32, 1500, 64, torch.bfloat16), (5_000, 20, 2100, 48, torch.float32),
-                                           (3_000, 7, 37, 16, torch.float32)])
+                                           (3_000, 7, 37, 16, torch.float32),
+                                           (40_000, 64, 1000, 64, torch.bfloat16), (6_000, 50, 2100, 64, torch.float32)])
 def test_tc_lsh_deferred_sign_fix_matches_simt(n, F, B, D, dtype):
     """The product path of the tensor-core LSH (no multi-hot words requested): near-zero projections are queued, settled
     with the fp32 FMA chain at the end of the row tile and applied as rank-one corrections.  One wrong sign moves an
