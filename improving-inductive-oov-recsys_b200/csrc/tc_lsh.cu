@@ -221,7 +221,28 @@ __device__ __noinline__ float exact_projection_fast(const float* __restrict__ fe
     const float* pr = planes + (size_t)b * F;
     float a = 0.f;
     if ((F & 3) == 0 && ((reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(pr)) & 15) == 0) {
-        for (int f0 = 0; f0 < F; f0 += L_FCH) {                        // one chain, f ascending: 32 features per round of loads
+        float4 xv[L_FCH / 4], pv[L_FCH / 4];
+#pragma unroll
+        for (int j = 0; j < L_FCH / 4; ++j)
+            if (4 * j < F) { xv[j] = __ldg(reinterpret_cast<const float4*>(xr) + j); pv[j] = __ldg(reinterpret_cast<const float4*>(pr) + j); }
+#pragma unroll
+        for (int j = 0; j < L_FCH / 4; ++j)
+            if (4 * j < F) {
+                a = fmaf(xv[j].x, pv[j].x, a); a = fmaf(xv[j].y, pv[j].y, a);
+                a = fmaf(xv[j].z, pv[j].z, a); a = fmaf(xv[j].w, pv[j].w, a);
+            }
+        return a;
+    }
+    for (int f = 0; f < F; ++f) a = fmaf(__ldg(xr + f), __ldg(pr + f), a);
+    return a;
+}
+// F > 32 (two feature chunks): the same chain, 32 features per round of loads
+__device__ __noinline__ float exact_projection_wide(const float* __restrict__ feat, const float* __restrict__ planes, int F, int64_t fr, int b) {
+    const float* xr = feat + fr * F;
+    const float* pr = planes + (size_t)b * F;
+    float a = 0.f;
+    if ((F & 3) == 0 && ((reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(pr)) & 15) == 0) {
+        for (int f0 = 0; f0 < F; f0 += L_FCH) {
             float4 xv[L_FCH / 4], pv[L_FCH / 4];
 #pragma unroll
             for (int j = 0; j < L_FCH / 4; ++j)
@@ -359,6 +380,7 @@ __device__ __noinline__ uint3 lsh_rare_chunk(const RareArgs a) {
 }
 
 
+template <int FC>      // feature chunks of 32 (compile-time: F <= 32 keeps the one-chunk instruction stream)
 __global__ void __launch_bounds__(L_THREADS, 1)
 tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmW, const LshParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -391,7 +413,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
     const int warp = (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int64_t n_tiles = (p.n + L_BM - 1) / L_BM;
     const int NT = p.NT;
-    const int SB = p.res_b ? NT * p.FC : L_BSTAGES;                  // stages in use (one B' tile per N tile and feature chunk)
+    const int SB = p.res_b ? NT * FC : L_BSTAGES;                  // stages in use (one B' tile per N tile and feature chunk)
     const int NW = NT * p.wsplit;                                    // bucket-table tiles per row tile
     const int SW = p.res_w ? NW : L_WSTAGES;
     // next row tile of this CTA (at or after t) that holds an OOV id — one byte per tile, written by lsh_flags_kernel
@@ -434,11 +456,11 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         for (int64_t t = next_oov(blockIdx.x); t < n_tiles && !(b_done && w_done); t = next_oov(t + gridDim.x)) {
             for (int nt = 0; nt < NT; ++nt) {
                 if (!b_done)
-                    for (int c = 0; c < p.FC; ++c) {                  // one B' tile per feature chunk, in consumption order
+                    for (int c = 0; c < FC; ++c) {                  // one B' tile per feature chunk, in consumption order
                         if (!p.res_b) mbar_wait_spin(&b_empty[bst], bphase ^ 1);
                         if (leader) {
                             mbar_arrive_expect_tx(&b_full[bst], L_BT_BYTES);
-                            tma_load_2d(sB + bst * L_BT_BYTES, &tmB, &b_full[bst], 0, (nt * p.FC + c) * L_BN);
+                            tma_load_2d(sB + bst * L_BT_BYTES, &tmB, &b_full[bst], 0, (nt * FC + c) * L_BN);
                         }
                         __syncwarp();
                         if (++bst == SB) { bst = 0; bphase ^= 1; }
@@ -474,7 +496,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                 if (leader) LTRACE(0, 1);
                 mbar_wait_spin(&acc1_empty[buf], (uint32_t)(((g1 >> 1) & 1) ^ 1));
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * L_BN);
-                for (int c = 0; c < p.FC; ++c) {                      // K loop over 32-feature chunks (F <= 32: one round)
+                for (int c = 0; c < FC; ++c) {                      // K loop over 32-feature chunks (F <= 32: one round)
                     mbar_wait_spin(&b_full[bs], p.res_b ? 0u : bph);  // resident: phase 0 completed once and for all
                     tc_fence_after();
                     const uint32_t a_tmem = tmem_base + A_COL + (uint32_t)(c * 32);
@@ -489,7 +511,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                         tc_mma_f16_ts(d_tmem, a_tmem + 0, bdesc + 4, idesc1, 1u);    // x0 p1
                         tc_mma_f16_ts(d_tmem, a_tmem + 8, bdesc + 6, idesc1, 1u);
                         if (!p.res_b) tc_commit(&b_empty[bs]);
-                        if (c == p.FC - 1) {
+                        if (c == FC - 1) {
                             tc_commit(&acc1_full[buf]);
                             if (nt == NT - 1) tc_commit(a_empty);     // A' may be rebuilt for the next row tile
                         }
@@ -555,7 +577,8 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             for (uint32_t e = (uint32_t)lane; e < nq; e += 32) {
                 const uint32_t ent = q_ent[par * L_QCAP + e];
                 const int r = (int)(ent >> 24), b = (int)((ent >> 1) & 0x7fffffu);
-                const float a = exact_projection_fast(p.feat, p.planes, p.F, s_fr[par * L_BM + r], b);
+                const float a = FC == 1 ? exact_projection_fast(p.feat, p.planes, p.F, s_fr[par * L_BM + r], b)
+                                        : exact_projection_wide(p.feat, p.planes, p.F, s_fr[par * L_BM + r], b);
                 const uint32_t bit = a < 0.f ? 0u : 1u;
                 if (fabsf(a) < p.tie_eps) ++ties;
                 if (bit != (ent & 1u)) f_ent[par * L_QCAP + atomicAdd(&s_fn[par], 1u)] = (ent & ~1u) | bit;
@@ -610,7 +633,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 8; ++j) { mx = fmaxf(mx, fabsf(gth.x[j])); n2 = fmaf(gth.x[j], gth.x[j], n2); }
             bool bad2 = false;
-            if (p.FC > 1) {
+            if (FC > 1) {
                 // second feature chunk (F > 32): only its maximum and squared norm are needed before the row scale is known;
                 // the values are loaded again (L1 / L2 hits) when they are converted — no registers held across the barrier
                 Gather g2;
@@ -637,7 +660,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             const uint32_t e = (__float_as_uint(m4) >> 23) & 0xffu;
             const float sc = __uint_as_float((e >= 13u ? (e <= 254u ? 267u - e : 1u) : 254u) << 23);
             // |sc x|: from the squared norm unless that may have under- / overflowed, then from sqrt(F) max|x_i| (looser)
-            const float xn = ((m4 > 1e-15f) & (m4 < 1e15f)) ? sqrtf(nn) * sc : (p.FC > 1 ? 8.f : 5.6568542f) * m4 * sc;
+            const float xn = ((m4 > 1e-15f) & (m4 < 1e15f)) ? sqrtf(nn) * sc : (FC > 1 ? 8.f : 5.6568542f) * m4 * sc;
             my_oov = gth.fr >= 0;
             force = !(m4 < INFINITY) || !(xn < INFINITY);
             // |R' - sc x.p^| < L_NEAR_REL |sc x|; |x.p| < tie_eps (the reported ties) lies inside 256 sc tie_eps / |p|
@@ -658,7 +681,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             // K element k lives in column k / 2: the 8 features are 4 columns at offset 4 * slot of each 16-column piece
             tc_st_32x4(a_lane + 0 * 16 + slot * 4, c0[0], c0[1], c0[2], c0[3]);
             tc_st_32x4(a_lane + 1 * 16 + slot * 4, c1[0], c1[1], c1[2], c1[3]);
-            if (p.FC > 1) {                                           // chunk 1 of A': columns 32-63, same layout
+            if (FC > 1) {                                           // chunk 1 of A': columns 32-63, same layout
                 gather_load(p, gth.fr, L_FCH + slot * 8, gth);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -690,7 +713,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             // look ahead: request tile tn's feature rows into L2, load the flag and the ids of the tile after it (consumed at
             // the end of this tile: the loads fly while this tile is projected)
             if (fr_n >= 0 && slot * 8 < p.F) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.feat + fr_n * p.F + slot * 8));
-            if (fr_n >= 0 && L_FCH + slot * 8 < p.F) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.feat + fr_n * p.F + L_FCH + slot * 8));
+            if (FC > 1 && fr_n >= 0 && L_FCH + slot * 8 < p.F) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.feat + fr_n * p.F + L_FCH + slot * 8));
             int64_t tnn = tn + gridDim.x;
             const uint8_t flag_nn = tnn < n_tiles ? p.flags[tnn] : (uint8_t)1;
             int64_t fr_nn = tnn < n_tiles ? gather_fr(p, tnn, row) : -1;
@@ -923,10 +946,11 @@ int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* plane
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&tmW, Wt, (uint64_t)nb, (uint64_t)(p.wsplit * L_DMAX), (uint64_t)nb * 2, L_DMAX);
     if (rc) return rc;
-    cudaError_t e = cudaFuncSetAttribute(tc_lsh_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM);
+    auto kern = p.FC == 1 ? tc_lsh_embed_kernel<1> : tc_lsh_embed_kernel<2>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM);
     OOV_REQUIRE(e == cudaSuccess, OOV_ERR_CUDA, "cudaFuncSetAttribute(tc_lsh_embed_kernel): %s", cudaGetErrorString(e));
     const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
-    tc_lsh_embed_kernel<<<grid, L_THREADS, L_SMEM, st>>>(tmB, tmW, p);
+    kern<<<grid, L_THREADS, L_SMEM, st>>>(tmB, tmW, p);
     OOV_LAUNCH_CHECK("tc_lsh_embed_kernel");
     return OOV_OK;
 }
