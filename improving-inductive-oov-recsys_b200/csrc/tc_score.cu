@@ -1090,14 +1090,16 @@ static int score2_stages(int k) {
 // one scan warp late — and loses to MODE 0 (every thread maintains its own user's list, 512 in parallel) when they are
 // not: a user sees ~(k + masked) x stride items above the sampled threshold, whatever N is, so the hit chunks per item
 // tile and CTA are ~(k + 4) x stride x 512 / tiles.  Measured on B200 (Q = 1024, k = 20): 2.4 per tile (10 M items,
-// stride 16) 1.60 -> 1.34 ms; 6 per tile (1 M items, stride 4, candidates clustered in the OOV half) 0.23 -> 0.36 ms.
+// stride 16) 1.60 -> 1.34 ms; 6 per tile (1 M items, stride 4, DHE table) 0.23 -> 0.36 ms.
 // OOV_SCORE_MAIN2 (read on every call; tests and profiling): 0 = never, 2 = whenever the pre-pass runs, else automatic.
 static bool score2_wanted(int k, int64_t stride, int64_t n_tiles) {
     const char* e = getenv("OOV_SCORE_MAIN2");
     const int mode = e ? atoi(e) : 1;
     if (mode == 0) return false;
     if (mode == 2) return true;
-    return (int64_t)(k + 4) * stride * SC_UG <= 3 * n_tiles;
+    // crossover measured on lsh10m shards (stride 16): 5 M rows (5.0 per tile) 0.94 -> 0.88 ms, 2.5 M rows (10 per tile)
+    // 0.57 -> 0.64 ms; 1 M rows at stride 4 (6.3 per tile, DHE table) loses
+    return 2 * (int64_t)(k + 4) * stride * SC_UG <= 11 * n_tiles;
 }
 
 bool score_tc_supported(int dtype, int D, int k) {
