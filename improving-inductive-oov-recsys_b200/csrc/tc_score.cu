@@ -98,6 +98,8 @@ struct ScoreParams {
     uint32_t* tile_max;                 // MODE 1 out: [Q][n_visit] ordered-float key of the user's best score in tile i
     const uint32_t* thr_init;           // MODE 0 in (optional): [Q] key no top-k score is below (0 = none)
     int share;                          // MODE 0: exchange thresholds between the CTAs of a user
+    const uint32_t* choice;             // optional device flag written by score_choose_kernel: 1 = the column-split main pass runs,
+                                        // 0 = the thread-per-user one; the kernel that is not chosen returns at once
 };
 
 // per-thread (= per-user) epilogue state.  The list is UNSORTED and split in two u32 arrays (ordered score / ~row):
@@ -324,6 +326,7 @@ tc_score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_const
     uint64_t* acc_empty = acc_full + SC_NUT;            // [SC_NUT]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + SC_NUT);
 
+    if (MODE == 0 && p.choice != nullptr && *p.choice == 1u) return;  // the column-split main pass was chosen (uniform exit)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t q0 = (int64_t)blockIdx.y * SC_UG;
     const int64_t q_left = p.Q - q0;
@@ -684,6 +687,7 @@ tc_score_main2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_cons
     uint32_t* pool_n = tmem_slot + 2;
     uint32_t* head_s = tmem_slot + 4;                                                    // [16] slots the collector has consumed, per scan warp
 
+    if (p.choice != nullptr && *p.choice != 1u) return;               // the thread-per-user main pass was chosen (uniform exit)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t q0 = (int64_t)blockIdx.y * SC_UG;
     const int64_t q_left = p.Q - q0;
@@ -1002,7 +1006,7 @@ __global__ void __launch_bounds__(THR_WARPS * 32)
 score_threshold_kernel(const uint32_t* __restrict__ tile_max, int64_t n_s, int64_t Q, int k, int64_t tile_first,
                        int64_t tile_stride, int64_t item_id_offset, int64_t N, int mask_pad,
                        const int32_t* __restrict__ hist_rowptr, const int32_t* __restrict__ hist_cols,
-                       uint32_t* __restrict__ thr_out) {
+                       uint32_t* __restrict__ thr_out, uint32_t* __restrict__ tile_hits) {
     __shared__ uint32_t hist_s[THR_WARPS][256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t user = (int64_t)blockIdx.x * THR_WARPS + warp;
@@ -1068,6 +1072,36 @@ score_threshold_kernel(const uint32_t* __restrict__ tile_max, int64_t n_s, int64
         __syncwarp();
     }
     if (lane == 0) thr_out[user] = prefix;
+    if (tile_hits != nullptr)                                         // how many users will see a candidate in sampled tile i
+        for (int64_t i = lane; i < n_s; i += 32)
+            if (__ldg(row + i) >= prefix) atomicAdd(tile_hits + i, 1u);
+}
+
+// Which main pass runs (device-side, so the choice can sit inside a captured graph).  Every user has exactly R sampled
+// tiles at or above its threshold; what differs between tables is how those tiles COINCIDE across users.  With
+// embeddings whose scores are dominated by the item (all-positive DHE rows: an item that scores high does so for every
+// such user) a few dozen tiles are hit by half of all users at once, and a scan warp of the column-split pass then has to
+// hand off up to 32 hit chunks in one step through a 4-slot ring — the thread-per-user pass takes such bursts in
+// parallel.  Statistic: h_i = users with a candidate in sampled tile i; co-hit = sum h_i^2 / sum h_i (how many users share
+// the tile of a random hit) against the mean.  Measured on the bench tables (1953 sampled tiles, mean 12): LSH 27 (2.2 x
+// the mean; main pass 0.52 -> 0.45 ms with the column-split kernel), DHE 296 (25 x; 0.17 -> 0.34 ms).  One tile with a
+// NaN item (a candidate of all 1024 users) adds ~45.  out[0] = 1 (column-split) while co-hit <= SC2_COHIT x mean.
+constexpr unsigned long long SC2_COHIT = 12;
+__global__ void score_choose_kernel(const uint32_t* __restrict__ tile_hits, int64_t n_s, uint32_t* __restrict__ out, int verbose) {
+    __shared__ unsigned long long s_sq[32], s_sum[32];
+    unsigned long long sq = 0ull, sum = 0ull;
+    for (int64_t i = threadIdx.x; i < n_s; i += blockDim.x) { const unsigned long long v = tile_hits[i]; sq += v * v; sum += v; }
+    for (int o = 16; o; o >>= 1) { sq += __shfl_xor_sync(0xffffffffu, sq, o); sum += __shfl_xor_sync(0xffffffffu, sum, o); }
+    if ((threadIdx.x & 31) == 0) { s_sq[threadIdx.x >> 5] = sq; s_sum[threadIdx.x >> 5] = sum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { sq += s_sq[w]; sum += s_sum[w]; }
+        // co-hit <= SC2_COHIT * mean  <=>  sq * n_s <= SC2_COHIT * sum^2   (sum <= Q * R ~ 1e5, sq * n_s < 2^63)
+        out[0] = (sum > 0ull && sq * (unsigned long long)n_s <= SC2_COHIT * sum * sum) ? 1u : 0u;
+        out[1] = (uint32_t)(sum > 0ull ? sq / sum : 0ull); out[2] = (uint32_t)(sum > 0xFFFFFFFFull ? 0xFFFFFFFFull : sum); out[3] = (uint32_t)n_s;
+        if (verbose) printf("score_choose: column-split %u (co-hit %.1f, mean %.1f over %lld sampled tiles)\n", out[0],
+                            sum > 0ull ? (double)sq / (double)sum : 0.0, n_s > 0 ? (double)sum / (double)n_s : 0.0, (long long)n_s);
+    }
 }
 
 static int score_stages(int k) {
@@ -1097,8 +1131,8 @@ static bool score2_wanted(int k, int64_t stride, int64_t n_tiles) {
     const int mode = e ? atoi(e) : 1;
     if (mode == 0) return false;
     if (mode == 2) return true;
-    // crossover measured on lsh10m shards (stride 16): 5 M rows (5.0 per tile) 0.94 -> 0.88 ms, 2.5 M rows (10 per tile)
-    // 0.57 -> 0.64 ms; 1 M rows at stride 4 (6.3 per tile, DHE table) loses
+    // crossover measured on LSH tables: 1.25 M rows at stride 4 (5 hit chunks per tile) 0.318 -> 0.304 ms, 2.5 M rows
+    // 0.52 -> 0.45 ms; below ~8 k tiles the start-up of the 800-thread kernel and the hit rate eat the gain
     return 2 * (int64_t)(k + 4) * stride * SC_UG <= 11 * n_tiles;
 }
 
@@ -1127,27 +1161,38 @@ static int64_t score_pre_stride(int64_t n_full_tiles) {
     if (forced < 0) { const char* e = getenv("OOV_SCORE_STRIDE"); forced = e ? atoi(e) : 0; }   // profiling only; 1 = no pre-pass
     if (forced == 1) return 0;
     if (forced > 1) return forced;
-    int64_t s = 2;
-    while (s < 16 && n_full_tiles / (2 * s) >= 1024) s *= 2;         // keep >= 1024 sampled tiles, at most 1/2 .. 1/16 extra work
-    return s;
+    // The pre-pass costs ~tiles / stride, the candidates it leaves cost ~stride (a user sees ~(k + masked) x stride items
+    // above its threshold whatever N is): measured optima on B200 (Q = 1024, k = 20) — 1 k tiles: 2; 8 k - 20 k tiles: 4
+    // (1.25 M rows 0.343 -> 0.30 ms, 2.5 M rows 0.57 -> 0.45 ms against the old "at least 1024 sampled tiles" rule);
+    // 39 k tiles: 8 (0.875 -> 0.77 ms); 78 k tiles: 16 (stride 8: 1.41 against 1.35 ms).
+    if (n_full_tiles < 4096) return 2;
+    if (n_full_tiles < 32768) return 4;
+    if (n_full_tiles < 65536) return 8;
+    return 16;
 }
 // most tiles any kept segment of an N-row shard can sample (the stride grows with the segment)
 static int64_t score_pre_max_visits(int64_t N) {
     const int64_t nf = N / SC_BN;
     if (score_pre_stride(nf) == 0) return 0;
     int64_t best = 0;
-    for (int64_t s = 2; s <= 16; s *= 2) {                            // segments whose stride is s have < 2048 s tiles (s < 16)
-        const int64_t top = s < 16 ? (nf < 2048 * s ? nf : 2048 * s) : nf;
-        if (cdiv(top, s) > best) best = cdiv(top, s);
+    for (int64_t m = SC_PRE_MIN_TILES; ; m *= 2) {                    // a kept segment has m <= nf full tiles: visits = ceil(m / stride(m))
+        const int64_t mm = m < nf ? m : nf;
+        for (int64_t d = 0; d < 2; ++d) {                             // just below every stride boundary and at the size itself
+            const int64_t x = mm - d > 0 ? mm - d : mm;
+            const int64_t st = score_pre_stride(x);
+            if (st > 0 && cdiv(x, st) > best) best = cdiv(x, st);
+        }
+        if (mm == nf) break;
     }
-    const int64_t f = score_pre_stride(nf);
-    if (f > 0 && cdiv(nf, f) > best) best = cdiv(nf, f);
+    for (int64_t b : {int64_t(4095), int64_t(32767), int64_t(65535)})
+        if (b <= nf && cdiv(b, score_pre_stride(b)) > best) best = cdiv(b, score_pre_stride(b));
     return best;
 }
 static size_t score_thr_bytes(int64_t Q) { return align_up((size_t)Q * 4, 256); }
+static size_t score_hits_bytes(int64_t nv) { return align_up((size_t)nv * 4 + 16, 256); }     // per sampled tile + the 4-word choice record
 static size_t score_pre_bytes(int64_t Q, int64_t N) {
     const int64_t nv = score_pre_max_visits(N);
-    return nv == 0 ? 0 : score_thr_bytes(Q) + align_up((size_t)Q * (size_t)nv * 4, 256);
+    return nv == 0 ? 0 : score_thr_bytes(Q) + align_up((size_t)Q * (size_t)nv * 4, 256) + score_hits_bytes(nv);
 }
 
 size_t score_tc_workspace(int64_t Q, int64_t N, int k) {
@@ -1187,6 +1232,7 @@ int score_tc_run(const void* users, const void* items, int64_t Q, int64_t N, int
     const int64_t full_begin = hi > lo ? cdiv(lo, SC_BN) : 0, full_end = hi > lo ? hi / SC_BN : 0;
     const int64_t pre_stride = score_pre_stride(full_end - full_begin);
     ScoreParams pa = p;
+    uint32_t* tile_hits = nullptr;
     if (pre_stride > 0) {
         pa.stages = SC_MAX_STAGES;                                    // no lists in the pre-pass: the whole shared memory is TMA ring
         pa.tile_begin = full_begin;
@@ -1195,7 +1241,9 @@ int score_tc_run(const void* users, const void* items, int64_t Q, int64_t N, int
         unsigned char* w = reinterpret_cast<unsigned char*>(workspace) + score_pub_bytes(Q, gx) + score_partial_bytes(Q, gx, k);
         uint32_t* thr = reinterpret_cast<uint32_t*>(w);
         pa.tile_max = reinterpret_cast<uint32_t*>(w + score_thr_bytes(Q));
-        const size_t need_pre = (size_t)(w - reinterpret_cast<unsigned char*>(workspace)) + score_thr_bytes(Q) + (size_t)Q * pa.n_visit * 4;
+        const size_t tm_bytes = align_up((size_t)Q * (size_t)pa.n_visit * 4, 256);
+        tile_hits = reinterpret_cast<uint32_t*>(w + score_thr_bytes(Q) + tm_bytes);     // [n_visit] + 4 words (choice, max, sum, n)
+        const size_t need_pre = (size_t)(w - reinterpret_cast<unsigned char*>(workspace)) + score_thr_bytes(Q) + tm_bytes + score_hits_bytes(pa.n_visit);
         OOV_REQUIRE(workspace_bytes >= need_pre, OOV_ERR_WORKSPACE, "oov_fullsort_topk (tcgen05): workspace %zu < %zu (pre-pass)",
                     workspace_bytes, need_pre);
         p.thr_init = thr;
@@ -1219,25 +1267,42 @@ int score_tc_run(const void* users, const void* items, int64_t Q, int64_t N, int
         OOV_REQUIRE(e == cudaSuccess, OOV_ERR_CUDA, "cudaFuncSetAttribute(tc_score_topk_kernel<1>): %s", cudaGetErrorString(e));
     }
     const dim3 grid((unsigned)gx, (unsigned)cdiv(Q, SC_UG));
+    // main pass: the column-split kernel when the table is large enough for it (score2_wanted), chosen against the
+    // thread-per-user kernel ON THE DEVICE from the burstiness of the sampled hits (both are launched, one returns at once)
+    const char* m2 = getenv("OOV_SCORE_MAIN2");
+    const int m2_mode = m2 ? atoi(m2) : 1;
+    const bool try2 = pre_stride > 0 && !p.share && !(p.debug & ~32) && score2_stages(k) >= 2 && score2_wanted(k, pre_stride, n_tiles);
+    const bool adaptive = try2 && m2_mode == 1;
     if (pre_stride > 0) {
         tc_score_topk_kernel<1><<<grid, SC_THREADS, score_smem_bytes(-SC_QCAP, pa.stages), st>>>(tmU, tmI, pa);
         OOV_LAUNCH_CHECK("tc_score_topk_kernel<1> (pre-pass)");
+        if (adaptive) {
+            cudaError_t ce = cudaMemsetAsync(tile_hits, 0, (size_t)pa.n_visit * 4, st);
+            OOV_REQUIRE(ce == cudaSuccess, OOV_ERR_CUDA, "cudaMemsetAsync(tile hits): %s", cudaGetErrorString(ce));
+        }
         score_threshold_kernel<<<(unsigned)cdiv(Q, THR_WARPS), THR_WARPS * 32, 0, st>>>(
             pa.tile_max, pa.n_visit, Q, k, pa.tile_begin, pa.tile_stride, item_id_offset, N, mask_pad, hist_rowptr, hist_cols,
-            const_cast<uint32_t*>(p.thr_init));
+            const_cast<uint32_t*>(p.thr_init), adaptive ? tile_hits : nullptr);
         OOV_LAUNCH_CHECK("score_threshold_kernel");
+        if (adaptive) {
+            score_choose_kernel<<<1, 256, 0, st>>>(tile_hits, pa.n_visit, tile_hits + pa.n_visit, (p.debug & 32) ? 1 : 0);
+            OOV_LAUNCH_CHECK("score_choose_kernel");
+            p.choice = tile_hits + pa.n_visit;
+        }
     }
-    if (pre_stride > 0 && !p.share && !(p.debug & ~32) && score2_stages(k) >= 2 && score2_wanted(k, pre_stride, n_tiles)) {
+    if (try2) {
         if (p.debug & 32) {
             cudaError_t ce = cudaMemsetAsync(p.pub, 0, (size_t)gx * cdiv(Q, SC_UG) * 4, st);
             OOV_REQUIRE(ce == cudaSuccess, OOV_ERR_CUDA, "cudaMemsetAsync(hit counters): %s", cudaGetErrorString(ce));
         }
         cudaError_t e = cudaFuncSetAttribute(tc_score_main2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM_MAX);
         OOV_REQUIRE(e == cudaSuccess, OOV_ERR_CUDA, "cudaFuncSetAttribute(tc_score_main2_kernel): %s", cudaGetErrorString(e));
-        p.stages = score2_stages(k);
-        tc_score_main2_kernel<<<grid, SC2_THREADS, score2_fixed_bytes(k) + (size_t)p.stages * SC_B_BYTES, st>>>(tmU, tmI, p);
+        ScoreParams p2 = p;
+        p2.stages = score2_stages(k);
+        tc_score_main2_kernel<<<grid, SC2_THREADS, score2_fixed_bytes(k) + (size_t)p2.stages * SC_B_BYTES, st>>>(tmU, tmI, p2);
         OOV_LAUNCH_CHECK("tc_score_main2_kernel");
-    } else {
+    }
+    if (!try2 || adaptive) {
         tc_score_topk_kernel<0><<<grid, SC_THREADS, smem, st>>>(tmU, tmI, p);
         OOV_LAUNCH_CHECK("tc_score_topk_kernel");
     }
