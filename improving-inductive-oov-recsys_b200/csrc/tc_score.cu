@@ -617,7 +617,8 @@ constexpr int SC2_RPC = SC_EPI_WARPS / SC2_NCOL;            // rings per collect
 constexpr int SC2_THREADS = (SC_EPI_WARPS + 1 + SC_NUT + SC2_NCOL) * 32;   // 800: 16 scan warps, TMA, 4 MMA issuers, 4 collectors
 constexpr int SC2_W_COLLECT = SC_EPI_WARPS + 1 + SC_NUT;    // 21 .. 24
 constexpr int SC2_RS = 4;                                   // hit-chunk slots per scan warp (single producer ring)
-constexpr int SC2_POOL = 2048;                              // masked local rows of the CTA's 512 users that lie in the CTA's tiles
+constexpr int SC2_HCAP = 4;                                 // masked local rows per user that lie in the CTA's tiles (more: CSR search)
+constexpr int SC2_POOL = SC_UG * SC2_HCAP;
 constexpr int SC2_SLOT_U4 = 9;                              // a slot: 32 scores (128 B) + {user column, first local row, sequence, -}
 constexpr int SC2_RING_BYTES = SC_EPI_WARPS * SC2_RS * SC2_SLOT_U4 * 16;     // 9 KB
 
@@ -684,7 +685,6 @@ tc_score_main2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_cons
     uint64_t* acc_empty = acc_full + SC_NUT;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + SC_NUT);
     uint32_t* done_cnt = tmem_slot + 1;
-    uint32_t* pool_n = tmem_slot + 2;
     uint32_t* head_s = tmem_slot + 4;                                                    // [16] slots the collector has consumed, per scan warp
 
     if (p.choice != nullptr && *p.choice != 1u) return;               // the thread-per-user main pass was chosen (uniform exit)
@@ -707,7 +707,7 @@ tc_score_main2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_cons
         mbar_init(a_full, 1);
         for (int a = 0; a < SC_NUT; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], SC_EPI_WARPS); }
         fence_barrier_init();
-        *done_cnt = 0u; *pool_n = 0u;
+        *done_cnt = 0u;
         for (int w = 0; w < SC_EPI_WARPS; ++w) head_s[w] = 0u;
     }
     if (warp == SC_W_ALLOC) tmem_alloc(tmem_slot, 512);
@@ -727,30 +727,29 @@ tc_score_main2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_cons
         cnt_s[ul] = 0u;
         int lo = 0, hi = 0;
         if (ok && p.hist_rowptr != nullptr) {
-            // the user's history is walked twice (count, then copy): the collector tests a candidate against a handful of
-            // rows in shared memory instead of searching the CSR row in global memory
+            // One walk over the user's history, eight independent loads in flight: the masked rows that lie in this CTA's
+            // tiles go to the user's SC2_HCAP pool slots, so the collector tests a candidate against a few rows in shared
+            // memory; a user with more of them (very long histories) is searched in the CSR row instead.
             const int b = p.hist_rowptr[user], e = p.hist_rowptr[user + 1];
             const uint32_t gx = gridDim.x, x = blockIdx.x;
-            auto mine = [&](int j, uint32_t& row) {
-                const int64_t loc = (int64_t)p.hist_cols[j] - p.item_id_offset;
-                if (loc < 0 || loc >= p.N) return false;
-                const int64_t vt = (loc >> 7) - p.tile_begin;         // SC_BN = 128 rows per tile
-                row = (uint32_t)loc;
-                return vt >= 0 && vt < p.n_visit && (uint32_t)vt % gx == x;
-            };
             int cnt = 0;
-            uint32_t row;
-            for (int j = b; j < e; ++j) cnt += mine(j, row) ? 1 : 0;
-            if (cnt > 0) {
-                const uint32_t start = atomicAdd(pool_n, (uint32_t)cnt);
-                if (start + (uint32_t)cnt <= (uint32_t)SC2_POOL) {
-                    uint32_t w = start;
-                    for (int j = b; j < e; ++j) if (mine(j, row)) pool[w++] = row;
-                    lo = (int)start; hi = (int)start + cnt;
-                } else {
-                    hi = -1;                                          // pool exhausted (very long histories): search the CSR row
+            for (int j0 = b; j0 < e; j0 += 8) {
+                int32_t v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = j0 + i < e ? __ldg(p.hist_cols + j0 + i) : 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (j0 + i >= e) continue;
+                    const int64_t loc = (int64_t)v[i] - p.item_id_offset;
+                    if (loc < 0 || loc >= p.N) continue;
+                    const int64_t vt = (loc >> 7) - p.tile_begin;     // SC_BN = 128 rows per tile
+                    if (vt < 0 || vt >= p.n_visit || (uint32_t)vt % gx != x) continue;
+                    if (cnt < SC2_HCAP) pool[ul * SC2_HCAP + cnt] = (uint32_t)loc;
+                    ++cnt;
                 }
             }
+            if (cnt > SC2_HCAP) hi = -1;
+            else { lo = ul * SC2_HCAP; hi = lo + cnt; }
         }
         h_lo[ul] = lo; h_hi[ul] = hi;
     }
