@@ -293,3 +293,75 @@ class DCNV2(InductiveContextRecommender):
 
     def predict(self, interaction) -> torch.Tensor:
         return self.forward(interaction)
+
+
+class WideDeep(InductiveContextRecommender):
+    """Wide & Deep on the OOV path (reference model/context_aware_recommender/widedeep.py:33-100): the wide part is the
+    D = 1 first-order linear over the token fields with its own OOV embedder (`InductiveFMFirstOrderLinear`,
+    `oov_first_order_sum`), the deep part an MLP (Linear + ReLU, no BatchNorm: MLPLayers defaults) on the flattened
+    `[B, fields * D]` embeddings and a 1-wide `deep_predict_layer`; `predict = sigmoid(wide + deep)`.  The MLP runs on
+    `oov_tc_linear` (bf16 operands, fp32 accumulate, ReLU epilogue); the reference's default widths (32, 16, 8) are small
+    GEMMs — the path is gather / HBM bound (BASELINE configs[3]).  Same parameter names as the reference
+    (`mlp_layers.mlp_layers.*`, `deep_predict_layer.*`, `first_order_linear.*`).  Token fields only; eval mode."""
+
+    def __init__(self, config, field_dims: Sequence[int], inductive_mapper=None, inductive_embedder=None,
+                 first_order_embedder=None, first_order_mapper=None):
+        super().__init__(config, field_dims, inductive_mapper=inductive_mapper, inductive_embedder=inductive_embedder,
+                         first_order_embedder=first_order_embedder, first_order_mapper=first_order_mapper)
+        if not hasattr(self, "first_order_linear"):
+            raise NotImplementedError("WideDeep needs a first-order embedder or mapper for its wide part")
+        try:
+            hidden = config["mlp_hidden_size"]
+        except (KeyError, IndexError):
+            hidden = None
+        self.mlp_hidden_size = list(hidden) if hidden is not None else [32, 16, 8]
+        try:
+            dp = config["dropout_prob"]
+        except (KeyError, IndexError):
+            dp = None
+        self.dropout_prob = 0.1 if dp is None else float(dp)
+        self.num_feature_field = len(field_dims)
+        self.mlp_layers = MLPLayers([self.embedding_size * self.num_feature_field] + self.mlp_hidden_size, self.dropout_prob, bn=False)
+        self.deep_predict_layer = nn.Linear(self.mlp_hidden_size[-1], 1)
+        for m in self.modules():                                     # widedeep.py:52-60 _init_weights
+            if isinstance(m, (nn.Embedding, nn.Linear)):
+                nn.init.xavier_normal_(m.weight.data)
+                if isinstance(m, nn.Linear) and m.bias is not None:
+                    nn.init.constant_(m.bias.data, 0)
+        self._packed = None
+
+    def pack_tower(self):
+        bf = torch.bfloat16
+
+        def pad(w, rows=0):                                          # K to a multiple of 8, N up to `rows`
+            w = torch.nn.functional.pad(w.detach().float(), (0, (-w.shape[1]) % 8, 0, max(0, rows - w.shape[0])))
+            return w.to(bf).contiguous()
+
+        layers = []
+        for w, b in self.mlp_layers.folded():
+            n8 = (-w.shape[0]) % 8                                   # the next layer's K must be a multiple of 8: pad this N with zero rows
+            layers.append((pad(w, w.shape[0] + n8), torch.nn.functional.pad(b, (0, n8)).contiguous()))
+        pw = pad(self.deep_predict_layer.weight, 8)
+        pb = torch.nn.functional.pad(self.deep_predict_layer.bias.detach().float(), (0, 7)).contiguous()
+        self._packed = dict(mlp=layers, pred=(pw, pb))
+        return self._packed
+
+    def deep(self, x0: torch.Tensor) -> torch.Tensor:
+        """[B, fields * D] bf16 -> [B] fp32 deep logits."""
+        pk = self._packed or self.pack_tower()
+        if x0.shape[1] % 8:
+            x0 = torch.nn.functional.pad(x0, (0, (-x0.shape[1]) % 8))
+        h = x0.contiguous()
+        for w, b in pk["mlp"]:
+            h = ops.tc_linear(h, w, b, act="relu", out_dtype=torch.bfloat16)
+        pw, pb = pk["pred"]
+        return ops.tc_linear(h, pw, pb, act="none", out_dtype=torch.float32)[:, 0]
+
+    def forward(self, interaction) -> torch.Tensor:
+        tokens = interaction if isinstance(interaction, torch.Tensor) else interaction["token_fields"]
+        emb = self.embed_token_fields(tokens, out_dtype=torch.bfloat16)
+        wide = self.first_order_linear(tokens).reshape(-1)           # [B] fp32 (layers.py:1634-1693)
+        return wide + self.deep(emb.reshape(emb.shape[0], -1))       # logits, widedeep.py:70-81
+
+    def predict(self, interaction) -> torch.Tensor:
+        return torch.sigmoid(self.forward(interaction))

@@ -536,3 +536,15 @@ def neg_sample_scores(origin_scores: np.ndarray, row_idx: np.ndarray, col_idx: n
     s = np.full((n_rows, n_items), -np.inf, dtype=np.float32)
     s[np.asarray(row_idx), np.asarray(col_idx)] = np.asarray(origin_scores, np.float32)
     return s
+
+
+def widedeep_forward(emb, fm, mlp_w, mlp_b, pred_w, pred_b, bf16_points: bool = False):
+    """model/context_aware_recommender/widedeep.py:70-81: logits = first_order_linear + deep_predict_layer(mlp_layers(
+    emb.view(B, -1))) with MLPLayers(bn=False, activation='relu') in eval mode (layers.py:33-92); predict = sigmoid(logits).
+    bf16_points: round the input and every hidden activation to bf16 (the rounding points of the tensor-core path)."""
+    r = round_bf16 if bf16_points else (lambda a: a)
+    h = r(np.asarray(emb, np.float32).reshape(np.asarray(emb).shape[0], -1))
+    for w, b in zip(mlp_w, mlp_b):
+        h = r(np.maximum(h @ np.asarray(w, np.float32).T + np.asarray(b, np.float32), 0).astype(np.float32))
+    deep = h @ np.asarray(pred_w, np.float32).reshape(-1) + np.float32(np.asarray(pred_b).reshape(-1)[0])
+    return (np.asarray(fm, np.float32).reshape(-1) + deep).astype(np.float32)

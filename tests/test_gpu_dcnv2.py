@@ -145,3 +145,42 @@ def test_dcnv2_forward_through_token_gather_and_oov_overwrite():
              for w, b in folded]
     want = o.dcnv2_forward(x.float().cpu().numpy(), [r(w) for w in cw], cb, ident, r(pw), pb, "stacked", bf16_points=True)
     assert np.abs(got - want).max() <= 1e-3 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("name", ["default", "wide"])
+def test_widedeep_head_vs_oracle_and_reference_golden(name):
+    """`WideDeep.deep` (tcgen05 linears with ReLU epilogue, widths 32 / 16 / 8 and 256 / 128, K = 260 padded to 264) + the
+    wide term against the oracle at the kernel's rounding points (bf16 input, weights and hidden activations) and the
+    reference's fp32 golden (tests/golden/widedeep_head.npz)."""
+    from oov_b200.model.context import WideDeep
+    from oov_b200.inductive.zero_embedder import ZeroEmbedder
+    from test_oracle_golden import _widedeep_case
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "widedeep_head.npz"))
+    emb, fm, ws, bs, pw, pb = _widedeep_case(g, name)
+    Bn, fields, D = emb.shape
+    cfg = {"embedding_size": D, "mlp_hidden_size": [w.shape[0] for w in ws], "dropout_prob": 0.1, "device": DEV}
+    z = lambda d: ZeroEmbedder(np.zeros((10, 1), np.float32), np.zeros((10, 1), np.float32), 40, 40, d, DEV)
+    m = WideDeep(cfg, [40, 40] + [50] * (fields - 2), inductive_embedder=z(D), first_order_embedder=z(1)).to(DEV).eval()
+    sd = m.state_dict()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    for l, (w, b) in enumerate(zip(ws, bs)):     # module indices without BatchNorm: Dropout 3l, Linear 3l+1, ReLU 3l+2 (layers.py:60-75)
+        sd[f"mlp_layers.mlp_layers.{3 * l + 1}.weight"] = t(w)
+        sd[f"mlp_layers.mlp_layers.{3 * l + 1}.bias"] = t(b)
+    sd["deep_predict_layer.weight"] = t(pw).reshape(1, -1)
+    sd["deep_predict_layer.bias"] = t(pb).reshape(1)
+    m.load_state_dict(sd)
+    m.pack_tower()
+    x16 = torch.from_numpy(emb.reshape(Bn, -1)).to(DEV).to(torch.bfloat16)
+    logits = (torch.from_numpy(fm.reshape(-1)).to(DEV) + m.deep(x16)).cpu().numpy()
+    r = o.round_bf16
+    want16 = o.widedeep_forward(r(emb), fm, [r(w) for w in ws], bs, r(pw), pb, bf16_points=True)
+    assert np.abs(logits - want16).max() <= 1e-3 * max(1.0, np.abs(want16).max()), np.abs(logits - want16).max()
+    err32 = np.abs(o.sigmoid(logits) - g[name + ".prob"]).max()
+    print(f"[widedeep {name}] vs oracle at bf16 points: {np.abs(logits - want16).max():.3e}; probabilities vs reference fp32 golden: {err32:.3e}")
+    assert err32 <= 5e-3
+    # whole forward through the token gather and both OOV embedders: finite, wide + deep, sigmoid in (0, 1)
+    tokens = torch.randint(0, 50, (257, fields), generator=torch.Generator().manual_seed(1)).to(DEV)
+    p = m.predict(tokens)
+    emb_t = m.embed_token_fields(tokens, out_dtype=torch.bfloat16)
+    want_p = torch.sigmoid(m.first_order_linear(tokens).reshape(-1) + m.deep(emb_t.reshape(257, -1)))
+    assert p.shape == (257,) and torch.equal(p, want_p) and bool(((p > 0) & (p < 1)).all())

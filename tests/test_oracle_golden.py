@@ -208,3 +208,23 @@ def test_oracle_sampled_negative_eval_vs_reference(name):
         vals, idx = o.topk(np.where(np.isneginf(seg), seg, dense), case.k)
         pu.sampled_rows_match(seg, np.where(np.isfinite(vals) | np.isnan(vals), vals, -np.inf),
                               np.where(np.isneginf(vals), -1, idx), case.k)
+
+
+def _widedeep_case(g, name):
+    pre = name + "."
+    ws, bs = [], []
+    l = 0
+    while pre + f"mlp_w{l}" in g.files:
+        ws.append(g[pre + f"mlp_w{l}"]); bs.append(g[pre + f"mlp_b{l}"])
+        l += 1
+    return g[pre + "emb"], g[pre + "fm"], ws, bs, g[pre + "pred_w"], g[pre + "pred_b"]
+
+
+@pytest.mark.parametrize("name", ["default", "wide"])
+def test_oracle_widedeep_head_vs_reference(name):
+    """oracle.widedeep_forward against the reference's WideDeep.forward / predict (tests/golden/make_golden_widedeep.py)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "widedeep_head.npz"))
+    emb, fm, ws, bs, pw, pb = _widedeep_case(g, name)
+    logits = o.widedeep_forward(emb, fm, ws, bs, pw, pb)
+    np.testing.assert_allclose(logits, g[name + ".logits"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(o.sigmoid(logits), g[name + ".prob"], rtol=1e-5, atol=1e-6)
