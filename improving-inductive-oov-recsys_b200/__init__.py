@@ -4,7 +4,7 @@
 Layout
     csrc/ + liboov_b200.so   hand-written sm_100a kernels behind the C-ABI in include/oov_b200.h
     _lib.py / ops.py         ctypes binding and tensor-level wrappers (no CPU fallback)
-    inductive/               mirror of recbole/inductive: lsh, slsh, dhe, mean, zero embedders,
+    inductive/               mirror of recbole/inductive: lsh, slsh, dhe, fdhe, dnn, mean, zero embedders,
                              random mapper, get_inductive_embedder / get_inductive_mapper
     model/                   BPR / DirectAU (fused assemble + full_sort_topk), context token gather
     evaluator.py             InductiveEvaluator / Collector on the fused path
@@ -17,7 +17,8 @@ or `importlib.import_module("improving-inductive-oov-recsys_b200")`.
 from . import _lib, ops, sharded, graphed, evaluator, interaction        # noqa: F401
 from .interaction import Interaction                             # noqa: F401
 from .inductive import (abstract_embedder, feature_cache, torch_hash, lsh_embedder, single_lsh_embedder,   # noqa: F401
-                        dh_embedder, mean_embedder, zero_embedder, random_mapper, get_inductive)
+                        dh_embedder, feat_dh_embedder, dnn_embedder, mean_embedder, zero_embedder, random_mapper,
+                        get_inductive)
 from .model import general, context                              # noqa: F401
 from .inductive.get_inductive import get_inductive_embedder, get_inductive_mapper   # noqa: F401
 from .model.general import BPR, DirectAU                         # noqa: F401

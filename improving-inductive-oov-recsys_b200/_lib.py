@@ -31,7 +31,7 @@ class OovRows(C.Structure):
 
 class OovDheNet(C.Structure):
     """struct oov_dhe_net (include/oov_b200.h)."""
-    _fields_ = [("w", c_vp * 4), ("b", c_vp * 4), ("H", c_i32), ("hidden", c_i32), ("D", c_i32), ("_pad", c_i32)]
+    _fields_ = [("w", c_vp * 4), ("b", c_vp * 4), ("H", c_i32), ("hidden", c_i32), ("D", c_i32), ("F", c_i32)]
 
 
 # name -> (restype, argtypes); must list EVERY symbol include/oov_b200.h declares
@@ -54,6 +54,8 @@ SIGNATURES = {
     "oov_dhe_planes_ld": (c_i64, [c_i32]),
     "oov_dhe_hash_planes": (c_i32, [c_vp, c_i64, c_i64, c_vp, c_i32, c_u64, c_vp, c_vp]),
     "oov_dhe_embed_planes": (c_i32, [c_vp, C.POINTER(OovDheNet), C.POINTER(OovRows), c_vp, c_sz, c_vp]),
+    "oov_fdhe_embed": (c_i32, [c_vp, c_u64, C.POINTER(OovDheNet), c_vp, c_i64, C.POINTER(OovRows), c_vp, c_sz, c_i32, c_vp]),
+    "oov_fdhe_workspace": (c_sz, [c_i64, C.POINTER(OovDheNet), c_i32]),
     "oov_tc_linear": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_i32, c_vp, c_i32, c_i64, c_vp]),
     "oov_col_mean": (c_i32, [c_vp, c_i32, c_i64, c_i32, c_vp, c_vp, c_sz, c_vp]),
     "oov_col_mean_workspace": (c_sz, [c_i64, c_i32]),

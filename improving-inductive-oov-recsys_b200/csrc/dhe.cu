@@ -163,7 +163,8 @@ bool dhe_tc_supported(const oov_dhe_net* net, uint64_t mod);
 int dhe_tc_run(const uint8_t* keys, uint64_t mod, const oov_dhe_net* net, const uint32_t* hashes_u32,
                const int64_t* ids, int64_t ids_stride, int64_t n, int64_t n_old, const void* iv_table, int iv_dtype,
                void* out, int out_dtype, int64_t out_stride, void* workspace, size_t workspace_bytes, cudaStream_t st,
-               const __nv_bfloat16* planes_in = nullptr);
+               const __nv_bfloat16* planes_in = nullptr, const float* feat = nullptr, int64_t n_feat_rows = 0,
+               int64_t prime_pad = 0);
 int64_t dhe_planes_ld(int H);
 int dhe_tc_hash_planes(const int64_t* ids, int64_t ids_stride, int64_t n, const uint8_t* keys, int H, uint64_t mod,
                        __nv_bfloat16* planes, cudaStream_t st);
@@ -177,9 +178,10 @@ static bool use_tc(int path, int out_dtype, const oov_dhe_net* net, uint64_t mod
 }
 constexpr int64_t DHE_CHUNK = 1 << 16;     // rows per pass of the fp32 path (bounds the workspace)
 
-static int check_net(const oov_dhe_net* net, const char* who) {
+static int check_net(const oov_dhe_net* net, const char* who, bool feat_ok = false) {
     OOV_REQUIRE(net != nullptr, OOV_ERR_ARG, "%s: net is NULL", who);
-    OOV_REQUIRE(net->H > 0 && net->hidden > 0 && net->D > 0, OOV_ERR_ARG, "%s: bad net dims", who);
+    OOV_REQUIRE(net->H >= 0 && net->F >= 0 && net->H + net->F > 0 && net->hidden > 0 && net->D > 0, OOV_ERR_ARG, "%s: bad net dims", who);
+    OOV_REQUIRE(feat_ok || (net->F == 0 && net->H > 0), OOV_ERR_ARG, "%s: a net with feature inputs (F=%d) goes through oov_fdhe_embed", who, net->F);
     for (int l = 0; l < 4; ++l) OOV_REQUIRE(net->w[l] && net->b[l], OOV_ERR_ARG, "%s: NULL weight/bias %d", who, l);
     return OOV_OK;
 }
@@ -201,11 +203,17 @@ static int launch_hash(const int64_t* ids, int64_t ids_stride, int64_t n, const 
 }
 
 // hashes: [n, H] u32 already computed; rows (optional) gives the assemble contract for the last layer
+// x_f32 (optional, [n, H + F] fp32) replaces the hashes as the first layer's input (fdhe / dnn)
 static int mlp_simt(const uint32_t* hashes, int64_t n, const oov_dhe_net* net, const oov_rows* rows,
-                    void* out, int out_dtype, int64_t out_stride, float* act0, float* act1, cudaStream_t st) {
+                    void* out, int out_dtype, int64_t out_stride, float* act0, float* act1, cudaStream_t st,
+                    const float* x_f32 = nullptr) {
     const dim3 blk(256);
     const unsigned gy = (unsigned)cdiv(n, 64);
     const int hid = net->hidden;
+    if (x_f32 != nullptr)
+        linear_act_simt<false, ACT_GELU><<<dim3((unsigned)cdiv(hid, 64), gy), blk, 0, st>>>(
+            x_f32, n, net->H + net->F, net->w[0], net->b[0], hid, act0, hid, nullptr, 1, 0, nullptr, 0, nullptr, 0, 0);
+    else
     linear_act_simt<true, ACT_GELU><<<dim3((unsigned)cdiv(hid, 64), gy), blk, 0, st>>>(
         hashes, n, net->H, net->w[0], net->b[0], hid, act0, hid, nullptr, 1, 0, nullptr, 0, nullptr, 0, 0);
     OOV_LAUNCH_CHECK("linear_act_simt L1");
@@ -221,6 +229,33 @@ static int mlp_simt(const uint32_t* hashes, int64_t n, const oov_dhe_net* net, c
         rows ? rows->iv_table : nullptr, rows ? rows->iv_dtype : 0, out, out_dtype, out_stride);
     OOV_LAUNCH_CHECK("linear_act_simt L4");
     return OOV_OK;
+}
+
+// fdhe / dnn first-layer input of the fp32 path: x[i] = [float(hash_0..H-1) | feat[id']]  (feat_dh_embedder.py:188-196)
+__global__ void fdhe_input_kernel(const uint32_t* __restrict__ hashes, int H, const float* __restrict__ feat, int64_t n_feat_rows,
+                                  int F, const int64_t* __restrict__ ids, int64_t ids_stride, int64_t n, int64_t prime_pad,
+                                  float* __restrict__ x) {
+    const int K = H + F;
+    const int64_t total = n * (int64_t)K;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / K;
+        const int j = (int)(t - i * K);
+        float v = 0.f;
+        if (j < H) {
+            v = (float)hashes[i * H + j];                       // < 2^24: exact
+        } else {
+            int64_t id = ids[i * ids_stride];
+            if (prime_pad > 0 && id >= prime_pad) id -= prime_pad;
+            if (id >= 0 && id < n_feat_rows) v = __ldg(feat + id * (int64_t)F + (j - H));
+        }
+        x[t] = v;
+    }
+}
+
+static size_t fdhe_simt_workspace(int64_t n, const oov_dhe_net* net) {
+    const int64_t c = n < DHE_CHUNK ? n : DHE_CHUNK;
+    return align_up((size_t)c * (net->H > 0 ? net->H : 1) * 4, 256) + align_up((size_t)c * (net->H + net->F) * 4, 256) +
+           2 * align_up((size_t)c * net->hidden * 4, 256);
 }
 
 }  // namespace oov
@@ -340,6 +375,68 @@ int oov_dhe_embed_planes(const void* planes, const oov_dhe_net* net, const oov_r
     return tc::dhe_tc_run(nullptr, 1ull << 24, net, nullptr, rows->ids, rows->ids_stride, rows->n, rows->n_old, rows->iv_table,
                           rows->iv_dtype, rows->out, rows->out_dtype, rows->out_stride, workspace, workspace_bytes,
                           (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(planes));
+}
+
+size_t oov_fdhe_workspace(int64_t n, const oov_dhe_net* net, int32_t path) {
+    if (!net || n <= 0) return 0;
+    const size_t a = fdhe_simt_workspace(n, net);
+    if (path == OOV_PATH_SIMT_FP32 || !tc::dhe_tc_supported(net, 1ull << 24)) return a;
+    const size_t b = tc::dhe_tc_workspace(n, net);
+    return a > b ? a : b;
+}
+
+int oov_fdhe_embed(const uint8_t* keys, uint64_t mod, const oov_dhe_net* net, const float* feat, int64_t n_feat_rows,
+                   const oov_rows* rows, void* workspace, size_t workspace_bytes, int32_t path, void* stream) {
+    int rc = check_net(net, "oov_fdhe_embed", true);
+    if (rc) return rc;
+    rc = check_rows_public(rows, "oov_fdhe_embed");
+    if (rc) return rc;
+    OOV_REQUIRE(net->H == 0 || keys, OOV_ERR_ARG, "oov_fdhe_embed: keys is NULL but the net has %d hash inputs", net->H);
+    OOV_REQUIRE(net->F == 0 || (feat && n_feat_rows > 0), OOV_ERR_ARG, "oov_fdhe_embed: feat is NULL / empty but the net has %d feature inputs", net->F);
+    OOV_REQUIRE(rows->D == net->D, OOV_ERR_ARG, "oov_fdhe_embed: rows->D=%d != net->D=%d", rows->D, net->D);
+    OOV_REQUIRE(mod >= 1 && mod <= (1ull << 32), OOV_ERR_ARG, "oov_fdhe_embed: mod must be in [1, 2^32]");
+    OOV_REQUIRE(path >= OOV_PATH_AUTO && path <= OOV_PATH_TCGEN05, OOV_ERR_ARG, "oov_fdhe_embed: unsupported path %d", path);
+    const int64_t n = rows->n;
+    if (n == 0) return OOV_OK;
+    OOV_REQUIRE(path != OOV_PATH_TCGEN05 || tc::dhe_tc_supported(net, mod), OOV_ERR_ARG,
+                "oov_fdhe_embed: net shape / modulus not supported by the tcgen05 path");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (use_tc(path, rows->out_dtype, net, mod))
+        return tc::dhe_tc_run(keys, mod, net, nullptr, rows->ids, rows->ids_stride, n, rows->n_old, rows->iv_table,
+                              rows->iv_dtype, rows->out, rows->out_dtype, rows->out_stride, workspace, workspace_bytes, st,
+                              nullptr, feat, n_feat_rows, rows->prime_pad);
+    const int64_t c = n < DHE_CHUNK ? n : DHE_CHUNK;
+    const int K = net->H + net->F;
+    const size_t hsz = align_up((size_t)c * (net->H > 0 ? net->H : 1) * 4, 256), xsz = align_up((size_t)c * K * 4, 256),
+                 asz = align_up((size_t)c * net->hidden * 4, 256);
+    OOV_REQUIRE(workspace && workspace_bytes >= hsz + xsz + 2 * asz, OOV_ERR_WORKSPACE, "oov_fdhe_embed: workspace %zu < %zu",
+                workspace_bytes, hsz + xsz + 2 * asz);
+    char* ws = reinterpret_cast<char*>(workspace);
+    uint32_t* hashes = reinterpret_cast<uint32_t*>(ws);
+    float* x = reinterpret_cast<float*>(ws + hsz);
+    float* act0 = reinterpret_cast<float*>(ws + hsz + xsz);
+    float* act1 = reinterpret_cast<float*>(ws + hsz + xsz + asz);
+    const size_t osz = dtype_size(rows->out_dtype);
+    for (int64_t r0 = 0; r0 < n; r0 += c) {
+        const int64_t cn = n - r0 < c ? n - r0 : c;
+        oov_rows sub = *rows;
+        sub.ids = rows->ids + r0 * rows->ids_stride;
+        sub.n = cn;
+        sub.out = reinterpret_cast<char*>(rows->out) + (size_t)r0 * rows->out_stride * osz;
+        if (net->H > 0) {       // the hashes use the ORIGINAL id (feat_dh_embedder.py:199-205)
+            rc = launch_hash(sub.ids, sub.ids_stride, cn, keys, net->H, mod, hashes, st);
+            if (rc) return rc;
+        }
+        int64_t blocks = cdiv(cn * (int64_t)K, 256);
+        const int64_t cap = (int64_t)num_sms() * 16;
+        if (blocks > cap) blocks = cap;
+        fdhe_input_kernel<<<(unsigned)blocks, 256, 0, st>>>(hashes, net->H, feat, n_feat_rows, net->F, sub.ids, sub.ids_stride, cn,
+                                                           rows->prime_pad, x);
+        OOV_LAUNCH_CHECK("fdhe_input_kernel");
+        rc = mlp_simt(nullptr, cn, net, &sub, sub.out, sub.out_dtype, sub.out_stride, act0, act1, st, x);
+        if (rc) return rc;
+    }
+    return OOV_OK;
 }
 
 }  // extern "C"

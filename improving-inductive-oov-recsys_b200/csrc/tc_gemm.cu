@@ -895,7 +895,7 @@ static void launch_hash_fast(const int64_t* ids, int64_t ids_stride, int64_t n, 
 
 // pack fp32 nn.Linear weights into bf16: layer 1 as [65536 W1 | 256 W1 | W1] (power-of-two scaling is exact)
 __global__ void dhe_pack_kernel(const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ w3,
-                                const float* __restrict__ w4, int H, int hid, int D, int K1p,
+                                const float* __restrict__ w4, int H, int F, int hid, int D, int K1p,
                                 __nv_bfloat16* __restrict__ p1, __nv_bfloat16* __restrict__ p2,
                                 __nv_bfloat16* __restrict__ p3, __nv_bfloat16* __restrict__ p4) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -905,8 +905,10 @@ __global__ void dhe_pack_kernel(const float* __restrict__ w1, const float* __res
         float v = 0.f;
         if (kk < 3 * H) {
             const int piece = kk / H, j = kk - piece * H;
-            const float wb = __bfloat162float(__float2bfloat16_rn(w1[(int64_t)o * H + j]));
+            const float wb = __bfloat162float(__float2bfloat16_rn(w1[(int64_t)o * (H + F) + j]));
             v = wb * (piece == 0 ? 65536.f : (piece == 1 ? 256.f : 1.f));
+        } else if (kk < 3 * H + F) {
+            v = w1[(int64_t)o * (H + F) + H + (kk - 3 * H)];      // plain feature columns (fdhe / dnn)
         }
         p1[t] = __float2bfloat16_rn(v);
     }
@@ -917,7 +919,7 @@ __global__ void dhe_pack_kernel(const float* __restrict__ w1, const float* __res
 struct DhePackedLayout { size_t off[4]; size_t total; int K1p; };
 static DhePackedLayout packed_layout(const oov_dhe_net* net) {
     DhePackedLayout L;
-    L.K1p = (3 * net->H + 7) / 8 * 8;                   // rows must be 16-byte multiples for TMA
+    L.K1p = (3 * net->H + net->F + 7) / 8 * 8;          // rows must be 16-byte multiples for TMA
     size_t o = 0;
     L.off[0] = o; o += align_up((size_t)net->hidden * L.K1p * 2, 256);
     L.off[1] = o; o += align_up((size_t)net->hidden * net->hidden * 2, 256);
@@ -952,8 +954,8 @@ int dhe_tc_pack(const oov_dhe_net* net, void* packed, cudaStream_t st) {
     const int64_t n1 = (int64_t)net->hidden * L.K1p, n2 = (int64_t)net->hidden * net->hidden, n4 = (int64_t)net->D * net->hidden;
     int64_t mx = n1 > n2 ? n1 : n2;
     if (n4 > mx) mx = n4;
-    dhe_pack_kernel<<<(unsigned)cdiv(mx, 256), 256, 0, st>>>(net->w[0], net->w[1], net->w[2], net->w[3], net->H, net->hidden,
-                                                            net->D, L.K1p, (__nv_bfloat16*)(p + L.off[0]),
+    dhe_pack_kernel<<<(unsigned)cdiv(mx, 256), 256, 0, st>>>(net->w[0], net->w[1], net->w[2], net->w[3], net->H, net->F,
+                                                            net->hidden, net->D, L.K1p, (__nv_bfloat16*)(p + L.off[0]),
                                                             (__nv_bfloat16*)(p + L.off[1]), (__nv_bfloat16*)(p + L.off[2]),
                                                             (__nv_bfloat16*)(p + L.off[3]));
     OOV_LAUNCH_CHECK("dhe_pack_kernel");
@@ -965,7 +967,26 @@ int dhe_tc_pack(const oov_dhe_net* net, void* packed, cudaStream_t st) {
 int dhe_tc_run(const uint8_t* keys, uint64_t mod, const oov_dhe_net* net, const uint32_t* hashes_u32,
                const int64_t* ids, int64_t ids_stride, int64_t n, int64_t n_old, const void* iv_table, int iv_dtype,
                void* out, int out_dtype, int64_t out_stride, void* workspace, size_t workspace_bytes, cudaStream_t st,
-               const __nv_bfloat16* planes_in = nullptr);
+               const __nv_bfloat16* planes_in = nullptr, const float* feat = nullptr, int64_t n_feat_rows = 0,
+               int64_t prime_pad = 0);
+
+// fdhe / dnn: bf16 feature row of every id behind the 3H byte-plane columns of the first-layer operand
+// (feat_dh_embedder.py:188-196, dnn_embedder.py:87-91); columns [col0 + F, lda) are zero padding.
+__global__ void feat_cols_kernel(const float* __restrict__ feat, int64_t n_feat_rows, int F, const int64_t* __restrict__ ids,
+                                 int64_t ids_stride, int64_t n, int64_t prime_pad, __nv_bfloat16* __restrict__ A1, int64_t lda,
+                                 int col0) {
+    const int W = (int)lda - col0;
+    const int64_t total = n * (int64_t)W;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / W;
+        const int j = (int)(t - i * W);
+        int64_t id = ids[i * ids_stride];
+        if (prime_pad > 0 && id >= prime_pad) id -= prime_pad;
+        float v = 0.f;
+        if (j < F && id >= 0 && id < n_feat_rows) v = __ldg(feat + id * (int64_t)F + j);
+        A1[i * lda + col0 + j] = __float2bfloat16_rn(v);
+    }
+}
 
 __global__ void split_u32_kernel(const uint32_t* __restrict__ h, int64_t n, int H, __nv_bfloat16* __restrict__ A1, int64_t lda) {
     const int64_t total = n * (int64_t)H;
@@ -1007,7 +1028,7 @@ int dhe_tc_hash_planes(const int64_t* ids, int64_t ids_stride, int64_t n, const 
 int dhe_tc_run(const uint8_t* keys, uint64_t mod, const oov_dhe_net* net, const uint32_t* hashes_u32,
                const int64_t* ids, int64_t ids_stride, int64_t n, int64_t n_old, const void* iv_table, int iv_dtype,
                void* out, int out_dtype, int64_t out_stride, void* workspace, size_t workspace_bytes, cudaStream_t st,
-               const __nv_bfloat16* planes_in) {
+               const __nv_bfloat16* planes_in, const float* feat, int64_t n_feat_rows, int64_t prime_pad) {
     const DhePackedLayout L = packed_layout(net);
     OOV_REQUIRE(workspace && workspace_bytes >= dhe_tc_workspace(n, net), OOV_ERR_WORKSPACE, "dhe (tcgen05): workspace %zu < %zu",
                 workspace_bytes, dhe_tc_workspace(n, net));
@@ -1029,10 +1050,16 @@ int dhe_tc_run(const uint8_t* keys, uint64_t mod, const oov_dhe_net* net, const 
         if (blocks > cap) blocks = cap;
         if (planes_in != nullptr) {
             A1 = const_cast<__nv_bfloat16*>(planes_in) + r0 * (int64_t)L.K1p;       // memoised: no hashing at all
+        } else if (net->F > 0) {
+            int64_t fb = cdiv(cn * (L.K1p - 3 * (int64_t)H), 256);
+            if (fb > cap) fb = cap;
+            feat_cols_kernel<<<(unsigned)fb, 256, 0, st>>>(feat, n_feat_rows, net->F, ids + r0 * ids_stride, ids_stride, cn,
+                                                          prime_pad, A1, L.K1p, 3 * H);
+            OOV_LAUNCH_CHECK("feat_cols_kernel");
         } else if (L.K1p != 3 * H) {
             cudaMemsetAsync(A1, 0, (size_t)cn * L.K1p * 2, st);
         }
-        if (planes_in != nullptr) {
+        if (planes_in != nullptr || H == 0) {
         } else if (hashes_u32 != nullptr) {
             split_u32_kernel<<<(unsigned)blocks, 256, 0, st>>>(hashes_u32 + r0 * H, cn, H, A1, L.K1p);
             OOV_LAUNCH_CHECK("split_u32_kernel");

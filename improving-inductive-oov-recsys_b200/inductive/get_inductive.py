@@ -1,10 +1,10 @@
 """Factory — mirrors reference inductive/get_inductive.py:16-138: same function names, keyword
 set, config keys and the module-global feature cache keyed by `mode`.
 
-Config keys honoured (properties/overall.yaml:59-119): inductive_embedder in {lsh, slsh, dhe,
+Config keys honoured (properties/overall.yaml:59-119): inductive_embedder in {lsh, slsh, dhe, fdhe, dnn,
 mean, zero}, inductive_mapper in {random}, user_oov_buckets, item_oov_buckets, embedding_size,
-device, oov_prime_pad, oov_normalization_type, dhe_num_hashes, oov_hash_function.
-The reference's knn / dnn / fdhe embedders are outside this path and raise.
+device, oov_prime_pad, oov_normalization_type, dhe_num_hashes, dhe_layer_size, oov_hash_function.
+The reference's knn embedder (ScaNN, a third-party ANN library) is outside this path and raises.
 """
 from __future__ import annotations
 
@@ -12,6 +12,8 @@ from typing import Union
 
 from .abstract_embedder import AbstractInductiveEmbedder
 from .dh_embedder import DeepHashEmbedder
+from .dnn_embedder import DNNEmbedder
+from .feat_dh_embedder import FeatDeepHashEmbedder
 from .feature_cache import InductiveFeatureCache
 from .lsh_embedder import LSHInductiveEmbedder
 from .mean_embedder import MeanEmbedder
@@ -79,7 +81,13 @@ def get_inductive_embedder(config, dataset, mode="transductive", user_num=None, 
         return MeanEmbedder(**common, **buckets, embedding_size=embedding_size, device=device)
     if kind == "zero":
         return ZeroEmbedder(**common, embedding_size=embedding_size, device=device)
-    if kind in ("knn", "dnn", "fdhe"):
+    if kind == "fdhe":          # get_inductive.py:99-110
+        return FeatDeepHashEmbedder(**common, **buckets, embedding_size=embedding_size, device=device, prime_pad=prime_pad,
+                                    num_hashes=_cfg(config, "dhe_num_hashes", 128), dhe_layer_size=_cfg(config, "dhe_layer_size", 512))
+    if kind == "dnn":           # get_inductive.py:111-121
+        return DNNEmbedder(**common, **buckets, embedding_size=embedding_size, device=device, prime_pad=prime_pad,
+                           dhe_layer_size=_cfg(config, "dhe_layer_size", 512))
+    if kind == "knn":
         raise NotImplementedError(
-            f"inductive_embedder={kind!r} is outside the accelerated path (lsh, slsh, dhe, mean, zero)")
+            "inductive_embedder='knn' (ScaNN) is outside the accelerated path (lsh, slsh, dhe, fdhe, dnn, mean, zero)")
     return None

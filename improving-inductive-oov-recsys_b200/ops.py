@@ -192,14 +192,19 @@ def slsh_embed(feat, planes, n_buckets: int, oov_weight, ids, out=None, out_dtyp
 class DheNet:
     """Device view of one 4-layer hash net (dh_embedder.py:70-89): fp32 nn.Linear weights [out, in]."""
 
-    def __init__(self, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor]):
+    def __init__(self, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], n_feat: int = 0):
+        """`n_feat`: the last n_feat inputs of layer 1 are plain features (fdhe: feat_dh_embedder.py:100-101; dnn:
+        dnn_embedder.py:65-66 with no hash inputs at all), the first H = in - n_feat are hash values."""
         if len(weights) != 4 or len(biases) != 4:
             raise ValueError("DHE net has exactly 4 Linear layers")
         self.w = [w.detach().contiguous() for w in weights]
         self.b = [b.detach().contiguous() for b in biases]
         for t in self.w + self.b:
             _cuda(t, "dhe weight", torch.float32)
-        self.H, self.hidden, self.D = self.w[0].shape[1], self.w[0].shape[0], self.w[3].shape[0]
+        self.F = int(n_feat)
+        self.H, self.hidden, self.D = self.w[0].shape[1] - self.F, self.w[0].shape[0], self.w[3].shape[0]
+        if self.H < 0:
+            raise ValueError("n_feat exceeds the first layer's input width")
         if self.w[1].shape != (self.hidden, self.hidden) or self.w[2].shape != (self.hidden, self.hidden) \
                 or self.w[3].shape[1] != self.hidden:
             raise ValueError("DHE net layer shapes are inconsistent")
@@ -207,13 +212,13 @@ class DheNet:
         for l in range(4):
             s.w[l] = self.w[l].data_ptr()
             s.b[l] = self.b[l].data_ptr()
-        s.H, s.hidden, s.D = self.H, self.hidden, self.D
+        s.H, s.hidden, s.D, s.F = self.H, self.hidden, self.D, self.F
         self.struct = s
 
     @classmethod
-    def from_sequential(cls, net: torch.nn.Sequential) -> "DheNet":
+    def from_sequential(cls, net: torch.nn.Sequential, n_feat: int = 0) -> "DheNet":
         lin = [m for m in net if isinstance(m, torch.nn.Linear)]
-        return cls([m.weight for m in lin], [m.bias for m in lin])
+        return cls([m.weight for m in lin], [m.bias for m in lin], n_feat)
 
 
 def keys_tensor(keys: Sequence[bytes], device) -> torch.Tensor:
@@ -285,6 +290,32 @@ def dhe_embed_planes(planes: torch.Tensor, ids, net: DheNet, out=None, out_dtype
         raise ValueError(f"planes must be contiguous [n={rows.n}, {int(lib.oov_dhe_planes_ld(net.H))}] (got {tuple(planes.shape)})")
     ws = _workspace(lib.oov_dhe_workspace(rows.n, C.byref(net.struct), PATH_TCGEN05), planes.device)
     _lib.check(lib.oov_dhe_embed_planes(_p(planes), C.byref(net.struct), C.byref(rows), _p(ws), ws.numel(), _stream()))
+    return out
+
+
+def fdhe_embed(ids, keys: Optional[torch.Tensor], net: DheNet, feat: Optional[torch.Tensor], out=None, out_dtype=torch.float32,
+               n_old: int = 0, iv_table=None, prime_pad: int = 0, mod: int = MAX_HASH, path: int = PATH_AUTO):
+    """`fdhe` (feat_dh_embedder.py:188-213) and, with net.H == 0, `dnn` (dnn_embedder.py:87-107): the 4-layer net on
+    [hashes of the raw id | feature row of the de-padded id] (+ in-vocab gather).  `prime_pad` > 0 = training mode."""
+    if net.H:
+        _cuda(keys, "keys", torch.uint8)
+        keys = keys.contiguous()
+        if keys.shape[0] != net.H:
+            raise ValueError(f"{keys.shape[0]} keys but the net expects H={net.H}")
+    else:
+        keys = None
+    if net.F:
+        _cuda(feat, "feat", torch.float32)
+        feat = feat.contiguous()
+        if feat.dim() != 2 or feat.shape[1] != net.F:
+            raise ValueError(f"feat must be [rows, F={net.F}] (got {tuple(feat.shape)})")
+    else:
+        feat = None
+    rows, out, keep = make_rows(ids, net.D, out, out_dtype, n_old, iv_table, prime_pad)
+    lib = _lib.load()
+    ws = _workspace(lib.oov_fdhe_workspace(rows.n, C.byref(net.struct), path), out.device)
+    _lib.check(lib.oov_fdhe_embed(_p(keys), int(mod), C.byref(net.struct), _p(feat), feat.shape[0] if feat is not None else 0,
+                                  C.byref(rows), _p(ws), ws.numel(), path, _stream()))
     return out
 
 

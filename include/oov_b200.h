@@ -118,9 +118,11 @@ int oov_dhe_hash(const int64_t* ids, int64_t ids_stride, int64_t n,
                  uint32_t* hashes, void* stream);
 
 typedef struct oov_dhe_net {
-    const float* w[4];      /* nn.Linear weights [out, in]: [hid,H], [hid,hid], [hid,hid], [D,hid] */
+    const float* w[4];      /* nn.Linear weights [out, in]: [hid,H+F], [hid,hid], [hid,hid], [D,hid] */
     const float* b[4];
-    int32_t H, hidden, D, _pad;
+    int32_t H, hidden, D;
+    int32_t F;              /* plain fp32 feature inputs after the H hash inputs of layer 1: 0 for `dhe`;
+                               `fdhe` H + F, `dnn` H = 0 (oov_fdhe_embed only)                        */
 } oov_dhe_net;
 
 /* out[i] = Sigmoid(L4(GELU(L3(GELU(L2(GELU(L1(float(hashes_i)))))))))  (erf GELU) */
@@ -144,6 +146,22 @@ int oov_dhe_hash_planes(const int64_t* ids, int64_t ids_stride, int64_t n,
                         void* planes /* bf16 [n, ld] */, void* stream);
 int oov_dhe_embed_planes(const void* planes, const oov_dhe_net* net, const oov_rows* rows,
                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * fdhe / dnn — replaces inductive/feat_dh_embedder.py:188-196 (_hash_users/_hash_items: hstack(hashes, feature row)
+ *              -> 4-layer net) and inductive/dnn_embedder.py:87-91 (feature row -> the same net without hashes).
+ * net->w[0] is [hidden, H + F]: columns [0, H) take the raw hash values (as fp32, like `dhe`), columns [H, H + F) the
+ * feature row feat[id'] with id' = id - prime_pad when rows->prime_pad > 0 and id >= prime_pad
+ * (feat_dh_embedder.py:199-205: the hashes use the ORIGINAL id, only the feature lookup is de-padded); a row id'
+ * outside [0, n_feat_rows) reads zeros.  net->H == 0 (keys may be NULL): `dnn`.  The tcgen05 path rounds features and
+ * weights to bf16 (hash inputs stay exact, three byte planes), fp32 accumulate; OOV_PATH_SIMT_FP32 is all fp32.
+ * workspace: oov_fdhe_workspace(n, net, path) bytes.
+ * ------------------------------------------------------------------------------------ */
+int oov_fdhe_embed(const uint8_t* keys, uint64_t mod, const oov_dhe_net* net,
+                   const float* feat, int64_t n_feat_rows,
+                   const oov_rows* rows, void* workspace, size_t workspace_bytes,
+                   int32_t path, void* stream);
+size_t oov_fdhe_workspace(int64_t n, const oov_dhe_net* net, int32_t path);
 
 /* One bf16 linear layer on the tensor cores (the building block of the tcgen05 DHE path):
  * out[M, N] = act(A[M, K] . W[N, K]^T + bias); A, W bf16 row-major (lda, ldw in elements, multiples of 8),

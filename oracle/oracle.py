@@ -264,6 +264,25 @@ def dhe_embed(ids, keys, weights, biases, bf16_points=False):
     return dhe_mlp(dhe_hashes(ids, keys), weights, biases, bf16_points)
 
 
+def featnet_feature_matrix(columns: Sequence[np.ndarray]) -> np.ndarray:
+    """feat_dh_embedder.py:96-99 / dnn_embedder.py:63-64: every column block viewed [n, -1], L2-normalised per row,
+    hstacked (no 'global' option here)."""
+    n = np.asarray(columns[0]).shape[0]
+    return np.hstack([l2_normalize(np.asarray(c, np.float32).reshape(n, -1)) for c in columns]).astype(np.float32)
+
+
+def fdhe_embed(ids, keys, feature_mat, weights, biases, training=False, prime_pad=OOV_PRIME_PAD, bf16_points=False):
+    """feat_dh_embedder.py:188-213 (`keys` given) and dnn_embedder.py:87-109 (`keys=None`): the 4-layer net on
+    hstack(hashes of the ORIGINAL id, feature row of the de-padded id).  `bf16_points`: the feature inputs are rounded
+    to bf16 like the hidden activations (the caller rounds the weights); hash inputs stay exact."""
+    ids = np.asarray(ids, np.int64)
+    feat = np.asarray(feature_mat, np.float32)[depad_ids(ids, training, prime_pad)]
+    if bf16_points:
+        feat = round_bf16(feat)
+    x = feat if keys is None else np.hstack([dhe_hashes(ids, keys).astype(np.float32), feat])
+    return dhe_mlp(x, weights, biases, bf16_points)
+
+
 # ---------------------------------------------------------------------------------------
 # mean / zero (mean_embedder.py:42-87, zero_embedder.py:36-60)
 # ---------------------------------------------------------------------------------------

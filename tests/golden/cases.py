@@ -259,3 +259,55 @@ def context_inputs(case: ContextCase) -> dict:
     for nm in ("user_planes", "item_planes", "user_planes1", "item_planes1"):   # *1 = first-order embedder's own planes
         out[nm] = g.standard_normal((p, case.F)).astype(np.float32)
     return out
+
+
+# ---------------------------------------------------------------------------------------
+# fdhe / dnn (feat_dh_embedder.py:86-210, dnn_embedder.py:8-112): the DHE net fed with [hashes | feature row]
+# ---------------------------------------------------------------------------------------
+@dataclass
+class FeatNetCase:
+    name: str
+    seed: int
+    kind: str                  # fdhe | dnn
+    n_hashes: int = 128        # fdhe only
+    layer: int = 512           # dhe_layer_size
+    D: int = 64
+    n_all: int = 300           # rows of the feature frames (every id the embedder may see)
+    n_ids: int = 257
+    h_scale: float = 2e-7      # 'trained-looking' scale of the hash columns of layer 1 (raw hashes are ~1e7)
+    widths: Tuple[int, ...] = (4, 3)   # float feature columns -> F = sum(widths)
+
+
+FEATNET_CASES: Dict[str, FeatNetCase] = {
+    "fdhe_f7": FeatNetCase("fdhe_f7", 201, "fdhe"),
+    "fdhe_small": FeatNetCase("fdhe_small", 202, "fdhe", n_hashes=32, layer=128, D=16, n_ids=131, h_scale=4e-7, widths=(8, 1, 16)),
+    "dnn_f7": FeatNetCase("dnn_f7", 203, "dnn"),
+    "dnn_wide": FeatNetCase("dnn_wide", 204, "dnn", layer=256, D=32, n_ids=200, widths=(24, 8, 5)),
+}
+
+
+def featnet_inputs(case: FeatNetCase) -> dict:
+    g = rng(case.seed)
+    ucols = feature_columns(g, case.n_all, [("float", w) for w in case.widths])
+    icols = feature_columns(g, case.n_all, [("float", w) for w in case.widths])
+    F = int(sum(case.widths))
+    H = case.n_hashes if case.kind == "fdhe" else 0
+    dims = [H + F, case.layer, case.layer, case.layer, case.D]
+    nets = {}
+    for side in ("user", "item"):
+        ws, bs = [], []
+        for l in range(4):
+            bound = 1.0 / np.sqrt(dims[l])
+            w = g.uniform(-bound, bound, size=(dims[l + 1], dims[l])).astype(np.float32)
+            b = g.uniform(-bound, bound, size=(dims[l + 1],)).astype(np.float32)
+            if l == 0 and H:
+                w[:, :H] *= np.float32(case.h_scale)
+                w[:, H:] *= np.float32(np.sqrt(dims[0] / F))           # features carry weight next to the hashes
+            ws.append(w)
+            bs.append(b)
+        nets[side] = (ws, bs)
+    ids = g.integers(0, case.n_all, size=case.n_ids, dtype=np.int64)
+    ids[:4] = [0, 1, case.n_all - 1, case.n_all // 2]
+    pad = g.random(case.n_ids) < 0.5                                   # training mode: half of the ids carry the prime pad
+    ids_train = ids + pad.astype(np.int64) * OOV_PRIME_PAD
+    return dict(user_cols=ucols, item_cols=icols, nets=nets, ids=ids, ids_train=ids_train, F=F, H=H)

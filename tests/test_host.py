@@ -102,9 +102,8 @@ def test_factory_rejects_out_of_scope_embedders_and_unknown_norm():
     case = cases.CASES["bpr_mean"]
     inp = cases.retrieval_inputs(case)
     ds = Dataset(case.n_old_users, case.n_old_items, _features("user_id", inp["user_cols"]), _features("item_id", inp["item_cols"]))
-    for kind in ("knn", "dnn", "fdhe"):
-        with pytest.raises(NotImplementedError):
-            oov_b200.get_inductive_embedder(_cfg(case, kind, user_oov_buckets=4, item_oov_buckets=4), ds, mode="x")
+    with pytest.raises(NotImplementedError):          # ScaNN-backed, third-party ANN: the one embedder left outside
+        oov_b200.get_inductive_embedder(_cfg(case, "knn", user_oov_buckets=4, item_oov_buckets=4), ds, mode="x")
     assert oov_b200.get_inductive_embedder(_cfg(case, None), ds, mode="x") is None
     with pytest.raises(ValueError, match="Invalid normalization type"):
         oov_b200.get_inductive_embedder(_cfg(case, "slsh", user_oov_buckets=4, item_oov_buckets=4,

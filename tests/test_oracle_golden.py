@@ -228,3 +228,24 @@ def test_oracle_widedeep_head_vs_reference(name):
     logits = o.widedeep_forward(emb, fm, ws, bs, pw, pb)
     np.testing.assert_allclose(logits, g[name + ".logits"], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(o.sigmoid(logits), g[name + ".prob"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", list(cases.FEATNET_CASES))
+def test_featnet_case(name):
+    """fdhe / dnn (feat_dh_embedder.py:188-213, dnn_embedder.py:87-109): the oracle restatement against the outputs of
+    the unmodified reference classes, eval and training mode (hashes of the padded id, features of the de-padded id)."""
+    case = cases.FEATNET_CASES[name]
+    inp = cases.featnet_inputs(case)
+    g = np.load(os.path.join(pu.GOLDEN_DIR, "featnet.npz"), allow_pickle=False)
+    keys = o.keys_to_array(cases.dhe_keys(case.seed, case.n_hashes)) if case.kind == "fdhe" else None
+    for side in ("user", "item"):
+        fm = o.featnet_feature_matrix(inp[f"{side}_cols"])
+        pu.assert_close(fm, g[f"{name}.{side}_feature_mat"], rtol=2e-6, atol=1e-7, what="feature_mat")
+        ws, bs = inp["nets"][side]
+        pu.assert_close(o.fdhe_embed(inp["ids"], keys, fm, ws, bs), g[f"{name}.{side}_emb"], rtol=1e-5, atol=1e-6, what=f"{side}_emb")
+        pu.assert_close(o.fdhe_embed(inp["ids_train"], keys, fm, ws, bs, training=True), g[f"{name}.{side}_emb_train"],
+                        rtol=1e-5, atol=1e-6, what=f"{side}_emb_train")
+    if case.kind == "fdhe":        # the pad changes the hashes, so the two modes must differ
+        assert np.abs(g[f"{name}.item_emb_train"] - g[f"{name}.item_emb"]).max() > 1e-3
+    want_keys = {f"{side}_hash_net.{i}.{p}" for side in ("user", "item") for i in (0, 2, 4, 6) for p in ("weight", "bias")}
+    assert want_keys <= set(g[f"{name}.state_dict_keys"].tolist())
