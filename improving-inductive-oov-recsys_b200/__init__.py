@@ -22,7 +22,7 @@ from .inductive import (abstract_embedder, feature_cache, torch_hash, lsh_embedd
 from .model import general, context                              # noqa: F401
 from .inductive.get_inductive import get_inductive_embedder, get_inductive_mapper   # noqa: F401
 from .model.general import BPR, DirectAU                         # noqa: F401
-from .model.context import DCNV2, WideDeep, InductiveContextRecommender    # noqa: F401
+from .model.context import DCNV2, WideDeep, xDeepFM, InductiveContextRecommender    # noqa: F401
 from .evaluator import InductiveEvaluator, Collector            # noqa: F401
 from .graphed import GraphedTopK, GraphedRanker                                 # noqa: F401
 

@@ -3,8 +3,8 @@ model/abstract_recommender.py:715-842 (InductiveContextRecommender.embed_token_f
 model/layers.py:130-153 (FMEmbedding) and :1617-1750 (InductiveFMFirstOrderLinear).
 
 The gather/OOV-overwrite step feeds the dense towers; of those, DCNV2's cross network + MLP
-(§8f row 2; dcnv2.py:120-144, 214-250) runs on the tensor-core linear here (class `DCNV2` below), the WideDeep /
-xDeepFM towers stay the caller's.
+(§8f row 2; dcnv2.py:120-144, 214-250) runs on the tensor-core linear here (class `DCNV2` below), as do the WideDeep
+MLP (`WideDeep`) and xDeepFM's compressed interaction network + MLP (`xDeepFM`).
 Column 0 of `token_fields` is the user id, column 1 the item id (abstract_recommender.py:691-692).
 """
 from __future__ import annotations
@@ -362,6 +362,124 @@ class WideDeep(InductiveContextRecommender):
         emb = self.embed_token_fields(tokens, out_dtype=torch.bfloat16)
         wide = self.first_order_linear(tokens).reshape(-1)           # [B] fp32 (layers.py:1634-1693)
         return wide + self.deep(emb.reshape(emb.shape[0], -1))       # logits, widedeep.py:70-81
+
+    def predict(self, interaction) -> torch.Tensor:
+        return torch.sigmoid(self.forward(interaction))
+
+
+class xDeepFM(InductiveContextRecommender):
+    """xDeepFM on the OOV path (reference model/context_aware_recommender/xdeepfm.py:33-225): first-order linear with its
+    own OOV embedder + compressed interaction network (CIN) + MLP on the gathered `[B, fields, D]` embeddings;
+    `predict = sigmoid(first_order + cin_linear(CIN) + mlp)`.
+
+    CIN layer k (xdeepfm.py:157-186): z = einsum("bhd,bmd->bhmd", X^{k-1}, X^0) viewed `[B, H*M, D]`, a kernel-size-1
+    Conv1d over the channel axis, ReLU, then (direct = False) the first half of the channels feeds the next layer and
+    the second half is sum-pooled over D into the output.  Here rows are (b, d) pairs: `oov_cin_outer` writes z as the
+    bf16 A operand `[B*D, H*M]`, the Conv1d is `oov_tc_linear` (tcgen05, ReLU epilogue) whose output `[B*D, H_k]` is
+    the next layer's X^k in place, and `oov_cin_pool_dot` folds the pooling with that layer's slice of `cin_linear`
+    in fp32.  The batch is walked in chunks so z (B*D x 1300 bf16 at the default sizes) stays bounded.
+    Same parameter names as the reference (`conv1d_list.{k}.*`, `mlp_layers.mlp_layers.*`, `cin_linear.*`,
+    `first_order_linear.*`).  Token fields only; eval mode."""
+
+    CIN_CHUNK = 8192          # batch rows per pass through the CIN (z: 8192 * D * H*M * 2 bytes)
+
+    def __init__(self, config, field_dims: Sequence[int], inductive_mapper=None, inductive_embedder=None,
+                 first_order_embedder=None, first_order_mapper=None):
+        super().__init__(config, field_dims, inductive_mapper=inductive_mapper, inductive_embedder=inductive_embedder,
+                         first_order_embedder=first_order_embedder, first_order_mapper=first_order_mapper)
+        if not hasattr(self, "first_order_linear"):
+            raise NotImplementedError("xDeepFM needs a first-order embedder or mapper for its linear part")
+
+        def cfg(key, default):
+            try:
+                v = config[key]
+            except (KeyError, IndexError):
+                v = None
+            return default if v is None else v
+
+        self.mlp_hidden_size = list(cfg("mlp_hidden_size", [128, 128, 128]))
+        self.dropout_prob = float(cfg("dropout_prob", 0.2))
+        self.direct = bool(cfg("direct", False))
+        self.cin_layer_size = list(cfg("cin_layer_size", [100, 100, 100]))
+        if not self.direct:                                          # xdeepfm.py:50-57: even sizes when the output is split
+            self.cin_layer_size = [int(x // 2 * 2) for x in self.cin_layer_size]
+        self.num_feature_field = len(field_dims)
+        self.conv1d_list = nn.ModuleList()
+        self.field_nums = [self.num_feature_field]
+        for layer_size in self.cin_layer_size:
+            self.conv1d_list.append(nn.Conv1d(self.field_nums[-1] * self.field_nums[0], layer_size, 1))
+            self.field_nums.append(layer_size if self.direct else layer_size // 2)
+        self.mlp_layers = MLPLayers([self.embedding_size * self.num_feature_field] + self.mlp_hidden_size + [1], self.dropout_prob, bn=False)
+        self.final_len = sum(self.cin_layer_size) if self.direct else sum(self.cin_layer_size[:-1]) // 2 + self.cin_layer_size[-1]
+        self.cin_linear = nn.Linear(self.final_len, 1)
+        for m in self.modules():                                     # xdeepfm.py:89-95 _init_weights
+            if isinstance(m, (nn.Embedding, nn.Conv1d, nn.Linear)):
+                nn.init.xavier_normal_(m.weight.data)
+                if isinstance(m, nn.Linear) and m.bias is not None:
+                    nn.init.constant_(m.bias.data, 0)
+        self._packed = None
+
+    def pack_tower(self):
+        bf = torch.bfloat16
+
+        def pad(w, rows=0):                                          # K to a multiple of 8, N up to `rows`
+            w = torch.nn.functional.pad(w.detach().float(), (0, (-w.shape[1]) % 8, 0, max(0, rows - w.shape[0])))
+            return w.to(bf).contiguous()
+
+        cin = []
+        for conv in self.conv1d_list:
+            w = conv.weight.detach()[:, :, 0]                         # [O, H*M, 1] -> [O, H*M]
+            o8 = (w.shape[0] + 7) // 8 * 8
+            cin.append((pad(w, o8), torch.nn.functional.pad(conv.bias.detach().float(), (0, o8 - w.shape[0])).contiguous()))
+        mlp = []
+        for w, b in self.mlp_layers.folded():
+            o8 = (w.shape[0] + 7) // 8 * 8
+            mlp.append((pad(w, o8), torch.nn.functional.pad(b, (0, o8 - w.shape[0])).contiguous()))
+        self._packed = dict(cin=cin, mlp=mlp, lin_w=self.cin_linear.weight.detach().float().reshape(-1).contiguous(),
+                            lin_b=float(self.cin_linear.bias.detach().float()[0]))
+        return self._packed
+
+    def compressed_interaction_network(self, emb: torch.Tensor) -> torch.Tensor:
+        """[B, fields, D] bf16 -> [B] fp32 = cin_linear(CIN(emb)) (xdeepfm.py:134-190, 198; activation ReLU)."""
+        pk = self._packed or self.pack_tower()
+        B, M, D = emb.shape
+        out = torch.empty((B,), dtype=torch.float32, device=emb.device)
+        last = len(self.cin_layer_size) - 1
+        for r0 in range(0, B, self.CIN_CHUNK):
+            x0 = emb[r0: r0 + self.CIN_CHUNK]
+            bc = x0.shape[0]
+            acc = out[r0: r0 + bc]
+            hidden, off = x0, 0
+            for i, ((w, b), size) in enumerate(zip(pk["cin"], self.cin_layer_size)):
+                z = ops.cin_outer(hidden, x0, D, first=(i == 0))
+                y = ops.tc_linear(z, w, b, act="relu", out_dtype=torch.bfloat16)       # [bc*D, size (padded to 8)]
+                if self.direct:
+                    lo, n, hidden = 0, size, y[:, :size]
+                elif i != last:                                       # torch.split(output, 2 * [size // 2], 1): (next_hidden, direct)
+                    lo, n, hidden = size // 2, size // 2, y[:, : size // 2]
+                else:
+                    lo, n = 0, size
+                ops.cin_pool_dot(y, lo, n, bc, D, pk["lin_w"][off: off + n], pk["lin_b"] if i == 0 else 0.0, acc, accumulate=i > 0)
+                off += n
+        return out
+
+    def deep(self, x0: torch.Tensor) -> torch.Tensor:
+        """[B, fields * D] bf16 -> [B] fp32: MLPLayers(... + [1]) — ReLU after every Linear, the last one included."""
+        pk = self._packed or self.pack_tower()
+        if x0.shape[1] % 8:
+            x0 = torch.nn.functional.pad(x0, (0, (-x0.shape[1]) % 8))
+        h = x0.contiguous()
+        for l, (w, b) in enumerate(pk["mlp"]):
+            final = l == len(pk["mlp"]) - 1
+            h = ops.tc_linear(h, w, b, act="relu", out_dtype=torch.float32 if final else torch.bfloat16)
+        return h[:, 0]
+
+    def forward(self, interaction) -> torch.Tensor:
+        tokens = interaction if isinstance(interaction, torch.Tensor) else interaction["token_fields"]
+        emb = self.embed_token_fields(tokens, out_dtype=torch.bfloat16)                # [B, fields, D]
+        cin = self.compressed_interaction_network(emb)
+        dnn = self.deep(emb.reshape(emb.shape[0], -1))
+        return self.first_order_linear(tokens).reshape(-1) + cin + dnn                # xdeepfm.py:205
 
     def predict(self, interaction) -> torch.Tensor:
         return torch.sigmoid(self.forward(interaction))

@@ -659,5 +659,44 @@ def cross_update(x0: torch.Tensor, t: torch.Tensor, xl: torch.Tensor, out: Optio
     return out
 
 
+def cin_outer(xi: torch.Tensor, x0: torch.Tensor, D: int, first: bool) -> torch.Tensor:
+    """z [B*D, align8(H*M)] bf16 with z[(b, d), h*M + m] = xi[b, h, d] * x0[b, m, d] (xdeepfm.py:160-165).
+    x0: the gathered embeddings [B, M, D]; xi: x0 itself (`first`) or a CIN layer's hidden channels, a column slice
+    [B*D, H] of the previous linear's output."""
+    _cuda(x0, "x0", torch.bfloat16)
+    _cuda(xi, "xi", torch.bfloat16)
+    if x0.dim() != 3 or x0.shape[2] != D or not x0.is_contiguous():
+        raise ValueError("x0 must be contiguous [B, M, D]")
+    B, M = x0.shape[0], x0.shape[1]
+    if first:
+        H, vi = M, (M * D, 1, D)
+    else:
+        if xi.dim() != 2 or xi.shape[0] != B * D or xi.stride(1) != 1:
+            raise ValueError("xi must be [B*D, H] with unit inner stride")
+        H, vi = xi.shape[1], (D * xi.stride(0), xi.stride(0), 1)
+    ldz = (H * M + 7) // 8 * 8
+    z = torch.empty((B * D, ldz), dtype=torch.bfloat16, device=x0.device)
+    _lib.check(_lib.load().oov_cin_outer(_p(xi), vi[0], vi[1], vi[2], H, _p(x0), M * D, 1, D, M, B, D, _p(z), ldz, _stream()))
+    return z
+
+
+def cin_pool_dot(y: torch.Tensor, col0: int, ncols: int, B: int, D: int, w: torch.Tensor, bias: float,
+                 acc: Optional[torch.Tensor] = None, accumulate: bool = False):
+    """acc[b] (+)= bias + sum_{d, c} y[(b, d), col0 + c] * w[c]  (xdeepfm.py:188-189 + :198); fp32 [B]."""
+    _cuda(y, "y", torch.bfloat16)
+    _cuda(w, "w", torch.float32)
+    if y.dim() != 2 or y.shape[0] != B * D or y.stride(1) != 1 or w.numel() != ncols or not w.is_contiguous():
+        raise ValueError("y must be [B*D, >= col0 + ncols] with unit inner stride, w contiguous [ncols]")
+    if acc is None:
+        if accumulate:
+            raise ValueError("accumulate needs an existing acc")
+        acc = torch.empty((B,), dtype=torch.float32, device=y.device)
+    _cuda(acc, "acc", torch.float32)
+    if acc.numel() != B or not acc.is_contiguous():
+        raise ValueError("acc must be contiguous fp32 [B]")
+    _lib.check(_lib.load().oov_cin_pool_dot(_p(y), y.stride(0), col0, ncols, B, D, _p(w), float(bias), int(accumulate), _p(acc), _stream()))
+    return acc
+
+
 def launch_count() -> int:
     return int(_lib.load().oov_launch_count())

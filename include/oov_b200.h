@@ -306,6 +306,22 @@ int oov_first_order_sum(const int64_t* tokens, int64_t Bn, int32_t fields, const
  * ------------------------------------------------------------------------------------ */
 int oov_cross_update(const void* x0, const void* t, const void* xl, int64_t n_elems, void* out, void* stream);
 
+/* xDeepFM compressed interaction network (xdeepfm.py:134-190) around oov_tc_linear.  All operands
+ * bf16; rows of z and of every CIN layer output are (b, d) pairs (b-major), channels run along the row.
+ * oov_cin_outer: z[(b*D + d) * ldz + h*M + m] = xi[b, d, h] * x0[b, d, m] (fp32 product, rounded once), channels
+ * [H*M, ldz) zero — the einsum "bhd,bmd->bhmd" + view of xdeepfm.py:160-165 as the A operand of the layer's
+ * kernel-size-1 Conv1d.  Element (b, d, c) of xi sits at xi[b*xi_sb + d*xi_sd + c*xi_sc] (elements), same for x0:
+ * the gathered embeddings [B, M, D] are read in place (sb = M*D, sd = 1, sc = D), a previous layer's output
+ * [B*D, ld] with (sb = D*ld, sd = ld, sc = 1).
+ * oov_cin_pool_dot: acc[b] = (accumulate ? acc[b] : 0) + bias + sum_{d, c < ncols} y[(b*D + d)*ldy + col0 + c] * w[c]
+ * — the sum pooling over the embedding axis (xdeepfm.py:188-189) of one layer's direct-connect channels folded with
+ * that layer's slice of cin_linear (xdeepfm.py:198), fp32. */
+int oov_cin_outer(const void* xi, int64_t xi_sb, int64_t xi_sd, int64_t xi_sc, int32_t H,
+                  const void* x0, int64_t x0_sb, int64_t x0_sd, int64_t x0_sc, int32_t M,
+                  int64_t B, int32_t D, void* z, int64_t ldz, void* stream);
+int oov_cin_pool_dot(const void* y, int64_t ldy, int32_t col0, int32_t ncols, int64_t B, int32_t D,
+                     const float* w, float bias, int32_t accumulate, float* acc, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Sampled-candidate evaluation (eval side) — replaces trainer.py:547-564 /
  * inductive/evaluator.py:116-133 (neg_sample_batch_eval: model.predict on (user, item) pairs, scatter into a

@@ -567,3 +567,45 @@ def widedeep_forward(emb, fm, mlp_w, mlp_b, pred_w, pred_b, bf16_points: bool = 
         h = r(np.maximum(h @ np.asarray(w, np.float32).T + np.asarray(b, np.float32), 0).astype(np.float32))
     deep = h @ np.asarray(pred_w, np.float32).reshape(-1) + np.float32(np.asarray(pred_b).reshape(-1)[0])
     return (np.asarray(fm, np.float32).reshape(-1) + deep).astype(np.float32)
+
+
+def xdeepfm_cin(emb, conv_w, conv_b, direct: bool = False, bf16_points: bool = False):
+    """model/context_aware_recommender/xdeepfm.py:134-190 (activation ReLU): per layer z = einsum("bhd,bmd->bhmd",
+    X^{k-1}, X^0) viewed [B, H*M, D], kernel-size-1 Conv1d (conv_w[k]: [O, H*M]), ReLU; direct = False splits the
+    output channels into (next_hidden, direct_connect) halves except for the last layer; the direct-connect parts are
+    concatenated and sum-pooled over D -> [B, final_len].
+    bf16_points: z and every layer output are rounded to bf16 (the tensor-core path's operand / activation precision)."""
+    r = round_bf16 if bf16_points else (lambda a: a)
+    x0 = np.asarray(emb, np.float32)
+    B, M, D = x0.shape
+    hidden, final = x0, []
+    n_layers = len(conv_w)
+    for i, (w, b) in enumerate(zip(conv_w, conv_b)):
+        z = r((hidden[:, :, None, :] * x0[:, None, :, :]).reshape(B, -1, D).astype(np.float32))
+        w = np.asarray(w, np.float32)
+        out = np.einsum("oc,bcd->bod", w.astype(np.float64), z.astype(np.float64)) + np.asarray(b, np.float64)[None, :, None]
+        out = r(np.maximum(out, 0).astype(np.float32))
+        size = w.shape[0]
+        if direct:
+            direct_connect, hidden = out, out
+        elif i != n_layers - 1:
+            hidden, direct_connect = out[:, : size // 2], out[:, size // 2:]
+        else:
+            direct_connect = out
+        final.append(direct_connect)
+    return np.concatenate(final, axis=1).astype(np.float64).sum(axis=-1).astype(np.float32)
+
+
+def xdeepfm_forward(emb, fm, conv_w, conv_b, lin_w, lin_b, mlp_w, mlp_b, direct: bool = False, bf16_points: bool = False):
+    """xdeepfm.py:192-207: logits = first_order_linear + cin_linear(CIN(emb)) + mlp_layers(emb.view(B, -1)), the MLP being
+    MLPLayers(sizes + [1]) with ReLU after EVERY Linear, the 1-wide last one included (layers.py:60-75)."""
+    r = round_bf16 if bf16_points else (lambda a: a)
+    emb = np.asarray(emb, np.float32)
+    cin = xdeepfm_cin(emb, conv_w, conv_b, direct, bf16_points)
+    cin = cin.astype(np.float64) @ np.asarray(lin_w, np.float64).reshape(-1) + float(np.asarray(lin_b).reshape(-1)[0])
+    h = r(emb.reshape(emb.shape[0], -1))
+    for l, (w, b) in enumerate(zip(mlp_w, mlp_b)):
+        h = np.maximum(h.astype(np.float64) @ np.asarray(w, np.float64).T + np.asarray(b, np.float64), 0).astype(np.float32)
+        if l != len(mlp_w) - 1:
+            h = r(h)
+    return (np.asarray(fm, np.float32).reshape(-1) + cin.astype(np.float32) + h[:, 0]).astype(np.float32)

@@ -1,0 +1,110 @@
+"""xDeepFM head on the GPU: the product `xDeepFM` (CIN = `oov_cin_outer` + tcgen05 linear with ReLU
+epilogue + `oov_cin_pool_dot`; MLP on the tensor-core linear) against the oracle restatement of xdeepfm.py:134-207 at the
+kernel's rounding points and against the reference-generated golden (tests/golden/xdeepfm_head.npz).
+
+Tolerances: vs the oracle at bf16 points (bf16 inputs / weights / z / layer outputs, fp32 accumulate) 1e-3 of the logit
+scale; vs the reference's fp32 golden 1e-2 absolute on the probabilities (the observed maximum is printed): three chained
+CIN layers multiply bf16 activations by bf16 activations, so the rounding compounds."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as o
+from test_oracle_golden import _xdeepfm_case
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "xdeepfm_head.npz")
+
+
+def _model(c, cin_sizes, chunk=None):
+    from oov_b200.model.context import xDeepFM
+    from oov_b200.inductive.zero_embedder import ZeroEmbedder
+    Bn, fields, D = c["emb"].shape
+    cfg = {"embedding_size": D, "mlp_hidden_size": [w.shape[0] for w in c["mlp_w"][:-1]], "dropout_prob": 0.2, "device": DEV,
+           "direct": c["direct"], "cin_layer_size": cin_sizes}
+    z = lambda d: ZeroEmbedder(np.zeros((10, 1), np.float32), np.zeros((10, 1), np.float32), 40, 40, d, DEV)
+    m = xDeepFM(cfg, [40, 40] + [50] * (fields - 2), inductive_embedder=z(D), first_order_embedder=z(1)).to(DEV).eval()
+    sd = m.state_dict()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    for l, (w, b) in enumerate(zip(c["conv_w"], c["conv_b"])):
+        assert tuple(sd[f"conv1d_list.{l}.weight"].shape) == (w.shape[0], w.shape[1], 1)
+        sd[f"conv1d_list.{l}.weight"] = t(w)[:, :, None]
+        sd[f"conv1d_list.{l}.bias"] = t(b)
+    for l, (w, b) in enumerate(zip(c["mlp_w"], c["mlp_b"])):     # Dropout 3l, Linear 3l+1, ReLU 3l+2 (layers.py:60-75)
+        sd[f"mlp_layers.mlp_layers.{3 * l + 1}.weight"] = t(w)
+        sd[f"mlp_layers.mlp_layers.{3 * l + 1}.bias"] = t(b)
+    sd["cin_linear.weight"] = t(c["lin_w"]).reshape(1, -1)
+    sd["cin_linear.bias"] = t(c["lin_b"]).reshape(1)
+    m.load_state_dict(sd)
+    if chunk:
+        m.CIN_CHUNK = chunk
+    m.pack_tower()
+    return m
+
+
+@pytest.mark.parametrize("name,cin_sizes,chunk", [("default", [100, 100, 100], None), ("default", [100, 100, 100], 64),
+                                                  ("direct", [24, 17, 8], None), ("odd", [13, 10], 50)])
+def test_xdeepfm_head_vs_oracle_and_reference_golden(name, cin_sizes, chunk):
+    g = np.load(GOLD)
+    c = _xdeepfm_case(g, name)
+    m = _model(c, cin_sizes, chunk)
+    Bn, fields, D = c["emb"].shape
+    x16 = torch.from_numpy(c["emb"]).to(DEV).to(torch.bfloat16)
+    r = o.round_bf16
+    # CIN + cin_linear alone
+    cin = m.compressed_interaction_network(x16).cpu().numpy()
+    want_cin = o.xdeepfm_cin(r(c["emb"]), [r(w) for w in c["conv_w"]], c["conv_b"], c["direct"], bf16_points=True)
+    want_cin = want_cin.astype(np.float64) @ c["lin_w"].reshape(-1).astype(np.float64) + float(c["lin_b"][0])
+    scale = max(1.0, np.abs(want_cin).max())
+    assert np.abs(cin - want_cin).max() <= 1e-3 * scale, (np.abs(cin - want_cin).max(), scale)
+    # whole head: wide + CIN + MLP
+    logits = (torch.from_numpy(c["fm"].reshape(-1)).to(DEV) + m.compressed_interaction_network(x16) + m.deep(x16.reshape(Bn, -1))).cpu().numpy()
+    want16 = o.xdeepfm_forward(r(c["emb"]), c["fm"], [r(w) for w in c["conv_w"]], c["conv_b"], c["lin_w"], c["lin_b"],
+                               [r(w) for w in c["mlp_w"]], c["mlp_b"], c["direct"], bf16_points=True)
+    e16 = np.abs(logits - want16).max()
+    assert e16 <= 1e-3 * max(1.0, np.abs(want16).max()), e16
+    err32 = np.abs(o.sigmoid(logits) - g[name + ".prob"]).max()
+    print(f"[xdeepfm {name} chunk={chunk}] logits vs oracle at bf16 points: {e16:.3e} (scale {np.abs(want16).max():.2f}); "
+          f"probabilities vs reference fp32 golden: {err32:.3e}")
+    assert err32 <= 1e-2
+
+
+def test_xdeepfm_forward_through_gather_and_oov_embedders():
+    g = np.load(GOLD)
+    c = _xdeepfm_case(g, "odd")
+    m = _model(c, [13, 10])
+    fields = c["emb"].shape[1]
+    tokens = torch.randint(0, 50, (257, fields), generator=torch.Generator().manual_seed(1)).to(DEV)
+    p = m.predict(tokens)
+    emb_t = m.embed_token_fields(tokens, out_dtype=torch.bfloat16)
+    want = torch.sigmoid(m.first_order_linear(tokens).reshape(-1) + m.compressed_interaction_network(emb_t) + m.deep(emb_t.reshape(257, -1)))
+    assert p.shape == (257,) and torch.equal(p, want) and bool(((p >= 0) & (p <= 1)).all())
+    ref_keys = {"cin_linear.weight", "cin_linear.bias", "conv1d_list.0.weight", "conv1d_list.1.bias", "mlp_layers.mlp_layers.1.weight",
+                "first_order_linear.token_embedding_table.embedding.weight", "token_embedding_table.embedding.weight"}
+    assert ref_keys <= set(m.state_dict().keys())
+
+
+def test_cin_outer_exact_products_and_padding():
+    """z[(b, d), h*M + m] = bf16(xi[b, h, d] * x0[b, m, d]); padding channels are zero."""
+    from oov_b200 import ops
+    gen = torch.Generator().manual_seed(5)
+    B, M, D, H = 37, 5, 6, 3
+    x0 = torch.randn(B, M, D, generator=gen).to(DEV).to(torch.bfloat16)
+    z = ops.cin_outer(x0, x0, D, first=True)
+    assert z.shape == (B * D, 32)            # 25 channels padded to 32
+    want = (x0.float()[:, :, None, :] * x0.float()[:, None, :, :]).reshape(B, M * M, D).permute(0, 2, 1).reshape(B * D, M * M).to(torch.bfloat16)
+    assert torch.equal(z[:, :25], want) and bool((z[:, 25:] == 0).all())
+    y = torch.randn(B * D, 8, generator=gen).to(DEV).to(torch.bfloat16)     # a previous layer's output, hidden = first 3 columns
+    z2 = ops.cin_outer(y[:, :H], x0, D, first=False)
+    xi = y[:, :H].float().reshape(B, D, H).permute(0, 2, 1)                 # [B, H, D]
+    want2 = (xi[:, :, None, :] * x0.float()[:, None, :, :]).reshape(B, H * M, D).permute(0, 2, 1).reshape(B * D, H * M).to(torch.bfloat16)
+    assert z2.shape == (B * D, 16) and torch.equal(z2[:, :15], want2) and bool((z2[:, 15:] == 0).all())
+    w = torch.randn(5, generator=gen).to(DEV)
+    acc = ops.cin_pool_dot(y, 3, 5, B, D, w, 0.5)
+    want_acc = (y[:, 3:8].float().reshape(B, D, 5).sum(1) * w).sum(1) + 0.5
+    assert torch.allclose(acc, want_acc, rtol=1e-5, atol=1e-5)
+    acc2 = ops.cin_pool_dot(y, 3, 5, B, D, w, 0.0, acc.clone(), accumulate=True)
+    assert torch.allclose(acc2, 2 * want_acc - 0.5, rtol=1e-5, atol=1e-5)

@@ -249,3 +249,31 @@ def test_featnet_case(name):
         assert np.abs(g[f"{name}.item_emb_train"] - g[f"{name}.item_emb"]).max() > 1e-3
     want_keys = {f"{side}_hash_net.{i}.{p}" for side in ("user", "item") for i in (0, 2, 4, 6) for p in ("weight", "bias")}
     assert want_keys <= set(g[f"{name}.state_dict_keys"].tolist())
+
+
+def _xdeepfm_case(g, name):
+    pre = name + "."
+
+    def seq(stem):
+        out, l = [], 0
+        while pre + f"{stem}{l}" in g.files:
+            out.append(g[pre + f"{stem}{l}"])
+            l += 1
+        return out
+
+    conv_w = [w[:, :, 0] for w in seq("conv_w")]
+    return dict(emb=g[pre + "emb"], fm=g[pre + "fm"], conv_w=conv_w, conv_b=seq("conv_b"), lin_w=g[pre + "lin_w"], lin_b=g[pre + "lin_b"],
+                mlp_w=seq("mlp_w"), mlp_b=seq("mlp_b"), direct=bool(int(g[pre + "direct"])))
+
+
+@pytest.mark.parametrize("name", ["default", "direct", "odd"])
+def test_oracle_xdeepfm_head_vs_reference(name):
+    """oracle.xdeepfm_cin / xdeepfm_forward against the reference's xDeepFM.compressed_interaction_network / forward /
+    predict (tests/golden/make_golden_xdeepfm.py)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "xdeepfm_head.npz"))
+    c = _xdeepfm_case(g, name)
+    cin = o.xdeepfm_cin(c["emb"], c["conv_w"], c["conv_b"], c["direct"])
+    np.testing.assert_allclose(cin, g[name + ".cin"], rtol=2e-5, atol=2e-5)
+    logits = o.xdeepfm_forward(c["emb"], c["fm"], c["conv_w"], c["conv_b"], c["lin_w"], c["lin_b"], c["mlp_w"], c["mlp_b"], c["direct"])
+    np.testing.assert_allclose(logits, g[name + ".logits"], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(o.sigmoid(logits), g[name + ".prob"], rtol=1e-5, atol=2e-6)
