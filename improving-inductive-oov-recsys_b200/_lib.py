@@ -80,6 +80,9 @@ SIGNATURES = {
                                     c_vp, c_vp]),
     "oov_map_ids": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp]),
     "oov_cross_update": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "oov_scatter_add_rows": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp]),
+    "oov_lsh_embed_backward": (c_i32, [c_vp, c_i32, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_sz, c_vp]),
+    "oov_lsh_embed_backward_workspace": (c_sz, [c_i64]),
     "oov_cin_outer": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_i64, c_i64, c_i64, c_i32, c_i64, c_i32, c_vp, c_i64, c_vp]),
     "oov_cin_pool_dot": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i64, c_i32, c_vp, c_f32, c_i32, c_vp, c_vp]),
     "oov_pair_topk": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i64, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp]),

@@ -62,6 +62,19 @@ class AbstractInductiveEmbedder(nn.Module):
         leaves in-vocab rows of `out` untouched.  `side` is 'user' or 'item'."""
         raise NotImplementedError()
 
+    # --- training-mode OOV path (SURVEY §8f row 4; trainer.py:1748-1837 differentiates the assemble) -----------------
+    def train_params(self, side: str, model) -> list:
+        """Parameters the OOV rows of `side` depend on (the autograd inputs next to the in-vocab table)."""
+        return []
+
+    def assemble_rows_train(self, side: str, ids: torch.Tensor, model, n_old: int, iv_table: torch.Tensor):
+        """fp32 assemble like `assemble_rows`, plus whatever `backward_rows` needs: returns (out, saved)."""
+        raise NotImplementedError(f"{type(self).__name__} has no training-mode (backward) path")
+
+    def backward_rows(self, side: str, saved, g: torch.Tensor, ids: torch.Tensor, n_old: int, model) -> list:
+        """Gradients of `train_params(side, model)` given g = d loss / d assembled rows (fp32 [n, D])."""
+        return []
+
     def _depad_inplace(self, ids: torch.Tensor, prime_pad: int) -> None:
         """Training mode mutates the caller's ids like lsh_embedder.py:153-155 does."""
         if self.training and prime_pad:

@@ -85,6 +85,21 @@ class LSHInductiveEmbedder(AbstractInductiveEmbedder):
                              iv_table=iv_table, prime_pad=self.prime_pad if self.training else 0,
                              tie_count=self.tie_count)
 
+    # training: out = (H W) / |H| is linear in W = model.*_oov_buckets.weight; the backward re-uses the forward's bits
+    def train_params(self, side, model):
+        return [(model.user_oov_buckets if side == "user" else model.item_oov_buckets).weight]
+
+    def assemble_rows_train(self, side, ids, model, n_old, iv_table):
+        lsh, fm = self._side(side)
+        w = self.train_params(side, model)[0].detach()
+        out, bits = ops.lsh_embed(fm, lsh.uniform_planes[0].data, w, ids, n_old=n_old, iv_table=iv_table,
+                                  prime_pad=self.prime_pad if self.training else 0, tie_count=self.tie_count, return_bits=True)
+        return out, bits
+
+    def backward_rows(self, side, saved, g, ids, n_old, model):
+        w = self.train_params(side, model)[0]
+        return [ops.lsh_embed_backward(saved, g, ids, n_old, torch.zeros_like(w, dtype=torch.float32))]
+
     def embed_user_ids(self, user_ids, model) -> torch.Tensor:
         self._depad_inplace(user_ids, self.prime_pad)
         return self.assemble_rows("user", user_ids, model, 0, None)

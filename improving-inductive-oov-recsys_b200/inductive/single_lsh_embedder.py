@@ -56,6 +56,21 @@ class SingleLSHInductiveEmbedder(AbstractInductiveEmbedder):
                               iv_table=iv_table, prime_pad=self.prime_pad if self.training else 0,
                               tie_count=self.tie_count)
 
+    # training: out = W[bucket]; the backward scatters g into the bucket rows the forward picked
+    def train_params(self, side, model):
+        return [(model.user_oov_buckets if side == "user" else model.item_oov_buckets).weight]
+
+    def assemble_rows_train(self, side, ids, model, n_old, iv_table):
+        lsh, fm, nb = self._side(side)
+        w = self.train_params(side, model)[0].detach()
+        out, buckets = ops.slsh_embed(fm, lsh.uniform_planes[0].data, nb, w, ids, n_old=n_old, iv_table=iv_table,
+                                      prime_pad=self.prime_pad if self.training else 0, tie_count=self.tie_count, return_buckets=True)
+        return out, buckets                        # bucket = -1 for in-vocab rows
+
+    def backward_rows(self, side, saved, g, ids, n_old, model):
+        w = self.train_params(side, model)[0]
+        return [ops.scatter_add_rows(g, saved, torch.zeros_like(w, dtype=torch.float32))]
+
     def embed_user_ids(self, user_ids, model) -> torch.Tensor:
         self._depad_inplace(user_ids, self.prime_pad)
         return self.assemble_rows("user", user_ids, model, 0, None)

@@ -17,6 +17,9 @@ class ZeroEmbedder(AbstractInductiveEmbedder):
     def assemble_rows(self, side, ids, model, n_old, iv_table, out=None, out_dtype=torch.float32):
         return ops.const_embed(None, ids, self.zero_vec.numel(), out=out, out_dtype=out_dtype, n_old=n_old, iv_table=iv_table)
 
+    def assemble_rows_train(self, side, ids, model, n_old, iv_table):      # OOV rows are constants: nothing to save
+        return self.assemble_rows(side, ids, model, n_old, iv_table), None
+
     def embed_user_ids(self, user_ids, model) -> torch.Tensor:
         return self.assemble_rows("user", user_ids, model, 0, None)
 

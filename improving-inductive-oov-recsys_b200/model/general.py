@@ -7,7 +7,9 @@ state_dict keys incl. `inductive_embedder.*`) and methods (`get_user_embedding`,
 `get_item_embedding`, `ind_full_sort_predict`, `full_sort_predict`, `predict`).  Differences are in
 HOW: in-vocab gather + OOV embed is one fused pass (`assemble_rows`), and `full_sort_topk` fuses
 scoring, the pad/history/segment masks and top-k so the [Q, N] score matrix is never written.
-Training (`calculate_loss`, backward through the OOV buckets) is outside this path.
+Training: `calculate_loss` runs the same assemble kernels under `torch.autograd` (`_AssembleTrain`):
+the backward scatters the row gradients into the in-vocab table and into the OOV buckets (`oov_scatter_add_rows`,
+`oov_lsh_embed_backward`), which is what trainer.py:1748-1837 (`_train_oov`) needs from the model.
 """
 from __future__ import annotations
 
@@ -37,6 +39,48 @@ def _cfg(config, key, default=None):
     except (KeyError, IndexError):
         v = None
     return default if v is None else v
+
+
+class _AssembleTrain(torch.autograd.Function):
+    """rows = assemble(ids) with gradients: in-vocab rows -> d table[id] += g (nn.Embedding backward, bpr.py:56-58), OOV
+    rows -> the embedder's `backward_rows` (lsh: H^T (g / |H|); slsh / mapper: scatter into the bucket rows; zero: none).
+    `table` and `params` are passed as inputs so autograd routes the gradients to the Parameters."""
+
+    @staticmethod
+    def forward(ctx, model, side, ids, table, *params):
+        n_old = model.n_users if side == "user" else model.n_items
+        emb, mapper = model.inductive_embedder, model.inductive_mapper
+        ids = ids.to(model.device).contiguous()
+        if mapper is not None:
+            ids = mapper.map_user_ids(ids) if side == "user" else mapper.map_item_ids(ids)
+        if emb is not None:
+            out, saved = emb.assemble_rows_train(side, ids, model, n_old, table.detach())
+        else:
+            out = torch.zeros((ids.shape[0], model.embedding_size), dtype=torch.float32, device=model.device)
+            ops.gather_rows(table.detach(), ids, out=out)
+            ops.gather_rows(params[0].detach(), ids, idx_offset=-n_old, out=out)
+            saved = None
+        ctx.model, ctx.side, ctx.n_old, ctx.ids, ctx.saved = model, side, n_old, ids, saved
+        ctx.table_shape = tuple(table.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        model, side, n_old, ids = ctx.model, ctx.side, ctx.n_old, ctx.ids
+        g = g.contiguous().float()
+        d_table = None
+        if ctx.needs_input_grad[3]:
+            d_table = ops.scatter_add_rows(g, ids, torch.zeros(ctx.table_shape, dtype=torch.float32, device=g.device))
+        n_params = len(ctx.needs_input_grad) - 4
+        d_params = [None] * n_params
+        if n_params and any(ctx.needs_input_grad[4:]):
+            if model.inductive_embedder is not None:
+                d_params = list(model.inductive_embedder.backward_rows(side, ctx.saved, g, ids, n_old, model))
+            else:                                   # mapper only: *_oov_buckets(id - n_old), bpr.py:71
+                w = (model.user_oov_buckets if side == "user" else model.item_oov_buckets).weight
+                d_params = [ops.scatter_add_rows(g, ids, torch.zeros_like(w, dtype=torch.float32), idx_offset=-n_old)]
+            d_params = [d if need else None for d, need in zip(d_params, ctx.needs_input_grad[4:])]
+        return (None, None, None, d_table, *d_params)
 
 
 class InductiveGeneralRecommender(nn.Module):
@@ -119,11 +163,35 @@ class InductiveGeneralRecommender(nn.Module):
         ops.gather_rows(buckets, ids, idx_offset=-n_old, out=out)               # skips ids < n_old
         return out
 
+    def _assemble_train(self, side: str, ids: torch.Tensor) -> torch.Tensor:
+        """fp32 rows carrying autograd history (used by `calculate_loss`)."""
+        table = (self.user_embedding if side == "user" else self.item_embedding).weight
+        if self.inductive_embedder is not None:
+            params = self.inductive_embedder.train_params(side, self)
+        else:
+            params = [(self.user_oov_buckets if side == "user" else self.item_oov_buckets).weight]
+        return _AssembleTrain.apply(self, side, ids, table, *params)
+
     def get_user_embedding(self, new_user_ids):
+        if self._autograd_assemble:
+            return self._assemble_train("user", new_user_ids)
         return self._assemble("user", new_user_ids)
 
     def get_item_embedding(self, item):
+        if self._autograd_assemble:
+            return self._assemble_train("item", item)
         return self._assemble("item", item)
+
+    _autograd_assemble = False       # set for the duration of calculate_loss
+
+    def _training_forward(self, fn):
+        if not torch.is_grad_enabled():
+            return fn()
+        self._autograd_assemble = True
+        try:
+            return fn()
+        finally:
+            self._autograd_assemble = False
 
     def forward(self, user, item):
         return self.get_user_embedding(user), self.get_item_embedding(item)
@@ -231,6 +299,16 @@ class BPR(InductiveGeneralRecommender):
         self.item_embedding = nn.Embedding(self.n_items, self.embedding_size)
         self.apply(xavier_normal_initialization)
 
+    def calculate_loss(self, interaction):
+        """bpr.py:132-144 with BPRLoss (model/loss.py: -log(1e-10 + sigmoid(pos - neg)).mean()); the three assembles run
+        through `_AssembleTrain`, the per-pair dot products and the loss are a few elementwise ops on [batch, D]."""
+        def fn():
+            user_e, pos_e = self.forward(interaction[self.USER_ID], interaction[self.ITEM_ID])
+            neg_e = self.get_item_embedding(interaction[self.NEG_ITEM_ID])
+            pos_s, neg_s = torch.mul(user_e, pos_e).sum(dim=1), torch.mul(user_e, neg_e).sum(dim=1)
+            return -torch.log(1e-10 + torch.sigmoid(pos_s - neg_s)).mean()
+        return self._training_forward(fn)
+
 
 class DirectAU(InductiveGeneralRecommender):
     """reference model/general_recommender/directau.py:18-198.  `forward`/`predict` L2-normalise,
@@ -253,3 +331,21 @@ class DirectAU(InductiveGeneralRecommender):
 
     def full_sort_predict(self, interaction):
         raise NotImplementedError()      # directau.py:183-184
+
+    @staticmethod
+    def alignment(x, y, alpha=2):
+        return (x - y).norm(p=2, dim=1).pow(alpha).mean()
+
+    @staticmethod
+    def uniformity(x, t=2):
+        return torch.pdist(x, p=2).pow(2).mul(-t).exp().mean().log()
+
+    def calculate_loss(self, interaction):
+        """directau.py:87-99: alignment + gamma * mean uniformity of the L2-normalised rows; the assembles run through
+        `_AssembleTrain`."""
+        self.restore_user_e, self.restore_item_e = None, None
+
+        def fn():
+            user_e, item_e = self.forward(interaction[self.USER_ID], interaction[self.ITEM_ID])
+            return self.alignment(user_e, item_e) + self.gamma * (self.uniformity(user_e) + self.uniformity(item_e)) / 2
+        return self._training_forward(fn)

@@ -698,5 +698,45 @@ def cin_pool_dot(y: torch.Tensor, col0: int, ncols: int, B: int, D: int, w: torc
     return acc
 
 
+def _grad2d(g: torch.Tensor, D: int) -> torch.Tensor:
+    _cuda(g, "grad", torch.float32)
+    if g.dim() != 2 or g.shape[1] != D:
+        raise ValueError(f"grad must be fp32 [n, D={D}]")
+    return g if g.stride(1) == 1 else g.contiguous()
+
+
+def scatter_add_rows(g: torch.Tensor, idx: torch.Tensor, dtable: torch.Tensor, idx_offset: int = 0) -> torch.Tensor:
+    """dtable[idx[i] + idx_offset] += g[i] for rows that land inside dtable (nn.Embedding backward; bpr.py:56-71)."""
+    _cuda(dtable, "dtable", torch.float32)
+    if dtable.dim() != 2 or not dtable.is_contiguous():
+        raise ValueError("dtable must be contiguous fp32 [rows, D]")
+    g = _grad2d(g, dtable.shape[1])
+    idx, stride = _ids_1d(idx, "idx")
+    if idx.shape[0] != g.shape[0]:
+        raise ValueError("idx / grad row counts differ")
+    _lib.check(_lib.load().oov_scatter_add_rows(_p(g), g.stride(0) if g.shape[0] > 1 else dtable.shape[1], _p(idx), stride, idx.shape[0],
+                                                int(idx_offset), dtable.shape[0], dtable.shape[1], _p(dtable), _stream()))
+    return dtable
+
+
+def lsh_embed_backward(bits: torch.Tensor, g: torch.Tensor, ids: torch.Tensor, n_old: int, dW: torch.Tensor) -> torch.Tensor:
+    """dW[b] += H_ib g_i / |H_i| over the OOV rows (ids >= n_old) of an `lsh_embed(..., return_bits=True)` call."""
+    _cuda(bits, "bits", torch.int32)
+    _cuda(dW, "dW", torch.float32)
+    if dW.dim() != 2 or not dW.is_contiguous():
+        raise ValueError("dW must be contiguous fp32 [B, D]")
+    B, D = dW.shape
+    g = _grad2d(g, D)
+    ids, stride = _ids_1d(ids)
+    n = ids.shape[0]
+    if bits.shape != (n, (B + 31) // 32) or not bits.is_contiguous() or g.shape[0] != n:
+        raise ValueError("bits must be contiguous [n, ceil(B / 32)] and grad [n, D]")
+    lib = _lib.load()
+    ws = _workspace(lib.oov_lsh_embed_backward_workspace(n), dW.device) if n else None
+    _lib.check(lib.oov_lsh_embed_backward(_p(bits), B, _p(g), g.stride(0) if n > 1 else D, _p(ids), stride, n, int(n_old), D, _p(dW),
+                                          _p(ws), 0 if ws is None else ws.numel(), _stream()))
+    return dW
+
+
 def launch_count() -> int:
     return int(_lib.load().oov_launch_count())

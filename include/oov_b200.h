@@ -306,6 +306,24 @@ int oov_first_order_sum(const int64_t* tokens, int64_t Bn, int32_t fields, const
  * ------------------------------------------------------------------------------------ */
 int oov_cross_update(const void* x0, const void* t, const void* xl, int64_t n_elems, void* out, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Training-mode OOV path — the backward of the assemble that trainer/trainer.py:1748-1837
+ * (_train_oov -> calculate_loss -> bpr.py:48-125 under autograd) differentiates.  The forward is the eval-path
+ * `*_embed` call with rows->prime_pad set.  g: fp32 [n, D] gradient of the assembled rows (row stride ldg).
+ * oov_scatter_add_rows: dtable[idx[i] + idx_offset] += g[i] for rows that land in [0, rows) — in-vocab rows
+ *   (idx = ids, rows = n_old: nn.Embedding backward), mapper rows (idx_offset = -n_old: bpr.py:71) and slsh rows
+ *   (idx = the bucket ids oov_slsh_embed returned, -1 for in-vocab: single_lsh_embedder.py:108).
+ * oov_lsh_embed_backward: dW[b] += H_ib * g_i / |H_i| for ids >= n_old (lsh_embedder.py:156-158), bits = the multi-hot
+ *   words oov_lsh_embed wrote to `bits_out`; an all-zero hash poisons dW with NaN like autograd's 0 * inf.
+ * Both ADD into their fp32 output (zero it first); accumulation order is not deterministic (atomics).
+ * ------------------------------------------------------------------------------------ */
+int oov_scatter_add_rows(const float* g, int64_t ldg, const int64_t* idx, int64_t idx_stride, int64_t n,
+                         int64_t idx_offset, int64_t rows, int32_t D, float* dtable, void* stream);
+int oov_lsh_embed_backward(const uint32_t* bits, int32_t B, const float* g, int64_t ldg,
+                           const int64_t* ids, int64_t ids_stride, int64_t n, int64_t n_old, int32_t D,
+                           float* dW, void* workspace, size_t workspace_bytes, void* stream);
+size_t oov_lsh_embed_backward_workspace(int64_t n);
+
 /* xDeepFM compressed interaction network (xdeepfm.py:134-190) around oov_tc_linear.  All operands
  * bf16; rows of z and of every CIN layer output are (b, d) pairs (b-major), channels run along the row.
  * oov_cin_outer: z[(b*D + d) * ldz + h*M + m] = xi[b, d, h] * x0[b, d, m] (fp32 product, rounded once), channels

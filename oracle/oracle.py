@@ -609,3 +609,21 @@ def xdeepfm_forward(emb, fm, conv_w, conv_b, lin_w, lin_b, mlp_w, mlp_b, direct:
         if l != len(mlp_w) - 1:
             h = r(h)
     return (np.asarray(fm, np.float32).reshape(-1) + cin.astype(np.float32) + h[:, 0]).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------ training-mode backward
+def lsh_embed_backward(multihot: np.ndarray, g: np.ndarray) -> np.ndarray:
+    """d/dW of new_embed = (H @ W) / H.sum(1) (lsh_embedder.py:156-158) given g = d loss / d new_embed: H^T (g / |H|),
+    which is what autograd computes (an all-zero row gives 0 * inf = NaN on every bucket)."""
+    H = np.asarray(multihot, np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return (H.T.astype(np.float64) @ (np.asarray(g, np.float64) / H.sum(axis=1, keepdims=True).astype(np.float64))).astype(np.float32)
+
+
+def scatter_add_rows(g: np.ndarray, idx: np.ndarray, rows: int) -> np.ndarray:
+    """nn.Embedding backward: d table[idx[i]] += g[i] for 0 <= idx[i] < rows."""
+    out = np.zeros((rows, np.asarray(g).shape[1]), np.float64)
+    idx = np.asarray(idx, np.int64)
+    ok = (idx >= 0) & (idx < rows)
+    np.add.at(out, idx[ok], np.asarray(g, np.float64)[ok])
+    return out.astype(np.float32)

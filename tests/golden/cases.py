@@ -311,3 +311,23 @@ def featnet_inputs(case: FeatNetCase) -> dict:
     pad = g.random(case.n_ids) < 0.5                                   # training mode: half of the ids carry the prime pad
     ids_train = ids + pad.astype(np.int64) * OOV_PRIME_PAD
     return dict(user_cols=ucols, item_cols=icols, nets=nets, ids=ids, ids_train=ids_train, F=F, H=H)
+
+
+# ---------------------------------------------------------------------------------------
+# Training-mode OOV batches (trainer.py:1748-1837 _train_oov + _transform_interaction_oov)
+# ---------------------------------------------------------------------------------------
+TRAIN_CASES = ["bpr_lsh_ml100k", "directau_lsh_global", "bpr_lsh_tinybuckets", "directau_slsh", "bpr_slsh_odd", "directau_zero"]
+
+
+def train_batch(case: RetrievalCase, batch: int = 192) -> dict:
+    """A training batch of in-vocab (user, pos item, neg item) ids; a seeded per-element mask adds the prime pad to user
+    and item ids (the reference pads whole columns by a coin flip, trainer.py:1748-1753 — a per-element mask covers both
+    outcomes and mixes in-vocab and OOV rows in one batch).  Ids repeat, so the scatter-adds collide."""
+    g = rng(case.seed + 77)
+    users = g.integers(1, case.n_old_users, size=batch, dtype=np.int64)
+    pos = g.integers(1, case.n_old_items, size=batch, dtype=np.int64)
+    neg = g.integers(1, case.n_old_items, size=batch, dtype=np.int64)
+    users[: batch // 8] = users[0]                       # heavy collisions on one row
+    pad_u = g.random(batch) < 0.5
+    pad_i = g.random(batch) < 0.5
+    return dict(users=users + pad_u * OOV_PRIME_PAD, pos=pos + pad_i * OOV_PRIME_PAD, neg=neg)
