@@ -83,6 +83,10 @@ SIGNATURES = {
     "oov_scatter_add_rows": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp]),
     "oov_lsh_embed_backward": (c_i32, [c_vp, c_i32, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_sz, c_vp]),
     "oov_lsh_embed_backward_workspace": (c_sz, [c_i64]),
+    "oov_fdhe_input": (c_i32, [c_vp, c_u64, c_i32, c_vp, c_i64, c_i32, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),
+    "oov_fdhe_input_workspace": (c_sz, [c_i64, c_i32]),
+    "oov_linear_f32": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp]),
+    "oov_act": (c_i32, [c_vp, c_vp, c_i32, c_i64, c_i32, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "oov_cin_outer": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_i64, c_i64, c_i64, c_i32, c_i64, c_i32, c_vp, c_i64, c_vp]),
     "oov_cin_pool_dot": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i64, c_i32, c_vp, c_f32, c_i32, c_vp, c_vp]),
     "oov_pair_topk": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i64, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp]),

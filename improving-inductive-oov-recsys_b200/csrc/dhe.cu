@@ -75,7 +75,7 @@ dhe_hash_kernel(const int64_t* __restrict__ ids, int64_t ids_stride, int64_t n,
 // fp32 linear + activation: C[n, N] = act(A[n, K] . W[N, K]^T + b)
 // 64x64 CTA tile, 16-deep K slices, 256 threads, 4x4 micro-tile.
 // ------------------------------------------------------------------------------------
-enum { ACT_GELU = 0, ACT_SIGMOID = 1 };
+enum { ACT_GELU = 0, ACT_SIGMOID = 1, ACT_NONE = 2 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
@@ -142,7 +142,7 @@ linear_act_simt(const void* __restrict__ A_, int64_t n, int K, const float* __re
             const int gn = n0 + tx * 4 + j;
             if (gn >= N) continue;
             float v = acc[i][j] + __ldg(bias + gn);
-            v = (ACT == ACT_GELU) ? gelu_erf(v) : sigmoidf(v);
+            v = (ACT == ACT_GELU) ? gelu_erf(v) : (ACT == ACT_SIGMOID ? sigmoidf(v) : v);
             if (ACT == ACT_SIGMOID && out != nullptr) {
                 if (is_iv) {
                     if (iv_table == nullptr || id < 0) continue;
@@ -249,6 +249,27 @@ __global__ void fdhe_input_kernel(const uint32_t* __restrict__ hashes, int H, co
             if (id >= 0 && id < n_feat_rows) v = __ldg(feat + id * (int64_t)F + (j - H));
         }
         x[t] = v;
+    }
+}
+
+// training: y = act(z) (dy == nullptr) or dz = dy * act'(z); rows whose id < n_old (in-vocab rows of an assembled batch,
+// which take the table row instead of the net's output) get dz = 0.  act: 0 none, 1 GELU(erf), 2 sigmoid.
+__global__ void act_kernel(const float* __restrict__ z, const float* __restrict__ dy, int act, int64_t rows, int N,
+                           const int64_t* __restrict__ ids, int64_t ids_stride, int64_t n_old, float* __restrict__ out) {
+    const int64_t total = rows * (int64_t)N;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const float x = z[t];
+        float v;
+        if (dy == nullptr) {
+            v = act == 1 ? gelu_erf(x) : (act == 2 ? sigmoidf(x) : x);
+        } else {
+            float d = 1.f;
+            if (act == 1) d = 0.5f * (1.f + erff(x * 0.70710678118654752440f)) + x * 0.39894228040143267794f * expf(-0.5f * x * x);
+            else if (act == 2) { const float s = sigmoidf(x); d = s * (1.f - s); }
+            v = dy[t] * d;
+            if (ids != nullptr && ids[(t / N) * ids_stride] < n_old) v = 0.f;
+        }
+        out[t] = v;
     }
 }
 
@@ -375,6 +396,61 @@ int oov_dhe_embed_planes(const void* planes, const oov_dhe_net* net, const oov_r
     return tc::dhe_tc_run(nullptr, 1ull << 24, net, nullptr, rows->ids, rows->ids_stride, rows->n, rows->n_old, rows->iv_table,
                           rows->iv_dtype, rows->out, rows->out_dtype, rows->out_stride, workspace, workspace_bytes,
                           (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(planes));
+}
+
+int oov_linear_f32(const float* A, const float* W, int64_t M, int32_t N, int32_t K, const float* bias, int32_t act, float* out,
+                   void* stream) {
+    OOV_REQUIRE(M >= 0 && N > 0 && K > 0 && act >= 0 && act <= 2, OOV_ERR_ARG, "oov_linear_f32: bad argument");
+    if (M == 0) return OOV_OK;
+    OOV_REQUIRE(A && W && bias && out, OOV_ERR_ARG, "oov_linear_f32: NULL pointer");
+    const dim3 grid((unsigned)cdiv(N, 64), (unsigned)cdiv(M, 64)), blk(256);
+    OOV_REQUIRE(grid.y <= 65535u, OOV_ERR_ARG, "oov_linear_f32: M=%lld too large (chunk the rows)", (long long)M);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (act == 1)
+        linear_act_simt<false, ACT_GELU><<<grid, blk, 0, st>>>(A, M, K, W, bias, N, out, N, nullptr, 1, 0, nullptr, 0, nullptr, 0, 0);
+    else if (act == 2)
+        linear_act_simt<false, ACT_SIGMOID><<<grid, blk, 0, st>>>(A, M, K, W, bias, N, out, N, nullptr, 1, 0, nullptr, 0, nullptr, 0, 0);
+    else
+        linear_act_simt<false, ACT_NONE><<<grid, blk, 0, st>>>(A, M, K, W, bias, N, out, N, nullptr, 1, 0, nullptr, 0, nullptr, 0, 0);
+    OOV_LAUNCH_CHECK("linear_act_simt");
+    return OOV_OK;
+}
+
+int oov_act(const float* z, const float* dy, int32_t act, int64_t rows, int32_t N, const int64_t* ids, int64_t ids_stride,
+            int64_t n_old, float* out, void* stream) {
+    OOV_REQUIRE(rows >= 0 && N > 0 && act >= 0 && act <= 2 && ids_stride >= 1, OOV_ERR_ARG, "oov_act: bad argument");
+    if (rows == 0) return OOV_OK;
+    OOV_REQUIRE(z && out, OOV_ERR_ARG, "oov_act: NULL pointer");
+    int64_t blocks = cdiv(rows * (int64_t)N, 256);
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    act_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(z, dy, act, rows, N, ids, ids_stride, n_old, out);
+    OOV_LAUNCH_CHECK("act_kernel");
+    return OOV_OK;
+}
+
+size_t oov_fdhe_input_workspace(int64_t n, int32_t H) { return n > 0 ? align_up((size_t)n * (H > 0 ? H : 1) * 4, 256) : 0; }
+
+int oov_fdhe_input(const uint8_t* keys, uint64_t mod, int32_t H, const float* feat, int64_t n_feat_rows, int32_t F,
+                   const int64_t* ids, int64_t ids_stride, int64_t n, int64_t prime_pad, float* x, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+    OOV_REQUIRE(n >= 0 && H >= 0 && F >= 0 && H + F > 0 && ids_stride >= 1, OOV_ERR_ARG, "oov_fdhe_input: bad shape");
+    OOV_REQUIRE(mod >= 1 && mod <= (1ull << 24), OOV_ERR_ARG, "oov_fdhe_input: mod must be in [1, 2^24] (exact in fp32)");
+    if (n == 0) return OOV_OK;
+    OOV_REQUIRE(ids && x && (H == 0 || keys) && (F == 0 || (feat && n_feat_rows > 0)), OOV_ERR_ARG, "oov_fdhe_input: NULL pointer");
+    OOV_REQUIRE(workspace && workspace_bytes >= oov_fdhe_input_workspace(n, H), OOV_ERR_WORKSPACE, "oov_fdhe_input: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* hashes = reinterpret_cast<uint32_t*>(workspace);
+    if (H > 0) {
+        int rc = launch_hash(ids, ids_stride, n, keys, H, mod, hashes, st);
+        if (rc) return rc;
+    }
+    int64_t blocks = cdiv(n * (int64_t)(H + F), 256);
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    fdhe_input_kernel<<<(unsigned)blocks, 256, 0, st>>>(hashes, H, feat, n_feat_rows, F, ids, ids_stride, n, prime_pad, x);
+    OOV_LAUNCH_CHECK("fdhe_input_kernel");
+    return OOV_OK;
 }
 
 size_t oov_fdhe_workspace(int64_t n, const oov_dhe_net* net, int32_t path) {

@@ -20,7 +20,49 @@ from .. import ops
 from .abstract_embedder import AbstractInductiveEmbedder, feature_block, feature_columns
 
 
-class DeepHashEmbedder(AbstractInductiveEmbedder):
+class HashNetTraining:
+    """Training-mode path shared by the dhe / fdhe / dnn embedders: the 4-layer net in fp32 with the
+    pre-activations kept, and its backward (dZ = dA * act'(Z), dW = dZ^T A_prev, db = colsum dZ, dA_prev = dZ W) on the
+    fp32 CUDA-core linear.  Embedders provide `_train_net(side)` -> (nn.Sequential, keys or None, feature matrix or None)."""
+
+    _ACTS = ("gelu", "gelu", "gelu", "sigmoid")
+
+    def train_params(self, side, model):
+        net = self._train_net(side)[0]
+        lin = [m for m in net if isinstance(m, nn.Linear)]
+        return [p for m in lin for p in (m.weight, m.bias)]
+
+    def assemble_rows_train(self, side, ids, model, n_old, iv_table):
+        net, keys, fm = self._train_net(side)
+        lin = [m for m in net if isinstance(m, nn.Linear)]
+        a = ops.fdhe_input(ids, keys, fm, prime_pad=self.prime_pad if (self.training and fm is not None) else 0)
+        acts, pre = [a], []
+        for m, act in zip(lin, self._ACTS):
+            z = ops.linear_f32(a, m.weight.detach(), m.bias.detach(), act="none")
+            a = ops.act_forward(z, act)
+            pre.append(z)
+            acts.append(a)
+        out = a
+        if iv_table is not None and n_old > 0:
+            ops.gather_rows(iv_table, ids, out=out)                # in-vocab rows take the table row (ids >= n_old are skipped)
+        return out, (acts[:-1], pre)
+
+    def backward_rows(self, side, saved, g, ids, n_old, model):
+        net = self._train_net(side)[0]
+        lin = [m for m in net if isinstance(m, nn.Linear)]
+        acts, pre = saved
+        grads = [None] * 8
+        da = g
+        for l in (3, 2, 1, 0):
+            dz = ops.act_backward(pre[l], da, self._ACTS[l], ids if (l == 3 and n_old > 0) else None, n_old)
+            grads[2 * l] = ops.linear_f32(dz.t().contiguous(), acts[l].t().contiguous())          # dW = dZ^T A_prev  [out, in]
+            grads[2 * l + 1] = ops.col_mean(dz) * dz.shape[0]                                      # db = colsum dZ
+            if l:
+                da = ops.linear_f32(dz, lin[l].weight.detach().t().contiguous())                    # dA_prev = dZ W
+        return grads
+
+
+class DeepHashEmbedder(HashNetTraining, AbstractInductiveEmbedder):
     HASH_KEY_PATH = "./hash_keys"
     MAX_HASH = 16777216
 
@@ -109,6 +151,9 @@ class DeepHashEmbedder(AbstractInductiveEmbedder):
             return ops.dhe_embed_planes(planes, ids, net, out=out, out_dtype=out_dtype, n_old=n_old, iv_table=iv_table)
         return ops.dhe_embed(ids, self._keys_dev, net, out=out, out_dtype=out_dtype, n_old=n_old,
                              iv_table=iv_table, mod=DeepHashEmbedder.MAX_HASH, path=self.compute_path)
+
+    def _train_net(self, side):
+        return (self.user_hash_net if side == "user" else self.item_hash_net), self._keys_dev, None
 
     def clear_hash_cache(self):
         """Drop the memoised hash planes (call after changing `hash_keys` / `_keys_dev`)."""

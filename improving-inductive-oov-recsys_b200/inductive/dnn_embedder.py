@@ -11,10 +11,11 @@ import torch
 
 from .. import ops
 from .abstract_embedder import AbstractInductiveEmbedder
+from .dh_embedder import HashNetTraining
 from .feat_dh_embedder import _feature_mats, _hash_net
 
 
-class DNNEmbedder(AbstractInductiveEmbedder):
+class DNNEmbedder(HashNetTraining, AbstractInductiveEmbedder):
     def __init__(self, user_features, item_features, n_original_users, n_original_items, n_user_oov_buckets,
                  n_item_oov_buckets, embedding_size, device, prime_pad, dhe_layer_size) -> None:
         super().__init__(user_features, item_features)
@@ -40,6 +41,10 @@ class DNNEmbedder(AbstractInductiveEmbedder):
         return ops.fdhe_embed(ids, None, ops.DheNet.from_sequential(net, n_feat=fm.shape[1]), fm, out=out, out_dtype=out_dtype,
                               n_old=n_old, iv_table=iv_table, prime_pad=self.prime_pad if self.training else 0,
                               path=self.compute_path)
+
+    def _train_net(self, side):
+        net, fm = self._side(side)
+        return net, None, fm
 
     def _hash_users(self, users, feat_lookup_users=None):
         return self.assemble_rows("user", users, None, 0, None)

@@ -15,7 +15,7 @@ from torch import nn
 
 from .. import ops
 from .abstract_embedder import AbstractInductiveEmbedder, feature_block, feature_columns
-from .dh_embedder import DeepHashEmbedder
+from .dh_embedder import DeepHashEmbedder, HashNetTraining
 
 
 def _hash_net(in_dim: int, layer: int, out_dim: int, device) -> nn.Sequential:
@@ -35,7 +35,7 @@ def _feature_mats(emb: AbstractInductiveEmbedder, device):
     return um.contiguous(), im.contiguous()
 
 
-class FeatDeepHashEmbedder(AbstractInductiveEmbedder):
+class FeatDeepHashEmbedder(HashNetTraining, AbstractInductiveEmbedder):
     HASH_KEY_PATH = "./hash_keys"
     MAX_HASH = 16777216
 
@@ -76,6 +76,10 @@ class FeatDeepHashEmbedder(AbstractInductiveEmbedder):
                               out_dtype=out_dtype, n_old=n_old, iv_table=iv_table,
                               prime_pad=self.prime_pad if self.training else 0, mod=FeatDeepHashEmbedder.MAX_HASH,
                               path=self.compute_path)
+
+    def _train_net(self, side):
+        net, fm = self._side(side)
+        return net, self._keys_dev, fm
 
     def _hash_users(self, users, feat_lookup_users=None):
         return self.assemble_rows("user", users, None, 0, None)

@@ -738,5 +738,66 @@ def lsh_embed_backward(bits: torch.Tensor, g: torch.Tensor, ids: torch.Tensor, n
     return dW
 
 
+_ACT = {"none": 0, "gelu": 1, "sigmoid": 2}
+
+
+def fdhe_input(ids, keys: Optional[torch.Tensor], feat: Optional[torch.Tensor], prime_pad: int = 0, mod: int = MAX_HASH) -> torch.Tensor:
+    """fp32 [n, H + F]: hashes of the raw id (as floats) | feature row of the de-padded id — layer 1's input in training."""
+    ids, stride = _ids_1d(ids)
+    H = 0 if keys is None else keys.shape[0]
+    F = 0 if feat is None else feat.shape[1]
+    if keys is not None:
+        _cuda(keys, "keys", torch.uint8)
+        keys = keys.contiguous()
+    if feat is not None:
+        _cuda(feat, "feat", torch.float32)
+        feat = feat.contiguous()
+    n = ids.shape[0]
+    x = torch.empty((n, H + F), dtype=torch.float32, device=ids.device)
+    lib = _lib.load()
+    ws = _workspace(lib.oov_fdhe_input_workspace(n, H), ids.device) if n else None
+    _lib.check(lib.oov_fdhe_input(_p(keys), int(mod), H, _p(feat), 0 if feat is None else feat.shape[0], F, _p(ids), stride, n,
+                                  int(prime_pad), _p(x), _p(ws), 0 if ws is None else ws.numel(), _stream()))
+    return x
+
+
+def linear_f32(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, act: str = "none") -> torch.Tensor:
+    """fp32 act(A @ W.T + bias) on the CUDA cores (training path; A [M, K], W [N, K])."""
+    _cuda(A, "A", torch.float32)
+    _cuda(W, "W", torch.float32)
+    A, W = A.contiguous(), W.contiguous()
+    if A.dim() != 2 or W.dim() != 2 or A.shape[1] != W.shape[1]:
+        raise ValueError("A [M, K] / W [N, K] inner dimensions differ")
+    if bias is None:
+        bias = torch.zeros((W.shape[0],), dtype=torch.float32, device=A.device)
+    _cuda(bias, "bias", torch.float32)
+    out = torch.empty((A.shape[0], W.shape[0]), dtype=torch.float32, device=A.device)
+    _lib.check(_lib.load().oov_linear_f32(_p(A), _p(W), A.shape[0], W.shape[0], A.shape[1], _p(bias.contiguous()), _ACT[act], _p(out), _stream()))
+    return out
+
+
+def act_forward(z: torch.Tensor, act: str) -> torch.Tensor:
+    _cuda(z, "z", torch.float32)
+    z = z.contiguous()
+    out = torch.empty_like(z)
+    _lib.check(_lib.load().oov_act(_p(z), None, _ACT[act], z.shape[0], z.shape[1], None, 1, 0, _p(out), _stream()))
+    return out
+
+
+def act_backward(z: torch.Tensor, dy: torch.Tensor, act: str, ids: Optional[torch.Tensor] = None, n_old: int = 0) -> torch.Tensor:
+    """dy * act'(z); with `ids`, rows whose id < n_old are zeroed."""
+    _cuda(z, "z", torch.float32)
+    _cuda(dy, "dy", torch.float32)
+    z, dy = z.contiguous(), dy.contiguous()
+    if z.shape != dy.shape:
+        raise ValueError("z / dy shapes differ")
+    stride = 1
+    if ids is not None:
+        ids, stride = _ids_1d(ids)
+    out = torch.empty_like(z)
+    _lib.check(_lib.load().oov_act(_p(z), _p(dy), _ACT[act], z.shape[0], z.shape[1], _p(ids), stride, int(n_old), _p(out), _stream()))
+    return out
+
+
 def launch_count() -> int:
     return int(_lib.load().oov_launch_count())

@@ -324,6 +324,23 @@ int oov_lsh_embed_backward(const uint32_t* bits, int32_t B, const float* g, int6
                            float* dW, void* workspace, size_t workspace_bytes, void* stream);
 size_t oov_lsh_embed_backward_workspace(int64_t n);
 
+/* Hash-net training (dhe / fdhe / dnn; dh_embedder.py:70-89 under autograd), all fp32:
+ * oov_fdhe_input: x[i] = [float(hash_0..H-1 of ids[i]) | feat[id'_i]] — the first layer's input, [n, H + F] contiguous
+ *   (same id rules as oov_fdhe_embed; H = 0 or F = 0 allowed); workspace oov_fdhe_input_workspace(n, H) bytes.
+ * oov_linear_f32: out[M, N] = act(A[M, K] . W[N, K]^T + bias), contiguous operands, act 0 none / 1 GELU(erf) / 2 sigmoid
+ *   — layer forward (act 0: the pre-activations the backward needs) and, with transposed operands, the backward
+ *   products dA = dZ W and dW = dZ^T A.
+ * oov_act: dy == NULL: out = act(z); else out = dy * act'(z), rows whose id < n_old zeroed when ids != NULL (in-vocab
+ *   rows of an assembled batch do not reach the net). */
+int oov_fdhe_input(const uint8_t* keys, uint64_t mod, int32_t H, const float* feat, int64_t n_feat_rows, int32_t F,
+                   const int64_t* ids, int64_t ids_stride, int64_t n, int64_t prime_pad, float* x,
+                   void* workspace, size_t workspace_bytes, void* stream);
+size_t oov_fdhe_input_workspace(int64_t n, int32_t H);
+int oov_linear_f32(const float* A, const float* W, int64_t M, int32_t N, int32_t K, const float* bias, int32_t act,
+                   float* out, void* stream);
+int oov_act(const float* z, const float* dy, int32_t act, int64_t rows, int32_t N,
+            const int64_t* ids, int64_t ids_stride, int64_t n_old, float* out, void* stream);
+
 /* xDeepFM compressed interaction network (xdeepfm.py:134-190) around oov_tc_linear.  All operands
  * bf16; rows of z and of every CIN layer output are (b, d) pairs (b-major), channels run along the row.
  * oov_cin_outer: z[(b*D + d) * ldz + h*M + m] = xi[b, d, h] * x0[b, d, m] (fp32 product, rounded once), channels

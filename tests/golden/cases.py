@@ -290,8 +290,8 @@ def featnet_inputs(case: FeatNetCase) -> dict:
     g = rng(case.seed)
     ucols = feature_columns(g, case.n_all, [("float", w) for w in case.widths])
     icols = feature_columns(g, case.n_all, [("float", w) for w in case.widths])
-    F = int(sum(case.widths))
-    H = case.n_hashes if case.kind == "fdhe" else 0
+    F = int(sum(case.widths)) if case.kind != "dhe" else 0          # the plain dhe net takes hashes only (dh_embedder.py:71)
+    H = case.n_hashes if case.kind in ("fdhe", "dhe") else 0
     dims = [H + F, case.layer, case.layer, case.layer, case.D]
     nets = {}
     for side in ("user", "item"):
@@ -302,7 +302,8 @@ def featnet_inputs(case: FeatNetCase) -> dict:
             b = g.uniform(-bound, bound, size=(dims[l + 1],)).astype(np.float32)
             if l == 0 and H:
                 w[:, :H] *= np.float32(case.h_scale)
-                w[:, H:] *= np.float32(np.sqrt(dims[0] / F))           # features carry weight next to the hashes
+                if F:
+                    w[:, H:] *= np.float32(np.sqrt(dims[0] / F))       # features carry weight next to the hashes
             ws.append(w)
             bs.append(b)
         nets[side] = (ws, bs)
@@ -331,3 +332,33 @@ def train_batch(case: RetrievalCase, batch: int = 192) -> dict:
     pad_u = g.random(batch) < 0.5
     pad_i = g.random(batch) < 0.5
     return dict(users=users + pad_u * OOV_PRIME_PAD, pos=pos + pad_i * OOV_PRIME_PAD, neg=neg)
+
+
+# hash-net embedders under training (BPR on top; n_old = n_all // 2 in-vocab ids per side)
+HASHNET_TRAIN_CASES: Dict[str, FeatNetCase] = {
+    "train_fdhe": FeatNetCase("train_fdhe", 211, "fdhe", n_hashes=32, layer=64, D=16, n_all=240, h_scale=4e-7, widths=(8, 1, 6)),
+    "train_dnn": FeatNetCase("train_dnn", 212, "dnn", layer=96, D=24, n_all=200, widths=(5, 8)),
+    "train_dhe": FeatNetCase("train_dhe", 213, "dhe", n_hashes=16, layer=512, D=16, n_all=200, h_scale=8e-7),
+}
+
+
+def hashnet_train_inputs(case: FeatNetCase, batch: int = 160) -> dict:
+    inp = featnet_inputs(case)
+    g = rng(case.seed + 99)
+    n_old = case.n_all // 2
+    inp["n_old"] = n_old
+    inp["user_table"] = xavier_normal(g, n_old, case.D)
+    inp["item_table"] = xavier_normal(g, n_old, case.D)
+    users = g.integers(1, n_old, size=batch, dtype=np.int64)
+    pos = g.integers(1, n_old, size=batch, dtype=np.int64)
+    neg = g.integers(1, n_old, size=batch, dtype=np.int64)
+    inp["batch"] = dict(users=users + (g.random(batch) < 0.5) * OOV_PRIME_PAD, pos=pos + (g.random(batch) < 0.5) * OOV_PRIME_PAD, neg=neg)
+    return inp
+
+
+def grad_slice(a: np.ndarray) -> np.ndarray:
+    """Fixtures keep every row of a small gradient and every s-th row of a large one (<= ~20k elements)."""
+    a = np.asarray(a)
+    if a.ndim < 2 or a.size <= 20000:
+        return a
+    return a[:: int(np.ceil(a.size / 20000))]

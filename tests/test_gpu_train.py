@@ -113,3 +113,61 @@ def test_scatter_add_rows_vs_oracle():
     dt.zero_()
     ops.scatter_add_rows(torch.from_numpy(gnp).to(DEV), torch.from_numpy(idx).to(DEV), dt, idx_offset=-100)
     pu.assert_close(dt.cpu().numpy(), o.scatter_add_rows(gnp, idx - 100, rows), rtol=1e-4, atol=1e-4, what="scatter add offset")
+
+
+@pytest.mark.parametrize("name", list(cases.HASHNET_TRAIN_CASES))
+def test_hash_net_training_vs_reference(name, tmp_path):
+    """BPR + dhe / fdhe / dnn in `set_oov_train()` mode: loss, table gradients and the gradients of all 16 hash-net
+    parameters against the unmodified reference under autograd (fp32 path, rtol 2e-4 of each tensor's scale)."""
+    import json
+    import gpu_util as G
+    import oov_b200
+    g = np.load(GOLD)
+    case = cases.HASHNET_TRAIN_CASES[name]
+    inp = cases.hashnet_train_inputs(case)
+    n_old = inp["n_old"]
+    keys = cases.dhe_keys(case.seed, case.n_hashes)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        os.makedirs("hash_keys", exist_ok=True)
+        with open(f"hash_keys/{case.n_hashes}.hashes", "w") as f:
+            json.dump([k.hex() for k in keys], f)
+        cfg = G.make_config(case, case.kind, user_oov_buckets=4, item_oov_buckets=4, dhe_num_hashes=case.n_hashes, dhe_layer_size=case.layer)
+        ds = G.Dataset(n_old, n_old, G.interaction("user_id", inp["user_cols"]), G.interaction("item_id", inp["item_cols"]))
+        emb = oov_b200.get_inductive_embedder(cfg, ds, mode=f"test-train-{name}", user_num=n_old, item_num=n_old)
+    finally:
+        os.chdir(cwd)
+    model = oov_b200.BPR(cfg, ds, inductive_mapper=None, inductive_embedder=emb).to(DEV)
+    with torch.no_grad():
+        model.user_embedding.weight.copy_(G.t(inp["user_table"]))
+        model.item_embedding.weight.copy_(G.t(inp["item_table"]))
+        for side, net in (("user", emb.user_hash_net), ("item", emb.item_hash_net)):
+            ws, bs = inp["nets"][side]
+            for l, li in enumerate((0, 2, 4, 6)):
+                net[li].weight.copy_(G.t(ws[l]))
+                net[li].bias.copy_(G.t(bs[l]))
+    model.train()
+    model.set_oov_train()
+    b = inp["batch"]
+    inter = oov_b200.Interaction({"user_id": G.t(b["users"]), "item_id": G.t(b["pos"]), "neg_item_id": G.t(b["neg"])})
+    loss = model.calculate_loss(inter)
+    loss.backward()
+    want_loss = float(g[f"{name}.loss"])
+    assert abs(loss.item() - want_loss) <= 1e-5 * max(1.0, abs(want_loss)), (loss.item(), want_loss)
+    got = {"user_embedding": model.user_embedding.weight.grad, "item_embedding": model.item_embedding.weight.grad}
+    for side, net in (("user", emb.user_hash_net), ("item", emb.item_hash_net)):
+        for li in (0, 2, 4, 6):
+            got[f"{side}_hash_net.{li}.weight"] = net[li].weight.grad
+            got[f"{side}_hash_net.{li}.bias"] = net[li].bias.grad
+    worst = 0.0
+    for nm, gr in got.items():
+        want = g[f"{name}.grad_{nm}"]
+        assert gr is not None, nm
+        have = cases.grad_slice(gr.cpu().numpy()) if nm.endswith("weight") and "hash_net" in nm else gr.cpu().numpy()
+        assert have.shape == want.shape, (nm, have.shape, want.shape)
+        scale = np.abs(want).max()
+        err = np.abs(have - want).max()
+        worst = max(worst, err / max(scale, 1e-30))
+        assert err <= 2e-4 * scale + 1e-9, (name, nm, err, scale)
+    print(f"[{name}] loss {loss.item():.6f}; worst gradient error / tensor scale {worst:.2e}")
