@@ -44,6 +44,8 @@ SIGNATURES = {
     "oov_lsh_bits": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, c_i64, c_i64, c_i64, c_f32, c_vp, c_vp, c_i32, c_vp]),
     "oov_lsh_embed": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, c_i32, C.POINTER(OovRows), c_f32, c_vp, c_vp,
                               c_vp, c_sz, c_i32, c_vp]),
+    "oov_lsh_embed_cast": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, c_i32, C.POINTER(OovRows), c_f32, c_vp, c_vp,
+                                   c_vp, c_sz, c_i32, c_vp, c_vp, c_i64, c_vp]),
     "oov_lsh_embed_workspace": (c_sz, [c_i64, c_i32, c_i32, c_i32]),
     "oov_slsh_embed": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, C.POINTER(OovRows), c_f32, c_vp,
                                c_vp, c_vp]),

@@ -454,9 +454,11 @@ int check_rows_public(const oov_rows* r, const char* who) { return check_rows(r,
 namespace tc {
 bool lsh_tc_supported(int F, int B, int D);
 size_t lsh_tc_workspace(int64_t n, int B);
+int launch_cast_f32_bf16(const float* src, void* dst, int64_t n_elems, cudaStream_t st);
 int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* planes, int B, const void* W, int w_dtype,
                const oov_rows* rows, float tie_eps, uint32_t* bits_out, unsigned long long* tie_count, void* workspace,
-               size_t workspace_bytes, cudaStream_t st);
+               size_t workspace_bytes, cudaStream_t st, const float* cast_src = nullptr, void* cast_dst = nullptr,
+               int64_t cast_elems = 0);
 }  // namespace tc
 
 }  // namespace oov
@@ -492,19 +494,33 @@ int oov_lsh_embed(const float* feat, int64_t n_feat_rows, int32_t F, const float
                   const void* W, int32_t w_dtype, const oov_rows* rows, float tie_eps,
                   uint32_t* bits_out, unsigned long long* tie_count,
                   void* workspace, size_t workspace_bytes, int32_t path, void* stream) {
+    return oov_lsh_embed_cast(feat, n_feat_rows, F, planes, B, W, w_dtype, rows, tie_eps, bits_out, tie_count, workspace,
+                              workspace_bytes, path, nullptr, nullptr, 0, stream);
+}
+
+int oov_lsh_embed_cast(const float* feat, int64_t n_feat_rows, int32_t F, const float* planes, int32_t B,
+                       const void* W, int32_t w_dtype, const oov_rows* rows, float tie_eps,
+                       uint32_t* bits_out, unsigned long long* tie_count,
+                       void* workspace, size_t workspace_bytes, int32_t path,
+                       const float* cast_src, void* cast_dst, int64_t cast_elems, void* stream) {
     int rc = check_rows(rows, "oov_lsh_embed");
     if (rc) return rc;
+    OOV_REQUIRE(cast_elems >= 0 && cast_elems % 8 == 0, OOV_ERR_ARG, "oov_lsh_embed_cast: cast_elems=%lld must be a multiple of 8", (long long)cast_elems);
+    OOV_REQUIRE(cast_elems == 0 || (cast_src && cast_dst && aligned(cast_src, 16) && aligned(cast_dst, 16)), OOV_ERR_ALIGN,
+                "oov_lsh_embed_cast: cast_src / cast_dst must be non-NULL and 16-byte aligned");
     OOV_REQUIRE(feat && planes && W && dtype_ok(w_dtype), OOV_ERR_ARG, "oov_lsh_embed: NULL pointer / bad dtype");
     OOV_REQUIRE(F > 0 && B > 0 && n_feat_rows > 0, OOV_ERR_ARG, "oov_lsh_embed: bad shape F=%d B=%d", F, B);
     OOV_REQUIRE(path >= OOV_PATH_AUTO && path <= OOV_PATH_TCGEN05, OOV_ERR_ARG, "oov_lsh_embed: unsupported path %d", path);
-    if (rows->n == 0) return OOV_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (rows->n == 0) return tc::launch_cast_f32_bf16(cast_src, cast_dst, cast_elems, st);
     // tensor cores (split-bf16 exact-sign GEMM fused with the bucket-mean GEMM) when the tile shapes allow
     const bool tc_ok = tc::lsh_tc_supported(F, B, rows->D);
     OOV_REQUIRE(path != OOV_PATH_TCGEN05 || tc_ok, OOV_ERR_ARG, "oov_lsh_embed: tcgen05 path needs F <= 64 and D <= 64 (F=%d D=%d)", F, rows->D);
     if (tc_ok && path != OOV_PATH_SIMT_FP32)
         return tc::lsh_tc_run(feat, n_feat_rows, F, planes, B, W, w_dtype, rows, tie_eps, bits_out, tie_count, workspace,
-                              workspace_bytes, st);
+                              workspace_bytes, st, cast_src, cast_dst, cast_elems);
+    rc = tc::launch_cast_f32_bf16(cast_src, cast_dst, cast_elems, st);
+    if (rc) return rc;
     const int words = (B + 31) / 32;
     const int64_t chunk = bits_out ? rows->n : (rows->n < (1 << 20) ? rows->n : (1 << 20));
     if (!bits_out) {

@@ -84,6 +84,7 @@ struct LshParams {
     const float* wsum;                                 // [64] column sums of the packed bucket table
     const __half* Wt; int64_t nb;                      // packed bucket table [wsplit * 64, nb] (rank-one sign corrections)
     const uint8_t* flags;                              // [ceil(n / 128)] 1 = the row tile holds an OOV id (lsh_flags_kernel)
+    const float* cast_src; __nv_bfloat16* cast_dst; int64_t cast_n8;   // side job of the TMA warp: bf16(cast_src[0 .. 8 cast_n8))
     unsigned long long* trace;                         // profiling only (OOV_LSH_TRACE_PTR): [4 roles][4096] event << 56 | clock of CTA 0
 };
 // one timestamp of CTA 0 (roles: 0 MMA1, 1 MMA2, 2 worker warp 0, 3 worker warp 15); a no-op unless a trace buffer is set
@@ -453,6 +454,38 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         // ===================== TMA: B' tiles and transposed bucket-table tiles (one ring each, filled in consumption order) =====================
         int bst = 0, wst = 0; uint32_t bphase = 0, wphase = 0;
         bool b_done = false, w_done = false;                          // resident operands are loaded once
+        // Side job: the fp32 -> bf16 cast of the in-vocab rows of the same item table (bpr.py:111-112 for a contiguous id
+        // range).  As its own launch this memory-bound copy cannot share an SM with the 640-thread / 96-register LSH CTAs
+        // and runs in front of them; here this warp does it a 4 KB group at a time WHILE IT WAITS for a free stage of the
+        // bucket-table ring (the ring is full then, so the consumers are not held up), in the shadow of the latency-bound
+        // GEMM pipeline (a few percent of the DRAM bandwidth).  A group = 32 lanes x 4 x 8 elements; the lines of the group
+        // four ahead are pulled into L2 first.
+        const int64_t cast_groups = (p.cast_n8 + 127) >> 7;
+        int64_t cast_g = blockIdx.x;
+        auto cast_step = [&]() {
+            const float4* src = reinterpret_cast<const float4*>(p.cast_src);
+            uint4* dst = reinterpret_cast<uint4*>(p.cast_dst);
+            const int64_t g = cast_g, gp = cast_g + 4 * (int64_t)gridDim.x;
+            cast_g += gridDim.x;
+            if (gp < cast_groups && (gp << 7) + lane * 4 < p.cast_n8)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(src) + (gp << 12) + lane * 128));
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t i8 = (g << 7) + j * 32 + lane;
+                if (i8 < p.cast_n8) { v[2 * j] = __ldcs(src + 2 * i8); v[2 * j + 1] = __ldcs(src + 2 * i8 + 1); }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t i8 = (g << 7) + j * 32 + lane;
+                if (i8 < p.cast_n8) {
+                    __nv_bfloat162 a = __floats2bfloat162_rn(v[2 * j].x, v[2 * j].y), b = __floats2bfloat162_rn(v[2 * j].z, v[2 * j].w);
+                    __nv_bfloat162 c = __floats2bfloat162_rn(v[2 * j + 1].x, v[2 * j + 1].y), d = __floats2bfloat162_rn(v[2 * j + 1].z, v[2 * j + 1].w);
+                    dst[i8] = make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b),
+                                         *reinterpret_cast<uint32_t*>(&c), *reinterpret_cast<uint32_t*>(&d));
+                }
+            }
+        };
         for (int64_t t = next_oov(blockIdx.x); t < n_tiles && !(b_done && w_done); t = next_oov(t + gridDim.x)) {
             for (int nt = 0; nt < NT; ++nt) {
                 if (!b_done)
@@ -467,7 +500,10 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                     }
                 if (!w_done)
                     for (int pc = 0; pc < p.wsplit; ++pc) {
-                        if (!p.res_w) mbar_wait_spin(&w_empty[wst], wphase ^ 1);
+                        if (!p.res_w) {
+                            while (cast_g < cast_groups && !mbar_test_wait(&w_empty[wst], wphase ^ 1)) cast_step();
+                            mbar_wait_spin(&w_empty[wst], wphase ^ 1);
+                        }
                         if (leader) {
                             mbar_arrive_expect_tx(&w_full[wst], L_WT_BYTES);
                             tma_load_2d(sW + wst * L_WT_BYTES, &tmW, &w_full[wst], nt * L_BN, pc * L_DMAX);
@@ -480,6 +516,7 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
             b_done = p.res_b != 0;
             w_done = p.res_w != 0;
         }
+        while (cast_g < cast_groups) cast_step();                    // what is left of the side job
     } else if (warp == W_MMA1) {
         // ===================== MMA issuer 1: projections =====================
         constexpr uint32_t idesc1 = make_idesc_bf16_f32(L_BM, L_BN) & ~((7u << 7) | (7u << 10));   // A, B = fp16 (format 0)
@@ -895,6 +932,27 @@ tc_lsh_embed_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
     }
 }
 
+// the side cast as its own launch (operands not resident: the TMA warp stays busy; or no OOV tile at all)
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, int64_t n8) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 u = __ldcs(src + 2 * i), w = __ldcs(src + 2 * i + 1);
+        __nv_bfloat162 a = __floats2bfloat162_rn(u.x, u.y), b = __floats2bfloat162_rn(u.z, u.w);
+        __nv_bfloat162 c = __floats2bfloat162_rn(w.x, w.y), d = __floats2bfloat162_rn(w.z, w.w);
+        dst[i] = make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b), *reinterpret_cast<uint32_t*>(&c),
+                            *reinterpret_cast<uint32_t*>(&d));
+    }
+}
+int launch_cast_f32_bf16(const float* src, void* dst, int64_t n_elems, cudaStream_t st) {
+    if (n_elems <= 0) return OOV_OK;
+    int64_t blocks = cdiv(n_elems / 8, 256);
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    cast_f32_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint4*>(dst), n_elems / 8);
+    OOV_LAUNCH_CHECK("cast_f32_bf16_kernel");
+    return OOV_OK;
+}
+
 // ---------------------------------------------------------------- host
 bool lsh_tc_supported(int F, int B, int D) { return F >= 1 && F <= L_FMAX && D >= 1 && D <= L_DMAX && B >= 1 && B <= (1 << 22); }
 
@@ -905,7 +963,7 @@ size_t lsh_tc_workspace(int64_t n, int B) { return lsh_bp_bytes(B) + lsh_wt_byte
 
 int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* planes, int B, const void* W, int w_dtype,
                const oov_rows* rows, float tie_eps, uint32_t* bits_out, unsigned long long* tie_count, void* workspace,
-               size_t workspace_bytes, cudaStream_t st) {
+               size_t workspace_bytes, cudaStream_t st, const float* cast_src, void* cast_dst, int64_t cast_elems) {
     OOV_REQUIRE(workspace && workspace_bytes >= lsh_tc_workspace(rows->n, B), OOV_ERR_WORKSPACE, "oov_lsh_embed (tcgen05): workspace %zu < %zu",
                 workspace_bytes, lsh_tc_workspace(rows->n, B));
     char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
@@ -928,6 +986,18 @@ int lsh_tc_run(const float* feat, int64_t n_feat_rows, int F, const float* plane
     p.res_w = NT * p.wsplit <= L_WSTAGES ? 1 : 0;
     p.tie_eps = tie_eps; p.bits_out = bits_out; p.words = (B + 31) / 32; p.tie_count = tie_count; p.pn_min = pn_min; p.wsum = wsum;
     p.Wt = Wt; p.nb = nb; p.flags = flags;
+    const int64_t n_tiles_ = cdiv(rows->n, L_BM);
+    static int fuse_cast = -1;
+    if (fuse_cast < 0) { const char* e = getenv("OOV_LSH_FUSE_CAST"); fuse_cast = e ? atoi(e) : 1; }   // A/B knob (profiling)
+    if (cast_elems > 0) {
+        // every CTA's TMA warp takes a share: the grid must fill the machine
+        if (fuse_cast && n_tiles_ >= num_sms()) {
+            p.cast_src = cast_src; p.cast_dst = reinterpret_cast<__nv_bfloat16*>(cast_dst); p.cast_n8 = cast_elems / 8;
+        } else {
+            int rc0 = launch_cast_f32_bf16(cast_src, cast_dst, cast_elems, st);
+            if (rc0) return rc0;
+        }
+    }
 #ifdef OOV_LSH_TRACE
     if (const char* tp = getenv("OOV_LSH_TRACE_PTR")) p.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0));   // profiling only
 #endif

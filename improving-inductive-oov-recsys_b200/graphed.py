@@ -78,9 +78,10 @@ class GraphedTopK:
                 # the in-vocab half of the table (a memory-bound gather-cast) joins the query-side branch, the OOV half
                 # (SipHash + MLP / LSH GEMMs) is the main branch
                 table = torch.empty((self.N, m.embedding_size), dtype=m.table_dtype, device=m.device)
-                with torch.cuda.stream(self._side):
-                    m.build_item_table(self.N, row_range=(0, split), out=table[:split])
-                m.build_item_table(self.N, row_range=(split, self.N), out=table[split:])
+                if not m.build_item_rows_fused((0, split), table[:split], (split, self.N), table[split:]):
+                    with torch.cuda.stream(self._side):
+                        m.build_item_table(self.N, row_range=(0, split), out=table[:split])
+                    m.build_item_table(self.N, row_range=(split, self.N), out=table[split:])
             else:
                 table = m.build_item_table(self.N)
             cur.wait_stream(self._side)

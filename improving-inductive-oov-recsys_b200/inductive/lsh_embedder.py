@@ -78,12 +78,14 @@ class LSHInductiveEmbedder(AbstractInductiveEmbedder):
         return self._hash_node(items, self.item_lsh, self.item_feature_mat)
 
     # --- embedding (lsh_embedder.py:141-179) ----------------------------------------------
-    def assemble_rows(self, side, ids, model, n_old, iv_table, out=None, out_dtype=torch.float32):
+    SIDE_CAST = True     # assemble_rows(side_cast=(src, dst)) folds a contiguous fp32 -> bf16 row cast into the launch
+
+    def assemble_rows(self, side, ids, model, n_old, iv_table, out=None, out_dtype=torch.float32, side_cast=None):
         lsh, fm = self._side(side)
         w = (model.user_oov_buckets if side == "user" else model.item_oov_buckets).weight.detach()
         return ops.lsh_embed(fm, lsh.uniform_planes[0].data, w, ids, out=out, out_dtype=out_dtype, n_old=n_old,
                              iv_table=iv_table, prime_pad=self.prime_pad if self.training else 0,
-                             tie_count=self.tie_count)
+                             tie_count=self.tie_count, side_cast=side_cast)
 
     # training: out = (H W) / |H| is linear in W = model.*_oov_buckets.weight; the backward re-uses the forward's bits
     def train_params(self, side, model):

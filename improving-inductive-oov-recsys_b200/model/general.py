@@ -251,6 +251,8 @@ class InductiveGeneralRecommender(nn.Module):
             ids = torch.arange(lo, hi, device=self.device, dtype=torch.int64)
             return self._assemble("item", ids, out=out, out_dtype=self.table_dtype)
         split = min(max(self.n_items, lo), hi)
+        if lo < split < hi and self.build_item_rows_fused((lo, split), out[: split - lo], (split, hi), out[split - lo:]):
+            return out
         if split > lo:
             ids_iv = self._id_range(lo, split)
             ops.gather_rows(self.item_embedding.weight.detach(), ids_iv, out=out[: split - lo])
@@ -260,6 +262,27 @@ class InductiveGeneralRecommender(nn.Module):
             self.inductive_embedder.assemble_rows("item", ids_oov, self, 0, None, out=out[split - lo:],
                                                   out_dtype=self.table_dtype, **kw)
         return out
+
+    def build_item_rows_fused(self, iv_range: Tuple[int, int], iv_out: torch.Tensor, oov_range: Tuple[int, int],
+                              oov_out: torch.Tensor) -> bool:
+        """In-vocab rows [iv_range) and OOV rows [oov_range) of the all-item table in ONE embedder launch: the in-vocab
+        part of a bf16 table is a contiguous fp32 -> bf16 cast of `item_embedding.weight` rows, which an embedder with
+        `SIDE_CAST` (lsh) runs inside its own kernel instead of as a separate memory-bound launch in front of it.
+        Returns False (nothing done) when the combination does not apply."""
+        emb, w = self.inductive_embedder, self.item_embedding.weight.detach()
+        (a, b), (c, d) = iv_range, oov_range
+        if emb is None or self.inductive_mapper is not None or not getattr(emb, "SIDE_CAST", False):
+            return False
+        if not (0 <= a < b <= self.n_items <= c < d) or self.table_dtype != torch.bfloat16 or w.dtype != torch.float32:
+            return False
+        D = self.embedding_size
+        if not (w.is_contiguous() and iv_out.is_contiguous() and iv_out.dtype == torch.bfloat16 and iv_out.shape == (b - a, D)):
+            return False
+        src = w[a:b]
+        if ((b - a) * D) % 8 or src.data_ptr() % 16 or iv_out.data_ptr() % 16:
+            return False
+        emb.assemble_rows("item", self._id_range(c, d), self, 0, None, out=oov_out, out_dtype=self.table_dtype, side_cast=(src, iv_out))
+        return True
 
     def _id_range(self, lo: int, hi: int) -> torch.Tensor:
         """arange(lo, hi) on the device, kept for the few ranges a model is asked for again and again (the halves of its

@@ -131,8 +131,10 @@ def lsh_bits(feat, planes, ids, prime_pad: int = 0, tie_eps: float = TIE_EPS,
 
 def lsh_embed(feat, planes, oov_weight, ids, out=None, out_dtype=torch.float32, n_old: int = 0, iv_table=None,
               prime_pad: int = 0, tie_eps: float = TIE_EPS, tie_count=None, return_bits: bool = False,
-              path: int = PATH_AUTO):
-    """(H @ W) / H.sum(1) for OOV rows (lsh_embedder.py:141-179) + in-vocab gather (bpr.py:94-125)."""
+              path: int = PATH_AUTO, side_cast=None):
+    """(H @ W) / H.sum(1) for OOV rows (lsh_embedder.py:141-179) + in-vocab gather (bpr.py:94-125).
+    `side_cast=(src fp32, dst bf16)`: contiguous tensors of equal size (a multiple of 8 elements); dst = bf16(src) is
+    done inside the same launch (the in-vocab half of a bf16 item table, see oov_lsh_embed_cast)."""
     feat, planes = _feat_planes(feat, planes)
     _cuda(oov_weight, "oov_weight")
     oov_weight = oov_weight.contiguous()
@@ -145,9 +147,17 @@ def lsh_embed(feat, planes, oov_weight, ids, out=None, out_dtype=torch.float32, 
     bits = torch.empty((rows.n, (B + 31) // 32), dtype=torch.int32, device=feat.device) if return_bits else None
     ws_bytes = lib.oov_lsh_embed_workspace(rows.n, B, D, path)
     ws = _workspace(ws_bytes, feat.device) if ws_bytes else None
-    _lib.check(lib.oov_lsh_embed(_p(feat), feat.shape[0], F, _p(planes), B, _p(oov_weight), _dt(oov_weight),
-                                 C.byref(rows), float(tie_eps), _p(bits), _p(tie_count), _p(ws),
-                                 0 if ws is None else ws.numel(), path, _stream()))
+    csrc = cdst = None
+    if side_cast is not None:
+        csrc, cdst = side_cast
+        _cuda(csrc, "side_cast src", torch.float32)
+        _cuda(cdst, "side_cast dst", torch.bfloat16)
+        if not (csrc.is_contiguous() and cdst.is_contiguous()) or csrc.numel() != cdst.numel() or csrc.numel() % 8:
+            raise ValueError("side_cast needs contiguous fp32 / bf16 tensors of equal size, a multiple of 8 elements")
+    _lib.check(lib.oov_lsh_embed_cast(_p(feat), feat.shape[0], F, _p(planes), B, _p(oov_weight), _dt(oov_weight),
+                                      C.byref(rows), float(tie_eps), _p(bits), _p(tie_count), _p(ws),
+                                      0 if ws is None else ws.numel(), path, _p(csrc), _p(cdst),
+                                      0 if csrc is None else csrc.numel(), _stream()))
     return (out, bits) if return_bits else out
 
 

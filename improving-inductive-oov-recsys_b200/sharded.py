@@ -89,6 +89,9 @@ class ShardedRetrieval:
             n1 = self.segments[1][1] - self.segments[1][0]
             self.table = torch.empty((n0 + n1, m.embedding_size), dtype=m.table_dtype, device=m.device)
             self.tables = [self.table[:n0], self.table[n0:]]
+            (a, b), (c, d) = self.segments
+            if b > a and d > c and m.build_item_rows_fused((a, b), self.tables[0], (c, d), self.tables[1]):
+                return self.tables                                 # in-vocab cast folded into the OOV embed launch
             for i, ((lo, hi), out) in enumerate(zip(self.segments, self.tables)):
                 if hi <= lo:
                     continue

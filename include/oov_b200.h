@@ -94,6 +94,18 @@ int oov_lsh_embed(const float* feat, int64_t n_feat_rows, int32_t F,
                   void* workspace, size_t workspace_bytes,
                   int32_t path, void* stream);
 size_t oov_lsh_embed_workspace(int64_t n, int32_t B, int32_t D, int32_t path);
+/* oov_lsh_embed plus a side job: cast_dst[0 .. cast_elems) = bf16(cast_src[0 .. cast_elems)) (cast_elems % 8 == 0, both
+ * 16-byte aligned) — the in-vocab half of the same bf16 item table when its ids are a contiguous range
+ * (bpr.py:111-112 `item_e[in_vocab_items] = item_embedding(item[in_vocab_items])` for item = arange).  On the tcgen05
+ * path with enough OOV rows to fill the machine the copy is done by the TMA warp of every CTA while it waits for a free
+ * ring stage, in the shadow of the GEMM pipeline; otherwise it is a separate launch on the same stream. */
+int oov_lsh_embed_cast(const float* feat, int64_t n_feat_rows, int32_t F,
+                       const float* planes, int32_t B,
+                       const void* oov_weight, int32_t w_dtype,
+                       const oov_rows* rows, float tie_eps,
+                       uint32_t* bits_out, unsigned long long* tie_count,
+                       void* workspace, size_t workspace_bytes, int32_t path,
+                       const float* cast_src, void* cast_dst, int64_t cast_elems, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * SLSH — replaces inductive/single_lsh_embedder.py:77-109.

@@ -512,3 +512,52 @@ def test_slsh_single_bucket_and_gather_rows_out_validation():
                 torch.empty((10, 8))):
         with pytest.raises((ValueError, RuntimeError)):
             ops.gather_rows(table, idx, out=bad)
+
+
+def test_lsh_side_cast_builds_the_same_item_table():
+    """`build_item_rows_fused`: the fp32 -> bf16 cast of the in-vocab rows done by the LSH kernel's idle TMA warp
+    (oov_lsh_embed_cast) gives the table of the two separate launches bit for bit — whole table, a row shard, sizes that
+    are not multiples of the copy group, and the stand-alone cast when the OOV part is too small to fill the machine."""
+    import oov_b200
+    import gpu_util as G
+    from oov_b200 import ops
+    gen = torch.Generator().manual_seed(9)
+    D, F_, B = 64, 32, 1000
+    n_old, n_all = 30011, 30011 + 40037
+
+    cfg = G.Config(USER_ID_FIELD="user_id", ITEM_ID_FIELD="item_id", NEG_PREFIX="neg_", device=DEV, embedding_size=D, add_oov_buckets=True,
+                   inductive_embedder="lsh", user_oov_buckets=B, item_oov_buckets=B, table_dtype="bfloat16", oov_normalization_type="global")
+    uf = oov_b200.Interaction({"user_id": torch.arange(64), "f0": torch.randn(64, F_, generator=gen)})
+    itf = oov_b200.Interaction({"item_id": torch.arange(n_all), "f0": torch.randn(n_all, F_, generator=gen)})
+    ds = G.Dataset(32, n_old, uf, itf)
+    emb = oov_b200.get_inductive_embedder(cfg, ds, mode="test-side-cast")
+    model = oov_b200.BPR(cfg, ds, inductive_embedder=emb).to(DEV).eval()
+    w = model.item_embedding.weight.detach()
+
+    def separate(a, b, c, d):
+        out = torch.empty((b - a + d - c, D), dtype=torch.bfloat16, device=DEV)
+        ops.gather_rows(w, torch.arange(a, b, device=DEV), out=out[: b - a])
+        emb.assemble_rows("item", torch.arange(c, d, device=DEV), model, 0, None, out=out[b - a:], out_dtype=torch.bfloat16)
+        return out
+
+    l0 = ops.launch_count()
+    table = model.build_item_table(n_all)
+    fused_launches = ops.launch_count() - l0
+    want = separate(0, n_old, n_old, n_all)
+    assert torch.equal(table.view(torch.int16), want.view(torch.int16))
+    l0 = ops.launch_count()
+    separate(0, n_old, n_old, n_all)
+    assert fused_launches == ops.launch_count() - l0 - 1            # one launch fewer: the gather-cast is gone
+    # a row shard [in-vocab slice | OOV slice] through the same entry
+    a, b, c, d = 1000, 20001, n_old + 777, n_old + 777 + 25000
+    out = torch.empty((b - a + d - c, D), dtype=torch.bfloat16, device=DEV)
+    assert model.build_item_rows_fused((a, b), out[: b - a], (c, d), out[b - a:])
+    assert torch.equal(out.view(torch.int16), separate(a, b, c, d).view(torch.int16))
+    # few OOV rows (fewer row tiles than SMs): the cast runs as its own launch, same result
+    a, b, c, d = 0, n_old, n_old, n_old + 300
+    out = torch.empty((b - a + d - c, D), dtype=torch.bfloat16, device=DEV)
+    assert model.build_item_rows_fused((a, b), out[: b - a], (c, d), out[b - a:])
+    assert torch.equal(out.view(torch.int16), separate(a, b, c, d).view(torch.int16))
+    # fp32 tables do not take the fused path
+    model.table_dtype = torch.float32
+    assert not model.build_item_rows_fused((0, 8), torch.empty((8, D), device=DEV), (n_old, n_old + 8), torch.empty((8, D), device=DEV))
