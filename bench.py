@@ -12,8 +12,9 @@ items (in-vocab gather + OOV embed) into the bf16 item table, score Q x N, mask 
 Default workload `lsh10m` = BASELINE.json configs[4], the configuration the metric's target is quoted on (BPR + lsh,
 10M items of which 5M OOV, F = 32, B = 1000, D = 64, Q = 1024, k = 20; it fits one B200).  The same JSON line carries
 a second block `workloads.dhe1m` = configs[1] (DirectAU + dhe, 1M items / 100k users, bf16) with its own value / e2e /
-roofline, measured in the same process (`--single` skips it), and at N = 1 a third block `workloads.dcnv2_criteo` =
-configs[2] (DCNV2 ranking tower with slsh OOV buckets, 65536 rows x 26 token fields per step, rows/s).
+roofline, measured in the same process (`--single` skips it), and at N = 1 the ranking blocks `workloads.dcnv2_criteo` =
+configs[2] (DCNV2 tower with slsh OOV buckets, 65536 rows x 26 token fields per step, rows/s) and
+`workloads.xdeepfm_criteo` = configs[3] (xDeepFM: first-order + CIN + MLP with the `mean` embedder, same rows).
 With N > 1 the item rows are sharded over the ranks (strong scaling: total work fixed), each rank embeds and
 scores its shard, one NCCL all-gather moves the [S, Q, k] candidates and every rank merges.
 Prints ONE JSON line on rank 0.
@@ -58,7 +59,7 @@ def parse_args():
     ap.add_argument("--workload", default="lsh10m", choices=list(WORKLOADS))
     ap.add_argument("--second", default="dhe1m", choices=list(WORKLOADS), help="second workload reported under `workloads`")
     ap.add_argument("--single", action="store_true", help="measure only --workload")
-    ap.add_argument("--no-dcnv2", dest="dcnv2", action="store_false", help="skip the workloads.dcnv2_criteo block (N = 1 only)")
+    ap.add_argument("--no-dcnv2", dest="dcnv2", action="store_false", help="skip the workloads.dcnv2_criteo / xdeepfm_criteo blocks (N = 1 only)")
     ap.add_argument("--Q", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
@@ -745,6 +746,152 @@ def run_dcnv2(args, device):
     return res
 
 
+XDEEPFM_WL = dict(rows=65536, fields=26, D=10, mlp=[128, 128, 128], cin=[100, 100, 100], n_users=100_000, n_old_users=50_000,
+                  n_items=100_000, n_old_items=50_000, other_vocab=100_000)
+
+
+def run_xdeepfm(args, device):
+    """BASELINE.json configs[3]: xDeepFM ranking with the `mean` OOV embedder on the same
+    Criteo-shaped synthetic rows — 26 token fields, batch 65536, embedding_size 10, CIN [100, 100, 100] (direct off), MLP
+    [128, 128, 128], first-order linear with its own `mean` embedder.  A step = token gather + OOV overwrite (bf16) +
+    first-order sum + CIN + MLP for one batch.  Reported under `workloads.xdeepfm_criteo` as rows/s (N = 1 only)."""
+    import torch
+    import oov_b200
+    from oov_b200 import ops
+    wl = XDEEPFM_WL
+    Bn, fields, D = wl["rows"], wl["fields"], wl["D"]
+
+    class Config(dict):
+        def __getitem__(self, key):
+            return dict.get(self, key, None)
+
+    class Dataset:
+        def __init__(self, uf, itf):
+            self._uf, self._if = uf, itf
+            self.user_num, self.item_num = wl["n_old_users"], wl["n_old_items"]
+
+        def num(self, f):
+            return {"user_id": self.user_num, "item_id": self.item_num}[f]
+
+        def get_user_feature(self):
+            return self._uf
+
+        def get_item_feature(self):
+            return self._if
+
+    cfg = Config(USER_ID_FIELD="user_id", ITEM_ID_FIELD="item_id", device=device, embedding_size=D, add_oov_buckets=True,
+                 inductive_embedder="mean", user_oov_buckets=10, item_oov_buckets=10, mlp_hidden_size=wl["mlp"],
+                 cin_layer_size=wl["cin"], direct=False, dropout_prob=0.2)
+    uf = oov_b200.Interaction({"user_id": torch.arange(wl["n_users"]), "f0": torch.ones(wl["n_users"], 1)})
+    itf = oov_b200.Interaction({"item_id": torch.arange(wl["n_items"]), "f0": torch.ones(wl["n_items"], 1)})
+    ds = Dataset(uf, itf)
+    emb = oov_b200.get_inductive_embedder(cfg, ds, mode="bench-xdeepfm")
+    emb1 = oov_b200.get_inductive_embedder(cfg, ds, mode="bench-xdeepfm", embedding_size=1, first_order=True)
+    dims = [wl["n_old_users"], wl["n_old_items"]] + [wl["other_vocab"]] * (fields - 2)
+    torch.manual_seed(2022)
+    model = oov_b200.xDeepFM(cfg, dims, inductive_embedder=emb, first_order_embedder=emb1).to(device).eval()
+    with torch.no_grad():                      # embeddings of O(0.3) keep the three chained Hadamard layers in bf16 range
+        model.token_embedding_table.embedding.weight.mul_(0.3 / model.token_embedding_table.embedding.weight.std())
+    model.pack_tower()
+    n_batches = 4
+    host = []
+    for b in range(n_batches):
+        gb = torch.Generator(device="cpu").manual_seed(400 + b)
+        t = torch.stack([torch.randint(0, wl["n_users"], (Bn,), generator=gb), torch.randint(0, wl["n_items"], (Bn,), generator=gb)] +
+                        [torch.randint(0, wl["other_vocab"], (Bn,), generator=gb) for _ in range(fields - 2)], dim=1)
+        host.append(t.pin_memory())
+    dev = [t.to(device) for t in host]
+    out_host = torch.empty((Bn,), dtype=torch.float32).pin_memory()
+    class Predict(torch.nn.Module):            # the graph replays `predict` (sigmoid of the logits), like the evaluator calls it
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, tok):
+            return self.m.predict(tok)
+
+    pred = Predict(model)
+    gstep = None if args.eager else oov_b200.GraphedRanker(pred, Bn, fields)
+
+    def step_resident(b):
+        return (gstep or pred)(dev[b % n_batches])
+
+    def step_e2e(b):
+        if gstep is not None:
+            out = gstep(host[b % n_batches])
+        else:
+            out = pred(host[b % n_batches].to(device, non_blocking=True))
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for b in range(steps):
+            fn(b)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    sampler = ClockSampler(int(str(device).split(":")[-1]))
+    sampler.start()
+    for b in range(max(args.warmup, 3)):
+        step_resident(b)
+        step_e2e(b)
+    l0 = ops.launch_count()
+    t0 = time.time()
+    ms = timed(step_resident, args.steps)
+    t1 = time.time()
+    launches = ops.launch_count() - l0 if gstep is None else gstep.launches_per_replay * args.steps
+    clocks = sampler.window(t0, t1)
+    ms_e2e = timed(step_e2e, args.steps)
+    sampler.stop()
+
+    def ev_time(fn, reps=5):
+        for _ in range(2):
+            fn()
+        return timed(lambda b: fn(), reps) / reps
+
+    x0 = model.embed_token_fields(dev[0], out_dtype=torch.bfloat16)
+    stages = {"token_gather_oov_ms": ev_time(lambda: model.embed_token_fields(dev[0], out_dtype=torch.bfloat16)),
+              "first_order_ms": ev_time(lambda: model.first_order_linear(dev[0])),
+              "cin_ms": ev_time(lambda: model.compressed_interaction_network(x0)),
+              "mlp_ms": ev_time(lambda: model.deep(x0.reshape(Bn, -1)))}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+    hs = [fields] + [c // 2 for c in wl["cin"][:-1]]
+    flops = 2.0 * Bn * D * sum(h * fields * c for h, c in zip(hs, wl["cin"]))
+    zbytes = 2.0 * Bn * D * sum(2 * ((h * fields + 7) // 8 * 8) for h in hs)          # z written once and read once, bf16
+    ach = flops / (stages["cin_ms"] * 1e-3) / 1e12
+    roofline = {"kernel": "xDeepFM CIN: 3 x (cin_outer + tc_linear<ReLU> + cin_pool_dot), 8 chunks of 8192 rows", "bound": "tensor",
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "launch_ms": stages["cin_ms"], "flops_per_launch": flops,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops" if peaks else "fallback 1590",
+                "note": "algorithmic flops 2 B D sum_k H_{k-1} M H_k over the time of the whole CIN; the outer-product operand z "
+                        f"({zbytes / 1e9:.1f} GB written + read per batch) goes through HBM: the CIN is bound by that traffic, not by the "
+                        "tensor pipe — generating z tiles in shared memory inside the GEMM is the next step (DESIGN 4.8)"}
+    res = {"metric": "xdeepfm_eval_rows_per_s", "value": Bn * args.steps / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms / args.steps,
+           "e2e": {"value": Bn * args.steps / (ms_e2e * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": Bn * fields * 8,
+                   "d2h_bytes_per_step": Bn * 4, "ms_per_step": ms_e2e / args.steps},
+           "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None, "stages": stages,
+           "config": {"workload": "xdeepfm_criteo", "model": "xDeepFM (direct off, eval)", "embedder": "mean (+ first-order mean)", "rows_per_step": Bn,
+                      "token_fields": fields, "embedding_size": D, "cin_layer_size": wl["cin"], "mlp_hidden_size": wl["mlp"],
+                      "l2": "z operands 0.2 - 0.4 GB per chunk + 4 rotating batches; no explicit flush",
+                      "launch": "eager" if gstep is None else "whole forward replayed from one CUDA graph (GraphedRanker)",
+                      "parallelism": "single GPU (replicas only: no exchange step)"},
+           "clocks": clocks, "steps": args.steps, "warmup": max(args.warmup, 3)}
+    gstep = None
+    del model, emb, emb1, dev
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -777,6 +924,7 @@ def main():
     results = [run_gpu(args, n, workload(n), rank, world, local_rank, with_cpu_baseline=(world == 1 and not args.no_cpu_baseline))
                for n in names]
     dcn = run_dcnv2(args, f"cuda:{local_rank}") if (world == 1 and args.dcnv2 and not args.single) else None
+    xdf = run_xdeepfm(args, f"cuda:{local_rank}") if (world == 1 and args.dcnv2 and not args.single) else None
     if rank == 0:
         line = results[0]
         if len(results) > 1:
@@ -785,6 +933,8 @@ def main():
                                  for n, r in zip(names[1:], results[1:])})
         if dcn is not None:
             line.setdefault("workloads", {})["dcnv2_criteo"] = dcn
+        if xdf is not None:
+            line.setdefault("workloads", {})["xdeepfm_criteo"] = xdf
         print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:

@@ -91,6 +91,9 @@ SIGNATURES = {
     "oov_act": (c_i32, [c_vp, c_vp, c_i32, c_i64, c_i32, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "oov_cin_outer": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_i64, c_i64, c_i64, c_i32, c_i64, c_i32, c_vp, c_i64, c_vp]),
     "oov_cin_pool_dot": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i64, c_i32, c_vp, c_f32, c_i32, c_vp, c_vp]),
+    "oov_cin_layer_supported": (c_i32, [c_i32, c_i32, c_i32, c_i32, c_i64]),
+    "oov_cin_layer": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_i64, c_i64, c_i64, c_i32, c_i64, c_i32, c_vp, c_i64, c_vp, c_i32,
+                              c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "oov_pair_topk": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i64, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp]),
 }
 

@@ -21,6 +21,13 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ReLU that keeps NaN (torch.relu(nan) = nan; fmaxf would return 0): max.NaN propagates
+__device__ __forceinline__ float relu_nan(float v) {
+    float r;
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(v));
+    return r;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -134,7 +134,7 @@ __device__ __forceinline__ uint32_t gelu_pair_bf16(uint64_t acc, uint64_t bias) 
 template <int ACT> __device__ __forceinline__ float act_apply(float v) {
     if (ACT == ACT_GELU) return gelu_fast(v);
     if (ACT == ACT_SIGMOID) return 1.f / (1.f + expf(-v));
-    if (ACT == ACT_RELU) return fmaxf(v, 0.f);
+    if (ACT == ACT_RELU) return relu_nan(v);          // NaN rows (e.g. all-zero LSH hashes) stay NaN like torch's ReLU
     return v;
 }
 

@@ -381,7 +381,14 @@ class xDeepFM(InductiveContextRecommender):
     Same parameter names as the reference (`conv1d_list.{k}.*`, `mlp_layers.mlp_layers.*`, `cin_linear.*`,
     `first_order_linear.*`).  Token fields only; eval mode."""
 
-    CIN_CHUNK = 8192          # batch rows per pass through the CIN (z: 8192 * D * H*M * 2 bytes)
+    CIN_CHUNK = 8192          # batch rows per pass through the unfused CIN (z: 8192 * D * H*M * 2 bytes)
+    fused_cin = True          # one kernel per CIN layer when the shapes allow (False: outer product + linear + pooling launches)
+
+    def _cin_fusable(self, M: int) -> bool:
+        hs = [M] + self.field_nums[1:-1]
+        n_hid = [(s if self.direct else s // 2) for s in self.cin_layer_size[:-1]] + [0]
+        return all(ops.cin_layer_supported(h, M, (s + 7) // 8 * 8, nh, (nh + 7) // 8 * 8)
+                   for h, s, nh in zip(hs, self.cin_layer_size, n_hid))
 
     def __init__(self, config, field_dims: Sequence[int], inductive_mapper=None, inductive_embedder=None,
                  first_order_embedder=None, first_order_mapper=None):
@@ -443,8 +450,25 @@ class xDeepFM(InductiveContextRecommender):
         """[B, fields, D] bf16 -> [B] fp32 = cin_linear(CIN(emb)) (xdeepfm.py:134-190, 198; activation ReLU)."""
         pk = self._packed or self.pack_tower()
         B, M, D = emb.shape
-        out = torch.empty((B,), dtype=torch.float32, device=emb.device)
         last = len(self.cin_layer_size) - 1
+        if self.fused_cin and self._cin_fusable(M):
+            # one tcgen05 kernel per layer: the outer-product operand never leaves the SM (oov_cin_layer)
+            out = torch.full((B,), pk["lin_b"], dtype=torch.float32, device=emb.device)
+            hidden, off = emb, 0
+            for i, ((w, b), size) in enumerate(zip(pk["cin"], self.cin_layer_size)):
+                if self.direct:
+                    n_hid, lo, n = size, 0, size
+                elif i != last:
+                    n_hid, lo, n = size // 2, size // 2, size // 2
+                else:
+                    n_hid, lo, n = 0, 0, size
+                if i == last:
+                    n_hid = 0                                         # nothing reads the last layer's hidden part
+                hid = ops.cin_layer(hidden, emb, D, i == 0, w, b, n_hid, lo, n, pk["lin_w"][off: off + n], out)
+                hidden = hid[:, :n_hid] if hid is not None else None
+                off += n
+            return out
+        out = torch.empty((B,), dtype=torch.float32, device=emb.device)
         for r0 in range(0, B, self.CIN_CHUNK):
             x0 = emb[r0: r0 + self.CIN_CHUNK]
             bc = x0.shape[0]

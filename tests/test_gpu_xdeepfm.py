@@ -108,3 +108,34 @@ def test_cin_outer_exact_products_and_padding():
     assert torch.allclose(acc, want_acc, rtol=1e-5, atol=1e-5)
     acc2 = ops.cin_pool_dot(y, 3, 5, B, D, w, 0.0, acc.clone(), accumulate=True)
     assert torch.allclose(acc2, 2 * want_acc - 0.5, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("Bn", [200, 3001, 40000])
+def test_fused_cin_layer_kernel_equals_the_three_launch_path(Bn):
+    """`oov_cin_layer` (outer-product operand generated in shared memory inside the tcgen05 GEMM, pooled epilogue) against
+    `oov_cin_outer` + `oov_tc_linear` + `oov_cin_pool_dot`: same rounding points, so the logits agree to fp32
+    accumulation order; also pinned to the reference golden through the head test above (the model default is fused)."""
+    g = np.load(GOLD)
+    c = _xdeepfm_case(g, "default")
+    m = _model(c, [100, 100, 100])
+    fields, D = c["emb"].shape[1], c["emb"].shape[2]
+    assert m._cin_fusable(fields)
+    gen = torch.Generator().manual_seed(Bn)
+    x16 = (torch.randn(Bn, fields, D, generator=gen) * 0.5).to(DEV).to(torch.bfloat16)
+    m.fused_cin = True
+    from oov_b200 import ops
+    l0 = ops.launch_count()
+    fused = m.compressed_interaction_network(x16)
+    n_fused = ops.launch_count() - l0
+    m.fused_cin = False
+    unfused = m.compressed_interaction_network(x16)
+    assert n_fused == 3                                               # one kernel per CIN layer
+    scale = float(unfused.abs().max())
+    err = float((fused - unfused).abs().max())
+    print(f"[fused CIN B={Bn}] max |fused - unfused| = {err:.3e} (scale {scale:.2f})")
+    assert err <= 2e-5 * max(scale, 1.0)
+    # NaN embeddings stay confined to their own batch row
+    x16[7, 3, 2] = float("nan")
+    m.fused_cin = True
+    out = m.compressed_interaction_network(x16)
+    assert bool(torch.isnan(out[7])) and int(torch.isnan(out).sum()) == 1
