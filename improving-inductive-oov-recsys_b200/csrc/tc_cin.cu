@@ -27,19 +27,21 @@ namespace oov {
 namespace tc {
 
 constexpr int C_BM = 128, C_BN = 128, C_BK = 64;
-constexpr int C_STAGES = 4;
-constexpr int C_A_BYTES = C_BM * C_BK * 2, C_B_BYTES = C_BN * C_BK * 2, C_STAGE_BYTES = C_A_BYTES + C_B_BYTES;
+constexpr int C_ASTAGES = 3, C_BSTAGES = 6;                  // separate rings: generated z tiles / W tiles (TMA latency needs the depth)
+constexpr int C_A_BYTES = C_BM * C_BK * 2, C_B_BYTES = C_BN * C_BK * 2;
+constexpr int C_RING_BYTES = C_ASTAGES * C_A_BYTES + C_BSTAGES * C_B_BYTES;
 constexpr int C_MMAX = 64, C_HMAX = 64;                       // fields / hidden channels of the previous layer
 constexpr int C_GEN_WARPS = 8, C_EPI_WARP0 = 8, C_W_TMA = 12, C_W_MMA = 13, C_W_ALLOC = 14;
 constexpr int C_THREADS = 15 * 32;
 constexpr int C_X0_BYTES = 2 * (C_MMAX / 2) * C_BM * 4;       // [2][M / 2][128] bf16 pairs
-constexpr int C_XI_BYTES = 2 * C_HMAX * C_BM * 2;             // [2][H][128] bf16
-constexpr int C_SMEM = 1024 + C_STAGES * C_STAGE_BYTES + C_X0_BYTES + C_XI_BYTES + 2 * C_BN * 4 + 256;
+constexpr int C_XROWS = C_HMAX + 32;                          // h of a padding channel reaches H + 62 / M <= H + 31 (rows >= H are zeros)
+constexpr int C_XI_BYTES = 2 * C_XROWS * C_BM * 2;            // [2][C_XROWS][128] bf16
+constexpr int C_SMEM = 1024 + C_RING_BYTES + C_X0_BYTES + C_XI_BYTES + 2 * C_BN * 4 + 256;
 static_assert(C_SMEM <= 232448, "tc_cin shared memory");
 
 struct CinParams {
-    const __nv_bfloat16* x0; int64_t x0_sb, x0_sd, x0_sc; int M;       // element (b, d, m) at x0[b*sb + d*sd + m*sc]
-    const __nv_bfloat16* xi; int64_t xi_sb, xi_sd, xi_sc; int H;
+    const __nv_bfloat16* x0; int64_t x0_sd; int M;                     // row r = (b, d) of X^0 at x0 + r * x0_sd, M channels (d-major)
+    const __nv_bfloat16* xi; int64_t xi_sd; int H;                     // row r of X^{k-1} at xi + r * xi_sd, H channels
     int64_t B; int D; int64_t R;                                       // R = B * D rows
     int k_blocks; int O;                                               // ceil(H*M / 64); output channels (<= 128)
     const float* bias;                                                 // [O]
@@ -51,19 +53,36 @@ __device__ __forceinline__ uint32_t bf16x2_mul(uint32_t a, uint32_t b) {
     __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
     return *reinterpret_cast<uint32_t*>(&r);
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void gen_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __global__ void __launch_bounds__(C_THREADS, 1)
 tc_cin_layer_kernel(const __grid_constant__ CUtensorMap tmW, const CinParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint32_t* x0s = reinterpret_cast<uint32_t*>(smem + C_STAGES * C_STAGE_BYTES);              // [2][32][128]
-    uint16_t* xis = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(x0s) + C_X0_BYTES);   // [2][64][128]
+    unsigned char* sA = smem;                                                                   // C_ASTAGES x 16 KB
+    unsigned char* sB = smem + C_ASTAGES * C_A_BYTES;                                           // C_BSTAGES x 16 KB
+    uint32_t* x0s = reinterpret_cast<uint32_t*>(smem + C_RING_BYTES);                           // [2][32][128]
+    uint16_t* xis = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(x0s) + C_X0_BYTES);   // [2][96][128]
     float* bias_s = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(xis) + C_XI_BYTES);      // [128]
     float* poolw_s = bias_s + C_BN;                                                            // [128] by output column
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(poolw_s + C_BN);
-    uint64_t* empty_bar = full_bar + C_STAGES;
-    uint64_t* tmem_full = empty_bar + C_STAGES;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(poolw_s + C_BN);
+    uint64_t* a_empty = a_full + C_ASTAGES;
+    uint64_t* b_full = a_empty + C_ASTAGES;
+    uint64_t* b_empty = b_full + C_BSTAGES;
+    uint64_t* tmem_full = b_empty + C_BSTAGES;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -73,11 +92,13 @@ tc_cin_layer_kernel(const __grid_constant__ CUtensorMap tmW, const CinParams p) 
 
     if (warp == C_W_TMA && lane == 0) tma_prefetch_desc(&tmW);
     if (warp == C_W_MMA && lane == 0) {
-        for (int s = 0; s < C_STAGES; ++s) { mbar_init(&full_bar[s], 1 + C_GEN_WARPS / 2); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < C_ASTAGES; ++s) { mbar_init(&a_full[s], C_GEN_WARPS / 2); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < C_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
         fence_barrier_init();
     }
     if (warp == C_W_ALLOC) tmem_alloc(tmem_slot, 2 * C_BN);
+    for (int i = threadIdx.x; i < C_XI_BYTES / 4; i += C_THREADS) reinterpret_cast<uint32_t*>(xis)[i] = 0u;   // rows >= H stay zero
     for (int i = threadIdx.x; i < C_BN; i += C_THREADS) {
         bias_s[i] = i < p.O ? __ldg(p.bias + i) : 0.f;
         const int c = i - p.pool_lo;
@@ -92,31 +113,26 @@ tc_cin_layer_kernel(const __grid_constant__ CUtensorMap tmW, const CinParams p) 
         // ===================== generators =====================
         const int row = threadIdx.x & (C_BM - 1), half = warp >> 2;     // this thread: tile row, k-blocks kb = half (mod 2)
         const int M = p.M, H = p.H, M2 = M >> 1;
+        const uint32_t inv_m = ((1u << 20) + (uint32_t)M - 1u) / (uint32_t)M;
         constexpr int NX = C_MMAX / 4, NH = C_HMAX / 2;                 // values of a tile this thread fetches: pairs m2 = half + 2 i, h = half + 2 j
         uint32_t px[NX];
-        uint16_t ph[NH];
+        // both operands are read with unit channel stride (rows of [R, ld] matrices, ld even): bf16 pairs as 32-bit loads, and
+        // nothing touches the loaded registers before store_tile — the loads stay in flight for a whole tile
+        uint32_t pw[NH / 2];
         auto load_tile = [&](int64_t tile) {
             const int64_t r = tile * C_BM + row;
             const bool ok = r < p.R;
-            const int64_t b = ok ? r / p.D : 0;
-            const int d = ok ? (int)(r - b * p.D) : 0;
-            const __nv_bfloat16* q0 = p.x0 + b * p.x0_sb + d * p.x0_sd;
-            const __nv_bfloat16* qi = p.xi + b * p.xi_sb + d * p.xi_sd;
+            const uint32_t* q0 = reinterpret_cast<const uint32_t*>(p.x0 + (ok ? r : 0) * p.x0_sd);
+            const uint32_t* qi = reinterpret_cast<const uint32_t*>(p.xi + (ok ? r : 0) * p.xi_sd);
 #pragma unroll
             for (int i = 0; i < NX; ++i) {
                 const int m2 = half + 2 * i;
-                uint32_t v = 0u;
-                if (ok && m2 < M2) {
-                    const uint32_t lo = *reinterpret_cast<const uint16_t*>(q0 + (int64_t)(2 * m2) * p.x0_sc);
-                    const uint32_t hi = *reinterpret_cast<const uint16_t*>(q0 + (int64_t)(2 * m2 + 1) * p.x0_sc);
-                    v = lo | (hi << 16);
-                }
-                px[i] = v;
+                px[i] = (ok && m2 < M2) ? __ldg(q0 + m2) : 0u;
             }
 #pragma unroll
-            for (int j = 0; j < NH; ++j) {
-                const int h = half + 2 * j;
-                ph[j] = (ok && h < H) ? *reinterpret_cast<const uint16_t*>(qi + (int64_t)h * p.xi_sc) : (uint16_t)0;
+            for (int j = 0; j < NH / 2; ++j) {
+                const int h2 = half + 2 * j;                            // channels 2 h2, 2 h2 + 1
+                pw[j] = (ok && 2 * h2 < H) ? __ldg(qi + h2) : 0u;
             }
         };
         auto store_tile = [&](int buf) {
@@ -126,9 +142,11 @@ tc_cin_layer_kernel(const __grid_constant__ CUtensorMap tmW, const CinParams p) 
                 if (m2 < M2) x0s[(buf * (C_MMAX / 2) + m2) * C_BM + row] = px[i];
             }
 #pragma unroll
-            for (int j = 0; j < NH; ++j) {
-                const int h = half + 2 * j;
-                if (h < H) xis[(buf * C_HMAX + h) * C_BM + row] = ph[j];
+            for (int j = 0; j < NH / 2; ++j) {
+                const int h2 = half + 2 * j;
+                const uint32_t v = pw[j];
+                xis[(buf * C_XROWS + 2 * h2) * C_BM + row] = (uint16_t)(v & 0xffffu);
+                xis[(buf * C_XROWS + 2 * h2 + 1) * C_BM + row] = (2 * h2 + 1 < H) ? (uint16_t)(v >> 16) : (uint16_t)0;   // rows >= H are zeros
             }
         };
         int64_t t = blockIdx.x;
@@ -139,36 +157,50 @@ tc_cin_layer_kernel(const __grid_constant__ CUtensorMap tmW, const CinParams p) 
             store_tile(buf);
             gen_bar();                                                  // the tile's rows are in shared memory (and buffer buf ^ 1 is free)
             if (t + gridDim.x < n_tiles) load_tile(t + gridDim.x);      // in flight while this tile is generated
-            const uint32_t* x0b = x0s + buf * (C_MMAX / 2) * C_BM + row;
-            const uint16_t* xib = xis + buf * C_HMAX * C_BM + row;
+            // 32-bit shared addresses of this thread's column of the two row buffers: x0 pair of fields (m, m + 1) at
+            // x0a + (m << 8), X^{k-1} channel h at xia + (h << 8)
+            const uint32_t x0a = smem_u32(x0s + buf * (C_MMAX / 2) * C_BM + row);
+            const uint32_t xia = smem_u32(xis + buf * C_XROWS * C_BM + row);
             const uint32_t sw = (uint32_t)(row & 7);
+            const uint32_t negM256 = 0u - ((uint32_t)M << 8);
             for (int kb = half; kb < KB; kb += 2) {
                 const uint32_t s = s_cnt + (uint32_t)kb;
-                const int stage = (int)(s % C_STAGES);
-                const uint32_t phase = (s / C_STAGES) & 1u;
-                mbar_wait_relaxed(&empty_bar[stage], phase ^ 1u);       // the MMAs that read this stage have retired
-                unsigned char* arow = smem + stage * C_STAGE_BYTES + row * 128;
-                int h = (kb * C_BK) / M, m = kb * C_BK - h * M;         // channel kb*64 = h*M + m (M even: a pair never straddles h)
-                uint32_t a2 = 0u;
-                if (h < H) { const uint32_t a = xib[h * C_BM]; a2 = a | (a << 16); }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    uint32_t w[4];
+                const int stage = (int)(s % C_ASTAGES);
+                const uint32_t phase = (s / C_ASTAGES) & 1u;
+                mbar_wait(&a_empty[stage], phase ^ 1u);                 // the MMAs that read this stage have retired
+                const uint32_t arow = smem_u32(sA + stage * C_A_BYTES + row * 128);
+                // channel c = kb*64 + 2*pair = h*M + m (M even: a pair never straddles h).  Every pair computes its own (h, m)
+                // with a multiply-shift division (c < 4160, M <= 64: exact with a 2^20 reciprocal), so the 32 pairs of a stage are
+                // independent instruction streams — a running (h, m) with a wrap branch per pair made the two generator warps
+                // of a scheduler latency-bound (~100 cycles per pair, tensor pipe 13 % busy).  Eight instructions per pair:
+                // IMAD + SHR (h), IMAD (x0 address), LDS, LEA, LDS.U16, IMAD (broadcast), HMUL2.BF16; the loads of chunk
+                // j + 1 are issued before the multiplies of chunk j.  Channels >= H*M multiply zero columns of W (and rows
+                // >= H of the buffer are zeros).
+                const uint32_t c0 = (uint32_t)(kb * C_BK);
+                const uint32_t c0inv = c0 * inv_m;
+                const uint32_t x0c = x0a + (c0 << 8);
+                uint32_t av[2][4], xv[2][4];
+                auto loads = [&](int j, uint32_t (&a)[4], uint32_t (&x)[4]) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        w[q] = bf16x2_mul(a2, x0b[(m >> 1) * C_BM]);
-                        m += 2;
-                        if (m == M) {
-                            m = 0; ++h;
-                            a2 = 0u;
-                            if (h < H) { const uint32_t a = xib[h * C_BM]; a2 = a | (a << 16); }
-                        }
+                        const uint32_t k = (uint32_t)(8 * j + 2 * q);
+                        const uint32_t h = (k * inv_m + c0inv) >> 20;
+                        x[q] = lds_u32(h * negM256 + x0c + (k << 8));          // (c - h M) << 8
+                        a[q] = lds_u16(xia + (h << 8));
                     }
-                    *reinterpret_cast<uint4*>(arow + (((uint32_t)j ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                };
+                loads(0, av[0], xv[0]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j + 1 < 8) loads(j + 1, av[(j + 1) & 1], xv[(j + 1) & 1]);
+                    uint32_t w[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) w[q] = bf16x2_mul(av[j & 1][q] * 0x10001u, xv[j & 1][q]);
+                    sts_v4(arow + (((uint32_t)j ^ sw) << 4), w[0], w[1], w[2], w[3]);
                 }
                 fence_proxy_async_smem();                               // generic-proxy stores -> visible to the tensor core's reads
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full_bar[stage]);
+                if (lane == 0) mbar_arrive(&a_full[stage]);
             }
         }
     } else if (warp == C_W_TMA) {
@@ -177,11 +209,11 @@ tc_cin_layer_kernel(const __grid_constant__ CUtensorMap tmW, const CinParams p) 
         uint32_t s = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             for (int kb = 0; kb < KB; ++kb, ++s) {
-                const int stage = (int)(s % C_STAGES);
-                mbar_wait_relaxed(&empty_bar[stage], ((s / C_STAGES) & 1u) ^ 1u);
+                const int stage = (int)(s % C_BSTAGES);
+                mbar_wait_relaxed(&b_empty[stage], ((s / C_BSTAGES) & 1u) ^ 1u);
                 if (issue) {
-                    mbar_arrive_expect_tx(&full_bar[stage], C_B_BYTES);
-                    tma_load_2d(smem + stage * C_STAGE_BYTES + C_A_BYTES, &tmW, &full_bar[stage], kb * C_BK, 0);
+                    mbar_arrive_expect_tx(&b_full[stage], C_B_BYTES);
+                    tma_load_2d(sB + stage * C_B_BYTES, &tmW, &b_full[stage], kb * C_BK, 0);
                 }
                 __syncwarp();
             }
@@ -197,16 +229,17 @@ tc_cin_layer_kernel(const __grid_constant__ CUtensorMap tmW, const CinParams p) 
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C_BN);
             for (int kb = 0; kb < KB; ++kb, ++s) {
-                const int stage = (int)(s % C_STAGES);
-                mbar_wait(&full_bar[stage], (s / C_STAGES) & 1u);       // W bytes landed and all four generator warps arrived
+                const int sa_i = (int)(s % C_ASTAGES), sb_i = (int)(s % C_BSTAGES);
+                mbar_wait(&b_full[sb_i], (s / C_BSTAGES) & 1u);         // W bytes landed
+                mbar_wait(&a_full[sa_i], (s / C_ASTAGES) & 1u);         // all four generator warps of this k-block arrived
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * C_STAGE_BYTES);
-                const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + C_A_BYTES);
+                const uint64_t adesc = make_sw128_desc(smem_u32(sA + sa_i * C_A_BYTES)), bdesc = make_sw128_desc(smem_u32(sB + sb_i * C_B_BYTES));
                 if (issue) {
 #pragma unroll
                     for (int k = 0; k < C_BK / 16; ++k)
                         tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-                    tc_commit(&empty_bar[stage]);
+                    tc_commit(&a_empty[sa_i]);
+                    tc_commit(&b_empty[sb_i]);
                     if (kb == KB - 1) tc_commit(&tmem_full[acc]);
                 }
                 __syncwarp();
@@ -285,8 +318,7 @@ int oov_cin_layer_supported(int32_t H, int32_t M, int32_t O, int32_t n_hidden, i
     return tc::cin_tc_supported(H, M, O, n_hidden, ld_h) ? 1 : 0;
 }
 
-int oov_cin_layer(const void* xi, int64_t xi_sb, int64_t xi_sd, int64_t xi_sc, int32_t H,
-                  const void* x0, int64_t x0_sb, int64_t x0_sd, int64_t x0_sc, int32_t M,
+int oov_cin_layer(const void* xi, int64_t ld_xi, int32_t H, const void* x0, int64_t ld_x0, int32_t M,
                   int64_t B, int32_t D, const void* W, int64_t ldw, const float* bias, int32_t O,
                   void* hid_out, int64_t ld_h, int32_t n_hidden,
                   int32_t pool_lo, int32_t pool_n, const float* pool_w, float* out_acc, void* stream) {
@@ -299,8 +331,10 @@ int oov_cin_layer(const void* xi, int64_t xi_sb, int64_t xi_sd, int64_t xi_sc, i
     OOV_REQUIRE(xi && x0 && W && bias && (n_hidden == 0 || hid_out) && (pool_n == 0 || (pool_w && out_acc)), OOV_ERR_ARG, "oov_cin_layer: NULL pointer");
     OOV_REQUIRE(n_hidden == 0 || (aligned(hid_out, 4) && ld_h >= n_hidden), OOV_ERR_ALIGN, "oov_cin_layer: hid_out must be 4-byte aligned with ld_h >= n_hidden");
     tc::CinParams p{};
-    p.x0 = reinterpret_cast<const __nv_bfloat16*>(x0); p.x0_sb = x0_sb; p.x0_sd = x0_sd; p.x0_sc = x0_sc; p.M = M;
-    p.xi = reinterpret_cast<const __nv_bfloat16*>(xi); p.xi_sb = xi_sb; p.xi_sd = xi_sd; p.xi_sc = xi_sc; p.H = H;
+    OOV_REQUIRE(aligned(xi, 4) && aligned(x0, 4) && ld_xi % 2 == 0 && ld_x0 % 2 == 0 && ld_xi >= H && ld_x0 >= M, OOV_ERR_ALIGN,
+                "oov_cin_layer: xi / x0 must be 4-byte aligned [B*D, ld] matrices with even ld >= H / M");
+    p.x0 = reinterpret_cast<const __nv_bfloat16*>(x0); p.x0_sd = ld_x0; p.M = M;
+    p.xi = reinterpret_cast<const __nv_bfloat16*>(xi); p.xi_sd = ld_xi; p.H = H;
     p.B = B; p.D = D; p.R = B * (int64_t)D;
     p.k_blocks = (int)cdiv((int64_t)H * M, tc::C_BK); p.O = O; p.bias = bias;
     p.hid_out = n_hidden ? reinterpret_cast<__nv_bfloat16*>(hid_out) : nullptr; p.ld_h = ld_h; p.n_hidden = n_hidden;

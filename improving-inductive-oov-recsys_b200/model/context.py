@@ -454,7 +454,8 @@ class xDeepFM(InductiveContextRecommender):
         if self.fused_cin and self._cin_fusable(M):
             # one tcgen05 kernel per layer: the outer-product operand never leaves the SM (oov_cin_layer)
             out = torch.full((B,), pk["lin_b"], dtype=torch.float32, device=emb.device)
-            hidden, off = emb, 0
+            x0t = emb.transpose(1, 2).contiguous().view(B * D, M)       # rows (b, d), fields along the row (34 MB at 65536 x 26 x 10)
+            hidden, off = x0t, 0
             for i, ((w, b), size) in enumerate(zip(pk["cin"], self.cin_layer_size)):
                 if self.direct:
                     n_hid, lo, n = size, 0, size
@@ -464,7 +465,7 @@ class xDeepFM(InductiveContextRecommender):
                     n_hid, lo, n = 0, 0, size
                 if i == last:
                     n_hid = 0                                         # nothing reads the last layer's hidden part
-                hid = ops.cin_layer(hidden, emb, D, i == 0, w, b, n_hid, lo, n, pk["lin_w"][off: off + n], out)
+                hid = ops.cin_layer(hidden, x0t, B, D, w, b, n_hid, lo, n, pk["lin_w"][off: off + n], out)
                 hidden = hid[:, :n_hid] if hid is not None else None
                 off += n
             return out

@@ -694,32 +694,25 @@ def cin_layer_supported(H: int, M: int, O: int, n_hidden: int, ld_h: int) -> boo
     return bool(_lib.load().oov_cin_layer_supported(int(H), int(M), int(O), int(n_hidden), int(ld_h)))
 
 
-def cin_layer(xi: torch.Tensor, x0: torch.Tensor, D: int, first: bool, W: torch.Tensor, bias: torch.Tensor, n_hidden: int,
+def cin_layer(xi: torch.Tensor, x0t: torch.Tensor, B: int, D: int, W: torch.Tensor, bias: torch.Tensor, n_hidden: int,
               pool_lo: int, pool_n: int, pool_w: torch.Tensor, out_acc: torch.Tensor) -> Optional[torch.Tensor]:
     """One CIN layer fused (oov_cin_layer): returns the hidden channels [B*D, ld_h] bf16 (first n_hidden columns valid;
-    None when n_hidden == 0) and ADDS the pooled direct-connect part into out_acc [B] fp32.  Operands like `cin_outer`."""
-    _cuda(x0, "x0", torch.bfloat16)
-    _cuda(xi, "xi", torch.bfloat16)
-    _cuda(W, "W", torch.bfloat16)
-    _cuda(bias, "bias", torch.float32)
-    _cuda(pool_w, "pool_w", torch.float32)
-    _cuda(out_acc, "out_acc", torch.float32)
-    if x0.dim() != 3 or x0.shape[2] != D or not x0.is_contiguous():
-        raise ValueError("x0 must be contiguous [B, M, D]")
-    B, M = x0.shape[0], x0.shape[1]
-    if first:
-        H, vi = M, (M * D, 1, D)
-    else:
-        if xi.dim() != 2 or xi.shape[0] != B * D or xi.stride(1) != 1:
-            raise ValueError("xi must be [B*D, H] with unit inner stride")
-        H, vi = xi.shape[1], (D * xi.stride(0), xi.stride(0), 1)
-    O = W.shape[0]
+    None when n_hidden == 0) and ADDS the pooled direct-connect part into out_acc [B] fp32.
+    x0t [B*D, M]: the embeddings with rows (b, d) and the fields along the row; xi [B*D, H] (unit inner stride): the
+    previous layer's hidden channels (x0t itself for the first layer)."""
+    for t, nm in ((x0t, "x0t"), (xi, "xi"), (W, "W")):
+        _cuda(t, nm, torch.bfloat16)
+    for t, nm in ((bias, "bias"), (pool_w, "pool_w"), (out_acc, "out_acc")):
+        _cuda(t, nm, torch.float32)
+    if x0t.dim() != 2 or xi.dim() != 2 or x0t.shape[0] != B * D or xi.shape[0] != B * D or x0t.stride(1) != 1 or xi.stride(1) != 1:
+        raise ValueError("x0t / xi must be [B*D, channels] with unit inner stride")
+    M, H, O = x0t.shape[1], xi.shape[1], W.shape[0]
     if not W.is_contiguous() or W.shape[1] < H * M or bias.numel() != O or pool_w.numel() != pool_n or not pool_w.is_contiguous() \
             or out_acc.numel() != B or not out_acc.is_contiguous():
         raise ValueError("cin_layer: W [O, >= H*M] contiguous, bias [O], pool_w [pool_n], out_acc [B]")
     ld_h = (n_hidden + 7) // 8 * 8
-    hid = torch.empty((B * D, ld_h), dtype=torch.bfloat16, device=x0.device) if n_hidden else None
-    _lib.check(_lib.load().oov_cin_layer(_p(xi), vi[0], vi[1], vi[2], H, _p(x0), M * D, 1, D, M, B, D, _p(W), W.shape[1], _p(bias.contiguous()), O,
+    hid = torch.empty((B * D, ld_h), dtype=torch.bfloat16, device=x0t.device) if n_hidden else None
+    _lib.check(_lib.load().oov_cin_layer(_p(xi), xi.stride(0), H, _p(x0t), x0t.stride(0), M, B, D, _p(W), W.shape[1], _p(bias.contiguous()), O,
                                          _p(hid), ld_h, n_hidden, pool_lo, pool_n, _p(pool_w), _p(out_acc), _stream()))
     return hid
 

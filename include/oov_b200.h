@@ -373,12 +373,13 @@ int oov_cin_pool_dot(const void* y, int64_t ldy, int32_t col0, int32_t ncols, in
  *   hid_out[(b*D + d) * ld_h + c] = bf16(Y[., c]) for c < n_hidden   (the next layer's xi: sb = D*ld_h, sd = ld_h, sc = 1)
  *   out_acc[b] += sum_{d, c < pool_n} bf16(Y[(b, d), pool_lo + c]) * pool_w[c]     (fp32 atomics; initialise out_acc with
  *                                                                                   cin_linear's bias)
- * Same operand views and rounding points as oov_cin_outer + oov_tc_linear + oov_cin_pool_dot.
+ * xi [B*D, ld_xi] / x0 [B*D, ld_x0]: rows are (b, d) pairs, channels contiguous (the embeddings transposed to [B, D, M]
+ * once per forward; a previous layer's hid_out as it is), even ld, 4-byte aligned.
+ * Same rounding points as oov_cin_outer + oov_tc_linear + oov_cin_pool_dot.
  * Shapes: even M <= 64, H <= 64, O <= 128, even n_hidden / ld_h — oov_cin_layer_supported tells; other shapes take
  * the three-call path. */
 int oov_cin_layer_supported(int32_t H, int32_t M, int32_t O, int32_t n_hidden, int64_t ld_h);
-int oov_cin_layer(const void* xi, int64_t xi_sb, int64_t xi_sd, int64_t xi_sc, int32_t H,
-                  const void* x0, int64_t x0_sb, int64_t x0_sd, int64_t x0_sc, int32_t M,
+int oov_cin_layer(const void* xi, int64_t ld_xi, int32_t H, const void* x0, int64_t ld_x0, int32_t M,
                   int64_t B, int32_t D, const void* W, int64_t ldw, const float* bias, int32_t O,
                   void* hid_out, int64_t ld_h, int32_t n_hidden,
                   int32_t pool_lo, int32_t pool_n, const float* pool_w, float* out_acc, void* stream);
