@@ -92,7 +92,7 @@ SIGNATURES = {
     "oov_cin_outer": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_i64, c_i64, c_i64, c_i32, c_i64, c_i32, c_vp, c_i64, c_vp]),
     "oov_cin_pool_dot": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i64, c_i32, c_vp, c_f32, c_i32, c_vp, c_vp]),
     "oov_cin_layer_supported": (c_i32, [c_i32, c_i32, c_i32, c_i32, c_i64]),
-    "oov_cin_layer": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_i64, c_vp, c_i32,
+    "oov_cin_layer": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i32, c_i64, c_i32, c_vp, c_i64, c_vp, c_i32,
                               c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "oov_pair_topk": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i64, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp]),
 }

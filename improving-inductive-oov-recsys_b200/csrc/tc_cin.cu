@@ -19,6 +19,7 @@
 // Rounding points are those of the unfused path (z rounded once to bf16: the packed bf16 multiply rounds the exact
 // product; Y rounded to bf16 before pooling), so both give the same values up to fp32 accumulation order.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -27,7 +28,7 @@ namespace oov {
 namespace tc {
 
 constexpr int C_BM = 128, C_BN = 128, C_BK = 64;
-constexpr int C_ASTAGES = 3, C_BSTAGES = 6;                  // separate rings: generated z tiles / W tiles (TMA latency needs the depth)
+constexpr int C_ASTAGES = 4, C_BSTAGES = 5;                  // separate rings: generated z tiles / W tiles (TMA latency needs the depth)
 constexpr int C_A_BYTES = C_BM * C_BK * 2, C_B_BYTES = C_BN * C_BK * 2;
 constexpr int C_RING_BYTES = C_ASTAGES * C_A_BYTES + C_BSTAGES * C_B_BYTES;
 constexpr int C_MMAX = 64, C_HMAX = 64;                       // fields / hidden channels of the previous layer
@@ -43,10 +44,12 @@ struct CinParams {
     const __nv_bfloat16* x0; int64_t x0_sd; int M;                     // row r = (b, d) of X^0 at x0 + r * x0_sd, M channels (d-major)
     const __nv_bfloat16* xi; int64_t xi_sd; int H;                     // row r of X^{k-1} at xi + r * xi_sd, H channels
     int64_t B; int D; int64_t R;                                       // R = B * D rows
-    int k_blocks; int O;                                               // ceil(H*M / 64); output channels (<= 128)
+    int mp_shift;                                                      // z channel = (h << mp_shift) + m, 2^mp_shift >= max(M, 8)
+    int k_blocks; int O;                                               // ceil((H << mp_shift) / 64); output channels (<= 128)
     const float* bias;                                                 // [O]
     __nv_bfloat16* hid_out; int64_t ld_h; int n_hidden;                // Y[:, :n_hidden] (even; 0: none)
     int pool_lo, pool_n; const float* pool_w; float* out_acc;          // direct-connect columns and their cin_linear weights
+    int debug;                                                         // profiling only (OOV_CIN_DEBUG): 1 = generators only signal, 2 = W tile loaded once per stage slot
 };
 
 __device__ __forceinline__ uint32_t bf16x2_mul(uint32_t a, uint32_t b) {
@@ -98,7 +101,7 @@ tc_cin_layer_kernel(const __grid_constant__ CUtensorMap tmW, const CinParams p) 
         fence_barrier_init();
     }
     if (warp == C_W_ALLOC) tmem_alloc(tmem_slot, 2 * C_BN);
-    for (int i = threadIdx.x; i < C_XI_BYTES / 4; i += C_THREADS) reinterpret_cast<uint32_t*>(xis)[i] = 0u;   // rows >= H stay zero
+    for (int i = threadIdx.x; i < (C_X0_BYTES + C_XI_BYTES) / 4; i += C_THREADS) x0s[i] = 0u;   // fields >= M / channels >= H stay zero
     for (int i = threadIdx.x; i < C_BN; i += C_THREADS) {
         bias_s[i] = i < p.O ? __ldg(p.bias + i) : 0.f;
         const int c = i - p.pool_lo;
@@ -113,7 +116,7 @@ tc_cin_layer_kernel(const __grid_constant__ CUtensorMap tmW, const CinParams p) 
         // ===================== generators =====================
         const int row = threadIdx.x & (C_BM - 1), half = warp >> 2;     // this thread: tile row, k-blocks kb = half (mod 2)
         const int M = p.M, H = p.H, M2 = M >> 1;
-        const uint32_t inv_m = ((1u << 20) + (uint32_t)M - 1u) / (uint32_t)M;
+        const uint32_t mp_shift = (uint32_t)p.mp_shift, mp_mask = (1u << mp_shift) - 1u;
         constexpr int NX = C_MMAX / 4, NH = C_HMAX / 2;                 // values of a tile this thread fetches: pairs m2 = half + 2 i, h = half + 2 j
         uint32_t px[NX];
         // both operands are read with unit channel stride (rows of [R, ld] matrices, ld even): bf16 pairs as 32-bit loads, and
@@ -162,40 +165,35 @@ tc_cin_layer_kernel(const __grid_constant__ CUtensorMap tmW, const CinParams p) 
             const uint32_t x0a = smem_u32(x0s + buf * (C_MMAX / 2) * C_BM + row);
             const uint32_t xia = smem_u32(xis + buf * C_XROWS * C_BM + row);
             const uint32_t sw = (uint32_t)(row & 7);
-            const uint32_t negM256 = 0u - ((uint32_t)M << 8);
             for (int kb = half; kb < KB; kb += 2) {
                 const uint32_t s = s_cnt + (uint32_t)kb;
                 const int stage = (int)(s % C_ASTAGES);
                 const uint32_t phase = (s / C_ASTAGES) & 1u;
                 mbar_wait(&a_empty[stage], phase ^ 1u);                 // the MMAs that read this stage have retired
                 const uint32_t arow = smem_u32(sA + stage * C_A_BYTES + row * 128);
-                // channel c = kb*64 + 2*pair = h*M + m (M even: a pair never straddles h).  Every pair computes its own (h, m)
-                // with a multiply-shift division (c < 4160, M <= 64: exact with a 2^20 reciprocal), so the 32 pairs of a stage are
-                // independent instruction streams — a running (h, m) with a wrap branch per pair made the two generator warps
-                // of a scheduler latency-bound (~100 cycles per pair, tensor pipe 13 % busy).  Eight instructions per pair:
-                // IMAD + SHR (h), IMAD (x0 address), LDS, LEA, LDS.U16, IMAD (broadcast), HMUL2.BF16; the loads of chunk
-                // j + 1 are issued before the multiplies of chunk j.  Channels >= H*M multiply zero columns of W (and rows
-                // >= H of the buffer are zeros).
+                // z channel c = h * Mp + m with Mp = the field count rounded up to a power of two (>= 8): a 16-byte chunk (8
+                // channels) has ONE h, and h / m are a shift and a mask — per chunk one LDS.U16 + broadcast for X^{k-1}[h], per
+                // pair one LDS (immediate offset) + one packed bf16 multiply.  (With c = h*M + m every pair needed its own
+                // multiply-shift division and two loads: 8 instructions per pair, the generators were issue-bound at 30 % tensor
+                // pipe.)  Fields m >= M are zero rows of the buffer and zero columns of W; so are channels h >= H.
                 const uint32_t c0 = (uint32_t)(kb * C_BK);
-                const uint32_t c0inv = c0 * inv_m;
-                const uint32_t x0c = x0a + (c0 << 8);
-                uint32_t av[2][4], xv[2][4];
-                auto loads = [&](int j, uint32_t (&a)[4], uint32_t (&x)[4]) {
+                uint32_t av[2], xv[2][4];
+                auto loads = [&](int j, uint32_t& a, uint32_t (&x)[4]) {
+                    const uint32_t c = c0 + (uint32_t)(8 * j);
+                    a = lds_u16(xia + ((c >> mp_shift) << 8));
+                    const uint32_t xa = x0a + ((c & mp_mask) << 8);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const uint32_t k = (uint32_t)(8 * j + 2 * q);
-                        const uint32_t h = (k * inv_m + c0inv) >> 20;
-                        x[q] = lds_u32(h * negM256 + x0c + (k << 8));          // (c - h M) << 8
-                        a[q] = lds_u16(xia + (h << 8));
-                    }
+                    for (int q = 0; q < 4; ++q) x[q] = lds_u32(xa + (uint32_t)(q * 512));
                 };
-                loads(0, av[0], xv[0]);
+                if (!(p.debug & 1)) loads(0, av[0], xv[0]);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
+                    if (p.debug & 1) break;
                     if (j + 1 < 8) loads(j + 1, av[(j + 1) & 1], xv[(j + 1) & 1]);
+                    const uint32_t a2 = av[j & 1] * 0x10001u;
                     uint32_t w[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) w[q] = bf16x2_mul(av[j & 1][q] * 0x10001u, xv[j & 1][q]);
+                    for (int q = 0; q < 4; ++q) w[q] = bf16x2_mul(a2, xv[j & 1][q]);
                     sts_v4(arow + (((uint32_t)j ^ sw) << 4), w[0], w[1], w[2], w[3]);
                 }
                 fence_proxy_async_smem();                               // generic-proxy stores -> visible to the tensor core's reads
@@ -212,8 +210,11 @@ tc_cin_layer_kernel(const __grid_constant__ CUtensorMap tmW, const CinParams p) 
                 const int stage = (int)(s % C_BSTAGES);
                 mbar_wait_relaxed(&b_empty[stage], ((s / C_BSTAGES) & 1u) ^ 1u);
                 if (issue) {
-                    mbar_arrive_expect_tx(&b_full[stage], C_B_BYTES);
-                    tma_load_2d(sB + stage * C_B_BYTES, &tmW, &b_full[stage], kb * C_BK, 0);
+                    if ((p.debug & 2) && s >= C_BSTAGES) mbar_arrive(&b_full[stage]);       // timing experiment: no load
+                    else {
+                        mbar_arrive_expect_tx(&b_full[stage], C_B_BYTES);
+                        tma_load_2d(sB + stage * C_B_BYTES, &tmW, &b_full[stage], kb * C_BK, 0);
+                    }
                 }
                 __syncwarp();
             }
@@ -237,7 +238,7 @@ tc_cin_layer_kernel(const __grid_constant__ CUtensorMap tmW, const CinParams p) 
                 if (issue) {
 #pragma unroll
                     for (int k = 0; k < C_BK / 16; ++k)
-                        tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                        if (!(p.debug & 8)) tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
                     tc_commit(&a_empty[sa_i]);
                     tc_commit(&b_empty[sb_i]);
                     if (kb == KB - 1) tc_commit(&tmem_full[acc]);
@@ -259,6 +260,7 @@ tc_cin_layer_kernel(const __grid_constant__ CUtensorMap tmW, const CinParams p) 
             float dot = 0.f;
             __nv_bfloat16* hrow = p.hid_out ? p.hid_out + (ok ? r : 0) * p.ld_h : nullptr;
             for (int c4 = 0; c4 < n_chunks; ++c4) {
+                if (p.debug & 4) break;                                 // timing experiment: no epilogue work
                 uint32_t v[32];
                 tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C_BN + c4 * 32), v);
                 tc_wait_ld();
@@ -318,14 +320,15 @@ int oov_cin_layer_supported(int32_t H, int32_t M, int32_t O, int32_t n_hidden, i
     return tc::cin_tc_supported(H, M, O, n_hidden, ld_h) ? 1 : 0;
 }
 
-int oov_cin_layer(const void* xi, int64_t ld_xi, int32_t H, const void* x0, int64_t ld_x0, int32_t M,
+int oov_cin_layer(const void* xi, int64_t ld_xi, int32_t H, const void* x0, int64_t ld_x0, int32_t M, int32_t Mp,
                   int64_t B, int32_t D, const void* W, int64_t ldw, const float* bias, int32_t O,
                   void* hid_out, int64_t ld_h, int32_t n_hidden,
                   int32_t pool_lo, int32_t pool_n, const float* pool_w, float* out_acc, void* stream) {
     OOV_REQUIRE(B >= 0 && D > 0 && H > 0 && M > 0 && O > 0, OOV_ERR_ARG, "oov_cin_layer: bad shape");
     OOV_REQUIRE(tc::cin_tc_supported(H, M, O, n_hidden, ld_h), OOV_ERR_ARG,
                 "oov_cin_layer: needs even M <= 64, H <= 64, O <= 128, even n_hidden / ld_h (H=%d M=%d O=%d); use oov_cin_outer + oov_tc_linear", H, M, O);
-    OOV_REQUIRE(ldw % 8 == 0 && ldw >= (int64_t)H * M, OOV_ERR_ALIGN, "oov_cin_layer: ldw must be a multiple of 8 >= H*M");
+    OOV_REQUIRE(Mp >= 8 && Mp >= M && Mp <= 64 && (Mp & (Mp - 1)) == 0, OOV_ERR_ARG, "oov_cin_layer: Mp=%d must be a power of two in [max(M, 8), 64]", Mp);
+    OOV_REQUIRE(ldw % 8 == 0 && ldw >= (int64_t)H * Mp, OOV_ERR_ALIGN, "oov_cin_layer: ldw must be a multiple of 8 >= H*Mp");
     OOV_REQUIRE(pool_lo >= 0 && pool_n >= 0 && pool_lo + pool_n <= O && n_hidden >= 0 && n_hidden <= O, OOV_ERR_ARG, "oov_cin_layer: bad column ranges");
     if (B == 0) return OOV_OK;
     OOV_REQUIRE(xi && x0 && W && bias && (n_hidden == 0 || hid_out) && (pool_n == 0 || (pool_w && out_acc)), OOV_ERR_ARG, "oov_cin_layer: NULL pointer");
@@ -336,9 +339,12 @@ int oov_cin_layer(const void* xi, int64_t ld_xi, int32_t H, const void* x0, int6
     p.x0 = reinterpret_cast<const __nv_bfloat16*>(x0); p.x0_sd = ld_x0; p.M = M;
     p.xi = reinterpret_cast<const __nv_bfloat16*>(xi); p.xi_sd = ld_xi; p.H = H;
     p.B = B; p.D = D; p.R = B * (int64_t)D;
-    p.k_blocks = (int)cdiv((int64_t)H * M, tc::C_BK); p.O = O; p.bias = bias;
+    p.mp_shift = 0;
+    while ((1 << p.mp_shift) < Mp) ++p.mp_shift;
+    p.k_blocks = (int)cdiv((int64_t)H * Mp, tc::C_BK); p.O = O; p.bias = bias;
     p.hid_out = n_hidden ? reinterpret_cast<__nv_bfloat16*>(hid_out) : nullptr; p.ld_h = ld_h; p.n_hidden = n_hidden;
     p.pool_lo = pool_lo; p.pool_n = pool_n; p.pool_w = pool_w; p.out_acc = out_acc;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("OOV_CIN_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
     return tc::cin_tc_run(p, W, ldw, (cudaStream_t)stream);
 }
 

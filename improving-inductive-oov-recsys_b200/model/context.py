@@ -433,16 +433,18 @@ class xDeepFM(InductiveContextRecommender):
             w = torch.nn.functional.pad(w.detach().float(), (0, (-w.shape[1]) % 8, 0, max(0, rows - w.shape[0])))
             return w.to(bf).contiguous()
 
-        cin = []
-        for conv in self.conv1d_list:
+        cin, cin_fused = [], []
+        for conv, h_prev in zip(self.conv1d_list, self.field_nums):
             w = conv.weight.detach()[:, :, 0]                         # [O, H*M, 1] -> [O, H*M]
             o8 = (w.shape[0] + 7) // 8 * 8
             cin.append((pad(w, o8), torch.nn.functional.pad(conv.bias.detach().float(), (0, o8 - w.shape[0])).contiguous()))
+            # the fused kernel's channel layout (column h*Mp + m, Mp = fields rounded up to a power of two)
+            cin_fused.append(ops.cin_pack_weight(w, h_prev, self.field_nums[0], o8) if self.field_nums[0] <= 64 else None)
         mlp = []
         for w, b in self.mlp_layers.folded():
             o8 = (w.shape[0] + 7) // 8 * 8
             mlp.append((pad(w, o8), torch.nn.functional.pad(b, (0, o8 - w.shape[0])).contiguous()))
-        self._packed = dict(cin=cin, mlp=mlp, lin_w=self.cin_linear.weight.detach().float().reshape(-1).contiguous(),
+        self._packed = dict(cin=cin, cin_fused=cin_fused, mlp=mlp, lin_w=self.cin_linear.weight.detach().float().reshape(-1).contiguous(),
                             lin_b=float(self.cin_linear.bias.detach().float()[0]))
         return self._packed
 
@@ -456,7 +458,7 @@ class xDeepFM(InductiveContextRecommender):
             out = torch.full((B,), pk["lin_b"], dtype=torch.float32, device=emb.device)
             x0t = emb.transpose(1, 2).contiguous().view(B * D, M)       # rows (b, d), fields along the row (34 MB at 65536 x 26 x 10)
             hidden, off = x0t, 0
-            for i, ((w, b), size) in enumerate(zip(pk["cin"], self.cin_layer_size)):
+            for i, ((_, b), w, size) in enumerate(zip(pk["cin"], pk["cin_fused"], self.cin_layer_size)):
                 if self.direct:
                     n_hid, lo, n = size, 0, size
                 elif i != last:

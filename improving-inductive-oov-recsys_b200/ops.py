@@ -694,6 +694,23 @@ def cin_layer_supported(H: int, M: int, O: int, n_hidden: int, ld_h: int) -> boo
     return bool(_lib.load().oov_cin_layer_supported(int(H), int(M), int(O), int(n_hidden), int(ld_h)))
 
 
+def cin_field_pitch(M: int) -> int:
+    """Mp of oov_cin_layer: the field count rounded up to a power of two, at least 8."""
+    p = 8
+    while p < M:
+        p *= 2
+    return p
+
+
+def cin_pack_weight(w: torch.Tensor, H: int, M: int, rows: int) -> torch.Tensor:
+    """conv1d weight [O, H*M] fp32 -> bf16 [rows, align8(H*Mp)] in the channel layout of oov_cin_layer (column h*Mp + m)."""
+    O, Mp = w.shape[0], cin_field_pitch(M)
+    out = torch.zeros((rows, H, Mp), dtype=torch.float32, device=w.device)
+    out[:O, :, :M] = w.float().reshape(O, H, M)
+    out = out.reshape(rows, H * Mp)
+    return torch.nn.functional.pad(out, (0, (-out.shape[1]) % 8)).to(torch.bfloat16).contiguous()
+
+
 def cin_layer(xi: torch.Tensor, x0t: torch.Tensor, B: int, D: int, W: torch.Tensor, bias: torch.Tensor, n_hidden: int,
               pool_lo: int, pool_n: int, pool_w: torch.Tensor, out_acc: torch.Tensor) -> Optional[torch.Tensor]:
     """One CIN layer fused (oov_cin_layer): returns the hidden channels [B*D, ld_h] bf16 (first n_hidden columns valid;
@@ -707,12 +724,13 @@ def cin_layer(xi: torch.Tensor, x0t: torch.Tensor, B: int, D: int, W: torch.Tens
     if x0t.dim() != 2 or xi.dim() != 2 or x0t.shape[0] != B * D or xi.shape[0] != B * D or x0t.stride(1) != 1 or xi.stride(1) != 1:
         raise ValueError("x0t / xi must be [B*D, channels] with unit inner stride")
     M, H, O = x0t.shape[1], xi.shape[1], W.shape[0]
-    if not W.is_contiguous() or W.shape[1] < H * M or bias.numel() != O or pool_w.numel() != pool_n or not pool_w.is_contiguous() \
+    Mp = cin_field_pitch(M)
+    if not W.is_contiguous() or W.shape[1] < H * Mp or bias.numel() != O or pool_w.numel() != pool_n or not pool_w.is_contiguous() \
             or out_acc.numel() != B or not out_acc.is_contiguous():
-        raise ValueError("cin_layer: W [O, >= H*M] contiguous, bias [O], pool_w [pool_n], out_acc [B]")
+        raise ValueError("cin_layer: W [O, >= H*Mp] contiguous (cin_pack_weight), bias [O], pool_w [pool_n], out_acc [B]")
     ld_h = (n_hidden + 7) // 8 * 8
     hid = torch.empty((B * D, ld_h), dtype=torch.bfloat16, device=x0t.device) if n_hidden else None
-    _lib.check(_lib.load().oov_cin_layer(_p(xi), xi.stride(0), H, _p(x0t), x0t.stride(0), M, B, D, _p(W), W.shape[1], _p(bias.contiguous()), O,
+    _lib.check(_lib.load().oov_cin_layer(_p(xi), xi.stride(0), H, _p(x0t), x0t.stride(0), M, Mp, B, D, _p(W), W.shape[1], _p(bias.contiguous()), O,
                                          _p(hid), ld_h, n_hidden, pool_lo, pool_n, _p(pool_w), _p(out_acc), _stream()))
     return hid
 

@@ -369,17 +369,19 @@ int oov_cin_outer(const void* xi, int64_t xi_sb, int64_t xi_sd, int64_t xi_sc, i
 int oov_cin_pool_dot(const void* y, int64_t ldy, int32_t col0, int32_t ncols, int64_t B, int32_t D,
                      const float* w, float bias, int32_t accumulate, float* acc, void* stream);
 /* One CIN layer in ONE tcgen05 kernel: the outer-product operand z is generated tile by tile in shared memory (never
- * written to HBM), Y = ReLU(z W^T + bias) with W bf16 [O, ldw] (columns [H*M, ldw) zero), then
+ * written to HBM), Y = ReLU(z W^T + bias), then
  *   hid_out[(b*D + d) * ld_h + c] = bf16(Y[., c]) for c < n_hidden   (the next layer's xi: sb = D*ld_h, sd = ld_h, sc = 1)
  *   out_acc[b] += sum_{d, c < pool_n} bf16(Y[(b, d), pool_lo + c]) * pool_w[c]     (fp32 atomics; initialise out_acc with
  *                                                                                   cin_linear's bias)
  * xi [B*D, ld_xi] / x0 [B*D, ld_x0]: rows are (b, d) pairs, channels contiguous (the embeddings transposed to [B, D, M]
  * once per forward; a previous layer's hid_out as it is), even ld, 4-byte aligned.
+ * W bf16 [O, ldw]: column h*Mp + m holds conv1d.weight[o, h*M + m, 0], Mp = the field count rounded up to a power of
+ * two (>= 8; columns with m >= M and columns >= H*Mp are zero) — so that 8 consecutive z channels share one h.
  * Same rounding points as oov_cin_outer + oov_tc_linear + oov_cin_pool_dot.
  * Shapes: even M <= 64, H <= 64, O <= 128, even n_hidden / ld_h — oov_cin_layer_supported tells; other shapes take
  * the three-call path. */
 int oov_cin_layer_supported(int32_t H, int32_t M, int32_t O, int32_t n_hidden, int64_t ld_h);
-int oov_cin_layer(const void* xi, int64_t ld_xi, int32_t H, const void* x0, int64_t ld_x0, int32_t M,
+int oov_cin_layer(const void* xi, int64_t ld_xi, int32_t H, const void* x0, int64_t ld_x0, int32_t M, int32_t Mp,
                   int64_t B, int32_t D, const void* W, int64_t ldw, const float* bias, int32_t O,
                   void* hid_out, int64_t ld_h, int32_t n_hidden,
                   int32_t pool_lo, int32_t pool_n, const float* pool_w, float* out_acc, void* stream);
