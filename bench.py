@@ -868,13 +868,16 @@ def run_xdeepfm(args, device):
     flops = 2.0 * Bn * D * sum(h * fields * c for h, c in zip(hs, wl["cin"]))
     zbytes = 2.0 * Bn * D * sum(2 * ((h * fields + 7) // 8 * 8) for h in hs)          # z written once and read once, bf16
     ach = flops / (stages["cin_ms"] * 1e-3) / 1e12
-    roofline = {"kernel": "xDeepFM CIN: 3 x (cin_outer + tc_linear<ReLU> + cin_pool_dot), 8 chunks of 8192 rows", "bound": "tensor",
+    fused = bool(model.fused_cin and model._cin_fusable(fields))
+    roofline = {"kernel": "xDeepFM CIN: 3 x tc_cin_layer_kernel (outer-product operand generated in shared memory, tcgen05, pooled epilogue)" if fused
+                else "xDeepFM CIN: 3 x (cin_outer + tc_linear<ReLU> + cin_pool_dot), 8 chunks of 8192 rows", "bound": "tensor",
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
                 "launch_ms": stages["cin_ms"], "flops_per_launch": flops,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops" if peaks else "fallback 1590",
-                "note": "algorithmic flops 2 B D sum_k H_{k-1} M H_k over the time of the whole CIN; the outer-product operand z "
-                        f"({zbytes / 1e9:.1f} GB written + read per batch) goes through HBM: the CIN is bound by that traffic, not by the "
-                        "tensor pipe — generating z tiles in shared memory inside the GEMM is the next step (DESIGN 4.8)"}
+                "note": "algorithmic flops 2 B D sum_k H_{k-1} M H_k over the time of the whole CIN (three launches + the d-major "
+                        "transpose of the embeddings); the issued MMA work is 1.6x that (N padded 100 -> 128, field pitch 26 -> 32). "
+                        + ("The operand z never reaches HBM; the kernel is bound by the per-k-block hand-over chain (DESIGN 4.8)." if fused else
+                           f"The outer-product operand z ({zbytes / 1e9:.1f} GB written + read per batch) goes through HBM.")}
     res = {"metric": "xdeepfm_eval_rows_per_s", "value": Bn * args.steps / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms / args.steps,
            "e2e": {"value": Bn * args.steps / (ms_e2e * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": Bn * fields * 8,
                    "d2h_bytes_per_step": Bn * 4, "ms_per_step": ms_e2e / args.steps},

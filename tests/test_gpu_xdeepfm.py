@@ -114,9 +114,11 @@ def test_cin_outer_exact_products_and_padding():
 def test_fused_cin_layer_kernel_equals_the_three_launch_path(Bn):
     """`oov_cin_layer` (outer-product operand generated in shared memory inside the tcgen05 GEMM, pooled epilogue) against
     `oov_cin_outer` + `oov_tc_linear` + `oov_cin_pool_dot`: same rounding points; the fused kernel lays the z channels out
-    with a power-of-two field pitch, so the fp32 accumulation order differs and a layer output that sits on a bf16 rounding
-    boundary may land on the other side — 3e-4 of the logit scale (observed 6e-5), a third of the bf16 contract.  Also pinned
-    to the reference golden through the head test above (the model default is fused)."""
+    with a power-of-two field pitch, so the fp32 accumulation order differs and a hidden channel that sits on a bf16 rounding
+    boundary may land on the other side (and feeds the next layer): the MAXIMUM over the batch is held to the bf16
+    contract, 1e-3 of the logit scale (observed 5.5e-5 / 2.5e-4 / 3.2e-4 at 200 / 3001 / 40000 rows — an extreme value that
+    grows with the sample count), the MEAN difference to 2e-5 of it (a wrong channel or row would show there).  Also pinned to
+    the reference golden through the head test above (the model default is fused)."""
     g = np.load(GOLD)
     c = _xdeepfm_case(g, "default")
     m = _model(c, [100, 100, 100])
@@ -134,8 +136,9 @@ def test_fused_cin_layer_kernel_equals_the_three_launch_path(Bn):
     assert n_fused == 3                                               # one kernel per CIN layer
     scale = float(unfused.abs().max())
     err = float((fused - unfused).abs().max())
-    print(f"[fused CIN B={Bn}] max |fused - unfused| = {err:.3e} (scale {scale:.2f})")
-    assert err <= 3e-4 * max(scale, 1.0)
+    mean_err = float((fused - unfused).abs().mean())
+    print(f"[fused CIN B={Bn}] |fused - unfused|: max {err:.3e}, mean {mean_err:.3e} (scale {scale:.2f})")
+    assert err <= 1e-3 * max(scale, 1.0) and mean_err <= 2e-5 * max(scale, 1.0)
     # NaN embeddings stay confined to their own batch row
     x16[7, 3, 2] = float("nan")
     m.fused_cin = True
