@@ -49,6 +49,11 @@ class MeanEmbedder(AbstractInductiveEmbedder):
         vec = self._mean(side, model)
         return ops.const_embed(vec, ids, vec.numel(), out=out, out_dtype=out_dtype, n_old=n_old, iv_table=iv_table)
 
+    def assemble_rows_train(self, side, ids, model, n_old, iv_table):
+        """Training mode: the reference embeds under `torch.no_grad()` (mean_embedder.py:40, 63) — the OOV rows are constants
+        (the mean cached at first use), only the in-vocab rows carry gradient."""
+        return self.assemble_rows(side, ids, model, n_old, iv_table), None
+
     @torch.no_grad()
     def embed_user_ids(self, user_ids, model) -> torch.Tensor:
         return self.assemble_rows("user", user_ids, model, 0, None)

@@ -317,7 +317,7 @@ def featnet_inputs(case: FeatNetCase) -> dict:
 # ---------------------------------------------------------------------------------------
 # Training-mode OOV batches (trainer.py:1748-1837 _train_oov + _transform_interaction_oov)
 # ---------------------------------------------------------------------------------------
-TRAIN_CASES = ["bpr_lsh_ml100k", "directau_lsh_global", "bpr_lsh_tinybuckets", "directau_slsh", "bpr_slsh_odd", "directau_zero"]
+TRAIN_CASES = ["bpr_lsh_ml100k", "directau_lsh_global", "bpr_lsh_tinybuckets", "directau_slsh", "bpr_slsh_odd", "directau_zero", "bpr_mean"]
 
 
 def train_batch(case: RetrievalCase, batch: int = 192) -> dict:
