@@ -282,3 +282,80 @@ def test_bench_cpu_arm_strided_slices_equal_the_unsliced_batch(name, slices):
         gap = np.minimum(np.abs(np.diff(v1, axis=1, prepend=np.inf)), np.abs(np.diff(v1, axis=1, append=-np.inf)))
         assert (gap[diff] <= 1e-5 * np.abs(v1[diff]) + 1e-6).all()
         assert diff.mean() < 0.05
+
+
+@pytest.mark.parametrize("name", list(cases.FEATNET_CASES))
+def test_featnet_embedders_host_side(name, tmp_path):
+    """fdhe / dnn constructors on the CPU: factory dispatch, feature matrices (per-column L2 normalisation, hstack) and
+    state_dict keys against the reference-generated fixture; layer shapes follow dhe_layer_size / F / num_hashes."""
+    import oov_b200
+    case = cases.FEATNET_CASES[name]
+    inp = cases.featnet_inputs(case)
+    g = np.load(os.path.join(pu.GOLDEN_DIR, "featnet.npz"), allow_pickle=False)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)                                  # ./hash_keys is CWD-relative (feat_dh_embedder.py:52)
+    try:
+        cfg = _cfg(case, case.kind, user_oov_buckets=4, item_oov_buckets=4, dhe_num_hashes=case.n_hashes, dhe_layer_size=case.layer)
+        ds = Dataset(4, 4, _features("user_id", inp["user_cols"]), _features("item_id", inp["item_cols"]))
+        emb = oov_b200.get_inductive_embedder(cfg, ds, mode=f"host-{name}", user_num=4, item_num=4)
+        if case.kind == "fdhe":                        # the key file protocol: written once, read back identically
+            emb2 = oov_b200.get_inductive_embedder(cfg, ds, mode=f"host-{name}", user_num=4, item_num=4)
+            assert emb2.hash_keys == emb.hash_keys and len(emb.hash_keys) == case.n_hashes
+            assert os.path.exists(os.path.join("hash_keys", f"{case.n_hashes}.hashes"))
+    finally:
+        os.chdir(cwd)
+    assert type(emb).__name__ == ("FeatDeepHashEmbedder" if case.kind == "fdhe" else "DNNEmbedder")
+    assert set(g[f"{name}.state_dict_keys"].tolist()) == set(emb.state_dict().keys())
+    for side in ("user", "item"):
+        pu.assert_close(getattr(emb, f"{side}_feature_mat").numpy(), g[f"{name}.{side}_feature_mat"], rtol=2e-6, atol=1e-7, what="feature_mat")
+    F_ = int(sum(case.widths))
+    H = case.n_hashes if case.kind == "fdhe" else 0
+    assert tuple(emb.item_hash_net[0].weight.shape) == (case.layer, H + F_)
+    assert tuple(emb.item_hash_net[6].weight.shape) == (case.D, case.layer)
+    assert not emb.training
+    emb.set_train()
+    assert emb.training
+    emb.set_eval()
+
+
+def test_xdeepfm_widedeep_module_tree_and_cin_weight_layout():
+    """Constructor surface of the ranking models on the CPU: parameter names of the reference module tree
+    (xdeepfm.py:43-86, widedeep.py:40-50), CIN channel bookkeeping (field_nums, final_len, even sizes when the output is
+    split), and the weight layout of the fused CIN kernel (column h*Mp + m)."""
+    import oov_b200
+    from oov_b200 import ops
+    from oov_b200.inductive.zero_embedder import ZeroEmbedder
+    z = lambda d: ZeroEmbedder(np.zeros((10, 1), np.float32), np.zeros((10, 1), np.float32), 40, 40, d, "cpu")
+    cfg = {"embedding_size": 10, "mlp_hidden_size": [128, 128, 128], "dropout_prob": 0.2, "device": "cpu", "direct": False,
+           "cin_layer_size": [100, 101, 100]}
+    m = oov_b200.xDeepFM(cfg, [40, 40] + [50] * 24, inductive_embedder=z(10), first_order_embedder=z(1))
+    assert m.cin_layer_size == [100, 100, 100] and m.field_nums == [26, 50, 50, 50] and m.final_len == 50 + 50 + 100
+    keys = set(m.state_dict().keys())
+    want = {"cin_linear.weight", "cin_linear.bias", "token_embedding_table.embedding.weight",
+            "first_order_linear.token_embedding_table.embedding.weight", "first_order_linear.bias"}
+    want |= {f"conv1d_list.{i}.{p}" for i in range(3) for p in ("weight", "bias")}
+    want |= {f"mlp_layers.mlp_layers.{i}.{p}" for i in (1, 4, 7, 10) for p in ("weight", "bias")}      # Dropout, Linear, ReLU triples
+    assert want <= keys, want - keys
+    assert tuple(m.conv1d_list[1].weight.shape) == (100, 50 * 26, 1) and tuple(m.cin_linear.weight.shape) == (1, 200)
+    assert tuple(m.mlp_layers.mlp_layers[10].weight.shape) == (1, 128)
+    with pytest.raises(NotImplementedError):
+        oov_b200.xDeepFM(cfg, [40, 40, 50], inductive_embedder=z(10))                  # no first-order embedder / mapper
+    md = oov_b200.xDeepFM(dict(cfg, direct=True, cin_layer_size=[24, 17, 8]), [40, 40, 50, 50, 50, 50], inductive_embedder=z(10), first_order_embedder=z(1))
+    assert md.cin_layer_size == [24, 17, 8] and md.field_nums == [6, 24, 17, 8] and md.final_len == 49
+    w = oov_b200.WideDeep({"embedding_size": 10, "device": "cpu"}, [40, 40, 50], inductive_embedder=z(10), first_order_embedder=z(1))
+    assert {"deep_predict_layer.weight", "mlp_layers.mlp_layers.1.weight", "mlp_layers.mlp_layers.7.bias"} <= set(w.state_dict().keys())
+    assert w.mlp_hidden_size == [32, 16, 8]
+    # fused-kernel weight layout: fields padded to a power of two, rows padded with zeros
+    assert [ops.cin_field_pitch(v) for v in (2, 8, 9, 26, 32, 33, 64)] == [8, 8, 16, 32, 32, 64, 64]
+    H, M, O = 3, 6, 5
+    cw = torch.arange(O * H * M, dtype=torch.float32).reshape(O, H * M) + 1
+    pk = ops.cin_pack_weight(cw, H, M, rows=8)
+    assert pk.shape == (8, 24) and pk.dtype == torch.bfloat16
+    for h in range(H):
+        assert torch.equal(pk[:O, h * 8: h * 8 + M].float(), cw[:, h * M: (h + 1) * M])
+        assert float(pk[:, h * 8 + M: (h + 1) * 8].abs().sum()) == 0.0
+    assert float(pk[O:].abs().sum()) == 0.0
+    # shapes the fused kernel takes (host-side predicate of the C-ABI; no GPU needed)
+    assert ops.cin_layer_supported(50, 26, 104, 50, 56) and not ops.cin_layer_supported(50, 27, 104, 50, 56)
+    assert not ops.cin_layer_supported(65, 26, 104, 50, 56) and not ops.cin_layer_supported(50, 26, 136, 50, 56)
+    assert not ops.cin_layer_supported(24, 6, 24, 17, 24)
