@@ -1001,6 +1001,7 @@ tc_score_main2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_cons
 // largest of the user's n_s tile maxima (ordered keys, radix select 4 x 8 bits over a warp-private histogram) is a
 // bound no top-k score is below.  0 = no bound (fewer than R sampled tiles).
 constexpr int THR_WARPS = 8;
+constexpr int THR_UNR = 16;
 __global__ void __launch_bounds__(THR_WARPS * 32)
 score_threshold_kernel(const uint32_t* __restrict__ tile_max, int64_t n_s, int64_t Q, int k, int64_t tile_first,
                        int64_t tile_stride, int64_t item_id_offset, int64_t N, int mask_pad,
@@ -1031,15 +1032,16 @@ score_threshold_kernel(const uint32_t* __restrict__ tile_max, int64_t n_s, int64
 #pragma unroll
         for (int j = 0; j < 8; ++j) hist[lane * 8 + j] = 0u;
         __syncwarp();
-        for (int64_t i0 = 0; i0 < n_s; i0 += 32 * 8) {                 // 8 loads in flight per lane: the pass is latency-bound
-            uint32_t v[8];
+        // THR_UNR loads in flight per lane: the pass is latency-bound (one warp walks its user's row: ~7 warps per SM)
+        for (int64_t i0 = 0; i0 < n_s; i0 += 32 * THR_UNR) {
+            uint32_t v[THR_UNR];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < THR_UNR; ++j) {
                 const int64_t i = i0 + j * 32 + lane;
                 v[j] = i < n_s ? __ldg(row + i) : 0u;
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < THR_UNR; ++j)
                 if (i0 + j * 32 + lane < n_s && (v[j] & mask) == prefix) atomicAdd(&hist[(v[j] >> shift) & 255u], 1u);
         }
         __syncwarp();
@@ -1072,8 +1074,17 @@ score_threshold_kernel(const uint32_t* __restrict__ tile_max, int64_t n_s, int64
     }
     if (lane == 0) thr_out[user] = prefix;
     if (tile_hits != nullptr)                                         // how many users will see a candidate in sampled tile i
-        for (int64_t i = lane; i < n_s; i += 32)
-            if (__ldg(row + i) >= prefix) atomicAdd(tile_hits + i, 1u);
+        for (int64_t i0 = 0; i0 < n_s; i0 += 32 * THR_UNR) {
+            uint32_t v[THR_UNR];
+#pragma unroll
+            for (int j = 0; j < THR_UNR; ++j) {
+                const int64_t i = i0 + j * 32 + lane;
+                v[j] = i < n_s ? __ldg(row + i) : 0u;                 // 0 < any threshold key that filters (prefix == 0: no bound, every tile counts)
+            }
+#pragma unroll
+            for (int j = 0; j < THR_UNR; ++j)
+                if (i0 + j * 32 + lane < n_s && v[j] >= prefix) atomicAdd(tile_hits + i0 + j * 32 + lane, 1u);
+        }
 }
 
 // Which main pass runs (device-side, so the choice can sit inside a captured graph).  Every user has exactly R sampled
